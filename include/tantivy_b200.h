@@ -1,0 +1,187 @@
+/*
+ * tantivy_b200.h — C ABI of the B200-native query-execution path for tantivy segments.
+ *
+ * The reference (quickwit-oss/tantivy, Rust) has no FFI; its boundary for this path is the
+ * trait surface  Searcher::search -> Collector::collect_segment -> Weight::for_each_pruning
+ * (src/core/searcher.rs:180-237, src/collector/mod.rs:173-184, src/query/weight.rs:123-132).
+ * The entry points below are what a Rust shim implementing `Collector::collect_segment`
+ * (or a `gpu_search(&Searcher, &dyn Query, k)` wrapper) would bind; INTEGRATION.md shows
+ * that shim.  Every pointer is a plain host pointer unless its name ends in `_dev`.
+ * No exceptions cross this boundary: every call returns TQ_OK or a negative error code and
+ * `tq_last_error` gives the message.  All entry points are thread-safe per `tq_ctx`
+ * (rayon threads call collect_segment concurrently, src/core/executor.rs:60-100).
+ *
+ * Doc ids are bit-exact w.r.t. the reference CPU path; scores are f32 computed with the
+ * reference's operation order (src/query/bm25.rs:158-175).
+ */
+#ifndef TANTIVY_B200_H
+#define TANTIVY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TQ_OK 0
+#define TQ_ERR_INVALID_ARGUMENT (-1)
+#define TQ_ERR_CUDA (-2)
+#define TQ_ERR_NOT_FOUND (-3)
+#define TQ_ERR_UNSUPPORTED (-4)
+#define TQ_ERR_OOM (-5)
+#define TQ_ERR_CORRUPT (-6)
+
+/* schema::IndexRecordOption (src/schema/index_record_option.rs): decides the skip record
+ * size 5 / 8 / 12 bytes (src/postings/skip.rs:205-253). */
+#define TQ_RECORD_BASIC 0
+#define TQ_RECORD_FREQS 1
+#define TQ_RECORD_FREQS_POSITIONS 2
+
+/* Query shapes accelerated: the three specialised scorers of the reference
+ * (TermWeight::for_each_pruning, term_weight.rs:118; SpecializedScorer::TermIntersection /
+ * TermUnion, boolean_weight.rs:17-21,581-600). */
+#define TQ_OP_TERM 0
+#define TQ_OP_AND 1
+#define TQ_OP_OR 2
+
+/* TERMINATED sentinel of src/docset.rs:12 */
+#define TQ_TERMINATED 0x7FFFFFFFu
+/* Largest k the device path keeps on chip. */
+#define TQ_MAX_K 1024u
+/* Largest number of clauses in one query on the device path. */
+#define TQ_MAX_TERMS 32u
+
+typedef struct tq_ctx tq_ctx;
+typedef struct tq_batch tq_batch;
+
+/* One (clause, segment) posting list: postings::TermInfo (src/postings/term_info.rs:9-16) as
+ * returned by InvertedIndexReader::get_term_info (src/index/inverted_index_reader.rs:96).
+ * postings_start/end are relative to the field's postings body, i.e. AFTER the 8-byte
+ * total_num_tokens header (inverted_index_reader.rs:72-73).  A (clause, segment) pair in
+ * which the term does not occur is simply not listed. */
+typedef struct {
+  uint32_t term_idx;    /* clause ordinal inside the query, 0..n_terms */
+  uint32_t segment_ord; /* as given to tq_segment_register */
+  uint32_t field;
+  uint32_t doc_freq;
+  uint64_t postings_start;
+  uint64_t postings_end;
+} tq_term_seg;
+
+/* One query = one `Weight` (built once for all segments, searcher.rs:226).
+ * weight[i]        = Bm25Weight.weight = idf * (1 + K1) * boost        (bm25.rs:141-151)
+ * avg_fieldnorm[i] = Bm25Weight.average_fieldnorm of clause i's field; the 256-entry tf
+ *                    cache is recomputed from it exactly as bm25.rs:56-69 does.
+ * tf_cache         = optional explicit caches [n_terms][256]; overrides avg_fieldnorm. */
+typedef struct {
+  int32_t op;
+  uint32_t n_terms;
+  uint32_t k; /* TopDocs limit+offset, 1..TQ_MAX_K */
+  uint32_t n_term_segs;
+  const tq_term_seg* term_segs;
+  const float* weight;
+  const float* avg_fieldnorm;
+  const float* tf_cache;
+} tq_query;
+
+/* Counters of the last finished batch (per ctx). */
+typedef struct {
+  uint64_t lists_cached;      /* posting-list block tables resident on the device */
+  uint64_t lists_built;       /* block tables built during the last batch */
+  uint64_t units;             /* work units launched in the last batch */
+  uint64_t kernel_launches;   /* CUDA kernels launched in the last batch */
+  uint64_t h2d_bytes;         /* host->device bytes moved by the last batch */
+  uint64_t d2h_bytes;         /* device->host bytes moved by the last batch */
+  uint64_t algorithmic_bytes; /* sum over (query,segment,term) of postings
+                                 range bytes + doc_freq fieldnorm bytes + 12*k output */
+  uint64_t postings;          /* sum of doc_freq over all lists touched */
+  float kernel_ms;            /* device time of the scoring kernels (CUDA events) */
+  float total_ms;             /* device time of the whole batch incl. copies */
+} tq_stats;
+
+/* ---- context ------------------------------------------------------------------------- */
+/* One context drives ONE device (one process per GPU; segments shard across processes). */
+int tq_ctx_create(int device, tq_ctx** out);
+void tq_ctx_destroy(tq_ctx*);
+const char* tq_last_error(tq_ctx*);
+int tq_get_stats(tq_ctx*, tq_stats* out);
+
+/* Uploads one field of one segment to HBM (copied; caller keeps ownership of its mmap).
+ * idx_body    = the field's sub-file of the `.idx` composite, INCLUDING the 8-byte
+ *               total_num_tokens header (serializer.rs:128).
+ * fieldnorm   = the field's sub-file of `.fieldnorm` (max_doc bytes); NULL => constant
+ *               fieldnorm 1 (term_weight.rs:218).
+ * alive_bitset= `.del` payload without its 4-byte max_value header: little-endian 64-bit
+ *               words, bit set = alive (common/src/bitset.rs:362-407); NULL => no deletes. */
+int tq_segment_register(tq_ctx*, uint32_t segment_ord, uint32_t field, uint32_t max_doc,
+                        int record_option, const uint8_t* idx_body, size_t idx_len,
+                        const uint8_t* fieldnorm, size_t fieldnorm_len,
+                        const uint8_t* alive_bitset, size_t alive_len);
+int tq_segment_unregister(tq_ctx*, uint32_t segment_ord, uint32_t field);
+
+/* ---- search -------------------------------------------------------------------------- */
+/* The whole hot path for a batch of queries, host buffers in / host buffers out:
+ * block decode -> AND/OR/term -> BM25 -> per-segment top-k -> merge_fruits.
+ * Replaces Searcher::search_with_executor's segment loop + merge (searcher.rs:220-237).
+ * Output row q holds out_count[q] <= k hits sorted by (score desc, segment_ord asc, doc asc)
+ * (top_score_collector.rs:591-600); rows are out_stride entries apart. */
+int tq_search_batch(tq_ctx*, const tq_query* queries, size_t nq, uint32_t out_stride,
+                    float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc,
+                    uint32_t* out_count);
+
+/* The same split in three so that callers can keep inputs/outputs device resident:
+ * prepare = host planning + H2D of descriptors + block-table builds (cached per term),
+ * run     = scoring kernels + final top-k, results stay in HBM,
+ * fetch   = D2H of the result rows. */
+int tq_batch_prepare(tq_ctx*, const tq_query* queries, size_t nq, tq_batch** out);
+int tq_batch_run(tq_batch*);
+int tq_batch_fetch(tq_batch*, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord,
+                   uint32_t* out_doc, uint32_t* out_count);
+/* Device pointers of the result rows of a finished run: row stride = k_max of the batch. */
+int tq_batch_results_dev(tq_batch*, const float** scores_dev, const uint32_t** segment_ord_dev,
+                         const uint32_t** doc_dev, const uint32_t** count_dev, uint32_t* stride);
+void tq_batch_destroy(tq_batch*);
+
+/* Cross-GPU merge_fruits (sort_key_top_collector.rs:76-95): merges `n_lists` result sets
+ * (e.g. the ranks' rows after an NCCL all-gather), all device resident, laid out
+ * [list][query][stride], into [query][stride] device rows; same ordering as above. */
+int tq_merge_topk_dev(tq_ctx*, uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k,
+                      const float* scores_dev, const uint32_t* segment_ord_dev,
+                      const uint32_t* doc_dev, const uint32_t* count_dev, float* out_scores_dev,
+                      uint32_t* out_segment_ord_dev, uint32_t* out_doc_dev,
+                      uint32_t* out_count_dev);
+
+/* ---- codec-level access (parity tests and the decode micro-benchmark) ----------------- */
+/* Decodes one whole posting list on the device (BlockSegmentPostings::open + advance loop,
+ * block_segment_postings.rs:97-140,343-399) into host arrays of doc_freq entries.
+ * out_tfs may be NULL. */
+int tq_decode_postings(tq_ctx*, const tq_term_seg* list, uint32_t* out_docs, uint32_t* out_tfs);
+/* Block-max scores of every full block (SkipReader::block_max_score, skip.rs:175-184) and
+ * last_doc_in_block, as the device block table holds them. n = doc_freq / 128 entries. */
+int tq_block_table(tq_ctx*, const tq_term_seg* list, float weight, float avg_fieldnorm,
+                   uint32_t* out_last_doc, float* out_block_max);
+
+/* ---- BM25 scalars (host; bit-identical to src/query/bm25.rs) -------------------------- */
+float tq_bm25_idf(uint64_t doc_freq, uint64_t doc_count);                  /* bm25.rs:52-56 */
+float tq_bm25_weight(uint64_t doc_freq, uint64_t doc_count, float boost);  /* bm25.rs:141-151,80-92 */
+void tq_bm25_tf_cache(float avg_fieldnorm, float out[256]);               /* bm25.rs:58-69 */
+uint32_t tq_id_to_fieldnorm(uint8_t id);                                   /* fieldnorm/code.rs:2-4 */
+uint8_t tq_fieldnorm_to_id(uint32_t fieldnorm);                            /* fieldnorm/code.rs:7-11 */
+
+/* ---- segment writer (host; produces tantivy-format bytes for tests and benchmarks) ----- */
+/* Restates PostingsSerializer (src/postings/serializer.rs:353-481): appends one term's
+ * posting list (docs ascending, tfs >= 1 or NULL) to `body`, returns TermInfo. */
+typedef struct tq_field_writer tq_field_writer;
+int tq_field_writer_create(int record_option, uint64_t total_num_tokens,
+                           const uint8_t* fieldnorm_ids, uint32_t max_doc, tq_field_writer** out);
+int tq_field_writer_add_term(tq_field_writer*, const uint32_t* docs, const uint32_t* tfs,
+                             uint32_t doc_freq, uint64_t* postings_start, uint64_t* postings_end);
+/* Field body = 8-byte LE total_num_tokens followed by every term's postings. */
+int tq_field_writer_body(tq_field_writer*, const uint8_t** body, size_t* len);
+void tq_field_writer_destroy(tq_field_writer*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TANTIVY_B200_H */

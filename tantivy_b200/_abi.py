@@ -1,0 +1,155 @@
+"""ctypes mirror of include/tantivy_b200.h (structs and constants only; no library is loaded here).
+
+Shared by the product binding (tantivy_b200/lib.py) and by the test-only oracle binding
+(oracle/tq_oracle.py) so that one marshalled query batch can be handed to either side.
+"""
+import ctypes as C
+
+import numpy as np
+
+TQ_OK = 0
+TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS = 0, 1, 2
+TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR = 0, 1, 2
+TERMINATED = 0x7FFFFFFF
+TQ_MAX_K = 1024
+TQ_MAX_TERMS = 32
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+f32p = C.POINTER(C.c_float)
+
+
+class TermSeg(C.Structure):
+    """tq_term_seg — postings::TermInfo of one (clause, segment) (src/postings/term_info.rs:9-16)."""
+    _fields_ = [
+        ("term_idx", C.c_uint32),
+        ("segment_ord", C.c_uint32),
+        ("field", C.c_uint32),
+        ("doc_freq", C.c_uint32),
+        ("postings_start", C.c_uint64),
+        ("postings_end", C.c_uint64),
+    ]
+
+
+TERM_SEG_DTYPE = np.dtype(
+    [("term_idx", "<u4"), ("segment_ord", "<u4"), ("field", "<u4"), ("doc_freq", "<u4"),
+     ("postings_start", "<u8"), ("postings_end", "<u8")]
+)
+assert TERM_SEG_DTYPE.itemsize == C.sizeof(TermSeg) == 32
+
+
+class Query(C.Structure):
+    """tq_query — one Weight for all segments (src/core/searcher.rs:226)."""
+    _fields_ = [
+        ("op", C.c_int32),
+        ("n_terms", C.c_uint32),
+        ("k", C.c_uint32),
+        ("n_term_segs", C.c_uint32),
+        ("term_segs", C.POINTER(TermSeg)),
+        ("weight", f32p),
+        ("avg_fieldnorm", f32p),
+        ("tf_cache", f32p),
+    ]
+
+
+QUERY_DTYPE = np.dtype(
+    [("op", "<i4"), ("n_terms", "<u4"), ("k", "<u4"), ("n_term_segs", "<u4"),
+     ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8")]
+)
+assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 48
+
+
+class Stats(C.Structure):
+    """tq_stats."""
+    _fields_ = [
+        ("lists_cached", C.c_uint64),
+        ("lists_built", C.c_uint64),
+        ("units", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("algorithmic_bytes", C.c_uint64),
+        ("postings", C.c_uint64),
+        ("kernel_ms", C.c_float),
+        ("total_ms", C.c_float),
+    ]
+
+
+def ptr(arr, typ):
+    """numpy array -> ctypes pointer (array must stay alive while the pointer is used)."""
+    if arr is None:
+        return typ()
+    return arr.ctypes.data_as(typ)
+
+
+class QueryBatch:
+    """A marshalled array of tq_query with everything it points to kept alive.
+
+    `queries` is an iterable of dicts / objects with fields
+      op, k, weights[n_terms], avg_fieldnorm[n_terms], term_segs: list of
+      (term_idx, segment_ord, field, doc_freq, postings_start, postings_end),
+      tf_cache (optional [n_terms,256]).
+    Built with numpy so that a batch of thousands of queries marshals in milliseconds.
+    """
+
+    def __init__(self, queries):
+        queries = list(queries)
+        self.nq = len(queries)
+        n_ts = sum(len(q["term_segs"]) for q in queries)
+        n_terms = sum(len(q["weights"]) for q in queries)
+        self.term_segs = np.zeros(max(n_ts, 1), dtype=TERM_SEG_DTYPE)
+        self.weights = np.zeros(max(n_terms, 1), dtype=np.float32)
+        self.avgs = np.zeros(max(n_terms, 1), dtype=np.float32)
+        self.caches = []
+        self.q = np.zeros(max(self.nq, 1), dtype=QUERY_DTYPE)
+        ts_base = self.term_segs.ctypes.data
+        w_base = self.weights.ctypes.data
+        a_base = self.avgs.ctypes.data
+        its, iw = 0, 0
+        self.kmax = 1
+        for i, q in enumerate(queries):
+            nt = len(q["weights"])
+            ts = q["term_segs"]
+            if len(ts):
+                block = np.asarray(ts, dtype=np.uint64).reshape(-1, 6)
+                v = self.term_segs[its:its + len(ts)]
+                v["term_idx"] = block[:, 0]
+                v["segment_ord"] = block[:, 1]
+                v["field"] = block[:, 2]
+                v["doc_freq"] = block[:, 3]
+                v["postings_start"] = block[:, 4]
+                v["postings_end"] = block[:, 5]
+            self.weights[iw:iw + nt] = q["weights"]
+            self.avgs[iw:iw + nt] = q["avg_fieldnorm"]
+            row = self.q[i]
+            row["op"] = q["op"]
+            row["n_terms"] = nt
+            row["k"] = q["k"]
+            row["n_term_segs"] = len(ts)
+            row["term_segs"] = ts_base + its * TERM_SEG_DTYPE.itemsize
+            row["weight"] = w_base + iw * 4
+            row["avg_fieldnorm"] = a_base + iw * 4
+            cache = q.get("tf_cache")
+            if cache is not None:
+                cache = np.ascontiguousarray(cache, dtype=np.float32).reshape(nt, 256)
+                self.caches.append(cache)
+                row["tf_cache"] = cache.ctypes.data
+            self.kmax = max(self.kmax, int(q["k"]))
+            its += len(ts)
+            iw += nt
+
+    @property
+    def ptr(self):
+        return C.cast(self.q.ctypes.data, C.POINTER(Query))
+
+    def alloc_out(self, stride=None):
+        stride = stride or self.kmax
+        n = max(self.nq, 1)
+        return (
+            stride,
+            np.zeros((n, stride), dtype=np.float32),
+            np.zeros((n, stride), dtype=np.uint32),
+            np.zeros((n, stride), dtype=np.uint32),
+            np.zeros(n, dtype=np.uint32),
+        )
