@@ -1,0 +1,331 @@
+// Device-side data layout and warp-level building blocks of the B200 query path.
+//
+// What each piece replaces in the reference (paths relative to /root/reference):
+//   decode_block        BlockSegmentPostings::load_block -> BlockDecoder::uncompress_block_sorted /
+//                       uncompress_block_unsorted (src/postings/block_segment_postings.rs:343-391,
+//                       src/postings/compression/mod.rs:105-150; BitPacker4x of crate bitpacking)
+//   bm25_score          Bm25Weight::score / tf_factor (src/query/bm25.rs:158-175) +
+//                       FieldNormReader::fieldnorm_id (src/fieldnorm/reader.rs:128-136)
+//   TopK (CTA buffer)   TopNHeap (src/collector/sort_key/sort_by_score.rs:121-161): same accepted set,
+//                       obtained by threshold filtering + exact selection instead of a binary heap
+//   first_block_ge      SkipReader::seek (src/postings/skip.rs:263-275) — random access over the
+//                       block table instead of a linear walk
+//
+// No tensor cores: the path is integer unpack + one f32 divide per posting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tq {
+
+constexpr uint32_t kTerminated = 0x7FFFFFFFu;  // src/docset.rs:12
+constexpr uint32_t kNoList = 0xFFFFFFFFu;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+constexpr int kThreads = 256;                 // 8 warps per CTA
+constexpr int kWarps = kThreads / 32;
+constexpr uint32_t kCap = 2048;               // CTA candidate buffer (u64 keys), power of two
+constexpr uint32_t kRoundMargin = kWarps * 128;  // most keys one round of 8 warps can push
+constexpr uint32_t kStageWords = 264;         // per-warp staging: 64 vectors of packed data + pad
+constexpr uint32_t kTileDocs = 8192;          // OR: doc-id tile width held in shared memory
+
+// One posting list of one (segment, field, term), device resident.  Built once per term by
+// k_build_tables from the raw tantivy bytes and cached for the life of the segment (segments
+// are immutable, ARCHITECTURE.md "Searcher").
+struct ListDesc {
+  const uint8_t* blocks;      // first bit-packed block inside the segment's .idx body (unaligned)
+  const uint32_t* last_doc;   // [n_total] last doc id of every block; entry n_blocks = last tail doc
+  const uint2* blk;           // [n_blocks + 1] .x byte offset from `blocks`, .y packed meta
+  const uint32_t* tail_docs;  // [tail_n] the VInt tail, decoded at build time
+  const uint32_t* tail_tfs;   // [tail_n]
+  const uint8_t* fieldnorm;   // the segment's fieldnorm ids for this field; null => constant id 1
+  uint32_t n_blocks;          // full 128-doc blocks
+  uint32_t tail_n;            // docs in the VInt tail (0..127)
+  uint32_t n_total;           // n_blocks + (tail_n ? 1 : 0)
+  uint32_t doc_freq;
+  uint32_t has_freq;          // term frequencies are stored (else tf = 1)
+  uint32_t build_status;      // 0 ok, else corrupt
+};
+// meta bits: [0:5) doc_bits, bit 6 strict-delta, [8:14) tf_bits, [16:24) block-max fieldnorm id,
+// [24:32) block-max tf code (255 = saturated), see src/postings/skip.rs:16-22,205-253.
+
+struct QList {  // one clause of one query in one segment
+  uint32_t list_id;
+  float weight;        // Bm25Weight.weight
+  uint32_t cache_idx;  // which 256-entry tf-norm table
+  uint32_t pad;
+};
+struct QSeg {  // one (query, segment): what Collector::collect_segment sees
+  uint32_t query;
+  uint32_t lists_base;  // index into qlists; AND: ascending doc_freq (leader first); OR/TERM: clause order
+  uint32_t n_lists;
+  uint32_t max_doc;
+  uint32_t segment_ord;
+  uint32_t pad;
+  const uint8_t* alive;  // alive bitset bytes or null
+};
+struct Unit {  // one CTA's share of a QSeg
+  uint32_t qseg;
+  uint32_t begin, end;  // TERM/AND: block range of the (leader) list; OR: tile range
+  uint32_t pad;
+};
+struct DQuery {
+  uint32_t k;
+  uint32_t cand_base;  // first slot of this query's candidate region
+  uint32_t cand_cap;
+  uint32_t op;
+};
+struct QState {  // zeroed before every run
+  unsigned int theta;       // score key: lower bound of the final k-th best score
+  unsigned int cand_count;
+};
+struct Cand { uint32_t score_key, segment_ord, doc, pad; };
+
+struct BatchParams {
+  const ListDesc* lists;
+  const float* caches;  // [n_caches][256]
+  const QList* qlists;
+  const QSeg* qsegs;
+  const Unit* units;
+  const DQuery* queries;
+  QState* qstate;
+  Cand* cands;
+  float* res_scores;
+  uint32_t* res_segs;
+  uint32_t* res_docs;
+  uint32_t* res_counts;
+  uint32_t res_stride;
+  uint32_t n_queries;
+};
+
+// ---- small helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t score_to_key(float f) {  // order preserving for every float
+  const uint32_t u = __float_as_uint(f);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_to_score(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
+}
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t doc) {
+  // larger key = better hit: higher score, then LOWER doc id (sort_by_score.rs:104-110)
+  return ((unsigned long long)score_to_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
+}
+__device__ __forceinline__ uint32_t lanemask_lt(uint32_t lane) { return (1u << lane) - 1u; }
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(kFull, v, o);
+    if ((int)lane >= o) v += n;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+
+// ---- K1: one warp decodes one 128-doc block ----------------------------------------------------
+// Lane L ends up with postings 4L..4L+3 of the block (ascending doc ids).
+// stage: per-warp shared memory, kStageWords u32, 16-byte aligned.
+__device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint32_t* stage, uint32_t lane,
+                                             uint32_t (&doc)[4], uint32_t (&tf)[4]) {
+  if (b >= L.n_blocks) {  // VInt tail, decoded when the table was built
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t j = lane * 4 + i;
+      const bool v = j < L.tail_n;
+      doc[i] = v ? __ldg(L.tail_docs + j) : kTerminated;
+      tf[i] = v ? __ldg(L.tail_tfs + j) : 1u;
+    }
+    return;
+  }
+  const uint2 rec = __ldg(L.blk + b);
+  const uint32_t meta = rec.y;
+  const uint32_t db = meta & 31u, strict = (meta >> 6) & 1u, tb = (meta >> 8) & 63u;
+  const uint32_t prev = b ? __ldg(L.last_doc + b - 1) : 0u;
+  const uint8_t* src = L.blocks + rec.x;
+  const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
+  const uint32_t nwords = 4u * (db + tb);
+  __syncwarp();  // earlier readers of `stage` are done
+  // Coalesced 128-byte rows from HBM; posting blocks start at arbitrary byte offsets inside the
+  // .idx body, so a row is realigned with one funnel shift per word.
+  if (mis == 0) {
+    for (uint32_t i = lane; i < nwords; i += 32) stage[i] = __ldg(src32 + i);
+  } else {
+    const uint32_t sh = mis * 8u;
+    for (uint32_t i = lane; i < nwords; i += 32) {
+      const uint32_t w0 = __ldg(src32 + i), w1 = __ldg(src32 + i + 1);
+      stage[i] = __funnelshift_r(w0, w1, sh);
+    }
+  }
+  __syncwarp();
+  const uint4* sv = reinterpret_cast<const uint4*>(stage);
+  uint32_t d0, d1, d2, d3;
+  {
+    const uint32_t bit = lane * db, w = bit >> 5, sh = bit & 31u;
+    const uint32_t mask = (1u << db) - 1u;  // db < 32 (skip.rs:16-22)
+    const uint4 lo = sv[w], hi = sv[w + 1];
+    d0 = __funnelshift_r(lo.x, hi.x, sh) & mask;
+    d1 = __funnelshift_r(lo.y, hi.y, sh) & mask;
+    d2 = __funnelshift_r(lo.z, hi.z, sh) & mask;
+    d3 = __funnelshift_r(lo.w, hi.w, sh) & mask;
+  }
+  if (L.has_freq) {
+    const uint32_t bit = lane * tb, w = db + (bit >> 5), sh = bit & 31u;
+    const uint32_t mask = tb >= 32u ? 0xFFFFFFFFu : ((1u << tb) - 1u);
+    const uint4 lo = sv[w], hi = sv[w + 1];
+    tf[0] = (__funnelshift_r(lo.x, hi.x, sh) & mask) + strict;  // v7: tf-1 stored (mod.rs:134-150)
+    tf[1] = (__funnelshift_r(lo.y, hi.y, sh) & mask) + strict;
+    tf[2] = (__funnelshift_r(lo.z, hi.z, sh) & mask) + strict;
+    tf[3] = (__funnelshift_r(lo.w, hi.w, sh) & mask) + strict;
+  } else {
+    tf[0] = tf[1] = tf[2] = tf[3] = 1u;
+  }
+  // inclusive prefix sum of the (strict) deltas across the 128 values
+  const uint32_t s0 = d0 + strict, s1 = s0 + d1 + strict, s2 = s1 + d2 + strict, s3 = s2 + d3 + strict;
+  const uint32_t incl = warp_incl_scan(s3, lane);
+  // offset 0 means "no previous doc" for strict deltas: predecessor is -1 (mod.rs:112-113)
+  const uint32_t base = ((strict && prev == 0u) ? 0xFFFFFFFFu : prev) + (incl - s3);
+  doc[0] = base + s0; doc[1] = base + s1; doc[2] = base + s2; doc[3] = base + s3;
+}
+
+// ---- K2: BM25 of one posting (f32, reference operation order, no contraction) -------------------
+__device__ __forceinline__ float bm25_score(float weight, const float* __restrict__ cache,
+                                            const uint8_t* __restrict__ fieldnorm, uint32_t doc, uint32_t tf) {
+  const uint32_t id = fieldnorm ? (uint32_t)__ldg(fieldnorm + doc) : 1u;  // constant fieldnorm 1 -> id 1
+  const float norm = __ldg(cache + id);
+  const float t = __uint2float_rn(tf);
+  return __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, norm)));
+}
+__device__ __forceinline__ float bm25_score_id(float weight, const float* __restrict__ cache, uint32_t id, uint32_t tf) {
+  const float norm = __ldg(cache + id);
+  const float t = __uint2float_rn(tf);
+  return __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, norm)));
+}
+
+// ---- first block whose last_doc >= target, searching [from, n) (SkipReader::seek) ---------------
+// Warp-cooperative: one coalesced probe of 32 entries at `from`, then a 32-ary search.
+// Returns n if there is none.
+__device__ __forceinline__ uint32_t first_block_ge(const uint32_t* __restrict__ last_doc, uint32_t from, uint32_t n,
+                                                   uint32_t target, uint32_t lane) {
+  if (from >= n) return n;
+  {
+    const uint32_t idx = from + lane;
+    const uint32_t v = idx < n ? __ldg(last_doc + idx) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(kFull, v >= target);
+    if (m) { const uint32_t j = from + (uint32_t)__ffs(m) - 1u; return j < n ? j : n; }
+  }
+  uint32_t lo = from + 32u, hi = n;  // answer in [lo, hi] (hi == n means none)
+  if (lo >= hi) return n;
+  if (__ldg(last_doc + (n - 1)) < target) return n;
+  // invariant: last_doc[hi-1] >= target, every index < lo is < target
+  while (hi - lo > 32u) {
+    const uint32_t step = (hi - lo + 31u) / 32u;
+    uint32_t idx = lo + (lane + 1u) * step - 1u;
+    if (idx > hi - 1u) idx = hi - 1u;
+    const uint32_t v = __ldg(last_doc + idx);
+    const unsigned m = __ballot_sync(kFull, v >= target);  // non-empty: lane 31 probes hi-1
+    const uint32_t f = (uint32_t)__ffs(m) - 1u;
+    uint32_t nhi = lo + (f + 1u) * step;
+    if (nhi > hi) nhi = hi;
+    lo = lo + f * step;
+    hi = nhi;
+  }
+  {
+    const uint32_t idx = lo + lane;
+    const uint32_t v = idx < hi ? __ldg(last_doc + idx) : 0xFFFFFFFFu;
+    const unsigned m = __ballot_sync(kFull, v >= target);
+    return lo + (uint32_t)__ffs(m) - 1u;
+  }
+}
+
+// ---- K6a: CTA-level exact top-k buffer ----------------------------------------------------------
+struct TopK {
+  unsigned long long* keys;   // [kCap] shared
+  unsigned int* count;        // shared
+  unsigned long long* theta;  // shared: keys below it can no longer enter the top-k
+};
+
+// All lanes of a warp call this together (pass may differ per lane).
+__device__ __forceinline__ void topk_push(const TopK& t, bool pass, unsigned long long key, uint32_t lane) {
+  const unsigned m = __ballot_sync(kFull, pass);
+  if (m == 0) return;
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if ((int)lane == leader) base = atomicAdd(t.count, (unsigned)__popc(m));
+  base = __shfl_sync(kFull, base, leader);
+  if (pass) t.keys[base + __popc(m & lanemask_lt(lane))] = key;
+}
+
+// Whole CTA. Sorts the buffer (descending) and keeps the best k; publishes the k-th score.
+__device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_global) {
+  __syncthreads();
+  const unsigned n = *t.count;
+  unsigned size = 2;
+  while (size < n) size <<= 1;
+  for (unsigned i = threadIdx.x; i < size; i += blockDim.x)
+    if (i >= n) t.keys[i] = 0ull;
+  __syncthreads();
+  for (unsigned kk = 2; kk <= size; kk <<= 1) {
+    for (unsigned j = kk >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < size; i += blockDim.x) {
+        const unsigned ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = t.keys[i], b = t.keys[ixj];
+          const bool desc = (i & kk) == 0;
+          if (desc ? (a < b) : (a > b)) { t.keys[i] = b; t.keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0 && n > k) {
+    *t.count = k;
+    const unsigned long long kth = t.keys[k - 1];
+    if (kth > *t.theta) *t.theta = kth;
+    atomicMax(theta_global, (unsigned)(kth >> 32));
+  }
+  __syncthreads();
+}
+
+// End of a round of the CTA: refresh the shared threshold from the query-wide one and make room.
+__device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsigned int* theta_global) {
+  __syncthreads();
+  if (*t.count > kCap - kRoundMargin) topk_compact(t, k, theta_global);
+  if (threadIdx.x == 0) {
+    const unsigned long long g = (unsigned long long)(*(volatile unsigned int*)theta_global) << 32;
+    if (g > *t.theta) *t.theta = g;
+  }
+  __syncthreads();
+}
+
+// End of a unit: the CTA's survivors go to the query's candidate region (at most k of them).
+__device__ void topk_flush(const TopK& t, const DQuery& q, QState* qs, Cand* cands, uint32_t segment_ord) {
+  __syncthreads();
+  if (*t.count > q.k) topk_compact(t, q.k, &qs->theta);
+  __shared__ unsigned s_base;
+  const unsigned n = *t.count;
+  if (threadIdx.x == 0) s_base = n ? atomicAdd(&qs->cand_count, n) : 0u;
+  __syncthreads();
+  const unsigned base = s_base;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    if (base + i < q.cand_cap) {
+      const unsigned long long key = t.keys[i];
+      Cand c;
+      c.score_key = (uint32_t)(key >> 32);
+      c.segment_ord = segment_ord;
+      c.doc = 0xFFFFFFFFu - (uint32_t)key;
+      c.pad = 0;
+      cands[q.cand_base + base + i] = c;
+    }
+  }
+}
+
+__device__ __forceinline__ bool is_alive(const uint8_t* __restrict__ alive, uint32_t doc) {
+  return alive == nullptr || ((__ldg(alive + (doc >> 3)) >> (doc & 7u)) & 1u);
+}
+
+}  // namespace tq

@@ -1,0 +1,757 @@
+// Host engine behind the C ABI of include/tantivy_b200.h: segment registry in HBM, per-term
+// block-table cache, batch planning, kernel launches, result fetch.
+//
+// Replaces, for TermQuery / all-MUST / all-SHOULD BooleanQuery of TermQuerys collected by
+// TopDocs::order_by_score, the reference's per-segment loop
+//   Searcher::search_with_executor            src/core/searcher.rs:220-237
+//   SortBySimilarityScore::collect_segment_top_k   src/collector/sort_key/sort_by_score.rs:35-66
+//   Weight::for_each_pruning                  src/query/weight.rs:123-132
+//   TopBySortKeyCollector::merge_fruits       src/collector/sort_key_top_collector.rs:54-60
+// There is NO CPU fallback: without a CUDA device every entry point fails with TQ_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/tantivy_b200.h"
+#include "bm25_host.hpp"
+#include "segment_writer.hpp"
+#include "tq_kernels.cuh"
+
+using namespace tq;
+
+namespace {
+
+thread_local std::string g_err;
+
+struct DevBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(n + n / 4, 1 << 20);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = std::max<size_t>(n + n / 4, 1 << 16);
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct Segment {
+  uint32_t segment_ord, field, max_doc;
+  int record_option;
+  uint8_t* d_idx = nullptr;  // field body incl. the 8-byte header, padded
+  size_t idx_len = 0;
+  uint8_t* d_fieldnorm = nullptr;
+  uint8_t* d_alive = nullptr;
+};
+
+struct ListKey {
+  uint32_t segment_ord, field;
+  uint64_t postings_start;
+  bool operator==(const ListKey& o) const { return segment_ord == o.segment_ord && field == o.field && postings_start == o.postings_start; }
+};
+struct ListKeyHash {
+  size_t operator()(const ListKey& k) const {
+    uint64_t h = k.postings_start * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.segment_ord << 32 | k.field) * 0xC2B2AE3D27D4EB4Full;
+    return (size_t)(h ^ (h >> 29));
+  }
+};
+
+// Bump allocator over big cudaMalloc chunks for the per-term block tables (immutable, never freed
+// individually; dropped with the context).
+struct Arena {
+  std::vector<uint8_t*> chunks;
+  size_t chunk_size = 64u << 20, used = 0;
+  uint8_t* alloc(size_t n, cudaError_t* err) {
+    n = (n + 255) & ~(size_t)255;
+    if (chunks.empty() || used + n > chunk_size) {
+      const size_t sz = std::max(chunk_size, n);
+      uint8_t* p = nullptr;
+      *err = cudaMalloc(&p, sz);
+      if (*err != cudaSuccess) return nullptr;
+      chunks.push_back(p);
+      used = 0;
+      if (sz > chunk_size) { used = sz; return p; }
+    }
+    uint8_t* r = chunks.back() + used;
+    used += n;
+    *err = cudaSuccess;
+    return r;
+  }
+  void release() { for (auto* c : chunks) cudaFree(c); chunks.clear(); used = 0; }
+};
+
+uint32_t env_u32(const char* name, uint32_t def) {
+  const char* v = getenv(name);
+  if (!v || !*v) return def;
+  return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+}  // namespace
+
+struct tq_ctx {
+  int device = 0;
+  std::mutex mu;  // guards segments, list cache, arena, batch pool, stats
+  std::map<std::pair<uint32_t, uint32_t>, Segment> segments;
+  ListDesc* d_lists = nullptr;
+  uint32_t lists_cap = 0, n_lists = 0;
+  std::unordered_map<ListKey, uint32_t, ListKeyHash> list_cache;
+  Arena arena;
+  cudaStream_t build_stream = nullptr;
+  PinBuf build_pin;
+  DevBuf build_dev;
+  std::vector<tq_batch*> pool;
+  tq_stats stats{};
+  uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
+};
+
+struct tq_batch {
+  tq_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+  PinBuf pin;      // staged descriptors (H2D source)
+  DevBuf dev;      // descriptors on device
+  DevBuf scratch;  // qstate + candidates + results
+  PinBuf res_pin;  // results (D2H target)
+  BatchParams params{};
+  size_t desc_bytes = 0;
+  uint32_t nq = 0, kmax = 0;
+  uint32_t n_units[3] = {0, 0, 0};
+  uint32_t unit_base[3] = {0, 0, 0};
+  size_t qstate_off = 0, cands_off = 0, res_off = 0, res_bytes = 0, n_cands = 0;
+  tq_stats stats{};
+  bool ran = false;
+};
+
+#define TQ_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      g_err = std::string(#expr) + ": " + cudaGetErrorString(_e);                             \
+      return TQ_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+extern "C" {
+
+const char* tq_last_error(tq_ctx*) { return g_err.c_str(); }
+
+int tq_ctx_create(int device, tq_ctx** out) {
+  if (!out) return fail(TQ_ERR_INVALID_ARGUMENT, "out is null");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(TQ_ERR_CUDA, std::string("no CUDA device: the B200 path has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (device < 0 || device >= n) return fail(TQ_ERR_INVALID_ARGUMENT, "bad device ordinal");
+  TQ_CUDA(cudaSetDevice(device));
+  auto* c = new tq_ctx();
+  c->device = device;
+  c->lists_cap = env_u32("TQ_MAX_LISTS", 1u << 20);
+  c->term_blocks_per_unit = env_u32("TQ_TERM_BLOCKS_PER_UNIT", 512);
+  c->and_blocks_per_unit = env_u32("TQ_AND_BLOCKS_PER_UNIT", 128);
+  c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
+  cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileDocs * sizeof(float)));
+  if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
+  *out = c;
+  return TQ_OK;
+}
+
+void tq_batch_destroy_real(tq_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  b->pin.release(); b->dev.release(); b->scratch.release(); b->res_pin.release();
+  if (b->ev_start) cudaEventDestroy(b->ev_start);
+  if (b->ev_k0) cudaEventDestroy(b->ev_k0);
+  if (b->ev_k1) cudaEventDestroy(b->ev_k1);
+  if (b->ev_end) cudaEventDestroy(b->ev_end);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+void tq_ctx_destroy(tq_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto* b : c->pool) tq_batch_destroy_real(b);
+  for (auto& kv : c->segments) {
+    cudaFree(kv.second.d_idx); cudaFree(kv.second.d_fieldnorm); cudaFree(kv.second.d_alive);
+  }
+  c->arena.release();
+  c->build_pin.release(); c->build_dev.release();
+  if (c->build_stream) cudaStreamDestroy(c->build_stream);
+  cudaFree(c->d_lists);
+  delete c;
+}
+
+int tq_get_stats(tq_ctx* c, tq_stats* out) {
+  if (!c || !out) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  std::lock_guard<std::mutex> g(c->mu);
+  *out = c->stats;
+  out->lists_cached = c->n_lists;
+  return TQ_OK;
+}
+
+int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_t max_doc, int record_option,
+                        const uint8_t* idx_body, size_t idx_len, const uint8_t* fieldnorm, size_t fieldnorm_len,
+                        const uint8_t* alive_bitset, size_t alive_len) {
+  if (!c || !idx_body || idx_len < 8) return fail(TQ_ERR_INVALID_ARGUMENT, "idx_body must hold the 8-byte header");
+  if (record_option < 0 || record_option > 2) return fail(TQ_ERR_INVALID_ARGUMENT, "record_option");
+  if (max_doc >= TQ_TERMINATED) return fail(TQ_ERR_INVALID_ARGUMENT, "max_doc");
+  if (fieldnorm && fieldnorm_len < max_doc) return fail(TQ_ERR_INVALID_ARGUMENT, "fieldnorm shorter than max_doc");
+  if (alive_bitset && alive_len * 8 < max_doc) return fail(TQ_ERR_INVALID_ARGUMENT, "alive bitset shorter than max_doc");
+  TQ_CUDA(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> g(c->mu);
+  if (c->segments.count({segment_ord, field})) return fail(TQ_ERR_INVALID_ARGUMENT, "segment/field already registered");
+  Segment s;
+  s.segment_ord = segment_ord; s.field = field; s.max_doc = max_doc; s.record_option = record_option; s.idx_len = idx_len;
+  const size_t pad = 64;  // decode_block may read one word past a block
+  TQ_CUDA(cudaMalloc(&s.d_idx, idx_len + pad));
+  TQ_CUDA(cudaMemset(s.d_idx + idx_len, 0, pad));
+  TQ_CUDA(cudaMemcpy(s.d_idx, idx_body, idx_len, cudaMemcpyHostToDevice));
+  if (fieldnorm) {
+    TQ_CUDA(cudaMalloc(&s.d_fieldnorm, std::max<size_t>(max_doc, 1)));
+    TQ_CUDA(cudaMemcpy(s.d_fieldnorm, fieldnorm, max_doc, cudaMemcpyHostToDevice));
+  }
+  if (alive_bitset) {
+    TQ_CUDA(cudaMalloc(&s.d_alive, std::max<size_t>(alive_len, 1)));
+    TQ_CUDA(cudaMemcpy(s.d_alive, alive_bitset, alive_len, cudaMemcpyHostToDevice));
+  }
+  c->segments[{segment_ord, field}] = s;
+  return TQ_OK;
+}
+
+int tq_segment_unregister(tq_ctx* c, uint32_t segment_ord, uint32_t field) {
+  if (!c) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  cudaSetDevice(c->device);
+  std::lock_guard<std::mutex> g(c->mu);
+  auto it = c->segments.find({segment_ord, field});
+  if (it == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "segment/field not registered");
+  cudaDeviceSynchronize();
+  cudaFree(it->second.d_idx); cudaFree(it->second.d_fieldnorm); cudaFree(it->second.d_alive);
+  c->segments.erase(it);
+  for (auto li = c->list_cache.begin(); li != c->list_cache.end();)
+    if (li->first.segment_ord == segment_ord && li->first.field == field) li = c->list_cache.erase(li); else ++li;
+  return TQ_OK;
+}
+
+}  // extern "C"
+
+// ---- list cache ---------------------------------------------------------------------------------
+namespace {
+
+struct PendingBuild { BuildJob job; ListDesc desc; };
+
+// Looks a posting list up in the cache or schedules its table build. ctx->mu held.
+int get_list(tq_ctx* c, const tq_term_seg& ts, std::vector<PendingBuild>& pending, uint32_t* list_id, const Segment** seg_out) {
+  auto sit = c->segments.find({ts.segment_ord, ts.field});
+  if (sit == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "term_seg names a segment/field that is not registered");
+  const Segment& seg = sit->second;
+  *seg_out = &seg;
+  if (ts.postings_end < ts.postings_start || ts.postings_end + 8 > seg.idx_len) return fail(TQ_ERR_INVALID_ARGUMENT, "postings range outside the field body");
+  if (ts.postings_end - ts.postings_start > 0xFFFFFFFFull) return fail(TQ_ERR_UNSUPPORTED, "posting list larger than 4 GiB");
+  const ListKey key{ts.segment_ord, ts.field, ts.postings_start};
+  auto it = c->list_cache.find(key);
+  if (it != c->list_cache.end()) { *list_id = it->second; return TQ_OK; }
+  if (c->n_lists >= c->lists_cap) return fail(TQ_ERR_OOM, "posting-list table cache full (TQ_MAX_LISTS)");
+  const uint32_t n_blocks = ts.doc_freq / 128u, tail_n = ts.doc_freq % 128u;
+  cudaError_t e;
+  const size_t n_last = (size_t)n_blocks + 1, n_blk = (size_t)n_blocks + 1;
+  uint8_t* mem = c->arena.alloc(n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
+  if (!mem) return fail(TQ_ERR_OOM, std::string("block table alloc: ") + cudaGetErrorString(e));
+  PendingBuild pb;
+  ListDesc& d = pb.desc;
+  memset(&d, 0, sizeof(d));
+  uint8_t* p = mem;
+  d.blk = reinterpret_cast<const uint2*>(p); p += n_blk * 8;
+  d.last_doc = reinterpret_cast<const uint32_t*>(p); p += n_last * 4;
+  d.tail_docs = reinterpret_cast<const uint32_t*>(p); p += (size_t)tail_n * 4;
+  d.tail_tfs = reinterpret_cast<const uint32_t*>(p);
+  d.fieldnorm = seg.d_fieldnorm;
+  d.n_blocks = n_blocks; d.tail_n = tail_n; d.n_total = n_blocks + (tail_n ? 1u : 0u); d.doc_freq = ts.doc_freq;
+  pb.job.bytes = seg.d_idx + 8 + ts.postings_start;
+  pb.job.len = (uint32_t)(ts.postings_end - ts.postings_start);
+  pb.job.doc_freq = ts.doc_freq;
+  pb.job.record_option = (uint32_t)seg.record_option;
+  pb.job.list_id = c->n_lists;
+  *list_id = c->n_lists++;
+  c->list_cache.emplace(key, *list_id);
+  pending.push_back(pb);
+  return TQ_OK;
+}
+
+// Builds every pending table and waits for it (first use of a term only). ctx->mu held.
+int flush_builds(tq_ctx* c, std::vector<PendingBuild>& pending, uint64_t* built) {
+  if (pending.empty()) return TQ_OK;
+  const size_t n = pending.size();
+  // new lists have consecutive ids
+  const uint32_t first_id = pending.front().job.list_id;
+  TQ_CUDA(c->build_pin.ensure(n * (sizeof(ListDesc) + sizeof(BuildJob))));
+  TQ_CUDA(c->build_dev.ensure(n * sizeof(BuildJob)));
+  ListDesc* hd = reinterpret_cast<ListDesc*>(c->build_pin.p);
+  BuildJob* hj = reinterpret_cast<BuildJob*>(c->build_pin.p + n * sizeof(ListDesc));
+  for (size_t i = 0; i < n; ++i) { hd[i] = pending[i].desc; hj[i] = pending[i].job; }
+  TQ_CUDA(cudaMemcpyAsync(c->d_lists + first_id, hd, n * sizeof(ListDesc), cudaMemcpyHostToDevice, c->build_stream));
+  TQ_CUDA(cudaMemcpyAsync(c->build_dev.p, hj, n * sizeof(BuildJob), cudaMemcpyHostToDevice, c->build_stream));
+  k_build_tables<<<(unsigned)n, kThreads, 0, c->build_stream>>>(reinterpret_cast<const BuildJob*>(c->build_dev.p), c->d_lists);
+  TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaMemcpyAsync(hd, c->d_lists + first_id, n * sizeof(ListDesc), cudaMemcpyDeviceToHost, c->build_stream));
+  TQ_CUDA(cudaStreamSynchronize(c->build_stream));
+  for (size_t i = 0; i < n; ++i)
+    if (hd[i].build_status != 0) return fail(TQ_ERR_CORRUPT, "posting list bytes are not a valid tantivy posting list");
+  *built += n;
+  pending.clear();
+  return TQ_OK;
+}
+
+struct CacheKey {
+  std::vector<float> table;
+};
+
+}  // namespace
+
+// ---- batches ---------------------------------------------------------------------------------------
+static tq_batch* acquire_batch(tq_ctx* c) {
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    if (!c->pool.empty()) { tq_batch* b = c->pool.back(); c->pool.pop_back(); return b; }
+  }
+  auto* b = new tq_batch();
+  b->ctx = c;
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev_start) != cudaSuccess ||
+      cudaEventCreate(&b->ev_k0) != cudaSuccess || cudaEventCreate(&b->ev_k1) != cudaSuccess || cudaEventCreate(&b->ev_end) != cudaSuccess) {
+    tq_batch_destroy_real(b);
+    return nullptr;
+  }
+  return b;
+}
+
+extern "C" {
+
+void tq_batch_destroy(tq_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->stream);
+  std::lock_guard<std::mutex> g(b->ctx->mu);
+  b->ctx->pool.push_back(b);  // buffers are recycled by the next batch
+}
+
+int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** out) {
+  if (!c || !out || (!queries && nq)) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  tq_batch* b = acquire_batch(c);
+  if (!b) return fail(TQ_ERR_CUDA, "stream/event creation failed");
+  struct Guard { tq_batch* b; bool ok = false; ~Guard() { if (!ok) tq_batch_destroy(b); } } guard{b};
+  b->ran = false;
+  b->nq = (uint32_t)nq;
+  b->stats = tq_stats{};
+
+  std::vector<QList> qlists;
+  std::vector<QSeg> qsegs;
+  std::vector<Unit> units[3];
+  std::vector<DQuery> dq(nq);
+  std::vector<float> caches;  // n_caches * 256
+  std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
+  std::vector<PendingBuild> pending;
+  uint64_t built = 0, alg_bytes = 0, postings = 0;
+  uint32_t kmax = 1;
+  size_t n_cands = 0;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    std::vector<const tq_term_seg*> order;
+    for (size_t qi = 0; qi < nq; ++qi) {
+      const tq_query& q = queries[qi];
+      if (q.k == 0 || q.k > TQ_MAX_K) return fail(TQ_ERR_INVALID_ARGUMENT, "k must be in 1..TQ_MAX_K");
+      if (q.n_terms == 0 || q.n_terms > TQ_MAX_TERMS) return fail(TQ_ERR_INVALID_ARGUMENT, "n_terms must be in 1..TQ_MAX_TERMS");
+      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
+      if (q.op == TQ_OP_TERM && q.n_terms != 1) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_TERM takes one term");
+      if (!q.weight || (!q.avg_fieldnorm && !q.tf_cache) || (!q.term_segs && q.n_term_segs)) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
+      kmax = std::max(kmax, q.k);
+      alg_bytes += 12ull * q.k;
+      // tf-norm tables of this query's clauses
+      uint32_t cache_idx[TQ_MAX_TERMS];
+      for (uint32_t t = 0; t < q.n_terms; ++t) {
+        if (q.tf_cache) {
+          cache_idx[t] = (uint32_t)(caches.size() / 256);
+          caches.insert(caches.end(), q.tf_cache + 256 * (size_t)t, q.tf_cache + 256 * (size_t)(t + 1));
+        } else {
+          uint32_t bits;
+          memcpy(&bits, &q.avg_fieldnorm[t], 4);
+          auto it = cache_by_avg.find(bits);
+          if (it == cache_by_avg.end()) {
+            float tab[256];
+            bm25_tf_cache(q.avg_fieldnorm[t], tab);
+            it = cache_by_avg.emplace(bits, (uint32_t)(caches.size() / 256)).first;
+            caches.insert(caches.end(), tab, tab + 256);
+          }
+          cache_idx[t] = it->second;
+        }
+      }
+      // effective shape: an AND / OR of one clause is that clause (boolean_weight.rs:57-68, block_wand_union.rs:154-157)
+      const int op = q.n_terms == 1 ? TQ_OP_TERM : q.op;
+      // group the (clause, segment) lists by segment
+      order.clear();
+      for (uint32_t i = 0; i < q.n_term_segs; ++i) {
+        if (q.term_segs[i].term_idx >= q.n_terms) return fail(TQ_ERR_INVALID_ARGUMENT, "term_idx out of range");
+        if (q.term_segs[i].doc_freq) order.push_back(&q.term_segs[i]);
+      }
+      std::stable_sort(order.begin(), order.end(), [](const tq_term_seg* a, const tq_term_seg* b) {
+        return a->segment_ord != b->segment_ord ? a->segment_ord < b->segment_ord : a->term_idx < b->term_idx;
+      });
+      uint32_t q_units = 0;
+      for (size_t i = 0; i < order.size();) {
+        size_t j = i;
+        while (j < order.size() && order[j]->segment_ord == order[i]->segment_ord) ++j;
+        // lists of this (query, segment), clause order
+        const size_t n_here = j - i;
+        bool dup = false;
+        for (size_t a = i + 1; a < j; ++a) dup |= order[a]->term_idx == order[a - 1]->term_idx;
+        if (dup) return fail(TQ_ERR_INVALID_ARGUMENT, "duplicate (term_idx, segment_ord)");
+        if (op == TQ_OP_AND && n_here != q.n_terms) { i = j; continue; }  // a clause is absent: empty intersection
+        QSeg qs;
+        memset(&qs, 0, sizeof(qs));
+        qs.query = (uint32_t)qi;
+        qs.lists_base = (uint32_t)qlists.size();
+        qs.segment_ord = order[i]->segment_ord;
+        uint32_t lead_total = 0;
+        std::vector<std::pair<uint32_t, QList>> here;  // (doc_freq, list)
+        const Segment* seg = nullptr;
+        for (size_t a = i; a < j; ++a) {
+          uint32_t id;
+          int rc = get_list(c, *order[a], pending, &id, &seg);
+          if (rc != TQ_OK) return rc;
+          QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
+          here.push_back({order[a]->doc_freq, ql});
+          alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          postings += order[a]->doc_freq;
+        }
+        qs.max_doc = seg->max_doc;
+        qs.alive = seg->d_alive;
+        if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
+          std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
+        for (auto& h : here) qlists.push_back(h.second);
+        qs.n_lists = (uint32_t)here.size();
+        lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
+        const uint32_t qseg_id = (uint32_t)qsegs.size();
+        qsegs.push_back(qs);
+        if (op == TQ_OP_OR) {
+          const uint32_t n_tiles = (qs.max_doc + kTileDocs - 1) / kTileDocs;
+          for (uint32_t t0 = 0; t0 < n_tiles; t0 += c->or_tiles_per_unit) {
+            units[TQ_OP_OR].push_back(Unit{qseg_id, t0, std::min(n_tiles, t0 + c->or_tiles_per_unit), 0});
+            ++q_units;
+          }
+        } else {
+          const uint32_t per = op == TQ_OP_TERM ? c->term_blocks_per_unit : c->and_blocks_per_unit;
+          for (uint32_t b0 = 0; b0 < lead_total; b0 += per) {
+            units[op].push_back(Unit{qseg_id, b0, std::min(lead_total, b0 + per), 0});
+            ++q_units;
+          }
+        }
+        i = j;
+      }
+      dq[qi].k = q.k;
+      dq[qi].op = (uint32_t)op;
+      dq[qi].cand_base = (uint32_t)n_cands;
+      dq[qi].cand_cap = q_units * q.k;
+      n_cands += (size_t)q_units * q.k;
+      if (n_cands > 0xFFFFFFF0ull) return fail(TQ_ERR_UNSUPPORTED, "batch too large: split it");
+    }
+    int rc = flush_builds(c, pending, &built);
+    if (rc != TQ_OK) return rc;
+  }
+  if (caches.empty()) caches.resize(256, 0.0f);
+
+  // ---- stage descriptors -------------------------------------------------------------------------
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t o_caches = off; off = align(off + caches.size() * 4);
+  const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
+  const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size();
+  const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
+  const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
+  b->desc_bytes = off;
+  TQ_CUDA(b->pin.ensure(off + 256));
+  TQ_CUDA(b->dev.ensure(off + 256));
+  memcpy(b->pin.p + o_caches, caches.data(), caches.size() * 4);
+  if (!qlists.empty()) memcpy(b->pin.p + o_qlists, qlists.data(), qlists.size() * sizeof(QList));
+  if (!qsegs.empty()) memcpy(b->pin.p + o_qsegs, qsegs.data(), qsegs.size() * sizeof(QSeg));
+  {
+    Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
+    uint32_t base = 0;
+    for (int op = 0; op < 3; ++op) {
+      b->unit_base[op] = base;
+      b->n_units[op] = (uint32_t)units[op].size();
+      if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
+      base += (uint32_t)units[op].size();
+    }
+  }
+  if (!dq.empty()) memcpy(b->pin.p + o_queries, dq.data(), dq.size() * sizeof(DQuery));
+
+  // ---- scratch: qstate | candidates | results ------------------------------------------------------
+  b->kmax = kmax;
+  b->n_cands = n_cands;
+  size_t so = 0;
+  b->qstate_off = so; so = align(so + std::max<size_t>(nq, 1) * sizeof(QState));
+  b->cands_off = so; so = align(so + std::max<size_t>(n_cands, 1) * sizeof(Cand));
+  b->res_off = so;
+  const size_t rows = std::max<size_t>(nq, 1) * kmax;
+  const size_t o_rs = 0, o_rg = align(rows * 4), o_rd = o_rg + align(rows * 4), o_rc = o_rd + align(rows * 4);
+  b->res_bytes = o_rc + align(std::max<size_t>(nq, 1) * 4);
+  so += b->res_bytes;
+  TQ_CUDA(b->scratch.ensure(so));
+  TQ_CUDA(b->res_pin.ensure(b->res_bytes));
+
+  BatchParams& P = b->params;
+  P.lists = c->d_lists;
+  P.caches = reinterpret_cast<const float*>(b->dev.p + o_caches);
+  P.qlists = reinterpret_cast<const QList*>(b->dev.p + o_qlists);
+  P.qsegs = reinterpret_cast<const QSeg*>(b->dev.p + o_qsegs);
+  P.units = reinterpret_cast<const Unit*>(b->dev.p + o_units);
+  P.queries = reinterpret_cast<const DQuery*>(b->dev.p + o_queries);
+  P.qstate = reinterpret_cast<QState*>(b->scratch.p + b->qstate_off);
+  P.cands = reinterpret_cast<Cand*>(b->scratch.p + b->cands_off);
+  uint8_t* r = b->scratch.p + b->res_off;
+  P.res_scores = reinterpret_cast<float*>(r + o_rs);
+  P.res_segs = reinterpret_cast<uint32_t*>(r + o_rg);
+  P.res_docs = reinterpret_cast<uint32_t*>(r + o_rd);
+  P.res_counts = reinterpret_cast<uint32_t*>(r + o_rc);
+  P.res_stride = kmax;
+  P.n_queries = (uint32_t)nq;
+
+  TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));
+  b->stats.lists_built = built;
+  b->stats.units = n_units_total;
+  b->stats.h2d_bytes = b->desc_bytes;
+  b->stats.algorithmic_bytes = alg_bytes;
+  b->stats.postings = postings;
+  guard.ok = true;
+  *out = b;
+  return TQ_OK;
+}
+
+int tq_batch_run(tq_batch* b) {
+  if (!b) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  const BatchParams& P = b->params;
+  uint64_t launches = 0;
+  TQ_CUDA(cudaMemsetAsync(P.qstate, 0, std::max<size_t>(b->nq, 1) * sizeof(QState), b->stream));
+  TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
+  if (b->n_units[TQ_OP_TERM]) { k_term<<<b->n_units[TQ_OP_TERM], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_TERM]); ++launches; }
+  if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
+  if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kTileDocs * sizeof(float), b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
+  TQ_CUDA(cudaGetLastError());
+  if (b->nq) { k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches; }
+  TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaEventRecord(b->ev_k1, b->stream));
+  b->stats.kernel_launches = launches;
+  b->ran = true;
+  return TQ_OK;
+}
+
+int tq_batch_results_dev(tq_batch* b, const float** scores_dev, const uint32_t** segment_ord_dev, const uint32_t** doc_dev,
+                         const uint32_t** count_dev, uint32_t* stride) {
+  if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  if (scores_dev) *scores_dev = b->params.res_scores;
+  if (segment_ord_dev) *segment_ord_dev = b->params.res_segs;
+  if (doc_dev) *doc_dev = b->params.res_docs;
+  if (count_dev) *count_dev = b->params.res_counts;
+  if (stride) *stride = b->kmax;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
+  std::lock_guard<std::mutex> g(b->ctx->mu);
+  b->ctx->stats = b->stats;
+  return TQ_OK;
+}
+
+int tq_batch_fetch(tq_batch* b, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc, uint32_t* out_count) {
+  if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  if (!out_scores || !out_segment_ord || !out_doc || !out_count) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  TQ_CUDA(cudaMemcpyAsync(b->res_pin.p, b->scratch.p + b->res_off, b->res_bytes, cudaMemcpyDeviceToHost, b->stream));
+  TQ_CUDA(cudaEventRecord(b->ev_end, b->stream));
+  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  const size_t rows = std::max<size_t>(b->nq, 1) * b->kmax;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const float* rs = reinterpret_cast<const float*>(b->res_pin.p);
+  const uint32_t* rg = reinterpret_cast<const uint32_t*>(b->res_pin.p + align(rows * 4));
+  const uint32_t* rd = reinterpret_cast<const uint32_t*>(b->res_pin.p + 2 * align(rows * 4));
+  const uint32_t* rc = reinterpret_cast<const uint32_t*>(b->res_pin.p + 3 * align(rows * 4));
+  for (uint32_t q = 0; q < b->nq; ++q) {
+    const uint32_t n = std::min(std::min(rc[q], b->kmax), out_stride);
+    out_count[q] = rc[q];
+    memcpy(out_scores + (size_t)q * out_stride, rs + (size_t)q * b->kmax, n * 4);
+    memcpy(out_segment_ord + (size_t)q * out_stride, rg + (size_t)q * b->kmax, n * 4);
+    memcpy(out_doc + (size_t)q * out_stride, rd + (size_t)q * b->kmax, n * 4);
+  }
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev_start, b->ev_end) == cudaSuccess) b->stats.total_ms = ms;
+  b->stats.d2h_bytes = b->res_bytes;
+  std::lock_guard<std::mutex> g(b->ctx->mu);
+  b->ctx->stats = b->stats;
+  return TQ_OK;
+}
+
+int tq_search_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord,
+                    uint32_t* out_doc, uint32_t* out_count) {
+  tq_batch* b = nullptr;
+  int rc = tq_batch_prepare(c, queries, nq, &b);
+  if (rc != TQ_OK) return rc;
+  rc = tq_batch_run(b);
+  if (rc == TQ_OK) rc = tq_batch_fetch(b, out_stride, out_scores, out_segment_ord, out_doc, out_count);
+  tq_batch_destroy(b);
+  return rc;
+}
+
+int tq_merge_topk_dev(tq_ctx* c, uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k, const float* scores_dev,
+                      const uint32_t* segment_ord_dev, const uint32_t* doc_dev, const uint32_t* count_dev, float* out_scores_dev,
+                      uint32_t* out_segment_ord_dev, uint32_t* out_doc_dev, uint32_t* out_count_dev) {
+  if (!c) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  if (k == 0 || k > TQ_MAX_K || stride < 1) return fail(TQ_ERR_INVALID_ARGUMENT, "k / stride");
+  TQ_CUDA(cudaSetDevice(c->device));
+  if (nq == 0) return TQ_OK;
+  k_merge<<<nq, kThreads, 0, 0>>>(n_lists, nq, stride, std::min(k, stride), scores_dev, segment_ord_dev, doc_dev, count_dev, out_scores_dev,
+                                  out_segment_ord_dev, out_doc_dev, out_count_dev);
+  TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaStreamSynchronize(0));
+  return TQ_OK;
+}
+
+// ---- codec-level access ---------------------------------------------------------------------------
+static int resolve_single(tq_ctx* c, const tq_term_seg* list, uint32_t* id) {
+  std::lock_guard<std::mutex> g(c->mu);
+  std::vector<PendingBuild> pending;
+  const Segment* seg;
+  uint64_t built = 0;
+  int rc = get_list(c, *list, pending, id, &seg);
+  if (rc != TQ_OK) return rc;
+  return flush_builds(c, pending, &built);
+}
+
+int tq_decode_postings(tq_ctx* c, const tq_term_seg* list, uint32_t* out_docs, uint32_t* out_tfs) {
+  if (!c || !list || !out_docs) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  if (list->doc_freq == 0) return TQ_OK;
+  uint32_t id;
+  int rc = resolve_single(c, list, &id);
+  if (rc != TQ_OK) return rc;
+  uint32_t *d_docs = nullptr, *d_tfs = nullptr;
+  const size_t bytes = (size_t)list->doc_freq * 4;
+  TQ_CUDA(cudaMalloc(&d_docs, bytes));
+  TQ_CUDA(cudaMalloc(&d_tfs, bytes));
+  const uint32_t n_total = list->doc_freq / 128u + ((list->doc_freq % 128u) ? 1u : 0u);
+  k_decode_list<<<(n_total + kWarps - 1) / kWarps, kThreads>>>(c->d_lists, id, d_docs, d_tfs);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out_docs, d_docs, bytes, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && out_tfs) e = cudaMemcpy(out_tfs, d_tfs, bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_docs); cudaFree(d_tfs);
+  if (e != cudaSuccess) return fail(TQ_ERR_CUDA, cudaGetErrorString(e));
+  return TQ_OK;
+}
+
+int tq_block_table(tq_ctx* c, const tq_term_seg* list, float weight, float avg_fieldnorm, uint32_t* out_last_doc, float* out_block_max) {
+  if (!c || !list || !out_last_doc || !out_block_max) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  const uint32_t n = list->doc_freq / 128u;
+  if (n == 0) return TQ_OK;
+  uint32_t id;
+  int rc = resolve_single(c, list, &id);
+  if (rc != TQ_OK) return rc;
+  float tab[256];
+  bm25_tf_cache(avg_fieldnorm, tab);
+  float *d_cache = nullptr, *d_bm = nullptr;
+  uint32_t* d_last = nullptr;
+  TQ_CUDA(cudaMalloc(&d_cache, 1024));
+  TQ_CUDA(cudaMalloc(&d_bm, (size_t)n * 4));
+  TQ_CUDA(cudaMalloc(&d_last, (size_t)n * 4));
+  cudaError_t e = cudaMemcpy(d_cache, tab, 1024, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_block_max<<<(n + 255) / 256, 256>>>(c->d_lists, id, weight, d_cache, d_last, d_bm);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out_last_doc, d_last, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(out_block_max, d_bm, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_cache); cudaFree(d_bm); cudaFree(d_last);
+  if (e != cudaSuccess) return fail(TQ_ERR_CUDA, cudaGetErrorString(e));
+  return TQ_OK;
+}
+
+// ---- BM25 scalars --------------------------------------------------------------------------------------
+float tq_bm25_idf(uint64_t doc_freq, uint64_t doc_count) { return bm25_idf(doc_freq, doc_count); }
+float tq_bm25_weight(uint64_t doc_freq, uint64_t doc_count, float boost) { return bm25_weight(doc_freq, doc_count, boost); }
+void tq_bm25_tf_cache(float avg_fieldnorm, float out[256]) { bm25_tf_cache(avg_fieldnorm, out); }
+uint32_t tq_id_to_fieldnorm(uint8_t id) { return id_to_fieldnorm(id); }
+uint8_t tq_fieldnorm_to_id(uint32_t fieldnorm) { return fieldnorm_to_id(fieldnorm); }
+
+// ---- segment writer ----------------------------------------------------------------------------------
+struct tq_field_writer {
+  std::vector<uint8_t> fieldnorm_ids;
+  FieldPostingsWriter* w = nullptr;
+};
+
+int tq_field_writer_create(int record_option, uint64_t total_num_tokens, const uint8_t* fieldnorm_ids, uint32_t max_doc, tq_field_writer** out) {
+  if (!out || record_option < 0 || record_option > 2) return fail(TQ_ERR_INVALID_ARGUMENT, "args");
+  auto* fw = new tq_field_writer();
+  if (fieldnorm_ids) fw->fieldnorm_ids.assign(fieldnorm_ids, fieldnorm_ids + max_doc);
+  fw->w = new FieldPostingsWriter(record_option, total_num_tokens, fieldnorm_ids ? fw->fieldnorm_ids.data() : nullptr, max_doc);
+  *out = fw;
+  return TQ_OK;
+}
+int tq_field_writer_add_term(tq_field_writer* fw, const uint32_t* docs, const uint32_t* tfs, uint32_t doc_freq, uint64_t* postings_start,
+                             uint64_t* postings_end) {
+  if (!fw || (!docs && doc_freq)) return fail(TQ_ERR_INVALID_ARGUMENT, "args");
+  for (uint32_t i = 0; i < doc_freq; ++i) {
+    if (i && docs[i] <= docs[i - 1]) return fail(TQ_ERR_INVALID_ARGUMENT, "docs must be strictly ascending");
+    if (docs[i] >= TQ_TERMINATED) return fail(TQ_ERR_INVALID_ARGUMENT, "doc id out of range");
+    if (tfs && tfs[i] == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "term frequency 0");
+  }
+  const TermInfoOut ti = fw->w->add_term(docs, tfs, doc_freq);
+  if (postings_start) *postings_start = ti.postings_start;
+  if (postings_end) *postings_end = ti.postings_end;
+  return TQ_OK;
+}
+int tq_field_writer_body(tq_field_writer* fw, const uint8_t** body, size_t* len) {
+  if (!fw || !body || !len) return fail(TQ_ERR_INVALID_ARGUMENT, "args");
+  *body = fw->w->body().data();
+  *len = fw->w->body().size();
+  return TQ_OK;
+}
+void tq_field_writer_destroy(tq_field_writer* fw) {
+  if (!fw) return;
+  delete fw->w;
+  delete fw;
+}
+
+}  // extern "C"

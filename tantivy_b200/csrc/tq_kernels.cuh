@@ -1,0 +1,478 @@
+// The sm_100a kernels of the query path.  One CTA (8 warps) per work unit; one warp per 128-doc
+// posting block; exact per-CTA top-k buffers reduced per query by k_final.
+//
+//   k_build_tables  SkipReader::read_block_info/advance as ONE exclusive scan (src/postings/skip.rs:205-302)
+//                   + decode_vint_block for the tail (src/postings/block_segment_postings.rs:56-76)
+//   k_term          block_wand_single_scorer's result set (block_wand_union.rs:226-265), exhaustive form
+//   k_and           block_wand_intersection's result set (block_wand_intersection.rs:19-179): leader =
+//                   rarest list, secondaries probed through their block tables; score summed
+//                   leader first, then secondaries by ascending doc_freq (:27,146-158)
+//   k_or            BufferedUnionScorer's shape (union/buffered_union.rs:63-151): a doc-id window of
+//                   score slots in shared memory, clauses accumulated in clause order
+//   k_final         TopBySortKeyCollector::merge_fruits / merge_top_k (sort_key_top_collector.rs:54-95)
+#pragma once
+#include "tq_device.cuh"
+
+namespace tq {
+
+struct BuildJob {
+  const uint8_t* bytes;  // the term's postings range
+  uint32_t len;
+  uint32_t doc_freq;
+  uint32_t record_option;
+  uint32_t list_id;
+};
+
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// One CTA per posting list.  Fills last_doc / blk / tail arrays of its ListDesc.
+__global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __restrict__ jobs, ListDesc* __restrict__ lists) {
+  const BuildJob J = jobs[blockIdx.x];
+  ListDesc& L = lists[J.list_id];
+  uint32_t* last_doc = const_cast<uint32_t*>(L.last_doc);
+  uint2* blk = const_cast<uint2*>(L.blk);
+  uint32_t* tail_docs = const_cast<uint32_t*>(L.tail_docs);
+  uint32_t* tail_tfs = const_cast<uint32_t*>(L.tail_tfs);
+  const uint32_t n_blocks = J.doc_freq / 128u, tail_n = J.doc_freq % 128u;
+  __shared__ uint32_t s_hdr, s_skip_len, s_rec, s_status, s_carry;
+  __shared__ uint32_t s_wsum[kWarps];
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  if (tid == 0) {
+    uint32_t hdr = 0, skip_len = 0, rec = J.record_option == 0 ? 5u : (J.record_option == 1 ? 8u : 12u), status = 0;
+    if (J.doc_freq >= 128u) {  // split_into_skips_and_postings (block_segment_postings.rs:78-88)
+      uint64_t v = 0;
+      uint32_t shift = 0;
+      bool done = false;
+      while (hdr < J.len && hdr < 10u) {
+        const uint8_t b = J.bytes[hdr++];
+        v |= (uint64_t)(b & 127u) << shift;
+        shift += 7;
+        if (b & 128u) { done = true; break; }
+      }
+      if (!done || v > (uint64_t)J.len - hdr) status = 1;
+      skip_len = (uint32_t)v;
+      // a field indexed with freqs can hold terms written without (block_segment_postings.rs:116-123)
+      if (rec != 5u && skip_len < 8u * n_blocks) rec = 5u;
+      if ((uint64_t)rec * n_blocks > skip_len) status = 1;
+    }
+    s_hdr = hdr; s_skip_len = skip_len; s_rec = rec; s_status = status; s_carry = 0;
+  }
+  __syncthreads();
+  const uint32_t rec = s_rec;
+  const uint8_t* skip = J.bytes + s_hdr;
+  const uint8_t* blocks = skip + s_skip_len;
+  const uint32_t avail = J.len - s_hdr - s_skip_len;
+  if (s_status == 0) {
+    for (uint32_t base = 0; base < n_blocks; base += kThreads) {
+      const uint32_t i = base + tid;
+      uint32_t size = 0, meta = 0, last = 0;
+      if (i < n_blocks) {
+        const uint8_t* r = skip + (size_t)i * rec;
+        last = load_u32_unaligned(r);
+        const uint32_t bw = r[4];
+        const uint32_t db = bw & 31u, strict = (bw >> 6) & 1u;
+        uint32_t tb = 0, bm_fn = 0, bm_tf = 0;
+        if (rec == 8u) { tb = r[5]; bm_fn = r[6]; bm_tf = r[7]; }
+        else if (rec == 12u) { tb = r[5]; bm_fn = r[10]; bm_tf = r[11]; }
+        if (tb > 32u) { tb = 32u; s_status = 1; }
+        size = 16u * (db + tb);
+        meta = db | (strict << 6) | (tb << 8) | (bm_fn << 16) | (bm_tf << 24);
+      }
+      const uint32_t incl = warp_incl_scan(size, lane);
+      if (lane == 31) s_wsum[warp] = incl;
+      __syncthreads();
+      uint32_t woff = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) woff += (w < (int)warp) ? s_wsum[w] : 0u;
+      const uint32_t excl = s_carry + woff + incl - size;
+      if (i < n_blocks) { last_doc[i] = last; blk[i] = make_uint2(excl, meta); }
+      __syncthreads();
+      if (tid == kThreads - 1) s_carry = excl + size;
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    uint32_t status = s_status;
+    const uint32_t total = s_carry;
+    blk[n_blocks] = make_uint2(total, 0u);
+    if (total > avail) status = 1;
+    if (tail_n && status == 0) {
+      // decode_vint_block: plain deltas from last_doc_in_previous_block, tfs raw (serializer.rs:456-468)
+      const uint8_t* p = blocks + total;
+      uint32_t remaining = avail - total, pos = 0;
+      uint32_t result = n_blocks ? load_u32_unaligned(skip + (size_t)(n_blocks - 1) * rec) : 0u;
+      for (uint32_t i = 0; i < tail_n && status == 0; ++i) {
+        uint32_t shift = 0;
+        for (;;) {
+          if (pos >= remaining) { status = 1; break; }
+          const uint8_t b = p[pos++];
+          result += (uint32_t)(b & 127u) << shift;
+          if (b & 128u) break;
+          shift += 7;
+        }
+        tail_docs[i] = result;
+      }
+      const bool read_freq = (rec != 5u) && pos < remaining;  // block_segment_postings.rs:66-75
+      for (uint32_t i = 0; i < tail_n && status == 0; ++i) {
+        uint32_t v = 1u;
+        if (read_freq) {
+          v = 0;
+          uint32_t shift = 0;
+          for (;;) {
+            if (pos >= remaining) { status = 1; break; }
+            const uint8_t b = p[pos++];
+            v += (uint32_t)(b & 127u) << shift;
+            if (b & 128u) break;
+            shift += 7;
+          }
+        }
+        tail_tfs[i] = v;
+      }
+      if (status == 0) last_doc[n_blocks] = tail_docs[tail_n - 1];
+    }
+    L.blocks = blocks;
+    L.has_freq = rec != 5u;
+    L.build_status = status;
+  }
+}
+
+// ---- K1 stand-alone: whole-list decode (parity tests, decode micro-benchmark) ------------------
+__global__ void __launch_bounds__(kThreads) k_decode_list(const ListDesc* __restrict__ lists, uint32_t list_id,
+                                                          uint32_t* __restrict__ out_docs, uint32_t* __restrict__ out_tfs) {
+  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
+  const ListDesc L = lists[list_id];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t b = blockIdx.x * kWarps + warp;
+  if (b >= L.n_total) return;
+  uint32_t doc[4], tf[4];
+  decode_block(L, b, s_stage[warp], lane, doc, tf);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t j = b * 128u + lane * 4u + i;
+    if (j < L.doc_freq) { out_docs[j] = doc[i]; if (out_tfs) out_tfs[j] = tf[i]; }
+  }
+}
+
+// Block-max score of every full block (SkipReader::block_max_score, skip.rs:175-184).
+__global__ void k_block_max(const ListDesc* __restrict__ lists, uint32_t list_id, float weight, const float* __restrict__ cache,
+                            uint32_t* __restrict__ out_last_doc, float* __restrict__ out_block_max) {
+  const ListDesc L = lists[list_id];
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= L.n_blocks) return;
+  const uint32_t meta = L.blk[b].y;
+  const uint32_t code = meta >> 24;
+  const uint32_t tf = code == 255u ? 0xFFFFFFFFu : code;
+  out_last_doc[b] = L.last_doc[b];
+  out_block_max[b] = bm25_score_id(weight, cache, (meta >> 16) & 255u, tf);
+}
+
+// ---- shared CTA scaffolding ------------------------------------------------------------------------
+struct CtaTopK {
+  unsigned long long keys[kCap];
+  unsigned int count;
+  unsigned long long theta;
+};
+
+// ---- single term ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t unit_base) {
+  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
+  __shared__ CtaTopK s_top;
+  const Unit U = P.units[unit_base + blockIdx.x];
+  const QSeg S = P.qsegs[U.qseg];
+  const DQuery Q = P.queries[S.query];
+  QState* qs = P.qstate + S.query;
+  const QList ql = P.qlists[S.lists_base];
+  const ListDesc L = P.lists[ql.list_id];
+  const float* cache = P.caches + 256u * ql.cache_idx;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
+  __syncthreads();
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  for (uint32_t r = U.begin; r < U.end; r += kWarps) {
+    const uint32_t b = r + warp;
+    if (b < U.end) {
+      uint32_t doc[4], tf[4];
+      decode_block(L, b, s_stage[warp], lane, doc, tf);
+      const unsigned long long theta = *T.theta;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const bool valid = doc[i] < S.max_doc;  // also rejects the kTerminated padding of the tail
+        const float score = valid ? bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+        const unsigned long long key = make_key(score, doc[i]);
+        bool pass = valid && key >= theta;
+        if (pass && S.alive) pass = is_alive(S.alive, doc[i]);
+        topk_push(T, pass, key, lane);
+      }
+    }
+    topk_round_end(T, Q.k, &qs->theta);
+  }
+  topk_flush(T, Q, qs, P.cands, S.segment_ord);
+}
+
+// ---- intersection ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t unit_base) {
+  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
+  __shared__ uint32_t s_dec[kWarps][256];  // a decoded secondary block: 128 docs, 128 tfs
+  __shared__ CtaTopK s_top;
+  const Unit U = P.units[unit_base + blockIdx.x];
+  const QSeg S = P.qsegs[U.qseg];
+  const DQuery Q = P.queries[S.query];
+  QState* qs = P.qstate + S.query;
+  const QList ql0 = P.qlists[S.lists_base];
+  const ListDesc L0 = P.lists[ql0.list_id];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* stage = s_stage[warp];
+  uint32_t* dec = s_dec[warp];
+  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
+  __syncthreads();
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  for (uint32_t r = U.begin; r < U.end; r += kWarps) {
+    const uint32_t b = r + warp;
+    if (b < U.end) {
+      uint32_t doc[4], tf0[4];
+      decode_block(L0, b, stage, lane, doc, tf0);
+      uint32_t alive_m = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) alive_m |= (doc[i] < S.max_doc) ? (1u << i) : 0u;  // rejects tail padding
+      float total[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t s = 1; s < S.n_lists; ++s) {
+        if (__ballot_sync(kFull, alive_m != 0) == 0) break;
+        const QList qls = P.qlists[S.lists_base + s];
+        const ListDesc Ls = P.lists[qls.list_id];
+        const float* cache_s = P.caches + 256u * qls.cache_idx;
+        uint32_t pending = alive_m;
+        uint32_t stf[4] = {1u, 1u, 1u, 1u};
+        uint32_t cur = 0;
+        for (;;) {
+          // smallest unresolved candidate of the warp (candidates ascend with lane*4+i)
+          const uint32_t c = (pending & 1u) ? doc[0] : (pending & 2u) ? doc[1] : (pending & 4u) ? doc[2] : (pending & 8u) ? doc[3] : 0xFFFFFFFFu;
+          const uint32_t cmin = warp_min(c);
+          if (cmin == 0xFFFFFFFFu) break;
+          const uint32_t j = first_block_ge(Ls.last_doc, cur, Ls.n_total, cmin, lane);
+          if (j >= Ls.n_total) { alive_m &= ~pending; pending = 0; break; }  // past the end of this list
+          const uint32_t blk_last = __ldg(Ls.last_doc + j);
+          uint32_t sd[4], st[4];
+          decode_block(Ls, j, stage, lane, sd, st);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dec[lane * 4 + i] = sd[i]; dec[128 + lane * 4 + i] = st[i]; }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (((pending >> i) & 1u) && doc[i] <= blk_last) {
+              uint32_t lo = 0;
+#pragma unroll
+              for (uint32_t step = 64; step > 0; step >>= 1)
+                if (dec[lo + step - 1] < doc[i]) lo += step;
+              if (dec[lo] == doc[i]) stf[i] = dec[128 + lo]; else alive_m &= ~(1u << i);
+              pending &= ~(1u << i);
+            }
+          }
+          cur = j + 1;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((alive_m >> i) & 1u) {
+            if (s == 1) total[i] = bm25_score(ql0.weight, P.caches + 256u * ql0.cache_idx, L0.fieldnorm, doc[i], tf0[i]);
+            total[i] = __fadd_rn(total[i], bm25_score(qls.weight, cache_s, Ls.fieldnorm, doc[i], stf[i]));
+          }
+        }
+      }
+      const unsigned long long theta = *T.theta;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned long long key = make_key(total[i], doc[i]);
+        bool pass = ((alive_m >> i) & 1u) && key >= theta;
+        if (pass && S.alive) pass = is_alive(S.alive, doc[i]);
+        topk_push(T, pass, key, lane);
+      }
+    }
+    topk_round_end(T, Q.k, &qs->theta);
+  }
+  topk_flush(T, Q, qs, P.cands, S.segment_ord);
+}
+
+// ---- union -------------------------------------------------------------------------------------------------
+// dynamic shared memory: kTileDocs f32 score slots.  A slot holding -0.0f has not been touched:
+// -0.0 + s == 0.0 + s bit for bit for every s except s == -0.0 (SumCombiner starts from 0.0).
+__global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t unit_base) {
+  extern __shared__ __align__(16) float s_acc[];
+  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
+  __shared__ CtaTopK s_top;
+  __shared__ uint32_t s_blo[32], s_bhi[32], s_cur[32];
+  __shared__ uint32_t s_any;
+  const Unit U = P.units[unit_base + blockIdx.x];
+  const QSeg S = P.qsegs[U.qseg];
+  const DQuery Q = P.queries[S.query];
+  QState* qs = P.qstate + S.query;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* stage = s_stage[warp];
+  const float neg_zero = __uint_as_float(0x80000000u);
+  for (uint32_t i = threadIdx.x; i < kTileDocs; i += kThreads) s_acc[i] = neg_zero;
+  if (threadIdx.x < 32) s_cur[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; s_any = 0; }
+  __syncthreads();
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  for (uint32_t tile = U.begin; tile < U.end; ++tile) {
+    const uint32_t lo = tile * kTileDocs;
+    const uint32_t hi = min(lo + kTileDocs, S.max_doc);
+    // which blocks of every clause overlap [lo, hi)
+    for (uint32_t t = warp; t < S.n_lists; t += kWarps) {
+      const QList ql = P.qlists[S.lists_base + t];
+      uint32_t blo = 1, bhi = 0, cur = 0;
+      if (ql.list_id != kNoList) {
+        const uint32_t* last_doc = P.lists[ql.list_id].last_doc;
+        const uint32_t n_total = P.lists[ql.list_id].n_total;
+        const uint32_t j_lo = first_block_ge(last_doc, s_cur[t], n_total, lo, lane);
+        cur = j_lo;
+        if (j_lo < n_total) {
+          // the block after the last one starting below hi is the first whose predecessor ends >= hi-1
+          uint32_t j_hi = first_block_ge(last_doc, j_lo, n_total, hi - 1u, lane);
+          if (j_hi >= n_total) j_hi = n_total - 1u;
+          blo = j_lo; bhi = j_hi;
+        }
+      }
+      if (lane == 0) { s_blo[t] = blo; s_bhi[t] = bhi; s_cur[t] = cur; if (blo <= bhi) s_any = 1; }
+    }
+    __syncthreads();
+    const bool any = s_any != 0;
+    if (any) {
+      for (uint32_t t = 0; t < S.n_lists; ++t) {
+        const uint32_t blo = s_blo[t], bhi = s_bhi[t];
+        if (blo <= bhi) {
+          const QList ql = P.qlists[S.lists_base + t];
+          const ListDesc L = P.lists[ql.list_id];
+          const float* cache = P.caches + 256u * ql.cache_idx;
+          for (uint32_t b = blo + warp; b <= bhi; b += kWarps) {
+            uint32_t doc[4], tf[4];
+            decode_block(L, b, stage, lane, doc, tf);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (doc[i] >= lo && doc[i] < hi) {
+                const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
+                const uint32_t slot = doc[i] - lo;
+                s_acc[slot] = __fadd_rn(s_acc[slot], sc);
+              }
+            }
+          }
+        }
+        __syncthreads();  // clause order is the f32 summation order
+      }
+      // harvest the window
+      for (uint32_t base = 0; base < kTileDocs; base += kThreads * 4) {
+        const uint32_t idx = base + threadIdx.x * 4;
+        float4 v = *reinterpret_cast<float4*>(s_acc + idx);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        const unsigned long long theta = *T.theta;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool touched = __float_as_uint(vv[c]) != 0x80000000u;
+          const uint32_t d = lo + idx + c;
+          const unsigned long long key = make_key(vv[c], d);
+          bool pass = touched && key >= theta;
+          if (pass && S.alive) pass = is_alive(S.alive, d);
+          topk_push(T, pass, key, lane);
+        }
+        *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+        topk_round_end(T, Q.k, &qs->theta);
+      }
+    }
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+  }
+  topk_flush(T, Q, qs, P.cands, S.segment_ord);
+}
+
+// ---- final per-query selection -----------------------------------------------------------------------------
+// Keys: a = score_key:32 | (0xFFFFFFFF - segment_ord):32, b = ~doc; descending (a, b) is
+// (score desc, segment_ord asc, doc asc) = compare_for_top_k (top_score_collector.rs:591-600).
+__device__ void sort_pairs_desc(unsigned long long* a, uint32_t* b, unsigned n) {
+  unsigned size = 2;
+  while (size < n) size <<= 1;
+  for (unsigned i = threadIdx.x; i < size; i += blockDim.x)
+    if (i >= n) { a[i] = 0ull; b[i] = 0u; }
+  __syncthreads();
+  for (unsigned kk = 2; kk <= size; kk <<= 1) {
+    for (unsigned j = kk >> 1; j > 0; j >>= 1) {
+      for (unsigned i = threadIdx.x; i < size; i += blockDim.x) {
+        const unsigned ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a1 = a[i], a2 = a[ixj];
+          const uint32_t b1 = b[i], b2 = b[ixj];
+          const bool first_less = a1 < a2 || (a1 == a2 && b1 < b2);
+          const bool first_greater = a1 > a2 || (a1 == a2 && b1 > b2);
+          const bool desc = (i & kk) == 0;
+          if (desc ? first_less : first_greater) { a[i] = a2; a[ixj] = a1; b[i] = b2; b[ixj] = b1; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
+  __shared__ unsigned long long s_a[kCap];
+  __shared__ uint32_t s_b[kCap];
+  const uint32_t q = blockIdx.x;
+  const DQuery Q = P.queries[q];
+  const uint32_t C = min(P.qstate[q].cand_count, Q.cand_cap);
+  uint32_t have = 0, next = 0;
+  for (;;) {
+    const uint32_t take = min(C - next, kCap - have);
+    for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) {
+      const Cand c = P.cands[Q.cand_base + next + i];
+      s_a[have + i] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
+      s_b[have + i] = ~c.doc;
+    }
+    next += take;
+    const uint32_t n = have + take;
+    __syncthreads();
+    sort_pairs_desc(s_a, s_b, n);
+    have = min(n, Q.k);
+    if (next >= C) break;
+  }
+  for (uint32_t i = threadIdx.x; i < have; i += blockDim.x) {
+    const size_t o = (size_t)q * P.res_stride + i;
+    P.res_scores[o] = key_to_score((uint32_t)(s_a[i] >> 32));
+    P.res_segs[o] = 0xFFFFFFFFu - (uint32_t)s_a[i];
+    P.res_docs[o] = ~s_b[i];
+  }
+  if (threadIdx.x == 0) P.res_counts[q] = have;
+}
+
+// K7 (device half): merge_fruits across result sets gathered from several GPUs.
+// in: [n_lists][nq][stride] rows sorted like k_final's output; out: [nq][stride].
+__global__ void __launch_bounds__(kThreads) k_merge(uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k,
+                                                    const float* __restrict__ in_scores, const uint32_t* __restrict__ in_segs,
+                                                    const uint32_t* __restrict__ in_docs, const uint32_t* __restrict__ in_counts,
+                                                    float* __restrict__ out_scores, uint32_t* __restrict__ out_segs,
+                                                    uint32_t* __restrict__ out_docs, uint32_t* __restrict__ out_counts) {
+  __shared__ unsigned long long s_a[kCap];
+  __shared__ uint32_t s_b[kCap];
+  const uint32_t q = blockIdx.x;
+  uint32_t have = 0;
+  for (uint32_t l = 0; l < n_lists; ++l) {
+    const uint32_t cnt = min(min(in_counts[(size_t)l * nq + q], stride), k);
+    // have <= k <= 1024 and cnt <= 1024, so have + cnt <= kCap
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const size_t o = ((size_t)l * nq + q) * stride + i;
+      s_a[have + i] = ((unsigned long long)score_to_key(in_scores[o]) << 32) | (unsigned long long)(0xFFFFFFFFu - in_segs[o]);
+      s_b[have + i] = ~in_docs[o];
+    }
+    const uint32_t n = have + cnt;
+    __syncthreads();
+    sort_pairs_desc(s_a, s_b, n);
+    have = min(n, k);
+  }
+  for (uint32_t i = threadIdx.x; i < have; i += blockDim.x) {
+    const size_t o = (size_t)q * stride + i;
+    out_scores[o] = key_to_score((uint32_t)(s_a[i] >> 32));
+    out_segs[o] = 0xFFFFFFFFu - (uint32_t)s_a[i];
+    out_docs[o] = ~s_b[i];
+  }
+  if (threadIdx.x == 0) out_counts[q] = have;
+}
+
+}  // namespace tq

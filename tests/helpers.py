@@ -16,19 +16,29 @@ def f32(x):
     return np.float32(x)
 
 
+_FN_TABLE = np.array(GOLDEN["field_norms_table"], dtype=np.uint64)
+
+
 def fieldnorm_ids(fieldnorms):
-    return np.array([O.fieldnorm_to_id(int(f)) for f in fieldnorms], dtype=np.uint8)
+    """fieldnorm_to_id for an array: index of the last table entry <= fieldnorm (code.rs:7-11)."""
+    f = np.asarray(fieldnorms, dtype=np.uint64)
+    return (np.searchsorted(_FN_TABLE, f, side="right") - 1).astype(np.uint8)
 
 
 class OracleSegment:
     """One segment, one field, built from explicit posting lists (docs, tfs) and doc lengths."""
 
     def __init__(self, posting_lists, fieldnorms, record_option=TQ_RECORD_FREQS, segment_ord=0, field=0,
-                 writer_cls=None, alive=None):
-        self.fieldnorms = np.asarray(fieldnorms, dtype=np.uint32)
-        self.max_doc = len(self.fieldnorms)
-        self.fn_ids = fieldnorm_ids(self.fieldnorms)
-        self.total_num_tokens = int(self.fieldnorms.astype(np.uint64).sum())
+                 writer_cls=None, alive=None, max_doc=None):
+        if fieldnorms is None:  # field without fieldnorms: constant fieldnorm 1 (term_weight.rs:218)
+            self.fieldnorms, self.fn_ids = None, None
+            self.max_doc = max_doc
+            self.total_num_tokens = max_doc
+        else:
+            self.fieldnorms = np.asarray(fieldnorms, dtype=np.uint32)
+            self.max_doc = len(self.fieldnorms)
+            self.fn_ids = fieldnorm_ids(self.fieldnorms)
+            self.total_num_tokens = int(self.fieldnorms.astype(np.uint64).sum())
         self.record_option = record_option
         self.segment_ord, self.field = segment_ord, field
         writer_cls = writer_cls or O.FieldWriter

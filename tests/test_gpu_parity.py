@@ -1,0 +1,341 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Doc ids and segment ordinals must be bit-exact; scores are compared bit-exact too
+(the device computes BM25 with the reference's f32 operation order; tolerance stated where the
+reference itself is order dependent).  Edge cases follow the reference's tests: empty / one-doc /
+127 / 128 / 129-doc lists, blocks starting at doc 0, every bit width, deletes, absent terms."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import tantivy_b200 as T  # noqa: E402
+from oracle import tq_oracle as O  # noqa: E402
+from tantivy_b200._abi import (TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM, TQ_RECORD_BASIC, TQ_RECORD_FREQS,  # noqa: E402
+                               TQ_RECORD_FREQS_POSITIONS, QueryBatch)
+from tests.helpers import OracleSegment, hits, make_query  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = T.Context(0)
+    yield c
+    c.close()
+
+
+_next_seg = [1000]
+
+
+def fresh_ord():
+    _next_seg[0] += 1
+    return _next_seg[0]
+
+
+def both(ctx, segments):
+    oi = O.OracleIndex()
+    for s in segments:
+        s.register(oi)
+        s.register(ctx)
+    return oi
+
+
+def assert_same(gpu_res, cpu_res, nq, exact_scores=True):
+    for i in range(nq):
+        g, c = hits(gpu_res, i), hits(cpu_res, i)
+        assert [(s, d) for _, s, d in g] == [(s, d) for _, s, d in c], f"query {i}: doc ids differ\n gpu={g[:8]}\n cpu={c[:8]}"
+        for (sg, _, _), (sc, _, _) in zip(g, c):
+            if exact_scores:
+                assert sg == sc, f"query {i}: score {sg!r} != {sc!r}"
+            else:
+                assert abs(sg - sc) <= 1e-5 * max(abs(sg), abs(sc))
+
+
+# ---- K1: block decode -------------------------------------------------------------------------------
+def _lists_all_widths(rng, max_doc):
+    lists = []
+    for bits in list(range(0, 21)) + [24]:
+        n = 128 * 3 + int(rng.integers(0, 128))
+        gaps = rng.integers(1, 2 ** bits + 1, size=n, dtype=np.uint64)
+        gaps[5] = 2 ** bits  # force the width
+        start = int(rng.integers(0, 3))
+        docs = start + np.cumsum(gaps) - gaps[0]
+        docs = docs[docs < max_doc].astype(np.uint32)
+        tf_bits = int(rng.integers(0, 12))
+        tfs = rng.integers(1, 2 ** tf_bits + 1, size=len(docs), dtype=np.uint64).astype(np.uint32)
+        lists.append((docs, tfs))
+    for n in (1, 2, 127, 128, 129, 255, 256, 257):
+        docs = np.sort(rng.choice(max_doc, size=n, replace=False)).astype(np.uint32)
+        lists.append((docs, rng.integers(1, 9, size=n).astype(np.uint32)))
+    lists.append((np.arange(0, 300, dtype=np.uint32), np.ones(300, np.uint32)))  # 0-bit deltas from doc 0
+    big = np.ones(200, np.uint32)
+    big[17] = 0xFFFFFFFF  # 32-bit tf width
+    lists.append((np.arange(5, 205, dtype=np.uint32), big))
+    return lists
+
+
+@pytest.mark.parametrize("record_option", [TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS])
+def test_decode_every_width_and_alignment(ctx, record_option):
+    rng = np.random.default_rng(42 + record_option)
+    max_doc = 2 ** 26
+    lists = _lists_all_widths(rng, max_doc)
+    if record_option == TQ_RECORD_BASIC:
+        lists = [(d, None) for d, _ in lists]
+    so = fresh_ord()
+    seg = OracleSegment(lists, None, record_option=record_option, segment_ord=so, writer_cls=T.FieldWriter, max_doc=max_doc)
+    oi = both(ctx, [seg])
+    starts = set()
+    for t, (docs, tfs) in enumerate(lists):
+        ts = seg.term_seg(t)
+        starts.add(ts[4] % 4)
+        d_g, f_g = ctx.decode_postings(ts)
+        d_c, f_c = oi.decode_postings(ts)
+        assert (d_g == d_c).all() and (d_g == docs).all(), f"term {t}"
+        assert (f_g == f_c).all(), f"term {t}"
+    assert len(starts) > 1  # both aligned and misaligned block starts were exercised
+
+
+def test_block_table_matches_skip_reader(ctx):
+    rng = np.random.default_rng(9)
+    max_doc = 400_000
+    fieldnorms = rng.integers(1, 2000, size=max_doc)
+    lists = []
+    for p in (0.3, 0.02, 0.004):
+        docs = np.nonzero(rng.random(max_doc) < p)[0].astype(np.uint32)
+        tfs = np.minimum(rng.geometric(0.7, size=len(docs)), 300).astype(np.uint32)
+        tfs[::97] = 300  # saturated block-max tf codes
+        lists.append((docs, tfs))
+    seg = OracleSegment(lists, fieldnorms, segment_ord=fresh_ord(), writer_cls=T.FieldWriter)
+    oi = both(ctx, [seg])
+    w, avg = O.bm25_weight(len(lists[0][0]), max_doc), float(np.float32(seg.total_num_tokens) / np.float32(max_doc))
+    for t in range(3):
+        lg, bg = ctx.block_table(seg.term_seg(t), w, avg)
+        lc, bc = oi.block_table(seg.term_seg(t), w, avg)
+        assert (lg == lc).all()
+        assert (bg == bc).all()
+
+
+# ---- queries on small random segments ------------------------------------------------------------------
+def _random_segments(rng, n_segments, n_terms, max_doc_range=(300, 40_000), dens=(0.5, 0.2, 0.05, 0.01, 0.002), deletes=False):
+    segs = []
+    for _ in range(n_segments):
+        max_doc = int(rng.integers(*max_doc_range))
+        fieldnorms = np.clip(np.round(np.exp(rng.normal(np.log(40), 0.7, size=max_doc))), 1, 4096).astype(np.uint32)
+        lists = []
+        for t in range(n_terms):
+            p = dens[t % len(dens)] * float(rng.uniform(0.5, 1.5))
+            docs = np.nonzero(rng.random(max_doc) < p)[0].astype(np.uint32)
+            tfs = np.minimum(rng.geometric(0.6, size=len(docs)), 10).astype(np.uint32)
+            lists.append((docs, tfs))
+        alive = None
+        if deletes:
+            alive_bits = rng.random(max_doc) > 0.2
+            alive = np.packbits(alive_bits, bitorder="little")
+        segs.append(OracleSegment(lists, fieldnorms, segment_ord=fresh_ord(), writer_cls=T.FieldWriter, alive=alive))
+    return segs
+
+
+def _run_both(ctx, segs, queries):
+    oi = both(ctx, segs)
+    qb = QueryBatch(queries)
+    return ctx.search_batch(qb), oi.search_batch(qb, mode=0), qb.nq
+
+
+@pytest.mark.parametrize("n_segments", [1, 3])
+def test_term_queries(ctx, n_segments):
+    rng = np.random.default_rng(100 + n_segments)
+    segs = _random_segments(rng, n_segments, 5)
+    queries = [make_query(TQ_OP_TERM, segs, [t], k) for t in range(5) for k in (1, 10, 100, 1000)]
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+@pytest.mark.parametrize("n_segments", [1, 3])
+def test_and_queries(ctx, n_segments):
+    rng = np.random.default_rng(200 + n_segments)
+    segs = _random_segments(rng, n_segments, 5)
+    combos = [[0, 1], [0, 4], [3, 0], [4, 3], [0, 1, 2], [4, 0, 2], [0, 1, 2, 3, 4], [2, 2 - 1]]
+    queries = [make_query(TQ_OP_AND, segs, terms, k) for terms in combos for k in (1, 10, 300)]
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+@pytest.mark.parametrize("n_segments", [1, 3])
+def test_or_queries(ctx, n_segments):
+    rng = np.random.default_rng(300 + n_segments)
+    segs = _random_segments(rng, n_segments, 5)
+    combos = [[0, 1], [4, 3], [3, 0], [0, 1, 2], [0, 1, 2, 3, 4], [4, 2, 0]]
+    queries = [make_query(TQ_OP_OR, segs, terms, k) for terms in combos for k in (1, 10, 100, 1024)]
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+def test_many_term_union_and_wide_segments(ctx):
+    rng = np.random.default_rng(400)
+    segs = _random_segments(rng, 2, 20, max_doc_range=(100_000, 200_000), dens=(0.05, 0.01, 0.002, 0.0005))
+    queries = [make_query(TQ_OP_OR, segs, list(range(20)), 10), make_query(TQ_OP_OR, segs, list(range(0, 20, 3)), 100),
+               make_query(TQ_OP_AND, segs, [0, 4, 8], 10), make_query(TQ_OP_TERM, segs, [3], 50)]
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+def test_deletes_and_absent_terms(ctx):
+    rng = np.random.default_rng(500)
+    segs = _random_segments(rng, 3, 4, deletes=True)
+    # make term 3 absent from segment 1 and term 2 absent everywhere but segment 0
+    segs[1].terms[3] = (0, 0, 0)
+    segs[1].terms[2] = (0, 0, 0)
+    segs[2].terms[2] = (0, 0, 0)
+    queries = [make_query(op, segs, terms, k) for op, terms in
+               [(TQ_OP_TERM, [3]), (TQ_OP_TERM, [2]), (TQ_OP_AND, [0, 3]), (TQ_OP_AND, [2, 1]), (TQ_OP_OR, [3, 2]), (TQ_OP_OR, [0, 2, 3])]
+               for k in (5, 50)]
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+def test_basic_record_option_and_no_fieldnorm(ctx):
+    rng = np.random.default_rng(600)
+    max_doc = 20_000
+    lists = [(np.nonzero(rng.random(max_doc) < p)[0].astype(np.uint32), None) for p in (0.3, 0.05)]
+    seg = OracleSegment(lists, None, record_option=TQ_RECORD_BASIC, segment_ord=fresh_ord(), writer_cls=T.FieldWriter, max_doc=max_doc)
+    oi = both(ctx, [seg])  # constant fieldnorm 1
+    qb = QueryBatch([make_query(TQ_OP_TERM, [seg], [0], 10), make_query(TQ_OP_AND, [seg], [0, 1], 10), make_query(TQ_OP_OR, [seg], [0, 1], 10)])
+    assert_same(ctx.search_batch(qb), oi.search_batch(qb, mode=0), qb.nq)
+
+
+def test_ties_pick_lowest_doc(ctx):
+    # every doc has the same length and tf: all scores tie; the top-k must be the k lowest doc ids
+    max_doc = 5000
+    docs = np.arange(7, max_doc, 3, dtype=np.uint32)
+    segs = [OracleSegment([(docs, np.ones(len(docs), np.uint32))], np.full(max_doc, 10), segment_ord=fresh_ord(), writer_cls=T.FieldWriter)
+            for _ in range(2)]
+    g, c, nq = _run_both(ctx, segs, [make_query(TQ_OP_TERM, segs, [0], k) for k in (1, 7, 200)])
+    assert_same(g, c, nq)
+    assert [d for _, _, d in hits(g, 1)] == list(range(7, 7 + 21, 3))
+    assert len({s for _, s, _ in hits(g, 1)}) == 1  # all from the lower segment ordinal
+
+
+def test_explicit_tf_cache_and_boost(ctx):
+    rng = np.random.default_rng(700)
+    segs = _random_segments(rng, 1, 3)
+    q = make_query(TQ_OP_OR, segs, [0, 1, 2], 20, boost=2.5)
+    q2 = dict(q)
+    q2["tf_cache"] = np.stack([O.bm25_tf_cache(np.float32(a)) for a in q["avg_fieldnorm"]])
+    g, c, nq = _run_both(ctx, segs, [q, q2])
+    assert_same(g, c, nq)
+    assert hits(g, 0) == hits(g, 1)
+
+
+def test_batch_split_and_idempotence(ctx):
+    rng = np.random.default_rng(800)
+    segs = _random_segments(rng, 2, 5)
+    for s in segs:
+        s.register(ctx)
+    queries = [make_query(op, segs, terms, 10) for op, terms in [(TQ_OP_TERM, [0]), (TQ_OP_AND, [0, 1]), (TQ_OP_OR, [1, 2, 3])] * 20]
+    qb = QueryBatch(queries)
+    a = ctx.search_batch(qb)
+    b = ctx.search_batch(qb)
+    for x, y in zip(a, b):
+        assert (x == y).all()
+    bt = ctx.prepare(qb)
+    bt.run()
+    bt.run()  # a prepared batch can be re-run
+    c3 = bt.fetch()
+    bt.close()
+    for x, y in zip(a, c3):
+        assert (x == y).all()
+    single = [ctx.search_batch(QueryBatch([q])) for q in queries[:6]]
+    for i, r in enumerate(single):
+        assert hits(r, 0) == hits(a, i)
+
+
+def test_invalid_arguments(ctx):
+    rng = np.random.default_rng(900)
+    segs = _random_segments(rng, 1, 2)
+    segs[0].register(ctx)
+    q = make_query(TQ_OP_TERM, segs, [0], 10)
+    bad = dict(q); bad["k"] = 0
+    with pytest.raises(T.TqError):
+        ctx.search_batch(QueryBatch([bad]))
+    bad = dict(q); bad["k"] = 5000
+    with pytest.raises(T.TqError):
+        ctx.search_batch(QueryBatch([bad]))
+    bad = dict(q); bad["term_segs"] = [(0, 999_999, 0, 10, 0, 10)]
+    with pytest.raises(T.TqError):
+        ctx.search_batch(QueryBatch([bad]))
+    # corrupt bytes: a list that claims a skip section but is two bytes long
+    df, s, e = segs[0].terms[0]
+    bad = dict(q); bad["term_segs"] = [(0, segs[0].segment_ord, 0, 1000, s, s + 2)]
+    with pytest.raises(T.TqError):
+        ctx.search_batch(QueryBatch([bad]))
+
+
+# ---- larger synthetic index (SURVEY.md §8d generator) ---------------------------------------------------------
+@pytest.fixture(scope="module")
+def synth(ctx):
+    dens = [0.3, 0.15, 0.05, 0.01, 0.002, 0.0001]
+    ix = T.SynthIndex(3, 1_000_000, dens, seed=77)
+    base = 5000
+    ix.register(ctx, segment_base=base)
+    oi = O.OracleIndex()
+    ix.register(oi, segment_base=base)
+    return ix, oi, base
+
+
+def test_synth_mixed_batch(ctx, synth):
+    ix, oi, base = synth
+    queries = []
+    for t in range(6):
+        queries.append(ix.query(TQ_OP_TERM, [t], 10, segment_base=base))
+    for terms in ([0, 1], [0, 3], [1, 4], [0, 5], [2, 3, 4], [0, 1, 2]):
+        queries.append(ix.query(TQ_OP_AND, terms, 10, segment_base=base))
+    for terms in ([0, 1], [3, 4], [4, 5], [0, 1, 2, 3, 4], [2, 5]):
+        queries.append(ix.query(TQ_OP_OR, terms, 100, segment_base=base))
+    qb = QueryBatch(queries)
+    g = ctx.search_batch(qb)
+    c = oi.search_batch(qb, mode=0, n_threads=8)
+    assert_same(g, c, qb.nq)
+    st = ctx.stats()
+    assert st["units"] > 0 and st["kernel_launches"] >= 3 and st["algorithmic_bytes"] > 0
+
+
+def test_synth_pruned_reference_path_agrees(ctx, synth):
+    """The reference-faithful CPU path (Block-WAND + TopNHeap) returns the same hits as the GPU for
+    term and AND queries (fixed summation order); for OR the reference's order-dependent f32 sum may
+    differ in the last bits: tolerance 1e-5 relative (BASELINE.json north_star)."""
+    ix, oi, base = synth
+    q_exact = [ix.query(TQ_OP_TERM, [2], 10, segment_base=base), ix.query(TQ_OP_AND, [1, 3], 10, segment_base=base)]
+    qb = QueryBatch(q_exact)
+    assert_same(ctx.search_batch(qb), oi.search_batch(qb, mode=1), qb.nq)
+    q_or = [ix.query(TQ_OP_OR, [1, 3, 4], 10, segment_base=base)]
+    qb = QueryBatch(q_or)
+    g, c = ctx.search_batch(qb), oi.search_batch(qb, mode=1)
+    gs, cs = hits(g), hits(c)
+    assert len(gs) == len(cs)
+    for (sg, _, _), (sc, _, _) in zip(gs, cs):
+        assert abs(sg - sc) <= 1e-5 * max(abs(sg), abs(sc))
+
+
+def test_merge_topk_dev_matches_merge_fruits(ctx, synth):
+    torch = pytest.importorskip("torch")
+    ix, oi, base = synth
+    queries = [ix.query(TQ_OP_OR, [1, 3], 50, segment_base=base), ix.query(TQ_OP_TERM, [2], 50, segment_base=base)]
+    per_seg = []
+    for s in range(ix.n_segments):
+        qs = [ix.query(q["op"], terms, 50, segment_base=base, segments=[s]) for q, terms in zip(queries, ([1, 3], [2]))]
+        per_seg.append(ctx.search_batch(QueryBatch(qs)))
+    full = ctx.search_batch(QueryBatch(queries))
+    dev = torch.device("cuda:0")
+    sc = torch.tensor(np.stack([r[0] for r in per_seg]), device=dev)
+    sg = torch.tensor(np.stack([r[1] for r in per_seg]).astype(np.int64), device=dev).to(torch.int32)
+    dc = torch.tensor(np.stack([r[2] for r in per_seg]).astype(np.int64), device=dev).to(torch.int32)
+    ct = torch.tensor(np.stack([r[3] for r in per_seg]).astype(np.int64), device=dev).to(torch.int32)
+    o_sc = torch.zeros((2, 50), dtype=torch.float32, device=dev)
+    o_sg = torch.zeros((2, 50), dtype=torch.int32, device=dev)
+    o_dc = torch.zeros((2, 50), dtype=torch.int32, device=dev)
+    o_ct = torch.zeros((2,), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.merge_topk_dev(ix.n_segments, 2, 50, 50, sc.data_ptr(), sg.data_ptr(), dc.data_ptr(), ct.data_ptr(), o_sc.data_ptr(),
+                       o_sg.data_ptr(), o_dc.data_ptr(), o_ct.data_ptr())
+    assert (o_sc.cpu().numpy() == full[0]).all()
+    assert (o_sg.cpu().numpy().astype(np.uint32) == full[1]).all()
+    assert (o_dc.cpu().numpy().astype(np.uint32) == full[2]).all()
+    assert (o_ct.cpu().numpy().astype(np.uint32) == full[3]).all()

@@ -1,0 +1,125 @@
+"""CPU-side checks of the product's host code against the oracle: the segment writer produces
+byte-identical postings, the synthetic generator emits valid tantivy posting lists, BM25 scalars
+agree bit for bit, and the C-ABI library exports every symbol include/tantivy_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import tantivy_b200 as T
+from oracle import tq_oracle as O
+from tantivy_b200._abi import TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS
+from tests.helpers import OracleSegment
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tantivy_b200.h")).read()
+    names = set(re.findall(r"\b(tq_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    lib = C.CDLL(T.lib.SO_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+
+
+def test_ctx_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(T.TqError):
+        T.Context(0)
+
+
+def test_bm25_scalars_bit_identical():
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        N = int(rng.integers(1, 10**9))
+        n = int(rng.integers(1, N + 1))
+        assert T.bm25_idf(n, N) == O.bm25_idf(n, N)
+        assert T.bm25_weight(n, N, 1.0) == O.bm25_weight(n, N, 1.0)
+        assert T.bm25_weight(n, N, 2.5) == O.bm25_weight(n, N, 2.5)
+    for avg in (0.5, 2.4, 13 / 3, 95.7, 1000.0):
+        assert (T.bm25_tf_cache(np.float32(avg)) == O.bm25_tf_cache(np.float32(avg))).all()
+    assert [T.id_to_fieldnorm(i) for i in range(256)] == [O.id_to_fieldnorm(i) for i in range(256)]
+    for f in list(range(0, 5000)) + [10**6, 2**31, 2**32 - 1]:
+        assert T.fieldnorm_to_id(f) == O.fieldnorm_to_id(f)
+
+
+def _random_list(rng, max_doc, n, max_gap_bits):
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+    if max_gap_bits is None:
+        docs = np.sort(rng.choice(max_doc, size=n, replace=False)).astype(np.uint32)
+    else:
+        gaps = rng.integers(1, 2 ** max_gap_bits + 1, size=n, dtype=np.uint64)
+        docs = (np.cumsum(gaps) - 1).astype(np.uint64)
+        docs = docs[docs < max_doc].astype(np.uint32)
+    tfs = rng.integers(1, 12, size=len(docs)).astype(np.uint32)
+    return docs, tfs
+
+
+@pytest.mark.parametrize("record_option", [TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS])
+def test_writer_bytes_match_oracle(record_option):
+    rng = np.random.default_rng(11 + record_option)
+    max_doc = 300_000
+    fieldnorms = rng.integers(1, 500, size=max_doc).astype(np.uint32)
+    lists = []
+    for n, bits in [(0, None), (1, None), (127, None), (128, None), (129, None), (1000, 1), (5000, 3), (4096, 5), (777, 8), (20000, None),
+                    (256, 10), (300, 0)]:
+        docs, tfs = _random_list(rng, max_doc, n, bits)
+        if record_option == TQ_RECORD_BASIC:
+            tfs = None
+        lists.append((docs, tfs))
+    # a block that starts at doc 0 and a list with huge tfs (32-bit tf width)
+    lists.append((np.arange(0, 256, dtype=np.uint32), None if record_option == TQ_RECORD_BASIC else np.full(256, 1, np.uint32)))
+    if record_option != TQ_RECORD_BASIC:
+        big = np.full(130, 1, np.uint32)
+        big[5] = 0xFFFFFFFF
+        big[77] = 300
+        lists.append((np.arange(10, 140, dtype=np.uint32), big))
+    a = OracleSegment(lists, fieldnorms, record_option=record_option, writer_cls=O.FieldWriter)
+    b = OracleSegment(lists, fieldnorms, record_option=record_option, writer_cls=T.FieldWriter)
+    assert a.terms == b.terms
+    assert a.body.tobytes() == b.body.tobytes()
+    # and the oracle decodes what the product wrote
+    ix = O.OracleIndex()
+    b.register(ix)
+    for t, (docs, tfs) in enumerate(lists):
+        if len(docs) == 0:
+            continue
+        d, f = ix.decode_postings(b.term_seg(t))
+        assert (d == docs).all()
+        assert (f == (tfs if tfs is not None else 1)).all()
+
+
+def test_writer_rejects_bad_input():
+    w = T.FieldWriter(TQ_RECORD_FREQS, 10, np.ones(10, np.uint8), 10)
+    with pytest.raises(T.TqError):
+        w.add_term([3, 3], [1, 1])
+    with pytest.raises(T.TqError):
+        w.add_term([1, 2], [1, 0])
+
+
+def test_synth_segments_are_valid_postings():
+    dens = [0.3, 0.05, 0.001, 0.00002]
+    ix = T.SynthIndex(2, 150_000, dens, seed=1234, n_threads=4)
+    ix2 = T.SynthIndex(2, 150_000, dens, seed=1234, n_threads=1)
+    oi = O.OracleIndex()
+    ix.register(oi)
+    for s in range(2):
+        assert ix.body(s).tobytes() == ix2.body(s).tobytes()  # independent of the thread count
+        fn = ix.fieldnorm(s)
+        assert len(fn) == 150_000 and fn.min() >= 1
+        for t, p in enumerate(dens):
+            df, st, en = ix.term_info[s][t]
+            assert abs(df - p * 150_000) <= 6 * np.sqrt(p * 150_000) + 3
+            if df == 0:
+                continue
+            docs, tfs = oi.decode_postings((0, s, 0, df, st, en))
+            assert (np.diff(docs.astype(np.int64)) > 0).all() and docs[-1] < 150_000
+            assert tfs.min() >= 1 and tfs.max() <= 10
+            lens = np.array([O.id_to_fieldnorm(int(i)) for i in fn[docs[:200]]])
+            assert (tfs[:200] <= np.maximum(lens, 1) * 2).all()
