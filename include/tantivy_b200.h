@@ -96,8 +96,11 @@ typedef struct {
   uint64_t algorithmic_bytes; /* sum over (query,segment,term) of postings
                                  range bytes + doc_freq fieldnorm bytes + 12*k output */
   uint64_t postings;          /* sum of doc_freq over all lists touched */
-  float kernel_ms;            /* device time of the scoring kernels (CUDA events) */
+  float kernel_ms;            /* device time of all kernels of the batch (CUDA events on its stream) */
   float total_ms;             /* device time of the whole batch incl. copies */
+  float term_ms, and_ms, or_ms, final_ms; /* per-kernel device time (CUDA events on the launching stream) */
+  uint64_t units_term, units_and, units_or; /* CTAs launched per kernel */
+  uint64_t bytes_term, bytes_and, bytes_or; /* algorithmic bytes per kernel (same formula) */
 } tq_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -141,6 +144,10 @@ int tq_batch_fetch(tq_batch*, uint32_t out_stride, float* out_scores, uint32_t* 
 /* Device pointers of the result rows of a finished run: row stride = k_max of the batch. */
 int tq_batch_results_dev(tq_batch*, const float** scores_dev, const uint32_t** segment_ord_dev,
                          const uint32_t** doc_dev, const uint32_t** count_dev, uint32_t* stride);
+/* Copies the result rows of a finished run into caller-owned DEVICE buffers (row stride = k_max of
+ * the batch), e.g. torch tensors about to be all-gathered over NCCL. */
+int tq_batch_results_copy_dev(tq_batch*, float* scores_dev, uint32_t* segment_ord_dev, uint32_t* doc_dev,
+                              uint32_t* count_dev);
 void tq_batch_destroy(tq_batch*);
 
 /* Cross-GPU merge_fruits (sort_key_top_collector.rs:76-95): merges `n_lists` result sets

@@ -73,6 +73,16 @@ class Stats(C.Structure):
         ("postings", C.c_uint64),
         ("kernel_ms", C.c_float),
         ("total_ms", C.c_float),
+        ("term_ms", C.c_float),
+        ("and_ms", C.c_float),
+        ("or_ms", C.c_float),
+        ("final_ms", C.c_float),
+        ("units_term", C.c_uint64),
+        ("units_and", C.c_uint64),
+        ("units_or", C.c_uint64),
+        ("bytes_term", C.c_uint64),
+        ("bytes_and", C.c_uint64),
+        ("bytes_or", C.c_uint64),
     ]
 
 

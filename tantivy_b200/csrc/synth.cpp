@@ -74,8 +74,10 @@ extern "C" {
 
 // densities[i] in (0, 1]: fraction of the segment's docs containing term i.
 // record_option: 1 (WithFreqs) or 2 (WithFreqsAndPositions; positions themselves are not written).
+// segment_base: global ordinal of the first generated segment (seeds depend on the global ordinal, so a
+// rank that generates only its own shard gets the same bytes as a full generation would give it).
 tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const double* densities, uint32_t n_terms,
-                        uint64_t seed, int record_option, int n_threads) {
+                        uint64_t seed, int record_option, int n_threads, uint32_t segment_base, uint32_t segment_stride) {
   auto* ix = new tqs_index();
   ix->segs.resize(n_segments);
   ix->densities.assign(densities, densities + n_terms);
@@ -90,7 +92,7 @@ tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const do
     const size_t n_chunks = (docs_per_segment + CHUNK - 1) / CHUNK;
     std::vector<uint64_t> partial(n_chunks, 0);
     parallel_for(n_chunks, n_threads, [&](size_t c) {
-      Rng rng(mix(seed + s, 0xF1E1D0, c));
+      Rng rng(mix(seed + segment_base + (uint64_t)s * segment_stride, 0xF1E1D0, c));
       const uint32_t lo = (uint32_t)c * CHUNK, hi = std::min<uint64_t>((uint64_t)lo + CHUNK, docs_per_segment);
       uint64_t sum = 0;
       for (uint32_t d = lo; d < hi; d += 2) {
@@ -120,7 +122,7 @@ tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const do
     const uint32_t s = (uint32_t)(task / n_terms), t = (uint32_t)(task % n_terms);
     Segment& sg = ix->segs[s];
     const double p = std::min(1.0, std::max(1e-12, densities[t]));
-    Rng rng(mix(seed + s, 0x7E63, t));
+    Rng rng(mix(seed + segment_base + (uint64_t)s * segment_stride, 0x7E63, t));
     std::vector<uint32_t> docs, tfs;
     docs.reserve((size_t)(p * sg.max_doc * 1.05) + 16);
     tfs.reserve(docs.capacity());

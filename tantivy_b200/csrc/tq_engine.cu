@@ -133,6 +133,7 @@ struct tq_batch {
   tq_ctx* ctx = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_op[4] = {nullptr, nullptr, nullptr, nullptr};  // after term / and / or / final
   PinBuf pin;      // staged descriptors (H2D source)
   DevBuf dev;      // descriptors on device
   DevBuf scratch;  // qstate + candidates + results
@@ -193,6 +194,7 @@ void tq_batch_destroy_real(tq_batch* b) {
   if (b->ev_k0) cudaEventDestroy(b->ev_k0);
   if (b->ev_k1) cudaEventDestroy(b->ev_k1);
   if (b->ev_end) cudaEventDestroy(b->ev_end);
+  for (auto& e : b->ev_op) if (e) cudaEventDestroy(e);
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -339,6 +341,15 @@ struct CacheKey {
 }  // namespace
 
 // ---- batches ---------------------------------------------------------------------------------------
+static void collect_times(tq_batch* b) {
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_op[0]) == cudaSuccess) b->stats.term_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev_op[0], b->ev_op[1]) == cudaSuccess) b->stats.and_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev_op[1], b->ev_op[2]) == cudaSuccess) b->stats.or_ms = ms;
+  if (cudaEventElapsedTime(&ms, b->ev_op[2], b->ev_op[3]) == cudaSuccess) b->stats.final_ms = ms;
+}
+
 static tq_batch* acquire_batch(tq_ctx* c) {
   {
     std::lock_guard<std::mutex> g(c->mu);
@@ -347,7 +358,9 @@ static tq_batch* acquire_batch(tq_ctx* c) {
   auto* b = new tq_batch();
   b->ctx = c;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev_start) != cudaSuccess ||
-      cudaEventCreate(&b->ev_k0) != cudaSuccess || cudaEventCreate(&b->ev_k1) != cudaSuccess || cudaEventCreate(&b->ev_end) != cudaSuccess) {
+      cudaEventCreate(&b->ev_k0) != cudaSuccess || cudaEventCreate(&b->ev_k1) != cudaSuccess || cudaEventCreate(&b->ev_end) != cudaSuccess ||
+      cudaEventCreate(&b->ev_op[0]) != cudaSuccess || cudaEventCreate(&b->ev_op[1]) != cudaSuccess || cudaEventCreate(&b->ev_op[2]) != cudaSuccess ||
+      cudaEventCreate(&b->ev_op[3]) != cudaSuccess) {
     tq_batch_destroy_real(b);
     return nullptr;
   }
@@ -381,7 +394,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
   std::vector<PendingBuild> pending;
-  uint64_t built = 0, alg_bytes = 0, postings = 0;
+  uint64_t built = 0, alg_bytes = 0, postings = 0, op_bytes[3] = {0, 0, 0};
   uint32_t kmax = 1;
   size_t n_cands = 0;
   {
@@ -396,6 +409,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       if (!q.weight || (!q.avg_fieldnorm && !q.tf_cache) || (!q.term_segs && q.n_term_segs)) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
       kmax = std::max(kmax, q.k);
       alg_bytes += 12ull * q.k;
+      op_bytes[q.n_terms == 1 ? TQ_OP_TERM : q.op] += 12ull * q.k;
       // tf-norm tables of this query's clauses
       uint32_t cache_idx[TQ_MAX_TERMS];
       for (uint32_t t = 0; t < q.n_terms; ++t) {
@@ -451,6 +465,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
           QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
           here.push_back({order[a]->doc_freq, ql});
           alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          op_bytes[op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
           postings += order[a]->doc_freq;
         }
         qs.max_doc = seg->max_doc;
@@ -554,6 +569,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size();
+  b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
   return TQ_OK;
@@ -567,11 +584,15 @@ int tq_batch_run(tq_batch* b) {
   TQ_CUDA(cudaMemsetAsync(P.qstate, 0, std::max<size_t>(b->nq, 1) * sizeof(QState), b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
   if (b->n_units[TQ_OP_TERM]) { k_term<<<b->n_units[TQ_OP_TERM], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_TERM]); ++launches; }
+  TQ_CUDA(cudaEventRecord(b->ev_op[0], b->stream));
   if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
+  TQ_CUDA(cudaEventRecord(b->ev_op[1], b->stream));
   if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kTileDocs * sizeof(float), b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
   TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));
   if (b->nq) { k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches; }
   TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaEventRecord(b->ev_op[3], b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_k1, b->stream));
   b->stats.kernel_launches = launches;
   b->ran = true;
@@ -588,8 +609,23 @@ int tq_batch_results_dev(tq_batch* b, const float** scores_dev, const uint32_t**
   if (doc_dev) *doc_dev = b->params.res_docs;
   if (count_dev) *count_dev = b->params.res_counts;
   if (stride) *stride = b->kmax;
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
+  collect_times(b);
+  std::lock_guard<std::mutex> g(b->ctx->mu);
+  b->ctx->stats = b->stats;
+  return TQ_OK;
+}
+
+int tq_batch_results_copy_dev(tq_batch* b, float* scores_dev, uint32_t* segment_ord_dev, uint32_t* doc_dev, uint32_t* count_dev) {
+  if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  if (!scores_dev || !segment_ord_dev || !doc_dev || !count_dev) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  const size_t rows = (size_t)b->nq * b->kmax * 4;
+  TQ_CUDA(cudaMemcpyAsync(scores_dev, b->params.res_scores, rows, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(segment_ord_dev, b->params.res_segs, rows, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(doc_dev, b->params.res_docs, rows, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(count_dev, b->params.res_counts, (size_t)b->nq * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  collect_times(b);
   std::lock_guard<std::mutex> g(b->ctx->mu);
   b->ctx->stats = b->stats;
   return TQ_OK;
@@ -615,8 +651,8 @@ int tq_batch_fetch(tq_batch* b, uint32_t out_stride, float* out_scores, uint32_t
     memcpy(out_segment_ord + (size_t)q * out_stride, rg + (size_t)q * b->kmax, n * 4);
     memcpy(out_doc + (size_t)q * out_stride, rd + (size_t)q * b->kmax, n * 4);
   }
+  collect_times(b);
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
   if (cudaEventElapsedTime(&ms, b->ev_start, b->ev_end) == cudaSuccess) b->stats.total_ms = ms;
   b->stats.d2h_bytes = b->res_bytes;
   std::lock_guard<std::mutex> g(b->ctx->mu);

@@ -35,6 +35,7 @@ def _load():
     lib.tq_batch_run.argtypes = [vp]
     lib.tq_batch_fetch.argtypes = [vp, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_results_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
+    lib.tq_batch_results_copy_dev.argtypes = [vp, vp, vp, vp, vp]
     lib.tq_batch_destroy.argtypes = [vp]
     lib.tq_merge_topk_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tq_decode_postings.argtypes = [vp, C.POINTER(TermSeg), u32p, u32p]
@@ -54,7 +55,7 @@ def _load():
     lib.tq_field_writer_destroy.argtypes = [vp]
     # synthetic segment generator (csrc/synth.cpp)
     lib.tqs_generate.restype = vp
-    lib.tqs_generate.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, C.c_uint64, C.c_int, C.c_int]
+    lib.tqs_generate.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32]
     lib.tqs_destroy.argtypes = [vp]
     lib.tqs_num_segments.restype = C.c_uint32
     lib.tqs_num_segments.argtypes = [vp]
@@ -128,12 +129,13 @@ class FieldWriter:
 class SynthIndex:
     """Deterministic synthetic segments in tantivy format (csrc/synth.cpp)."""
 
-    def __init__(self, n_segments, docs_per_segment, densities, seed=0x7A6E7469, record_option=1, n_threads=0):
+    def __init__(self, n_segments, docs_per_segment, densities, seed=0x7A6E7469, record_option=1, n_threads=0, segment_base=0,
+                 segment_stride=1):
         dens = np.ascontiguousarray(densities, dtype=np.float64)
         self.densities = dens
         self.n_threads = n_threads or (os.cpu_count() or 1)
         self.h = LIB.tqs_generate(n_segments, docs_per_segment, dens.ctypes.data_as(C.POINTER(C.c_double)), len(dens), seed,
-                                  record_option, self.n_threads)
+                                  record_option, self.n_threads, segment_base, segment_stride)
         self.n_segments = n_segments
         self.record_option = record_option
         self.max_doc = [LIB.tqs_max_doc(self.h, s) for s in range(n_segments)]
@@ -274,6 +276,10 @@ class Batch:
         stride = C.c_uint32()
         _check(LIB.tq_batch_results_dev(self.h, C.byref(s), C.byref(g), C.byref(d), C.byref(c), C.byref(stride)), self.ctx.h)
         return s.value, g.value, d.value, c.value, stride.value
+
+    def results_copy_dev(self, scores, segs, docs, counts):
+        """raw device addresses (e.g. torch tensor .data_ptr()) of [nq, kmax] / [nq] buffers"""
+        _check(LIB.tq_batch_results_copy_dev(self.h, scores, segs, docs, counts), self.ctx.h)
 
     def close(self):
         if getattr(self, "h", None):
