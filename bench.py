@@ -89,54 +89,20 @@ def build_query_plan(wl, nq, n_batches, seed):
 OPS = {"term": 0, "and": 1, "or": 2}
 
 
-class Shard:
-    """This rank's segments of the synthetic index + global BM25 statistics."""
+def make_shard(wl, dens, rank, world, seed, dist=None, device=None):
+    """This rank's segments of the synthetic index (segment s always has seed base+s) + global statistics."""
+    import tantivy_b200 as T
+    from tantivy_b200.sharding import ShardedIndex, assign_segments
+    ords = assign_segments(wl["n_segments"], world, rank)
+    t0 = time.time()
+    ix = T.SynthIndex(len(ords), wl["docs_per_segment"], dens, seed=seed, segment_base=rank, segment_stride=world) if ords else None
+    shard = ShardedIndex(ix, ords, len(dens), dist, device)
+    shard.gen_s = time.time() - t0
+    return shard
 
-    def __init__(self, wl, dens, rank, world, seed, dist=None):
-        import tantivy_b200 as T
-        self.T = T
-        n_seg = wl["n_segments"]
-        self.global_ords = [s for s in range(n_seg) if s % world == rank]
-        t0 = time.time()
-        # segment s of the index always has seed base+s, whichever rank builds it
-        self.ix = T.SynthIndex(len(self.global_ords), wl["docs_per_segment"], dens, seed=seed, segment_base=rank, segment_stride=world) \
-            if self.global_ords else None
-        self.gen_s = time.time() - t0
-        nt = len(dens)
-        df = np.zeros(nt, dtype=np.int64)
-        tokens, docs = 0, 0
-        if self.ix:
-            for s in range(self.ix.n_segments):
-                df += np.array([self.ix.term_info[s][t][0] for t in range(nt)], dtype=np.int64)
-            tokens, docs = sum(self.ix.total_num_tokens), self.ix.num_docs()
-        stats = np.concatenate([df, [tokens, docs]]).astype(np.int64)
-        if dist is not None:  # Bm25StatisticsProvider over all shards (src/query/bm25.rs:27-50)
-            import torch
-            t = torch.from_numpy(stats).cuda()
-            dist.all_reduce(t)
-            stats = t.cpu().numpy()
-        self.df = stats[:nt]
-        self.total_tokens, self.total_docs = int(stats[nt]), int(stats[nt + 1])
-        self.avg = np.float32(np.float32(self.total_tokens) / np.float32(self.total_docs))
-        self.index_bytes = sum(self.ix.body(s).size + self.ix.fieldnorm(s).size for s in range(self.ix.n_segments)) if self.ix else 0
 
-    def register(self, target):
-        for i, g in enumerate(self.global_ords):
-            target.segment_register(g, 0, self.ix.max_doc[i], self.ix.record_option, self.ix.body(i), self.ix.fieldnorm(i), None)
-
-    def marshal(self, queries):
-        T = self.T
-        out = []
-        for op, terms, k in queries:
-            weights = [T.bm25_weight(int(self.df[t]), self.total_docs, 1.0) for t in terms]
-            term_segs = []
-            for clause, t in enumerate(terms):
-                for i, g in enumerate(self.global_ords):
-                    d, st, en = self.ix.term_info[i][t]
-                    if d:
-                        term_segs.append((clause, g, 0, d, st, en))
-            out.append(dict(op=OPS[op], k=k, weights=weights, avg_fieldnorm=[self.avg] * len(terms), term_segs=term_segs))
-        return T.QueryBatch(out)
+def marshal(shard, queries):
+    return shard.marshal([(OPS[op], terms, k) for op, terms, k in queries])
 
 
 class ClockSampler:
@@ -191,7 +157,7 @@ def cpu_reference_run(wl, shard, batches, steps, warmup, sample_queries, threads
     times = []
     for i in range(warmup + steps):
         qs = [flat[(i * sample_queries + j) % len(flat)] for j in range(sample_queries)]
-        qb = shard.marshal(qs)
+        qb = marshal(shard, qs)
         t0 = time.perf_counter()
         oi.search_batch(qb, mode=1, n_threads=threads)
         dt = time.perf_counter() - t0
@@ -234,7 +200,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        shard = Shard(wl, dens, 0, 1, args.seed)
+        shard = make_shard(wl, dens, 0, 1, args.seed)
         sample = args.cpu_sample or 64
         qps, ms = cpu_reference_run(wl, shard, batches, args.steps, args.warmup, sample, host_threads)
         line = {"metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -264,40 +230,18 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    shard = Shard(wl, dens, rank, world, args.seed, dist)
+    shard = make_shard(wl, dens, rank, world, args.seed, dist, dev)
     ctx = T.Context(local_rank)
     shard.register(ctx)
-    qbs = [shard.marshal(b) for b in batches]
+    qbs = [marshal(shard, b) for b in batches]
     k = wl["k"]
     nq = args.nq
     n_total = args.warmup + args.steps
 
-    # device buffers for the cross-GPU merge (K7)
+    cross_gpu_merge = None
     if world > 1:
-        g_sc = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
-        g_sg = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
-        g_dc = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
-        g_ct = torch.empty((world, nq), dtype=torch.int32, device=dev)
-        o_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        o_sg = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        o_dc = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        o_ct = torch.empty((nq,), dtype=torch.int32, device=dev)
-        l_sc = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        l_sg = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        l_dc = torch.empty((nq, k), dtype=torch.int32, device=dev)
-        l_ct = torch.empty((nq,), dtype=torch.int32, device=dev)
-
-    def cross_gpu_merge(batch):
-        """NCCL all-gather of this rank's rows + device merge. Returns device tensors on every rank."""
-        batch.results_copy_dev(l_sc.data_ptr(), l_sg.data_ptr(), l_dc.data_ptr(), l_ct.data_ptr())  # syncs the batch's stream
-        dist.all_gather_into_tensor(g_sc, l_sc)
-        dist.all_gather_into_tensor(g_sg, l_sg)
-        dist.all_gather_into_tensor(g_dc, l_dc)
-        dist.all_gather_into_tensor(g_ct, l_ct)
-        torch.cuda.synchronize()
-        ctx.merge_topk_dev(world, nq, k, k, g_sc.data_ptr(), g_sg.data_ptr(), g_dc.data_ptr(), g_ct.data_ptr(), o_sc.data_ptr(),
-                           o_sg.data_ptr(), o_dc.data_ptr(), o_ct.data_ptr())
-        return o_sc, o_sg, o_dc, o_ct
+        from tantivy_b200.sharding import CrossGpuMerger
+        cross_gpu_merge = CrossGpuMerger(ctx, dist, dev, nq, k)  # NCCL all-gather + device merge (K7)
 
     # ---- leg 1: `value` — descriptors resident, kernels only -----------------------------------------
     prepared = [ctx.prepare(qbs[i % len(qbs)]) for i in range(n_total)]  # also warms the block-table cache
@@ -309,24 +253,25 @@ def main():
     barrier_sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # per-launch device times of the timed steps: CUDA events recorded by the library on the stream each
+    # kernel is launched on; steps are serialised (sync per step) so that the intervals do not overlap.
+    kern = {"term_ms": [], "and_ms": [], "or_ms": [], "final_ms": [], "kernel_ms": []}
+    launches = 0
+    stats = None
     t0 = time.perf_counter()
     for i in range(args.warmup, n_total):
         prepared[i].run()
         if world > 1:
             cross_gpu_merge(prepared[i])
-    barrier_sync()
-    dt_value = time.perf_counter() - t0
-    clocks = sampler.stop()
-    # per-launch device times of the timed steps (CUDA events on each batch's stream)
-    kern = {"term_ms": [], "and_ms": [], "or_ms": [], "final_ms": [], "kernel_ms": []}
-    launches = 0
-    stats = None
-    for i in range(args.warmup, n_total):
-        prepared[i].results_dev()
+        else:
+            prepared[i].results_dev()  # waits for the step
         stats = ctx.stats()
         for key in kern:
             kern[key].append(stats[key])
         launches += stats["kernel_launches"] + (1 if world > 1 else 0)
+    barrier_sync()
+    dt_value = time.perf_counter() - t0
+    clocks = sampler.stop()
     for b in prepared:
         b.close()
 

@@ -61,8 +61,9 @@ struct QSeg {  // one (query, segment): what Collector::collect_segment sees
   uint32_t n_lists;
   uint32_t max_doc;
   uint32_t segment_ord;
-  uint32_t pad;
+  uint32_t flags;        // bit 0: every clause reads the same fieldnorm array (`fieldnorm` below)
   const uint8_t* alive;  // alive bitset bytes or null
+  const uint8_t* fieldnorm;  // shared fieldnorm ids (padded to a multiple of kTileDocs) when flags&1
 };
 struct Unit {  // one CTA's share of a QSeg
   uint32_t qseg;
@@ -106,6 +107,12 @@ __device__ __forceinline__ uint32_t score_to_key(float f) {  // order preserving
 __device__ __forceinline__ float key_to_score(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k ^ 0x80000000u) : ~k);
 }
+// Float lower bound equivalent to a key threshold, for cheap pre-filtering: every score whose key is
+// >= (k << 32) satisfies score >= threshold_score(k). No threshold yet (k == 0, or a NaN pattern) => -inf.
+__device__ __forceinline__ float threshold_score(uint32_t k) {
+  const float f = key_to_score(k);
+  return (k == 0u || f != f) ? __int_as_float(0xff800000) : f;
+}
 __device__ __forceinline__ unsigned long long make_key(float score, uint32_t doc) {
   // larger key = better hit: higher score, then LOWER doc id (sort_by_score.rs:104-110)
   return ((unsigned long long)score_to_key(score) << 32) | (unsigned long long)(0xFFFFFFFFu - doc);
@@ -127,11 +134,43 @@ __device__ __forceinline__ uint32_t warp_min(uint32_t v) {
 }
 
 // ---- K1: one warp decodes one 128-doc block ----------------------------------------------------
+// Split in two so that the HBM round trips of block b+1 overlap the scoring of block b:
+//   fetch_issue   block-table record -> packed words into registers (nothing is consumed yet)
+//   fetch_decode  realign, stage in shared memory, unpack 4 docs + 4 tfs per lane, prefix-sum
 // Lane L ends up with postings 4L..4L+3 of the block (ascending doc ids).
+constexpr int kRaw = 5;  // packed words held per lane: covers blocks of up to 159 words when prefetched
+
+struct BlockFetch {
+  uint32_t raw[kRaw];
+  uint32_t meta;    // 0xFFFFFFFF marks the VInt tail pseudo block
+  uint32_t prev;    // last doc of the previous block
+  uint32_t off;     // byte offset of the block
+};
+
+__device__ __forceinline__ void fetch_issue(const ListDesc& L, uint32_t b, uint32_t lane, BlockFetch& f) {
+  if (b >= L.n_blocks) { f.meta = 0xFFFFFFFFu; return; }
+  const uint2 rec = __ldg(L.blk + b);
+  f.meta = rec.y;
+  f.off = rec.x;
+  f.prev = b ? __ldg(L.last_doc + b - 1) : 0u;
+  const uint32_t db = rec.y & 31u, tb = (rec.y >> 8) & 63u;
+  const uint8_t* src = L.blocks + rec.x;
+  const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
+  const uint32_t need = 4u * (db + tb) + (mis ? 1u : 0u);  // aligned words that hold the block
+  if (need <= 32u * kRaw) {
+#pragma unroll
+    for (int j = 0; j < kRaw; ++j) {
+      const uint32_t i = lane + 32u * j;
+      f.raw[j] = i < need ? __ldg(src32 + i) : 0u;
+    }
+  }
+}
+
 // stage: per-warp shared memory, kStageWords u32, 16-byte aligned.
-__device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint32_t* stage, uint32_t lane,
+__device__ __forceinline__ void fetch_decode(const ListDesc& L, uint32_t b, const BlockFetch& f, uint32_t* stage, uint32_t lane,
                                              uint32_t (&doc)[4], uint32_t (&tf)[4]) {
-  if (b >= L.n_blocks) {  // VInt tail, decoded when the table was built
+  if (f.meta == 0xFFFFFFFFu) {  // VInt tail, decoded when the table was built
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint32_t j = lane * 4 + i;
@@ -141,24 +180,32 @@ __device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint
     }
     return;
   }
-  const uint2 rec = __ldg(L.blk + b);
-  const uint32_t meta = rec.y;
+  const uint32_t meta = f.meta;
   const uint32_t db = meta & 31u, strict = (meta >> 6) & 1u, tb = (meta >> 8) & 63u;
-  const uint32_t prev = b ? __ldg(L.last_doc + b - 1) : 0u;
-  const uint8_t* src = L.blocks + rec.x;
+  const uint8_t* src = L.blocks + f.off;
   const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
-  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
   const uint32_t nwords = 4u * (db + tb);
+  const uint32_t need = nwords + (mis ? 1u : 0u);
   __syncwarp();  // earlier readers of `stage` are done
-  // Coalesced 128-byte rows from HBM; posting blocks start at arbitrary byte offsets inside the
-  // .idx body, so a row is realigned with one funnel shift per word.
-  if (mis == 0) {
-    for (uint32_t i = lane; i < nwords; i += 32) stage[i] = __ldg(src32 + i);
-  } else {
+  // Posting blocks start at arbitrary byte offsets inside the .idx body: rows are fetched as aligned
+  // 128-byte lines and realigned with one funnel shift per word.
+  if (need <= 32u * kRaw) {
+    const uint32_t sh = mis * 8u;
+#pragma unroll
+    for (int j = 0; j < kRaw; ++j) {
+      const uint32_t i = lane + 32u * j;
+      const uint32_t up = __shfl_down_sync(kFull, f.raw[j], 1);
+      const uint32_t nxt = (j + 1 < kRaw) ? f.raw[(j + 1 < kRaw) ? j + 1 : 0] : 0u;
+      const uint32_t wrap = __shfl_sync(kFull, nxt, 0);
+      const uint32_t hi = lane == 31u ? wrap : up;
+      if (i < nwords) stage[i] = mis ? __funnelshift_r(f.raw[j], hi, sh) : f.raw[j];
+    }
+  } else {  // very wide block: fetched here, not prefetched
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
     const uint32_t sh = mis * 8u;
     for (uint32_t i = lane; i < nwords; i += 32) {
-      const uint32_t w0 = __ldg(src32 + i), w1 = __ldg(src32 + i + 1);
-      stage[i] = __funnelshift_r(w0, w1, sh);
+      const uint32_t w0 = __ldg(src32 + i), w1 = mis ? __ldg(src32 + i + 1) : 0u;
+      stage[i] = mis ? __funnelshift_r(w0, w1, sh) : w0;
     }
   }
   __syncwarp();
@@ -188,8 +235,15 @@ __device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint
   const uint32_t s0 = d0 + strict, s1 = s0 + d1 + strict, s2 = s1 + d2 + strict, s3 = s2 + d3 + strict;
   const uint32_t incl = warp_incl_scan(s3, lane);
   // offset 0 means "no previous doc" for strict deltas: predecessor is -1 (mod.rs:112-113)
-  const uint32_t base = ((strict && prev == 0u) ? 0xFFFFFFFFu : prev) + (incl - s3);
+  const uint32_t base = ((strict && f.prev == 0u) ? 0xFFFFFFFFu : f.prev) + (incl - s3);
   doc[0] = base + s0; doc[1] = base + s1; doc[2] = base + s2; doc[3] = base + s3;
+}
+
+__device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint32_t* stage, uint32_t lane,
+                                             uint32_t (&doc)[4], uint32_t (&tf)[4]) {
+  BlockFetch f;
+  fetch_issue(L, b, lane, f);
+  fetch_decode(L, b, f, stage, lane, doc, tf);
 }
 
 // ---- K2: BM25 of one posting (f32, reference operation order, no contraction) -------------------

@@ -25,6 +25,8 @@
 
 using namespace tq;
 
+static constexpr size_t kOrDynSmem = kTileDocs * sizeof(float) + kTileDocs;  // score slots + fieldnorm bytes
+
 namespace {
 
 thread_local std::string g_err;
@@ -179,7 +181,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTileDocs * sizeof(float)));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
   *out = c;
   return TQ_OK;
@@ -240,7 +242,9 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
   TQ_CUDA(cudaMemset(s.d_idx + idx_len, 0, pad));
   TQ_CUDA(cudaMemcpy(s.d_idx, idx_body, idx_len, cudaMemcpyHostToDevice));
   if (fieldnorm) {
-    TQ_CUDA(cudaMalloc(&s.d_fieldnorm, std::max<size_t>(max_doc, 1)));
+    const size_t padded = ((size_t)max_doc + kTileDocs - 1) / kTileDocs * kTileDocs + kTileDocs;  // k_or stages whole windows
+    TQ_CUDA(cudaMalloc(&s.d_fieldnorm, padded));
+    TQ_CUDA(cudaMemset(s.d_fieldnorm, 0, padded));
     TQ_CUDA(cudaMemcpy(s.d_fieldnorm, fieldnorm, max_doc, cudaMemcpyHostToDevice));
   }
   if (alive_bitset) {
@@ -397,6 +401,9 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   uint64_t built = 0, alg_bytes = 0, postings = 0, op_bytes[3] = {0, 0, 0};
   uint32_t kmax = 1;
   size_t n_cands = 0;
+  std::vector<int> qseg_op;
+  std::vector<uint32_t> qseg_total;
+  uint32_t n_qsegs_op[3] = {0, 0, 0};
   {
     std::lock_guard<std::mutex> g(c->mu);
     std::vector<const tq_term_seg*> order;
@@ -440,7 +447,6 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       std::stable_sort(order.begin(), order.end(), [](const tq_term_seg* a, const tq_term_seg* b) {
         return a->segment_ord != b->segment_ord ? a->segment_ord < b->segment_ord : a->term_idx < b->term_idx;
       });
-      uint32_t q_units = 0;
       for (size_t i = 0; i < order.size();) {
         size_t j = i;
         while (j < order.size() && order[j]->segment_ord == order[i]->segment_ord) ++j;
@@ -458,10 +464,13 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         uint32_t lead_total = 0;
         std::vector<std::pair<uint32_t, QList>> here;  // (doc_freq, list)
         const Segment* seg = nullptr;
+        const uint8_t* fn0 = nullptr;
+        bool uniform_fn = true;
         for (size_t a = i; a < j; ++a) {
           uint32_t id;
           int rc = get_list(c, *order[a], pending, &id, &seg);
           if (rc != TQ_OK) return rc;
+          if (a == i) fn0 = seg->d_fieldnorm; else uniform_fn &= (seg->d_fieldnorm == fn0);
           QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
           here.push_back({order[a]->doc_freq, ql});
           alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
@@ -470,33 +479,42 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         }
         qs.max_doc = seg->max_doc;
         qs.alive = seg->d_alive;
+        qs.flags = uniform_fn ? 1u : 0u;
+        qs.fieldnorm = uniform_fn ? fn0 : nullptr;
         if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
           std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
         for (auto& h : here) qlists.push_back(h.second);
         qs.n_lists = (uint32_t)here.size();
         lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
-        const uint32_t qseg_id = (uint32_t)qsegs.size();
         qsegs.push_back(qs);
-        if (op == TQ_OP_OR) {
-          const uint32_t n_tiles = (qs.max_doc + kTileDocs - 1) / kTileDocs;
-          for (uint32_t t0 = 0; t0 < n_tiles; t0 += c->or_tiles_per_unit) {
-            units[TQ_OP_OR].push_back(Unit{qseg_id, t0, std::min(n_tiles, t0 + c->or_tiles_per_unit), 0});
-            ++q_units;
-          }
-        } else {
-          const uint32_t per = op == TQ_OP_TERM ? c->term_blocks_per_unit : c->and_blocks_per_unit;
-          for (uint32_t b0 = 0; b0 < lead_total; b0 += per) {
-            units[op].push_back(Unit{qseg_id, b0, std::min(lead_total, b0 + per), 0});
-            ++q_units;
-          }
-        }
+        qseg_op.push_back(op);
+        qseg_total.push_back(op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total);
+        ++n_qsegs_op[op];
         i = j;
       }
       dq[qi].k = q.k;
       dq[qi].op = (uint32_t)op;
+    }
+    // Work units. A unit is one CTA's share of a (query, segment). With few (query, segment) pairs in the
+    // batch every pair is cut into many units (latency); with many, units grow so that a CTA's local
+    // top-k threshold gets tight and few candidates reach k_final (throughput).
+    const uint32_t target_units = env_u32("TQ_TARGET_UNITS", 148u * 4u * 16u);
+    std::vector<uint32_t> q_units(nq, 0);
+    for (size_t s = 0; s < qsegs.size(); ++s) {
+      const int op = qseg_op[s];
+      const uint32_t total = qseg_total[s];
+      const uint32_t min_per = op == TQ_OP_TERM ? c->term_blocks_per_unit : (op == TQ_OP_AND ? c->and_blocks_per_unit : c->or_tiles_per_unit);
+      const uint32_t want_units = std::max<uint32_t>(1u, (target_units + n_qsegs_op[op] - 1) / n_qsegs_op[op]);
+      const uint32_t per = std::max<uint32_t>(min_per, (total + want_units - 1) / want_units);
+      for (uint32_t b0 = 0; b0 < total; b0 += per) {
+        units[op].push_back(Unit{(uint32_t)s, b0, std::min(total, b0 + per), 0});
+        ++q_units[qsegs[s].query];
+      }
+    }
+    for (size_t qi = 0; qi < nq; ++qi) {
       dq[qi].cand_base = (uint32_t)n_cands;
-      dq[qi].cand_cap = q_units * q.k;
-      n_cands += (size_t)q_units * q.k;
+      dq[qi].cand_cap = q_units[qi] * dq[qi].k;
+      n_cands += (size_t)q_units[qi] * dq[qi].k;
       if (n_cands > 0xFFFFFFF0ull) return fail(TQ_ERR_UNSUPPORTED, "batch too large: split it");
     }
     int rc = flush_builds(c, pending, &built);
@@ -587,7 +605,7 @@ int tq_batch_run(tq_batch* b) {
   TQ_CUDA(cudaEventRecord(b->ev_op[0], b->stream));
   if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
   TQ_CUDA(cudaEventRecord(b->ev_op[1], b->stream));
-  if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kTileDocs * sizeof(float), b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
+  if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));
   if (b->nq) { k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches; }

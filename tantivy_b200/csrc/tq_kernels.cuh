@@ -190,11 +190,14 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
   const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  BlockFetch f;
+  if (U.begin + warp < U.end) fetch_issue(L, U.begin + warp, lane, f);
   for (uint32_t r = U.begin; r < U.end; r += kWarps) {
     const uint32_t b = r + warp;
     if (b < U.end) {
       uint32_t doc[4], tf[4];
-      decode_block(L, b, s_stage[warp], lane, doc, tf);
+      fetch_decode(L, b, f, s_stage[warp], lane, doc, tf);
+      if (b + kWarps < U.end) fetch_issue(L, b + kWarps, lane, f);  // next round's block travels while this one is scored
       const unsigned long long theta = *T.theta;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -295,14 +298,51 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
 }
 
 // ---- union -------------------------------------------------------------------------------------------------
-// dynamic shared memory: kTileDocs f32 score slots.  A slot holding -0.0f has not been touched:
-// -0.0 + s == 0.0 + s bit for bit for every s except s == -0.0 (SumCombiner starts from 0.0).
+// Shared memory per CTA: kTileDocs f32 score slots (dynamic) + kTileDocs fieldnorm bytes.
+// A slot holding -0.0f has not been touched: -0.0 + s == 0.0 + s bit for bit for every s except
+// s == -0.0 (SumCombiner starts from 0.0, score_combiner.rs:39-57).
+struct OrShared {
+  uint32_t blo[2][32], bhi[2][32];  // per clause: block range overlapping the tile (double buffered)
+  uint32_t cur[32];                 // per clause: search cursor
+  uint32_t any[2];
+  uint32_t npass;
+};
+
+__device__ __forceinline__ void or_tile_ranges(const BatchParams& P, const QSeg& S, OrShared& sh, int buf, uint32_t tile,
+                                               uint32_t warp, uint32_t lane) {
+  const uint32_t lo = tile * kTileDocs;
+  const uint32_t hi = min(lo + kTileDocs, S.max_doc);
+  for (uint32_t t = warp; t < S.n_lists; t += kWarps) {
+    const QList ql = P.qlists[S.lists_base + t];
+    const uint32_t* last_doc = P.lists[ql.list_id].last_doc;
+    const uint32_t n_total = P.lists[ql.list_id].n_total;
+    uint32_t blo = 1, bhi = 0;
+    const uint32_t j_lo = first_block_ge(last_doc, sh.cur[t], n_total, lo, lane);
+    if (j_lo < n_total) {
+      // the last block that can hold a doc < hi is the first one whose last doc is >= hi-1
+      uint32_t j_hi = first_block_ge(last_doc, j_lo, n_total, hi - 1u, lane);
+      if (j_hi >= n_total) j_hi = n_total - 1u;
+      blo = j_lo; bhi = j_hi;
+    }
+    if (lane == 0) { sh.blo[buf][t] = blo; sh.bhi[buf][t] = bhi; sh.cur[t] = j_lo; if (blo <= bhi) sh.any[buf] = 1; }
+  }
+}
+
+// next (clause, block) of this warp at or after (t, b) in tile buffer `buf`; t == n_lists when none
+__device__ __forceinline__ void or_next_item(const OrShared& sh, int buf, uint32_t n_lists, uint32_t warp, uint32_t& t, uint32_t& b) {
+  while (t < n_lists) {
+    if (b <= sh.bhi[buf][t] && sh.blo[buf][t] <= sh.bhi[buf][t]) return;
+    ++t;
+    if (t < n_lists) b = sh.blo[buf][t] + warp;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t unit_base) {
-  extern __shared__ __align__(16) float s_acc[];
+  extern __shared__ __align__(16) float s_acc[];                  // [kTileDocs]
+  uint8_t* s_fn = reinterpret_cast<uint8_t*>(s_acc + kTileDocs);  // [kTileDocs]
   __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
   __shared__ CtaTopK s_top;
-  __shared__ uint32_t s_blo[32], s_bhi[32], s_cur[32];
-  __shared__ uint32_t s_any;
+  __shared__ OrShared sh;
   const Unit U = P.units[unit_base + blockIdx.x];
   const QSeg S = P.qsegs[U.qseg];
   const DQuery Q = P.queries[S.query];
@@ -310,77 +350,131 @@ __global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t u
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   uint32_t* stage = s_stage[warp];
   const float neg_zero = __uint_as_float(0x80000000u);
+  const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
   for (uint32_t i = threadIdx.x; i < kTileDocs; i += kThreads) s_acc[i] = neg_zero;
-  if (threadIdx.x < 32) s_cur[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; s_any = 0; }
+  if (threadIdx.x < 32) sh.cur[threadIdx.x] = 0;
+  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; sh.any[0] = sh.any[1] = 0; sh.npass = 0; }
   __syncthreads();
   const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  or_tile_ranges(P, S, sh, 0, U.begin, warp, lane);
+  __syncthreads();
   for (uint32_t tile = U.begin; tile < U.end; ++tile) {
+    const int buf = (int)((tile - U.begin) & 1u);
     const uint32_t lo = tile * kTileDocs;
     const uint32_t hi = min(lo + kTileDocs, S.max_doc);
-    // which blocks of every clause overlap [lo, hi)
-    for (uint32_t t = warp; t < S.n_lists; t += kWarps) {
-      const QList ql = P.qlists[S.lists_base + t];
-      uint32_t blo = 1, bhi = 0, cur = 0;
-      if (ql.list_id != kNoList) {
-        const uint32_t* last_doc = P.lists[ql.list_id].last_doc;
-        const uint32_t n_total = P.lists[ql.list_id].n_total;
-        const uint32_t j_lo = first_block_ge(last_doc, s_cur[t], n_total, lo, lane);
-        cur = j_lo;
-        if (j_lo < n_total) {
-          // the block after the last one starting below hi is the first whose predecessor ends >= hi-1
-          uint32_t j_hi = first_block_ge(last_doc, j_lo, n_total, hi - 1u, lane);
-          if (j_hi >= n_total) j_hi = n_total - 1u;
-          blo = j_lo; bhi = j_hi;
-        }
-      }
-      if (lane == 0) { s_blo[t] = blo; s_bhi[t] = bhi; s_cur[t] = cur; if (blo <= bhi) s_any = 1; }
-    }
-    __syncthreads();
-    const bool any = s_any != 0;
+    const bool any = sh.any[buf] != 0;
     if (any) {
-      for (uint32_t t = 0; t < S.n_lists; ++t) {
-        const uint32_t blo = s_blo[t], bhi = s_bhi[t];
-        if (blo <= bhi) {
-          const QList ql = P.qlists[S.lists_base + t];
-          const ListDesc L = P.lists[ql.list_id];
+      // fieldnorm bytes of the window: one coalesced 16-byte row per thread pair instead of a byte gather per posting
+      if (staged_fn) {
+        const uint4* src = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
+        uint4* dst = reinterpret_cast<uint4*>(s_fn);
+        for (uint32_t i = threadIdx.x; i < kTileDocs / 16; i += kThreads) dst[i] = __ldg(src + i);
+      }
+      // first work item of this warp, fetched before the barrier
+      uint32_t t = 0, b = sh.blo[buf][0] + warp;
+      or_next_item(sh, buf, S.n_lists, warp, t, b);
+      BlockFetch f;
+      QList ql;
+      ListDesc L;
+      if (t < S.n_lists) { ql = P.qlists[S.lists_base + t]; L = P.lists[ql.list_id]; fetch_issue(L, b, lane, f); }
+      __syncthreads();  // s_fn ready
+      for (uint32_t tt = 0; tt < S.n_lists; ++tt) {
+        while (t == tt) {
+          uint32_t doc[4], tf[4];
+          fetch_decode(L, b, f, stage, lane, doc, tf);
+          const float weight = ql.weight;
           const float* cache = P.caches + 256u * ql.cache_idx;
-          for (uint32_t b = blo + warp; b <= bhi; b += kWarps) {
-            uint32_t doc[4], tf[4];
-            decode_block(L, b, stage, lane, doc, tf);
+          const uint8_t* fn_global = L.fieldnorm;
+          // next item (same clause or a later one) starts travelling now
+          uint32_t nt = t, nb = b + kWarps;
+          or_next_item(sh, buf, S.n_lists, warp, nt, nb);
+          if (nt < S.n_lists) {
+            if (nt != t) { ql = P.qlists[S.lists_base + nt]; L = P.lists[ql.list_id]; }
+            fetch_issue(L, nb, lane, f);
+          }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (doc[i] >= lo && doc[i] < hi) {
-                const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
-                const uint32_t slot = doc[i] - lo;
-                s_acc[slot] = __fadd_rn(s_acc[slot], sc);
-              }
+          for (int i = 0; i < 4; ++i) {
+            if (doc[i] >= lo && doc[i] < hi) {
+              const uint32_t slot = doc[i] - lo;
+              const uint32_t id = staged_fn ? (uint32_t)s_fn[slot] : (fn_global ? (uint32_t)__ldg(fn_global + doc[i]) : 1u);
+              const float sc = bm25_score_id(weight, cache, id, tf[i]);
+              s_acc[slot] = __fadd_rn(s_acc[slot], sc);
             }
           }
+          t = nt; b = nb;
         }
         __syncthreads();  // clause order is the f32 summation order
       }
-      // harvest the window
-      for (uint32_t base = 0; base < kTileDocs; base += kThreads * 4) {
-        const uint32_t idx = base + threadIdx.x * 4;
-        float4 v = *reinterpret_cast<float4*>(s_acc + idx);
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        const unsigned long long theta = *T.theta;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const bool touched = __float_as_uint(vv[c]) != 0x80000000u;
-          const uint32_t d = lo + idx + c;
-          const unsigned long long key = make_key(vv[c], d);
-          bool pass = touched && key >= theta;
-          if (pass && S.alive) pass = is_alive(S.alive, d);
-          topk_push(T, pass, key, lane);
-        }
-        *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
-        topk_round_end(T, Q.k, &qs->theta);
-      }
     }
-    if (threadIdx.x == 0) s_any = 0;
-    __syncthreads();
+    // ranges of the next tile: the searches overlap the harvest below
+    if (tile + 1 < U.end) {
+      if (threadIdx.x == 0) sh.any[buf ^ 1] = 0;
+      __syncthreads();
+      or_tile_ranges(P, S, sh, buf ^ 1, tile + 1, warp, lane);
+    }
+    if (any) {
+      // harvest: count what passes, then push in one go when it fits.
+      // A float compare against the threshold score rejects nearly every slot (untouched slots hold
+      // -0.0, which is below any positive threshold); the exact key test runs only on the survivors.
+      const unsigned long long theta = *T.theta;
+      const float theta_f = threshold_score((uint32_t)(theta >> 32));
+      uint32_t passmask = 0;
+#pragma unroll
+      for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+        const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+        if (v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f) {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t d = lo + idx + c;
+            bool pass = vv[c] >= theta_f && __float_as_uint(vv[c]) != 0x80000000u && make_key(vv[c], d) >= theta;
+            if (pass && S.alive) pass = is_alive(S.alive, d);
+            passmask |= pass ? (1u << (j * 4 + c)) : 0u;
+          }
+        }
+      }
+      const uint32_t wsum = __reduce_add_sync(kFull, (uint32_t)__popc(passmask));
+      if (lane == 0 && wsum) atomicAdd(&sh.npass, wsum);
+      __syncthreads();
+      const uint32_t npass = sh.npass;
+      const bool fits = *T.count + npass <= kCap;
+      __syncthreads();
+      if (fits) {
+#pragma unroll
+        for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+          const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+          const uint32_t sub = (passmask >> (j * 4)) & 15u;
+          if (__ballot_sync(kFull, sub != 0)) {
+            const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) topk_push(T, (sub >> c) & 1u, make_key(vv[c], lo + idx + c), lane);
+          }
+          *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+        }
+        if (threadIdx.x == 0) sh.npass = 0;
+        topk_round_end(T, Q.k, &qs->theta);
+      } else {  // cold start: more survivors than the buffer holds; go in rounds with compaction between
+        if (threadIdx.x == 0) sh.npass = 0;
+        topk_round_end(T, Q.k, &qs->theta);  // leaves at most kCap - kRoundMargin keys
+        for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+          const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+          const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+          const unsigned long long th = *T.theta;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const unsigned long long key = make_key(vv[c], lo + idx + c);
+            topk_push(T, ((passmask >> (j * 4 + c)) & 1u) && key >= th, key, lane);
+          }
+          *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+          topk_round_end(T, Q.k, &qs->theta);
+        }
+      }
+    } else {
+      __syncthreads();
+    }
   }
   topk_flush(T, Q, qs, P.cands, S.segment_ord);
 }
@@ -412,26 +506,107 @@ __device__ void sort_pairs_desc(unsigned long long* a, uint32_t* b, unsigned n) 
   }
 }
 
+// Exact top-k of a query's candidates. Small sets are sorted directly; large ones go through a
+// 4-pass radix select on the score key (O(C)), then only the survivors and the boundary ties are sorted.
 __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
   __shared__ unsigned long long s_a[kCap];
   __shared__ uint32_t s_b[kCap];
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_need, s_n, s_ties;
   const uint32_t q = blockIdx.x;
   const DQuery Q = P.queries[q];
   const uint32_t C = min(P.qstate[q].cand_count, Q.cand_cap);
-  uint32_t have = 0, next = 0;
-  for (;;) {
-    const uint32_t take = min(C - next, kCap - have);
-    for (uint32_t i = threadIdx.x; i < take; i += blockDim.x) {
-      const Cand c = P.cands[Q.cand_base + next + i];
-      s_a[have + i] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
-      s_b[have + i] = ~c.doc;
+  const Cand* cands = P.cands + Q.cand_base;
+  uint32_t have = 0;
+  if (C <= kCap) {
+    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+      const Cand c = cands[i];
+      s_a[i] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
+      s_b[i] = ~c.doc;
     }
-    next += take;
-    const uint32_t n = have + take;
     __syncthreads();
-    sort_pairs_desc(s_a, s_b, n);
-    have = min(n, Q.k);
-    if (next >= C) break;
+    sort_pairs_desc(s_a, s_b, C);
+    have = min(C, Q.k);
+  } else {
+    // k-th largest score key (C > kCap >= k)
+    if (threadIdx.x == 0) { s_prefix = 0; s_need = Q.k; }
+    uint32_t mask = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+        const uint32_t key = cands[i].score_key;
+        if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t need = s_need, bsel = 0;
+        for (int bin = 255; bin >= 0; --bin) {
+          const uint32_t h = s_hist[bin];
+          if (h >= need) { bsel = (uint32_t)bin; s_ties = h; break; }
+          need -= h;
+        }
+        s_need = need;
+        s_prefix = prefix | (bsel << shift);
+      }
+      mask |= 0xFFu << shift;
+      __syncthreads();
+    }
+    const uint32_t kth = s_prefix;       // exactly the k-th largest score key
+    const uint32_t ties_total = s_ties;   // how many candidates carry exactly that key
+    const uint32_t above_total = Q.k - s_need;  // strictly better ones (< k)
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (above_total + ties_total <= kCap) {  // the usual case: one sweep, one sort
+      for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+        const Cand c = cands[i];
+        if (c.score_key >= kth) {
+          const uint32_t slot = atomicAdd(&s_n, 1u);
+          s_a[slot] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
+          s_b[slot] = ~c.doc;
+        }
+      }
+      __syncthreads();
+      const uint32_t n = s_n;
+      __syncthreads();
+      sort_pairs_desc(s_a, s_b, n);
+      have = min(n, Q.k);
+    } else {  // a flood of equal scores: keep the best (segment, doc) of the ties slab by slab
+      for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+        const Cand c = cands[i];
+        if (c.score_key > kth) {
+          const uint32_t slot = atomicAdd(&s_n, 1u);
+          s_a[slot] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
+          s_b[slot] = ~c.doc;
+        }
+      }
+      __syncthreads();
+      have = s_n;
+      uint32_t next = 0;
+      for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_n = have;
+        __syncthreads();
+        const uint32_t slab_end = min(C, next + (kCap - have));
+        for (uint32_t i = next + threadIdx.x; i < slab_end; i += blockDim.x) {
+          const Cand c = cands[i];
+          if (c.score_key == kth) {
+            const uint32_t slot = atomicAdd(&s_n, 1u);
+            s_a[slot] = ((unsigned long long)c.score_key << 32) | (unsigned long long)(0xFFFFFFFFu - c.segment_ord);
+            s_b[slot] = ~c.doc;
+          }
+        }
+        __syncthreads();
+        const uint32_t n = s_n;
+        __syncthreads();
+        sort_pairs_desc(s_a, s_b, n);
+        have = min(n, Q.k);
+        next = slab_end;
+        if (next >= C) break;
+      }
+    }
   }
   for (uint32_t i = threadIdx.x; i < have; i += blockDim.x) {
     const size_t o = (size_t)q * P.res_stride + i;
