@@ -101,6 +101,10 @@ typedef struct {
   float term_ms, and_ms, or_ms, final_ms; /* per-kernel device time (CUDA events on the launching stream) */
   uint64_t units_term, units_and, units_or; /* CTAs launched per kernel */
   uint64_t bytes_term, bytes_and, bytes_or; /* algorithmic bytes per kernel (same formula) */
+  /* cumulative since ctx creation: k_or doc-id windows by route: 0 skipped, 1 exhaustive, 2 entered the
+   * MaxScore route, 3 ..and had no promising doc, 4 essential-list overflow, 5 promising overflow,
+   * 6 promising docs scored exactly, 7 essential postings scored */
+  uint64_t or_windows[8];
 } tq_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

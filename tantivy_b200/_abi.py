@@ -83,6 +83,7 @@ class Stats(C.Structure):
         ("bytes_term", C.c_uint64),
         ("bytes_and", C.c_uint64),
         ("bytes_or", C.c_uint64),
+        ("or_windows", C.c_uint64 * 8),
     ]
 
 

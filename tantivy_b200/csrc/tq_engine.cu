@@ -129,6 +129,8 @@ struct tq_ctx {
   std::vector<tq_batch*> pool;
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
+  unsigned long long* d_counters = nullptr;
+  uint32_t or_prune = 1;
 };
 
 struct tq_batch {
@@ -179,7 +181,10 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->term_blocks_per_unit = env_u32("TQ_TERM_BLOCKS_PER_UNIT", 512);
   c->and_blocks_per_unit = env_u32("TQ_AND_BLOCKS_PER_UNIT", 128);
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
+  c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
+  if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
@@ -213,6 +218,7 @@ void tq_ctx_destroy(tq_ctx* c) {
   c->build_pin.release(); c->build_dev.release();
   if (c->build_stream) cudaStreamDestroy(c->build_stream);
   cudaFree(c->d_lists);
+  cudaFree(c->d_counters);
   delete c;
 }
 
@@ -221,6 +227,10 @@ int tq_get_stats(tq_ctx* c, tq_stats* out) {
   std::lock_guard<std::mutex> g(c->mu);
   *out = c->stats;
   out->lists_cached = c->n_lists;
+  cudaSetDevice(c->device);
+  unsigned long long h[8];
+  if (cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+    for (int i = 0; i < 8; ++i) out->or_windows[i] = h[i];
   return TQ_OK;
 }
 
@@ -579,6 +589,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   P.res_counts = reinterpret_cast<uint32_t*>(r + o_rc);
   P.res_stride = kmax;
   P.n_queries = (uint32_t)nq;
+  P.counters = c->d_counters;
+  P.or_prune = c->or_prune;
 
   TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
   TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));

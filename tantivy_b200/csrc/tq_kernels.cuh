@@ -301,11 +301,31 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
 // Shared memory per CTA: kTileDocs f32 score slots (dynamic) + kTileDocs fieldnorm bytes.
 // A slot holding -0.0f has not been touched: -0.0 + s == 0.0 + s bit for bit for every s except
 // s == -0.0 (SumCombiner starts from 0.0, score_combiner.rs:39-57).
+//
+// Two ways through a window of kTileDocs doc ids:
+//  * exhaustive: every clause's blocks are decoded and added in clause order, then the window is harvested;
+//  * MaxScore-pruned (once the threshold is high enough): clauses whose maximum scores add up to less
+//    than the threshold are "non-essential" (find_pivot_doc's prefix, block_wand_union.rs:16-43). Only the
+//    essential clauses are decoded; a doc is "promising" if its essential score plus the non-essential
+//    bound can reach the threshold, and only promising docs get their exact clause-ordered score.
+//    Every doc that is skipped provably scores below the threshold, so the result set is unchanged.
+constexpr uint32_t kTouchedCap = 2048;
+constexpr uint32_t kPromisingCap = 64;
+
 struct OrShared {
   uint32_t blo[2][32], bhi[2][32];  // per clause: block range overlapping the tile (double buffered)
   uint32_t cur[32];                 // per clause: search cursor
   uint32_t any[2];
   uint32_t npass;
+  float prefix[33];      // prefix[i] = sum of the i smallest clause maxima
+  uint8_t order[32];     // clause ordinals by ascending maximum score
+  uint32_t ne_mask;      // non-essential clauses for the current threshold
+  float ne_bound;        // upper bound of their joint contribution
+  uint32_t mode;         // 0 skip, 1 exhaustive, 2 pruned
+  uint32_t touched_n, p_n, overflow;
+  uint16_t touched[kTouchedCap];
+  uint16_t plist[kPromisingCap];
+  uint32_t pbits[kTileDocs / 32];
 };
 
 __device__ __forceinline__ void or_tile_ranges(const BatchParams& P, const QSeg& S, OrShared& sh, int buf, uint32_t tile,
@@ -328,16 +348,22 @@ __device__ __forceinline__ void or_tile_ranges(const BatchParams& P, const QSeg&
   }
 }
 
+// Blocks of clause t are dealt to the warps rotated by the clause ordinal: the single block of a rare
+// clause lands on warp (t mod 8), so the rare clauses of a window are fetched by different warps at the same
+// time instead of queueing on warp 0.
+__device__ __forceinline__ uint32_t or_first_block(const OrShared& sh, int buf, uint32_t t, uint32_t warp) {
+  return sh.blo[buf][t] + ((warp + kWarps - (t & (kWarps - 1))) & (kWarps - 1));
+}
 // next (clause, block) of this warp at or after (t, b) in tile buffer `buf`; t == n_lists when none
 __device__ __forceinline__ void or_next_item(const OrShared& sh, int buf, uint32_t n_lists, uint32_t warp, uint32_t& t, uint32_t& b) {
   while (t < n_lists) {
     if (b <= sh.bhi[buf][t] && sh.blo[buf][t] <= sh.bhi[buf][t]) return;
     ++t;
-    if (t < n_lists) b = sh.blo[buf][t] + warp;
+    if (t < n_lists) b = or_first_block(sh, buf, t, warp);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t unit_base) {
+__global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_t unit_base) {
   extern __shared__ __align__(16) float s_acc[];                  // [kTileDocs]
   uint8_t* s_fn = reinterpret_cast<uint8_t*>(s_acc + kTileDocs);  // [kTileDocs]
   __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
@@ -352,18 +378,178 @@ __global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t u
   const float neg_zero = __uint_as_float(0x80000000u);
   const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
   for (uint32_t i = threadIdx.x; i < kTileDocs; i += kThreads) s_acc[i] = neg_zero;
+  for (uint32_t i = threadIdx.x; i < kTileDocs / 32; i += kThreads) sh.pbits[i] = 0;
   if (threadIdx.x < 32) sh.cur[threadIdx.x] = 0;
-  if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; sh.any[0] = sh.any[1] = 0; sh.npass = 0; }
+  if (threadIdx.x == 0) {
+    s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32;
+    sh.any[0] = sh.any[1] = 0; sh.npass = 0; sh.touched_n = 0; sh.p_n = 0; sh.overflow = 0;
+    // clauses by ascending maximum score; a clause can add at most its weight (tf/(tf+norm) < 1, bm25.rs:170-175)
+    float mx[32];
+    for (uint32_t t = 0; t < S.n_lists; ++t) { mx[t] = fmaxf(P.qlists[S.lists_base + t].weight, 0.0f); sh.order[t] = (uint8_t)t; }
+    for (uint32_t i = 1; i < S.n_lists; ++i) {
+      const uint8_t o = sh.order[i];
+      uint32_t j = i;
+      while (j > 0 && mx[sh.order[j - 1]] > mx[o]) { sh.order[j] = sh.order[j - 1]; --j; }
+      sh.order[j] = o;
+    }
+    sh.prefix[0] = 0.0f;
+    for (uint32_t i = 0; i < S.n_lists; ++i) sh.prefix[i + 1] = sh.prefix[i] + mx[sh.order[i]];
+  }
   __syncthreads();
   const TopK T{s_top.keys, &s_top.count, &s_top.theta};
   or_tile_ranges(P, S, sh, 0, U.begin, warp, lane);
+  unsigned int theta_g_seen = 0;  // thread 0: query-wide threshold sampled one window ago
   __syncthreads();
   for (uint32_t tile = U.begin; tile < U.end; ++tile) {
     const int buf = (int)((tile - U.begin) & 1u);
     const uint32_t lo = tile * kTileDocs;
     const uint32_t hi = min(lo + kTileDocs, S.max_doc);
-    const bool any = sh.any[buf] != 0;
-    if (any) {
+    // ---- decide how to go through this window ------------------------------------------------------
+    if (threadIdx.x == 0) {
+      const unsigned long long g = (unsigned long long)theta_g_seen << 32;
+      if (g > s_top.theta) s_top.theta = g;
+      theta_g_seen = *(volatile unsigned int*)&qs->theta;  // consumed at the next window
+      const float theta_f = threshold_score((uint32_t)(s_top.theta >> 32));
+      uint32_t n_ne = 0, mask = 0;
+      while (n_ne < S.n_lists && sh.prefix[n_ne + 1] * 1.00001f < theta_f) { mask |= 1u << sh.order[n_ne]; ++n_ne; }
+      sh.ne_mask = mask;
+      sh.ne_bound = sh.prefix[n_ne] * 1.00001f;  // f32 sums of up to 32 terms differ by < 4e-6 relative
+      if (!P.or_prune && n_ne != S.n_lists) { n_ne = 0; sh.ne_mask = 0; sh.ne_bound = 0.0f; }
+      sh.mode = (!sh.any[buf] || n_ne == S.n_lists) ? 0u : (n_ne == 0 ? 1u : 2u);  // all non-essential: nothing here can enter the top-k
+      atomicAdd(&P.counters[sh.mode == 0 ? 0 : (sh.mode == 1 ? 1 : 2)], 1ull);
+    }
+    __syncthreads();
+    uint32_t mode = sh.mode;
+    const unsigned long long theta = *T.theta;
+    const float theta_f = threshold_score((uint32_t)(theta >> 32));
+
+    if (mode == 2) {
+      // ---- pruned, stage 1: essential clauses only, order-free estimate ---------------------------
+      const uint32_t ne_mask = sh.ne_mask;
+      uint32_t rr = 0;
+      for (uint32_t t = 0; t < S.n_lists; ++t) {
+        if ((ne_mask >> t) & 1u) continue;
+        const uint32_t blo = sh.blo[buf][t], bhi = sh.bhi[buf][t];
+        if (blo > bhi) continue;
+        const uint32_t nb = bhi - blo + 1u;
+        const QList ql = P.qlists[S.lists_base + t];
+        const ListDesc L = P.lists[ql.list_id];
+        const float* cache = P.caches + 256u * ql.cache_idx;
+        for (uint32_t b = blo + ((warp + kWarps - (rr & (kWarps - 1))) & (kWarps - 1)); b <= bhi; b += kWarps) {
+          uint32_t doc[4], tf[4];
+          decode_block(L, b, stage, lane, doc, tf);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (doc[i] >= lo && doc[i] < hi) {
+              const uint32_t slot = doc[i] - lo;
+              const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
+              const float old = atomicAdd(&s_acc[slot], sc);
+              if (__float_as_uint(old) == 0x80000000u) {
+                const uint32_t idx = atomicAdd(&sh.touched_n, 1u);
+                if (idx < kTouchedCap) sh.touched[idx] = (uint16_t)slot; else sh.overflow = 1;
+              }
+            }
+          }
+        }
+        rr += nb;
+      }
+      __syncthreads();
+      if (sh.overflow) {  // too many essential postings for the list: clean up and take the exhaustive route
+        if (threadIdx.x == 0) atomicAdd(&P.counters[4], 1ull);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < kTileDocs; i += kThreads) s_acc[i] = neg_zero;
+        if (threadIdx.x == 0) { sh.touched_n = 0; sh.overflow = 0; }
+        mode = 1;
+        __syncthreads();
+      } else {
+        // which touched docs could still reach the threshold once the non-essential clauses are added
+        const uint32_t n_touched = sh.touched_n;
+        const float ne_bound = sh.ne_bound;
+        for (uint32_t i = threadIdx.x; i < n_touched; i += kThreads) {
+          const uint32_t slot = sh.touched[i];
+          const float est = s_acc[slot];
+          s_acc[slot] = neg_zero;
+          if (est + fabsf(est) * 1e-5f + ne_bound >= theta_f) {
+            const uint32_t j = atomicAdd(&sh.p_n, 1u);
+            if (j < kPromisingCap) { sh.plist[j] = (uint16_t)slot; atomicOr(&sh.pbits[slot >> 5], 1u << (slot & 31u)); }
+            else sh.overflow = 1;
+          }
+        }
+        __syncthreads();
+        const uint32_t p_n = sh.p_n;
+        const bool too_many = sh.overflow != 0;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          atomicAdd(&P.counters[7], (unsigned long long)sh.touched_n);
+          atomicAdd(&P.counters[too_many ? 5 : (p_n == 0 ? 3 : 6)], too_many ? 1ull : (p_n == 0 ? 1ull : (unsigned long long)p_n));
+          sh.touched_n = 0; sh.overflow = 0;
+        }
+        if (too_many) {
+          for (uint32_t i = threadIdx.x; i < kTileDocs / 32; i += kThreads) sh.pbits[i] = 0;
+          if (threadIdx.x == 0) sh.p_n = 0;
+          mode = 1;
+          __syncthreads();
+        } else if (p_n == 0) {
+          mode = 0;
+        } else {
+          // ---- pruned, stage 2: exact clause-ordered score of the promising docs only -------------------
+          for (uint32_t tt = 0; tt < S.n_lists; ++tt) {
+            const uint32_t blo = sh.blo[buf][tt], bhi = sh.bhi[buf][tt];
+            if (blo <= bhi) {
+              const QList ql = P.qlists[S.lists_base + tt];
+              const ListDesc L = P.lists[ql.list_id];
+              const float* cache = P.caches + 256u * ql.cache_idx;
+              for (uint32_t b = blo + warp; b <= bhi; b += kWarps) {
+                // does this block's doc range hold a promising doc?
+                const uint32_t last = __ldg(L.last_doc + b);
+                const uint32_t prev = b ? __ldg(L.last_doc + b - 1) : 0u;
+                bool mine = false;
+                for (uint32_t i = lane; i < p_n; i += 32) {
+                  const uint32_t d = lo + sh.plist[i];
+                  mine |= (d <= last) && (b == 0 || d > prev);
+                }
+                if (__ballot_sync(kFull, mine) == 0) continue;
+                uint32_t doc[4], tf[4];
+                decode_block(L, b, stage, lane, doc, tf);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if (doc[i] >= lo && doc[i] < hi) {
+                    const uint32_t slot = doc[i] - lo;
+                    if ((sh.pbits[slot >> 5] >> (slot & 31u)) & 1u) {
+                      const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
+                      s_acc[slot] = __fadd_rn(s_acc[slot], sc);
+                    }
+                  }
+                }
+              }
+            }
+            __syncthreads();  // clause order is the f32 summation order
+          }
+          for (uint32_t base = 0; base < p_n; base += kThreads) {
+            const uint32_t i = base + threadIdx.x;
+            bool pass = false;
+            unsigned long long key = 0;
+            if (i < p_n) {
+              const uint32_t slot = sh.plist[i];
+              const float v = s_acc[slot];
+              s_acc[slot] = neg_zero;
+              sh.pbits[slot >> 5] = 0;  // every bit of that word belongs to a promising slot being reset
+              const uint32_t d = lo + slot;
+              key = make_key(v, d);
+              pass = __float_as_uint(v) != 0x80000000u && key >= theta;
+              if (pass && S.alive) pass = is_alive(S.alive, d);
+            }
+            topk_push(T, pass, key, lane);
+          }
+          if (threadIdx.x == 0) sh.p_n = 0;
+          topk_round_end(T, Q.k, &qs->theta);
+          mode = 3;  // done
+        }
+      }
+    }
+
+    if (mode == 1) {
+      // ---- exhaustive accumulate -----------------------------------------------------------------------
       // fieldnorm bytes of the window: one coalesced 16-byte row per thread pair instead of a byte gather per posting
       if (staged_fn) {
         const uint4* src = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
@@ -371,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t u
         for (uint32_t i = threadIdx.x; i < kTileDocs / 16; i += kThreads) dst[i] = __ldg(src + i);
       }
       // first work item of this warp, fetched before the barrier
-      uint32_t t = 0, b = sh.blo[buf][0] + warp;
+      uint32_t t = 0, b = or_first_block(sh, buf, 0, warp);
       or_next_item(sh, buf, S.n_lists, warp, t, b);
       BlockFetch f;
       QList ql;
@@ -406,18 +592,18 @@ __global__ void __launch_bounds__(kThreads) k_or(const BatchParams P, uint32_t u
         __syncthreads();  // clause order is the f32 summation order
       }
     }
-    // ranges of the next tile: the searches overlap the harvest below
+
+    // ranges of the next window: the searches overlap the harvest below
     if (tile + 1 < U.end) {
       if (threadIdx.x == 0) sh.any[buf ^ 1] = 0;
       __syncthreads();
       or_tile_ranges(P, S, sh, buf ^ 1, tile + 1, warp, lane);
     }
-    if (any) {
+
+    if (mode == 1) {
       // harvest: count what passes, then push in one go when it fits.
       // A float compare against the threshold score rejects nearly every slot (untouched slots hold
       // -0.0, which is below any positive threshold); the exact key test runs only on the survivors.
-      const unsigned long long theta = *T.theta;
-      const float theta_f = threshold_score((uint32_t)(theta >> 32));
       uint32_t passmask = 0;
 #pragma unroll
       for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {

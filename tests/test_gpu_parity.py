@@ -297,6 +297,24 @@ def test_synth_mixed_batch(ctx, synth):
     assert st["units"] > 0 and st["kernel_launches"] >= 3 and st["algorithmic_bytes"] > 0
 
 
+def test_synth_union_pruning_is_exact(ctx, synth):
+    """Unions of dense and rare terms with small k make k_or switch to its MaxScore-pruned route after
+    the first windows; the result must stay identical to the exhaustive oracle, hit for hit."""
+    ix, oi, base = synth
+    queries = []
+    for k in (1, 3, 10, 50):
+        for terms in ([0, 5], [0, 4, 5], [1, 0, 5, 3], [5, 4, 3, 2, 1, 0], [0, 1, 2], [2, 3, 4], [0, 3]):
+            queries.append(ix.query(TQ_OP_OR, terms, k, segment_base=base))
+    qb = QueryBatch(queries)
+    g = ctx.search_batch(qb)
+    c = oi.search_batch(qb, mode=0, n_threads=8)
+    assert_same(g, c, qb.nq)
+    # single-query batches use small units (many cold starts + threshold sharing between CTAs)
+    for q in queries[:8]:
+        qb1 = QueryBatch([q])
+        assert_same(ctx.search_batch(qb1), oi.search_batch(qb1, mode=0), 1)
+
+
 def test_synth_pruned_reference_path_agrees(ctx, synth):
     """The reference-faithful CPU path (Block-WAND + TopNHeap) returns the same hits as the GPU for
     term and AND queries (fixed summation order); for OR the reference's order-dependent f32 sum may
