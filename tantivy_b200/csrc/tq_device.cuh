@@ -26,14 +26,15 @@ constexpr int kThreads = 256;                 // 8 warps per CTA
 constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kCap = 2048;               // CTA candidate buffer (u64 keys), power of two
 constexpr uint32_t kRoundMargin = kWarps * 128;  // most keys one round of 8 warps can push
-constexpr uint32_t kStageWords = 264;         // per-warp staging: 64 vectors of packed data + pad
 constexpr uint32_t kTileDocs = 8192;          // OR: doc-id tile width held in shared memory
+constexpr uint32_t kTfRows = 16;              // term frequencies below this use the precomputed factor table
 
 // One posting list of one (segment, field, term), device resident.  Built once per term by
 // k_build_tables from the raw tantivy bytes and cached for the life of the segment (segments
 // are immutable, ARCHITECTURE.md "Searcher").
 struct ListDesc {
-  const uint8_t* blocks;      // first bit-packed block inside the segment's .idx body (unaligned)
+  const uint8_t* blocks;      // the list's bit-packed blocks, copied 16-byte aligned when the table is built
+                              // (posting lists start at arbitrary byte offsets inside the .idx body)
   const uint32_t* last_doc;   // [n_total] last doc id of every block; entry n_blocks = last tail doc
   const uint2* blk;           // [n_blocks + 1] .x byte offset from `blocks`, .y packed meta
   const uint32_t* tail_docs;  // [tail_n] the VInt tail, decoded at build time
@@ -84,7 +85,8 @@ struct Cand { uint32_t score_key, segment_ord, doc, pad; };
 
 struct BatchParams {
   const ListDesc* lists;
-  const float* caches;  // [n_caches][256]
+  const float* caches;  // [n_caches][256] tf-norm tables (bm25.rs:58-69)
+  const float* tf_tables;  // [n_caches][kTfRows][256]: tf / (tf + norm[id]) for tf < kTfRows
   const QList* qlists;
   const QSeg* qsegs;
   const Unit* units;
@@ -138,40 +140,36 @@ __device__ __forceinline__ uint32_t warp_min(uint32_t v) {
 
 // ---- K1: one warp decodes one 128-doc block ----------------------------------------------------
 // Split in two so that the HBM round trips of block b+1 overlap the scoring of block b:
-//   fetch_issue   block-table record -> packed words into registers (nothing is consumed yet)
-//   fetch_decode  realign, stage in shared memory, unpack 4 docs + 4 tfs per lane, prefix-sum
-// Lane L ends up with postings 4L..4L+3 of the block (ascending doc ids).
-constexpr int kRaw = 5;  // packed words held per lane: covers blocks of up to 159 words when prefetched
-
+//   fetch_issue   block-table record -> the two 16-byte vectors of doc bits and of tf bits this lane needs
+//   fetch_decode  funnel-shift the 4+4 fields out, add 1 to tf (v7), inclusive prefix sum of the doc gaps
+// BitPacker4x layout: value j sits in bit stream j&3 at bit (j>>2)*b; word w of stream c is the c-th word of
+// 16-byte vector w.  Lane L takes values 4L..4L+3 = row L of the four streams = ONE vector (plus the next one
+// when the field straddles a word).  Blocks are 16-byte aligned in the cached copy, so these are plain
+// LDG.128; a warp's 32 loads cover the block's b vectors contiguously.
 struct BlockFetch {
-  uint32_t raw[kRaw];
-  uint32_t meta;    // 0xFFFFFFFF marks the VInt tail pseudo block
-  uint32_t prev;    // last doc of the previous block
-  uint32_t off;     // byte offset of the block
+  uint4 dlo, dhi, tlo, thi;
+  uint32_t meta;  // 0xFFFFFFFF marks the VInt tail pseudo block
+  uint32_t prev;  // last doc of the previous block
 };
 
 __device__ __forceinline__ void fetch_issue(const ListDesc& L, uint32_t b, uint32_t lane, BlockFetch& f) {
   if (b >= L.n_blocks) { f.meta = 0xFFFFFFFFu; return; }
   const uint2 rec = __ldg(L.blk + b);
   f.meta = rec.y;
-  f.off = rec.x;
   f.prev = b ? __ldg(L.last_doc + b - 1) : 0u;
   const uint32_t db = rec.y & 31u, tb = (rec.y >> 8) & 63u;
-  const uint8_t* src = L.blocks + rec.x;
-  const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
-  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
-  const uint32_t need = 4u * (db + tb) + (mis ? 1u : 0u);  // aligned words that hold the block
-  if (need <= 32u * kRaw) {
-#pragma unroll
-    for (int j = 0; j < kRaw; ++j) {
-      const uint32_t i = lane + 32u * j;
-      f.raw[j] = i < need ? __ldg(src32 + i) : 0u;
-    }
+  const uint4* v = reinterpret_cast<const uint4*>(L.blocks + rec.x);
+  const uint32_t wd = (lane * db) >> 5;
+  f.dlo = __ldg(v + wd);
+  f.dhi = __ldg(v + wd + 1);  // may belong to the next field/block; masked out when not needed (copy is padded)
+  if (L.has_freq) {
+    const uint32_t wt = db + ((lane * tb) >> 5);
+    f.tlo = __ldg(v + wt);
+    f.thi = __ldg(v + wt + 1);
   }
 }
 
-// stage: per-warp shared memory, kStageWords u32, 16-byte aligned.
-__device__ __forceinline__ void fetch_decode(const ListDesc& L, uint32_t b, const BlockFetch& f, uint32_t* stage, uint32_t lane,
+__device__ __forceinline__ void fetch_decode(const ListDesc& L, uint32_t b, const BlockFetch& f, uint32_t lane,
                                              uint32_t (&doc)[4], uint32_t (&tf)[4]) {
   if (f.meta == 0xFFFFFFFFu) {  // VInt tail, decoded when the table was built
 #pragma unroll
@@ -185,52 +183,22 @@ __device__ __forceinline__ void fetch_decode(const ListDesc& L, uint32_t b, cons
   }
   const uint32_t meta = f.meta;
   const uint32_t db = meta & 31u, strict = (meta >> 6) & 1u, tb = (meta >> 8) & 63u;
-  const uint8_t* src = L.blocks + f.off;
-  const uint32_t mis = (uint32_t)((uintptr_t)src & 3u);
-  const uint32_t nwords = 4u * (db + tb);
-  const uint32_t need = nwords + (mis ? 1u : 0u);
-  __syncwarp();  // earlier readers of `stage` are done
-  // Posting blocks start at arbitrary byte offsets inside the .idx body: rows are fetched as aligned
-  // 128-byte lines and realigned with one funnel shift per word.
-  if (need <= 32u * kRaw) {
-    const uint32_t sh = mis * 8u;
-#pragma unroll
-    for (int j = 0; j < kRaw; ++j) {
-      const uint32_t i = lane + 32u * j;
-      const uint32_t up = __shfl_down_sync(kFull, f.raw[j], 1);
-      const uint32_t nxt = (j + 1 < kRaw) ? f.raw[(j + 1 < kRaw) ? j + 1 : 0] : 0u;
-      const uint32_t wrap = __shfl_sync(kFull, nxt, 0);
-      const uint32_t hi = lane == 31u ? wrap : up;
-      if (i < nwords) stage[i] = mis ? __funnelshift_r(f.raw[j], hi, sh) : f.raw[j];
-    }
-  } else {  // very wide block: fetched here, not prefetched
-    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src - mis);
-    const uint32_t sh = mis * 8u;
-    for (uint32_t i = lane; i < nwords; i += 32) {
-      const uint32_t w0 = __ldg(src32 + i), w1 = mis ? __ldg(src32 + i + 1) : 0u;
-      stage[i] = mis ? __funnelshift_r(w0, w1, sh) : w0;
-    }
-  }
-  __syncwarp();
-  const uint4* sv = reinterpret_cast<const uint4*>(stage);
   uint32_t d0, d1, d2, d3;
   {
-    const uint32_t bit = lane * db, w = bit >> 5, sh = bit & 31u;
+    const uint32_t sh = (lane * db) & 31u;
     const uint32_t mask = (1u << db) - 1u;  // db < 32 (skip.rs:16-22)
-    const uint4 lo = sv[w], hi = sv[w + 1];
-    d0 = __funnelshift_r(lo.x, hi.x, sh) & mask;
-    d1 = __funnelshift_r(lo.y, hi.y, sh) & mask;
-    d2 = __funnelshift_r(lo.z, hi.z, sh) & mask;
-    d3 = __funnelshift_r(lo.w, hi.w, sh) & mask;
+    d0 = __funnelshift_r(f.dlo.x, f.dhi.x, sh) & mask;
+    d1 = __funnelshift_r(f.dlo.y, f.dhi.y, sh) & mask;
+    d2 = __funnelshift_r(f.dlo.z, f.dhi.z, sh) & mask;
+    d3 = __funnelshift_r(f.dlo.w, f.dhi.w, sh) & mask;
   }
   if (L.has_freq) {
-    const uint32_t bit = lane * tb, w = db + (bit >> 5), sh = bit & 31u;
+    const uint32_t sh = (lane * tb) & 31u;
     const uint32_t mask = tb >= 32u ? 0xFFFFFFFFu : ((1u << tb) - 1u);
-    const uint4 lo = sv[w], hi = sv[w + 1];
-    tf[0] = (__funnelshift_r(lo.x, hi.x, sh) & mask) + strict;  // v7: tf-1 stored (mod.rs:134-150)
-    tf[1] = (__funnelshift_r(lo.y, hi.y, sh) & mask) + strict;
-    tf[2] = (__funnelshift_r(lo.z, hi.z, sh) & mask) + strict;
-    tf[3] = (__funnelshift_r(lo.w, hi.w, sh) & mask) + strict;
+    tf[0] = (__funnelshift_r(f.tlo.x, f.thi.x, sh) & mask) + strict;  // v7: tf-1 stored (mod.rs:134-150)
+    tf[1] = (__funnelshift_r(f.tlo.y, f.thi.y, sh) & mask) + strict;
+    tf[2] = (__funnelshift_r(f.tlo.z, f.thi.z, sh) & mask) + strict;
+    tf[3] = (__funnelshift_r(f.tlo.w, f.thi.w, sh) & mask) + strict;
   } else {
     tf[0] = tf[1] = tf[2] = tf[3] = 1u;
   }
@@ -242,25 +210,37 @@ __device__ __forceinline__ void fetch_decode(const ListDesc& L, uint32_t b, cons
   doc[0] = base + s0; doc[1] = base + s1; doc[2] = base + s2; doc[3] = base + s3;
 }
 
-__device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint32_t* stage, uint32_t lane,
-                                             uint32_t (&doc)[4], uint32_t (&tf)[4]) {
+__device__ __forceinline__ void decode_block(const ListDesc& L, uint32_t b, uint32_t lane, uint32_t (&doc)[4], uint32_t (&tf)[4]) {
   BlockFetch f;
   fetch_issue(L, b, lane, f);
-  fetch_decode(L, b, f, stage, lane, doc, tf);
+  fetch_decode(L, b, f, lane, doc, tf);
 }
 
 // ---- K2: BM25 of one posting (f32, reference operation order, no contraction) -------------------
-__device__ __forceinline__ float bm25_score(float weight, const float* __restrict__ cache,
-                                            const uint8_t* __restrict__ fieldnorm, uint32_t doc, uint32_t tf) {
-  const uint32_t id = fieldnorm ? (uint32_t)__ldg(fieldnorm + doc) : 1u;  // constant fieldnorm 1 -> id 1
-  const float norm = __ldg(cache + id);
-  const float t = __uint2float_rn(tf);
-  return __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, norm)));
+// score = weight * (tf / (tf + norm[fieldnorm_id]))  (bm25.rs:158-175).  The inner factor depends only on
+// (tf, fieldnorm id) for a given average fieldnorm, so it is tabulated per batch for tf < kTfRows with the
+// very same IEEE operations (k_build_tf_tables); larger tfs take the divide.
+struct Scorer {
+  float weight;
+  const float* cache;     // [256] norms
+  const float* tf_table;  // [kTfRows][256]
+};
+__device__ __forceinline__ float bm25_score_id(const Scorer& sc, uint32_t id, uint32_t tf) {
+  float fac;
+  if (tf < kTfRows) {
+    fac = __ldg(sc.tf_table + (tf << 8) + id);
+  } else {
+    const float t = __uint2float_rn(tf);
+    fac = __fdiv_rn(t, __fadd_rn(t, __ldg(sc.cache + id)));
+  }
+  return __fmul_rn(sc.weight, fac);
 }
-__device__ __forceinline__ float bm25_score_id(float weight, const float* __restrict__ cache, uint32_t id, uint32_t tf) {
-  const float norm = __ldg(cache + id);
-  const float t = __uint2float_rn(tf);
-  return __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, norm)));
+__device__ __forceinline__ float bm25_score(const Scorer& sc, const uint8_t* __restrict__ fieldnorm, uint32_t doc, uint32_t tf) {
+  const uint32_t id = fieldnorm ? (uint32_t)__ldg(fieldnorm + doc) : 1u;  // constant fieldnorm 1 -> id 1
+  return bm25_score_id(sc, id, tf);
+}
+__device__ __forceinline__ Scorer make_scorer(const BatchParams& P, const QList& ql) {
+  return Scorer{ql.weight, P.caches + 256u * ql.cache_idx, P.tf_tables + (size_t)(kTfRows * 256u) * ql.cache_idx};
 }
 
 // ---- first block whose last_doc >= target, searching [from, n) (SkipReader::seek) ---------------

@@ -301,12 +301,15 @@ int get_list(tq_ctx* c, const tq_term_seg& ts, std::vector<PendingBuild>& pendin
   const uint32_t n_blocks = ts.doc_freq / 128u, tail_n = ts.doc_freq % 128u;
   cudaError_t e;
   const size_t n_last = (size_t)n_blocks + 1, n_blk = (size_t)n_blocks + 1;
-  uint8_t* mem = c->arena.alloc(n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
+  const size_t len = (size_t)(ts.postings_end - ts.postings_start);
+  const size_t copy_bytes = ((len + 15) & ~(size_t)15) + 128;  // 16-byte aligned copy of the blocks + slack
+  uint8_t* mem = c->arena.alloc(copy_bytes + n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
   if (!mem) return fail(TQ_ERR_OOM, std::string("block table alloc: ") + cudaGetErrorString(e));
   PendingBuild pb;
   ListDesc& d = pb.desc;
   memset(&d, 0, sizeof(d));
   uint8_t* p = mem;
+  d.blocks = p; p += copy_bytes;  // filled by k_build_tables
   d.blk = reinterpret_cast<const uint2*>(p); p += n_blk * 8;
   d.last_doc = reinterpret_cast<const uint32_t*>(p); p += n_last * 4;
   d.tail_docs = reinterpret_cast<const uint32_t*>(p); p += (size_t)tail_n * 4;
@@ -536,6 +539,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
   const size_t o_caches = off; off = align(off + caches.size() * 4);
+  const size_t n_caches = caches.size() / 256;
+  const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
   const size_t n_units_total = units[0].size() + units[1].size() + units[2].size();
@@ -576,6 +581,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   BatchParams& P = b->params;
   P.lists = c->d_lists;
   P.caches = reinterpret_cast<const float*>(b->dev.p + o_caches);
+  P.tf_tables = reinterpret_cast<const float*>(b->dev.p + o_tftab);
   P.qlists = reinterpret_cast<const QList*>(b->dev.p + o_qlists);
   P.qsegs = reinterpret_cast<const QSeg*>(b->dev.p + o_qsegs);
   P.units = reinterpret_cast<const Unit*>(b->dev.p + o_units);
@@ -594,6 +600,11 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
 
   TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
   TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));
+  {
+    const unsigned n = (unsigned)(n_caches * kTfRows * 256);
+    k_build_tf_tables<<<(n + 255) / 256, 256, 0, b->stream>>>(P.caches, reinterpret_cast<float*>(b->dev.p + o_tftab), (uint32_t)n_caches);
+    TQ_CUDA(cudaGetLastError());
+  }
   b->stats.lists_built = built;
   b->stats.units = n_units_total;
   b->stats.h2d_bytes = b->desc_bytes;

@@ -132,22 +132,45 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
       }
       if (status == 0) last_doc[n_blocks] = tail_docs[tail_n - 1];
     }
-    L.blocks = blocks;
     L.has_freq = rec != 5u;
     L.build_status = status;
   }
+  // 16-byte aligned copy of the bit-packed blocks (L.blocks was pre-set by the host to an arena region of
+  // >= len + 64 bytes): posting lists start at arbitrary byte offsets inside the .idx body; the copy lets
+  // every lane fetch its vectors with plain LDG.128.
+  __syncthreads();
+  if (s_status == 0 && s_carry <= avail) {
+    const uint32_t total_words = s_carry / 4u + 16u;  // + 64 bytes of slack after the last block
+    const uint32_t mis = (uint32_t)((uintptr_t)blocks & 3u);
+    const uint32_t* src32 = reinterpret_cast<const uint32_t*>(blocks - mis);
+    uint32_t* dst32 = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(L.blocks));
+    const uint32_t sh = mis * 8u;
+    for (uint32_t i = tid; i < total_words; i += kThreads) {
+      const uint32_t w0 = src32[i], w1 = src32[i + 1];  // the segment body is padded by 64+ bytes on the device
+      dst32[i] = mis ? __funnelshift_r(w0, w1, sh) : w0;
+    }
+  }
+}
+
+// tf / (tf + norm[id]) for tf < kTfRows, one table per tf-norm cache of the batch; same IEEE operations and
+// order as Bm25Weight::tf_factor (bm25.rs:170-175).
+__global__ void k_build_tf_tables(const float* __restrict__ caches, float* __restrict__ tables, uint32_t n_caches) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_caches * kTfRows * 256u) return;
+  const uint32_t c = i / (kTfRows * 256u), tf = (i >> 8) % kTfRows, id = i & 255u;
+  const float t = __uint2float_rn(tf);
+  tables[i] = __fdiv_rn(t, __fadd_rn(t, caches[c * 256u + id]));
 }
 
 // ---- K1 stand-alone: whole-list decode (parity tests, decode micro-benchmark) ------------------
 __global__ void __launch_bounds__(kThreads) k_decode_list(const ListDesc* __restrict__ lists, uint32_t list_id,
                                                           uint32_t* __restrict__ out_docs, uint32_t* __restrict__ out_tfs) {
-  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
   const ListDesc L = lists[list_id];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t b = blockIdx.x * kWarps + warp;
   if (b >= L.n_total) return;
   uint32_t doc[4], tf[4];
-  decode_block(L, b, s_stage[warp], lane, doc, tf);
+  decode_block(L, b, lane, doc, tf);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint32_t j = b * 128u + lane * 4u + i;
@@ -165,7 +188,8 @@ __global__ void k_block_max(const ListDesc* __restrict__ lists, uint32_t list_id
   const uint32_t code = meta >> 24;
   const uint32_t tf = code == 255u ? 0xFFFFFFFFu : code;
   out_last_doc[b] = L.last_doc[b];
-  out_block_max[b] = bm25_score_id(weight, cache, (meta >> 16) & 255u, tf);
+  const float t = __uint2float_rn(tf);
+  out_block_max[b] = __fmul_rn(weight, __fdiv_rn(t, __fadd_rn(t, __ldg(cache + ((meta >> 16) & 255u)))));
 }
 
 // ---- shared CTA scaffolding ------------------------------------------------------------------------
@@ -177,7 +201,6 @@ struct CtaTopK {
 
 // ---- single term ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t unit_base) {
-  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
   __shared__ CtaTopK s_top;
   const Unit U = P.units[unit_base + blockIdx.x];
   const QSeg S = P.qsegs[U.qseg];
@@ -185,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
   QState* qs = P.qstate + S.query;
   const QList ql = P.qlists[S.lists_base];
   const ListDesc L = P.lists[ql.list_id];
-  const float* cache = P.caches + 256u * ql.cache_idx;
+  const Scorer sc = make_scorer(P, ql);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
@@ -196,17 +219,26 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
     const uint32_t b = r + warp;
     if (b < U.end) {
       uint32_t doc[4], tf[4];
-      fetch_decode(L, b, f, s_stage[warp], lane, doc, tf);
+      fetch_decode(L, b, f, lane, doc, tf);
       if (b + kWarps < U.end) fetch_issue(L, b + kWarps, lane, f);  // next round's block travels while this one is scored
       const unsigned long long theta = *T.theta;
+      const float theta_f = threshold_score((uint32_t)(theta >> 32));
+      bool pass[4];
+      float score[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const bool valid = doc[i] < S.max_doc;  // also rejects the kTerminated padding of the tail
-        const float score = valid ? bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]) : 0.0f;
-        const unsigned long long key = make_key(score, doc[i]);
-        bool pass = valid && key >= theta;
-        if (pass && S.alive) pass = is_alive(S.alive, doc[i]);
-        topk_push(T, pass, key, lane);
+        score[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+        pass[i] = valid && score[i] >= theta_f;  // cheap float test first; the exact key test only on survivors
+      }
+      if (__ballot_sync(kFull, pass[0] | pass[1] | pass[2] | pass[3])) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const unsigned long long key = make_key(score[i], doc[i]);
+          bool p = pass[i] && key >= theta;
+          if (p && S.alive) p = is_alive(S.alive, doc[i]);
+          topk_push(T, p, key, lane);
+        }
       }
     }
     topk_round_end(T, Q.k, &qs->theta);
@@ -216,7 +248,6 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
 
 // ---- intersection ----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t unit_base) {
-  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
   __shared__ uint32_t s_dec[kWarps][256];  // a decoded secondary block: 128 docs, 128 tfs
   __shared__ CtaTopK s_top;
   const Unit U = P.units[unit_base + blockIdx.x];
@@ -226,7 +257,6 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
   const QList ql0 = P.qlists[S.lists_base];
   const ListDesc L0 = P.lists[ql0.list_id];
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t* stage = s_stage[warp];
   uint32_t* dec = s_dec[warp];
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
@@ -235,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
     const uint32_t b = r + warp;
     if (b < U.end) {
       uint32_t doc[4], tf0[4];
-      decode_block(L0, b, stage, lane, doc, tf0);
+      decode_block(L0, b, lane, doc, tf0);
       uint32_t alive_m = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) alive_m |= (doc[i] < S.max_doc) ? (1u << i) : 0u;  // rejects tail padding
@@ -244,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
         if (__ballot_sync(kFull, alive_m != 0) == 0) break;
         const QList qls = P.qlists[S.lists_base + s];
         const ListDesc Ls = P.lists[qls.list_id];
-        const float* cache_s = P.caches + 256u * qls.cache_idx;
+        const Scorer sc_s = make_scorer(P, qls);
         uint32_t pending = alive_m;
         uint32_t stf[4] = {1u, 1u, 1u, 1u};
         uint32_t cur = 0;
@@ -257,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
           if (j >= Ls.n_total) { alive_m &= ~pending; pending = 0; break; }  // past the end of this list
           const uint32_t blk_last = __ldg(Ls.last_doc + j);
           uint32_t sd[4], st[4];
-          decode_block(Ls, j, stage, lane, sd, st);
+          decode_block(Ls, j, lane, sd, st);
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 4; ++i) { dec[lane * 4 + i] = sd[i]; dec[128 + lane * 4 + i] = st[i]; }
@@ -278,8 +308,8 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if ((alive_m >> i) & 1u) {
-            if (s == 1) total[i] = bm25_score(ql0.weight, P.caches + 256u * ql0.cache_idx, L0.fieldnorm, doc[i], tf0[i]);
-            total[i] = __fadd_rn(total[i], bm25_score(qls.weight, cache_s, Ls.fieldnorm, doc[i], stf[i]));
+            if (s == 1) total[i] = bm25_score(make_scorer(P, ql0), L0.fieldnorm, doc[i], tf0[i]);
+            total[i] = __fadd_rn(total[i], bm25_score(sc_s, Ls.fieldnorm, doc[i], stf[i]));
           }
         }
       }
@@ -366,7 +396,6 @@ __device__ __forceinline__ void or_next_item(const OrShared& sh, int buf, uint32
 __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_t unit_base) {
   extern __shared__ __align__(16) float s_acc[];                  // [kTileDocs]
   uint8_t* s_fn = reinterpret_cast<uint8_t*>(s_acc + kTileDocs);  // [kTileDocs]
-  __shared__ __align__(16) uint32_t s_stage[kWarps][kStageWords];
   __shared__ CtaTopK s_top;
   __shared__ OrShared sh;
   const Unit U = P.units[unit_base + blockIdx.x];
@@ -374,7 +403,6 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
   const DQuery Q = P.queries[S.query];
   QState* qs = P.qstate + S.query;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t* stage = s_stage[warp];
   const float neg_zero = __uint_as_float(0x80000000u);
   const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
   for (uint32_t i = threadIdx.x; i < kTileDocs; i += kThreads) s_acc[i] = neg_zero;
@@ -434,15 +462,15 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
         const uint32_t nb = bhi - blo + 1u;
         const QList ql = P.qlists[S.lists_base + t];
         const ListDesc L = P.lists[ql.list_id];
-        const float* cache = P.caches + 256u * ql.cache_idx;
+        const Scorer scr = make_scorer(P, ql);
         for (uint32_t b = blo + ((warp + kWarps - (rr & (kWarps - 1))) & (kWarps - 1)); b <= bhi; b += kWarps) {
           uint32_t doc[4], tf[4];
-          decode_block(L, b, stage, lane, doc, tf);
+          decode_block(L, b, lane, doc, tf);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             if (doc[i] >= lo && doc[i] < hi) {
               const uint32_t slot = doc[i] - lo;
-              const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
+              const float sc = bm25_score(scr, L.fieldnorm, doc[i], tf[i]);
               const float old = atomicAdd(&s_acc[slot], sc);
               if (__float_as_uint(old) == 0x80000000u) {
                 const uint32_t idx = atomicAdd(&sh.touched_n, 1u);
@@ -498,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
             if (blo <= bhi) {
               const QList ql = P.qlists[S.lists_base + tt];
               const ListDesc L = P.lists[ql.list_id];
-              const float* cache = P.caches + 256u * ql.cache_idx;
+              const Scorer scr = make_scorer(P, ql);
               for (uint32_t b = blo + warp; b <= bhi; b += kWarps) {
                 // does this block's doc range hold a promising doc?
                 const uint32_t last = __ldg(L.last_doc + b);
@@ -510,13 +538,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
                 }
                 if (__ballot_sync(kFull, mine) == 0) continue;
                 uint32_t doc[4], tf[4];
-                decode_block(L, b, stage, lane, doc, tf);
+                decode_block(L, b, lane, doc, tf);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   if (doc[i] >= lo && doc[i] < hi) {
                     const uint32_t slot = doc[i] - lo;
                     if ((sh.pbits[slot >> 5] >> (slot & 31u)) & 1u) {
-                      const float sc = bm25_score(ql.weight, cache, L.fieldnorm, doc[i], tf[i]);
+                      const float sc = bm25_score(scr, L.fieldnorm, doc[i], tf[i]);
                       s_acc[slot] = __fadd_rn(s_acc[slot], sc);
                     }
                   }
@@ -567,9 +595,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
       for (uint32_t tt = 0; tt < S.n_lists; ++tt) {
         while (t == tt) {
           uint32_t doc[4], tf[4];
-          fetch_decode(L, b, f, stage, lane, doc, tf);
-          const float weight = ql.weight;
-          const float* cache = P.caches + 256u * ql.cache_idx;
+          fetch_decode(L, b, f, lane, doc, tf);
+          const Scorer scr = make_scorer(P, ql);
           const uint8_t* fn_global = L.fieldnorm;
           // next item (same clause or a later one) starts travelling now
           uint32_t nt = t, nb = b + kWarps;
@@ -583,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
             if (doc[i] >= lo && doc[i] < hi) {
               const uint32_t slot = doc[i] - lo;
               const uint32_t id = staged_fn ? (uint32_t)s_fn[slot] : (fn_global ? (uint32_t)__ldg(fn_global + doc[i]) : 1u);
-              const float sc = bm25_score_id(weight, cache, id, tf[i]);
+              const float sc = bm25_score_id(scr, id, tf[i]);
               s_acc[slot] = __fadd_rn(s_acc[slot], sc);
             }
           }
