@@ -280,10 +280,17 @@ __device__ __forceinline__ uint32_t first_block_ge(const uint32_t* __restrict__ 
 }
 
 // ---- K6a: CTA-level exact top-k buffer ----------------------------------------------------------
+struct TopKScratch {  // shared memory used by the histogram compaction
+  unsigned int hist[256];
+  unsigned short holes[kCap / 2];
+  unsigned int kmin, kmax, hole_n, mover_n, keep, cut;
+};
 struct TopK {
   unsigned long long* keys;   // [kCap] shared
   unsigned int* count;        // shared
   unsigned long long* theta;  // shared: keys below it can no longer enter the top-k
+  TopKScratch* scratch;       // shared
+  unsigned long long* counters;  // global diagnostics (BatchParams::counters)
 };
 
 // All lanes of a warp call this together (pass may differ per lane).
@@ -328,10 +335,87 @@ __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_glob
   __syncthreads();
 }
 
+// Cheap compaction.  The CTA only has to keep a SUPERSET of its k best keys and a threshold that is a valid
+// lower bound of its k-th best score (k_final selects exactly).  One histogram of the score keys (256 bins
+// between the smallest and largest key in the buffer) finds the highest bin edge with >= k keys at or above
+// it; keys below that edge are dropped by moving the survivors of the upper part into the holes of the lower
+// part.  Falls back to the exact sort when the boundary bin is too crowded (ties) to make room.
+__device__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, unsigned int* theta_global) {
+  TopKScratch& sc = *t.scratch;
+  __syncthreads();
+  const unsigned n = *t.count;
+  if (n <= k) return;  // uniform
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) sc.hist[i] = 0;
+  if (threadIdx.x == 0) { sc.kmin = 0xFFFFFFFFu; sc.kmax = 0; sc.hole_n = 0; sc.mover_n = 0; }
+  __syncthreads();
+  unsigned lmin = 0xFFFFFFFFu, lmax = 0;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned sk = (unsigned)(t.keys[i] >> 32);
+    lmin = min(lmin, sk); lmax = max(lmax, sk);
+  }
+  lmin = __reduce_min_sync(kFull, lmin);
+  lmax = __reduce_max_sync(kFull, lmax);
+  if ((threadIdx.x & 31u) == 0) { atomicMin(&sc.kmin, lmin); atomicMax(&sc.kmax, lmax); }
+  __syncthreads();
+  const unsigned kmin = sc.kmin, span = sc.kmax - kmin;
+  const unsigned shift = span < 256u ? 0u : (unsigned)(32 - __clz(span)) - 8u;  // (key - kmin) >> shift in [0, 255]
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sc.hist[((unsigned)(t.keys[i] >> 32) - kmin) >> shift], 1u);
+  __syncthreads();
+  if (threadIdx.x < 32) {  // suffix sums over the 256 bins: 8 per lane
+    const unsigned lane = threadIdx.x;
+    unsigned loc[8], tot = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) { tot += sc.hist[lane * 8 + j]; loc[j] = tot; }  // inclusive suffix within the lane's bins
+    // inclusive suffix sum of the lane totals, then what lies above this lane's bins
+    unsigned run = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned v = __shfl_down_sync(kFull, run, o);
+      if (lane + o < 32) run += v;
+    }
+    const unsigned above = run - tot;
+    // the boundary bin: the highest bin b with (#keys in bins >= b) >= k
+    int cut = -1; unsigned keep = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; --j) {
+      const unsigned ge = above + loc[j];
+      if (cut < 0 && ge >= k) { cut = (int)(lane * 8 + j); keep = ge; }
+    }
+    const unsigned has = __ballot_sync(kFull, cut >= 0);
+    const int src = 31 - __clz(has);  // highest lane that found one (n > k guarantees at least one)
+    cut = __shfl_sync(kFull, cut, src);
+    keep = __shfl_sync(kFull, keep, src);
+    if (lane == 0) { sc.cut = (unsigned)cut; sc.keep = keep; }
+  }
+  __syncthreads();
+  const unsigned keep = sc.keep;
+  if (threadIdx.x == 0) { atomicAdd(&t.counters[3], 1ull); if (keep > keep_max || keep == n) atomicAdd(&t.counters[4], 1ull); }
+  if (keep > keep_max || keep == n) {  // crowded boundary bin (ties) or nothing to drop: exact route
+    topk_compact(t, k, theta_global);
+    return;
+  }
+  const unsigned edge = kmin + (sc.cut << shift);  // every survivor has score key >= edge, and there are >= k of them
+  for (unsigned i = threadIdx.x; i < keep; i += blockDim.x)
+    if ((unsigned)(t.keys[i] >> 32) < edge) sc.holes[atomicAdd(&sc.hole_n, 1u)] = (unsigned short)i;
+  __syncthreads();
+  for (unsigned i = keep + threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long key = t.keys[i];
+    if ((unsigned)(key >> 32) >= edge) t.keys[sc.holes[atomicAdd(&sc.mover_n, 1u)]] = key;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *t.count = keep;
+    const unsigned long long th = (unsigned long long)edge << 32;
+    if (th > *t.theta) *t.theta = th;
+    atomicMax(theta_global, edge);
+  }
+  __syncthreads();
+}
+
 // End of a round of the CTA: refresh the shared threshold from the query-wide one and make room.
 __device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsigned int* theta_global) {
   __syncthreads();
-  if (*t.count > kCap - kRoundMargin) topk_compact(t, k, theta_global);
+  if (*t.count > kCap - kRoundMargin) topk_compact_hist(t, k, kCap - kRoundMargin, theta_global);
   if (threadIdx.x == 0) {
     const unsigned long long g = (unsigned long long)(*(volatile unsigned int*)theta_global) << 32;
     if (g > *t.theta) *t.theta = g;
@@ -339,10 +423,10 @@ __device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsign
   __syncthreads();
 }
 
-// End of a unit: the CTA's survivors go to the query's candidate region (at most k of them).
+// End of a unit: the CTA's survivors go to the query's candidate region (at most 2k of them).
 __device__ void topk_flush(const TopK& t, const DQuery& q, QState* qs, Cand* cands, uint32_t segment_ord) {
   __syncthreads();
-  if (*t.count > q.k) topk_compact(t, q.k, &qs->theta);
+  if (*t.count > 2u * q.k) topk_compact_hist(t, q.k, min(2u * q.k, kCap / 2u), &qs->theta);
   __shared__ unsigned s_base;
   const unsigned n = *t.count;
   if (threadIdx.x == 0) s_base = n ? atomicAdd(&qs->cand_count, n) : 0u;

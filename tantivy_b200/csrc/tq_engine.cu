@@ -526,8 +526,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     }
     for (size_t qi = 0; qi < nq; ++qi) {
       dq[qi].cand_base = (uint32_t)n_cands;
-      dq[qi].cand_cap = q_units[qi] * dq[qi].k;
-      n_cands += (size_t)q_units[qi] * dq[qi].k;
+      dq[qi].cand_cap = q_units[qi] * 2u * dq[qi].k;  // a unit hands over at most 2k keys (topk_flush)
+      n_cands += (size_t)q_units[qi] * 2u * dq[qi].k;
       if (n_cands > 0xFFFFFFF0ull) return fail(TQ_ERR_UNSUPPORTED, "batch too large: split it");
     }
     int rc = flush_builds(c, pending, &built);

@@ -197,6 +197,7 @@ struct CtaTopK {
   unsigned long long keys[kCap];
   unsigned int count;
   unsigned long long theta;
+  TopKScratch scratch;
 };
 
 // ---- single term ---------------------------------------------------------------------------------------
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
   BlockFetch f;
   if (U.begin + warp < U.end) fetch_issue(L, U.begin + warp, lane, f);
   for (uint32_t r = U.begin; r < U.end; r += kWarps) {
@@ -260,7 +261,7 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
   uint32_t* dec = s_dec[warp];
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
   for (uint32_t r = U.begin; r < U.end; r += kWarps) {
     const uint32_t b = r + warp;
     if (b < U.end) {
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
     for (uint32_t i = 0; i < S.n_lists; ++i) sh.prefix[i + 1] = sh.prefix[i] + mx[sh.order[i]];
   }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
   or_tile_ranges(P, S, sh, 0, U.begin, warp, lane);
   unsigned int theta_g_seen = 0;  // thread 0: query-wide threshold sampled one window ago
   __syncthreads();
