@@ -37,6 +37,8 @@ struct ListDesc {
                               // (posting lists start at arbitrary byte offsets inside the .idx body)
   const uint32_t* last_doc;   // [n_total] last doc id of every block; entry n_blocks = last tail doc
   const uint2* blk;           // [n_blocks + 1] .x byte offset from `blocks`, .y packed meta
+  const uint4* tab4;          // [n_total] {last_doc, byte offset, meta, last doc of the previous block (0xFFFFFFFF: none)}
+                              // one 16-byte record per block so that a 32-wide probe yields position AND record
   const uint32_t* tail_docs;  // [tail_n] the VInt tail, decoded at build time
   const uint32_t* tail_tfs;   // [tail_n]
   const uint8_t* fieldnorm;   // the segment's fieldnorm ids for this field; null => constant id 1

@@ -130,7 +130,7 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;
-  uint32_t or_prune = 1;
+  uint32_t or_prune = 1, or_strip = 1;
 };
 
 struct tq_batch {
@@ -145,8 +145,9 @@ struct tq_batch {
   BatchParams params{};
   size_t desc_bytes = 0;
   uint32_t nq = 0, kmax = 0;
-  uint32_t n_units[3] = {0, 0, 0};
-  uint32_t unit_base[3] = {0, 0, 0};
+  uint32_t n_units[4] = {0, 0, 0, 0};    // term, and, or (window kernel), or (strip kernel)
+  uint32_t unit_base[4] = {0, 0, 0, 0};
+  uint32_t strip_cached_max = 0;
   size_t qstate_off = 0, cands_off = 0, res_off = 0, res_bytes = 0, n_cands = 0;
   tq_stats stats{};
   bool ran = false;
@@ -181,12 +182,14 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->term_blocks_per_unit = env_u32("TQ_TERM_BLOCKS_PER_UNIT", 512);
   c->and_blocks_per_unit = env_u32("TQ_AND_BLOCKS_PER_UNIT", 128);
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
+  c->or_strip = env_u32("TQ_OR_STRIP", 1);
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem_bytes(kMaxCached));
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
   *out = c;
   return TQ_OK;
@@ -303,13 +306,14 @@ int get_list(tq_ctx* c, const tq_term_seg& ts, std::vector<PendingBuild>& pendin
   const size_t n_last = (size_t)n_blocks + 1, n_blk = (size_t)n_blocks + 1;
   const size_t len = (size_t)(ts.postings_end - ts.postings_start);
   const size_t copy_bytes = ((len + 15) & ~(size_t)15) + 128;  // 16-byte aligned copy of the blocks + slack
-  uint8_t* mem = c->arena.alloc(copy_bytes + n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
+  uint8_t* mem = c->arena.alloc(copy_bytes + n_last * 16 + n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
   if (!mem) return fail(TQ_ERR_OOM, std::string("block table alloc: ") + cudaGetErrorString(e));
   PendingBuild pb;
   ListDesc& d = pb.desc;
   memset(&d, 0, sizeof(d));
   uint8_t* p = mem;
   d.blocks = p; p += copy_bytes;  // filled by k_build_tables
+  d.tab4 = reinterpret_cast<const uint4*>(p); p += n_last * 16;
   d.blk = reinterpret_cast<const uint2*>(p); p += n_blk * 8;
   d.last_doc = reinterpret_cast<const uint32_t*>(p); p += n_last * 4;
   d.tail_docs = reinterpret_cast<const uint32_t*>(p); p += (size_t)tail_n * 4;
@@ -406,7 +410,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
-  std::vector<Unit> units[3];
+  std::vector<Unit> units[4];
   std::vector<DQuery> dq(nq);
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
@@ -416,7 +420,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   size_t n_cands = 0;
   std::vector<int> qseg_op;
   std::vector<uint32_t> qseg_total;
-  uint32_t n_qsegs_op[3] = {0, 0, 0};
+  uint32_t n_qsegs_op[4] = {0, 0, 0, 0};
+  uint32_t strip_cached_max = 0;
   {
     std::lock_guard<std::mutex> g(c->mu);
     std::vector<const tq_term_seg*> order;
@@ -496,13 +501,25 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         qs.fieldnorm = uniform_fn ? fn0 : nullptr;
         if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
           std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
+        int unit_class = op;
+        if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
+          // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
+          uint32_t n_thin = 0;
+          for (auto& h : here) if ((uint64_t)h.first * (kWin / 128u) < qs.max_doc) ++n_thin;
+          if (n_thin <= kMaxCached) {
+            uint32_t slot = 0;
+            for (auto& h : here) h.second.pad = ((uint64_t)h.first * (kWin / 128u) < qs.max_doc) ? (1u | (slot++ << 1)) : 0u;
+            strip_cached_max = std::max(strip_cached_max, n_thin);
+            unit_class = 3;
+          }
+        }
         for (auto& h : here) qlists.push_back(h.second);
         qs.n_lists = (uint32_t)here.size();
         lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
         qsegs.push_back(qs);
-        qseg_op.push_back(op);
-        qseg_total.push_back(op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total);
-        ++n_qsegs_op[op];
+        qseg_op.push_back(unit_class);
+        qseg_total.push_back(unit_class == 3 ? (qs.max_doc + kWin - 1) / kWin : (op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total));
+        ++n_qsegs_op[unit_class];
         i = j;
       }
       dq[qi].k = q.k;
@@ -512,22 +529,23 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     // batch every pair is cut into many units (latency); with many, units grow so that a CTA's local
     // top-k threshold gets tight and few candidates reach k_final (throughput).
     const uint32_t target_units = env_u32("TQ_TARGET_UNITS", 148u * 4u * 16u);
-    std::vector<uint32_t> q_units(nq, 0);
+    std::vector<size_t> q_cands(nq, 0);
     for (size_t s = 0; s < qsegs.size(); ++s) {
       const int op = qseg_op[s];
       const uint32_t total = qseg_total[s];
-      const uint32_t min_per = op == TQ_OP_TERM ? c->term_blocks_per_unit : (op == TQ_OP_AND ? c->and_blocks_per_unit : c->or_tiles_per_unit);
+      const uint32_t min_per = op == TQ_OP_TERM ? c->term_blocks_per_unit : (op == TQ_OP_AND ? c->and_blocks_per_unit : (op == 3 ? kStripWarps * 64u : c->or_tiles_per_unit));
       const uint32_t want_units = std::max<uint32_t>(1u, (target_units + n_qsegs_op[op] - 1) / n_qsegs_op[op]);
       const uint32_t per = std::max<uint32_t>(min_per, (total + want_units - 1) / want_units);
+      const uint32_t k = dq[qsegs[s].query].k;
       for (uint32_t b0 = 0; b0 < total; b0 += per) {
         units[op].push_back(Unit{(uint32_t)s, b0, std::min(total, b0 + per), 0});
-        ++q_units[qsegs[s].query];
+        q_cands[qsegs[s].query] += op == 3 ? (size_t)kStripWarps * k : 2u * (size_t)k;  // what one unit may hand over
       }
     }
     for (size_t qi = 0; qi < nq; ++qi) {
       dq[qi].cand_base = (uint32_t)n_cands;
-      dq[qi].cand_cap = q_units[qi] * 2u * dq[qi].k;  // a unit hands over at most 2k keys (topk_flush)
-      n_cands += (size_t)q_units[qi] * 2u * dq[qi].k;
+      dq[qi].cand_cap = (uint32_t)q_cands[qi];
+      n_cands += q_cands[qi];
       if (n_cands > 0xFFFFFFF0ull) return fail(TQ_ERR_UNSUPPORTED, "batch too large: split it");
     }
     int rc = flush_builds(c, pending, &built);
@@ -543,7 +561,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
-  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size();
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size();
+  b->strip_cached_max = strip_cached_max;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
   const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
   b->desc_bytes = off;
@@ -555,7 +574,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   {
     Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
     uint32_t base = 0;
-    for (int op = 0; op < 3; ++op) {
+    for (int op = 0; op < 4; ++op) {
       b->unit_base[op] = base;
       b->n_units[op] = (uint32_t)units[op].size();
       if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
@@ -610,7 +629,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
-  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size();
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
@@ -629,6 +648,7 @@ int tq_batch_run(tq_batch* b) {
   if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
   TQ_CUDA(cudaEventRecord(b->ev_op[1], b->stream));
   if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
+  if (b->n_units[3]) { k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches; }
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));
   if (b->nq) { k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches; }

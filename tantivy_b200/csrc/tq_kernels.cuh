@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
   ListDesc& L = lists[J.list_id];
   uint32_t* last_doc = const_cast<uint32_t*>(L.last_doc);
   uint2* blk = const_cast<uint2*>(L.blk);
+  uint4* tab4 = const_cast<uint4*>(L.tab4);
   uint32_t* tail_docs = const_cast<uint32_t*>(L.tail_docs);
   uint32_t* tail_tfs = const_cast<uint32_t*>(L.tail_tfs);
   const uint32_t n_blocks = J.doc_freq / 128u, tail_n = J.doc_freq % 128u;
@@ -87,7 +88,12 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) woff += (w < (int)warp) ? s_wsum[w] : 0u;
       const uint32_t excl = s_carry + woff + incl - size;
-      if (i < n_blocks) { last_doc[i] = last; blk[i] = make_uint2(excl, meta); }
+      if (i < n_blocks) {
+        last_doc[i] = last;
+        blk[i] = make_uint2(excl, meta);
+        const uint32_t prev_last = i ? load_u32_unaligned(skip + (size_t)(i - 1) * rec) : 0xFFFFFFFFu;
+        tab4[i] = make_uint4(last, excl, meta, prev_last);
+      }
       __syncthreads();
       if (tid == kThreads - 1) s_carry = excl + size;
       __syncthreads();
@@ -130,7 +136,11 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
         }
         tail_tfs[i] = v;
       }
-      if (status == 0) last_doc[n_blocks] = tail_docs[tail_n - 1];
+      if (status == 0) {
+        last_doc[n_blocks] = tail_docs[tail_n - 1];
+        const uint32_t prev_last = n_blocks ? load_u32_unaligned(skip + (size_t)(n_blocks - 1) * rec) : 0xFFFFFFFFu;
+        tab4[n_blocks] = make_uint4(tail_docs[tail_n - 1], total, 0xFFFFFFFFu, prev_last);
+      }
     }
     L.has_freq = rec != 5u;
     L.build_status = status;
@@ -691,6 +701,317 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
     }
   }
   topk_flush(T, Q, qs, P.cands, S.segment_ord);
+}
+
+// ---- union, strip form ----------------------------------------------------------------------------------------
+// The same result as k_or, organised for latency tolerance: NO block-wide barrier in the loop.  Every warp owns a
+// contiguous strip of doc ids and walks it in windows of kWin docs with private score slots, private fieldnorm
+// bytes, a private candidate buffer and its own threshold (plus the query-wide one).  Clause order inside a warp
+// is program order, so the f32 sum is still taken clause by clause.
+//  * thick clauses (>= 1 block per window on average) are decoded window by window: one 32-wide probe of the
+//    16-byte block records gives position and record, the packed vectors follow (2 dependent loads);
+//  * thinner clauses keep their current block DECODED AND SCORED in shared memory (docs + scores); a window only
+//    looks at it when the block's next unread doc falls inside the window, so a block is decoded once per strip.
+// Eligible when k <= kStripMaxK, <= kStripMaxLists clauses and <= kMaxCached thin clauses; otherwise k_or.
+constexpr uint32_t kWin = 1024;
+constexpr uint32_t kWBuf = 256;
+constexpr uint32_t kMaxCached = 6;
+constexpr uint32_t kStripWarps = 4;
+constexpr uint32_t kStripThreads = kStripWarps * 32;
+constexpr uint32_t kStripMaxLists = 8;
+constexpr uint32_t kStripMaxK = 128;
+constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
+
+struct StripWarpFixed {  // per warp, dynamic shared memory; followed by n_cached x StripCache
+  float acc[kWin];
+  unsigned long long keys[kWBuf];
+  uint8_t fn[kWin];
+  uint32_t cur[kStripMaxLists];       // thick: first block that can still matter; thin: block held in the cache
+  uint32_t next_doc[kStripMaxLists];  // thin: smallest cached doc not applied yet (kNoDoc: clause exhausted)
+};
+struct StripCache {
+  uint32_t doc[128];
+  float score[128];
+};
+__host__ __device__ constexpr size_t strip_smem_bytes(uint32_t n_cached) {
+  return kStripWarps * (sizeof(StripWarpFixed) + (size_t)n_cached * sizeof(StripCache));
+}
+
+__device__ __forceinline__ void fetch_issue_rec(const ListDesc& L, const uint4 rec, uint32_t lane, BlockFetch& f) {
+  f.meta = rec.z;
+  if (rec.z == 0xFFFFFFFFu) return;  // VInt tail
+  f.prev = rec.w == 0xFFFFFFFFu ? 0u : rec.w;
+  const uint32_t db = rec.z & 31u, tb = (rec.z >> 8) & 63u;
+  const uint4* v = reinterpret_cast<const uint4*>(L.blocks + rec.y);
+  const uint32_t wd = (lane * db) >> 5;
+  f.dlo = __ldg(v + wd);
+  f.dhi = __ldg(v + wd + 1);
+  if (L.has_freq) {
+    const uint32_t wt = db + ((lane * tb) >> 5);
+    f.tlo = __ldg(v + wt);
+    f.thi = __ldg(v + wt + 1);
+  }
+}
+
+// warp-level: sort the candidate buffer (descending) and keep the best k
+__device__ __forceinline__ void strip_compact(unsigned long long* keys, uint32_t& cnt, uint32_t k, unsigned long long& theta,
+                                              unsigned int* theta_global, uint32_t lane) {
+  for (uint32_t i = cnt + lane; i < kWBuf; i += 32) keys[i] = 0ull;
+  __syncwarp();
+  for (uint32_t kk = 2; kk <= kWBuf; kk <<= 1) {
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      for (uint32_t p = lane; p < kWBuf / 2; p += 32) {
+        const uint32_t i = ((p & ~(j - 1u)) << 1) | (p & (j - 1u));
+        const uint32_t ixj = i | j;
+        const unsigned long long a = keys[i], b = keys[ixj];
+        const bool desc = (i & kk) == 0;
+        if (desc ? (a < b) : (a > b)) { keys[i] = b; keys[ixj] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  if (cnt > k) {
+    cnt = k;
+    const unsigned long long kth = keys[k - 1];
+    if (kth > theta) theta = kth;
+    if (lane == 0) atomicMax(theta_global, (unsigned)(kth >> 32));
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P, uint32_t unit_base, uint32_t n_cached_max) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  __shared__ ListDesc s_list[kStripMaxLists];
+  __shared__ QList s_ql[kStripMaxLists];
+  const Unit U = P.units[unit_base + blockIdx.x];
+  const QSeg S = P.qsegs[U.qseg];
+  const DQuery Q = P.queries[S.query];
+  QState* qs = P.qstate + S.query;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (threadIdx.x < S.n_lists) {
+    s_ql[threadIdx.x] = P.qlists[S.lists_base + threadIdx.x];
+    s_list[threadIdx.x] = P.lists[s_ql[threadIdx.x].list_id];
+  }
+  __syncthreads();  // the only block-wide barrier
+  const size_t per_warp = sizeof(StripWarpFixed) + (size_t)n_cached_max * sizeof(StripCache);
+  StripWarpFixed& W = *reinterpret_cast<StripWarpFixed*>(s_dyn + warp * per_warp);
+  StripCache* C = reinterpret_cast<StripCache*>(s_dyn + warp * per_warp + sizeof(StripWarpFixed));
+  const float neg_zero = __uint_as_float(0x80000000u);
+  // this warp's windows
+  const uint32_t n_win = U.end - U.begin;
+  const uint32_t w_begin = U.begin + (uint32_t)(((unsigned long long)n_win * warp) / kStripWarps);
+  const uint32_t w_end = U.begin + (uint32_t)(((unsigned long long)n_win * (warp + 1)) / kStripWarps);
+  for (uint32_t i = lane; i < kWin; i += 32) W.acc[i] = neg_zero;
+  const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
+  bool any_thick = false;
+  uint32_t cnt = 0;
+  unsigned long long theta = (unsigned long long)(*(volatile unsigned int*)&qs->theta) << 32;
+  if (w_begin < w_end) {
+    // ---- strip start: position every clause -------------------------------------------------------------
+    const uint32_t lo0 = w_begin * kWin;
+    for (uint32_t t = 0; t < S.n_lists; ++t) {
+      const ListDesc& L = s_list[t];
+      const bool thin = (s_ql[t].pad & 1u) != 0;
+      const uint32_t j = first_block_ge(L.last_doc, 0, L.n_total, lo0, lane);
+      if (!thin) {
+        any_thick = true;
+        if (lane == 0) { W.cur[t] = j; W.next_doc[t] = 0; }
+      } else {
+        uint32_t nd = kNoDoc;
+        if (j < L.n_total) {
+          StripCache& cc = C[s_ql[t].pad >> 1];
+          const Scorer sc = make_scorer(P, s_ql[t]);
+          uint32_t doc[4], tf[4];
+          decode_block(L, j, lane, doc, tf);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool valid = doc[i] < S.max_doc;
+            cc.doc[lane * 4 + i] = valid ? doc[i] : kNoDoc;
+            cc.score[lane * 4 + i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+            if (valid && doc[i] >= lo0) nd = min(nd, doc[i]);
+          }
+          nd = warp_min(nd);
+        }
+        if (lane == 0) { W.cur[t] = j; W.next_doc[t] = nd; }
+      }
+    }
+    __syncwarp();
+    // ---- the windows ---------------------------------------------------------------------------------------
+    uint32_t since_refresh = 0;
+    for (uint32_t w = w_begin; w < w_end; ++w) {
+      if (!any_thick) {  // only thin clauses: jump to the window of the next unread doc
+        uint32_t nd = lane < S.n_lists ? W.next_doc[lane] : kNoDoc;
+        nd = warp_min(nd);
+        if (nd == kNoDoc) break;
+        const uint32_t wj = nd / kWin;
+        if (wj >= w_end) break;
+        if (wj > w) w = wj;
+      }
+      const uint32_t lo = w * kWin;
+      const uint32_t hi = min(lo + kWin, S.max_doc);
+      if (++since_refresh == 16u) {  // pick up the query-wide threshold now and then
+        since_refresh = 0;
+        unsigned int g = lane == 0 ? *(volatile unsigned int*)&qs->theta : 0u;
+        g = __shfl_sync(kFull, g, 0);
+        const unsigned long long gt = (unsigned long long)g << 32;
+        if (gt > theta) theta = gt;
+      }
+      if (staged_fn && any_thick) {
+        const uint4* src = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
+        uint4* dst = reinterpret_cast<uint4*>(W.fn);
+        dst[lane] = __ldg(src + lane);
+        dst[lane + 32] = __ldg(src + lane + 32);
+        __syncwarp();
+      }
+      uint32_t touched = 0;  // which 128-slot groups of the window received a score
+      for (uint32_t t = 0; t < S.n_lists; ++t) {
+        const ListDesc& L = s_list[t];
+        const bool thin = (s_ql[t].pad & 1u) != 0;
+        if (!thin) {
+          // ---- thick clause: decode the blocks that overlap [lo, hi) ---------------------------------------
+          uint32_t cur = W.cur[t];
+          if (cur >= L.n_total) continue;
+          uint4 r;
+          unsigned m;
+          for (;;) {
+            const uint32_t idx = cur + lane;
+            r = idx < L.n_total ? __ldg(L.tab4 + idx) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+            m = __ballot_sync(kFull, r.x >= lo);
+            if (m) break;
+            cur += 32;
+          }
+          uint32_t src = (uint32_t)__ffs(m) - 1u;
+          uint32_t j = cur + src;
+          if (lane == 0) W.cur[t] = j;
+          if (j >= L.n_total) continue;
+          const Scorer sc = make_scorer(P, s_ql[t]);
+          uint4 rec;
+          rec.x = __shfl_sync(kFull, r.x, src); rec.y = __shfl_sync(kFull, r.y, src);
+          rec.z = __shfl_sync(kFull, r.z, src); rec.w = __shfl_sync(kFull, r.w, src);
+          if (rec.w != 0xFFFFFFFFu && rec.w + 1u >= hi) continue;  // the block starts at or after the window's end
+          BlockFetch f;
+          fetch_issue_rec(L, rec, lane, f);
+          for (;;) {
+            uint32_t doc[4], tf[4];
+            fetch_decode(L, j, f, lane, doc, tf);
+            // the next block is needed iff this one ends before the window does
+            const bool more = rec.x < hi - 1u && j + 1u < L.n_total;
+            if (more) {
+              ++j; ++src;
+              if (src == 32u) {  // ran off the probe: fetch the next 32 records
+                cur = j; src = 0;
+                const uint32_t idx = cur + lane;
+                r = idx < L.n_total ? __ldg(L.tab4 + idx) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+              }
+              rec.x = __shfl_sync(kFull, r.x, src); rec.y = __shfl_sync(kFull, r.y, src);
+              rec.z = __shfl_sync(kFull, r.z, src); rec.w = __shfl_sync(kFull, r.w, src);
+              fetch_issue_rec(L, rec, lane, f);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (doc[i] >= lo && doc[i] < hi) {
+                const uint32_t slot = doc[i] - lo;
+                const uint32_t id = staged_fn ? (uint32_t)W.fn[slot] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[i]) : 1u);
+                W.acc[slot] = __fadd_rn(W.acc[slot], bm25_score_id(sc, id, tf[i]));
+                touched |= 1u << (slot >> 7);
+              }
+            }
+            if (!more) break;
+          }
+          __syncwarp();
+        } else {
+          // ---- thin clause: the decoded block lives in shared memory ---------------------------------------
+          StripCache& cc = C[s_ql[t].pad >> 1];
+          for (;;) {
+            const uint32_t nd = W.next_doc[t];
+            if (nd >= hi) break;  // nothing of this clause in the window (also: clause exhausted)
+            uint32_t mn = kNoDoc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t d = cc.doc[lane * 4 + i];
+              if (d >= lo && d < hi) {
+                const uint32_t slot = d - lo;
+                W.acc[slot] = __fadd_rn(W.acc[slot], cc.score[lane * 4 + i]);
+                touched |= 1u << (slot >> 7);
+              } else if (d >= hi && d != kNoDoc) {
+                mn = min(mn, d);
+              }
+            }
+            mn = warp_min(mn);
+            __syncwarp();
+            if (mn != kNoDoc) { if (lane == 0) W.next_doc[t] = mn; __syncwarp(); break; }
+            // block used up: bring in the next one
+            const uint32_t jb = W.cur[t] + 1u;
+            if (jb >= L.n_total) { if (lane == 0) W.next_doc[t] = kNoDoc; __syncwarp(); break; }
+            const Scorer sc = make_scorer(P, s_ql[t]);
+            uint32_t doc[4], tf[4];
+            decode_block(L, jb, lane, doc, tf);
+            uint32_t first = kNoDoc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const bool valid = doc[i] < S.max_doc;
+              cc.doc[lane * 4 + i] = valid ? doc[i] : kNoDoc;
+              cc.score[lane * 4 + i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+              if (valid) first = min(first, doc[i]);
+            }
+            first = warp_min(first);
+            if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; }
+            __syncwarp();
+          }
+        }
+      }
+      // ---- harvest the groups that were touched --------------------------------------------------------------
+      touched = __reduce_or_sync(kFull, touched);
+      if (touched) {
+        const float theta_f = threshold_score((uint32_t)(theta >> 32));
+        for (uint32_t g = 0; g < kWin / 128; ++g) {
+          if (!((touched >> g) & 1u)) continue;
+          const uint32_t idx = g * 128 + lane * 4;
+          const float4 v = *reinterpret_cast<const float4*>(W.acc + idx);
+          *reinterpret_cast<float4*>(W.acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+          // float test first (nearly everything fails it); keys are built for the survivors only
+          if (__ballot_sync(kFull, v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f)) {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t d = lo + idx + c;
+              const unsigned long long key = make_key(vv[c], d);
+              bool pass = vv[c] >= theta_f && __float_as_uint(vv[c]) != 0x80000000u && key >= theta;
+              if (pass && S.alive) pass = is_alive(S.alive, d);
+              unsigned mm = __ballot_sync(kFull, pass);
+              if (mm) {
+                if (cnt + 32u > kWBuf) {  // make room for one key per lane; the threshold may rise
+                  strip_compact(W.keys, cnt, Q.k, theta, &qs->theta, lane);
+                  pass = pass && key >= theta;
+                  mm = __ballot_sync(kFull, pass);
+                }
+                if (pass) W.keys[cnt + __popc(mm & lanemask_lt(lane))] = key;
+                cnt += __popc(mm);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();  // cursor updates of this window are visible to the next one
+    }
+  }
+  // ---- hand the survivors over ------------------------------------------------------------------------------
+  if (cnt > Q.k) strip_compact(W.keys, cnt, Q.k, theta, &qs->theta, lane);
+  unsigned base = 0;
+  if (lane == 0 && cnt) base = atomicAdd(&qs->cand_count, cnt);
+  base = __shfl_sync(kFull, base, 0);
+  for (uint32_t i = lane; i < cnt; i += 32) {
+    if (base + i < Q.cand_cap) {
+      const unsigned long long key = W.keys[i];
+      Cand c;
+      c.score_key = (uint32_t)(key >> 32);
+      c.segment_ord = S.segment_ord;
+      c.doc = 0xFFFFFFFFu - (uint32_t)key;
+      c.pad = 0;
+      P.cands[Q.cand_base + base + i] = c;
+    }
+  }
 }
 
 // ---- final per-query selection -----------------------------------------------------------------------------
