@@ -293,7 +293,12 @@ struct TopK {
   unsigned long long* theta;  // shared: keys below it can no longer enter the top-k
   TopKScratch* scratch;       // shared
   unsigned long long* counters;  // global diagnostics (BatchParams::counters)
+  unsigned named;     // 0: the whole CTA takes part (__syncthreads); 1: only the first `nthreads` threads (bar.sync 1)
+  unsigned nthreads;  // threads that take part (threadIdx.x < nthreads)
 };
+__device__ __forceinline__ void topk_sync(const TopK& t) {
+  if (t.named) asm volatile("bar.sync 1, 256;" ::: "memory"); else __syncthreads();
+}
 
 // All lanes of a warp call this together (pass may differ per lane).
 __device__ __forceinline__ void topk_push(const TopK& t, bool pass, unsigned long long key, uint32_t lane) {
@@ -308,16 +313,16 @@ __device__ __forceinline__ void topk_push(const TopK& t, bool pass, unsigned lon
 
 // Whole CTA. Sorts the buffer (descending) and keeps the best k; publishes the k-th score.
 __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_global) {
-  __syncthreads();
+  topk_sync(t);
   const unsigned n = *t.count;
   unsigned size = 2;
   while (size < n) size <<= 1;
-  for (unsigned i = threadIdx.x; i < size; i += blockDim.x)
+  for (unsigned i = threadIdx.x; i < size; i += t.nthreads)
     if (i >= n) t.keys[i] = 0ull;
-  __syncthreads();
+  topk_sync(t);
   for (unsigned kk = 2; kk <= size; kk <<= 1) {
     for (unsigned j = kk >> 1; j > 0; j >>= 1) {
-      for (unsigned i = threadIdx.x; i < size; i += blockDim.x) {
+      for (unsigned i = threadIdx.x; i < size; i += t.nthreads) {
         const unsigned ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long a = t.keys[i], b = t.keys[ixj];
@@ -325,7 +330,7 @@ __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_glob
           if (desc ? (a < b) : (a > b)) { t.keys[i] = b; t.keys[ixj] = a; }
         }
       }
-      __syncthreads();
+      topk_sync(t);
     }
   }
   if (threadIdx.x == 0 && n > k) {
@@ -334,7 +339,7 @@ __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_glob
     if (kth > *t.theta) *t.theta = kth;
     atomicMax(theta_global, (unsigned)(kth >> 32));
   }
-  __syncthreads();
+  topk_sync(t);
 }
 
 // Cheap compaction.  The CTA only has to keep a SUPERSET of its k best keys and a threshold that is a valid
@@ -344,25 +349,25 @@ __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_glob
 // part.  Falls back to the exact sort when the boundary bin is too crowded (ties) to make room.
 __device__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, unsigned int* theta_global) {
   TopKScratch& sc = *t.scratch;
-  __syncthreads();
+  topk_sync(t);
   const unsigned n = *t.count;
   if (n <= k) return;  // uniform
-  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) sc.hist[i] = 0;
+  for (unsigned i = threadIdx.x; i < 256; i += t.nthreads) sc.hist[i] = 0;
   if (threadIdx.x == 0) { sc.kmin = 0xFFFFFFFFu; sc.kmax = 0; sc.hole_n = 0; sc.mover_n = 0; }
-  __syncthreads();
+  topk_sync(t);
   unsigned lmin = 0xFFFFFFFFu, lmax = 0;
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+  for (unsigned i = threadIdx.x; i < n; i += t.nthreads) {
     const unsigned sk = (unsigned)(t.keys[i] >> 32);
     lmin = min(lmin, sk); lmax = max(lmax, sk);
   }
   lmin = __reduce_min_sync(kFull, lmin);
   lmax = __reduce_max_sync(kFull, lmax);
   if ((threadIdx.x & 31u) == 0) { atomicMin(&sc.kmin, lmin); atomicMax(&sc.kmax, lmax); }
-  __syncthreads();
+  topk_sync(t);
   const unsigned kmin = sc.kmin, span = sc.kmax - kmin;
   const unsigned shift = span < 256u ? 0u : (unsigned)(32 - __clz(span)) - 8u;  // (key - kmin) >> shift in [0, 255]
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&sc.hist[((unsigned)(t.keys[i] >> 32) - kmin) >> shift], 1u);
-  __syncthreads();
+  for (unsigned i = threadIdx.x; i < n; i += t.nthreads) atomicAdd(&sc.hist[((unsigned)(t.keys[i] >> 32) - kmin) >> shift], 1u);
+  topk_sync(t);
   if (threadIdx.x < 32) {  // suffix sums over the 256 bins: 8 per lane
     const unsigned lane = threadIdx.x;
     unsigned loc[8], tot = 0;
@@ -389,7 +394,7 @@ __device__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, 
     keep = __shfl_sync(kFull, keep, src);
     if (lane == 0) { sc.cut = (unsigned)cut; sc.keep = keep; }
   }
-  __syncthreads();
+  topk_sync(t);
   const unsigned keep = sc.keep;
   if (threadIdx.x == 0) { atomicAdd(&t.counters[3], 1ull); if (keep > keep_max || keep == n) atomicAdd(&t.counters[4], 1ull); }
   if (keep > keep_max || keep == n) {  // crowded boundary bin (ties) or nothing to drop: exact route
@@ -397,44 +402,44 @@ __device__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, 
     return;
   }
   const unsigned edge = kmin + (sc.cut << shift);  // every survivor has score key >= edge, and there are >= k of them
-  for (unsigned i = threadIdx.x; i < keep; i += blockDim.x)
+  for (unsigned i = threadIdx.x; i < keep; i += t.nthreads)
     if ((unsigned)(t.keys[i] >> 32) < edge) sc.holes[atomicAdd(&sc.hole_n, 1u)] = (unsigned short)i;
-  __syncthreads();
-  for (unsigned i = keep + threadIdx.x; i < n; i += blockDim.x) {
+  topk_sync(t);
+  for (unsigned i = keep + threadIdx.x; i < n; i += t.nthreads) {
     const unsigned long long key = t.keys[i];
     if ((unsigned)(key >> 32) >= edge) t.keys[sc.holes[atomicAdd(&sc.mover_n, 1u)]] = key;
   }
-  __syncthreads();
+  topk_sync(t);
   if (threadIdx.x == 0) {
     *t.count = keep;
     const unsigned long long th = (unsigned long long)edge << 32;
     if (th > *t.theta) *t.theta = th;
     atomicMax(theta_global, edge);
   }
-  __syncthreads();
+  topk_sync(t);
 }
 
 // End of a round of the CTA: refresh the shared threshold from the query-wide one and make room.
 __device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsigned int* theta_global) {
-  __syncthreads();
+  topk_sync(t);
   if (*t.count > kCap - kRoundMargin) topk_compact_hist(t, k, kCap - kRoundMargin, theta_global);
   if (threadIdx.x == 0) {
     const unsigned long long g = (unsigned long long)(*(volatile unsigned int*)theta_global) << 32;
     if (g > *t.theta) *t.theta = g;
   }
-  __syncthreads();
+  topk_sync(t);
 }
 
 // End of a unit: the CTA's survivors go to the query's candidate region (at most 2k of them).
 __device__ void topk_flush(const TopK& t, const DQuery& q, QState* qs, Cand* cands, uint32_t segment_ord) {
-  __syncthreads();
+  topk_sync(t);
   if (*t.count > 2u * q.k) topk_compact_hist(t, q.k, min(2u * q.k, kCap / 2u), &qs->theta);
   __shared__ unsigned s_base;
   const unsigned n = *t.count;
   if (threadIdx.x == 0) s_base = n ? atomicAdd(&qs->cand_count, n) : 0u;
-  __syncthreads();
+  topk_sync(t);
   const unsigned base = s_base;
-  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+  for (unsigned i = threadIdx.x; i < n; i += t.nthreads) {
     if (base + i < q.cand_cap) {
       const unsigned long long key = t.keys[i];
       Cand c;

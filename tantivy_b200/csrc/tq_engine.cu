@@ -130,7 +130,7 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;
-  uint32_t or_prune = 1, or_strip = 1;
+  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1;
 };
 
 struct tq_batch {
@@ -148,6 +148,7 @@ struct tq_batch {
   uint32_t n_units[4] = {0, 0, 0, 0};    // term, and, or (window kernel), or (strip kernel)
   uint32_t unit_base[4] = {0, 0, 0, 0};
   uint32_t strip_cached_max = 0;
+  uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
   size_t qstate_off = 0, cands_off = 0, res_off = 0, res_bytes = 0, n_cands = 0;
   tq_stats stats{};
   bool ran = false;
@@ -183,12 +184,14 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->and_blocks_per_unit = env_u32("TQ_AND_BLOCKS_PER_UNIT", 128);
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
   c->or_strip = env_u32("TQ_OR_STRIP", 1);
+  c->or_pipe = env_u32("TQ_OR_PIPE", 1);
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes());
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem_bytes(kMaxCached));
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
   *out = c;
@@ -421,7 +424,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   std::vector<int> qseg_op;
   std::vector<uint32_t> qseg_total;
   uint32_t n_qsegs_op[4] = {0, 0, 0, 0};
-  uint32_t strip_cached_max = 0;
+  uint32_t strip_cached_max = 0, or_max_lists = 0;
   {
     std::lock_guard<std::mutex> g(c->mu);
     std::vector<const tq_term_seg*> order;
@@ -513,6 +516,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
             unit_class = 3;
           }
         }
+        if (unit_class == TQ_OP_OR) or_max_lists = std::max<uint32_t>(or_max_lists, (uint32_t)here.size());
         for (auto& h : here) qlists.push_back(h.second);
         qs.n_lists = (uint32_t)here.size();
         lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
@@ -563,6 +567,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
   const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size();
   b->strip_cached_max = strip_cached_max;
+  b->or_max_lists = or_max_lists;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
   const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
   b->desc_bytes = off;
@@ -647,7 +652,14 @@ int tq_batch_run(tq_batch* b) {
   TQ_CUDA(cudaEventRecord(b->ev_op[0], b->stream));
   if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
   TQ_CUDA(cudaEventRecord(b->ev_op[1], b->stream));
-  if (b->n_units[TQ_OP_OR]) { k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]); ++launches; }
+  if (b->n_units[TQ_OP_OR]) {
+    // window unions: the TMA/mbarrier pipeline when every union has few enough clauses for its tables, else the plain kernel
+    if (b->ctx->or_pipe && b->or_max_lists <= kPipeMaxLists && !b->ctx->or_prune)
+      k_or_pipe<<<b->n_units[TQ_OP_OR], kPipeThreads, pipe_smem_bytes(), b->stream>>>(P, b->unit_base[TQ_OP_OR]);
+    else
+      k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
+    ++launches;
+  }
   if (b->n_units[3]) { k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches; }
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));

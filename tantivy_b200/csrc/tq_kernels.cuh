@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kThreads) k_term(const BatchParams P, uint32_t
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters, 0u, (unsigned)kThreads};
   BlockFetch f;
   if (U.begin + warp < U.end) fetch_issue(L, U.begin + warp, lane, f);
   for (uint32_t r = U.begin; r < U.end; r += kWarps) {
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
   uint32_t* dec = s_dec[warp];
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters, 0u, (unsigned)kThreads};
   for (uint32_t r = U.begin; r < U.end; r += kWarps) {
     const uint32_t b = r + warp;
     if (b < U.end) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
     for (uint32_t i = 0; i < S.n_lists; ++i) sh.prefix[i + 1] = sh.prefix[i] + mx[sh.order[i]];
   }
   __syncthreads();
-  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters};
+  const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters, 0u, (unsigned)kThreads};
   or_tile_ranges(P, S, sh, 0, U.begin, warp, lane);
   unsigned int theta_g_seen = 0;  // thread 0: query-wide threshold sampled one window ago
   __syncthreads();
@@ -1011,6 +1011,291 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
       c.pad = 0;
       P.cands[Q.cand_base + base + i] = c;
     }
+  }
+}
+
+// ---- union, pipelined form: TMA bulk copies + mbarrier ring ------------------------------------------------------
+// ncu showed k_or latency bound (about one block per warp in flight, IPC ~1 per SM).  Here a PRODUCER warp walks the
+// block tables of all clauses, one doc-id window after the other, and streams every packed block the window needs
+// into a shared-memory ring with cp.async.bulk (TMA), many blocks and several windows ahead of the 8 CONSUMER warps,
+// which only ever touch shared memory: wait on the slot's mbarrier, pull their vectors, decode, score, add in clause
+// order (named barrier among the consumers between clauses), harvest.  Bytes in flight per SM go from a few hundred
+// to tens of KB.  The window's fieldnorm bytes arrive the same way.
+constexpr uint32_t kPipeSlots = 24;         // ring slots of 1 KB (a block is at most 63 vectors = 1008 B)
+constexpr uint32_t kPipeSlotBytes = 1024 + 16;
+constexpr uint32_t kPipeThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
+constexpr uint32_t kPipeMaxLists = 8;
+
+struct PipeWindow {  // written by the producer, read by the consumers
+  uint32_t lo, hi, any, pad;
+  uint32_t first[kPipeMaxLists];  // ring item number of the clause's first block in this window
+  uint32_t cnt[kPipeMaxLists];    // how many blocks of the clause overlap the window
+};
+struct PipeShared {
+  unsigned long long full[kPipeSlots], empty[kPipeSlots];
+  unsigned long long win_full[2], win_empty[2];
+  uint2 desc[kPipeSlots];  // .x meta (0xFFFFFFFF: VInt tail, no bytes), .y last doc of the previous block, low bit of block index in... see below
+  uint32_t blk[kPipeSlots]; // block ordinal (needed for the tail pseudo block)
+  PipeWindow win[2];
+};
+__host__ __device__ constexpr size_t pipe_smem_bytes() {
+  return kTileDocs * sizeof(float) + 2 * kTileDocs + kPipeSlots * kPipeSlotBytes;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// A wait that can never hang the device: a protocol error traps after ~2^26 polls instead of spinning for ever.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pipe_consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P, uint32_t unit_base) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_acc = reinterpret_cast<float*>(s_raw);                                  // [kTileDocs]
+  uint8_t* s_fn = s_raw + kTileDocs * sizeof(float);                               // [2][kTileDocs]
+  unsigned char* s_ring = s_fn + 2 * kTileDocs;                                    // [kPipeSlots][kPipeSlotBytes]
+  __shared__ CtaTopK s_top;
+  __shared__ PipeShared ps;
+  __shared__ ListDesc s_list[kPipeMaxLists];
+  __shared__ QList s_ql[kPipeMaxLists];
+  const Unit U = P.units[unit_base + blockIdx.x];
+  const QSeg S = P.qsegs[U.qseg];
+  const DQuery Q = P.queries[S.query];
+  QState* qs = P.qstate + S.query;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
+  const float neg_zero = __uint_as_float(0x80000000u);
+  if (threadIdx.x < S.n_lists) {
+    s_ql[threadIdx.x] = P.qlists[S.lists_base + threadIdx.x];
+    s_list[threadIdx.x] = P.lists[s_ql[threadIdx.x].list_id];
+  }
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < kPipeSlots; ++i) { mbar_init(&ps.full[i], 1); mbar_init(&ps.empty[i], 1); }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(&ps.win_full[i], 1); mbar_init(&ps.win_empty[i], kWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32;
+  }
+  for (uint32_t i = threadIdx.x; i < kTileDocs; i += kPipeThreads) s_acc[i] = neg_zero;
+  __syncthreads();
+  const uint32_t n_windows = U.end - U.begin;
+
+  if (warp == kWarps) {
+    // =========================== producer ======================================================================
+    uint32_t cur[kPipeMaxLists];
+#pragma unroll
+    for (uint32_t t = 0; t < kPipeMaxLists; ++t) cur[t] = 0;
+    uint32_t n_item = 0;  // ring item counter
+    for (uint32_t wi = 0; wi < n_windows; ++wi) {
+      const uint32_t tile = U.begin + wi;
+      const uint32_t lo = tile * kTileDocs, hi = min(lo + kTileDocs, S.max_doc);
+      const uint32_t buf = wi & 1u;
+      if (wi >= 2) mbar_wait(&ps.win_empty[buf], ((wi >> 1) - 1u) & 1u);  // the consumers are done with this buffer's previous window
+      // where every clause stands in this window: one 32-wide probe of the 16-byte block records per clause
+      uint32_t blo[kPipeMaxLists], cntv[kPipeMaxLists];
+      uint32_t total = 0;
+#pragma unroll
+      for (uint32_t t = 0; t < kPipeMaxLists; ++t) {
+        blo[t] = 0; cntv[t] = 0;
+        if (t < S.n_lists) {
+          const ListDesc& L = s_list[t];
+          const uint32_t j_lo = first_block_ge(L.last_doc, cur[t], L.n_total, lo, lane);
+          cur[t] = j_lo;
+          if (j_lo < L.n_total) {
+            uint32_t j_hi = first_block_ge(L.last_doc, j_lo, L.n_total, hi - 1u, lane);
+            if (j_hi >= L.n_total) j_hi = L.n_total - 1u;
+            blo[t] = j_lo; cntv[t] = j_hi - j_lo + 1u;
+          }
+        }
+        total += cntv[t];
+      }
+      if (lane == 0) {
+        PipeWindow& w = ps.win[buf];
+        w.lo = lo; w.hi = hi; w.any = total;
+        uint32_t n = n_item;
+#pragma unroll
+        for (uint32_t t = 0; t < kPipeMaxLists; ++t) { w.first[t] = n; w.cnt[t] = cntv[t]; n += cntv[t]; }
+        if (staged_fn && total) {
+          mbar_arrive_expect_tx(&ps.win_full[buf], kTileDocs);
+          bulk_g2s(s_fn + buf * kTileDocs, S.fieldnorm + lo, kTileDocs, &ps.win_full[buf]);
+        } else {
+          mbar_arrive(&ps.win_full[buf]);
+        }
+      }
+      __syncwarp();
+      // the blocks, 32 at a time, one lane per block
+#pragma unroll
+      for (uint32_t t = 0; t < kPipeMaxLists; ++t) {
+        if (t < S.n_lists) {
+          const ListDesc& L = s_list[t];
+          // 16 blocks per step: a lane never waits for a slot that a lane of the SAME step still has to fill
+          // (kPipeSlots >= 16), so the step cannot deadlock on itself whatever the reconvergence order
+          for (uint32_t base = 0; base < cntv[t]; base += 16) {
+            const uint32_t i = base + lane;
+            if (lane < 16 && i < cntv[t]) {
+              const uint32_t b = blo[t] + i;
+              const uint32_t n = n_item + i;
+              const uint32_t slot = n % kPipeSlots, round = n / kPipeSlots;
+              mbar_wait(&ps.empty[slot], (round & 1u) ^ 1u);  // free (passes at once in the first round)
+              ps.blk[slot] = b;
+              if (b >= L.n_blocks) {  // VInt tail: already decoded in global memory, nothing to copy
+                ps.desc[slot] = make_uint2(0xFFFFFFFFu, 0u);
+                mbar_arrive(&ps.full[slot]);
+              } else {
+                const uint4 rec = __ldg(L.tab4 + b);
+                ps.desc[slot] = make_uint2(rec.z, rec.w == 0xFFFFFFFFu ? 0u : rec.w);
+                const uint32_t bytes = 16u * ((rec.z & 31u) + (L.has_freq ? ((rec.z >> 8) & 63u) : 0u));
+                if (bytes) {
+                  mbar_arrive_expect_tx(&ps.full[slot], bytes);
+                  bulk_g2s(s_ring + slot * kPipeSlotBytes, L.blocks + rec.y, bytes, &ps.full[slot]);
+                } else {
+                  mbar_arrive(&ps.full[slot]);
+                }
+              }
+            }
+            __syncwarp();
+          }
+          n_item += cntv[t];
+        }
+      }
+    }
+  } else {
+    // =========================== consumers =====================================================================
+    const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters, 1u, (unsigned)kThreads};
+    unsigned int theta_g_seen = 0;
+    for (uint32_t wi = 0; wi < n_windows; ++wi) {
+      const uint32_t buf = wi & 1u;
+      mbar_wait(&ps.win_full[buf], (wi >> 1) & 1u);
+      const PipeWindow& w = ps.win[buf];
+      const uint32_t lo = w.lo, hi = w.hi;
+      const bool any = w.any != 0;
+      if (threadIdx.x == 0) {
+        const unsigned long long g = (unsigned long long)theta_g_seen << 32;
+        if (g > s_top.theta) s_top.theta = g;
+        theta_g_seen = *(volatile unsigned int*)&qs->theta;
+      }
+      if (any) {
+        const uint8_t* fn_tile = s_fn + buf * kTileDocs;
+        for (uint32_t t = 0; t < S.n_lists; ++t) {
+          const uint32_t cnt = w.cnt[t];
+          if (cnt == 0) continue;
+          const ListDesc& L = s_list[t];
+          const Scorer scr = make_scorer(P, s_ql[t]);
+          const uint32_t first = w.first[t];
+          // blocks of clause t are dealt to the warps rotated by the clause ordinal
+          for (uint32_t i = (warp + kWarps - (t & (kWarps - 1))) & (kWarps - 1); i < cnt; i += kWarps) {
+            const uint32_t n = first + i;
+            const uint32_t slot = n % kPipeSlots, round = n / kPipeSlots;
+            mbar_wait(&ps.full[slot], round & 1u);
+            const uint2 d = ps.desc[slot];
+            const uint32_t b = ps.blk[slot];
+            BlockFetch f;
+            f.meta = d.x; f.prev = d.y;
+            if (d.x != 0xFFFFFFFFu) {
+              const uint32_t db = d.x & 31u, tb = (d.x >> 8) & 63u;
+              const uint4* v = reinterpret_cast<const uint4*>(s_ring + slot * kPipeSlotBytes);
+              const uint32_t wd = (lane * db) >> 5;
+              f.dlo = v[wd]; f.dhi = v[wd + 1];
+              if (L.has_freq) { const uint32_t wt = db + ((lane * tb) >> 5); f.tlo = v[wt]; f.thi = v[wt + 1]; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.empty[slot]);  // the slot can be refilled: everything needed is in registers
+            uint32_t doc[4], tf[4];
+            fetch_decode(L, b, f, lane, doc, tf);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              if (doc[k4] >= lo && doc[k4] < hi) {
+                const uint32_t slot_d = doc[k4] - lo;
+                const uint32_t id = staged_fn ? (uint32_t)fn_tile[slot_d] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[k4]) : 1u);
+                s_acc[slot_d] = __fadd_rn(s_acc[slot_d], bm25_score_id(scr, id, tf[k4]));
+              }
+            }
+          }
+          pipe_consumer_sync();  // clause order is the f32 summation order
+        }
+        // ---- harvest (same as k_or, consumers only) -----------------------------------------------------------
+        const unsigned long long theta = *T.theta;
+        const float theta_f = threshold_score((uint32_t)(theta >> 32));
+        uint32_t passmask = 0;
+#pragma unroll
+        for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+          const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+          const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+          if (v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f) {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t dd = lo + idx + c;
+              bool pass = vv[c] >= theta_f && __float_as_uint(vv[c]) != 0x80000000u && make_key(vv[c], dd) >= theta;
+              if (pass && S.alive) pass = is_alive(S.alive, dd);
+              passmask |= pass ? (1u << (j * 4 + c)) : 0u;
+            }
+          }
+        }
+        // room check: the buffer keeps at most kCap - kRoundMargin keys between windows, a window adds at most... see below
+        const uint32_t wsum = __reduce_add_sync(kFull, (uint32_t)__popc(passmask));
+        __shared__ uint32_t s_npass;
+        if (threadIdx.x == 0) s_npass = 0;
+        pipe_consumer_sync();
+        if (lane == 0 && wsum) atomicAdd(&s_npass, wsum);
+        pipe_consumer_sync();
+        const bool fits = *T.count + s_npass <= kCap;
+        if (fits) {
+#pragma unroll
+          for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+            const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+            const uint32_t sub = (passmask >> (j * 4)) & 15u;
+            if (__ballot_sync(kFull, sub != 0)) {
+              const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+              const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int c = 0; c < 4; ++c) topk_push(T, (sub >> c) & 1u, make_key(vv[c], lo + idx + c), lane);
+            }
+            *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+          }
+          topk_round_end(T, Q.k, &qs->theta);
+        } else {  // cold start: go in rounds with compaction between
+          topk_round_end(T, Q.k, &qs->theta);
+          for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
+            const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
+            const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            const unsigned long long th = *T.theta;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const unsigned long long key = make_key(vv[c], lo + idx + c);
+              topk_push(T, ((passmask >> (j * 4 + c)) & 1u) && key >= th, key, lane);
+            }
+            *reinterpret_cast<float4*>(s_acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+            topk_round_end(T, Q.k, &qs->theta);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ps.win_empty[buf]);  // this warp no longer reads the window's table or fieldnorms
+    }
+    topk_flush(T, Q, qs, P.cands, S.segment_ord);
   }
 }
 
