@@ -227,14 +227,12 @@ struct Scorer {
   const float* cache;     // [256] norms
   const float* tf_table;  // [kTfRows][256]
 };
+__device__ __noinline__ float bm25_factor_large_tf(const float* __restrict__ cache, uint32_t id, uint32_t tf) {
+  const float t = __uint2float_rn(tf);
+  return __fdiv_rn(t, __fadd_rn(t, __ldg(cache + id)));
+}
 __device__ __forceinline__ float bm25_score_id(const Scorer& sc, uint32_t id, uint32_t tf) {
-  float fac;
-  if (tf < kTfRows) {
-    fac = __ldg(sc.tf_table + (tf << 8) + id);
-  } else {
-    const float t = __uint2float_rn(tf);
-    fac = __fdiv_rn(t, __fadd_rn(t, __ldg(sc.cache + id)));
-  }
+  const float fac = tf < kTfRows ? __ldg(sc.tf_table + (tf << 8) + id) : bm25_factor_large_tf(sc.cache, id, tf);
   return __fmul_rn(sc.weight, fac);
 }
 __device__ __forceinline__ float bm25_score(const Scorer& sc, const uint8_t* __restrict__ fieldnorm, uint32_t doc, uint32_t tf) {
@@ -248,7 +246,7 @@ __device__ __forceinline__ Scorer make_scorer(const BatchParams& P, const QList&
 // ---- first block whose last_doc >= target, searching [from, n) (SkipReader::seek) ---------------
 // Warp-cooperative: one coalesced probe of 32 entries at `from`, then a 32-ary search.
 // Returns n if there is none.
-__device__ __forceinline__ uint32_t first_block_ge(const uint32_t* __restrict__ last_doc, uint32_t from, uint32_t n,
+__device__ __noinline__ uint32_t first_block_ge(const uint32_t* __restrict__ last_doc, uint32_t from, uint32_t n,
                                                    uint32_t target, uint32_t lane) {
   if (from >= n) return n;
   {
@@ -312,7 +310,7 @@ __device__ __forceinline__ void topk_push(const TopK& t, bool pass, unsigned lon
 }
 
 // Whole CTA. Sorts the buffer (descending) and keeps the best k; publishes the k-th score.
-__device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_global) {
+__device__ __noinline__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_global) {
   topk_sync(t);
   const unsigned n = *t.count;
   unsigned size = 2;
@@ -347,7 +345,7 @@ __device__ void topk_compact(const TopK& t, uint32_t k, unsigned int* theta_glob
 // between the smallest and largest key in the buffer) finds the highest bin edge with >= k keys at or above
 // it; keys below that edge are dropped by moving the survivors of the upper part into the holes of the lower
 // part.  Falls back to the exact sort when the boundary bin is too crowded (ties) to make room.
-__device__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, unsigned int* theta_global) {
+__device__ __noinline__ void topk_compact_hist(const TopK& t, uint32_t k, uint32_t keep_max, unsigned int* theta_global) {
   TopKScratch& sc = *t.scratch;
   topk_sync(t);
   const unsigned n = *t.count;
@@ -431,7 +429,7 @@ __device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsign
 }
 
 // End of a unit: the CTA's survivors go to the query's candidate region (at most 2k of them).
-__device__ void topk_flush(const TopK& t, const DQuery& q, QState* qs, Cand* cands, uint32_t segment_ord) {
+__device__ __noinline__ void topk_flush(const TopK& t, const DQuery& q, QState* qs, Cand* cands, uint32_t segment_ord) {
   topk_sync(t);
   if (*t.count > 2u * q.k) topk_compact_hist(t, q.k, min(2u * q.k, kCap / 2u), &qs->theta);
   __shared__ unsigned s_base;

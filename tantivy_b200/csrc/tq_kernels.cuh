@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
       // A float compare against the threshold score rejects nearly every slot (untouched slots hold
       // -0.0, which is below any positive threshold); the exact key test runs only on the survivors.
       uint32_t passmask = 0;
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
         const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
         const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
@@ -665,7 +665,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
       const bool fits = *T.count + npass <= kCap;
       __syncthreads();
       if (fits) {
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
           const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
           const uint32_t sub = (passmask >> (j * 4)) & 15u;
@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
       } else {  // cold start: more survivors than the buffer holds; go in rounds with compaction between
         if (threadIdx.x == 0) sh.npass = 0;
         topk_round_end(T, Q.k, &qs->theta);  // leaves at most kCap - kRoundMargin keys
+#pragma unroll 1
         for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
           const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
           const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
@@ -754,7 +755,7 @@ __device__ __forceinline__ void fetch_issue_rec(const ListDesc& L, const uint4 r
 }
 
 // warp-level: sort the candidate buffer (descending) and keep the best k
-__device__ __forceinline__ void strip_compact(unsigned long long* keys, uint32_t& cnt, uint32_t k, unsigned long long& theta,
+__device__ __noinline__ void strip_compact(unsigned long long* keys, uint32_t& cnt, uint32_t k, unsigned long long& theta,
                                               unsigned int* theta_global, uint32_t lane) {
   for (uint32_t i = cnt + lane; i < kWBuf; i += 32) keys[i] = 0ull;
   __syncwarp();
@@ -1025,6 +1026,7 @@ constexpr uint32_t kPipeSlots = 24;         // ring slots of 1 KB (a block is at
 constexpr uint32_t kPipeSlotBytes = 1024 + 16;
 constexpr uint32_t kPipeThreads = kThreads + 32;  // 8 consumer warps + 1 producer warp
 constexpr uint32_t kPipeMaxLists = 8;
+constexpr uint32_t kPipeBatch = 16;          // blocks decoded in parallel before the ordered add (<= kPipeSlots - 8)
 
 struct PipeWindow {  // written by the producer, read by the consumers
   uint32_t lo, hi, any, pad;
@@ -1062,7 +1064,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if (++spins > (1u << 22)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
@@ -1103,39 +1105,39 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
 
   if (warp == kWarps) {
     // =========================== producer ======================================================================
-    uint32_t cur[kPipeMaxLists];
-#pragma unroll
-    for (uint32_t t = 0; t < kPipeMaxLists; ++t) cur[t] = 0;
+    __shared__ uint32_t p_cur[kPipeMaxLists], p_blo[kPipeMaxLists], p_cnt[kPipeMaxLists];
+    if (lane < kPipeMaxLists) p_cur[lane] = 0;
+    __syncwarp();
     uint32_t n_item = 0;  // ring item counter
     for (uint32_t wi = 0; wi < n_windows; ++wi) {
       const uint32_t tile = U.begin + wi;
       const uint32_t lo = tile * kTileDocs, hi = min(lo + kTileDocs, S.max_doc);
       const uint32_t buf = wi & 1u;
       if (wi >= 2) mbar_wait(&ps.win_empty[buf], ((wi >> 1) - 1u) & 1u);  // the consumers are done with this buffer's previous window
-      // where every clause stands in this window: one 32-wide probe of the 16-byte block records per clause
-      uint32_t blo[kPipeMaxLists], cntv[kPipeMaxLists];
+      // where every clause stands in this window
       uint32_t total = 0;
-#pragma unroll
-      for (uint32_t t = 0; t < kPipeMaxLists; ++t) {
-        blo[t] = 0; cntv[t] = 0;
-        if (t < S.n_lists) {
-          const ListDesc& L = s_list[t];
-          const uint32_t j_lo = first_block_ge(L.last_doc, cur[t], L.n_total, lo, lane);
-          cur[t] = j_lo;
-          if (j_lo < L.n_total) {
-            uint32_t j_hi = first_block_ge(L.last_doc, j_lo, L.n_total, hi - 1u, lane);
-            if (j_hi >= L.n_total) j_hi = L.n_total - 1u;
-            blo[t] = j_lo; cntv[t] = j_hi - j_lo + 1u;
-          }
+      for (uint32_t t = 0; t < S.n_lists; ++t) {
+        const ListDesc& L = s_list[t];
+        uint32_t blo = 0, cnt = 0;
+        const uint32_t j_lo = first_block_ge(L.last_doc, p_cur[t], L.n_total, lo, lane);
+        if (j_lo < L.n_total) {
+          uint32_t j_hi = first_block_ge(L.last_doc, j_lo, L.n_total, hi - 1u, lane);
+          if (j_hi >= L.n_total) j_hi = L.n_total - 1u;
+          blo = j_lo; cnt = j_hi - j_lo + 1u;
         }
-        total += cntv[t];
+        __syncwarp();
+        if (lane == 0) { p_cur[t] = j_lo; p_blo[t] = blo; p_cnt[t] = cnt; }
+        total += cnt;
       }
+      __syncwarp();
       if (lane == 0) {
         PipeWindow& w = ps.win[buf];
         w.lo = lo; w.hi = hi; w.any = total;
         uint32_t n = n_item;
-#pragma unroll
-        for (uint32_t t = 0; t < kPipeMaxLists; ++t) { w.first[t] = n; w.cnt[t] = cntv[t]; n += cntv[t]; }
+        for (uint32_t t = 0; t < kPipeMaxLists; ++t) {
+          const uint32_t c = t < S.n_lists ? p_cnt[t] : 0u;
+          w.first[t] = n; w.cnt[t] = c; n += c;
+        }
         if (staged_fn && total) {
           mbar_arrive_expect_tx(&ps.win_full[buf], kTileDocs);
           bulk_g2s(s_fn + buf * kTileDocs, S.fieldnorm + lo, kTileDocs, &ps.win_full[buf]);
@@ -1144,20 +1146,22 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
         }
       }
       __syncwarp();
-      // the blocks, 32 at a time, one lane per block
-#pragma unroll
-      for (uint32_t t = 0; t < kPipeMaxLists; ++t) {
-        if (t < S.n_lists) {
-          const ListDesc& L = s_list[t];
-          // 16 blocks per step: a lane never waits for a slot that a lane of the SAME step still has to fill
-          // (kPipeSlots >= 16), so the step cannot deadlock on itself whatever the reconvergence order
-          for (uint32_t base = 0; base < cntv[t]; base += 16) {
-            const uint32_t i = base + lane;
-            if (lane < 16 && i < cntv[t]) {
-              const uint32_t b = blo[t] + i;
-              const uint32_t n = n_item + i;
-              const uint32_t slot = n % kPipeSlots, round = n / kPipeSlots;
-              mbar_wait(&ps.empty[slot], (round & 1u) ^ 1u);  // free (passes at once in the first round)
+      for (uint32_t t = 0; t < S.n_lists; ++t) {
+        const ListDesc& L = s_list[t];
+        const uint32_t cnt = p_cnt[t], blo = p_blo[t];
+        // 16 blocks per step, one lane per block.  A slot frees up only when the consumers have added a whole BATCH,
+        // and that batch may contain blocks of this very step, so a lane must never make another lane wait: every
+        // lane polls its slot once per turn and issues the moment it is free.
+        for (uint32_t base = 0; base < cnt; base += 16) {
+          const uint32_t i = base + lane;
+          bool pending = lane < 16 && i < cnt;
+          const uint32_t b = blo + i;
+          const uint32_t n = n_item + i;
+          const uint32_t slot = n % kPipeSlots, round = n / kPipeSlots;
+          uint32_t turns = 0;
+          while (__ballot_sync(kFull, pending)) {
+            if (pending && mbar_try_wait(&ps.empty[slot], (round & 1u) ^ 1u)) {  // free (true at once in the first round)
+              pending = false;
               ps.blk[slot] = b;
               if (b >= L.n_blocks) {  // VInt tail: already decoded in global memory, nothing to copy
                 ps.desc[slot] = make_uint2(0xFFFFFFFFu, 0u);
@@ -1174,10 +1178,10 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
                 }
               }
             }
-            __syncwarp();
+            if (++turns > (1u << 24)) __trap();  // protocol error: fail loudly instead of hanging the device
           }
-          n_item += cntv[t];
         }
+        n_item += cnt;
       }
     }
   } else {
@@ -1197,48 +1201,81 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
       }
       if (any) {
         const uint8_t* fn_tile = s_fn + buf * kTileDocs;
-        for (uint32_t t = 0; t < S.n_lists; ++t) {
-          const uint32_t cnt = w.cnt[t];
-          if (cnt == 0) continue;
-          const ListDesc& L = s_list[t];
-          const Scorer scr = make_scorer(P, s_ql[t]);
-          const uint32_t first = w.first[t];
-          // blocks of clause t are dealt to the warps rotated by the clause ordinal
-          for (uint32_t i = (warp + kWarps - (t & (kWarps - 1))) & (kWarps - 1); i < cnt; i += kWarps) {
-            const uint32_t n = first + i;
+        // The window's blocks are taken in batches of kPipeBatch (clause order).  Phase 1, no ordering needed: the
+        // warps decode and SCORE the batch's blocks in parallel and park (slot, score) pairs in the block's own ring
+        // slot.  Phase 2, ordered: clause by clause the pairs are added to the score slots (a few instructions per
+        // posting), with a consumer barrier between clauses.  Only the cheap phase is serialised by the clause order.
+        const uint32_t n0 = w.first[0];
+        const uint32_t total = w.any;
+        for (uint32_t done = 0; done < total; done += kPipeBatch) {
+          const uint32_t nb = min(total - done, kPipeBatch);
+          for (uint32_t j = done + warp; j < done + nb; j += kWarps) {
+            uint32_t t = 0;
+            while (t + 1 < S.n_lists && j >= w.first[t + 1] - n0) ++t;  // clause of item j (first[] is non-decreasing)
+            const ListDesc& L = s_list[t];
+            const Scorer scr = make_scorer(P, s_ql[t]);
+            const uint32_t n = n0 + j;
             const uint32_t slot = n % kPipeSlots, round = n / kPipeSlots;
             mbar_wait(&ps.full[slot], round & 1u);
             const uint2 d = ps.desc[slot];
             const uint32_t b = ps.blk[slot];
+            unsigned char* sbase = s_ring + slot * kPipeSlotBytes;
             BlockFetch f;
             f.meta = d.x; f.prev = d.y;
             if (d.x != 0xFFFFFFFFu) {
               const uint32_t db = d.x & 31u, tb = (d.x >> 8) & 63u;
-              const uint4* v = reinterpret_cast<const uint4*>(s_ring + slot * kPipeSlotBytes);
+              const uint4* v = reinterpret_cast<const uint4*>(sbase);
               const uint32_t wd = (lane * db) >> 5;
               f.dlo = v[wd]; f.dhi = v[wd + 1];
               if (L.has_freq) { const uint32_t wt = db + ((lane * tb) >> 5); f.tlo = v[wt]; f.thi = v[wt + 1]; }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ps.empty[slot]);  // the slot can be refilled: everything needed is in registers
             uint32_t doc[4], tf[4];
             fetch_decode(L, b, f, lane, doc, tf);
+            __syncwarp();  // every lane has its vectors: the slot's bytes can be overwritten by the pairs
+            uint16_t* pslot = reinterpret_cast<uint16_t*>(sbase);
+            float* pscore = reinterpret_cast<float*>(sbase + 256);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
+              uint16_t s16 = 0xFFFFu;
+              float sc = 0.0f;
               if (doc[k4] >= lo && doc[k4] < hi) {
                 const uint32_t slot_d = doc[k4] - lo;
                 const uint32_t id = staged_fn ? (uint32_t)fn_tile[slot_d] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[k4]) : 1u);
-                s_acc[slot_d] = __fadd_rn(s_acc[slot_d], bm25_score_id(scr, id, tf[k4]));
+                sc = bm25_score_id(scr, id, tf[k4]);
+                s16 = (uint16_t)slot_d;
               }
+              pslot[lane * 4 + k4] = s16;
+              pscore[lane * 4 + k4] = sc;
             }
           }
-          pipe_consumer_sync();  // clause order is the f32 summation order
+          pipe_consumer_sync();  // all pairs of the batch are parked
+          for (uint32_t t = 0; t < S.n_lists; ++t) {
+            if (w.cnt[t] == 0) continue;
+            const uint32_t c_lo = w.first[t] - n0, c_hi = c_lo + w.cnt[t];
+            const uint32_t j_lo = max(c_lo, done), j_hi = min(c_hi, done + nb);
+            if (j_lo >= j_hi) continue;  // clause not in this batch (uniform across the consumers)
+            for (uint32_t j = j_lo + ((warp + kWarps - (j_lo & (kWarps - 1))) & (kWarps - 1)); j < j_hi; j += kWarps) {
+              // j % kWarps == warp: the warp that parked the pairs also adds them and then frees the slot
+              const uint32_t n = n0 + j;
+              const uint32_t slot = n % kPipeSlots;
+              const unsigned char* sbase = s_ring + slot * kPipeSlotBytes;
+              const ushort4 s4 = reinterpret_cast<const ushort4*>(sbase)[lane];
+              const float4 v4 = reinterpret_cast<const float4*>(sbase + 256)[lane];
+              if (s4.x != 0xFFFFu) s_acc[s4.x] = __fadd_rn(s_acc[s4.x], v4.x);
+              if (s4.y != 0xFFFFu) s_acc[s4.y] = __fadd_rn(s_acc[s4.y], v4.y);
+              if (s4.z != 0xFFFFu) s_acc[s4.z] = __fadd_rn(s_acc[s4.z], v4.z);
+              if (s4.w != 0xFFFFu) s_acc[s4.w] = __fadd_rn(s_acc[s4.w], v4.w);
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&ps.empty[slot]);
+            }
+            pipe_consumer_sync();  // clause order is the f32 summation order
+          }
         }
         // ---- harvest (same as k_or, consumers only) -----------------------------------------------------------
         const unsigned long long theta = *T.theta;
         const float theta_f = threshold_score((uint32_t)(theta >> 32));
         uint32_t passmask = 0;
-#pragma unroll
+#pragma unroll 1
         for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
           const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
           const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
@@ -1261,8 +1298,9 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
         if (lane == 0 && wsum) atomicAdd(&s_npass, wsum);
         pipe_consumer_sync();
         const bool fits = *T.count + s_npass <= kCap;
+        pipe_consumer_sync();  // every consumer has read the count before anyone starts pushing (the branch must be uniform)
         if (fits) {
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
             const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
             const uint32_t sub = (passmask >> (j * 4)) & 15u;
@@ -1277,6 +1315,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
           topk_round_end(T, Q.k, &qs->theta);
         } else {  // cold start: go in rounds with compaction between
           topk_round_end(T, Q.k, &qs->theta);
+#pragma unroll 1
           for (int j = 0; j < (int)(kTileDocs / (kThreads * 4)); ++j) {
             const uint32_t idx = (j * kThreads + threadIdx.x) * 4;
             const float4 v = *reinterpret_cast<const float4*>(s_acc + idx);
@@ -1302,7 +1341,7 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_or_pipe(const BatchParams P
 // ---- final per-query selection -----------------------------------------------------------------------------
 // Keys: a = score_key:32 | (0xFFFFFFFF - segment_ord):32, b = ~doc; descending (a, b) is
 // (score desc, segment_ord asc, doc asc) = compare_for_top_k (top_score_collector.rs:591-600).
-__device__ void sort_pairs_desc(unsigned long long* a, uint32_t* b, unsigned n) {
+__device__ __noinline__ void sort_pairs_desc(unsigned long long* a, uint32_t* b, unsigned n) {
   unsigned size = 2;
   while (size < n) size <<= 1;
   for (unsigned i = threadIdx.x; i < size; i += blockDim.x)
