@@ -729,6 +729,7 @@ struct StripWarpFixed {  // per warp, dynamic shared memory; followed by n_cache
   uint8_t fn[kWin];
   uint32_t cur[kStripMaxLists];       // thick: first block that can still matter; thin: block held in the cache
   uint32_t next_doc[kStripMaxLists];  // thin: smallest cached doc not applied yet (kNoDoc: clause exhausted)
+  uint32_t pos[kStripMaxLists];       // thin: its index in the cached block (entries are in doc order)
 };
 struct StripCache {
   uint32_t doc[128];
@@ -824,14 +825,18 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           const Scorer sc = make_scorer(P, s_ql[t]);
           uint32_t doc[4], tf[4];
           decode_block(L, j, lane, doc, tf);
+          uint32_t below = 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const bool valid = doc[i] < S.max_doc;
             cc.doc[lane * 4 + i] = valid ? doc[i] : kNoDoc;
             cc.score[lane * 4 + i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
             if (valid && doc[i] >= lo0) nd = min(nd, doc[i]);
+            below += (valid && doc[i] < lo0) ? 1u : 0u;
           }
           nd = warp_min(nd);
+          below = __reduce_add_sync(kFull, below);  // entries before the strip: already behind the cursor
+          if (lane == 0) W.pos[t] = below;
         }
         if (lane == 0) { W.cur[t] = j; W.next_doc[t] = nd; }
       }
@@ -864,7 +869,8 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
         dst[lane + 32] = __ldg(src + lane + 32);
         __syncwarp();
       }
-      uint32_t touched = 0;  // which 128-slot groups of the window received a score
+      bool dirty = false;   // the window received at least one score
+      float wmax = 0.0f;    // largest partial sum written by this lane (scores are non-negative: it bounds the final sums)
       for (uint32_t t = 0; t < S.n_lists; ++t) {
         const ListDesc& L = s_list[t];
         const bool thin = (s_ql[t].pad & 1u) != 0;
@@ -892,6 +898,7 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           if (rec.w != 0xFFFFFFFFu && rec.w + 1u >= hi) continue;  // the block starts at or after the window's end
           BlockFetch f;
           fetch_issue_rec(L, rec, lane, f);
+          dirty = true;
           for (;;) {
             uint32_t doc[4], tf[4];
             fetch_decode(L, j, f, lane, doc, tf);
@@ -913,8 +920,9 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
               if (doc[i] >= lo && doc[i] < hi) {
                 const uint32_t slot = doc[i] - lo;
                 const uint32_t id = staged_fn ? (uint32_t)W.fn[slot] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[i]) : 1u);
-                W.acc[slot] = __fadd_rn(W.acc[slot], bm25_score_id(sc, id, tf[i]));
-                touched |= 1u << (slot >> 7);
+                const float nv = __fadd_rn(W.acc[slot], bm25_score_id(sc, id, tf[i]));
+                W.acc[slot] = nv;
+                wmax = fmaxf(wmax, nv);
               }
             }
             if (!more) break;
@@ -924,23 +932,28 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           // ---- thin clause: the decoded block lives in shared memory ---------------------------------------
           StripCache& cc = C[s_ql[t].pad >> 1];
           for (;;) {
-            const uint32_t nd = W.next_doc[t];
-            if (nd >= hi) break;  // nothing of this clause in the window (also: clause exhausted)
-            uint32_t mn = kNoDoc;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint32_t d = cc.doc[lane * 4 + i];
-              if (d >= lo && d < hi) {
-                const uint32_t slot = d - lo;
-                W.acc[slot] = __fadd_rn(W.acc[slot], cc.score[lane * 4 + i]);
-                touched |= 1u << (slot >> 7);
-              } else if (d >= hi && d != kNoDoc) {
-                mn = min(mn, d);
-              }
+            if (W.next_doc[t] >= hi) break;  // nothing of this clause in the window (also: clause exhausted)
+            // entries are in doc order: the window's postings are the next few entries, one per lane
+            uint32_t pos = W.pos[t];
+            const uint32_t e = pos + lane;
+            const uint32_t d = e < 128u ? cc.doc[e] : kNoDoc;
+            const bool in = d < hi;  // d >= lo: everything before the cursor is consumed
+            const uint32_t napp = (uint32_t)__popc(__ballot_sync(kFull, in));
+            if (in) {
+              const uint32_t slot = d - lo;
+              const float nv = __fadd_rn(W.acc[slot], cc.score[e]);
+              W.acc[slot] = nv;
+              wmax = fmaxf(wmax, nv);
             }
-            mn = warp_min(mn);
+            dirty = true;
+            pos += napp;
+            const uint32_t nxt = napp < 32u ? __shfl_sync(kFull, d, napp) : (pos < 128u ? cc.doc[pos] : kNoDoc);
             __syncwarp();
-            if (mn != kNoDoc) { if (lane == 0) W.next_doc[t] = mn; __syncwarp(); break; }
+            if (nxt != kNoDoc) {  // the block still holds unread docs (in this window only if all 32 lanes applied)
+              if (lane == 0) { W.pos[t] = pos; W.next_doc[t] = nxt; }
+              __syncwarp();
+              continue;
+            }
             // block used up: bring in the next one
             const uint32_t jb = W.cur[t] + 1u;
             if (jb >= L.n_total) { if (lane == 0) W.next_doc[t] = kNoDoc; __syncwarp(); break; }
@@ -956,22 +969,25 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
               if (valid) first = min(first, doc[i]);
             }
             first = warp_min(first);
-            if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; }
+            if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; W.pos[t] = 0; }
             __syncwarp();
           }
         }
       }
-      // ---- harvest the groups that were touched --------------------------------------------------------------
-      touched = __reduce_or_sync(kFull, touched);
-      if (touched) {
+      // ---- harvest -----------------------------------------------------------------------------------------------
+      if (dirty) {
         const float theta_f = threshold_score((uint32_t)(theta >> 32));
+        // the largest partial sum any lane wrote bounds every final score of the window (scores >= 0; a negative
+        // one makes the uint compare fail safe): when it is below the threshold the window is only cleared
+        const uint32_t mx = __reduce_max_sync(kFull, __float_as_uint(wmax));
+        const bool may_pass = !(theta_f > 0.0f) || mx >= __float_as_uint(theta_f);
         for (uint32_t g = 0; g < kWin / 128; ++g) {
-          if (!((touched >> g) & 1u)) continue;
           const uint32_t idx = g * 128 + lane * 4;
-          const float4 v = *reinterpret_cast<const float4*>(W.acc + idx);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (may_pass) v = *reinterpret_cast<const float4*>(W.acc + idx);
           *reinterpret_cast<float4*>(W.acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
           // float test first (nearly everything fails it); keys are built for the survivors only
-          if (__ballot_sync(kFull, v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f)) {
+          if (may_pass && __ballot_sync(kFull, v.x >= theta_f || v.y >= theta_f || v.z >= theta_f || v.w >= theta_f)) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
