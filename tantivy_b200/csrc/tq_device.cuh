@@ -148,6 +148,14 @@ __device__ __forceinline__ uint32_t warp_min(uint32_t v) {
 // 16-byte vector w.  Lane L takes values 4L..4L+3 = row L of the four streams = ONE vector (plus the next one
 // when the field straddles a word).  Blocks are 16-byte aligned in the cached copy, so these are plain
 // LDG.128; a warp's 32 loads cover the block's b vectors contiguously.
+// Packed posting vectors are read exactly once: fetch them around L1 so that they do not evict what IS re-used
+// there (the tf-factor table, block records, fieldnorm lines).
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 struct BlockFetch {
   uint4 dlo, dhi, tlo, thi;
   uint32_t meta;  // 0xFFFFFFFF marks the VInt tail pseudo block
@@ -162,12 +170,12 @@ __device__ __forceinline__ void fetch_issue(const ListDesc& L, uint32_t b, uint3
   const uint32_t db = rec.y & 31u, tb = (rec.y >> 8) & 63u;
   const uint4* v = reinterpret_cast<const uint4*>(L.blocks + rec.x);
   const uint32_t wd = (lane * db) >> 5;
-  f.dlo = __ldg(v + wd);
-  f.dhi = __ldg(v + wd + 1);  // may belong to the next field/block; masked out when not needed (copy is padded)
+  f.dlo = ldg_stream(v + wd);
+  f.dhi = ldg_stream(v + wd + 1);  // may belong to the next field/block; masked out when not needed (copy is padded)
   if (L.has_freq) {
     const uint32_t wt = db + ((lane * tb) >> 5);
-    f.tlo = __ldg(v + wt);
-    f.thi = __ldg(v + wt + 1);
+    f.tlo = ldg_stream(v + wt);
+    f.thi = ldg_stream(v + wt + 1);
   }
 }
 

@@ -724,7 +724,7 @@ constexpr uint32_t kStripMaxK = 128;
 constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
 
 struct StripWarpFixed {  // per warp, dynamic shared memory; followed by n_cached x StripCache
-  float acc[kWin];
+  float acc[kWin + 128];              // + 4 private dummy slots per lane for postings outside the window
   unsigned long long keys[kWBuf];
   uint8_t fn[kWin];
   uint32_t cur[kStripMaxLists];       // thick: first block that can still matter; thin: block held in the cache
@@ -746,12 +746,12 @@ __device__ __forceinline__ void fetch_issue_rec(const ListDesc& L, const uint4 r
   const uint32_t db = rec.z & 31u, tb = (rec.z >> 8) & 63u;
   const uint4* v = reinterpret_cast<const uint4*>(L.blocks + rec.y);
   const uint32_t wd = (lane * db) >> 5;
-  f.dlo = __ldg(v + wd);
-  f.dhi = __ldg(v + wd + 1);
+  f.dlo = ldg_stream(v + wd);
+  f.dhi = ldg_stream(v + wd + 1);
   if (L.has_freq) {
     const uint32_t wt = db + ((lane * tb) >> 5);
-    f.tlo = __ldg(v + wt);
-    f.thi = __ldg(v + wt + 1);
+    f.tlo = ldg_stream(v + wt);
+    f.thi = ldg_stream(v + wt + 1);
   }
 }
 
@@ -915,15 +915,40 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
               rec.z = __shfl_sync(kFull, r.z, src); rec.w = __shfl_sync(kFull, r.w, src);
               fetch_issue_rec(L, rec, lane, f);
             }
+            // Branch-free: the four postings of a lane form four independent load chains (fieldnorm byte -> factor
+            // table -> score slot) that overlap instead of running one after the other behind divergent branches.
+            // Postings outside the window are steered to a private dummy slot behind the window.
+            bool in[4];
+            uint32_t slot[4];
+            float fac[4];
+            bool big = false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (doc[i] >= lo && doc[i] < hi) {
-                const uint32_t slot = doc[i] - lo;
-                const uint32_t id = staged_fn ? (uint32_t)W.fn[slot] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[i]) : 1u);
-                const float nv = __fadd_rn(W.acc[slot], bm25_score_id(sc, id, tf[i]));
-                W.acc[slot] = nv;
-                wmax = fmaxf(wmax, nv);
+              in[i] = doc[i] >= lo && doc[i] < hi;
+              slot[i] = in[i] ? doc[i] - lo : kWin + lane * 4u + (uint32_t)i;
+              const uint32_t id = staged_fn ? (uint32_t)W.fn[in[i] ? slot[i] : 0u]
+                                            : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + (in[i] ? doc[i] : 0u)) : 1u);
+              const uint32_t tfc = min(tf[i], kTfRows - 1u);
+              fac[i] = __ldg(sc.tf_table + (tfc << 8) + id);
+              big |= in[i] && tf[i] >= kTfRows;
+            }
+            if (__ballot_sync(kFull, big)) {  // a term frequency beyond the table: take the divide for those
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (in[i] && tf[i] >= kTfRows) {
+                  const uint32_t id = staged_fn ? (uint32_t)W.fn[slot[i]] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[i]) : 1u);
+                  fac[i] = bm25_factor_large_tf(sc.cache, id, tf[i]);
+                }
               }
+            }
+            float a[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = W.acc[slot[i]];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float nv = __fadd_rn(a[i], __fmul_rn(sc.weight, fac[i]));
+              W.acc[slot[i]] = nv;
+              wmax = in[i] ? fmaxf(wmax, nv) : wmax;
             }
             if (!more) break;
           }
