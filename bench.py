@@ -320,11 +320,14 @@ def main():
         dominant = max(op_ms, key=op_ms.get)
         alg_bytes = stats["bytes_" + dominant]
         achieved = alg_bytes / (op_ms[dominant] * 1e-3) / 1e9 if op_ms[dominant] > 0 else 0.0
+        kernel_name = "k_" + dominant
+        if dominant == "or" and stats.get("units_or_strip", 0) * 2 > stats["units_or"]:
+            kernel_name = "k_or_strip"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("k_" + dominant)
-        roofline = {"bound": "hbm", "kernel": "k_" + dominant, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(kernel_name)
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": op_ms[dominant],
                     "postings_per_launch": stats["postings"], "kernel_ms_per_step": {k2: float(np.mean(v)) for k2, v in kern.items()}}

@@ -105,6 +105,7 @@ typedef struct {
    * MaxScore route, 3 ..and had no promising doc, 4 essential-list overflow, 5 promising overflow,
    * 6 promising docs scored exactly, 7 essential postings scored */
   uint64_t or_windows[8];
+  uint64_t units_or_strip; /* of units_or: CTAs of the barrier-free strip kernel (k_or_strip); the rest ran k_or / k_or_pipe */
 } tq_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

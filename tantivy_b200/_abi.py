@@ -84,6 +84,7 @@ class Stats(C.Structure):
         ("bytes_and", C.c_uint64),
         ("bytes_or", C.c_uint64),
         ("or_windows", C.c_uint64 * 8),
+        ("units_or_strip", C.c_uint64),
     ]
 
 

@@ -634,7 +634,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
-  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size();
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size(); b->stats.units_or_strip = units[3].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
