@@ -27,7 +27,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr uint32_t kCap = 2048;               // CTA candidate buffer (u64 keys), power of two
 constexpr uint32_t kRoundMargin = kWarps * 128;  // most keys one round of 8 warps can push
 constexpr uint32_t kTileDocs = 8192;          // OR: doc-id tile width held in shared memory
-constexpr uint32_t kTfRows = 16;              // term frequencies below this use the precomputed factor table
+constexpr uint32_t kTfRows = 17;              // term frequencies below this use the precomputed factor table (tf_bits <= 4 => tf <= 16)
 
 // One posting list of one (segment, field, term), device resident.  Built once per term by
 // k_build_tables from the raw tantivy bytes and cached for the life of the segment (segments

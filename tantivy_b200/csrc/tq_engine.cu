@@ -508,10 +508,12 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
           // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
           uint32_t n_thin = 0;
-          for (auto& h : here) if ((uint64_t)h.first * (kWin / 128u) < qs.max_doc) ++n_thin;
+          static const uint64_t thin_mult = env_u32("TQ_STRIP_THIN_MULT", 1u);
+          auto is_thin = [&](uint32_t df) { return (uint64_t)df * (kWin / 128u) < (uint64_t)qs.max_doc * thin_mult; };
+          for (auto& h : here) if (is_thin(h.first)) ++n_thin;
           if (n_thin <= kMaxCached) {
             uint32_t slot = 0;
-            for (auto& h : here) h.second.pad = ((uint64_t)h.first * (kWin / 128u) < qs.max_doc) ? (1u | (slot++ << 1)) : 0u;
+            for (auto& h : here) h.second.pad = is_thin(h.first) ? (1u | (slot++ << 1)) : 0u;
             strip_cached_max = std::max(strip_cached_max, n_thin);
             unit_class = 3;
           }

@@ -724,7 +724,7 @@ constexpr uint32_t kStripMaxK = 128;
 constexpr uint32_t kNoDoc = 0xFFFFFFFFu;
 
 struct StripWarpFixed {  // per warp, dynamic shared memory; followed by n_cached x StripCache
-  float acc[kWin + 128];              // + 4 private dummy slots per lane for postings outside the window
+  float acc[kWin + 32];               // + one private dummy slot per lane for postings outside the window
   unsigned long long keys[kWBuf];
   uint8_t fn[kWin];
   uint32_t cur[kStripMaxLists];       // thick: first block that can still matter; thin: block held in the cache
@@ -826,14 +826,18 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           uint32_t doc[4], tf[4];
           decode_block(L, j, lane, doc, tf);
           uint32_t below = 0;
+          uint32_t cd[4];
+          float cs[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const bool valid = doc[i] < S.max_doc;
-            cc.doc[lane * 4 + i] = valid ? doc[i] : kNoDoc;
-            cc.score[lane * 4 + i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+            cd[i] = valid ? doc[i] : kNoDoc;
+            cs[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
             if (valid && doc[i] >= lo0) nd = min(nd, doc[i]);
             below += (valid && doc[i] < lo0) ? 1u : 0u;
           }
+          reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);  // one conflict-free 16-B store
+          reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
           nd = warp_min(nd);
           below = __reduce_add_sync(kFull, below);  // entries before the strip: already behind the cursor
           if (lane == 0) W.pos[t] = below;
@@ -901,6 +905,7 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           dirty = true;
           for (;;) {
             uint32_t doc[4], tf[4];
+            const bool small_tf = ((f.meta >> 8) & 63u) <= 4u;  // (the VInt tail's marker reads as 63 bits)
             fetch_decode(L, j, f, lane, doc, tf);
             // the next block is needed iff this one ends before the window does
             const bool more = rec.x < hi - 1u && j + 1u < L.n_total;
@@ -917,28 +922,32 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             }
             // Branch-free: the four postings of a lane form four independent load chains (fieldnorm byte -> factor
             // table -> score slot) that overlap instead of running one after the other behind divergent branches.
-            // Postings outside the window are steered to a private dummy slot behind the window.
+            // Postings outside the window are steered to the lane's dummy slot behind the window (its value is never read back
+            // for a result: all four loads precede the four stores).
             bool in[4];
-            uint32_t slot[4];
+            uint32_t slot[4], id[4];
             float fac[4];
-            bool big = false;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               in[i] = doc[i] >= lo && doc[i] < hi;
-              slot[i] = in[i] ? doc[i] - lo : kWin + lane * 4u + (uint32_t)i;
-              const uint32_t id = staged_fn ? (uint32_t)W.fn[in[i] ? slot[i] : 0u]
-                                            : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + (in[i] ? doc[i] : 0u)) : 1u);
-              const uint32_t tfc = min(tf[i], kTfRows - 1u);
-              fac[i] = __ldg(sc.tf_table + (tfc << 8) + id);
-              big |= in[i] && tf[i] >= kTfRows;
+              slot[i] = in[i] ? doc[i] - lo : kWin + lane;
+              id[i] = staged_fn ? (uint32_t)W.fn[in[i] ? slot[i] : 0u]
+                                : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + (in[i] ? doc[i] : 0u)) : 1u);
             }
-            if (__ballot_sync(kFull, big)) {  // a term frequency beyond the table: take the divide for those
+            if (small_tf) {  // tf_bits <= 4: every term frequency of the block is inside the factor table
+#pragma unroll
+              for (int i = 0; i < 4; ++i) fac[i] = __ldg(sc.tf_table + (tf[i] << 8) + id[i]);
+            } else {
+              bool big = false;
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                if (in[i] && tf[i] >= kTfRows) {
-                  const uint32_t id = staged_fn ? (uint32_t)W.fn[slot[i]] : (L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + doc[i]) : 1u);
-                  fac[i] = bm25_factor_large_tf(sc.cache, id, tf[i]);
-                }
+                fac[i] = __ldg(sc.tf_table + (min(tf[i], kTfRows - 1u) << 8) + id[i]);
+                big |= in[i] && tf[i] >= kTfRows;
+              }
+              if (__ballot_sync(kFull, big)) {  // a term frequency beyond the table: take the divide for those
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (in[i] && tf[i] >= kTfRows) fac[i] = bm25_factor_large_tf(sc.cache, id[i], tf[i]);
               }
             }
             float a[4];
@@ -986,13 +995,17 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             uint32_t doc[4], tf[4];
             decode_block(L, jb, lane, doc, tf);
             uint32_t first = kNoDoc;
+            uint32_t cd[4];
+            float cs[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const bool valid = doc[i] < S.max_doc;
-              cc.doc[lane * 4 + i] = valid ? doc[i] : kNoDoc;
-              cc.score[lane * 4 + i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+              cd[i] = valid ? doc[i] : kNoDoc;
+              cs[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
               if (valid) first = min(first, doc[i]);
             }
+            reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);
+            reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
             first = warp_min(first);
             if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; W.pos[t] = 0; }
             __syncwarp();
