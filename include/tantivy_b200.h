@@ -73,7 +73,12 @@ typedef struct {
  * weight[i]        = Bm25Weight.weight = idf * (1 + K1) * boost        (bm25.rs:141-151)
  * avg_fieldnorm[i] = Bm25Weight.average_fieldnorm of clause i's field; the 256-entry tf
  *                    cache is recomputed from it exactly as bm25.rs:56-69 does.
- * tf_cache         = optional explicit caches [n_terms][256]; overrides avg_fieldnorm. */
+ * tf_cache         = optional explicit caches [n_terms][256]; overrides avg_fieldnorm.
+ * term_flags       = optional [n_terms] bytes (NULL = all 0).  TQ_TERM_IGNORE_FREQ: the clause is a
+ *                    TermQuery::new(term, IndexRecordOption::Basic) on a field indexed WITH term
+ *                    frequencies: the reference then skips the tf blocks and scores with tf = 1
+ *                    (FreqReadingOption::SkipFreq, block_segment_postings.rs:97-140,343-360). */
+#define TQ_TERM_IGNORE_FREQ 1u
 typedef struct {
   int32_t op;
   uint32_t n_terms;
@@ -83,6 +88,7 @@ typedef struct {
   const float* weight;
   const float* avg_fieldnorm;
   const float* tf_cache;
+  const uint8_t* term_flags;
 } tq_query;
 
 /* Counters of the last finished batch (per ctx). */

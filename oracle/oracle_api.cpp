@@ -30,12 +30,12 @@ struct tqo_index {
   std::string err;
 };
 
-static TermScorer make_term_scorer(const OSegment& seg, const tq_term_seg& ts, const Bm25Weight& w, uint32_t clause) {
+static TermScorer make_term_scorer(const OSegment& seg, const tq_term_seg& ts, const Bm25Weight& w, uint32_t clause, bool basic_requested = false) {
   TermScorer t;
   const uint8_t* base = seg.idx_body.data() + 8 + ts.postings_start;
   const size_t len = (size_t)(ts.postings_end - ts.postings_start);
   // read_postings_from_terminfo(term_info, option).downgrade(record_option): request freqs if available
-  IndexRecordOption requested = seg.record_option == Basic ? Basic : WithFreqs;
+  IndexRecordOption requested = (seg.record_option == Basic || basic_requested) ? Basic : WithFreqs;
   t.postings.block_cursor = BlockSegmentPostings::open(ts.doc_freq, base, len, seg.record_option, requested);
   t.postings.cur = 0;
   t.fieldnorm_reader = seg.has_fieldnorm ? FieldNormReader::from_data(seg.fieldnorm.data(), seg.max_doc)
@@ -75,7 +75,7 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
       continue;
     }
     const OSegment& s = ix.segs.at({per_term[t]->segment_ord, per_term[t]->field});
-    scorers.push_back(make_term_scorer(s, *per_term[t], weight_for(q, t), t));
+    scorers.push_back(make_term_scorer(s, *per_term[t], weight_for(q, t), t, q.term_flags && (q.term_flags[t] & TQ_TERM_IGNORE_FREQ)));
   }
   if (scorers.empty()) return;
   TopNHeap top_n(q.k);

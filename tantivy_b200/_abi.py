@@ -13,6 +13,7 @@ TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR = 0, 1, 2
 TERMINATED = 0x7FFFFFFF
 TQ_MAX_K = 1024
 TQ_MAX_TERMS = 32
+TQ_TERM_IGNORE_FREQ = 1
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -50,14 +51,15 @@ class Query(C.Structure):
         ("weight", f32p),
         ("avg_fieldnorm", f32p),
         ("tf_cache", f32p),
+        ("term_flags", u8p),
     ]
 
 
 QUERY_DTYPE = np.dtype(
     [("op", "<i4"), ("n_terms", "<u4"), ("k", "<u4"), ("n_term_segs", "<u4"),
-     ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8")]
+     ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8"), ("term_flags", "<u8")]
 )
-assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 48
+assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 56
 
 
 class Stats(C.Structure):
@@ -101,7 +103,7 @@ class QueryBatch:
     `queries` is an iterable of dicts / objects with fields
       op, k, weights[n_terms], avg_fieldnorm[n_terms], term_segs: list of
       (term_idx, segment_ord, field, doc_freq, postings_start, postings_end),
-      tf_cache (optional [n_terms,256]).
+      tf_cache (optional [n_terms,256]), term_flags (optional [n_terms] bytes, TQ_TERM_IGNORE_FREQ).
     Built with numpy so that a batch of thousands of queries marshals in milliseconds.
     """
 
@@ -147,6 +149,11 @@ class QueryBatch:
                 cache = np.ascontiguousarray(cache, dtype=np.float32).reshape(nt, 256)
                 self.caches.append(cache)
                 row["tf_cache"] = cache.ctypes.data
+            flags = q.get("term_flags")
+            if flags is not None:
+                flags = np.ascontiguousarray(flags, dtype=np.uint8).reshape(nt)
+                self.caches.append(flags)
+                row["term_flags"] = flags.ctypes.data
             self.kmax = max(self.kmax, int(q["k"]))
             its += len(ts)
             iw += nt

@@ -73,7 +73,7 @@ struct Segment {
 
 struct ListKey {
   uint32_t segment_ord, field;
-  uint64_t postings_start;
+  uint64_t postings_start;  // bit 63: the table was built with term frequencies ignored (TQ_TERM_IGNORE_FREQ)
   bool operator==(const ListKey& o) const { return segment_ord == o.segment_ord && field == o.field && postings_start == o.postings_start; }
 };
 struct ListKeyHash {
@@ -293,14 +293,15 @@ namespace {
 struct PendingBuild { BuildJob job; ListDesc desc; };
 
 // Looks a posting list up in the cache or schedules its table build. ctx->mu held.
-int get_list(tq_ctx* c, const tq_term_seg& ts, std::vector<PendingBuild>& pending, uint32_t* list_id, const Segment** seg_out) {
+int get_list(tq_ctx* c, const tq_term_seg& ts, bool ignore_freq, std::vector<PendingBuild>& pending, uint32_t* list_id, const Segment** seg_out) {
   auto sit = c->segments.find({ts.segment_ord, ts.field});
   if (sit == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "term_seg names a segment/field that is not registered");
   const Segment& seg = sit->second;
   *seg_out = &seg;
   if (ts.postings_end < ts.postings_start || ts.postings_end + 8 > seg.idx_len) return fail(TQ_ERR_INVALID_ARGUMENT, "postings range outside the field body");
   if (ts.postings_end - ts.postings_start > 0xFFFFFFFFull) return fail(TQ_ERR_UNSUPPORTED, "posting list larger than 4 GiB");
-  const ListKey key{ts.segment_ord, ts.field, ts.postings_start};
+  ignore_freq = ignore_freq && seg.record_option != 0;
+  const ListKey key{ts.segment_ord, ts.field, ts.postings_start | (ignore_freq ? 1ull << 63 : 0ull)};
   auto it = c->list_cache.find(key);
   if (it != c->list_cache.end()) { *list_id = it->second; return TQ_OK; }
   if (c->n_lists >= c->lists_cap) return fail(TQ_ERR_OOM, "posting-list table cache full (TQ_MAX_LISTS)");
@@ -326,7 +327,7 @@ int get_list(tq_ctx* c, const tq_term_seg& ts, std::vector<PendingBuild>& pendin
   pb.job.bytes = seg.d_idx + 8 + ts.postings_start;
   pb.job.len = (uint32_t)(ts.postings_end - ts.postings_start);
   pb.job.doc_freq = ts.doc_freq;
-  pb.job.record_option = (uint32_t)seg.record_option;
+  pb.job.record_option = (uint32_t)seg.record_option | (ignore_freq ? 0x100u : 0u);
   pb.job.list_id = c->n_lists;
   *list_id = c->n_lists++;
   c->list_cache.emplace(key, *list_id);
@@ -489,7 +490,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         bool uniform_fn = true;
         for (size_t a = i; a < j; ++a) {
           uint32_t id;
-          int rc = get_list(c, *order[a], pending, &id, &seg);
+          int rc = get_list(c, *order[a], q.term_flags && (q.term_flags[order[a]->term_idx] & TQ_TERM_IGNORE_FREQ), pending, &id, &seg);
           if (rc != TQ_OK) return rc;
           if (a == i) fn0 = seg->d_fieldnorm; else uniform_fn &= (seg->d_fieldnorm == fn0);
           QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
@@ -766,7 +767,7 @@ static int resolve_single(tq_ctx* c, const tq_term_seg* list, uint32_t* id) {
   std::vector<PendingBuild> pending;
   const Segment* seg;
   uint64_t built = 0;
-  int rc = get_list(c, *list, pending, id, &seg);
+  int rc = get_list(c, *list, false, pending, id, &seg);
   if (rc != TQ_OK) return rc;
   return flush_builds(c, pending, &built);
 }

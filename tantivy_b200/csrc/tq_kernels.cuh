@@ -19,7 +19,7 @@ struct BuildJob {
   const uint8_t* bytes;  // the term's postings range
   uint32_t len;
   uint32_t doc_freq;
-  uint32_t record_option;
+  uint32_t record_option;  // 0/1/2; bit 8: ignore term frequencies (score with tf = 1)
   uint32_t list_id;
 };
 
@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
   __shared__ uint32_t s_wsum[kWarps];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   if (tid == 0) {
-    uint32_t hdr = 0, skip_len = 0, rec = J.record_option == 0 ? 5u : (J.record_option == 1 ? 8u : 12u), status = 0;
+    const uint32_t ro = J.record_option & 0xFFu;
+    uint32_t hdr = 0, skip_len = 0, rec = ro == 0 ? 5u : (ro == 1 ? 8u : 12u), status = 0;
     if (J.doc_freq >= 128u) {  // split_into_skips_and_postings (block_segment_postings.rs:78-88)
       uint64_t v = 0;
       uint32_t shift = 0;
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
         }
         tail_docs[i] = result;
       }
-      const bool read_freq = (rec != 5u) && pos < remaining;  // block_segment_postings.rs:66-75
+      const bool read_freq = (rec != 5u) && pos < remaining && !(J.record_option & 0x100u);  // block_segment_postings.rs:66-75
       for (uint32_t i = 0; i < tail_n && status == 0; ++i) {
         uint32_t v = 1u;
         if (read_freq) {
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
         tab4[n_blocks] = make_uint4(tail_docs[tail_n - 1], total, 0xFFFFFFFFu, prev_last);
       }
     }
-    L.has_freq = rec != 5u;
+    L.has_freq = rec != 5u && !(J.record_option & 0x100u);  // SkipFreq: the tf bits stay in the block sizes, nobody reads them
     L.build_status = status;
   }
   // 16-byte aligned copy of the bit-packed blocks (L.blocks was pre-set by the host to an arena region of

@@ -201,6 +201,23 @@ def test_basic_record_option_and_no_fieldnorm(ctx):
     assert_same(ctx.search_batch(qb), oi.search_batch(qb, mode=0), qb.nq)
 
 
+def test_basic_option_requested_on_a_field_with_freqs(ctx):
+    """TermQuery::new(term, IndexRecordOption::Basic) on a WithFreqs field: tf blocks are skipped and
+    every posting scores with tf = 1 (FreqReadingOption::SkipFreq, block_segment_postings.rs:97-140)."""
+    rng = np.random.default_rng(650)
+    segs = _random_segments(rng, 2, 4)
+    queries = []
+    for op, terms in [(TQ_OP_TERM, [0]), (TQ_OP_TERM, [3]), (TQ_OP_AND, [0, 1]), (TQ_OP_OR, [0, 2, 3]), (TQ_OP_OR, [1, 0])]:
+        for flags in ([1] * len(terms), [1] + [0] * (len(terms) - 1)):
+            q = make_query(op, segs, terms, 25)
+            q["term_flags"] = flags
+            queries.append(q)
+    plain = make_query(TQ_OP_TERM, segs, [0], 25)  # the same list WITH freqs, in the same batch
+    g, c, nq = _run_both(ctx, segs, queries + [plain])
+    assert_same(g, c, nq)
+    assert [s for s, _, _ in hits(g, 0)] != [s for s, _, _ in hits(g, nq - 1)]  # the flag changes the scores
+
+
 def test_ties_pick_lowest_doc(ctx):
     # every doc has the same length and tf: all scores tie; the top-k must be the k lowest doc ids
     max_doc = 5000

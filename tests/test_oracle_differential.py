@@ -132,3 +132,25 @@ def test_search_block_matches_linear_scan():
             if target > int(padded[-1]):
                 continue
             assert L.tqo_search_block(O.ptr(padded, O.u32p), int(target)) == int((padded < target).sum())
+
+
+def test_basic_requested_on_freq_field_scores_with_tf_one():
+    """FreqReadingOption::SkipFreq (block_segment_postings.rs:97-140): the Basic-requested scores of a
+    WithFreqs list equal the scores of the same docs written with every tf = 1."""
+    rng = np.random.default_rng(11)
+    max_doc = 3000
+    fieldnorms = rng.integers(1, 300, size=max_doc)
+    docs = np.sort(rng.choice(max_doc, size=700, replace=False)).astype(np.uint32)  # 5 blocks + a VInt tail
+    tfs = rng.integers(1, 9, size=len(docs)).astype(np.uint32)
+    with_tf = OracleSegment([(docs, tfs)], fieldnorms, segment_ord=0)
+    ones = OracleSegment([(docs, np.ones_like(tfs))], fieldnorms, segment_ord=0)
+    out = []
+    for seg, flags in ((with_tf, [1]), (ones, None), (with_tf, None)):
+        ix = O.OracleIndex()
+        seg.register(ix)
+        q = make_query(TQ_OP_TERM, [seg], [0], 50)
+        if flags:
+            q["term_flags"] = flags
+        out.append([hits(ix.search_batch(QueryBatch([q]), mode=m)) for m in (0, 1)])
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert out[0][0] != out[2][0]
