@@ -1,0 +1,813 @@
+// tantivy_host.hpp — host-side mirror, in C++, of the reference's search API for the accelerated path.
+//
+// The reference is Rust and no Rust toolchain exists in the build image, so the code that would sit in
+// the reference above the C ABI is written here with the reference's names, argument
+// meaning and error behaviour, so that tests/cpp/host_mirror_tests.cpp reads like the reference's own tests:
+//
+//   Schema / SchemaBuilder / TEXT / STRING      src/schema/schema.rs, src/schema/text_options.rs:264-285
+//   Term::from_field_text                        src/schema/term.rs
+//   Index::create_in_ram, IndexWriter            src/index/index.rs, src/indexer/index_writer.rs (add_document,
+//                                                delete_term, commit — one segment per commit, single thread)
+//   IndexReader::searcher, Searcher              src/core/searcher.rs:133-141,180-237 (search, doc_freq, num_docs)
+//   TermQuery, BooleanQuery, BoostQuery, Occur   src/query/term_query/term_query.rs, boolean_query/boolean_query.rs,
+//                                                src/query/boost_query.rs
+//   TopDocs::with_limit(..).and_offset(..)       src/collector/top_score_collector.rs:61-64,93-96,226-228
+//   QueryParser (terms, +must, field:term only)  src/query/query_parser/query_parser.rs
+//   CompositeFile / Footer readers (N1)          src/directory/composite_file.rs:111-170, src/directory/footer.rs
+//
+// Everything the hot path does — block decode, AND/OR, BM25, top-k, merge — happens behind
+// tq_search_batch (include/tantivy_b200.h).  There is NO CPU search path in this file: a query shape the
+// device path does not cover raises TantivyError (the reference-side shim would delegate those to
+// Searcher::search, boolean_weight.rs:595-597), and a machine without a CUDA device raises on first search.
+// The indexing side (tokenizer -> postings -> segment bytes) is host code, as in the reference; it exists so
+// that tests and examples can build real segments without the Rust crate.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/tantivy_b200.h"
+#include "../csrc/bm25_host.hpp"
+#include "../csrc/segment_writer.hpp"
+
+namespace tantivy_b200 {
+
+using DocId = uint32_t;
+using Score = float;
+using SegmentOrdinal = uint32_t;
+using Opstamp = uint64_t;
+
+// ---- errors (src/error.rs: TantivyError::{InvalidArgument, SchemaError, SystemError, ...}) --------------------
+class TantivyError : public std::runtime_error {
+ public:
+  enum Kind { InvalidArgument, SchemaError, DataCorruption, SystemError, Unsupported };
+  TantivyError(Kind kind, const std::string& msg) : std::runtime_error(msg), kind_(kind) {}
+  Kind kind() const { return kind_; }
+
+ private:
+  Kind kind_;
+};
+
+// ---- schema ------------------------------------------------------------------------------------------------
+enum class IndexRecordOption { Basic = 0, WithFreqs = 1, WithFreqsAndPositions = 2 };
+
+struct TextFieldIndexing {
+  std::string tokenizer = "default";
+  bool fieldnorms = true;
+  IndexRecordOption record = IndexRecordOption::Basic;
+  TextFieldIndexing set_tokenizer(const std::string& t) const { auto c = *this; c.tokenizer = t; return c; }
+  TextFieldIndexing set_fieldnorms(bool f) const { auto c = *this; c.fieldnorms = f; return c; }
+  TextFieldIndexing set_index_option(IndexRecordOption r) const { auto c = *this; c.record = r; return c; }
+};
+struct TextOptions {
+  std::optional<TextFieldIndexing> indexing;
+  TextOptions set_indexing_options(const TextFieldIndexing& i) const { auto c = *this; c.indexing = i; return c; }
+};
+// text_options.rs:264-285
+inline const TextOptions STRING{TextFieldIndexing{"raw", true, IndexRecordOption::Basic}};
+inline const TextOptions TEXT{TextFieldIndexing{"default", true, IndexRecordOption::WithFreqsAndPositions}};
+
+struct Field {
+  uint32_t id = 0;
+  uint32_t field_id() const { return id; }
+  bool operator==(const Field& o) const { return id == o.id; }
+  bool operator<(const Field& o) const { return id < o.id; }
+};
+struct FieldEntry {
+  std::string name;
+  TextOptions options;
+};
+class Schema {
+ public:
+  std::optional<Field> get_field(const std::string& name) const {
+    for (uint32_t i = 0; i < entries_.size(); ++i)
+      if (entries_[i].name == name) return Field{i};
+    return std::nullopt;
+  }
+  const FieldEntry& get_field_entry(Field f) const {
+    if (f.id >= entries_.size()) throw TantivyError(TantivyError::SchemaError, "field does not exist");
+    return entries_[f.id];
+  }
+  size_t num_fields() const { return entries_.size(); }
+
+ private:
+  friend class SchemaBuilder;
+  std::vector<FieldEntry> entries_;
+};
+class SchemaBuilder {
+ public:
+  Field add_text_field(const std::string& name, const TextOptions& options) {
+    for (auto& e : schema_.entries_)
+      if (e.name == name) throw TantivyError(TantivyError::SchemaError, "field already exists: " + name);
+    schema_.entries_.push_back({name, options});
+    return Field{(uint32_t)schema_.entries_.size() - 1};
+  }
+  Schema build() { return schema_; }
+
+ private:
+  Schema schema_;
+};
+
+struct Term {
+  Field field_;
+  std::string text_;
+  static Term from_field_text(Field field, const std::string& text) { return Term{field, text}; }
+  Field field() const { return field_; }
+  const std::string& text() const { return text_; }
+};
+
+struct DocAddress {
+  SegmentOrdinal segment_ord = 0;
+  DocId doc_id = 0;
+  DocAddress() = default;
+  DocAddress(SegmentOrdinal s, DocId d) : segment_ord(s), doc_id(d) {}
+  bool operator==(const DocAddress& o) const { return segment_ord == o.segment_ord && doc_id == o.doc_id; }
+  bool operator<(const DocAddress& o) const { return segment_ord != o.segment_ord ? segment_ord < o.segment_ord : doc_id < o.doc_id; }
+};
+
+class Document {
+ public:
+  Document& add_text(Field f, const std::string& text) { values_.push_back({f, text}); return *this; }
+  const std::vector<std::pair<Field, std::string>>& field_values() const { return values_; }
+
+ private:
+  std::vector<std::pair<Field, std::string>> values_;
+};
+
+// ---- tokenizers ("default" = SimpleTokenizer + RemoveLongFilter(40) + LowerCaser, "raw"; tokenizer_manager.rs:53-70)
+// ASCII rules: alphanumeric = [0-9A-Za-z] plus every byte >= 0x80 (multi-byte UTF-8 sequences stay inside a token);
+// lower-casing touches ASCII only.
+inline std::vector<std::string> tokenize(const std::string& tokenizer, const std::string& text) {
+  std::vector<std::string> out;
+  if (tokenizer == "raw") {
+    out.push_back(text);
+    return out;
+  }
+  if (tokenizer != "default") throw TantivyError(TantivyError::SchemaError, "unknown tokenizer: " + tokenizer);
+  std::string cur;
+  auto flush = [&]() {
+    if (!cur.empty() && cur.size() < 40) out.push_back(cur);
+    cur.clear();
+  };
+  for (unsigned char ch : text) {
+    const bool alnum = (ch >= '0' && ch <= '9') || (ch >= 'a' && ch <= 'z') || (ch >= 'A' && ch <= 'Z') || ch >= 0x80;
+    if (!alnum) { flush(); continue; }
+    cur.push_back((ch >= 'A' && ch <= 'Z') ? (char)(ch - 'A' + 'a') : (char)ch);
+  }
+  flush();
+  return out;
+}
+
+// ---- segment data --------------------------------------------------------------------------------------------
+struct TermInfo {  // src/postings/term_info.rs:9-16 (positions range left out: not on this path)
+  uint32_t doc_freq = 0;
+  uint64_t postings_start = 0, postings_end = 0;
+};
+
+struct FieldSegmentData {
+  bool indexed = false;
+  IndexRecordOption record = IndexRecordOption::Basic;
+  bool has_fieldnorms = false;
+  std::vector<uint8_t> idx_body;   // the field's `.idx` sub-file: u64 total_num_tokens + posting lists (serializer.rs:128)
+  std::vector<uint8_t> fieldnorms; // the field's `.fieldnorm` sub-file: one fieldnorm id per doc
+  std::map<std::string, TermInfo> term_dict;          // term bytes -> TermInfo (the `.term` file, N2, is not read yet)
+  std::map<std::string, std::vector<DocId>> term_docs; // kept by the in-RAM writer only, for delete_term
+  uint64_t total_num_tokens() const {
+    uint64_t v = 0;
+    if (idx_body.size() >= 8) std::memcpy(&v, idx_body.data(), 8);
+    return v;
+  }
+};
+
+struct SegmentData {
+  uint32_t max_doc = 0;
+  std::vector<FieldSegmentData> fields;  // by field id
+  std::vector<uint8_t> alive;            // empty = no deletes; else 64-bit LE words, bit set = alive (common/src/bitset.rs:362-407)
+  uint32_t num_deleted = 0;
+  bool is_alive(DocId d) const { return alive.empty() || ((alive[d >> 3] >> (d & 7u)) & 1u); }
+};
+
+class InvertedIndexReader {  // src/index/inverted_index_reader.rs:96 (get_term_info), :120-140 (doc_freq)
+ public:
+  explicit InvertedIndexReader(const FieldSegmentData* f) : f_(f) {}
+  std::optional<TermInfo> get_term_info(const Term& term) const {
+    auto it = f_->term_dict.find(term.text());
+    if (it == f_->term_dict.end()) return std::nullopt;
+    return it->second;
+  }
+  uint32_t doc_freq(const Term& term) const {
+    auto ti = get_term_info(term);
+    return ti ? ti->doc_freq : 0u;
+  }
+  uint64_t total_num_tokens() const { return f_->total_num_tokens(); }
+
+ private:
+  const FieldSegmentData* f_;
+};
+
+class SegmentReader {
+ public:
+  SegmentReader(std::shared_ptr<const SegmentData> data, SegmentOrdinal ord) : data_(std::move(data)), ord_(ord) {}
+  uint32_t max_doc() const { return data_->max_doc; }
+  uint32_t num_docs() const { return data_->max_doc - data_->num_deleted; }
+  uint32_t num_deleted_docs() const { return data_->num_deleted; }
+  bool is_deleted(DocId d) const { return !data_->is_alive(d); }
+  SegmentOrdinal segment_ord() const { return ord_; }
+  InvertedIndexReader inverted_index(Field field) const {
+    if (field.id >= data_->fields.size() || !data_->fields[field.id].indexed)
+      throw TantivyError(TantivyError::SchemaError, "field is not indexed");
+    return InvertedIndexReader(&data_->fields[field.id]);
+  }
+  const SegmentData& data() const { return *data_; }
+
+ private:
+  std::shared_ptr<const SegmentData> data_;
+  SegmentOrdinal ord_;
+};
+
+// ---- queries ---------------------------------------------------------------------------------------------------
+enum class Occur { Should, Must, MustNot };
+
+class Query {
+ public:
+  virtual ~Query() = default;
+  virtual std::unique_ptr<Query> box_clone() const = 0;
+};
+using QueryBox = std::unique_ptr<Query>;
+
+class TermQuery : public Query {
+ public:
+  TermQuery(Term term, IndexRecordOption option) : term_(std::move(term)), option_(option) {}
+  const Term& term() const { return term_; }
+  IndexRecordOption index_record_option() const { return option_; }
+  QueryBox box_clone() const override { return std::make_unique<TermQuery>(*this); }
+
+ private:
+  Term term_;
+  IndexRecordOption option_;
+};
+
+class BoostQuery : public Query {
+ public:
+  BoostQuery(QueryBox query, Score boost) : query_(std::move(query)), boost_(boost) {}
+  BoostQuery(const BoostQuery& o) : query_(o.query_->box_clone()), boost_(o.boost_) {}
+  const Query& inner() const { return *query_; }
+  Score boost() const { return boost_; }
+  QueryBox box_clone() const override { return std::make_unique<BoostQuery>(*this); }
+
+ private:
+  QueryBox query_;
+  Score boost_;
+};
+
+class BooleanQuery : public Query {
+ public:
+  BooleanQuery() = default;
+  explicit BooleanQuery(std::vector<std::pair<Occur, QueryBox>> clauses) : clauses_(std::move(clauses)) {}
+  BooleanQuery(const BooleanQuery& o) {
+    for (auto& c : o.clauses_) clauses_.emplace_back(c.first, c.second->box_clone());
+  }
+  // BooleanQuery::new_multiterms_query (boolean_query.rs): a disjunction of term queries
+  static BooleanQuery new_multiterms_query(const std::vector<Term>& terms) {
+    BooleanQuery q;
+    for (auto& t : terms) q.clauses_.emplace_back(Occur::Should, std::make_unique<TermQuery>(t, IndexRecordOption::WithFreqs));
+    return q;
+  }
+  const std::vector<std::pair<Occur, QueryBox>>& clauses() const { return clauses_; }
+  QueryBox box_clone() const override { return std::make_unique<BooleanQuery>(*this); }
+
+ private:
+  std::vector<std::pair<Occur, QueryBox>> clauses_;
+};
+
+template <class Q>
+QueryBox boxed(Q q) { return std::make_unique<Q>(std::move(q)); }
+
+// ---- collector -------------------------------------------------------------------------------------------------
+class TopDocs {
+ public:
+  // top_score_collector.rs:226-228: "Limit must be strictly greater than 0" (the reference panics)
+  static TopDocs with_limit(size_t limit) {
+    if (limit == 0) throw TantivyError(TantivyError::InvalidArgument, "Limit must be strictly greater than 0.");
+    TopDocs t;
+    t.limit_ = limit;
+    return t;
+  }
+  TopDocs and_offset(size_t offset) const { TopDocs t = *this; t.offset_ = offset; return t; }
+  TopDocs order_by_score() const { return *this; }
+  size_t limit() const { return limit_; }
+  size_t offset() const { return offset_; }
+
+ private:
+  size_t limit_ = 0, offset_ = 0;
+};
+
+// ---- device context shared by the searchers of one reader snapshot ------------------------------------------
+class DeviceIndex {
+ public:
+  explicit DeviceIndex(int device) : device_(device) {}
+  ~DeviceIndex() { if (ctx_) tq_ctx_destroy(ctx_); }
+  DeviceIndex(const DeviceIndex&) = delete;
+  DeviceIndex& operator=(const DeviceIndex&) = delete;
+
+  // Uploads every indexed field of every segment once (segments are immutable).
+  tq_ctx* ensure(const std::vector<SegmentReader>& segments) {
+    std::lock_guard<std::mutex> g(mu_);
+    if (ctx_) return ctx_;
+    tq_ctx* c = nullptr;
+    if (tq_ctx_create(device_, &c) != TQ_OK) {
+      std::string msg = std::string("no usable CUDA device for the search path: ") + tq_last_error(nullptr);
+      throw TantivyError(TantivyError::SystemError, msg);
+    }
+    for (auto& seg : segments) {
+      const SegmentData& d = seg.data();
+      for (uint32_t f = 0; f < d.fields.size(); ++f) {
+        const FieldSegmentData& fd = d.fields[f];
+        if (!fd.indexed) continue;
+        const int rc = tq_segment_register(c, seg.segment_ord(), f, d.max_doc, (int)fd.record, fd.idx_body.data(), fd.idx_body.size(),
+                                           fd.has_fieldnorms ? fd.fieldnorms.data() : nullptr, fd.has_fieldnorms ? fd.fieldnorms.size() : 0,
+                                           d.alive.empty() ? nullptr : d.alive.data(), d.alive.size());
+        if (rc != TQ_OK) {
+          std::string msg = std::string("tq_segment_register: ") + tq_last_error(c);
+          tq_ctx_destroy(c);
+          throw TantivyError(TantivyError::SystemError, msg);
+        }
+      }
+    }
+    ctx_ = c;
+    return ctx_;
+  }
+
+ private:
+  int device_;
+  tq_ctx* ctx_ = nullptr;
+  std::mutex mu_;
+};
+
+// ---- searcher --------------------------------------------------------------------------------------------------
+class Searcher {
+ public:
+  Searcher(Schema schema, std::vector<SegmentReader> segments, std::shared_ptr<DeviceIndex> device)
+      : schema_(std::move(schema)), segments_(std::move(segments)), device_(std::move(device)) {}
+
+  const Schema& schema() const { return schema_; }
+  const std::vector<SegmentReader>& segment_readers() const { return segments_; }
+  const SegmentReader& segment_reader(SegmentOrdinal ord) const { return segments_.at(ord); }
+  // searcher.rs:133-141: alive docs
+  uint64_t num_docs() const {
+    uint64_t n = 0;
+    for (auto& s : segments_) n += s.num_docs();
+    return n;
+  }
+  // Bm25StatisticsProvider for Searcher (src/query/bm25.rs:27-50): N counts deleted docs too
+  uint64_t total_num_docs() const {
+    uint64_t n = 0;
+    for (auto& s : segments_) n += s.max_doc();
+    return n;
+  }
+  uint64_t total_num_tokens(Field field) const {
+    uint64_t n = 0;
+    for (auto& s : segments_) n += s.inverted_index(field).total_num_tokens();
+    return n;
+  }
+  uint64_t doc_freq(const Term& term) const {
+    uint64_t n = 0;
+    for (auto& s : segments_) n += s.inverted_index(term.field()).doc_freq(term);
+    return n;
+  }
+
+  // Searcher::search(query, &TopDocs::with_limit(k).and_offset(o).order_by_score())  (searcher.rs:180-237)
+  std::vector<std::pair<Score, DocAddress>> search(const Query& query, const TopDocs& collector) const {
+    std::vector<const Query*> one{&query};
+    return std::move(search_batch(one, collector)[0]);
+  }
+
+  // Many queries in one device batch (throughput; single queries are launch-latency bound).
+  std::vector<std::vector<std::pair<Score, DocAddress>>> search_batch(const std::vector<const Query*>& queries, const TopDocs& collector) const {
+    const size_t k = collector.limit() + collector.offset();
+    if (k > TQ_MAX_K) throw TantivyError(TantivyError::InvalidArgument, "limit + offset exceeds TQ_MAX_K");
+    const size_t nq = queries.size();
+    std::vector<Plan> plans(nq);
+    std::vector<tq_query> tq(nq);
+    std::vector<size_t> live;
+    for (size_t i = 0; i < nq; ++i) {
+      plans[i] = plan(*queries[i], (uint32_t)k);
+      if (plans[i].matches_nothing) continue;
+      Plan& p = plans[i];
+      tq_query q;
+      std::memset(&q, 0, sizeof(q));
+      q.op = p.op; q.n_terms = (uint32_t)p.weight.size(); q.k = (uint32_t)k; q.n_term_segs = (uint32_t)p.term_segs.size();
+      q.term_segs = p.term_segs.data(); q.weight = p.weight.data(); q.avg_fieldnorm = p.avg.data(); q.term_flags = p.flags.data();
+      tq[live.size()] = q;
+      live.push_back(i);
+    }
+    std::vector<std::vector<std::pair<Score, DocAddress>>> out(nq);
+    if (live.empty()) return out;
+    tq_ctx* ctx = device_->ensure(segments_);
+    const size_t n = live.size();
+    std::vector<float> sc(n * k);
+    std::vector<uint32_t> sg(n * k), dc(n * k), cnt(n);
+    if (tq_search_batch(ctx, tq.data(), n, (uint32_t)k, sc.data(), sg.data(), dc.data(), cnt.data()) != TQ_OK)
+      throw TantivyError(TantivyError::SystemError, std::string("tq_search_batch: ") + tq_last_error(ctx));
+    for (size_t j = 0; j < n; ++j) {
+      auto& rows = out[live[j]];
+      for (size_t r = collector.offset(); r < cnt[j]; ++r) rows.emplace_back(sc[j * k + r], DocAddress(sg[j * k + r], dc[j * k + r]));
+    }
+    return out;
+  }
+
+ private:
+  struct Clause {
+    Term term;
+    IndexRecordOption option;
+    Score boost;
+  };
+  struct Plan {
+    int32_t op = TQ_OP_TERM;
+    bool matches_nothing = false;
+    std::vector<float> weight, avg;
+    std::vector<uint8_t> flags;
+    std::vector<tq_term_seg> term_segs;
+  };
+
+  // SpecializedScorer classification (boolean_weight.rs:17-21,57-68,318-330): TermQuery -> TERM, BooleanQuery of
+  // only-Must TermQuerys -> AND, only-Should -> OR; BoostQuery multiplies the Bm25Weight (bm25.rs:129-131).
+  static void flatten(const Query& q, Score boost, std::vector<Clause>& out, int32_t* op) {
+    if (auto* t = dynamic_cast<const TermQuery*>(&q)) {
+      out.push_back({t->term(), t->index_record_option(), boost});
+      *op = TQ_OP_TERM;
+      return;
+    }
+    if (auto* b = dynamic_cast<const BoostQuery*>(&q)) return flatten(b->inner(), boost * b->boost(), out, op);
+    if (auto* b = dynamic_cast<const BooleanQuery*>(&q)) {
+      std::optional<Occur> occur;
+      for (auto& c : b->clauses()) {
+        if (c.first == Occur::MustNot || (occur && *occur != c.first))
+          throw TantivyError(TantivyError::Unsupported, "only all-Must or all-Should term clauses run on the device path");
+        occur = c.first;
+        const Query* inner = c.second.get();
+        Score cb = boost;
+        while (auto* bq = dynamic_cast<const BoostQuery*>(inner)) { cb *= bq->boost(); inner = &bq->inner(); }
+        auto* t = dynamic_cast<const TermQuery*>(inner);
+        if (!t) throw TantivyError(TantivyError::Unsupported, "nested boolean clauses do not run on the device path");
+        out.push_back({t->term(), t->index_record_option(), cb});
+      }
+      *op = (!occur || out.size() == 1) ? TQ_OP_TERM : (*occur == Occur::Must ? TQ_OP_AND : TQ_OP_OR);
+      return;
+    }
+    throw TantivyError(TantivyError::Unsupported, "query type does not run on the device path");
+  }
+
+  Plan plan(const Query& query, uint32_t) const {
+    Plan p;
+    std::vector<Clause> clauses;
+    flatten(query, 1.0f, clauses, &p.op);
+    if (clauses.empty()) { p.matches_nothing = true; return p; }
+    if (clauses.size() > TQ_MAX_TERMS) throw TantivyError(TantivyError::InvalidArgument, "too many clauses for the device path");
+    const uint64_t n_docs = total_num_docs();
+    for (uint32_t i = 0; i < clauses.size(); ++i) {
+      const Clause& c = clauses[i];
+      const FieldEntry& fe = schema_.get_field_entry(c.term.field());
+      if (!fe.options.indexing) throw TantivyError(TantivyError::SchemaError, "field " + fe.name + " is not indexed");
+      // Bm25Weight::for_terms (bm25.rs:95-118)
+      const uint64_t df = doc_freq(c.term);
+      p.weight.push_back(tq::bm25_weight(df, n_docs, c.boost));
+      p.avg.push_back(n_docs ? (float)total_num_tokens(c.term.field()) / (float)n_docs : 0.0f);
+      const bool field_has_freq = fe.options.indexing->record != IndexRecordOption::Basic;
+      p.flags.push_back((field_has_freq && c.option == IndexRecordOption::Basic) ? TQ_TERM_IGNORE_FREQ : 0);
+      for (auto& s : segments_) {
+        auto ti = s.inverted_index(c.term.field()).get_term_info(c.term);
+        if (ti && ti->doc_freq)
+          p.term_segs.push_back(tq_term_seg{i, s.segment_ord(), c.term.field().id, ti->doc_freq, ti->postings_start, ti->postings_end});
+      }
+    }
+    if (p.term_segs.empty()) p.matches_nothing = true;
+    return p;
+  }
+
+  Schema schema_;
+  std::vector<SegmentReader> segments_;
+  std::shared_ptr<DeviceIndex> device_;
+};
+
+class IndexReader {
+ public:
+  IndexReader(Schema schema, std::vector<std::shared_ptr<const SegmentData>> segments, int device) : schema_(std::move(schema)) {
+    for (size_t i = 0; i < segments.size(); ++i) readers_.emplace_back(segments[i], (SegmentOrdinal)i);
+    device_ = std::make_shared<DeviceIndex>(device);
+  }
+  Searcher searcher() const { return Searcher(schema_, readers_, device_); }
+
+ private:
+  Schema schema_;
+  std::vector<SegmentReader> readers_;
+  std::shared_ptr<DeviceIndex> device_;
+};
+
+// ---- index + writer ----------------------------------------------------------------------------------------------
+class Index;
+class IndexWriter {
+ public:
+  explicit IndexWriter(Index* index) : index_(index) {}
+  Opstamp add_document(const Document& doc) {
+    pending_.push_back({doc, ++opstamp_});
+    return opstamp_;
+  }
+  Opstamp delete_term(const Term& term) {
+    deletes_.push_back({term, ++opstamp_});
+    return opstamp_;
+  }
+  Opstamp commit();
+
+ private:
+  struct PendingDoc { Document doc; Opstamp opstamp; };
+  struct PendingDelete { Term term; Opstamp opstamp; };
+  Index* index_;
+  std::vector<PendingDoc> pending_;
+  std::vector<PendingDelete> deletes_;
+  Opstamp opstamp_ = 0;
+};
+
+class Index {
+ public:
+  static Index create_in_ram(const Schema& schema) { return Index(schema); }
+  // An index over segments read from files the reference wrote (N1): the caller supplies each segment's data.
+  static Index from_segments(const Schema& schema, std::vector<std::shared_ptr<const SegmentData>> segments) {
+    Index ix(schema);
+    ix.segments_ = std::move(segments);
+    return ix;
+  }
+  const Schema& schema() const { return schema_; }
+  IndexWriter writer() { return IndexWriter(this); }
+  IndexWriter writer_for_tests() { return IndexWriter(this); }
+  IndexReader reader() const { return IndexReader(schema_, segments_, device_); }
+  void set_device(int device) { device_ = device; }
+  const std::vector<std::shared_ptr<const SegmentData>>& segments() const { return segments_; }
+
+ private:
+  friend class IndexWriter;
+  explicit Index(const Schema& schema) : schema_(schema) {}
+  Schema schema_;
+  std::vector<std::shared_ptr<const SegmentData>> segments_;
+  int device_ = 0;
+};
+
+namespace detail {
+inline void set_deleted(SegmentData& seg, DocId d) {
+  if (seg.alive.empty()) {
+    seg.alive.assign(((size_t)seg.max_doc + 63) / 64 * 8, 0);
+    for (DocId i = 0; i < seg.max_doc; ++i) seg.alive[i >> 3] |= (uint8_t)(1u << (i & 7u));
+  }
+  if (seg.is_alive(d)) {
+    seg.alive[d >> 3] &= (uint8_t)~(1u << (d & 7u));
+    ++seg.num_deleted;
+  }
+}
+}  // namespace detail
+
+// One segment per commit (the reference's single-threaded writer, index_writer.rs; segment_writer.rs for the
+// per-field token counting -> fieldnorm, serializer.rs for the bytes).
+inline Opstamp IndexWriter::commit() {
+  const Schema& schema = index_->schema_;
+  // deletes hit every doc of the committed segments and the pending docs added before the delete (opstamp order)
+  for (auto& del : deletes_) {
+    for (auto& sp : index_->segments_) {
+      const FieldSegmentData& fd = sp->fields.at(del.term.field().id);
+      auto it = fd.term_docs.find(del.term.text());
+      if (it == fd.term_docs.end()) continue;
+      auto copy = std::make_shared<SegmentData>(*sp);
+      for (DocId d : it->second) detail::set_deleted(*copy, d);
+      sp = copy;
+    }
+  }
+  if (!pending_.empty()) {
+    auto seg = std::make_shared<SegmentData>();
+    seg->max_doc = (uint32_t)pending_.size();
+    const size_t nf = schema.num_fields();
+    seg->fields.resize(nf);
+    std::vector<std::map<std::string, std::vector<std::pair<DocId, uint32_t>>>> postings(nf);
+    std::vector<std::vector<uint32_t>> num_tokens(nf, std::vector<uint32_t>(seg->max_doc, 0));
+    for (DocId d = 0; d < seg->max_doc; ++d) {
+      for (auto& fv : pending_[d].doc.field_values()) {
+        const FieldEntry& fe = schema.get_field_entry(fv.first);
+        if (!fe.options.indexing) continue;
+        for (auto& tok : tokenize(fe.options.indexing->tokenizer, fv.second)) {
+          auto& pl = postings[fv.first.id][tok];
+          if (!pl.empty() && pl.back().first == d) ++pl.back().second; else pl.push_back({d, 1u});
+          ++num_tokens[fv.first.id][d];
+        }
+      }
+    }
+    for (uint32_t f = 0; f < nf; ++f) {
+      const FieldEntry& fe = schema.get_field_entry(Field{f});
+      FieldSegmentData& fd = seg->fields[f];
+      if (!fe.options.indexing) continue;
+      fd.indexed = true;
+      fd.record = fe.options.indexing->record;
+      fd.has_fieldnorms = fe.options.indexing->fieldnorms;
+      uint64_t total = 0;
+      for (uint32_t n : num_tokens[f]) total += n;
+      if (fd.has_fieldnorms) {
+        fd.fieldnorms.resize(seg->max_doc);
+        for (DocId d = 0; d < seg->max_doc; ++d) fd.fieldnorms[d] = tq::fieldnorm_to_id(num_tokens[f][d]);
+      }
+      tq::FieldPostingsWriter w((int)fd.record, total, fd.has_fieldnorms ? fd.fieldnorms.data() : nullptr, seg->max_doc);
+      std::vector<uint32_t> docs, tfs;
+      for (auto& kv : postings[f]) {  // std::map: terms in byte order, as the term dictionary requires
+        docs.clear(); tfs.clear();
+        for (auto& p : kv.second) { docs.push_back(p.first); tfs.push_back(p.second); }
+        const tq::TermInfoOut ti = w.add_term(docs.data(), fd.record == IndexRecordOption::Basic ? nullptr : tfs.data(), (uint32_t)docs.size());
+        fd.term_dict[kv.first] = TermInfo{ti.doc_freq, ti.postings_start, ti.postings_end};
+        fd.term_docs[kv.first] = docs;
+      }
+      fd.idx_body = w.body();
+    }
+    for (auto& del : deletes_) {
+      auto it = seg->fields.at(del.term.field().id).term_docs.find(del.term.text());
+      if (it == seg->fields[del.term.field().id].term_docs.end()) continue;
+      for (DocId d : it->second)
+        if (pending_[d].opstamp < del.opstamp) detail::set_deleted(*seg, d);
+    }
+    index_->segments_.push_back(seg);
+  }
+  pending_.clear();
+  deletes_.clear();
+  return ++opstamp_;
+}
+
+// ---- a small query parser: whitespace separated terms, optional '+' (Must) and 'field:' prefixes ---------------
+class QueryParser {
+ public:
+  static QueryParser for_index(const Index& index, std::vector<Field> default_fields) { return QueryParser(index.schema(), std::move(default_fields)); }
+  QueryBox parse_query(const std::string& text) const {
+    std::vector<std::pair<Occur, QueryBox>> clauses;
+    size_t i = 0;
+    while (i < text.size()) {
+      while (i < text.size() && text[i] == ' ') ++i;
+      size_t j = i;
+      while (j < text.size() && text[j] != ' ') ++j;
+      if (j == i) break;
+      std::string tok = text.substr(i, j - i);
+      i = j;
+      Occur occur = Occur::Should;
+      if (tok[0] == '+') { occur = Occur::Must; tok.erase(0, 1); }
+      else if (tok[0] == '-') { occur = Occur::MustNot; tok.erase(0, 1); }
+      std::vector<Field> fields = default_fields_;
+      const size_t colon = tok.find(':');
+      if (colon != std::string::npos) {
+        auto f = schema_.get_field(tok.substr(0, colon));
+        if (!f) throw TantivyError(TantivyError::InvalidArgument, "Field does not exist: '" + tok.substr(0, colon) + "'");
+        fields = {*f};
+        tok.erase(0, colon + 1);
+      }
+      if (fields.size() != 1) throw TantivyError(TantivyError::Unsupported, "exactly one default field (or a field: prefix) is supported");
+      const FieldEntry& fe = schema_.get_field_entry(fields[0]);
+      if (!fe.options.indexing) throw TantivyError(TantivyError::SchemaError, "field is not indexed");
+      auto toks = tokenize(fe.options.indexing->tokenizer, tok);
+      if (toks.size() != 1) throw TantivyError(TantivyError::Unsupported, "phrases are not supported by this parser");
+      const IndexRecordOption opt = fe.options.indexing->record == IndexRecordOption::Basic ? IndexRecordOption::Basic : IndexRecordOption::WithFreqs;
+      clauses.emplace_back(occur, std::make_unique<TermQuery>(Term::from_field_text(fields[0], toks[0]), opt));
+    }
+    if (clauses.size() == 1 && clauses[0].first != Occur::MustNot) return std::move(clauses[0].second);
+    return std::make_unique<BooleanQuery>(std::move(clauses));
+  }
+
+ private:
+  QueryParser(Schema schema, std::vector<Field> fields) : schema_(std::move(schema)), default_fields_(std::move(fields)) {}
+  Schema schema_;
+  std::vector<Field> default_fields_;
+};
+
+// ---- N1: file framing written by the reference ---------------------------------------------------------------
+namespace files {
+
+inline uint32_t crc32(const uint8_t* p, size_t n) {  // IEEE 802.3, as crc32fast (footer.rs)
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; ++i) c = table[(c ^ p[i]) & 0xFFu] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
+struct Footer {
+  uint32_t index_format_version = 0;
+  uint32_t crc = 0;
+  size_t body_len = 0;  // bytes before the footer
+};
+
+// file = body ‖ JSON footer ‖ u32 json_len ‖ u32 magic (1337)   (src/directory/footer.rs:18-22,44-51,85-120)
+inline Footer read_footer(const uint8_t* file, size_t len, bool verify_crc = true) {
+  auto u32_at = [&](size_t off) { uint32_t v; std::memcpy(&v, file + off, 4); return v; };
+  if (len < 8) throw TantivyError(TantivyError::DataCorruption, "file too short for a footer");
+  if (u32_at(len - 4) != 1337u) throw TantivyError(TantivyError::DataCorruption, "footer magic byte mismatch");
+  const uint32_t json_len = u32_at(len - 8);
+  if ((size_t)json_len + 8 > len) throw TantivyError(TantivyError::DataCorruption, "footer length out of range");
+  const std::string json(reinterpret_cast<const char*>(file + len - 8 - json_len), json_len);
+  auto number_after = [&](const std::string& key) -> uint64_t {
+    const size_t k = json.find("\"" + key + "\"");
+    if (k == std::string::npos) throw TantivyError(TantivyError::DataCorruption, "footer lacks " + key);
+    size_t p = json.find(':', k) + 1;
+    while (p < json.size() && json[p] == ' ') ++p;
+    uint64_t v = 0;
+    bool any = false;
+    while (p < json.size() && json[p] >= '0' && json[p] <= '9') { v = v * 10 + (uint64_t)(json[p++] - '0'); any = true; }
+    if (!any) throw TantivyError(TantivyError::DataCorruption, "footer field " + key + " is not a number");
+    return v;
+  };
+  Footer f;
+  f.index_format_version = (uint32_t)number_after("index_format_version");
+  f.crc = (uint32_t)number_after("crc");
+  f.body_len = len - 8 - json_len;
+  if (verify_crc && crc32(file, f.body_len) != f.crc) throw TantivyError(TantivyError::DataCorruption, "crc mismatch");
+  return f;
+}
+
+inline uint64_t read_vint(const uint8_t* p, size_t len, size_t* pos) {  // common/src/vint.rs: 7 bits per byte, stop bit 0x80
+  uint64_t v = 0;
+  uint32_t shift = 0;
+  while (*pos < len) {
+    const uint8_t b = p[(*pos)++];
+    v |= (uint64_t)(b & 127u) << shift;
+    if (b & 128u) return v;
+    shift += 7;
+    if (shift > 63) break;
+  }
+  throw TantivyError(TantivyError::DataCorruption, "truncated vint");
+}
+
+struct FileSlice { size_t offset = 0, len = 0; };
+
+// composite = sub-files ‖ VInt(n) ‖ n x (VInt(offset delta), u32 field LE, VInt(idx)) ‖ u32 footer_len
+// (src/directory/composite_file.rs:71-85,111-145). Returns (field, idx) -> byte range inside `body`.
+inline std::map<std::pair<uint32_t, uint32_t>, FileSlice> open_composite(const uint8_t* body, size_t len) {
+  if (len < 4) throw TantivyError(TantivyError::DataCorruption, "composite file too short");
+  uint32_t footer_len;
+  std::memcpy(&footer_len, body + len - 4, 4);
+  if ((size_t)footer_len + 4 > len) throw TantivyError(TantivyError::DataCorruption, "composite footer length out of range");
+  const size_t data_len = len - 4 - footer_len;
+  const uint8_t* foot = body + data_len;
+  size_t pos = 0;
+  const uint64_t n = read_vint(foot, footer_len, &pos);
+  std::vector<std::pair<std::pair<uint32_t, uint32_t>, size_t>> starts;
+  size_t offset = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    offset += (size_t)read_vint(foot, footer_len, &pos);
+    if (pos + 4 > footer_len) throw TantivyError(TantivyError::DataCorruption, "truncated composite footer");
+    uint32_t field;
+    std::memcpy(&field, foot + pos, 4);
+    pos += 4;
+    const uint32_t idx = (uint32_t)read_vint(foot, footer_len, &pos);
+    starts.push_back({{field, idx}, offset});
+  }
+  std::map<std::pair<uint32_t, uint32_t>, FileSlice> out;
+  for (size_t i = 0; i < starts.size(); ++i) {
+    const size_t end = i + 1 < starts.size() ? starts[i + 1].second : data_len;
+    if (starts[i].second > end || end > data_len) throw TantivyError(TantivyError::DataCorruption, "composite offsets out of order");
+    out[starts[i].first] = FileSlice{starts[i].second, end - starts[i].second};
+  }
+  return out;
+}
+
+// Fills one field of a SegmentData from the segment's `.idx` and `.fieldnorm` files as written by the reference.
+inline void load_field(SegmentData& seg, Field field, IndexRecordOption record, const std::vector<uint8_t>& idx_file,
+                       const std::vector<uint8_t>* fieldnorm_file) {
+  if (seg.fields.size() <= field.id) seg.fields.resize(field.id + 1);
+  FieldSegmentData& fd = seg.fields[field.id];
+  const Footer fi = read_footer(idx_file.data(), idx_file.size());
+  auto idx_parts = open_composite(idx_file.data(), fi.body_len);
+  auto it = idx_parts.find({field.id, 0});
+  if (it == idx_parts.end()) throw TantivyError(TantivyError::DataCorruption, "field has no postings sub-file");
+  fd.indexed = true;
+  fd.record = record;
+  fd.idx_body.assign(idx_file.begin() + (long)it->second.offset, idx_file.begin() + (long)(it->second.offset + it->second.len));
+  if (fd.idx_body.size() < 8) throw TantivyError(TantivyError::DataCorruption, "postings sub-file lacks total_num_tokens");
+  if (fieldnorm_file) {
+    const Footer ff = read_footer(fieldnorm_file->data(), fieldnorm_file->size());
+    auto fn_parts = open_composite(fieldnorm_file->data(), ff.body_len);
+    auto fit = fn_parts.find({field.id, 0});
+    if (fit != fn_parts.end()) {
+      if (fit->second.len != seg.max_doc) throw TantivyError(TantivyError::DataCorruption, "fieldnorm sub-file length != max_doc");
+      fd.has_fieldnorms = true;
+      fd.fieldnorms.assign(fieldnorm_file->begin() + (long)fit->second.offset, fieldnorm_file->begin() + (long)(fit->second.offset + fit->second.len));
+    }
+  }
+}
+
+}  // namespace files
+}  // namespace tantivy_b200

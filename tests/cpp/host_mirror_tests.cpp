@@ -1,0 +1,526 @@
+// Tests of the C++ host mirror (tantivy_b200/host/tantivy_host.hpp), written in the shape of the reference's own
+// tests for this path.  Every test names the reference test it restates; the expected scores are the reference's.
+//
+//   host_mirror_tests               run every search test on cuda:0 (needs a GPU)
+//   host_mirror_tests --dump DIR    write the segment bytes of every test index under DIR (CPU only; the Python
+//                                   suite feeds them to the oracle and checks the same golden scores there)
+//   host_mirror_tests --cpu         host-only checks: tokenizer, fieldnorms, statistics, file framing, error kinds,
+//                                   and that a search without a CUDA device raises (no CPU fallback)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <sstream>
+
+#include "../../tantivy_b200/host/tantivy_host.hpp"
+
+using namespace tantivy_b200;
+
+static int g_failed = 0;
+#define CHECK(cond)                                                                  \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      std::printf("    CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond);        \
+      ++g_failed;                                                                    \
+    }                                                                                \
+  } while (0)
+// the reference's assert_nearly_equals! uses |l - r| <= 0.0005 (src/lib.rs:406-427); this port is 500x tighter
+#define CHECK_NEARLY(left, right)                                                                              \
+  do {                                                                                                         \
+    const double l_ = (left), r_ = (right);                                                                    \
+    if (!(std::fabs(l_ - r_) <= 1e-6 * std::max(std::fabs(l_), std::fabs(r_)))) {                                 \
+      std::printf("    CHECK_NEARLY failed %s:%d: %.9g vs %.9g\n", __FILE__, __LINE__, l_, r_);               \
+      ++g_failed;                                                                                              \
+    }                                                                                                          \
+  } while (0)
+
+static Document doc(Field f, const std::string& text) {
+  Document d;
+  d.add_text(f, text);
+  return d;
+}
+static QueryBox term_query(Field f, const std::string& text, IndexRecordOption opt) {
+  return std::make_unique<TermQuery>(Term::from_field_text(f, text), opt);
+}
+
+// ---- index builders shared by the search tests and by --dump -------------------------------------------------
+struct Named { std::string name; Index index; };
+
+// term_query/mod.rs:21-44
+static Index index_one_doc_string() {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", STRING);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  w.add_document(doc(text, "a"));
+  w.commit();
+  return index;
+}
+// term_query/mod.rs:46-78
+static Index index_block_len_docs() {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", STRING);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  for (int i = 0; i < 128; ++i) w.add_document(doc(text, "a"));
+  w.commit();
+  return index;
+}
+// term_query/mod.rs:80-100
+static Index index_term_weight() {
+  SchemaBuilder sb;
+  Field left = sb.add_text_field("left", TEXT);
+  Field right = sb.add_text_field("right", TEXT);
+  Field large = sb.add_text_field("large", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  std::string big;
+  for (int i = 0; i <= 286; ++i) big += (i ? " large" : "large") + std::to_string(i);
+  Document d;
+  d.add_text(left, "left1 left2 left2 left2f2 left2f2 left3 abcde abcde abcde abcde abcde abcde abcde abcde abcde abcewde abcde abcde");
+  d.add_text(right, "right1 right2");
+  d.add_text(large, big);
+  w.add_document(d);
+  w.add_document(doc(left, "left4 left1"));
+  w.commit();
+  return index;
+}
+// boolean_query/mod.rs:27-44 (aux_test_helper)
+static Index index_boolean_aux() {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  for (const char* t : {"a b c", "a c", "b c", "a b c d", "d"}) w.add_document(doc(text, t));
+  w.commit();
+  return index;
+}
+// boolean_query/mod.rs:221-233
+static Index index_boolean_weight() {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  for (const char* t : {"a b c", "a c", "b c"}) w.add_document(doc(text, t));
+  w.commit();
+  return index;
+}
+// top_score_collector.rs:718-729 (make_index)
+static Index index_droopy() {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  w.add_document(doc(text, "Hello happy tax payer."));
+  w.add_document(doc(text, "Droopy says hello happy tax payer"));
+  w.add_document(doc(text, "I like Droopy"));
+  w.commit();
+  return index;
+}
+// several commits -> several segments, a delete in between, multi-block lists with tf > 1
+static Index index_multi_segment() {
+  SchemaBuilder sb;
+  Field body = sb.add_text_field("body", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  uint32_t x = 12345;
+  auto next = [&]() { x = x * 1664525u + 1013904223u; return x >> 8; };
+  for (int seg = 0; seg < 3; ++seg) {
+    for (int d = 0; d < 700 + 111 * seg; ++d) {
+      std::string t = "w" + std::to_string(next() % 7);
+      const int len = 1 + (int)(next() % 30);
+      for (int i = 0; i < len; ++i) t += " w" + std::to_string(next() % (4 + 13 * (i % 3)));
+      if (next() % 5 == 0) t += " rare";
+      w.add_document(doc(body, t));
+    }
+    if (seg == 1) w.delete_term(Term::from_field_text(body, "rare"));
+    w.commit();
+  }
+  return index;
+}
+
+static std::vector<Named> all_indexes() {
+  std::vector<Named> v;
+  v.push_back({"one_doc_string", index_one_doc_string()});
+  v.push_back({"block_len_docs", index_block_len_docs()});
+  v.push_back({"term_weight", index_term_weight()});
+  v.push_back({"boolean_aux", index_boolean_aux()});
+  v.push_back({"boolean_weight", index_boolean_weight()});
+  v.push_back({"droopy", index_droopy()});
+  v.push_back({"multi_segment", index_multi_segment()});
+  return v;
+}
+
+// ---- search tests (GPU) --------------------------------------------------------------------------------------------
+static void test_term_query_no_freq() {  // term_query/mod.rs:21-44
+  Index index = index_one_doc_string();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  TermQuery q(Term::from_field_text(text, "a"), IndexRecordOption::Basic);
+  auto top = searcher.search(q, TopDocs::with_limit(1));
+  CHECK(top.size() == 1);
+  CHECK(top[0].second == DocAddress(0, 0));
+  CHECK_NEARLY(top[0].first, 0.28768212);
+}
+
+static void test_term_query_multiple_of_block_len() {  // term_query/mod.rs:46-78: the scorer visits docs 0..127, then TERMINATED
+  Index index = index_block_len_docs();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  TermQuery q(Term::from_field_text(text, "a"), IndexRecordOption::Basic);
+  auto top = searcher.search(q, TopDocs::with_limit(200));
+  CHECK(top.size() == 128);
+  for (uint32_t i = 0; i < top.size(); ++i) CHECK(top[i].second == DocAddress(0, i));  // equal scores: ascending doc
+}
+
+static void test_term_weight() {  // term_query/mod.rs:80-129
+  Index index = index_term_weight();
+  Field left = *index.schema().get_field("left");
+  Searcher searcher = index.reader().searcher();
+  {
+    TermQuery q(Term::from_field_text(left, "left2"), IndexRecordOption::WithFreqs);
+    auto top = searcher.search(q, TopDocs::with_limit(2).order_by_score());
+    CHECK(top.size() == 1);
+    CHECK_NEARLY(top[0].first, 0.77802235);
+  }
+  {
+    TermQuery q(Term::from_field_text(left, "left1"), IndexRecordOption::WithFreqs);
+    auto top = searcher.search(q, TopDocs::with_limit(2).order_by_score());
+    CHECK(top.size() == 2);
+    CHECK_NEARLY(top[0].first, 0.27101856);
+    CHECK_NEARLY(top[1].first, 0.13736556);
+  }
+  {
+    QueryParser parser = QueryParser::for_index(index, {});
+    QueryBox q = parser.parse_query("left:left2 left:left1");
+    auto top = searcher.search(*q, TopDocs::with_limit(2).order_by_score());
+    CHECK(top.size() == 2);
+    CHECK_NEARLY(top[0].first, 0.9153879);
+    CHECK_NEARLY(top[1].first, 0.27101856);
+  }
+}
+
+static void test_boolean_query_with_weight() {  // boolean_query/mod.rs:221-259
+  Index index = index_boolean_weight();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  std::vector<std::pair<Occur, QueryBox>> clauses;
+  clauses.emplace_back(Occur::Should, term_query(text, "a", IndexRecordOption::WithFreqs));
+  clauses.emplace_back(Occur::Should, term_query(text, "b", IndexRecordOption::WithFreqs));
+  BooleanQuery q(std::move(clauses));
+  {
+    auto top = searcher.search(q, TopDocs::with_limit(3));
+    CHECK(top.size() == 3);
+    CHECK(top[0].second == DocAddress(0, 0));
+    CHECK_NEARLY(top[0].first, 0.84163445);
+  }
+  {  // boolean_weight.scorer(reader, 2.0): the boost multiplies every clause's weight
+    BoostQuery boosted(q.box_clone(), 2.0f);
+    auto top = searcher.search(boosted, TopDocs::with_limit(3));
+    CHECK(top[0].second == DocAddress(0, 0));
+    CHECK_NEARLY(top[0].first, 1.6832689);
+  }
+}
+
+static void test_intersection_score() {  // boolean_query/mod.rs:262-291
+  Index index = index_boolean_aux();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  std::vector<std::pair<Occur, QueryBox>> clauses;
+  clauses.emplace_back(Occur::Must, term_query(text, "a", IndexRecordOption::Basic));
+  clauses.emplace_back(Occur::Must, term_query(text, "b", IndexRecordOption::Basic));
+  BooleanQuery q(std::move(clauses));
+  auto top = searcher.search(q, TopDocs::with_limit(10));
+  CHECK(top.size() == 2);
+  CHECK(top[0].second == DocAddress(0, 0));
+  CHECK_NEARLY(top[0].first, 0.977973);
+  CHECK(top[1].second == DocAddress(0, 3));
+  CHECK_NEARLY(top[1].first, 0.84699446);
+}
+
+static void check_results(const std::vector<std::pair<Score, DocAddress>>& got, const std::vector<std::pair<Score, DocAddress>>& want) {
+  CHECK(got.size() == want.size());
+  for (size_t i = 0; i < std::min(got.size(), want.size()); ++i) {
+    CHECK(got[i].second == want[i].second);
+    CHECK_NEARLY(got[i].first, want[i].first);
+  }
+}
+
+static void test_top_collector() {  // top_score_collector.rs:838-921 (the four capacity / offset cases)
+  Index index = index_droopy();
+  Field text = *index.schema().get_field("text");
+  QueryBox q = QueryParser::for_index(index, {text}).parse_query("droopy tax");
+  Searcher searcher = index.reader().searcher();
+  check_results(searcher.search(*q, TopDocs::with_limit(4).order_by_score()),
+                {{0.81221175f, DocAddress(0, 1)}, {0.5376842f, DocAddress(0, 2)}, {0.48527452f, DocAddress(0, 0)}});
+  check_results(searcher.search(*q, TopDocs::with_limit(4).and_offset(2).order_by_score()), {{0.48527452f, DocAddress(0, 0)}});
+  check_results(searcher.search(*q, TopDocs::with_limit(2).order_by_score()),
+                {{0.81221175f, DocAddress(0, 1)}, {0.5376842f, DocAddress(0, 2)}});
+  check_results(searcher.search(*q, TopDocs::with_limit(2).and_offset(1).order_by_score()),
+                {{0.5376842f, DocAddress(0, 2)}, {0.48527452f, DocAddress(0, 0)}});
+}
+
+static void test_multi_segment_deletes_and_paging() {
+  // top_score_collector.rs:923-957 (stable sorting: growing pages are prefixes of each other), on three segments
+  // with deleted docs; and Searcher statistics (searcher.rs:133-141, bm25.rs:27-50)
+  Index index = index_multi_segment();
+  Field body = *index.schema().get_field("body");
+  Searcher searcher = index.reader().searcher();
+  CHECK(searcher.segment_readers().size() == 3);
+  CHECK(searcher.total_num_docs() == 700 + 811 + 922);
+  CHECK(searcher.num_docs() < searcher.total_num_docs());
+  CHECK(searcher.segment_reader(2).num_deleted_docs() == 0);  // the delete preceded the third commit's docs
+  const Term rare = Term::from_field_text(body, "rare");
+  CHECK(searcher.doc_freq(rare) > 0);  // doc_freq still counts deleted docs
+  {
+    TermQuery q(rare, IndexRecordOption::WithFreqs);
+    auto top = searcher.search(q, TopDocs::with_limit(1000));
+    CHECK(!top.empty());
+    for (auto& h : top) CHECK(h.second.segment_ord == 2);  // every "rare" doc of segments 0 and 1 is deleted
+    CHECK(top.size() == searcher.segment_reader(2).inverted_index(body).doc_freq(rare));
+  }
+  std::vector<std::pair<Occur, QueryBox>> clauses;
+  for (const char* t : {"w0", "w3", "w11"}) clauses.emplace_back(Occur::Should, term_query(body, t, IndexRecordOption::WithFreqs));
+  BooleanQuery q(std::move(clauses));
+  auto page3 = searcher.search(q, TopDocs::with_limit(300));
+  auto page2 = searcher.search(q, TopDocs::with_limit(120));
+  auto tail = searcher.search(q, TopDocs::with_limit(100).and_offset(200));
+  CHECK(page3.size() == 300 && page2.size() == 120 && tail.size() == 100);
+  for (size_t i = 0; i < page2.size(); ++i) CHECK(page2[i] == page3[i]);
+  for (size_t i = 0; i < tail.size(); ++i) CHECK(tail[i] == page3[200 + i]);
+  for (size_t i = 1; i < page3.size(); ++i)  // (score desc, DocAddress asc), top_score_collector.rs:591-600
+    CHECK(page3[i - 1].first > page3[i].first || (page3[i - 1].first == page3[i].first && page3[i - 1].second < page3[i].second));
+  for (auto& h : page3) CHECK(!searcher.segment_reader(h.second.segment_ord).is_deleted(h.second.doc_id));
+  // the same queries as one device batch give the same rows
+  TermQuery tq1(rare, IndexRecordOption::WithFreqs);
+  auto batch = searcher.search_batch({&q, &tq1, &q}, TopDocs::with_limit(120));
+  CHECK(batch.size() == 3 && batch[0] == page2 && batch[2] == page2);
+  // a conjunction never returns more than its rarest clause
+  std::vector<std::pair<Occur, QueryBox>> must;
+  must.emplace_back(Occur::Must, term_query(body, "rare", IndexRecordOption::WithFreqs));
+  must.emplace_back(Occur::Must, term_query(body, "w1", IndexRecordOption::WithFreqs));
+  auto both = searcher.search(BooleanQuery(std::move(must)), TopDocs::with_limit(1000));
+  CHECK(!both.empty() && both.size() <= searcher.doc_freq(rare));
+}
+
+static void test_absent_terms_and_unsupported_shapes() {
+  Index index = index_boolean_aux();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  CHECK(searcher.search(TermQuery(Term::from_field_text(text, "zzz"), IndexRecordOption::WithFreqs), TopDocs::with_limit(5)).empty());
+  CHECK(searcher.search(BooleanQuery(), TopDocs::with_limit(5)).empty());
+  {
+    std::vector<std::pair<Occur, QueryBox>> c;  // a Must clause without postings: nothing matches
+    c.emplace_back(Occur::Must, term_query(text, "a", IndexRecordOption::WithFreqs));
+    c.emplace_back(Occur::Must, term_query(text, "zzz", IndexRecordOption::WithFreqs));
+    CHECK(searcher.search(BooleanQuery(std::move(c)), TopDocs::with_limit(5)).empty());
+  }
+  auto throws = [&](const Query& q, TantivyError::Kind kind) {
+    try {
+      searcher.search(q, TopDocs::with_limit(5));
+    } catch (const TantivyError& e) {
+      return e.kind() == kind;
+    }
+    return false;
+  };
+  {
+    std::vector<std::pair<Occur, QueryBox>> c;  // boolean_query/mod.rs:186-216 shapes stay on the reference's CPU path
+    c.emplace_back(Occur::Must, term_query(text, "d", IndexRecordOption::Basic));
+    c.emplace_back(Occur::MustNot, term_query(text, "a", IndexRecordOption::Basic));
+    CHECK(throws(BooleanQuery(std::move(c)), TantivyError::Unsupported));
+  }
+  {
+    QueryBox mixed = QueryParser::for_index(index, {text}).parse_query("+a b");
+    CHECK(throws(*mixed, TantivyError::Unsupported));
+  }
+  bool limit_zero = false;
+  try { TopDocs::with_limit(0); } catch (const TantivyError& e) { limit_zero = e.kind() == TantivyError::InvalidArgument; }
+  CHECK(limit_zero);
+}
+
+// ---- host-only checks ------------------------------------------------------------------------------------------------
+static void test_host_tokenizer_and_statistics() {
+  auto toks = tokenize("default", "Hello, happy tax-payer! ÜBER x" + std::string(45, 'y') + " Z9");
+  // "x" + 45 x 'y' is dropped by RemoveLongFilter(40); only ASCII letters are lower-cased (the U-umlaut's bytes stay)
+  CHECK((toks == std::vector<std::string>{"hello", "happy", "tax", "payer", "\xC3\x9C" "ber", "z9"}));
+  CHECK(tokenize("raw", "Hello World").size() == 1);
+  Index index = index_term_weight();
+  Field left = *index.schema().get_field("left"), large = *index.schema().get_field("large");
+  Searcher searcher = index.reader().searcher();
+  CHECK(searcher.total_num_docs() == 2 && searcher.num_docs() == 2);
+  CHECK(searcher.total_num_tokens(left) == 18 + 2);
+  CHECK(searcher.total_num_tokens(large) == 287);
+  CHECK(searcher.doc_freq(Term::from_field_text(left, "left1")) == 2);
+  CHECK(searcher.doc_freq(Term::from_field_text(left, "left2")) == 1);
+  const SegmentData& seg = searcher.segment_reader(0).data();
+  CHECK(seg.fields[left.id].fieldnorms[0] == 18 && seg.fields[left.id].fieldnorms[1] == 2);  // ids < 24 are exact (code.rs)
+  CHECK(seg.fields[large.id].fieldnorms[0] == tq::fieldnorm_to_id(287) && seg.fields[large.id].fieldnorms[1] == 0);
+  CHECK(tq::id_to_fieldnorm(seg.fields[large.id].fieldnorms[0]) == 280);  // fieldnorm/reader.rs:168-193 (300 -> 280 bucket)
+  auto ti = searcher.segment_reader(0).inverted_index(left).get_term_info(Term::from_field_text(left, "abcde"));
+  CHECK(ti && ti->doc_freq == 1);
+  // a 1-doc list with freqs: VInt(doc delta) + VInt(tf), stop bit on the last byte (vint.rs)
+  const auto& body = seg.fields[left.id].idx_body;
+  CHECK(ti->postings_end - ti->postings_start == 2);
+  CHECK(body[8 + ti->postings_start] == (0x80 | 0) && body[8 + ti->postings_start + 1] == (0x80 | 11));
+}
+
+static void test_host_search_without_device_raises() {
+  Index index = index_one_doc_string();
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  bool raised = false;
+  try {
+    searcher.search(TermQuery(Term::from_field_text(text, "a"), IndexRecordOption::Basic), TopDocs::with_limit(1));
+  } catch (const TantivyError& e) {
+    raised = e.kind() == TantivyError::SystemError;
+    std::printf("    (raised as expected: %s)\n", e.what());
+  }
+  CHECK(raised);
+}
+
+static std::vector<uint8_t> read_file(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+}
+
+// N1: the reference's compat fixture (tests/compat_tests_data/index_v7, src/compat_tests.rs:39-56), handed over as
+// files by the Python suite (hex in tests/golden/reference_fixtures.json).  label field: one doc, one token.
+static Index index_from_compat_files(const std::string& dir) {
+  SchemaBuilder sb;
+  Field label = sb.add_text_field("label", TEXT);
+  auto seg = std::make_shared<SegmentData>();
+  seg->max_doc = 1;
+  const auto idx = read_file(dir + "/compat.idx"), fn = read_file(dir + "/compat.fieldnorm");
+  files::load_field(*seg, label, IndexRecordOption::WithFreqsAndPositions, idx, &fn);
+  // the `.term` dictionary is N2: the TermInfo of the only term is supplied (postings bytes 0..2 of the sub-file)
+  seg->fields[label.id].term_dict["dateformat"] = TermInfo{1, 0, 2};
+  return Index::from_segments(sb.build(), {seg});
+}
+
+static void test_host_compat_framing(const std::string& dir) {
+  const auto idx = read_file(dir + "/compat.idx");
+  CHECK(!idx.empty());
+  const files::Footer f = files::read_footer(idx.data(), idx.size());
+  CHECK(f.index_format_version == 7);
+  auto parts = files::open_composite(idx.data(), f.body_len);
+  CHECK(parts.size() == 2);  // label (text) and date fields
+  Index index = index_from_compat_files(dir);
+  const SegmentData& seg = *index.segments()[0];
+  CHECK(seg.fields[0].total_num_tokens() == 1);
+  CHECK(seg.fields[0].idx_body.size() == 10 && seg.fields[0].idx_body[8] == 0x80 && seg.fields[0].idx_body[9] == 0x81);
+  CHECK(seg.fields[0].fieldnorms.size() == 1 && seg.fields[0].fieldnorms[0] == 1);
+  auto corrupted = idx;
+  corrupted[0] ^= 1;
+  bool crc = false;
+  try { files::read_footer(corrupted.data(), corrupted.size()); } catch (const TantivyError& e) { crc = e.kind() == TantivyError::DataCorruption; }
+  CHECK(crc);
+}
+
+static void test_compat_index_search(const std::string& dir) {  // GPU: a segment the reference wrote, searched on the device
+  Index index = index_from_compat_files(dir);
+  Field label = *index.schema().get_field("label");
+  Searcher searcher = index.reader().searcher();
+  auto top = searcher.search(TermQuery(Term::from_field_text(label, "dateformat"), IndexRecordOption::WithFreqs), TopDocs::with_limit(3));
+  CHECK(top.size() == 1);
+  CHECK(top[0].second == DocAddress(0, 0));
+  CHECK_NEARLY(top[0].first, 0.28768212);  // one doc, one token: idf(1,1) * 2.2 * 1/(1+1.2)
+}
+
+// ---- --dump -------------------------------------------------------------------------------------------------------------
+static void write_file(const std::string& path, const uint8_t* p, size_t n) {
+  std::ofstream f(path, std::ios::binary);
+  f.write(reinterpret_cast<const char*>(p), (std::streamsize)n);
+}
+static std::string json_escape(const std::string& s) {
+  std::string o;
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o += '\\'; o += (char)c; }
+    else if (c < 0x20 || c >= 0x7F) { char b[8]; std::snprintf(b, sizeof b, "\\u%04x", c); o += b; }
+    else o += (char)c;
+  }
+  return o;
+}
+static void dump_all(const std::string& dir) {
+  std::ostringstream m;
+  m << "{\n";
+  auto all = all_indexes();
+  for (size_t n = 0; n < all.size(); ++n) {
+    const Index& ix = all[n].index;
+    m << "  \"" << all[n].name << "\": {\"fields\": [";
+    for (uint32_t f = 0; f < ix.schema().num_fields(); ++f) m << (f ? ", " : "") << "\"" << ix.schema().get_field_entry(Field{f}).name << "\"";
+    m << "], \"segments\": [\n";
+    for (size_t s = 0; s < ix.segments().size(); ++s) {
+      const SegmentData& sd = *ix.segments()[s];
+      m << "    {\"max_doc\": " << sd.max_doc << ", \"alive\": ";
+      if (sd.alive.empty()) m << "null";
+      else {
+        const std::string p = all[n].name + ".seg" + std::to_string(s) + ".alive";
+        write_file(dir + "/" + p, sd.alive.data(), sd.alive.size());
+        m << "\"" << p << "\"";
+      }
+      m << ", \"fields\": [";
+      for (uint32_t f = 0; f < sd.fields.size(); ++f) {
+        const FieldSegmentData& fd = sd.fields[f];
+        const std::string base = all[n].name + ".seg" + std::to_string(s) + ".f" + std::to_string(f);
+        write_file(dir + "/" + base + ".idx", fd.idx_body.data(), fd.idx_body.size());
+        if (fd.has_fieldnorms) write_file(dir + "/" + base + ".fieldnorm", fd.fieldnorms.data(), fd.fieldnorms.size());
+        m << (f ? ", " : "") << "{\"record\": " << (int)fd.record << ", \"idx\": \"" << base << ".idx\", \"fieldnorm\": "
+          << (fd.has_fieldnorms ? "\"" + base + ".fieldnorm\"" : std::string("null")) << ", \"terms\": {";
+        bool first = true;
+        for (auto& kv : fd.term_dict) {
+          m << (first ? "" : ", ") << "\"" << json_escape(kv.first) << "\": [" << kv.second.doc_freq << ", " << kv.second.postings_start << ", "
+            << kv.second.postings_end << "]";
+          first = false;
+        }
+        m << "}}";
+      }
+      m << "]}" << (s + 1 < ix.segments().size() ? "," : "") << "\n";
+    }
+    m << "  ]}" << (n + 1 < all.size() ? "," : "") << "\n";
+  }
+  m << "}\n";
+  const std::string text = m.str();
+  write_file(dir + "/manifest.json", reinterpret_cast<const uint8_t*>(text.data()), text.size());
+}
+
+int main(int argc, char** argv) {
+  std::string mode = argc > 1 ? argv[1] : "";
+  std::string dir = argc > 2 ? argv[2] : "";
+  if (mode == "--dump") {
+    dump_all(dir);
+    return 0;
+  }
+  std::vector<std::pair<std::string, std::function<void()>>> tests;
+  if (mode == "--cpu") {
+    tests = {{"host_tokenizer_and_statistics", test_host_tokenizer_and_statistics},
+             {"host_search_without_device_raises", test_host_search_without_device_raises}};
+    if (!dir.empty()) tests.push_back({"host_compat_framing", [dir]() { test_host_compat_framing(dir); }});
+  } else {
+    tests = {{"term_query_no_freq", test_term_query_no_freq},
+             {"term_query_multiple_of_block_len", test_term_query_multiple_of_block_len},
+             {"term_weight", test_term_weight},
+             {"boolean_query_with_weight", test_boolean_query_with_weight},
+             {"intersection_score", test_intersection_score},
+             {"top_collector", test_top_collector},
+             {"multi_segment_deletes_and_paging", test_multi_segment_deletes_and_paging},
+             {"absent_terms_and_unsupported_shapes", test_absent_terms_and_unsupported_shapes},
+             {"host_tokenizer_and_statistics", test_host_tokenizer_and_statistics}};
+    if (mode == "--compat" && !dir.empty()) tests.push_back({"compat_index_search", [dir]() { test_compat_index_search(dir); }});
+  }
+  int bad = 0;
+  for (auto& t : tests) {
+    const int before = g_failed;
+    try {
+      t.second();
+    } catch (const std::exception& e) {
+      std::printf("    exception: %s\n", e.what());
+      ++g_failed;
+    }
+    std::printf("%s %s\n", g_failed == before ? "ok  " : "FAIL", t.first.c_str());
+    bad += g_failed != before;
+  }
+  std::printf("%d test(s) failed\n", bad);
+  return bad ? 1 : 0;
+}
