@@ -77,8 +77,12 @@ typedef struct {
  * term_flags       = optional [n_terms] bytes (NULL = all 0).  TQ_TERM_IGNORE_FREQ: the clause is a
  *                    TermQuery::new(term, IndexRecordOption::Basic) on a field indexed WITH term
  *                    frequencies: the reference then skips the tf blocks and scores with tf = 1
- *                    (FreqReadingOption::SkipFreq, block_segment_postings.rs:97-140,343-360). */
+ *                    (FreqReadingOption::SkipFreq, block_segment_postings.rs:97-140,343-360).
+ * flags/threshold  = TQ_QUERY_HAS_THRESHOLD: only docs with score > threshold are collected -- the initial
+ *                    `threshold` argument of Weight::for_each_pruning (src/query/weight.rs:123-132); a caller that
+ *                    already holds k hits (another shard, an earlier page) passes its k-th score to prune more. */
 #define TQ_TERM_IGNORE_FREQ 1u
+#define TQ_QUERY_HAS_THRESHOLD 1u
 typedef struct {
   int32_t op;
   uint32_t n_terms;
@@ -89,6 +93,8 @@ typedef struct {
   const float* avg_fieldnorm;
   const float* tf_cache;
   const uint8_t* term_flags;
+  uint32_t flags;
+  float threshold;
 } tq_query;
 
 /* Counters of the last finished batch (per ctx). */

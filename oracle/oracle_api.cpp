@@ -79,8 +79,10 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
   }
   if (scorers.empty()) return;
   TopNHeap top_n(q.k);
+  const bool has_threshold = (q.flags & TQ_QUERY_HAS_THRESHOLD) && q.threshold == q.threshold;
   auto push = [&](uint32_t doc, Score score) {
     if (!seg->is_alive(doc)) return;
+    if (has_threshold && !(score > q.threshold)) return;  // for_each_pruning(threshold, ..): only scores above it (weight.rs:123-132)
     top_n.push(score, doc);
   };
   if (mode == 0) {
@@ -90,14 +92,18 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
     } else if (q.op == TQ_OP_AND) {
       for_each_intersection(scorers, push);
     } else {
+      // canonical union order: descending Bm25Weight.weight, ties in clause order (the reference's order is data
+      // dependent: block_wand_union.rs:205-208, buffered_union.rs:69-85) -- SumCombiner then adds in this order
+      std::stable_sort(scorers.begin(), scorers.end(), [](const TermScorer& a, const TermScorer& b) { return a.similarity_weight.weight > b.similarity_weight.weight; });
       for_each_union(scorers, push);
     }
   } else {
-    Score threshold = std::numeric_limits<Score>::lowest();
+    Score threshold = has_threshold ? q.threshold : std::numeric_limits<Score>::lowest();
+    const Score initial_threshold = threshold;
     PruningCallback cb = [&](uint32_t doc, Score score) -> Score {
       if (!seg->is_alive(doc)) return threshold;  // sort_by_score.rs:44-53
       top_n.push(score, doc);
-      threshold = top_n.threshold_or_min();
+      threshold = std::max(initial_threshold, top_n.threshold_or_min());
       return threshold;
     };
     if (scorers.size() == 1) block_wand_single_scorer(scorers[0], threshold, cb);

@@ -14,6 +14,7 @@ TERMINATED = 0x7FFFFFFF
 TQ_MAX_K = 1024
 TQ_MAX_TERMS = 32
 TQ_TERM_IGNORE_FREQ = 1
+TQ_QUERY_HAS_THRESHOLD = 1
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -52,14 +53,17 @@ class Query(C.Structure):
         ("avg_fieldnorm", f32p),
         ("tf_cache", f32p),
         ("term_flags", u8p),
+        ("flags", C.c_uint32),
+        ("threshold", C.c_float),
     ]
 
 
 QUERY_DTYPE = np.dtype(
     [("op", "<i4"), ("n_terms", "<u4"), ("k", "<u4"), ("n_term_segs", "<u4"),
-     ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8"), ("term_flags", "<u8")]
+     ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8"), ("term_flags", "<u8"),
+     ("flags", "<u4"), ("threshold", "<f4")]
 )
-assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 56
+assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 64
 
 
 class Stats(C.Structure):
@@ -103,7 +107,8 @@ class QueryBatch:
     `queries` is an iterable of dicts / objects with fields
       op, k, weights[n_terms], avg_fieldnorm[n_terms], term_segs: list of
       (term_idx, segment_ord, field, doc_freq, postings_start, postings_end),
-      tf_cache (optional [n_terms,256]), term_flags (optional [n_terms] bytes, TQ_TERM_IGNORE_FREQ).
+      tf_cache (optional [n_terms,256]), term_flags (optional [n_terms] bytes, TQ_TERM_IGNORE_FREQ),
+      threshold (optional float: only docs scoring above it are collected).
     Built with numpy so that a batch of thousands of queries marshals in milliseconds.
     """
 
@@ -149,6 +154,9 @@ class QueryBatch:
                 cache = np.ascontiguousarray(cache, dtype=np.float32).reshape(nt, 256)
                 self.caches.append(cache)
                 row["tf_cache"] = cache.ctypes.data
+            if q.get("threshold") is not None:
+                row["flags"] = TQ_QUERY_HAS_THRESHOLD
+                row["threshold"] = q["threshold"]
             flags = q.get("term_flags")
             if flags is not None:
                 flags = np.ascontiguousarray(flags, dtype=np.uint8).reshape(nt)

@@ -103,7 +103,8 @@ struct BatchParams {
   uint32_t n_queries;
   unsigned long long* counters;  // [8] k_or window routes: 0 skipped, 1 exhaustive, 2 pruned+scored, 3 pruned+empty,
                                  //     4 essential overflow, 5 promising overflow, 6 promising docs, 7 essential postings
-  uint32_t or_prune;             // 0 disables the MaxScore route (A/B measurements)
+  uint32_t or_prune;             // 0 disables the MaxScore route of k_or (A/B measurements)
+  uint32_t strip_prune;          // 0 disables the essential / non-essential split of k_or_strip
 };
 
 // ---- small helpers ---------------------------------------------------------------------------

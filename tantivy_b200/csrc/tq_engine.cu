@@ -130,7 +130,7 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;
-  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1;
+  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 16;
 };
 
 struct tq_batch {
@@ -145,10 +145,11 @@ struct tq_batch {
   BatchParams params{};
   size_t desc_bytes = 0;
   uint32_t nq = 0, kmax = 0;
-  uint32_t n_units[4] = {0, 0, 0, 0};    // term, and, or (window kernel), or (strip kernel)
-  uint32_t unit_base[4] = {0, 0, 0, 0};
+  uint32_t n_units[5] = {0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), or (strip kernel, threshold sample)
+  uint32_t unit_base[5] = {0, 0, 0, 0, 0};
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
+  size_t qinit_off = 0;
   size_t qstate_off = 0, cands_off = 0, res_off = 0, res_bytes = 0, n_cands = 0;
   tq_stats stats{};
   bool ran = false;
@@ -164,6 +165,13 @@ struct tq_batch {
   } while (0)
 
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// host twin of score_to_key (tq_device.cuh): order-preserving u32 image of a float
+static uint32_t host_score_key(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
 
 extern "C" {
 
@@ -185,6 +193,8 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
   c->or_strip = env_u32("TQ_OR_STRIP", 1);
   c->or_pipe = env_u32("TQ_OR_PIPE", 1);
+  c->strip_sample_div = env_u32("TQ_STRIP_SAMPLE_DIV", 16);  // share of a pair's windows in the threshold sample (0/1: off)
+  c->strip_prune = env_u32("TQ_STRIP_PRUNE", 1);  // MaxScore split inside k_or_strip (exact)
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long));
@@ -414,7 +424,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
-  std::vector<Unit> units[4];
+  std::vector<Unit> units[5];
   std::vector<DQuery> dq(nq);
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
@@ -425,6 +435,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   std::vector<int> qseg_op;
   std::vector<uint32_t> qseg_total;
   uint32_t n_qsegs_op[4] = {0, 0, 0, 0};
+  std::vector<char> qseg_sample;  // strip pairs that get a threshold sample pass (MaxScore can then skip their dense clauses)
   uint32_t strip_cached_max = 0, or_max_lists = 0;
   {
     std::lock_guard<std::mutex> g(c->mu);
@@ -501,10 +512,19 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         }
         qs.max_doc = seg->max_doc;
         qs.alive = seg->d_alive;
-        qs.flags = uniform_fn ? 1u : 0u;
         qs.fieldnorm = uniform_fn ? fn0 : nullptr;
         if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
           std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
+        bool prunable = false;
+        if (op == TQ_OP_OR) {
+          // Canonical union order = descending Bm25Weight.weight, ties in clause order (the reference's own order is
+          // data dependent, block_wand_union.rs:205-208): the f32 sum is taken in this order, and the clauses with the
+          // smallest score bounds form a suffix, which is what the MaxScore split of k_or_strip needs.
+          std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.second.weight > b.second.weight; });
+          prunable = true;
+          for (auto& h : here) prunable = prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
+        }
+        qs.flags = (uniform_fn ? 1u : 0u) | (prunable ? 2u : 0u);
         int unit_class = op;
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
           // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
@@ -525,6 +545,11 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
         qsegs.push_back(qs);
         qseg_op.push_back(unit_class);
+        {
+          bool any_thick = false;
+          for (auto& h : here) any_thick = any_thick || (h.second.pad & 1u) == 0;
+          qseg_sample.push_back(unit_class == 3 && prunable && any_thick);
+        }
         qseg_total.push_back(unit_class == 3 ? (qs.max_doc + kWin - 1) / kWin : (op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total));
         ++n_qsegs_op[unit_class];
         i = j;
@@ -544,7 +569,18 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       const uint32_t want_units = std::max<uint32_t>(1u, (target_units + n_qsegs_op[op] - 1) / n_qsegs_op[op]);
       const uint32_t per = std::max<uint32_t>(min_per, (total + want_units - 1) / want_units);
       const uint32_t k = dq[qsegs[s].query].k;
-      for (uint32_t b0 = 0; b0 < total; b0 += per) {
+      // Threshold sample: the first 1/sample_div of a strip pair's windows run in a launch of their own; the exact k-th
+      // best score over all sampled windows of the query (k_theta) then seeds the threshold of the main launch, whose
+      // MaxScore split drops the dense clauses from the first window on.  Nothing is scored twice.
+      uint32_t first = 0;
+      if (op == 3 && qseg_sample[s] && c->strip_sample_div > 1 && total >= 8u * c->strip_sample_div) {
+        first = std::max<uint32_t>(kStripWarps, total / c->strip_sample_div);
+        for (uint32_t b0 = 0; b0 < first; b0 += per) {
+          units[4].push_back(Unit{(uint32_t)s, b0, std::min(first, b0 + per), 0});
+          q_cands[qsegs[s].query] += (size_t)kStripWarps * k;
+        }
+      }
+      for (uint32_t b0 = first; b0 < total; b0 += per) {
         units[op].push_back(Unit{(uint32_t)s, b0, std::min(total, b0 + per), 0});
         q_cands[qsegs[s].query] += op == 3 ? (size_t)kStripWarps * k : 2u * (size_t)k;  // what one unit may hand over
       }
@@ -568,11 +604,12 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
-  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size();
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size();
   b->strip_cached_max = strip_cached_max;
   b->or_max_lists = or_max_lists;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
   const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
+  const size_t o_qinit = off; off = align(off + std::max<size_t>(nq, 1) * sizeof(QState));  // per-run initial state (threshold keys)
   b->desc_bytes = off;
   TQ_CUDA(b->pin.ensure(off + 256));
   TQ_CUDA(b->dev.ensure(off + 256));
@@ -582,7 +619,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   {
     Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
     uint32_t base = 0;
-    for (int op = 0; op < 4; ++op) {
+    for (int op = 0; op < 5; ++op) {
       b->unit_base[op] = base;
       b->n_units[op] = (uint32_t)units[op].size();
       if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
@@ -590,6 +627,19 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     }
   }
   if (!dq.empty()) memcpy(b->pin.p + o_queries, dq.data(), dq.size() * sizeof(DQuery));
+  {
+    QState* qi0 = reinterpret_cast<QState*>(b->pin.p + o_qinit);
+    for (size_t qi = 0; qi < std::max<size_t>(nq, 1); ++qi) {
+      qi0[qi].theta = 0; qi0[qi].cand_count = 0;
+      if (qi < nq && (queries[qi].flags & TQ_QUERY_HAS_THRESHOLD)) {
+        // collect score > threshold: the smallest accepted key is the next representable score (NaN: no filter)
+        float th = queries[qi].threshold;
+        if (th == 0.0f) th = 0.0f;  // -0.0 and +0.0 are the same threshold
+        if (th == th) { const uint32_t key = host_score_key(th); qi0[qi].theta = key == 0xFFFFFFFFu ? key : key + 1u; }
+      }
+    }
+  }
+  b->qinit_off = o_qinit;
 
   // ---- scratch: qstate | candidates | results ------------------------------------------------------
   b->kmax = kmax;
@@ -624,6 +674,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   P.n_queries = (uint32_t)nq;
   P.counters = c->d_counters;
   P.or_prune = c->or_prune;
+  P.strip_prune = c->strip_prune;
 
   TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
   TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));
@@ -637,7 +688,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
-  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size(); b->stats.units_or_strip = units[3].size();
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size(); b->stats.units_or_strip = units[3].size() + units[4].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
@@ -649,7 +700,7 @@ int tq_batch_run(tq_batch* b) {
   TQ_CUDA(cudaSetDevice(b->ctx->device));
   const BatchParams& P = b->params;
   uint64_t launches = 0;
-  TQ_CUDA(cudaMemsetAsync(P.qstate, 0, std::max<size_t>(b->nq, 1) * sizeof(QState), b->stream));
+  TQ_CUDA(cudaMemcpyAsync(P.qstate, b->dev.p + b->qinit_off, std::max<size_t>(b->nq, 1) * sizeof(QState), cudaMemcpyDeviceToDevice, b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
   if (b->n_units[TQ_OP_TERM]) { k_term<<<b->n_units[TQ_OP_TERM], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_TERM]); ++launches; }
   TQ_CUDA(cudaEventRecord(b->ev_op[0], b->stream));
@@ -662,6 +713,11 @@ int tq_batch_run(tq_batch* b) {
     else
       k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
     ++launches;
+  }
+  if (b->n_units[4]) {  // threshold sample, then the exact k-th best of the sample per query
+    k_or_strip<<<b->n_units[4], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[4], b->strip_cached_max);
+    k_theta<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P);
+    launches += 2;
   }
   if (b->n_units[3]) { k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches; }
   TQ_CUDA(cudaGetLastError());

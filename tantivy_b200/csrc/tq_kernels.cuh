@@ -782,6 +782,49 @@ __device__ __noinline__ void strip_compact(unsigned long long* keys, uint32_t& c
   __syncwarp();
 }
 
+// Decodes block j of a thin clause into the warp's cache, scored (one conflict-free 16-byte store per lane and array).
+__device__ __noinline__ void strip_cache_block(const ListDesc& L, uint32_t j, const Scorer sc, uint32_t max_doc, StripCache& cc, uint32_t lane) {
+  uint32_t doc[4], tf[4];
+  decode_block(L, j, lane, doc, tf);
+  uint32_t cd[4];
+  float cs[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool valid = doc[i] < max_doc;
+    cd[i] = valid ? doc[i] : kNoDoc;
+    cs[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
+  }
+  reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);
+  reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+  __syncwarp();
+}
+
+// Positions a thin clause on the first posting >= lo: keeps the cached block when it still reaches lo, else seeks through
+// the block table (SkipReader::seek) and caches that block.  cur = block in the cache (n_total: exhausted).
+__device__ __noinline__ void strip_thin_seek(const ListDesc& L, const Scorer sc, uint32_t max_doc, StripCache& cc, bool cache_valid,
+                                                uint32_t lo, uint32_t lane, uint32_t& cur, uint32_t& pos, uint32_t& next_doc) {
+  uint32_t j = cur;
+  if (!(cache_valid && j < L.n_total && __ldg(L.last_doc + j) >= lo)) {
+    j = first_block_ge(L.last_doc, cache_valid ? j + 1u : 0u, L.n_total, lo, lane);
+    cur = j;
+    if (j >= L.n_total) { pos = 128u; next_doc = kNoDoc; return; }
+    strip_cache_block(L, j, sc, max_doc, cc, lane);
+  }
+  uint32_t below = 0;  // entries are in doc order, padding is kNoDoc: count what lies before lo
+#pragma unroll
+  for (uint32_t g = 0; g < 4; ++g) below += (uint32_t)__popc(__ballot_sync(kFull, cc.doc[g * 32u + lane] < lo));
+  pos = below;
+  next_doc = below < 128u ? cc.doc[below] : kNoDoc;
+}
+
+// MaxScore on top of the strips (exact).  The planner orders a union's clauses by descending Bm25Weight.weight — that is
+// the order the f32 sum is taken in — so the clauses whose upper bounds (score < weight, since tf/(tf+norm) < 1) add up
+// to less than the current threshold are always a SUFFIX of the clause list: the non-essential clauses.  Per window the
+// warp applies the essential prefix; if the largest partial sum plus the non-essential bound cannot reach the threshold,
+// the window is cold and the non-essential clauses (the dense, expensive ones) are not decoded at all; otherwise they
+// are added on top, in order, which continues the very same f32 sum.  A doc without any essential posting scores below
+// the threshold by construction.  Non-essential clauses fall behind while windows stay cold and catch up through the
+// block table when a window turns hot.
 __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P, uint32_t unit_base, uint32_t n_cached_max) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ ListDesc s_list[kStripMaxLists];
@@ -806,8 +849,12 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
   const uint32_t w_end = U.begin + (uint32_t)(((unsigned long long)n_win * (warp + 1)) / kStripWarps);
   for (uint32_t i = lane; i < kWin; i += 32) W.acc[i] = neg_zero;
   const bool staged_fn = (S.flags & 1u) && S.fieldnorm != nullptr;
-  bool any_thick = false;
+  const bool prunable = (S.flags & 2u) != 0 && P.strip_prune != 0;  // every weight finite and >= 0
+  uint32_t thick_mask = 0;
+  uint32_t n_e_min = 0;  // only the thick clauses at the end of the list may turn non-essential: thin ones are cheap to
+                         // apply and every clause kept essential tightens the cold-window test
   uint32_t cnt = 0;
+  uint32_t n_exh = 0, n_hot = 0, n_cold = 0;
   unsigned long long theta = (unsigned long long)(*(volatile unsigned int*)&qs->theta) << 32;
   if (w_begin < w_end) {
     // ---- strip start: position every clause -------------------------------------------------------------
@@ -815,43 +862,39 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
     for (uint32_t t = 0; t < S.n_lists; ++t) {
       const ListDesc& L = s_list[t];
       const bool thin = (s_ql[t].pad & 1u) != 0;
-      const uint32_t j = first_block_ge(L.last_doc, 0, L.n_total, lo0, lane);
       if (!thin) {
-        any_thick = true;
+        thick_mask |= 1u << t;
+        const uint32_t j = first_block_ge(L.last_doc, 0, L.n_total, lo0, lane);
         if (lane == 0) { W.cur[t] = j; W.next_doc[t] = 0; }
       } else {
-        uint32_t nd = kNoDoc;
-        if (j < L.n_total) {
-          StripCache& cc = C[s_ql[t].pad >> 1];
-          const Scorer sc = make_scorer(P, s_ql[t]);
-          uint32_t doc[4], tf[4];
-          decode_block(L, j, lane, doc, tf);
-          uint32_t below = 0;
-          uint32_t cd[4];
-          float cs[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const bool valid = doc[i] < S.max_doc;
-            cd[i] = valid ? doc[i] : kNoDoc;
-            cs[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
-            if (valid && doc[i] >= lo0) nd = min(nd, doc[i]);
-            below += (valid && doc[i] < lo0) ? 1u : 0u;
-          }
-          reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);  // one conflict-free 16-B store
-          reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
-          nd = warp_min(nd);
-          below = __reduce_add_sync(kFull, below);  // entries before the strip: already behind the cursor
-          if (lane == 0) W.pos[t] = below;
-        }
-        if (lane == 0) { W.cur[t] = j; W.next_doc[t] = nd; }
+        uint32_t cur = 0, pos = 0, nd = kNoDoc;
+        strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, C[s_ql[t].pad >> 1], false, lo0, lane, cur, pos, nd);
+        if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; }
       }
     }
     __syncwarp();
+    if (P.strip_prune != 3u) {  // (3: A/B switch, any clause may turn non-essential)
+      n_e_min = S.n_lists;
+      while (n_e_min > 0 && (thick_mask >> (n_e_min - 1u)) & 1u) --n_e_min;
+    }
     // ---- the windows ---------------------------------------------------------------------------------------
     uint32_t since_refresh = 0;
     for (uint32_t w = w_begin; w < w_end; ++w) {
-      if (!any_thick) {  // only thin clauses: jump to the window of the next unread doc
-        uint32_t nd = lane < S.n_lists ? W.next_doc[lane] : kNoDoc;
+      const float theta_f = threshold_score((uint32_t)(theta >> 32));
+      // essential prefix [0, n_e) / non-essential suffix and its score bound under the current threshold
+      uint32_t n_e = S.n_lists;
+      float ne_bound = 0.0f;
+      if (prunable && theta_f > 0.0f) {
+        while (n_e > n_e_min) {
+          const float nb = ne_bound + s_ql[n_e - 1u].weight;
+          if (!(nb * 1.00001f < theta_f)) break;
+          ne_bound = nb;
+          --n_e;
+        }
+        if (n_e == 0) break;  // no doc of this segment can reach the threshold any more
+      }
+      if (!(thick_mask & ((1u << n_e) - 1u))) {  // only thin essential clauses: jump to the window of their next unread doc
+        uint32_t nd = lane < n_e ? W.next_doc[lane] : kNoDoc;
         nd = warp_min(nd);
         if (nd == kNoDoc) break;
         const uint32_t wj = nd / kWin;
@@ -867,16 +910,21 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
         const unsigned long long gt = (unsigned long long)g << 32;
         if (gt > theta) theta = gt;
       }
-      if (staged_fn && any_thick) {
-        const uint4* src = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
-        uint4* dst = reinterpret_cast<uint4*>(W.fn);
-        dst[lane] = __ldg(src + lane);
-        dst[lane + 32] = __ldg(src + lane + 32);
-        __syncwarp();
-      }
-      bool dirty = false;   // the window received at least one score
-      float wmax = 0.0f;    // largest partial sum written by this lane (scores are non-negative: it bounds the final sums)
+      bool fn_ready = false;  // the window's fieldnorm bytes are staged when the first thick clause needs them
+      bool dirty = false;     // the window received at least one score
+      bool cold = false;
+      float wmax = 0.0f;      // largest partial sum written by this lane (scores are non-negative: it bounds the final sums)
       for (uint32_t t = 0; t < S.n_lists; ++t) {
+        if (t == n_e) {  // the essential clauses are in: can the rest still lift a doc of this window over the threshold?
+          const float mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(wmax)));
+          if ((mx + ne_bound) * 1.00001f < theta_f) { cold = true; break; }
+          if (P.strip_prune == 2u) {  // instrumentation: how many docs of a hot window are promising at all?
+            uint32_t np = 0;
+            for (uint32_t i = lane; i < kWin; i += 32) np += ((W.acc[i] + ne_bound) * 1.00001f >= theta_f) ? 1u : 0u;
+            np = __reduce_add_sync(kFull, np);
+            if (lane == 0 && np) atomicAdd(&P.counters[4], (unsigned long long)np);
+          }
+        }
         const ListDesc& L = s_list[t];
         const bool thin = (s_ql[t].pad & 1u) != 0;
         if (!thin) {
@@ -885,12 +933,16 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           if (cur >= L.n_total) continue;
           uint4 r;
           unsigned m;
-          for (;;) {
+          {
             const uint32_t idx = cur + lane;
             r = idx < L.n_total ? __ldg(L.tab4 + idx) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
             m = __ballot_sync(kFull, r.x >= lo);
-            if (m) break;
-            cur += 32;
+            if (!m) {  // the clause sat out many windows: seek through the block table
+              cur = first_block_ge(L.last_doc, cur + 32u, L.n_total, lo, lane);
+              const uint32_t idx2 = cur + lane;
+              r = idx2 < L.n_total ? __ldg(L.tab4 + idx2) : make_uint4(0xFFFFFFFFu, 0, 0, 0);
+              m = __ballot_sync(kFull, r.x >= lo);
+            }
           }
           uint32_t src = (uint32_t)__ffs(m) - 1u;
           uint32_t j = cur + src;
@@ -903,6 +955,14 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           if (rec.w != 0xFFFFFFFFu && rec.w + 1u >= hi) continue;  // the block starts at or after the window's end
           BlockFetch f;
           fetch_issue_rec(L, rec, lane, f);
+          if (staged_fn && !fn_ready) {
+            const uint4* fsrc = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
+            uint4* dst = reinterpret_cast<uint4*>(W.fn);
+            dst[lane] = __ldg(fsrc + lane);
+            dst[lane + 32] = __ldg(fsrc + lane + 32);
+            __syncwarp();
+            fn_ready = true;
+          }
           dirty = true;
           for (;;) {
             uint32_t doc[4], tf[4];
@@ -966,6 +1026,13 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
         } else {
           // ---- thin clause: the decoded block lives in shared memory ---------------------------------------
           StripCache& cc = C[s_ql[t].pad >> 1];
+          if (W.next_doc[t] < lo) {  // it sat out some windows as a non-essential clause: skip what lies before this one
+            uint32_t cur = W.cur[t], pos = 0, nd = kNoDoc;
+            strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, cc, cur < L.n_total, lo, lane, cur, pos, nd);
+            __syncwarp();
+            if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; }
+            __syncwarp();
+          }
           for (;;) {
             if (W.next_doc[t] >= hi) break;  // nothing of this clause in the window (also: clause exhausted)
             // entries are in doc order: the window's postings are the next few entries, one per lane
@@ -991,35 +1058,21 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             }
             // block used up: bring in the next one
             const uint32_t jb = W.cur[t] + 1u;
-            if (jb >= L.n_total) { if (lane == 0) W.next_doc[t] = kNoDoc; __syncwarp(); break; }
-            const Scorer sc = make_scorer(P, s_ql[t]);
-            uint32_t doc[4], tf[4];
-            decode_block(L, jb, lane, doc, tf);
-            uint32_t first = kNoDoc;
-            uint32_t cd[4];
-            float cs[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool valid = doc[i] < S.max_doc;
-              cd[i] = valid ? doc[i] : kNoDoc;
-              cs[i] = valid ? bm25_score(sc, L.fieldnorm, doc[i], tf[i]) : 0.0f;
-              if (valid) first = min(first, doc[i]);
-            }
-            reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);
-            reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
-            first = warp_min(first);
+            if (jb >= L.n_total) { if (lane == 0) { W.cur[t] = L.n_total; W.next_doc[t] = kNoDoc; } __syncwarp(); break; }
+            strip_cache_block(L, jb, make_scorer(P, s_ql[t]), S.max_doc, cc, lane);
+            const uint32_t first = cc.doc[0];  // a block's first entry is always a real doc
             if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; W.pos[t] = 0; }
             __syncwarp();
           }
         }
       }
+      if (n_e == S.n_lists) ++n_exh; else if (cold) ++n_cold; else ++n_hot;
       // ---- harvest -----------------------------------------------------------------------------------------------
       if (dirty) {
-        const float theta_f = threshold_score((uint32_t)(theta >> 32));
         // the largest partial sum any lane wrote bounds every final score of the window (scores >= 0; a negative
         // one makes the uint compare fail safe): when it is below the threshold the window is only cleared
         const uint32_t mx = __reduce_max_sync(kFull, __float_as_uint(wmax));
-        const bool may_pass = !(theta_f > 0.0f) || mx >= __float_as_uint(theta_f);
+        const bool may_pass = !cold && (!(theta_f > 0.0f) || mx >= __float_as_uint(theta_f));
         for (uint32_t g = 0; g < kWin / 128; ++g) {
           const uint32_t idx = g * 128 + lane * 4;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1051,6 +1104,11 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
       }
       __syncwarp();  // cursor updates of this window are visible to the next one
     }
+  }
+  if (lane == 0 && P.counters) {
+    if (n_exh) atomicAdd(&P.counters[1], (unsigned long long)n_exh);
+    if (n_hot) atomicAdd(&P.counters[2], (unsigned long long)n_hot);
+    if (n_cold) atomicAdd(&P.counters[3], (unsigned long long)n_cold);
   }
   // ---- hand the survivors over ------------------------------------------------------------------------------
   if (cnt > Q.k) strip_compact(W.keys, cnt, Q.k, theta, &qs->theta, lane);
@@ -1418,6 +1476,44 @@ __device__ __noinline__ void sort_pairs_desc(unsigned long long* a, uint32_t* b,
       __syncthreads();
     }
   }
+}
+
+// The exact k-th largest score key among a query's candidates so far (4-pass radix select) becomes a lower bound of
+// its threshold: run between the sampled windows and the main launch of k_or_strip.
+__global__ void __launch_bounds__(kThreads) k_theta(const BatchParams P) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_need;
+  const uint32_t q = blockIdx.x;
+  const DQuery Q = P.queries[q];
+  const uint32_t C = min(P.qstate[q].cand_count, Q.cand_cap);
+  if (C < Q.k) return;  // fewer than k hits so far: no bound
+  const Cand* cands = P.cands + Q.cand_base;
+  if (threadIdx.x == 0) { s_prefix = 0; s_need = Q.k; }
+  uint32_t mask = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
+      const uint32_t key = cands[i].score_key;
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t need = s_need, bsel = 0;
+      for (int bin = 255; bin >= 0; --bin) {
+        const uint32_t h = s_hist[bin];
+        if (h >= need) { bsel = (uint32_t)bin; break; }
+        need -= h;
+      }
+      s_need = need;
+      s_prefix = prefix | (bsel << shift);
+    }
+    mask |= 0xFFu << shift;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicMax(&P.qstate[q].theta, s_prefix);
 }
 
 // Exact top-k of a query's candidates. Small sets are sorted directly; large ones go through a

@@ -218,6 +218,35 @@ def test_basic_option_requested_on_a_field_with_freqs(ctx):
     assert [s for s, _, _ in hits(g, 0)] != [s for s, _, _ in hits(g, nq - 1)]  # the flag changes the scores
 
 
+def test_initial_threshold_like_for_each_pruning(ctx):
+    """tq_query.threshold = the `threshold` argument of Weight::for_each_pruning (weight.rs:123-132): only docs scoring
+    strictly above it are collected; passing the k-th score of a finished search returns the k-1 docs above it."""
+    rng = np.random.default_rng(660)
+    segs = _random_segments(rng, 3, 5)
+    base = [make_query(op, segs, terms, 20) for op, terms in
+            [(TQ_OP_TERM, [1]), (TQ_OP_AND, [0, 1]), (TQ_OP_OR, [0, 1, 2, 3, 4]), (TQ_OP_OR, [4, 2]), (TQ_OP_OR, [0, 3, 4])]]
+    oi = both(ctx, segs)
+    qb0 = QueryBatch(base)
+    g0, c0 = ctx.search_batch(qb0), oi.search_batch(qb0, mode=0)
+    assert_same(g0, c0, qb0.nq)
+    queries = []
+    for i, q in enumerate(base):
+        h = hits(g0, i)
+        for thr in (h[len(h) // 2][0], h[-1][0], h[0][0], 0.0, -1.0, 1e9):
+            q2 = dict(q)
+            q2["threshold"] = float(thr)
+            q2["k"] = 50
+            queries.append(q2)
+    qb = QueryBatch(queries)
+    g, c, nq = ctx.search_batch(qb), oi.search_batch(qb, mode=0), qb.nq
+    assert_same(g, c, nq)
+    for i, q in enumerate(queries):
+        assert all(s > np.float32(q["threshold"]) for s, _, _ in hits(g, i))
+    mid = hits(g0, 2)[10][0]  # the OR query again, threshold = its 11th score: exactly the hits above it come back
+    above = [h for h in hits(g0, 2) if h[0] > mid]
+    assert hits(g, 2 * 6)[:len(above)] == above
+
+
 def test_ties_pick_lowest_doc(ctx):
     # every doc has the same length and tf: all scores tie; the top-k must be the k lowest doc ids
     max_doc = 5000

@@ -154,3 +154,26 @@ def test_basic_requested_on_freq_field_scores_with_tf_one():
         out.append([hits(ix.search_batch(QueryBatch([q]), mode=m)) for m in (0, 1)])
     assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
     assert out[0][0] != out[2][0]
+
+
+def test_initial_threshold_exhaustive_vs_pruned():
+    """for_each_pruning(threshold, ..) (weight.rs:123-132): with an initial threshold both oracle paths return the
+    docs scoring strictly above it."""
+    rng = np.random.default_rng(12)
+    max_doc = 4000
+    lists = []
+    for p in (0.4, 0.1, 0.02):
+        docs = np.nonzero(rng.random(max_doc) < p)[0].astype(np.uint32)
+        lists.append((docs, rng.integers(1, 6, size=len(docs)).astype(np.uint32)))
+    seg = OracleSegment(lists, rng.integers(1, 300, size=max_doc))
+    ix = O.OracleIndex()
+    seg.register(ix)
+    for op, terms in [(TQ_OP_TERM, [1]), (TQ_OP_AND, [0, 1]), (TQ_OP_OR, [0, 1, 2])]:
+        q = make_query(op, [seg], terms, 30)
+        full = hits(ix.search_batch(QueryBatch([q]), mode=0))
+        thr = full[12][0]
+        q["threshold"] = float(thr)
+        a = hits(ix.search_batch(QueryBatch([q]), mode=0))
+        b = hits(ix.search_batch(QueryBatch([q]), mode=1))
+        assert a == [h for h in full if h[0] > thr]
+        assert [(g, d) for _, g, d in a] == [(g, d) for _, g, d in b]
