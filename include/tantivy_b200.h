@@ -113,9 +113,11 @@ typedef struct {
   float term_ms, and_ms, or_ms, final_ms; /* per-kernel device time (CUDA events on the launching stream) */
   uint64_t units_term, units_and, units_or; /* CTAs launched per kernel */
   uint64_t bytes_term, bytes_and, bytes_or; /* algorithmic bytes per kernel (same formula) */
-  /* cumulative since ctx creation: k_or doc-id windows by route: 0 skipped, 1 exhaustive, 2 entered the
-   * MaxScore route, 3 ..and had no promising doc, 4 essential-list overflow, 5 promising overflow,
-   * 6 promising docs scored exactly, 7 essential postings scored */
+  /* cumulative since ctx creation.  k_or_strip (default union kernel): [1] windows scored exhaustively (no
+   * non-essential clause under the threshold), [2] hot windows (non-essential clauses applied after the essential
+   * ones), [3] cold windows (essential clauses only), [5] bytes of packed postings + fieldnorms actually read
+   * (the roofline figure of a pruned kernel).  k_or with TQ_OR_PRUNE=1 uses the slots for its own
+   * routes (0 skipped, 1 exhaustive, 2 MaxScore route, 3 no promising doc, 4/5 overflows, 6/7 docs/postings scored). */
   uint64_t or_windows[8];
   uint64_t units_or_strip; /* of units_or: CTAs of the barrier-free strip kernel (k_or_strip); the rest ran k_or / k_or_pipe */
 } tq_stats;

@@ -105,6 +105,8 @@ struct BatchParams {
                                  //     4 essential overflow, 5 promising overflow, 6 promising docs, 7 essential postings
   uint32_t or_prune;             // 0 disables the MaxScore route of k_or (A/B measurements)
   uint32_t strip_prune;          // 0 disables the essential / non-essential split of k_or_strip
+  uint32_t strip_ne_div;         // clauses with >= 1 posting per this many docs may turn non-essential
+  uint32_t strip_ne_div2;        // ...and the densest clause of a union without such a clause, under this looser bound
 };
 
 // ---- small helpers ---------------------------------------------------------------------------

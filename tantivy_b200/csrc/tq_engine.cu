@@ -130,7 +130,7 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;
-  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 16;
+  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_ne_div = 8, strip_ne_div2 = 64;
 };
 
 struct tq_batch {
@@ -145,8 +145,8 @@ struct tq_batch {
   BatchParams params{};
   size_t desc_bytes = 0;
   uint32_t nq = 0, kmax = 0;
-  uint32_t n_units[5] = {0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), or (strip kernel, threshold sample)
-  uint32_t unit_base[5] = {0, 0, 0, 0, 0};
+  uint32_t n_units[6] = {0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold samples 1 and 2
+  uint32_t unit_base[6] = {0, 0, 0, 0, 0, 0};
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
   size_t qinit_off = 0;
@@ -193,7 +193,10 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->or_tiles_per_unit = env_u32("TQ_OR_TILES_PER_UNIT", 16);
   c->or_strip = env_u32("TQ_OR_STRIP", 1);
   c->or_pipe = env_u32("TQ_OR_PIPE", 1);
-  c->strip_sample_div = env_u32("TQ_STRIP_SAMPLE_DIV", 16);  // share of a pair's windows in the threshold sample (0/1: off)
+  c->strip_sample_div = env_u32("TQ_STRIP_SAMPLE_DIV", 32);  // share of a pair's windows in the threshold sample (0/1: off)
+  c->strip_sample_div2 = env_u32("TQ_STRIP_SAMPLE_DIV2", 8);  // second sample round ends at this share (0/1: one round only)
+  c->strip_ne_div = env_u32("TQ_STRIP_NE_DIV", 8);
+  c->strip_ne_div2 = env_u32("TQ_STRIP_NE_DIV2", 64);
   c->strip_prune = env_u32("TQ_STRIP_PRUNE", 1);  // MaxScore split inside k_or_strip (exact)
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
@@ -424,7 +427,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
-  std::vector<Unit> units[5];
+  std::vector<Unit> units[6];
   std::vector<DQuery> dq(nq);
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
@@ -547,7 +550,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         qseg_op.push_back(unit_class);
         {
           bool any_thick = false;
-          for (auto& h : here) any_thick = any_thick || (h.second.pad & 1u) == 0;
+          for (auto& h : here) any_thick = any_thick || (uint64_t)h.first * std::max(c->strip_ne_div, c->strip_ne_div2) >= qs.max_doc;
           qseg_sample.push_back(unit_class == 3 && prunable && any_thick);
         }
         qseg_total.push_back(unit_class == 3 ? (qs.max_doc + kWin - 1) / kWin : (op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total));
@@ -574,11 +577,15 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       // MaxScore split drops the dense clauses from the first window on.  Nothing is scored twice.
       uint32_t first = 0;
       if (op == 3 && qseg_sample[s] && c->strip_sample_div > 1 && total >= 8u * c->strip_sample_div) {
-        first = std::max<uint32_t>(kStripWarps, total / c->strip_sample_div);
-        for (uint32_t b0 = 0; b0 < first; b0 += per) {
-          units[4].push_back(Unit{(uint32_t)s, b0, std::min(first, b0 + per), 0});
-          q_cands[qsegs[s].query] += (size_t)kStripWarps * k;
-        }
+        const uint32_t cut1 = std::max<uint32_t>(kStripWarps, total / c->strip_sample_div);
+        const uint32_t cut2 = c->strip_sample_div2 > 1 && c->strip_sample_div2 < c->strip_sample_div ? std::max(cut1, total / c->strip_sample_div2) : cut1;
+        const uint32_t cuts[3] = {0, cut1, cut2};
+        for (int r = 0; r < 2; ++r)  // round r covers [cuts[r], cuts[r+1]); a k_theta pass follows each round
+          for (uint32_t b0 = cuts[r]; b0 < cuts[r + 1]; b0 += per) {
+            units[4 + r].push_back(Unit{(uint32_t)s, b0, std::min(cuts[r + 1], b0 + per), 0});
+            q_cands[qsegs[s].query] += (size_t)kStripWarps * k;
+          }
+        first = cut2;
       }
       for (uint32_t b0 = first; b0 < total; b0 += per) {
         units[op].push_back(Unit{(uint32_t)s, b0, std::min(total, b0 + per), 0});
@@ -604,7 +611,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
-  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size();
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size();
   b->strip_cached_max = strip_cached_max;
   b->or_max_lists = or_max_lists;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
@@ -619,7 +626,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   {
     Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
     uint32_t base = 0;
-    for (int op = 0; op < 5; ++op) {
+    for (int op = 0; op < 6; ++op) {
       b->unit_base[op] = base;
       b->n_units[op] = (uint32_t)units[op].size();
       if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
@@ -675,6 +682,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   P.counters = c->d_counters;
   P.or_prune = c->or_prune;
   P.strip_prune = c->strip_prune;
+  P.strip_ne_div = c->strip_ne_div;
+  P.strip_ne_div2 = c->strip_ne_div2;
 
   TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
   TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));
@@ -688,7 +697,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
-  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size(); b->stats.units_or_strip = units[3].size() + units[4].size();
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size() + units[5].size(); b->stats.units_or_strip = units[3].size() + units[4].size() + units[5].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
@@ -714,8 +723,9 @@ int tq_batch_run(tq_batch* b) {
       k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
     ++launches;
   }
-  if (b->n_units[4]) {  // threshold sample, then the exact k-th best of the sample per query
-    k_or_strip<<<b->n_units[4], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[4], b->strip_cached_max);
+  for (int r = 4; r <= 5; ++r) {  // threshold samples: after each round the exact k-th best so far, per query
+    if (!b->n_units[r]) continue;
+    k_or_strip<<<b->n_units[r], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[r], b->strip_cached_max);
     k_theta<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P);
     launches += 2;
   }

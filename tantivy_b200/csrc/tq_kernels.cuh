@@ -715,7 +715,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_or(const BatchParams P, uint32_
 //  * thinner clauses keep their current block DECODED AND SCORED in shared memory (docs + scores); a window only
 //    looks at it when the block's next unread doc falls inside the window, so a block is decoded once per strip.
 // Eligible when k <= kStripMaxK, <= kStripMaxLists clauses and <= kMaxCached thin clauses; otherwise k_or.
-constexpr uint32_t kWin = 1024;
+#ifndef TQ_KWIN
+#define TQ_KWIN 1024
+#endif
+constexpr uint32_t kWin = TQ_KWIN;  // docs per window (multiple of 512)
 constexpr uint32_t kWBuf = 256;
 constexpr uint32_t kMaxCached = 6;
 constexpr uint32_t kStripWarps = 4;
@@ -731,6 +734,7 @@ struct StripWarpFixed {  // per warp, dynamic shared memory; followed by n_cache
   uint32_t cur[kStripMaxLists];       // thick: first block that can still matter; thin: block held in the cache
   uint32_t next_doc[kStripMaxLists];  // thin: smallest cached doc not applied yet (kNoDoc: clause exhausted)
   uint32_t pos[kStripMaxLists];       // thin: its index in the cached block (entries are in doc order)
+  uint32_t stat[8];                   // lane 0: windows by route (1 exhaustive, 2 hot, 3 cold), [5] 16-byte units read
 };
 struct StripCache {
   uint32_t doc[128];
@@ -783,7 +787,7 @@ __device__ __noinline__ void strip_compact(unsigned long long* keys, uint32_t& c
 }
 
 // Decodes block j of a thin clause into the warp's cache, scored (one conflict-free 16-byte store per lane and array).
-__device__ __noinline__ void strip_cache_block(const ListDesc& L, uint32_t j, const Scorer sc, uint32_t max_doc, StripCache& cc, uint32_t lane) {
+__device__ __noinline__ uint32_t strip_cache_block(const ListDesc& L, uint32_t j, const Scorer sc, uint32_t max_doc, StripCache& cc, uint32_t lane) {
   uint32_t doc[4], tf[4];
   decode_block(L, j, lane, doc, tf);
   uint32_t cd[4];
@@ -797,24 +801,27 @@ __device__ __noinline__ void strip_cache_block(const ListDesc& L, uint32_t j, co
   reinterpret_cast<uint4*>(cc.doc)[lane] = make_uint4(cd[0], cd[1], cd[2], cd[3]);
   reinterpret_cast<float4*>(cc.score)[lane] = make_float4(cs[0], cs[1], cs[2], cs[3]);
   __syncwarp();
+  // bytes this touched, in 16-byte units: the packed block (or the decoded tail) + one fieldnorm byte per posting
+  return (j < L.n_blocks ? (__ldg(&L.blk[j + 1].x) - __ldg(&L.blk[j].x)) / 16u : L.tail_n / 2u) + 8u;
 }
 
 // Positions a thin clause on the first posting >= lo: keeps the cached block when it still reaches lo, else seeks through
 // the block table (SkipReader::seek) and caches that block.  cur = block in the cache (n_total: exhausted).
-__device__ __noinline__ void strip_thin_seek(const ListDesc& L, const Scorer sc, uint32_t max_doc, StripCache& cc, bool cache_valid,
-                                                uint32_t lo, uint32_t lane, uint32_t& cur, uint32_t& pos, uint32_t& next_doc) {
-  uint32_t j = cur;
+__device__ __noinline__ uint32_t strip_thin_seek(const ListDesc& L, const Scorer sc, uint32_t max_doc, StripCache& cc, bool cache_valid,
+                                                    uint32_t lo, uint32_t lane, uint32_t& cur, uint32_t& pos, uint32_t& next_doc) {
+  uint32_t j = cur, touched16 = 0;
   if (!(cache_valid && j < L.n_total && __ldg(L.last_doc + j) >= lo)) {
     j = first_block_ge(L.last_doc, cache_valid ? j + 1u : 0u, L.n_total, lo, lane);
     cur = j;
-    if (j >= L.n_total) { pos = 128u; next_doc = kNoDoc; return; }
-    strip_cache_block(L, j, sc, max_doc, cc, lane);
+    if (j >= L.n_total) { pos = 128u; next_doc = kNoDoc; return 0; }
+    touched16 = strip_cache_block(L, j, sc, max_doc, cc, lane);
   }
   uint32_t below = 0;  // entries are in doc order, padding is kNoDoc: count what lies before lo
 #pragma unroll
   for (uint32_t g = 0; g < 4; ++g) below += (uint32_t)__popc(__ballot_sync(kFull, cc.doc[g * 32u + lane] < lo));
   pos = below;
   next_doc = below < 128u ? cc.doc[below] : kNoDoc;
+  return touched16;
 }
 
 // MaxScore on top of the strips (exact).  The planner orders a union's clauses by descending Bm25Weight.weight — that is
@@ -854,7 +861,8 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
   uint32_t n_e_min = 0;  // only the thick clauses at the end of the list may turn non-essential: thin ones are cheap to
                          // apply and every clause kept essential tightens the cold-window test
   uint32_t cnt = 0;
-  uint32_t n_exh = 0, n_hot = 0, n_cold = 0;
+  if (lane < 8) W.stat[lane] = 0;  // [5]: postings and fieldnorm bytes actually read, in 16-byte units (pruned kernels)
+  __syncwarp();
   unsigned long long theta = (unsigned long long)(*(volatile unsigned int*)&qs->theta) << 32;
   if (w_begin < w_end) {
     // ---- strip start: position every clause -------------------------------------------------------------
@@ -868,14 +876,16 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
         if (lane == 0) { W.cur[t] = j; W.next_doc[t] = 0; }
       } else {
         uint32_t cur = 0, pos = 0, nd = kNoDoc;
-        strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, C[s_ql[t].pad >> 1], false, lo0, lane, cur, pos, nd);
-        if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; }
+        const uint32_t t16 = strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, C[s_ql[t].pad >> 1], false, lo0, lane, cur, pos, nd);
+        if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; W.stat[5] += t16; }
       }
     }
     __syncwarp();
-    if (P.strip_prune != 3u) {  // (3: A/B switch, any clause may turn non-essential)
+    {  // a clause may turn non-essential when it has at least one posting per ne_div docs (thick clauses: 1 per 8)
       n_e_min = S.n_lists;
-      while (n_e_min > 0 && (thick_mask >> (n_e_min - 1u)) & 1u) --n_e_min;
+      while (n_e_min > 0 && (unsigned long long)s_list[n_e_min - 1u].doc_freq * P.strip_ne_div >= S.max_doc) --n_e_min;
+      // no such clause: the single densest one may still go if it is dense enough to matter (strip_ne_div2)
+      if (n_e_min == S.n_lists && n_e_min > 1 && (unsigned long long)s_list[n_e_min - 1u].doc_freq * P.strip_ne_div2 >= S.max_doc) --n_e_min;
     }
     // ---- the windows ---------------------------------------------------------------------------------------
     uint32_t since_refresh = 0;
@@ -958,15 +968,17 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           if (staged_fn && !fn_ready) {
             const uint4* fsrc = reinterpret_cast<const uint4*>(S.fieldnorm + lo);
             uint4* dst = reinterpret_cast<uint4*>(W.fn);
-            dst[lane] = __ldg(fsrc + lane);
-            dst[lane + 32] = __ldg(fsrc + lane + 32);
+            for (uint32_t i = lane; i < kWin / 16u; i += 32) dst[i] = __ldg(fsrc + i);
             __syncwarp();
             fn_ready = true;
+            if (lane == 0) W.stat[5] += kWin / 16u;
           }
           dirty = true;
+          uint32_t t16 = 0;  // 16-byte units of packed postings read for this clause and window
           for (;;) {
             uint32_t doc[4], tf[4];
             const bool small_tf = ((f.meta >> 8) & 63u) <= 4u;  // (the VInt tail's marker reads as 63 bits)
+            t16 += f.meta == 0xFFFFFFFFu ? L.tail_n / 2u : (f.meta & 31u) + ((f.meta >> 8) & 63u);
             fetch_decode(L, j, f, lane, doc, tf);
             // the next block is needed iff this one ends before the window does
             const bool more = rec.x < hi - 1u && j + 1u < L.n_total;
@@ -1022,15 +1034,16 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             }
             if (!more) break;
           }
+          if (lane == 0) W.stat[5] += t16;
           __syncwarp();
         } else {
           // ---- thin clause: the decoded block lives in shared memory ---------------------------------------
           StripCache& cc = C[s_ql[t].pad >> 1];
           if (W.next_doc[t] < lo) {  // it sat out some windows as a non-essential clause: skip what lies before this one
             uint32_t cur = W.cur[t], pos = 0, nd = kNoDoc;
-            strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, cc, cur < L.n_total, lo, lane, cur, pos, nd);
+            const uint32_t t16 = strip_thin_seek(L, make_scorer(P, s_ql[t]), S.max_doc, cc, cur < L.n_total, lo, lane, cur, pos, nd);
             __syncwarp();
-            if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; }
+            if (lane == 0) { W.cur[t] = cur; W.pos[t] = pos; W.next_doc[t] = nd; W.stat[5] += t16; }
             __syncwarp();
           }
           for (;;) {
@@ -1059,14 +1072,14 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             // block used up: bring in the next one
             const uint32_t jb = W.cur[t] + 1u;
             if (jb >= L.n_total) { if (lane == 0) { W.cur[t] = L.n_total; W.next_doc[t] = kNoDoc; } __syncwarp(); break; }
-            strip_cache_block(L, jb, make_scorer(P, s_ql[t]), S.max_doc, cc, lane);
+            const uint32_t t16 = strip_cache_block(L, jb, make_scorer(P, s_ql[t]), S.max_doc, cc, lane);
             const uint32_t first = cc.doc[0];  // a block's first entry is always a real doc
-            if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; W.pos[t] = 0; }
+            if (lane == 0) { W.cur[t] = jb; W.next_doc[t] = first; W.pos[t] = 0; W.stat[5] += t16; }
             __syncwarp();
           }
         }
       }
-      if (n_e == S.n_lists) ++n_exh; else if (cold) ++n_cold; else ++n_hot;
+      if (lane == 0) ++W.stat[n_e == S.n_lists ? 1 : (cold ? 3 : 2)];
       // ---- harvest -----------------------------------------------------------------------------------------------
       if (dirty) {
         // the largest partial sum any lane wrote bounds every final score of the window (scores >= 0; a negative
@@ -1105,11 +1118,9 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
       __syncwarp();  // cursor updates of this window are visible to the next one
     }
   }
-  if (lane == 0 && P.counters) {
-    if (n_exh) atomicAdd(&P.counters[1], (unsigned long long)n_exh);
-    if (n_hot) atomicAdd(&P.counters[2], (unsigned long long)n_hot);
-    if (n_cold) atomicAdd(&P.counters[3], (unsigned long long)n_cold);
-  }
+  __syncwarp();
+  if (P.counters && (lane == 1 || lane == 2 || lane == 3 || lane == 5) && W.stat[lane])
+    atomicAdd(&P.counters[lane], (unsigned long long)W.stat[lane] * (lane == 5 ? 16ull : 1ull));
   // ---- hand the survivors over ------------------------------------------------------------------------------
   if (cnt > Q.k) strip_compact(W.keys, cnt, Q.k, theta, &qs->theta, lane);
   unsigned base = 0;

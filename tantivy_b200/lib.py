@@ -9,7 +9,7 @@ import numpy as np
 from ._abi import Query, QueryBatch, Stats, TermSeg, f32p, ptr, u8p, u32p, u64p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "_lib", "libtantivy_b200.so")
+SO_PATH = os.environ.get("TANTIVY_B200_LIB") or os.path.join(_HERE, "_lib", "libtantivy_b200.so")  # (override: A/B builds)
 
 
 class TqError(RuntimeError):
