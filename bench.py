@@ -247,9 +247,11 @@ def main():
     prepared = [ctx.prepare(qbs[i % len(qbs)]) for i in range(n_total)]  # also warms the block-table cache
     barrier_sync()
     for i in range(args.warmup):
-        prepared[i].run()
         if world > 1:
+            cross_gpu_merge.run(prepared[i])
             cross_gpu_merge(prepared[i])
+        else:
+            prepared[i].run()
     barrier_sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -261,15 +263,16 @@ def main():
     touched0 = ctx.stats()["or_windows"][5]  # cumulative bytes the pruned union kernel actually read
     t0 = time.perf_counter()
     for i in range(args.warmup, n_total):
-        prepared[i].run()
         if world > 1:
+            cross_gpu_merge.run(prepared[i])  # threshold exchange between the sample and the main pass
             cross_gpu_merge(prepared[i])
         else:
+            prepared[i].run()
             prepared[i].results_dev()  # waits for the step
         stats = ctx.stats()
         for key in kern:
             kern[key].append(stats[key])
-        launches += stats["kernel_launches"] + (1 if world > 1 else 0)
+        launches += stats["kernel_launches"] + (3 if world > 1 else 0)  # + threshold export / import, cross-GPU merge
     barrier_sync()
     dt_value = time.perf_counter() - t0
     touched_per_step = (stats["or_windows"][5] - touched0) / max(args.steps, 1) if stats else 0
@@ -292,7 +295,7 @@ def main():
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
         else:
             bt = ctx.prepare(qbs[i % len(qbs)])
-            bt.run()
+            cross_gpu_merge.run(bt)
             o = cross_gpu_merge(bt)
             st = ctx.stats()
             h2d, d2h = st["h2d_bytes"], 0

@@ -158,6 +158,16 @@ int tq_search_batch(tq_ctx*, const tq_query* queries, size_t nq, uint32_t out_st
  * fetch   = D2H of the result rows. */
 int tq_batch_prepare(tq_ctx*, const tq_query* queries, size_t nq, tq_batch** out);
 int tq_batch_run(tq_batch*);
+/* The run in two halves, for callers that shard an index over several GPUs/processes: phase 0 = everything up to the
+ * unions' threshold samples (each query now holds the exact k-th best score over its sampled windows), phase 1 = the
+ * rest.  Between the two, tq_batch_thresholds_export_dev writes the nq score keys (order-preserving u32 image of the
+ * f32 score, zero-extended to int64; 0 = no bound yet) to a DEVICE array; the caller takes the element-wise MAX over all
+ * shards (e.g. ncclAllReduce) and hands it back with tq_batch_thresholds_import_dev.  Every shard then prunes against
+ * the best bound any shard found: a valid lower bound of the global k-th score (SURVEY.md §8e "broadcast the running
+ * global threshold").  tq_batch_run == phase 0 + phase 1. */
+int tq_batch_run_phase(tq_batch*, int phase);
+int tq_batch_thresholds_export_dev(tq_batch*, int64_t* keys_dev);
+int tq_batch_thresholds_import_dev(tq_batch*, const int64_t* keys_dev);
 int tq_batch_fetch(tq_batch*, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord,
                    uint32_t* out_doc, uint32_t* out_count);
 /* Device pointers of the result rows of a finished run: row stride = k_max of the batch. */

@@ -1527,6 +1527,15 @@ __global__ void __launch_bounds__(kThreads) k_theta(const BatchParams P) {
   if (threadIdx.x == 0) atomicMax(&P.qstate[q].theta, s_prefix);
 }
 
+__global__ void k_theta_export(const QState* __restrict__ qs, long long* __restrict__ out, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (long long)qs[i].theta;
+}
+__global__ void k_theta_import(QState* __restrict__ qs, const long long* __restrict__ in, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMax(&qs[i].theta, (unsigned int)in[i]);
+}
+
 // Exact top-k of a query's candidates. Small sets are sorted directly; large ones go through a
 // 4-pass radix select on the score key (O(C)), then only the survivors and the boundary ties are sorted.
 __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {

@@ -33,6 +33,9 @@ def _load():
     lib.tq_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_prepare.argtypes = [vp, C.POINTER(Query), sz, C.POINTER(vp)]
     lib.tq_batch_run.argtypes = [vp]
+    lib.tq_batch_run_phase.argtypes = [vp, C.c_int]
+    lib.tq_batch_thresholds_export_dev.argtypes = [vp, vp]
+    lib.tq_batch_thresholds_import_dev.argtypes = [vp, vp]
     lib.tq_batch_fetch.argtypes = [vp, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_results_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
     lib.tq_batch_results_copy_dev.argtypes = [vp, vp, vp, vp, vp]
@@ -265,6 +268,17 @@ class Batch:
 
     def run(self):
         _check(LIB.tq_batch_run(self.h), self.ctx.h)
+
+    def run_phase(self, phase):
+        """0: up to the unions' threshold samples; 1: the rest (see tq_batch_run_phase)."""
+        _check(LIB.tq_batch_run_phase(self.h, phase), self.ctx.h)
+
+    def thresholds_export_dev(self, keys_dev):
+        """keys_dev: device address of nq int64 (e.g. a torch tensor's data_ptr()); waits for the batch's stream."""
+        _check(LIB.tq_batch_thresholds_export_dev(self.h, keys_dev), self.ctx.h)
+
+    def thresholds_import_dev(self, keys_dev):
+        _check(LIB.tq_batch_thresholds_import_dev(self.h, keys_dev), self.ctx.h)
 
     def fetch(self, out=None):
         stride, scores, segs, docs, counts = out or self.qb.alloc_out()

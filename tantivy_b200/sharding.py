@@ -105,7 +105,19 @@ class CrossGpuMerger:
         self.l = (mk((nq, k), f32), mk((nq, k), i32), mk((nq, k), i32), mk((nq,), i32))
         self.g = (mk((self.world, nq, k), f32), mk((self.world, nq, k), i32), mk((self.world, nq, k), i32), mk((self.world, nq), i32))
         self.o = (mk((nq, k), f32), mk((nq, k), i32), mk((nq, k), i32), mk((nq,), i32))
+        self.theta = mk((nq,), torch.int64)
         self.torch = torch
+
+    def run(self, batch):
+        """Runs a prepared batch with the cross-rank threshold exchange: phase 0 (up to the unions' threshold samples),
+        all-reduce MAX of the per-query score keys over NCCL (8 bytes per query), phase 1.  Every rank then prunes
+        against the best lower bound any rank found."""
+        batch.run_phase(0)
+        batch.thresholds_export_dev(self.theta.data_ptr())  # waits for the batch's stream
+        self.dist.all_reduce(self.theta, op=self.dist.ReduceOp.MAX)
+        self.torch.cuda.synchronize()
+        batch.thresholds_import_dev(self.theta.data_ptr())
+        batch.run_phase(1)
 
     def __call__(self, batch):
         """batch: a finished tantivy_b200.Batch of this rank. Returns merged device tensors (every rank)."""

@@ -403,3 +403,37 @@ def test_merge_topk_dev_matches_merge_fruits(ctx, synth):
     assert (o_sg.cpu().numpy().astype(np.uint32) == full[1]).all()
     assert (o_dc.cpu().numpy().astype(np.uint32) == full[2]).all()
     assert (o_ct.cpu().numpy().astype(np.uint32) == full[3]).all()
+
+
+def test_two_phase_run_with_threshold_exchange(ctx, synth):
+    """tq_batch_run_phase(0) / thresholds export + import / phase(1): the split run returns what the plain run returns,
+    and a foreign bound that is valid (another shard's k-th best, here: this shard's own final k-th score) only prunes."""
+    import torch
+    ix, oi, base = synth
+    qb = QueryBatch([ix.query(TQ_OP_OR, terms, k, segment_base=base)
+                     for terms, k in [([0, 1, 2, 3, 4], 100), ([0, 3, 5], 100), ([1, 2], 10), ([0, 4, 5], 50), ([2, 3, 4, 5], 100)]])
+    plain = ctx.search_batch(qb)
+    keys = torch.zeros(qb.nq, dtype=torch.int64, device="cuda:0")
+    b = ctx.prepare(qb)
+    b.run_phase(0)
+    b.thresholds_export_dev(keys.data_ptr())
+    sampled = keys.cpu().numpy().copy()
+    b.thresholds_import_dev(keys.data_ptr())
+    b.run_phase(1)
+    split = b.fetch()
+    for a, c in zip(plain, split):
+        assert (a == c).all()
+    # the exported keys are lower bounds of the final k-th score keys
+    final_kth = np.array([plain[0][i, plain[3][i] - 1] if plain[3][i] == qb.q["k"][i] else -np.inf for i in range(qb.nq)], dtype=np.float32)
+    u = final_kth.view(np.uint32).astype(np.int64)
+    final_keys = np.where(final_kth == -np.inf, 0, u ^ np.where(u >> 31, 0xFFFFFFFF, 0x80000000))
+    assert (sampled <= final_keys).all()
+    # hand the final k-th keys in as if another rank had found them: same rows again
+    b.run_phase(0)
+    keys2 = torch.from_numpy(final_keys.astype(np.int64)).to("cuda:0")
+    b.thresholds_import_dev(keys2.data_ptr())
+    b.run_phase(1)
+    again = b.fetch()
+    for a, c in zip(plain, again):
+        assert (a == c).all()
+    b.close()
