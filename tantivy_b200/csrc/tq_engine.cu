@@ -564,7 +564,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     // Work units. A unit is one CTA's share of a (query, segment). With few (query, segment) pairs in the
     // batch every pair is cut into many units (latency); with many, units grow so that a CTA's local
     // top-k threshold gets tight and few candidates reach k_final (throughput).
-    const uint32_t target_units = env_u32("TQ_TARGET_UNITS", 148u * 4u * 16u);
+    const uint32_t target_units = env_u32("TQ_TARGET_UNITS", 148u * 4u * 32u);
     std::vector<size_t> q_cands(nq, 0);
     for (size_t s = 0; s < qsegs.size(); ++s) {
       const int op = qseg_op[s];
