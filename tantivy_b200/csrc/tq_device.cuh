@@ -429,9 +429,10 @@ __device__ __noinline__ void topk_compact_hist(const TopK& t, uint32_t k, uint32
 }
 
 // End of a round of the CTA: refresh the shared threshold from the query-wide one and make room.
-__device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsigned int* theta_global) {
+// `limit`: compact as soon as this many keys are buffered (a pruning kernel wants its threshold early).
+__device__ __forceinline__ void topk_round_end(const TopK& t, uint32_t k, unsigned int* theta_global, uint32_t limit = kCap - kRoundMargin) {
   topk_sync(t);
-  if (*t.count > kCap - kRoundMargin) topk_compact_hist(t, k, kCap - kRoundMargin, theta_global);
+  if (*t.count > limit) topk_compact_hist(t, k, kCap - kRoundMargin, theta_global);
   if (threadIdx.x == 0) {
     const unsigned long long g = (unsigned long long)(*(volatile unsigned int*)theta_global) << 32;
     if (g > *t.theta) *t.theta = g;

@@ -520,6 +520,10 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
           std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
         bool prunable = false;
+        if (op == TQ_OP_AND) {
+          prunable = true;
+          for (auto& h : here) prunable = prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
+        }
         if (op == TQ_OP_OR) {
           // Canonical union order = descending Bm25Weight.weight, ties in clause order (the reference's own order is
           // data dependent, block_wand_union.rs:205-208): the f32 sum is taken in this order, and the clauses with the

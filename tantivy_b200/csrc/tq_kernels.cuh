@@ -273,15 +273,35 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
   if (threadIdx.x == 0) { s_top.count = 0; s_top.theta = (unsigned long long)qs->theta << 32; }
   __syncthreads();
   const TopK T{s_top.keys, &s_top.count, &s_top.theta, &s_top.scratch, P.counters, 0u, (unsigned)kThreads};
-  for (uint32_t r = U.begin; r < U.end; r += kWarps) {
+  // MaxScore for the conjunction (exact): a leader doc whose own score plus the secondaries' bounds (score < weight)
+  // cannot reach the threshold is dropped BEFORE its secondary blocks are looked up and decoded -- the lookups are
+  // what this kernel spends its time on (block_wand_intersection.rs:60-120 prunes on block maxima for the same reason).
+  const bool prunable = (S.flags & 2u) != 0;
+  const Scorer sc0 = make_scorer(P, ql0);
+  float ub_secondaries = 0.0f;
+  for (uint32_t s = 1; s < S.n_lists; ++s) ub_secondaries += P.qlists[S.lists_base + s].weight;
+  // Without a threshold the first round would look up every leader doc of 8 blocks; one block (one warp) is enough to
+  // get a first threshold, the other seven then start pruned.
+  bool narrow = prunable && s_top.theta == 0ull;
+  for (uint32_t r = U.begin; r < U.end;) {
+    const uint32_t width = narrow ? 1u : (uint32_t)kWarps;
     const uint32_t b = r + warp;
-    if (b < U.end) {
+    if (warp < width && b < U.end) {
       uint32_t doc[4], tf0[4];
       decode_block(L0, b, lane, doc, tf0);
       uint32_t alive_m = 0;
 #pragma unroll
       for (int i = 0; i < 4; ++i) alive_m |= (doc[i] < S.max_doc) ? (1u << i) : 0u;  // rejects tail padding
       float total[4] = {0.f, 0.f, 0.f, 0.f};
+      float ub = ub_secondaries;
+      const float theta_f = prunable ? threshold_score((uint32_t)(*(volatile unsigned long long*)T.theta >> 32)) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if ((alive_m >> i) & 1u) {
+          total[i] = bm25_score(sc0, L0.fieldnorm, doc[i], tf0[i]);
+          if (theta_f > 0.0f && (total[i] + ub) * 1.00001f < theta_f) alive_m &= ~(1u << i);
+        }
+      }
       for (uint32_t s = 1; s < S.n_lists; ++s) {
         if (__ballot_sync(kFull, alive_m != 0) == 0) break;
         const QList qls = P.qlists[S.lists_base + s];
@@ -317,11 +337,12 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
           }
           cur = j + 1;
         }
+        ub -= qls.weight;  // what the clauses still to come can add at most
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if ((alive_m >> i) & 1u) {
-            if (s == 1) total[i] = bm25_score(make_scorer(P, ql0), L0.fieldnorm, doc[i], tf0[i]);
             total[i] = __fadd_rn(total[i], bm25_score(sc_s, Ls.fieldnorm, doc[i], stf[i]));
+            if (theta_f > 0.0f && s + 1u < S.n_lists && (total[i] + ub) * 1.00001f < theta_f) alive_m &= ~(1u << i);
           }
         }
       }
@@ -334,7 +355,9 @@ __global__ void __launch_bounds__(kThreads) k_and(const BatchParams P, uint32_t 
         topk_push(T, pass, key, lane);
       }
     }
-    topk_round_end(T, Q.k, &qs->theta);
+    topk_round_end(T, Q.k, &qs->theta, !prunable ? kCap - kRoundMargin : (narrow ? Q.k : min(max(4u * Q.k, 128u), kCap - kRoundMargin)));
+    r += width;
+    narrow = false;
   }
   topk_flush(T, Q, qs, P.cands, S.segment_ord);
 }
