@@ -267,7 +267,7 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
   if (c->segments.count({segment_ord, field})) return fail(TQ_ERR_INVALID_ARGUMENT, "segment/field already registered");
   Segment s;
   s.segment_ord = segment_ord; s.field = field; s.max_doc = max_doc; s.record_option = record_option; s.idx_len = idx_len;
-  const size_t pad = 64;  // decode_block may read one word past a block
+  const size_t pad = 256;  // decode_block reads one word past a block; the aligned block copy of k_build_tables reads 64 + 8 bytes past the last block
   TQ_CUDA(cudaMalloc(&s.d_idx, idx_len + pad));
   TQ_CUDA(cudaMemset(s.d_idx + idx_len, 0, pad));
   TQ_CUDA(cudaMemcpy(s.d_idx, idx_body, idx_len, cudaMemcpyHostToDevice));

@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
     uint32_t* dst32 = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(L.blocks));
     const uint32_t sh = mis * 8u;
     for (uint32_t i = tid; i < total_words; i += kThreads) {
-      const uint32_t w0 = src32[i], w1 = src32[i + 1];  // the segment body is padded by 64+ bytes on the device
+      const uint32_t w0 = src32[i], w1 = src32[i + 1];  // the segment body is padded by 256 bytes on the device
       dst32[i] = mis ? __funnelshift_r(w0, w1, sh) : w0;
     }
   }
