@@ -979,6 +979,7 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
           }
           uint32_t src = (uint32_t)__ffs(m) - 1u;
           uint32_t j = cur + src;
+          __syncwarp();  // every lane has read W.cur[t]
           if (lane == 0) W.cur[t] = j;
           if (j >= L.n_total) continue;
           const Scorer sc = make_scorer(P, s_ql[t]);
@@ -1094,6 +1095,7 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
             }
             // block used up: bring in the next one
             const uint32_t jb = W.cur[t] + 1u;
+            __syncwarp();  // every lane has read W.cur[t]
             if (jb >= L.n_total) { if (lane == 0) { W.cur[t] = L.n_total; W.next_doc[t] = kNoDoc; } __syncwarp(); break; }
             const uint32_t t16 = strip_cache_block(L, jb, make_scorer(P, s_ql[t]), S.max_doc, cc, lane);
             const uint32_t first = cc.doc[0];  // a block's first entry is always a real doc
@@ -1582,7 +1584,8 @@ __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
     have = min(C, Q.k);
   } else {
     // k-th largest score key (C > kCap >= k)
-    if (threadIdx.x == 0) { s_prefix = 0; s_need = Q.k; }
+    if (threadIdx.x == 0) { s_prefix = 0; s_need = Q.k; s_n = 0; }  // (s_n: set here, behind the loop's barriers -- the four
+                                                                    // words share one vector load further down)
     uint32_t mask = 0;
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
@@ -1610,8 +1613,6 @@ __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
     const uint32_t kth = s_prefix;       // exactly the k-th largest score key
     const uint32_t ties_total = s_ties;   // how many candidates carry exactly that key
     const uint32_t above_total = Q.k - s_need;  // strictly better ones (< k)
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
     if (above_total + ties_total <= kCap) {  // the usual case: one sweep, one sort
       for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) {
         const Cand c = cands[i];
