@@ -130,7 +130,7 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;
-  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_ne_div = 8, strip_ne_div2 = 64;
+  uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
 
 struct tq_batch {
@@ -145,8 +145,8 @@ struct tq_batch {
   BatchParams params{};
   size_t desc_bytes = 0;
   uint32_t nq = 0, kmax = 0;
-  uint32_t n_units[6] = {0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold samples 1 and 2
-  uint32_t unit_base[6] = {0, 0, 0, 0, 0, 0};
+  uint32_t n_units[7] = {0, 0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold rounds 1..3
+  uint32_t unit_base[7] = {0, 0, 0, 0, 0, 0, 0};
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
   size_t qinit_off = 0;
@@ -196,6 +196,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->or_pipe = env_u32("TQ_OR_PIPE", 1);
   c->strip_sample_div = env_u32("TQ_STRIP_SAMPLE_DIV", 32);  // share of a pair's windows in the threshold sample (0/1: off)
   c->strip_sample_div2 = env_u32("TQ_STRIP_SAMPLE_DIV2", 8);  // second sample round ends at this share (0/1: one round only)
+  c->strip_sample_div3 = env_u32("TQ_STRIP_SAMPLE_DIV3", 2);  // third round: up to half of the windows
   c->strip_ne_div = env_u32("TQ_STRIP_NE_DIV", 8);
   c->strip_ne_div2 = env_u32("TQ_STRIP_NE_DIV2", 64);
   c->strip_prune = env_u32("TQ_STRIP_PRUNE", 1);  // MaxScore split inside k_or_strip (exact)
@@ -428,7 +429,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
-  std::vector<Unit> units[6];
+  std::vector<Unit> units[7];
   std::vector<DQuery> dq(nq);
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
@@ -584,13 +585,14 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       if (op == 3 && qseg_sample[s] && c->strip_sample_div > 1 && total >= 8u * c->strip_sample_div) {
         const uint32_t cut1 = std::max<uint32_t>(kStripWarps, total / c->strip_sample_div);
         const uint32_t cut2 = c->strip_sample_div2 > 1 && c->strip_sample_div2 < c->strip_sample_div ? std::max(cut1, total / c->strip_sample_div2) : cut1;
-        const uint32_t cuts[3] = {0, cut1, cut2};
-        for (int r = 0; r < 2; ++r)  // round r covers [cuts[r], cuts[r+1]); a k_theta pass follows each round
+        const uint32_t cut3 = c->strip_sample_div3 > 1 && c->strip_sample_div3 < c->strip_sample_div2 ? std::max(cut2, total / c->strip_sample_div3) : cut2;
+        const uint32_t cuts[4] = {0, cut1, cut2, cut3};
+        for (int r = 0; r < 3; ++r)  // round r covers [cuts[r], cuts[r+1]); a k_theta pass follows each round
           for (uint32_t b0 = cuts[r]; b0 < cuts[r + 1]; b0 += per) {
             units[4 + r].push_back(Unit{(uint32_t)s, b0, std::min(cuts[r + 1], b0 + per), 0});
             q_cands[qsegs[s].query] += (size_t)kStripWarps * k;
           }
-        first = cut2;
+        first = cut3;
       }
       for (uint32_t b0 = first; b0 < total; b0 += per) {
         units[op].push_back(Unit{(uint32_t)s, b0, std::min(total, b0 + per), 0});
@@ -616,7 +618,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
-  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size();
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size();
   b->strip_cached_max = strip_cached_max;
   b->or_max_lists = or_max_lists;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
@@ -631,7 +633,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   {
     Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
     uint32_t base = 0;
-    for (int op = 0; op < 6; ++op) {
+    for (int op = 0; op < 7; ++op) {
       b->unit_base[op] = base;
       b->n_units[op] = (uint32_t)units[op].size();
       if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
@@ -702,7 +704,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
-  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size() + units[5].size(); b->stats.units_or_strip = units[3].size() + units[4].size() + units[5].size();
+  b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size(); b->stats.units_or_strip = units[3].size() + units[4].size() + units[5].size() + units[6].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   guard.ok = true;
   *out = b;
@@ -728,7 +730,7 @@ static int run_phase(tq_batch* b, int phase) {
         k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
       ++launches;
     }
-    for (int r = 4; r <= 5; ++r) {  // threshold samples: after each round the exact k-th best so far, per query
+    for (int r = 4; r <= 6; ++r) {  // threshold samples: after each round the exact k-th best so far, per query
       if (!b->n_units[r]) continue;
       k_or_strip<<<b->n_units[r], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[r], b->strip_cached_max);
       k_theta<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P);
