@@ -948,15 +948,11 @@ __global__ void __launch_bounds__(kStripThreads) k_or_strip(const BatchParams P,
       bool cold = false;
       float wmax = 0.0f;      // largest partial sum written by this lane (scores are non-negative: it bounds the final sums)
       for (uint32_t t = 0; t < S.n_lists; ++t) {
-        if (t == n_e) {  // the essential clauses are in: can the rest still lift a doc of this window over the threshold?
+        if (t >= n_e) {  // can the clauses still to come lift a doc of this window over the threshold?  (asked again
+                         // after every non-essential clause: the densest ones come last)
           const float mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(wmax)));
           if ((mx + ne_bound) * 1.00001f < theta_f) { cold = true; break; }
-          if (P.strip_prune == 2u) {  // instrumentation: how many docs of a hot window are promising at all?
-            uint32_t np = 0;
-            for (uint32_t i = lane; i < kWin; i += 32) np += ((W.acc[i] + ne_bound) * 1.00001f >= theta_f) ? 1u : 0u;
-            np = __reduce_add_sync(kFull, np);
-            if (lane == 0 && np) atomicAdd(&P.counters[4], (unsigned long long)np);
-          }
+          ne_bound -= s_ql[t].weight;  // (rounding stays far inside the 1e-5 margin of the test)
         }
         const ListDesc& L = s_list[t];
         const bool thin = (s_ql[t].pad & 1u) != 0;
