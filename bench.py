@@ -272,7 +272,7 @@ def main():
         stats = ctx.stats()
         for key in kern:
             kern[key].append(stats[key])
-        launches += stats["kernel_launches"] + (3 if world > 1 else 0)  # + threshold export / import, cross-GPU merge
+        launches += stats["kernel_launches"] + (7 if world > 1 else 0)  # + 3 x threshold export / import, cross-GPU merge
     barrier_sync()
     dt_value = time.perf_counter() - t0
     touched_per_step = (stats["or_windows"][5] - touched0) / max(args.steps, 1) if stats else 0

@@ -158,13 +158,15 @@ int tq_search_batch(tq_ctx*, const tq_query* queries, size_t nq, uint32_t out_st
  * fetch   = D2H of the result rows. */
 int tq_batch_prepare(tq_ctx*, const tq_query* queries, size_t nq, tq_batch** out);
 int tq_batch_run(tq_batch*);
-/* The run in two halves, for callers that shard an index over several GPUs/processes: phase 0 = everything up to the
- * unions' threshold samples (each query now holds the exact k-th best score over its sampled windows), phase 1 = the
- * rest.  Between the two, tq_batch_thresholds_export_dev writes the nq score keys (order-preserving u32 image of the
- * f32 score, zero-extended to int64; 0 = no bound yet) to a DEVICE array; the caller takes the element-wise MAX over all
- * shards (e.g. ncclAllReduce) and hands it back with tq_batch_thresholds_import_dev.  Every shard then prunes against
- * the best bound any shard found: a valid lower bound of the global k-th score (SURVEY.md §8e "broadcast the running
- * global threshold").  tq_batch_run == phase 0 + phase 1. */
+/* The run in tq_batch_phases() consecutive phases, for callers that shard an index over several GPUs/processes:
+ * phase 0 = everything up to the unions' first threshold round (each query then holds the exact k-th best score over
+ * the windows scored so far), the middle phases = the further threshold rounds, the last phase = the rest.  Between
+ * two phases tq_batch_thresholds_export_dev writes the nq score keys (order-preserving u32 image of the f32 score,
+ * zero-extended to int64; 0 = no bound yet) to a DEVICE array; the caller takes the element-wise MAX over all shards
+ * (e.g. ncclAllReduce) and hands it back with tq_batch_thresholds_import_dev.  Every shard then prunes against the best
+ * bound any shard found: a valid lower bound of the global k-th score (SURVEY.md §8e "broadcast the running global
+ * threshold").  tq_batch_run == all phases in order. */
+int tq_batch_phases(tq_batch*);
 int tq_batch_run_phase(tq_batch*, int phase);
 int tq_batch_thresholds_export_dev(tq_batch*, int64_t* keys_dev);
 int tq_batch_thresholds_import_dev(tq_batch*, const int64_t* keys_dev);

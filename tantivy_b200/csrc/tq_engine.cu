@@ -150,7 +150,7 @@ struct tq_batch {
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
   size_t qinit_off = 0;
-  bool phase0_done = false;
+  int next_phase = 0;  // of the current run (0: none started)
   size_t qstate_off = 0, cands_off = 0, res_off = 0, res_bytes = 0, n_cands = 0;
   tq_stats stats{};
   bool ran = false;
@@ -711,10 +711,15 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   return TQ_OK;
 }
 
+// Phases of a run: 0 = term / AND / window-union kernels + the unions' first threshold round, 1 and 2 = the second
+// and third threshold rounds, 3 = the unions' main launch + k_final.  Sharded callers exchange thresholds in between.
+constexpr int kPhases = 4;
+
 static int run_phase(tq_batch* b, int phase) {
   TQ_CUDA(cudaSetDevice(b->ctx->device));
   const BatchParams& P = b->params;
   uint64_t launches = 0;
+  if (phase != b->next_phase) return fail(TQ_ERR_INVALID_ARGUMENT, "phases run in order, each once per run");
   if (phase == 0) {
     TQ_CUDA(cudaMemcpyAsync(P.qstate, b->dev.p + b->qinit_off, std::max<size_t>(b->nq, 1) * sizeof(QState), cudaMemcpyDeviceToDevice, b->stream));
     TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
@@ -730,18 +735,20 @@ static int run_phase(tq_batch* b, int phase) {
         k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
       ++launches;
     }
-    for (int r = 4; r <= 6; ++r) {  // threshold samples: after each round the exact k-th best so far, per query
-      if (!b->n_units[r]) continue;
+    b->stats.kernel_launches = 0;
+  }
+  if (phase < kPhases - 1) {  // threshold round `phase`: its windows, then the exact k-th best so far per query
+    const int r = 4 + phase;
+    if (b->n_units[r]) {
       k_or_strip<<<b->n_units[r], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[r], b->strip_cached_max);
       k_theta<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P);
       launches += 2;
     }
     TQ_CUDA(cudaGetLastError());
-    b->stats.kernel_launches = launches;
-    b->phase0_done = true;
+    b->stats.kernel_launches += launches;
+    b->next_phase = phase + 1;
     return TQ_OK;
   }
-  if (!b->phase0_done) return fail(TQ_ERR_INVALID_ARGUMENT, "phase 1 before phase 0");
   if (b->n_units[3]) { k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches; }
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));
@@ -750,24 +757,29 @@ static int run_phase(tq_batch* b, int phase) {
   TQ_CUDA(cudaEventRecord(b->ev_op[3], b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_k1, b->stream));
   b->stats.kernel_launches += launches;
-  b->phase0_done = false;
+  b->next_phase = 0;
   b->ran = true;
   return TQ_OK;
 }
 
 int tq_batch_run(tq_batch* b) {
   if (!b) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
-  const int rc = run_phase(b, 0);
-  return rc != TQ_OK ? rc : run_phase(b, 1);
+  for (int p = b->next_phase; p < kPhases; ++p) {
+    const int rc = run_phase(b, p);
+    if (rc != TQ_OK) return rc;
+  }
+  return TQ_OK;
 }
 
+int tq_batch_phases(tq_batch* b) { return b ? kPhases : 0; }
+
 int tq_batch_run_phase(tq_batch* b, int phase) {
-  if (!b || phase < 0 || phase > 1) return fail(TQ_ERR_INVALID_ARGUMENT, "batch / phase");
+  if (!b || phase < 0 || phase >= kPhases) return fail(TQ_ERR_INVALID_ARGUMENT, "batch / phase");
   return run_phase(b, phase);
 }
 
 int tq_batch_thresholds_export_dev(tq_batch* b, int64_t* keys_dev) {
-  if (!b || !keys_dev || !b->phase0_done) return fail(TQ_ERR_INVALID_ARGUMENT, "export needs a batch between phase 0 and phase 1");
+  if (!b || !keys_dev || b->next_phase == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "export needs a batch between two phases of a run");
   TQ_CUDA(cudaSetDevice(b->ctx->device));
   if (b->nq) k_theta_export<<<(unsigned)((b->nq + 255) / 256), 256, 0, b->stream>>>(b->params.qstate, reinterpret_cast<long long*>(keys_dev), (uint32_t)b->nq);
   TQ_CUDA(cudaGetLastError());
@@ -776,7 +788,7 @@ int tq_batch_thresholds_export_dev(tq_batch* b, int64_t* keys_dev) {
 }
 
 int tq_batch_thresholds_import_dev(tq_batch* b, const int64_t* keys_dev) {
-  if (!b || !keys_dev || !b->phase0_done) return fail(TQ_ERR_INVALID_ARGUMENT, "import needs a batch between phase 0 and phase 1");
+  if (!b || !keys_dev || b->next_phase == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "import needs a batch between two phases of a run");
   TQ_CUDA(cudaSetDevice(b->ctx->device));
   if (b->nq) k_theta_import<<<(unsigned)((b->nq + 255) / 256), 256, 0, b->stream>>>(b->params.qstate, reinterpret_cast<const long long*>(keys_dev), (uint32_t)b->nq);
   TQ_CUDA(cudaGetLastError());

@@ -34,6 +34,7 @@ def _load():
     lib.tq_batch_prepare.argtypes = [vp, C.POINTER(Query), sz, C.POINTER(vp)]
     lib.tq_batch_run.argtypes = [vp]
     lib.tq_batch_run_phase.argtypes = [vp, C.c_int]
+    lib.tq_batch_phases.argtypes = [vp]
     lib.tq_batch_thresholds_export_dev.argtypes = [vp, vp]
     lib.tq_batch_thresholds_import_dev.argtypes = [vp, vp]
     lib.tq_batch_fetch.argtypes = [vp, C.c_uint32, f32p, u32p, u32p, u32p]
@@ -269,8 +270,11 @@ class Batch:
     def run(self):
         _check(LIB.tq_batch_run(self.h), self.ctx.h)
 
+    def phases(self):
+        return LIB.tq_batch_phases(self.h)
+
     def run_phase(self, phase):
-        """0: up to the unions' threshold samples; 1: the rest (see tq_batch_run_phase)."""
+        """Phases 0 .. phases()-1 in order; thresholds may be exchanged between two of them (tq_batch_run_phase)."""
         _check(LIB.tq_batch_run_phase(self.h, phase), self.ctx.h)
 
     def thresholds_export_dev(self, keys_dev):

@@ -109,15 +109,17 @@ class CrossGpuMerger:
         self.torch = torch
 
     def run(self, batch):
-        """Runs a prepared batch with the cross-rank threshold exchange: phase 0 (up to the unions' threshold samples),
-        all-reduce MAX of the per-query score keys over NCCL (8 bytes per query), phase 1.  Every rank then prunes
-        against the best lower bound any rank found."""
-        batch.run_phase(0)
-        batch.thresholds_export_dev(self.theta.data_ptr())  # waits for the batch's stream
-        self.dist.all_reduce(self.theta, op=self.dist.ReduceOp.MAX)
-        self.torch.cuda.synchronize()
-        batch.thresholds_import_dev(self.theta.data_ptr())
-        batch.run_phase(1)
+        """Runs a prepared batch with the cross-rank threshold exchange: after every threshold round of the unions the
+        per-query score keys are all-reduced (MAX, 8 bytes per query) over NCCL, so that every rank prunes against the
+        best lower bound any rank has found so far."""
+        n = batch.phases()
+        for phase in range(n):
+            batch.run_phase(phase)
+            if phase + 1 < n:
+                batch.thresholds_export_dev(self.theta.data_ptr())  # waits for the batch's stream
+                self.dist.all_reduce(self.theta, op=self.dist.ReduceOp.MAX)
+                self.torch.cuda.synchronize()
+                batch.thresholds_import_dev(self.theta.data_ptr())
 
     def __call__(self, batch):
         """batch: a finished tantivy_b200.Batch of this rank. Returns merged device tensors (every rank)."""

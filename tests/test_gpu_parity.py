@@ -415,11 +415,17 @@ def test_two_phase_run_with_threshold_exchange(ctx, synth):
     plain = ctx.search_batch(qb)
     keys = torch.zeros(qb.nq, dtype=torch.int64, device="cuda:0")
     b = ctx.prepare(qb)
-    b.run_phase(0)
-    b.thresholds_export_dev(keys.data_ptr())
-    sampled = keys.cpu().numpy().copy()
-    b.thresholds_import_dev(keys.data_ptr())
-    b.run_phase(1)
+    n_phases = b.phases()
+    assert n_phases >= 2
+    sampled = None
+    for phase in range(n_phases):
+        b.run_phase(phase)
+        if phase + 1 < n_phases:
+            b.thresholds_export_dev(keys.data_ptr())
+            now = keys.cpu().numpy().copy()
+            assert sampled is None or (now >= sampled).all()  # thresholds only rise
+            sampled = now
+            b.thresholds_import_dev(keys.data_ptr())
     split = b.fetch()
     for a, c in zip(plain, split):
         assert (a == c).all()
@@ -432,7 +438,8 @@ def test_two_phase_run_with_threshold_exchange(ctx, synth):
     b.run_phase(0)
     keys2 = torch.from_numpy(final_keys.astype(np.int64)).to("cuda:0")
     b.thresholds_import_dev(keys2.data_ptr())
-    b.run_phase(1)
+    for phase in range(1, n_phases):
+        b.run_phase(phase)
     again = b.fetch()
     for a, c in zip(plain, again):
         assert (a == c).all()
