@@ -152,6 +152,12 @@ int tq_search_batch(tq_ctx*, const tq_query* queries, size_t nq, uint32_t out_st
                     float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc,
                     uint32_t* out_count);
 
+/* The Count collector for the same query shapes (src/collector/count_collector.rs; Weight::count,
+ * term_weight.rs:179-219): out_counts[q] = number of ALIVE docs matching query q over all its segments.  k, weights
+ * and thresholds of the queries are ignored.  A term query on a segment without deletes is answered from doc_freq,
+ * as the reference does. */
+int tq_count_batch(tq_ctx*, const tq_query* queries, size_t nq, uint64_t* out_counts);
+
 /* The same split in three so that callers can keep inputs/outputs device resident:
  * prepare = host planning + H2D of descriptors + block-table builds (cached per term),
  * run     = scoring kernels + final top-k, results stay in HBM,

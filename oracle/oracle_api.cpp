@@ -187,6 +187,53 @@ int tqo_search_batch(tqo_index* ix, const tq_query* queries, size_t nq, int mode
   } catch (const std::exception& e) { ix->err = e.what(); return TQ_ERR_INVALID_ARGUMENT; }
 }
 
+// Count collector (src/collector/count_collector.rs): Weight::count per segment, summed.  Exhaustive iteration of the
+// scorers; alive docs only (a term query without deletes would read doc_freq: the same number).
+int tqo_count_batch(tqo_index* ix, const tq_query* queries, size_t nq, uint64_t* out_counts) {
+  try {
+    for (size_t qi = 0; qi < nq; ++qi) {
+      const tq_query& q = queries[qi];
+      std::vector<uint32_t> seg_ords;
+      for (uint32_t i = 0; i < q.n_term_segs; ++i) seg_ords.push_back(q.term_segs[i].segment_ord);
+      std::sort(seg_ords.begin(), seg_ords.end());
+      seg_ords.erase(std::unique(seg_ords.begin(), seg_ords.end()), seg_ords.end());
+      uint64_t total = 0;
+      for (uint32_t so : seg_ords) {
+        std::vector<const tq_term_seg*> per_term(q.n_terms, nullptr);
+        const OSegment* seg = nullptr;
+        for (uint32_t i = 0; i < q.n_term_segs; ++i) {
+          const tq_term_seg& ts = q.term_segs[i];
+          if (ts.segment_ord != so) continue;
+          per_term[ts.term_idx] = &ts;
+          if (!seg) seg = &ix->segs.at({ts.segment_ord, ts.field});
+        }
+        std::vector<TermScorer> scorers;
+        bool empty = false;
+        for (uint32_t t = 0; t < q.n_terms; ++t) {
+          if (!per_term[t] || per_term[t]->doc_freq == 0) { if (q.op != TQ_OP_OR) empty = true; continue; }
+          const OSegment& s = ix->segs.at({per_term[t]->segment_ord, per_term[t]->field});
+          Bm25Weight w{};
+          w.weight = 1.0f; w.average_fieldnorm = 1.0f;
+          for (int id = 0; id < 256; ++id) w.cache[id] = 1.0f;
+          scorers.push_back(make_term_scorer(s, *per_term[t], w, t));
+        }
+        if (empty || scorers.empty()) continue;
+        auto hit = [&](uint32_t doc, Score) { if (seg->is_alive(doc)) ++total; };
+        if (scorers.size() == 1) {
+          TermScorer& s = scorers[0];
+          for (uint32_t d = s.doc(); d != TERMINATED; d = s.advance()) hit(d, 0.0f);
+        } else if (q.op == TQ_OP_AND) {
+          for_each_intersection(scorers, hit);
+        } else {
+          for_each_union(scorers, hit);
+        }
+      }
+      out_counts[qi] = total;
+    }
+  } catch (const std::exception& e) { ix->err = e.what(); return TQ_ERR_INVALID_ARGUMENT; }
+  return TQ_OK;
+}
+
 int tqo_decode_postings(tqo_index* ix, const tq_term_seg* ts, uint32_t* out_docs, uint32_t* out_tfs) {
   try {
     const OSegment& seg = ix->segs.at({ts->segment_ord, ts->field});

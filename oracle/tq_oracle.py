@@ -34,6 +34,7 @@ def _load():
     lib.tqo_last_error.argtypes = [vp]
     lib.tqo_segment_register.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
     lib.tqo_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_int, C.c_int, C.c_uint32, f32p, u32p, u32p, u32p]
+    lib.tqo_count_batch.argtypes = [vp, C.POINTER(Query), sz, u64p]
     lib.tqo_decode_postings.argtypes = [vp, C.POINTER(TermSeg), u32p, u32p]
     lib.tqo_block_table.argtypes = [vp, C.POINTER(TermSeg), C.c_float, C.c_float, u32p, f32p]
     lib.tqo_term_scorer_open.restype = vp
@@ -160,6 +161,14 @@ class OracleIndex:
         if rc != 0:
             raise RuntimeError(lib().tqo_last_error(self.h).decode())
         return scores, segs, docs, counts
+
+    def count_batch(self, batch: QueryBatch):
+        """Count collector: alive docs matching each query (src/collector/count_collector.rs)."""
+        out = np.zeros(max(batch.nq, 1), dtype=np.uint64)
+        rc = lib().tqo_count_batch(self.h, batch.ptr, batch.nq, ptr(out, u64p))
+        if rc != 0:
+            raise RuntimeError(lib().tqo_last_error(self.h).decode())
+        return out[:batch.nq]
 
     def decode_postings(self, term_seg):
         ts = TermSeg(*[int(x) for x in term_seg])

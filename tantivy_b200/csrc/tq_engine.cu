@@ -279,7 +279,9 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
     TQ_CUDA(cudaMemcpy(s.d_fieldnorm, fieldnorm, max_doc, cudaMemcpyHostToDevice));
   }
   if (alive_bitset) {
-    TQ_CUDA(cudaMalloc(&s.d_alive, std::max<size_t>(alive_len, 1)));
+    const size_t alive_padded = ((alive_len + 7) & ~(size_t)7) + 8;  // k_count reads whole 32-bit words
+    TQ_CUDA(cudaMalloc(&s.d_alive, alive_padded));
+    TQ_CUDA(cudaMemset(s.d_alive, 0, alive_padded));
     TQ_CUDA(cudaMemcpy(s.d_alive, alive_bitset, alive_len, cudaMemcpyHostToDevice));
   }
   c->segments[{segment_ord, field}] = s;
@@ -878,6 +880,98 @@ int tq_merge_topk_dev(tq_ctx* c, uint32_t n_lists, uint32_t nq, uint32_t stride,
                                   out_segment_ord_dev, out_doc_dev, out_count_dev);
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaStreamSynchronize(0));
+  return TQ_OK;
+}
+
+// ---- Count collector -------------------------------------------------------------------------------------------
+int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_counts) {
+  if (!c || (!queries && nq) || (!out_counts && nq)) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  for (size_t qi = 0; qi < nq; ++qi) out_counts[qi] = 0;
+  if (!nq) return TQ_OK;
+  tq_batch* b = acquire_batch(c);
+  if (!b) return fail(TQ_ERR_CUDA, "stream/event creation failed");
+  struct Guard { tq_batch* b; ~Guard() { tq_batch_destroy(b); } } guard{b};
+  std::vector<uint32_t> list_ids;
+  std::vector<CountSeg> segs;
+  std::vector<Unit> units;
+  {
+    std::lock_guard<std::mutex> g(c->mu);
+    std::vector<PendingBuild> pending;
+    uint64_t built = 0;
+    std::vector<const tq_term_seg*> order;
+    for (size_t qi = 0; qi < nq; ++qi) {
+      const tq_query& q = queries[qi];
+      if (q.n_terms == 0 || q.n_terms > TQ_MAX_TERMS) return fail(TQ_ERR_INVALID_ARGUMENT, "n_terms must be in 1..TQ_MAX_TERMS");
+      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
+      if (q.op == TQ_OP_TERM && q.n_terms != 1) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_TERM takes one term");
+      if (!q.term_segs && q.n_term_segs) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
+      order.clear();
+      for (uint32_t i = 0; i < q.n_term_segs; ++i) {
+        if (q.term_segs[i].term_idx >= q.n_terms) return fail(TQ_ERR_INVALID_ARGUMENT, "term_idx out of range");
+        if (q.term_segs[i].doc_freq) order.push_back(&q.term_segs[i]);
+      }
+      std::stable_sort(order.begin(), order.end(), [](const tq_term_seg* a, const tq_term_seg* b) {
+        return a->segment_ord != b->segment_ord ? a->segment_ord < b->segment_ord : a->term_idx < b->term_idx;
+      });
+      for (size_t i = 0; i < order.size();) {
+        size_t j = i;
+        while (j < order.size() && order[j]->segment_ord == order[i]->segment_ord) ++j;
+        const uint32_t n_here = (uint32_t)(j - i);
+        if (q.op == TQ_OP_AND && n_here < q.n_terms) { i = j; continue; }  // a clause without postings: empty intersection
+        CountSeg cs{};
+        cs.query = (uint32_t)qi; cs.lists_base = (uint32_t)list_ids.size(); cs.n_lists = n_here; cs.op = (uint32_t)q.op;
+        const Segment* seg = nullptr;
+        uint64_t df_single = 0;
+        for (size_t a = i; a < j; ++a) {
+          uint32_t id;
+          int rc = get_list(c, *order[a], false, pending, &id, &seg);
+          if (rc != TQ_OK) return rc;
+          list_ids.push_back(id);
+          df_single = order[a]->doc_freq;
+        }
+        cs.max_doc = seg->max_doc;
+        cs.alive = seg->d_alive;
+        if (n_here == 1 && !seg->d_alive) {  // TermWeight::count without deletes: the term's doc_freq (term_weight.rs:179-190)
+          out_counts[qi] += df_single;
+          list_ids.resize(cs.lists_base);
+        } else {
+          const uint32_t tiles = (cs.max_doc + kTileDocs - 1) / kTileDocs, per = 8;
+          for (uint32_t t0 = 0; t0 < tiles; t0 += per) units.push_back(Unit{(uint32_t)segs.size(), t0, std::min(tiles, t0 + per), 0});
+          segs.push_back(cs);
+        }
+        i = j;
+      }
+    }
+    int rc = flush_builds(c, pending, &built);
+    if (rc != TQ_OK) return rc;
+  }
+  if (units.empty()) return TQ_OK;
+  auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t o_ids = off; off = align(off + list_ids.size() * 4);
+  const size_t o_segs = off; off = align(off + segs.size() * sizeof(CountSeg));
+  const size_t o_units = off; off = align(off + units.size() * sizeof(Unit));
+  const size_t o_counts = off; off = align(off + nq * 8);
+  TQ_CUDA(b->pin.ensure(off + 256));
+  TQ_CUDA(b->dev.ensure(off + 256));
+  memcpy(b->pin.p + o_ids, list_ids.data(), list_ids.size() * 4);
+  memcpy(b->pin.p + o_segs, segs.data(), segs.size() * sizeof(CountSeg));
+  memcpy(b->pin.p + o_units, units.data(), units.size() * sizeof(Unit));
+  memset(b->pin.p + o_counts, 0, nq * 8);
+  TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, off, cudaMemcpyHostToDevice, b->stream));
+  CountParams P;
+  P.lists = c->d_lists;
+  P.list_ids = reinterpret_cast<const uint32_t*>(b->dev.p + o_ids);
+  P.segs = reinterpret_cast<const CountSeg*>(b->dev.p + o_segs);
+  P.units = reinterpret_cast<const Unit*>(b->dev.p + o_units);
+  P.counts = reinterpret_cast<unsigned long long*>(b->dev.p + o_counts);
+  k_count<<<(unsigned)units.size(), kThreads, 0, b->stream>>>(P);
+  TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaMemcpyAsync(b->pin.p + o_counts, b->dev.p + o_counts, nq * 8, cudaMemcpyDeviceToHost, b->stream));
+  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  const unsigned long long* dc = reinterpret_cast<const unsigned long long*>(b->pin.p + o_counts);
+  for (size_t qi = 0; qi < nq; ++qi) out_counts[qi] += dc[qi];
   return TQ_OK;
 }
 

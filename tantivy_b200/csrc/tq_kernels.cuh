@@ -1510,6 +1510,72 @@ __device__ __noinline__ void sort_pairs_desc(unsigned long long* a, uint32_t* b,
   }
 }
 
+// ---- Count collector (N4): how many alive docs match, no scores ----------------------------------------------------
+// src/collector/count_collector.rs + Weight::count (term_weight.rs:179-219, boolean_weight.rs): one CTA walks its share
+// of a (query, segment)'s doc-id tiles; a tile is a bitmap in shared memory, a clause sets the bits of its postings
+// (OR: into the result, AND: into a scratch bitmap that is then intersected), the alive bitset is and-ed in, popcount.
+struct CountSeg {
+  uint32_t query, lists_base, n_lists, max_doc;
+  const uint8_t* alive;
+  uint32_t op, pad;
+};
+struct CountParams {
+  const ListDesc* lists;
+  const uint32_t* list_ids;
+  const CountSeg* segs;
+  const Unit* units;
+  unsigned long long* counts;
+};
+
+__global__ void __launch_bounds__(kThreads) k_count(const CountParams P) {
+  constexpr uint32_t kWords = kTileDocs / 32u;
+  __shared__ uint32_t s_acc[kWords], s_tmp[kWords];
+  __shared__ uint32_t s_part[kWarps];
+  const Unit U = P.units[blockIdx.x];
+  const CountSeg S = P.segs[U.qseg];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t total = 0;
+  for (uint32_t tile = U.begin; tile < U.end; ++tile) {
+    const uint32_t lo = tile * kTileDocs, hi = min(lo + kTileDocs, S.max_doc);
+    for (uint32_t c = 0; c < S.n_lists; ++c) {
+      uint32_t* bitmap = (S.op == 1u && c > 0) ? s_tmp : s_acc;  // 1 == TQ_OP_AND
+      if (c == 0 || S.op == 1u)
+        for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) bitmap[w] = 0;
+      __syncthreads();
+      const ListDesc L = P.lists[P.list_ids[S.lists_base + c]];
+      const uint32_t j0 = first_block_ge(L.last_doc, 0, L.n_total, lo, lane);
+      for (uint32_t j = j0 + warp; j < L.n_total; j += kWarps) {
+        const uint32_t prev = __ldg(&L.tab4[j].w);
+        if (prev != 0xFFFFFFFFu && prev + 1u >= hi) break;  // the block starts at or after the tile's end
+        uint32_t doc[4], tf[4];
+        decode_block(L, j, lane, doc, tf);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (doc[i] >= lo && doc[i] < hi) atomicOr(&bitmap[(doc[i] - lo) >> 5], 1u << ((doc[i] - lo) & 31u));
+      }
+      __syncthreads();
+      if (S.op == 1u && c > 0) {
+        for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_acc[w] &= s_tmp[w];
+        __syncthreads();
+      }
+    }
+    for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) {
+      uint32_t bits = s_acc[w];
+      if (bits && S.alive) bits &= __ldg(reinterpret_cast<const uint32_t*>(S.alive) + ((lo >> 5) + w));  // 32 docs per word, little endian
+      total += (uint32_t)__popc(bits);
+    }
+    __syncthreads();
+  }
+  total = __reduce_add_sync(kFull, total);
+  if (lane == 0) s_part[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long sum = 0;
+    for (int w = 0; w < kWarps; ++w) sum += s_part[w];
+    if (sum) atomicAdd(&P.counts[S.query], sum);
+  }
+}
+
 // The exact k-th largest score key among a query's candidates so far (4-pass radix select) becomes a lower bound of
 // its threshold: run between the sampled windows and the main launch of k_or_strip.
 __global__ void __launch_bounds__(kThreads) k_theta(const BatchParams P) {

@@ -310,6 +310,9 @@ class TopDocs {
   size_t limit_ = 0, offset_ = 0;
 };
 
+// Count collector (src/collector/count_collector.rs): searcher.search(query, Count{}) -> number of alive matching docs
+struct Count {};
+
 // ---- device context shared by the searchers of one reader snapshot ------------------------------------------
 class DeviceIndex {
  public:
@@ -388,6 +391,20 @@ class Searcher {
   std::vector<std::pair<Score, DocAddress>> search(const Query& query, const TopDocs& collector) const {
     std::vector<const Query*> one{&query};
     return std::move(search_batch(one, collector)[0]);
+  }
+
+  // searcher.search(&query, &Count)
+  size_t search(const Query& query, const Count&) const {
+    Plan p = plan(query, 1);
+    if (p.matches_nothing) return 0;
+    tq_query q;
+    std::memset(&q, 0, sizeof(q));
+    q.op = p.op; q.n_terms = (uint32_t)p.weight.size(); q.k = 1; q.n_term_segs = (uint32_t)p.term_segs.size();
+    q.term_segs = p.term_segs.data(); q.weight = p.weight.data(); q.avg_fieldnorm = p.avg.data(); q.term_flags = p.flags.data();
+    tq_ctx* ctx = device_->ensure(segments_);
+    uint64_t n = 0;
+    if (tq_count_batch(ctx, &q, 1, &n) != TQ_OK) throw TantivyError(TantivyError::SystemError, std::string("tq_count_batch: ") + tq_last_error(ctx));
+    return (size_t)n;
   }
 
   // Many queries in one device batch (throughput; single queries are launch-latency bound).

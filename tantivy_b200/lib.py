@@ -32,6 +32,7 @@ def _load():
     lib.tq_segment_unregister.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.tq_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_prepare.argtypes = [vp, C.POINTER(Query), sz, C.POINTER(vp)]
+    lib.tq_count_batch.argtypes = [vp, C.POINTER(Query), sz, u64p]
     lib.tq_batch_run.argtypes = [vp]
     lib.tq_batch_run_phase.argtypes = [vp, C.c_int]
     lib.tq_batch_phases.argtypes = [vp]
@@ -220,6 +221,12 @@ class Context:
         _check(LIB.tq_search_batch(self.h, batch.ptr, batch.nq, stride, ptr(scores, f32p), ptr(segs, u32p), ptr(docs, u32p),
                                    ptr(counts, u32p)), self.h)
         return scores, segs, docs, counts
+
+    def count_batch(self, qb: QueryBatch):
+        """Count collector: alive docs matching each query (tq_count_batch)."""
+        out = np.zeros(max(qb.nq, 1), dtype=np.uint64)
+        _check(LIB.tq_count_batch(self.h, qb.ptr, qb.nq, ptr(out, u64p)), self.h)
+        return out[:qb.nq]
 
     def prepare(self, batch: QueryBatch):
         return Batch(self, batch)

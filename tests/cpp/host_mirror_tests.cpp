@@ -305,6 +305,28 @@ static void test_multi_segment_deletes_and_paging() {
   CHECK(!both.empty() && both.size() <= searcher.doc_freq(rare));
 }
 
+static void test_count_collector() {  // boolean_query/mod.rs:46-75 shapes on the aux index: searcher.search(&query, &Count)
+  Index index = index_boolean_aux();   // docs: "a b c", "a c", "b c", "a b c d", "d"
+  Field text = *index.schema().get_field("text");
+  Searcher searcher = index.reader().searcher();
+  QueryParser parser = QueryParser::for_index(index, {text});
+  CHECK(searcher.search(*parser.parse_query("+a"), Count{}) == 3);
+  CHECK(searcher.search(*parser.parse_query("+a +b"), Count{}) == 2);
+  CHECK(searcher.search(*parser.parse_query("a d"), Count{}) == 4);
+  CHECK(searcher.search(*parser.parse_query("a b c d"), Count{}) == 5);
+  CHECK(searcher.search(*parser.parse_query("+a +d"), Count{}) == 1);
+  CHECK(searcher.search(*parser.parse_query("zzz"), Count{}) == 0);
+  Index multi = index_multi_segment();  // deletes in two of the three segments
+  Field body = *multi.schema().get_field("body");
+  Searcher s2 = multi.reader().searcher();
+  const Term rare = Term::from_field_text(body, "rare");
+  const size_t alive_rare = s2.search(TermQuery(rare, IndexRecordOption::Basic), Count{});
+  CHECK(alive_rare == s2.segment_reader(2).inverted_index(body).doc_freq(rare));  // segments 0 and 1 lost theirs
+  CHECK(alive_rare < s2.doc_freq(rare));
+  auto top = s2.search(TermQuery(Term::from_field_text(body, "w5"), IndexRecordOption::WithFreqs), TopDocs::with_limit(1000));
+  CHECK(top.size() == std::min<size_t>(1000, s2.search(TermQuery(Term::from_field_text(body, "w5"), IndexRecordOption::Basic), Count{})));
+}
+
 static void test_absent_terms_and_unsupported_shapes() {
   Index index = index_boolean_aux();
   Field text = *index.schema().get_field("text");
@@ -505,6 +527,7 @@ int main(int argc, char** argv) {
              {"intersection_score", test_intersection_score},
              {"top_collector", test_top_collector},
              {"multi_segment_deletes_and_paging", test_multi_segment_deletes_and_paging},
+             {"count_collector", test_count_collector},
              {"absent_terms_and_unsupported_shapes", test_absent_terms_and_unsupported_shapes},
              {"host_tokenizer_and_statistics", test_host_tokenizer_and_statistics}};
     if (mode == "--compat" && !dir.empty()) tests.push_back({"compat_index_search", [dir]() { test_compat_index_search(dir); }});

@@ -444,3 +444,29 @@ def test_two_phase_run_with_threshold_exchange(ctx, synth):
     for a, c in zip(plain, again):
         assert (a == c).all()
     b.close()
+
+
+def test_count_collector(ctx):
+    """tq_count_batch = searcher.search(&query, &Count) (src/collector/count_collector.rs): alive matching docs, over
+    several segments, with and without deletes, for term / AND / OR, absent terms included."""
+    rng = np.random.default_rng(900)
+    for deletes in (False, True):
+        segs = _random_segments(rng, 3, 5, deletes=deletes)
+        segs[1].terms[3] = (0, 0, 0)  # term 3 absent from one segment
+        oi = both(ctx, segs)
+        queries = [make_query(TQ_OP_TERM, segs, [t], 1) for t in range(5)]
+        queries += [make_query(TQ_OP_AND, segs, ts, 1) for ts in ([0, 1], [0, 3], [1, 2, 4], [4, 3], [0, 1, 2, 3, 4])]
+        queries += [make_query(TQ_OP_OR, segs, ts, 1) for ts in ([0, 1], [3], [3, 4], [0, 1, 2, 3, 4], [2, 4])]
+        qb = QueryBatch(queries)
+        g, c = ctx.count_batch(qb), oi.count_batch(qb)
+        assert (g == c).all(), (g, c)
+        assert g[:5].sum() > 0 and (g[5:10] <= g[0]).any()
+        if not deletes:  # a term query without deletes is its doc_freq (term_weight.rs:179-190)
+            assert [int(x) for x in g[:5]] == [sum(s.terms[t][0] for s in segs) for t in range(5)]
+
+
+def test_count_collector_synth(ctx, synth):
+    ix, oi, base = synth
+    qb = QueryBatch([ix.query(op, terms, 1, segment_base=base) for op, terms in
+                     [(TQ_OP_OR, [0, 1, 2, 3, 4, 5]), (TQ_OP_AND, [0, 1]), (TQ_OP_AND, [2, 0, 3]), (TQ_OP_OR, [4, 5]), (TQ_OP_TERM, [1])]])
+    assert (ctx.count_batch(qb) == oi.count_batch(qb)).all()

@@ -177,3 +177,22 @@ def test_initial_threshold_exhaustive_vs_pruned():
         b = hits(ix.search_batch(QueryBatch([q]), mode=1))
         assert a == [h for h in full if h[0] > thr]
         assert [(g, d) for _, g, d in a] == [(g, d) for _, g, d in b]
+
+
+def test_count_matches_set_arithmetic():
+    """The oracle's Count collector against numpy set arithmetic on the posting lists."""
+    rng = np.random.default_rng(13)
+    max_doc = 5000
+    lists = []
+    for p in (0.4, 0.1, 0.02):
+        docs = np.nonzero(rng.random(max_doc) < p)[0].astype(np.uint32)
+        lists.append((docs, np.ones(len(docs), np.uint32)))
+    alive_bits = rng.random(max_doc) > 0.3
+    seg = OracleSegment(lists, rng.integers(1, 300, size=max_doc), alive=np.packbits(alive_bits, bitorder="little"))
+    ix = O.OracleIndex()
+    seg.register(ix)
+    sets = [set(int(d) for d in docs if alive_bits[d]) for docs, _ in lists]
+    qb = QueryBatch([make_query(TQ_OP_TERM, [seg], [0], 1), make_query(TQ_OP_AND, [seg], [0, 1], 1), make_query(TQ_OP_AND, [seg], [0, 1, 2], 1),
+                     make_query(TQ_OP_OR, [seg], [1, 2], 1), make_query(TQ_OP_OR, [seg], [0, 1, 2], 1)])
+    want = [len(sets[0]), len(sets[0] & sets[1]), len(sets[0] & sets[1] & sets[2]), len(sets[1] | sets[2]), len(sets[0] | sets[1] | sets[2])]
+    assert [int(x) for x in ix.count_batch(qb)] == want
