@@ -23,8 +23,10 @@
 // that tests and examples can build real segments without the Rust crate.
 #pragma once
 #include <algorithm>
+#include <cctype>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -110,6 +112,9 @@ class SchemaBuilder {
     schema_.entries_.push_back({name, options});
     return Field{(uint32_t)schema_.entries_.size() - 1};
   }
+  // a field of another type (date, u64, ...): keeps the field ids of a schema read from meta.json aligned; the search
+  // path of this library does not cover it
+  Field add_other_field(const std::string& name) { return add_text_field(name, TextOptions{}); }
   Schema build() { return schema_; }
 
  private:
@@ -824,6 +829,187 @@ inline void load_field(SegmentData& seg, Field field, IndexRecordOption record, 
       fd.fieldnorms.assign(fieldnorm_file->begin() + (long)fit->second.offset, fieldnorm_file->begin() + (long)(fit->second.offset + fit->second.len));
     }
   }
+}
+
+// ---- meta.json (src/index/index_meta.rs: IndexMeta { index_settings, segments, schema, opstamp }) ---------------------
+// A small JSON reader, enough for the meta file the reference writes.
+struct Json {
+  enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+  bool b = false;
+  double num = 0;
+  std::string str;
+  std::vector<Json> arr;
+  std::vector<std::pair<std::string, Json>> obj;
+  const Json* get(const std::string& key) const {
+    for (auto& kv : obj) if (kv.first == key) return &kv.second;
+    return nullptr;
+  }
+};
+namespace detail {
+struct JsonParser {
+  const std::string& s;
+  size_t i = 0;
+  [[noreturn]] void bad(const char* what) const { throw TantivyError(TantivyError::DataCorruption, std::string("meta.json: ") + what); }
+  void ws() { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) ++i; }
+  Json value() {
+    ws();
+    if (i >= s.size()) bad("unexpected end");
+    Json v;
+    const char c = s[i];
+    if (c == '{') {
+      v.type = Json::Object; ++i; ws();
+      if (i < s.size() && s[i] == '}') { ++i; return v; }
+      for (;;) {
+        ws();
+        Json k = value();
+        if (k.type != Json::String) bad("object key is not a string");
+        ws();
+        if (i >= s.size() || s[i] != ':') bad("':' expected");
+        ++i;
+        v.obj.emplace_back(k.str, value());
+        ws();
+        if (i < s.size() && s[i] == ',') { ++i; continue; }
+        if (i < s.size() && s[i] == '}') { ++i; return v; }
+        bad("',' or '}' expected");
+      }
+    }
+    if (c == '[') {
+      v.type = Json::Array; ++i; ws();
+      if (i < s.size() && s[i] == ']') { ++i; return v; }
+      for (;;) {
+        v.arr.push_back(value());
+        ws();
+        if (i < s.size() && s[i] == ',') { ++i; continue; }
+        if (i < s.size() && s[i] == ']') { ++i; return v; }
+        bad("',' or ']' expected");
+      }
+    }
+    if (c == '"') {
+      v.type = Json::String; ++i;
+      while (i < s.size() && s[i] != '"') {
+        if (s[i] == '\\' && i + 1 < s.size()) {
+          const char e = s[i + 1];
+          if (e == 'n') v.str.push_back('\n'); else if (e == 't') v.str.push_back('\t');
+          else if (e == 'u' && i + 5 < s.size()) { v.str.push_back((char)std::stoi(s.substr(i + 2, 4), nullptr, 16)); i += 4; }
+          else v.str.push_back(e);
+          i += 2;
+        } else v.str.push_back(s[i++]);
+      }
+      if (i >= s.size()) bad("unterminated string");
+      ++i;
+      return v;
+    }
+    if (s.compare(i, 4, "true") == 0) { v.type = Json::Bool; v.b = true; i += 4; return v; }
+    if (s.compare(i, 5, "false") == 0) { v.type = Json::Bool; i += 5; return v; }
+    if (s.compare(i, 4, "null") == 0) { i += 4; return v; }
+    size_t j = i;
+    while (j < s.size() && (std::isdigit((unsigned char)s[j]) || s[j] == '-' || s[j] == '+' || s[j] == '.' || s[j] == 'e' || s[j] == 'E')) ++j;
+    if (j == i) bad("unexpected character");
+    v.type = Json::Number;
+    v.num = std::stod(s.substr(i, j - i));
+    i = j;
+    return v;
+  }
+};
+}  // namespace detail
+inline Json parse_json(const std::string& text) {
+  detail::JsonParser p{text};
+  Json v = p.value();
+  p.ws();
+  if (p.i != text.size()) p.bad("trailing characters");
+  return v;
+}
+
+struct SegmentMeta {  // index_meta.rs: InnerSegmentMeta { segment_id, max_doc, deletes: Option<DeleteMeta{num_deleted_docs, opstamp}> }
+  std::string segment_id;  // with dashes, as written
+  uint32_t max_doc = 0;
+  bool has_deletes = false;
+  uint32_t num_deleted_docs = 0;
+  uint64_t delete_opstamp = 0;
+  std::string file_stem() const {  // SegmentId::uuid_string(): the uuid without dashes (index/segment_id.rs)
+    std::string out;
+    for (char ch : segment_id) if (ch != '-') out.push_back(ch);
+    return out;
+  }
+};
+struct IndexMeta {
+  std::vector<SegmentMeta> segments;
+  Schema schema;
+  uint64_t opstamp = 0;
+};
+
+inline IndexMeta read_meta(const std::string& meta_json) {
+  const Json root = parse_json(meta_json);
+  if (root.type != Json::Object) throw TantivyError(TantivyError::DataCorruption, "meta.json: not an object");
+  IndexMeta meta;
+  if (const Json* o = root.get("opstamp")) meta.opstamp = (uint64_t)o->num;
+  const Json* segs = root.get("segments");
+  const Json* schema = root.get("schema");
+  if (!segs || segs->type != Json::Array || !schema || schema->type != Json::Array)
+    throw TantivyError(TantivyError::DataCorruption, "meta.json: segments / schema missing");
+  for (const Json& sj : segs->arr) {
+    SegmentMeta sm;
+    const Json* id = sj.get("segment_id");
+    const Json* md = sj.get("max_doc");
+    if (!id || id->type != Json::String || !md || md->type != Json::Number) throw TantivyError(TantivyError::DataCorruption, "meta.json: bad segment entry");
+    sm.segment_id = id->str;
+    sm.max_doc = (uint32_t)md->num;
+    const Json* del = sj.get("deletes");
+    if (del && del->type == Json::Object) {
+      sm.has_deletes = true;
+      if (const Json* n = del->get("num_deleted_docs")) sm.num_deleted_docs = (uint32_t)n->num;
+      if (const Json* o = del->get("opstamp")) sm.delete_opstamp = (uint64_t)o->num;
+    }
+    meta.segments.push_back(sm);
+  }
+  SchemaBuilder sb;
+  for (const Json& fj : schema->arr) {
+    const Json* name = fj.get("name");
+    const Json* type = fj.get("type");
+    if (!name || name->type != Json::String || !type || type->type != Json::String) throw TantivyError(TantivyError::DataCorruption, "meta.json: bad field entry");
+    const Json* options = fj.get("options");
+    const Json* indexing = (type->str == "text" && options) ? options->get("indexing") : nullptr;
+    if (indexing && indexing->type == Json::Object) {  // schema/text_options.rs: TextFieldIndexing { record, fieldnorms, tokenizer }
+      TextFieldIndexing ti;
+      if (const Json* r = indexing->get("record")) {
+        if (r->str == "basic") ti.record = IndexRecordOption::Basic;
+        else if (r->str == "freq") ti.record = IndexRecordOption::WithFreqs;
+        else if (r->str == "position") ti.record = IndexRecordOption::WithFreqsAndPositions;
+        else throw TantivyError(TantivyError::DataCorruption, "meta.json: unknown record option " + r->str);
+      }
+      if (const Json* f = indexing->get("fieldnorms")) ti.fieldnorms = f->b;
+      if (const Json* t = indexing->get("tokenizer")) ti.tokenizer = t->str;
+      sb.add_text_field(name->str, TextOptions{ti});
+    } else {
+      sb.add_other_field(name->str);
+    }
+  }
+  meta.schema = sb.build();
+  return meta;
+}
+
+// Index::open_in_dir for this path: meta.json + every segment's `.idx` / `.fieldnorm` (read through `read_file(name)`),
+// one SegmentData per segment in meta order.  Term dictionaries (`.term`, N2) are not read: terms are looked up through
+// FieldSegmentData::term_dict, which the caller fills.  Segments with deletes need their `.del` file's bitset, which
+// no fixture of the reference pins yet: refused.
+inline Index open_index(const std::string& meta_json, const std::function<std::vector<uint8_t>(const std::string&)>& read_file) {
+  const IndexMeta meta = read_meta(meta_json);
+  std::vector<std::shared_ptr<const SegmentData>> segments;
+  for (const SegmentMeta& sm : meta.segments) {
+    if (sm.has_deletes) throw TantivyError(TantivyError::Unsupported, "segment " + sm.segment_id + " has deletes (.del is not read yet)");
+    auto seg = std::make_shared<SegmentData>();
+    seg->max_doc = sm.max_doc;
+    seg->fields.resize(meta.schema.num_fields());
+    const std::vector<uint8_t> idx = read_file(sm.file_stem() + ".idx");
+    const std::vector<uint8_t> fn = read_file(sm.file_stem() + ".fieldnorm");
+    for (uint32_t f = 0; f < meta.schema.num_fields(); ++f) {
+      const FieldEntry& fe = meta.schema.get_field_entry(Field{f});
+      if (!fe.options.indexing) continue;
+      load_field(*seg, Field{f}, fe.options.indexing->record, idx, fe.options.indexing->fieldnorms ? &fn : nullptr);
+    }
+    segments.push_back(seg);
+  }
+  return Index::from_segments(meta.schema, std::move(segments));
 }
 
 }  // namespace files

@@ -407,47 +407,66 @@ static std::vector<uint8_t> read_file(const std::string& path) {
   return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
 }
 
-// N1: the reference's compat fixture (tests/compat_tests_data/index_v7, src/compat_tests.rs:39-56), handed over as
-// files by the Python suite (hex in tests/golden/reference_fixtures.json).  label field: one doc, one token.
-static Index index_from_compat_files(const std::string& dir) {
-  SchemaBuilder sb;
-  Field label = sb.add_text_field("label", TEXT);
-  auto seg = std::make_shared<SegmentData>();
-  seg->max_doc = 1;
-  const auto idx = read_file(dir + "/compat.idx"), fn = read_file(dir + "/compat.fieldnorm");
-  files::load_field(*seg, label, IndexRecordOption::WithFreqsAndPositions, idx, &fn);
+// N1: the reference's compat fixtures (tests/compat_tests_data/index_v{6,7}, src/compat_tests.rs:39-56), handed over
+// as files by the Python suite (hex in tests/golden/reference_fixtures.json): DIR/<version>/meta.json and the segment's
+// files under their own names.  One doc: label = "dateformat".
+static Index index_from_compat_files(const std::string& dir, const std::string& version) {
+  const std::string base = dir + "/" + version + "/";
+  const auto meta_bytes = read_file(base + "meta.json");
+  Index index = files::open_index(std::string(meta_bytes.begin(), meta_bytes.end()), [&](const std::string& name) { return read_file(base + name); });
   // the `.term` dictionary is N2: the TermInfo of the only term is supplied (postings bytes 0..2 of the sub-file)
+  Field label = *index.schema().get_field("label");
+  auto seg = std::make_shared<SegmentData>(*index.segments()[0]);
   seg->fields[label.id].term_dict["dateformat"] = TermInfo{1, 0, 2};
-  return Index::from_segments(sb.build(), {seg});
+  return Index::from_segments(index.schema(), {seg});
 }
 
 static void test_host_compat_framing(const std::string& dir) {
-  const auto idx = read_file(dir + "/compat.idx");
-  CHECK(!idx.empty());
-  const files::Footer f = files::read_footer(idx.data(), idx.size());
-  CHECK(f.index_format_version == 7);
-  auto parts = files::open_composite(idx.data(), f.body_len);
-  CHECK(parts.size() == 2);  // label (text) and date fields
-  Index index = index_from_compat_files(dir);
-  const SegmentData& seg = *index.segments()[0];
-  CHECK(seg.fields[0].total_num_tokens() == 1);
-  CHECK(seg.fields[0].idx_body.size() == 10 && seg.fields[0].idx_body[8] == 0x80 && seg.fields[0].idx_body[9] == 0x81);
-  CHECK(seg.fields[0].fieldnorms.size() == 1 && seg.fields[0].fieldnorms[0] == 1);
-  auto corrupted = idx;
-  corrupted[0] ^= 1;
-  bool crc = false;
-  try { files::read_footer(corrupted.data(), corrupted.size()); } catch (const TantivyError& e) { crc = e.kind() == TantivyError::DataCorruption; }
-  CHECK(crc);
+  for (const std::string version : {"index_v6", "index_v7"}) {
+    const auto meta_bytes = read_file(dir + "/" + version + "/meta.json");
+    const files::IndexMeta meta = files::read_meta(std::string(meta_bytes.begin(), meta_bytes.end()));
+    CHECK(meta.segments.size() == 1 && meta.segments[0].max_doc == 1 && !meta.segments[0].has_deletes && meta.opstamp == 2);
+    CHECK(meta.schema.num_fields() == 2);
+    const FieldEntry& label = meta.schema.get_field_entry(Field{0});
+    CHECK(label.name == "label" && label.options.indexing && label.options.indexing->record == IndexRecordOption::WithFreqsAndPositions &&
+          label.options.indexing->fieldnorms && label.options.indexing->tokenizer == "default");
+    CHECK(meta.schema.get_field_entry(Field{1}).name == "date" && !meta.schema.get_field_entry(Field{1}).options.indexing);
+    const auto idx = read_file(dir + "/" + version + "/" + meta.segments[0].file_stem() + ".idx");
+    CHECK(!idx.empty());
+    const files::Footer f = files::read_footer(idx.data(), idx.size());
+    CHECK(f.index_format_version == (version == "index_v6" ? 6u : 7u));
+    auto parts = files::open_composite(idx.data(), f.body_len);
+    CHECK(parts.size() == 2);  // label (text) and date fields
+    Index index = index_from_compat_files(dir, version);
+    const SegmentData& seg = *index.segments()[0];
+    CHECK(seg.max_doc == 1 && seg.fields.size() == 2 && !seg.fields[1].indexed);
+    CHECK(seg.fields[0].total_num_tokens() == 1);
+    CHECK(seg.fields[0].idx_body.size() == 10 && seg.fields[0].idx_body[8] == 0x80 && seg.fields[0].idx_body[9] == 0x81);
+    CHECK(seg.fields[0].fieldnorms.size() == 1 && seg.fields[0].fieldnorms[0] == 1);
+    auto corrupted = idx;
+    corrupted[0] ^= 1;
+    bool crc = false;
+    try { files::read_footer(corrupted.data(), corrupted.size()); } catch (const TantivyError& e) { crc = e.kind() == TantivyError::DataCorruption; }
+    CHECK(crc);
+  }
+  bool bad_meta = false;
+  try { files::read_meta("{\"segments\": 3}"); } catch (const TantivyError& e) { bad_meta = e.kind() == TantivyError::DataCorruption; }
+  CHECK(bad_meta);
 }
 
-static void test_compat_index_search(const std::string& dir) {  // GPU: a segment the reference wrote, searched on the device
-  Index index = index_from_compat_files(dir);
-  Field label = *index.schema().get_field("label");
-  Searcher searcher = index.reader().searcher();
-  auto top = searcher.search(TermQuery(Term::from_field_text(label, "dateformat"), IndexRecordOption::WithFreqs), TopDocs::with_limit(3));
-  CHECK(top.size() == 1);
-  CHECK(top[0].second == DocAddress(0, 0));
-  CHECK_NEARLY(top[0].first, 0.28768212);  // one doc, one token: idf(1,1) * 2.2 * 1/(1+1.2)
+static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
+  for (const std::string version : {"index_v6", "index_v7"}) {
+    Index index = index_from_compat_files(dir, version);
+    Field label = *index.schema().get_field("label");
+    Searcher searcher = index.reader().searcher();
+    // assert_date_time_precision (compat_tests.rs:57-80): parse_query("dateformat"), TopDocs::with_limit(1) -> 1 hit
+    QueryBox q = QueryParser::for_index(index, {label}).parse_query("dateformat");
+    auto top = searcher.search(*q, TopDocs::with_limit(1).order_by_score());
+    CHECK(top.size() == 1);
+    CHECK(top[0].second == DocAddress(0, 0));
+    CHECK_NEARLY(top[0].first, 0.28768212);  // one doc, one token: idf(1,1) * 2.2 * 1/(1+1.2)
+    CHECK(searcher.search(*q, Count{}) == 1);
+  }
 }
 
 // ---- --dump -------------------------------------------------------------------------------------------------------------

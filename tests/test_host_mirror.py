@@ -30,9 +30,13 @@ def _run(args, **kw):
 @pytest.fixture(scope="module")
 def workdir(tmp_path_factory):
     d = tmp_path_factory.mktemp("host_mirror")
-    v7 = GOLDEN["compat"]["index_v7"]
-    (d / "compat.idx").write_bytes(bytes.fromhex(v7["idx"]))
-    (d / "compat.fieldnorm").write_bytes(bytes.fromhex(v7["fieldnorm"]))
+    for version, fx in GOLDEN["compat"].items():  # the reference's index_v6 / index_v7 directories, rebuilt from the fixture
+        sub = d / version
+        sub.mkdir()
+        (sub / "meta.json").write_text(json.dumps(fx["meta"], indent=2))
+        stem = fx["meta"]["segments"][0]["segment_id"].replace("-", "")
+        for ext in ("idx", "fieldnorm", "pos", "term"):
+            (sub / f"{stem}.{ext}").write_bytes(bytes.fromhex(fx[ext]))
     r = _run(["--dump", str(d)])
     assert r.returncode == 0, r.stdout + r.stderr
     return d
