@@ -56,6 +56,27 @@ def merge_rows_host(scores, segs, docs, counts, k):
     return o_sc, o_sg, o_dc, o_ct
 
 
+def score_keys(scores):
+    """Order-preserving u32 image of f32 scores, as int64 (host twin of score_to_key in csrc/tq_device.cuh):
+    the unit in which shards exchange thresholds; 0 = no bound."""
+    u = np.asarray(scores, dtype=np.float32).view(np.uint32).astype(np.int64)
+    return np.where(u >> 31, u ^ 0xFFFFFFFF, u ^ 0x80000000)
+
+
+def key_scores(keys):
+    """Inverse of score_keys."""
+    k = np.asarray(keys, dtype=np.int64)
+    u = np.where(k >> 31, k ^ 0x80000000, k ^ 0xFFFFFFFF).astype(np.uint32)
+    return u.view(np.float32)
+
+
+def exchange_thresholds(dist, keys):
+    """Element-wise MAX of every rank's per-query threshold keys (a torch int64 tensor, in place): any rank's k-th best
+    score is a lower bound of the global k-th best, so the largest one is the bound every rank may prune against."""
+    dist.all_reduce(keys, op=dist.ReduceOp.MAX)
+    return keys
+
+
 class ShardedIndex:
     """This rank's segments of a SynthIndex-like index plus the global statistics.
 
@@ -117,7 +138,7 @@ class CrossGpuMerger:
             batch.run_phase(phase)
             if phase + 1 < n:
                 batch.thresholds_export_dev(self.theta.data_ptr())  # waits for the batch's stream
-                self.dist.all_reduce(self.theta, op=self.dist.ReduceOp.MAX)
+                exchange_thresholds(self.dist, self.theta)
                 self.torch.cuda.synchronize()
                 batch.thresholds_import_dev(self.theta.data_ptr())
 

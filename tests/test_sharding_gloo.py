@@ -14,7 +14,8 @@ import torch.multiprocessing as mp  # noqa: E402
 
 import tantivy_b200 as T  # noqa: E402
 from tantivy_b200._abi import TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM  # noqa: E402
-from tantivy_b200.sharding import ShardedIndex, assign_segments, merge_rows_host  # noqa: E402
+from tantivy_b200.sharding import (ShardedIndex, assign_segments, exchange_thresholds, key_scores, merge_rows_host,  # noqa: E402
+                                   score_keys)
 
 DENS = [0.2, 0.05, 0.01, 0.001]
 N_SEG, DOCS = 4, 60_000
@@ -89,3 +90,95 @@ def test_assign_segments_partitions():
     for world in (1, 2, 3, 4, 8):
         seen = sorted(s for r in range(world) for s in assign_segments(8, world, r))
         assert seen == list(range(8))
+
+
+def _threshold_worker(rank, world, port, out):
+    """The cross-shard threshold protocol of CrossGpuMerger.run on CPU: every rank finds its local k-th best (here with
+    the oracle over a SAMPLE of its shard: one segment), the keys are max-reduced over gloo, every rank then searches
+    its whole shard with the exchanged bound as tq_query.threshold."""
+    from oracle import tq_oracle as O
+    from tantivy_b200._abi import QueryBatch
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ords = assign_segments(N_SEG, world, rank)
+        ix = T.SynthIndex(len(ords), DOCS, DENS, seed=99, segment_base=rank, segment_stride=world, n_threads=2)
+        shard = ShardedIndex(ix, ords, len(DENS), dist)
+        oi = O.OracleIndex()
+        shard.register(oi)
+        qb = shard.marshal(QUERIES)
+        nq = len(QUERIES)
+        # "threshold round": the first local segment only
+        sample = shard.marshal(QUERIES)
+        keep = sample.term_segs["segment_ord"] == ords[0]
+        for i in range(nq):  # restrict every query to the sampled segment
+            row = sample.q[i]
+            first = (int(row["term_segs"]) - sample.term_segs.ctypes.data) // sample.term_segs.itemsize
+            sel = [j for j in range(first, first + int(row["n_term_segs"])) if keep[j]]
+            sample.term_segs[first:first + len(sel)] = sample.term_segs[sel]
+            row["n_term_segs"] = len(sel)
+        sc, _, _, ct = oi.search_batch(sample, mode=0)
+        ks = [q[2] for q in QUERIES]
+        local = np.array([score_keys(sc[i, ks[i] - 1]) if ct[i] >= ks[i] else 0 for i in range(nq)], dtype=np.int64)
+        keys = torch.from_numpy(local.copy())
+        exchange_thresholds(dist, keys)
+        glob = keys.numpy()
+        assert (glob >= local).all()
+        # main pass: everything strictly above the next lower score stays, i.e. every score >= the exchanged bound
+        thr = [float(np.nextafter(key_scores(glob[i]), np.float32(-np.inf))) if glob[i] else None for i in range(nq)]
+        queries = []
+        for i, (op, terms, k) in enumerate(QUERIES):
+            queries.append((op, terms, k))
+        main = shard.marshal(queries)
+        for i in range(nq):
+            if thr[i] is not None:
+                main.q[i]["flags"] = 1
+                main.q[i]["threshold"] = thr[i]
+        rows_without = int(oi.search_batch(qb, mode=0)[3].sum())  # the same shard without the exchanged bounds
+        sc, sg, dc, ct = oi.search_batch(main, mode=0)
+        rows_with = torch.tensor([int(ct.sum()), rows_without])
+        dist.all_reduce(rows_with)
+        gathered = []
+        for arr, dt in ((sc, torch.float32), (sg.astype(np.int64), torch.int64), (dc.astype(np.int64), torch.int64), (ct.astype(np.int64), torch.int64)):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dt)
+            lst = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(lst, t)
+            gathered.append(torch.stack(lst).numpy())
+        merged = merge_rows_host(gathered[0], gathered[1].astype(np.uint32), gathered[2].astype(np.uint32), gathered[3].astype(np.uint32), KMAX)
+        if rank == 0:
+            out.put(dict(merged=[m.tolist() for m in merged], rows=rows_with.tolist(), bounds=glob.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_threshold_exchange_loses_nothing():
+    from oracle import tq_oracle as O
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_threshold_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ix = T.SynthIndex(N_SEG, DOCS, DENS, seed=99, n_threads=2)
+    shard = ShardedIndex(ix, list(range(N_SEG)), len(DENS))
+    oi = O.OracleIndex()
+    shard.register(oi)
+    sc, sg, dc, ct = oi.search_batch(shard.marshal(QUERIES), mode=0)
+    m_sc, m_sg, m_dc, m_ct = [np.array(x) for x in res["merged"]]
+    for i, (_, _, k) in enumerate(QUERIES):
+        n = int(ct[i])
+        assert int(m_ct[i]) >= n  # (the host merge keeps up to KMAX rows; the first k are the answer)
+        assert (m_sg[i, :n] == sg[i, :n]).all() and (m_dc[i, :n] == dc[i, :n]).all()
+        assert (m_sc[i, :n].astype(np.float32) == sc[i, :n]).all()
+    assert any(b > 0 for b in res["bounds"])  # the exchange did hand out bounds
+    assert res["rows"][0] <= res["rows"][1]     # ... which can only remove rows
+    for i, (_, _, k) in enumerate(QUERIES):    # every exchanged bound is a lower bound of the global k-th best score
+        if res["bounds"][i] and int(ct[i]) == k:
+            assert key_scores(res["bounds"][i]) <= sc[i, k - 1]
+    # key mapping round trip
+    x = np.array([0.0, 1.5, 3.25e-3, 1e9], dtype=np.float32)
+    assert (key_scores(score_keys(x)) == x).all() and (np.diff(score_keys(x)) > 0).all()
