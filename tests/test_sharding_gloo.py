@@ -180,5 +180,5 @@ def test_two_rank_threshold_exchange_loses_nothing():
         if res["bounds"][i] and int(ct[i]) == k:
             assert key_scores(res["bounds"][i]) <= sc[i, k - 1]
     # key mapping round trip
-    x = np.array([0.0, 1.5, 3.25e-3, 1e9], dtype=np.float32)
+    x = np.array([0.0, 3.25e-3, 1.5, 1e9], dtype=np.float32)
     assert (key_scores(score_keys(x)) == x).all() and (np.diff(score_keys(x)) > 0).all()
