@@ -13,6 +13,7 @@
 #include <thread>
 
 #include "../include/tantivy_b200.h"
+#include "positions.hpp"
 #include "query.hpp"
 
 using namespace tqo;
@@ -331,6 +332,28 @@ uint8_t tqo_fieldnorm_to_id(uint32_t f) { return fieldnorm_to_id(f); }
 struct tqo_field_writer {
   std::vector<uint8_t> body; IndexRecordOption mode; std::vector<uint8_t> fieldnorm_ids; bool has_fn; float avg;
 };
+// ---- positions codec (N3 groundwork) ---------------------------------------------------------------------------
+// One term: serialises `n` position deltas handed over in chunks of `chunk` (write_positions_delta may be called
+// several times per term); returns the byte length, bytes in *out (malloc'd by the caller via two calls: out == NULL
+// just sizes).
+size_t tqo_positions_serialize(const uint32_t* deltas, size_t n, size_t chunk, uint8_t* out, size_t out_cap) {
+  PositionSerializer ser;
+  if (chunk == 0) chunk = n ? n : 1;
+  for (size_t i = 0; i < n; i += chunk) ser.write_positions_delta(deltas + i, std::min(chunk, n - i));
+  ser.close_term();
+  if (out && out_cap >= ser.out.size()) std::memcpy(out, ser.out.data(), ser.out.size());
+  return ser.out.size();
+}
+struct tqo_position_reader { std::vector<uint8_t> data; PositionReader r; };
+tqo_position_reader* tqo_position_reader_open(const uint8_t* data, size_t len) {
+  auto* h = new tqo_position_reader();
+  h->data.assign(data, data + len);
+  if (!PositionReader::open(h->data.data(), h->data.size(), &h->r)) { delete h; return nullptr; }
+  return h;
+}
+void tqo_position_reader_read(tqo_position_reader* h, uint64_t offset, uint32_t* out, size_t n) { h->r.read(offset, out, n); }
+void tqo_position_reader_close(tqo_position_reader* h) { delete h; }
+
 tqo_field_writer* tqo_field_writer_create(int record_option, uint64_t total_num_tokens, const uint8_t* fieldnorm_ids, uint32_t max_doc) {
   auto* w = new tqo_field_writer();
   w->mode = (IndexRecordOption)record_option; w->has_fn = fieldnorm_ids != nullptr;

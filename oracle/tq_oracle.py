@@ -35,6 +35,12 @@ def _load():
     lib.tqo_segment_register.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
     lib.tqo_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_int, C.c_int, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tqo_count_batch.argtypes = [vp, C.POINTER(Query), sz, u64p]
+    lib.tqo_positions_serialize.restype = sz
+    lib.tqo_positions_serialize.argtypes = [u32p, sz, sz, u8p, sz]
+    lib.tqo_position_reader_open.restype = vp
+    lib.tqo_position_reader_open.argtypes = [u8p, sz]
+    lib.tqo_position_reader_read.argtypes = [vp, C.c_uint64, u32p, sz]
+    lib.tqo_position_reader_close.argtypes = [vp]
     lib.tqo_decode_postings.argtypes = [vp, C.POINTER(TermSeg), u32p, u32p]
     lib.tqo_block_table.argtypes = [vp, C.POINTER(TermSeg), C.c_float, C.c_float, u32p, f32p]
     lib.tqo_term_scorer_open.restype = vp
@@ -254,3 +260,33 @@ def merge_top_k(hits, start, end):
     os_, og, od = np.zeros(max(end, 1), np.float32), np.zeros(max(end, 1), np.uint32), np.zeros(max(end, 1), np.uint32)
     m = lib().tqo_merge_top_k(ptr(sc, f32p), ptr(sg, u32p), ptr(dc, u32p), n, start, end, ptr(os_, f32p), ptr(og, u32p), ptr(od, u32p))
     return list(zip(os_[:m].tolist(), og[:m].tolist(), od[:m].tolist()))
+
+
+# ---- positions codec (src/positions, N3 groundwork) -------------------------------------------------------------
+def positions_serialize(deltas, chunk=0):
+    """PositionSerializer: write_positions_delta (in chunks of `chunk`) + close_term -> the term's bytes."""
+    d = np.ascontiguousarray(deltas, dtype=np.uint32)
+    n = lib().tqo_positions_serialize(ptr(d, u32p), len(d), chunk, None, 0)
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    lib().tqo_positions_serialize(ptr(d, u32p), len(d), chunk, ptr(out, u8p), n)
+    return out[:n]
+
+
+class PositionReader:
+    def __init__(self, data):
+        self._data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.h = lib().tqo_position_reader_open(ptr(self._data, u8p), len(self._data))
+        if not self.h:
+            raise ValueError("corrupt positions data")
+
+    def read(self, offset, n):
+        out = np.zeros(max(n, 1), dtype=np.uint32)
+        lib().tqo_position_reader_read(self.h, offset, ptr(out, u32p), n)
+        return out[:n]
+
+    def close(self):
+        if self.h:
+            lib().tqo_position_reader_close(self.h)
+            self.h = None
+
+    __del__ = close

@@ -266,3 +266,72 @@ def test_merge_top_k():
     assert [(s, d) for s, _, d in O.merge_top_k(vals, 0, 2)] == [(9.0, 9), (8.0, 8)]
     assert [(s, d) for s, _, d in O.merge_top_k(vals, 2, 4)] == [(7.0, 7), (6.0, 6)]
     assert len(O.merge_top_k(vals, 0, 11)) == 10
+
+
+# ---- positions codec (SURVEY.md §8f N3 groundwork): src/positions/mod.rs tests ------------------------------------
+def _positions(vals, chunk=0):
+    data = O.positions_serialize(vals, chunk)
+    return data, O.PositionReader(data)
+
+
+def test_positions_sizes_pinned_by_the_reference():
+    # positions/mod.rs:82-96,131-134 (1000 deltas 0..999 -> 1224 bytes), :190-194 (512 -> 533),
+    # :167-171 (2_000_000 -> 5_003_499), :204-209 (2_000_000 x 9 -> 1_015_627), :100-108 (empty term is readable)
+    assert len(O.positions_serialize(np.arange(1000))) == 1224
+    assert len(O.positions_serialize(np.arange(512))) == 533
+    assert len(O.positions_serialize(np.arange(2_000_000))) == 5_003_499
+    assert len(O.positions_serialize(np.full(2_000_000, 9))) == 1_015_627
+    empty = O.positions_serialize([])
+    assert bytes(empty) == b"\x80"  # VInt(0) bit-packed blocks, nothing else
+    O.PositionReader(empty)
+    # postings/mod.rs:61-81 test_position_write: 120 docs x deltas [1, 2, 3, 2] -> a 207-byte `.pos` FILE = this term's
+    # 196 bytes (VInt(3) + 3 widths + 3 x 32-byte blocks of 2-bit deltas + 96 VInt bytes) + the 11-byte composite footer
+    assert len(O.positions_serialize(np.tile([1, 2, 3, 2], 120))) == 207 - 11
+
+
+def test_positions_read_offsets_and_rereads():
+    data, r = _positions(np.arange(1000))
+    for n in (1, 10, 127, 128, 130, 312):  # mod.rs:82-96
+        assert (r.read(0, n) == np.arange(n)).all()
+    for offset in (1, 10, 127, 128, 130, 312):  # mod.rs:131-146
+        for n in (1, 10, 130, 500):
+            assert (r.read(offset, n) == np.arange(offset, offset + n)).all()
+    _, r = _positions(np.arange(1000))
+    c = 0
+    for step in range(100):  # mod.rs:149-166 read twice, then skip
+        a = r.read(7 * step, 7)
+        b = r.read(7 * step, 7)
+        assert (a == b).all() and (a == np.arange(c, c + 7)).all()
+        c += 7
+    _, r = _positions(np.arange(512))
+    assert r.read(230, 1)[0] == 230 and r.read(9, 1)[0] == 9  # mod.rs:190-201 going back resets the reader
+    _, r = _positions(np.arange(2_000_000))
+    for _ in range(2):  # mod.rs:168-183 anchor != block
+        assert (r.read(128, 256) == np.arange(128, 384)).all()
+    data, _ = _positions(np.arange(2_000_000))
+    for offset in (10, 128 * 1024, 128 * 1024 - 1, 128 * 1024 + 7, 128 * 10 * 1024 + 10):  # mod.rs:213-235
+        assert O.PositionReader(data).read(offset, 1)[0] == offset
+
+
+def test_positions_multiple_writes_and_random_round_trips():
+    data = O.positions_serialize([1, 12, 4, 17, 443], chunk=2)  # mod.rs:110-129: several write_positions_delta calls
+    assert (O.PositionReader(data).read(0, 5) == [1, 12, 4, 17, 443]).all()
+    assert bytes(data) == bytes(O.positions_serialize([1, 12, 4, 17, 443]))
+    rng = np.random.default_rng(21)
+    for n in (0, 1, 70, 127, 128, 129, 200, 255, 256, 257, 270):  # mod.rs:57-66 proptest sizes
+        vals = rng.choice([1, 2, 4, 8, 16], size=n).astype(np.uint32)
+        data = O.positions_serialize(vals, chunk=int(rng.integers(1, 50)))
+        r = O.PositionReader(data)
+        for i in range(n):
+            assert r.read(i, 1)[0] == vals[i]
+        if n:
+            assert (O.PositionReader(data).read(0, n) == vals).all()
+
+
+def test_positions_of_the_compat_fixture():
+    # tests/compat_tests_data/index_v{6,7}/*.pos: the label field's only term has one position, 0:
+    # VInt(0 blocks) + VInt(0) = 80 80 (the TermInfo in the `.term` file says positions_range 0..2)
+    for ver in ("index_v6", "index_v7"):
+        pos = bytes.fromhex(GOLDEN["compat"][ver]["pos"])
+        assert pos[:2] == bytes(O.positions_serialize([0])) == b"\x80\x80"
+        assert O.PositionReader(np.frombuffer(pos[:2], dtype=np.uint8)).read(0, 1)[0] == 0
