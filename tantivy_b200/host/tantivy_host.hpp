@@ -172,9 +172,14 @@ inline std::vector<std::string> tokenize(const std::string& tokenizer, const std
 }
 
 // ---- segment data --------------------------------------------------------------------------------------------
-struct TermInfo {  // src/postings/term_info.rs:9-16 (positions range left out: not on this path)
+struct TermInfo {  // src/postings/term_info.rs:9-16
   uint32_t doc_freq = 0;
   uint64_t postings_start = 0, postings_end = 0;
+  uint64_t positions_start = 0, positions_end = 0;  // byte range in the `.pos` sub-file (not used by this path yet)
+  bool operator==(const TermInfo& o) const {
+    return doc_freq == o.doc_freq && postings_start == o.postings_start && postings_end == o.postings_end &&
+           positions_start == o.positions_start && positions_end == o.positions_end;
+  }
 };
 
 struct FieldSegmentData {
@@ -829,6 +834,95 @@ inline void load_field(SegmentData& seg, Field field, IndexRecordOption record, 
       fd.fieldnorms.assign(fieldnorm_file->begin() + (long)fit->second.offset, fieldnorm_file->begin() + (long)(fit->second.offset + fit->second.len));
     }
   }
+}
+
+// ---- term dictionary framing (N2, the part the reference tree specifies) ------------------------------------------
+// A field's `.term` sub-file = [fst][TermInfoStore][u64 store_len][u32 FST_VERSION = 1][u32 dictionary type = 1]
+// (src/termdict/fst_termdict/termdict.rs:78-89,125-143; src/termdict/mod.rs:51-90).  The FST (term bytes -> ordinal) is
+// crate tantivy-fst 0.5, not in the reference tree: it is handed back as raw bytes.  The TermInfoStore (ordinal ->
+// TermInfo) is in-tree (term_info_store.rs:12-158) and is read here.
+inline uint64_t extract_bits(const uint8_t* data, size_t len, size_t addr_bits, uint8_t num_bits) {  // term_info_store.rs:106-124
+  const size_t addr_byte = addr_bits / 8;
+  uint8_t buf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (addr_byte < len) std::memcpy(buf, data + addr_byte, std::min<size_t>(8, len - addr_byte));
+  uint64_t v;
+  std::memcpy(&v, buf, 8);
+  v >>= (addr_bits % 8);
+  return num_bits >= 64 ? v : v & ((1ull << num_bits) - 1ull);
+}
+
+class TermInfoStore {
+ public:
+  static constexpr size_t kBlockLen = 256, kBlockMetaBytes = 8 + 28 + 3;
+  TermInfoStore() = default;
+  TermInfoStore(const uint8_t* data, size_t len) {  // TermInfoStore::open
+    if (len < 16) throw TantivyError(TantivyError::DataCorruption, "term info store too short");
+    uint64_t meta_len;
+    std::memcpy(&meta_len, data, 8);
+    std::memcpy(&num_terms_, data + 8, 8);
+    if (16 + meta_len > len) throw TantivyError(TantivyError::DataCorruption, "term info store: block metas out of range");
+    metas_.assign(data + 16, data + 16 + meta_len);
+    bits_.assign(data + 16 + meta_len, data + len);
+  }
+  uint64_t num_terms() const { return num_terms_; }
+  TermInfo get(uint64_t term_ord) const {  // TermInfoStore::get + TermInfoBlockMeta::deserialize_term_info
+    if (term_ord >= num_terms_) throw TantivyError(TantivyError::InvalidArgument, "term ordinal out of range");
+    const size_t block = (size_t)(term_ord / kBlockLen), inner = (size_t)(term_ord % kBlockLen);
+    if ((block + 1) * kBlockMetaBytes > metas_.size()) throw TantivyError(TantivyError::DataCorruption, "term info store: missing block meta");
+    const uint8_t* m = metas_.data() + block * kBlockMetaBytes;
+    uint64_t offset, post_start, pos_start;
+    uint32_t doc_freq, post_len, pos_len;
+    std::memcpy(&offset, m, 8);
+    std::memcpy(&doc_freq, m + 8, 4);
+    std::memcpy(&post_start, m + 12, 8);
+    std::memcpy(&post_len, m + 20, 4);
+    std::memcpy(&pos_start, m + 24, 8);
+    std::memcpy(&pos_len, m + 32, 4);
+    TermInfo ref;
+    ref.doc_freq = doc_freq; ref.postings_start = post_start; ref.postings_end = post_start + post_len;
+    ref.positions_start = pos_start; ref.positions_end = pos_start + pos_len;
+    if (inner == 0) return ref;
+    const uint8_t df_bits = m[36], post_bits = m[37], pos_bits = m[38];
+    const size_t nbits = (size_t)df_bits + post_bits + pos_bits;
+    if (offset > bits_.size()) throw TantivyError(TantivyError::DataCorruption, "term info store: block offset out of range");
+    const uint8_t* d = bits_.data() + offset;
+    const size_t dl = bits_.size() - (size_t)offset;
+    const size_t a_post = nbits * (inner - 1);  // the end of an entry is the start of the next one
+    const size_t a_pos = a_post + post_bits;
+    const size_t a_df = a_pos + pos_bits;
+    TermInfo ti;
+    ti.postings_start = ref.postings_start + extract_bits(d, dl, a_post, post_bits);
+    ti.postings_end = ref.postings_start + extract_bits(d, dl, a_post + nbits, post_bits);
+    ti.positions_start = ref.positions_start + extract_bits(d, dl, a_pos, pos_bits);
+    ti.positions_end = ref.positions_start + extract_bits(d, dl, a_pos + nbits, pos_bits);
+    ti.doc_freq = (uint32_t)extract_bits(d, dl, a_df, df_bits);
+    return ti;
+  }
+
+ private:
+  uint64_t num_terms_ = 0;
+  std::vector<uint8_t> metas_, bits_;
+};
+
+struct TermDictionaryParts {
+  std::vector<uint8_t> fst;  // tantivy-fst 0.5 bytes (not decoded here)
+  TermInfoStore store;
+};
+inline TermDictionaryParts open_term_dictionary(const uint8_t* sub, size_t len) {
+  if (len < 16) throw TantivyError(TantivyError::DataCorruption, "term dictionary too short");
+  uint32_t dict_type, fst_version;
+  uint64_t store_len;
+  std::memcpy(&dict_type, sub + len - 4, 4);
+  std::memcpy(&fst_version, sub + len - 8, 4);
+  std::memcpy(&store_len, sub + len - 16, 8);
+  if (dict_type != 1u) throw TantivyError(TantivyError::Unsupported, "term dictionary is not the FST kind (sstable dictionaries: quickwit feature)");
+  if (fst_version != 1u) throw TantivyError(TantivyError::DataCorruption, "unsupported FST_VERSION");
+  if (store_len + 16 > len) throw TantivyError(TantivyError::DataCorruption, "term dictionary: store length out of range");
+  TermDictionaryParts parts;
+  const size_t fst_len = len - 16 - (size_t)store_len;
+  parts.fst.assign(sub, sub + fst_len);
+  parts.store = TermInfoStore(sub + fst_len, (size_t)store_len);
+  return parts;
 }
 
 // ---- meta.json (src/index/index_meta.rs: IndexMeta { index_settings, segments, schema, opstamp }) ---------------------

@@ -388,6 +388,76 @@ static void test_host_tokenizer_and_statistics() {
   CHECK(body[8 + ti->postings_start] == (0x80 | 0) && body[8 + ti->postings_start + 1] == (0x80 | 11));
 }
 
+// TermInfoStoreWriter restated for the test (term_info_store.rs:160-294): blocks of 256, the first entry verbatim in the
+// 39-byte block meta, the others bit-packed as (postings start, positions start, doc_freq) deltas, the block's end offsets last.
+static std::vector<uint8_t> write_term_info_store(const std::vector<TermInfo>& infos) {
+  auto nbits = [](uint64_t v) { uint8_t n = 0; while (v) { ++n; v >>= 1; } return n; };
+  std::vector<uint8_t> metas, bits;
+  auto put = [](std::vector<uint8_t>& out, const void* p, size_t n) { const uint8_t* b = (const uint8_t*)p; out.insert(out.end(), b, b + n); };
+  for (size_t b0 = 0; b0 < infos.size(); b0 += 256) {
+    const size_t n = std::min<size_t>(256, infos.size() - b0);
+    const TermInfo& ref = infos[b0];
+    const TermInfo& last = infos[b0 + n - 1];
+    const uint64_t post_end = last.postings_end - ref.postings_start, pos_end = last.positions_end - ref.positions_start;
+    uint32_t max_df = 0;
+    for (size_t i = 1; i < n; ++i) max_df = std::max(max_df, infos[b0 + i].doc_freq);
+    const uint8_t df_bits = nbits(max_df), post_bits = nbits(post_end), pos_bits = nbits(pos_end);
+    const uint64_t offset = bits.size();
+    const uint32_t post_len = (uint32_t)(ref.postings_end - ref.postings_start), pos_len = (uint32_t)(ref.positions_end - ref.positions_start);
+    put(metas, &offset, 8); put(metas, &ref.doc_freq, 4); put(metas, &ref.postings_start, 8); put(metas, &post_len, 4);
+    put(metas, &ref.positions_start, 8); put(metas, &pos_len, 4);
+    metas.push_back(df_bits); metas.push_back(post_bits); metas.push_back(pos_bits);
+    unsigned __int128 acc = 0;  // LSB-first bit packer (tantivy_bitpacker::BitPacker)
+    int filled = 0;
+    auto write_bits = [&](uint64_t v, uint8_t nb) {
+      acc |= (unsigned __int128)v << filled;
+      filled += nb;
+      while (filled >= 8) { bits.push_back((uint8_t)acc); acc >>= 8; filled -= 8; }
+    };
+    for (size_t i = 1; i < n; ++i) {
+      write_bits(infos[b0 + i].postings_start - ref.postings_start, post_bits);
+      write_bits(infos[b0 + i].positions_start - ref.positions_start, pos_bits);
+      write_bits(infos[b0 + i].doc_freq, df_bits);
+    }
+    write_bits(post_end, post_bits);
+    write_bits(pos_end, pos_bits);
+    if (filled) { bits.push_back((uint8_t)acc); acc = 0; filled = 0; }  // a block ends on a byte boundary
+  }
+  std::vector<uint8_t> out;
+  const uint64_t len = metas.size(), num = infos.size();
+  put(out, &len, 8); put(out, &num, 8);
+  out.insert(out.end(), metas.begin(), metas.end());
+  out.insert(out.end(), bits.begin(), bits.end());
+  return out;
+}
+
+static void test_host_term_info_store() {
+  // term_info_store.rs:308-324 test_bitpacked: 321 in 9 bits, 2 in 2 bits, 51 in 6 bits -> 3 bytes
+  const uint8_t packed[3] = {(uint8_t)(321 & 0xFF), (uint8_t)((321 >> 8) | (2 << 1) | ((51 & 0x1F) << 3)), (uint8_t)(51 >> 5)};
+  CHECK(files::extract_bits(packed, 3, 0, 9) == 321 && files::extract_bits(packed, 3, 9, 2) == 2 && files::extract_bits(packed, 3, 11, 6) == 51);
+  // term_info_store.rs:349-380 test_pack shape: consecutive postings / positions ranges, 1000 terms = 4 blocks
+  std::vector<TermInfo> infos;
+  uint64_t post = 0, pos = 0;
+  uint32_t x = 7;
+  for (int i = 0; i < 1000; ++i) {
+    x = x * 1664525u + 1013904223u;
+    TermInfo ti;
+    ti.doc_freq = 1 + (x >> 8) % 5000;
+    ti.postings_start = post; post += 1 + (x >> 12) % 700; ti.postings_end = post;
+    ti.positions_start = pos; pos += (x >> 20) % 3000; ti.positions_end = pos;
+    infos.push_back(ti);
+  }
+  const std::vector<uint8_t> bytes = write_term_info_store(infos);
+  files::TermInfoStore store(bytes.data(), bytes.size());
+  CHECK(store.num_terms() == 1000);
+  bool all = true;
+  for (size_t i = 0; i < infos.size(); ++i) all = all && store.get(i) == infos[i];
+  CHECK(all);
+  bool range = false;
+  try { store.get(1000); } catch (const TantivyError& e) { range = e.kind() == TantivyError::InvalidArgument; }
+  CHECK(range);
+}
+
 static void test_host_search_without_device_raises() {
   Index index = index_one_doc_string();
   Field text = *index.schema().get_field("text");
@@ -414,10 +484,18 @@ static Index index_from_compat_files(const std::string& dir, const std::string& 
   const std::string base = dir + "/" + version + "/";
   const auto meta_bytes = read_file(base + "meta.json");
   Index index = files::open_index(std::string(meta_bytes.begin(), meta_bytes.end()), [&](const std::string& name) { return read_file(base + name); });
-  // the `.term` dictionary is N2: the TermInfo of the only term is supplied (postings bytes 0..2 of the sub-file)
+  // the `.term` file: its framing and TermInfoStore are read (term ordinal 0 -> TermInfo); the FST that maps term
+  // bytes to the ordinal is crate tantivy-fst (N2, not decoded): the dictionary has exactly one term, "dateformat"
   Field label = *index.schema().get_field("label");
+  const files::IndexMeta meta = files::read_meta(std::string(meta_bytes.begin(), meta_bytes.end()));
+  const auto term_file = read_file(base + meta.segments[0].file_stem() + ".term");
+  const files::Footer tf = files::read_footer(term_file.data(), term_file.size());
+  auto parts = files::open_composite(term_file.data(), tf.body_len);
+  const files::FileSlice sl = parts.at({label.id, 0});
+  const files::TermDictionaryParts dict = files::open_term_dictionary(term_file.data() + sl.offset, sl.len);
+  if (dict.store.num_terms() != 1) throw TantivyError(TantivyError::DataCorruption, "compat fixture: one term expected");
   auto seg = std::make_shared<SegmentData>(*index.segments()[0]);
-  seg->fields[label.id].term_dict["dateformat"] = TermInfo{1, 0, 2};
+  seg->fields[label.id].term_dict["dateformat"] = dict.store.get(0);
   return Index::from_segments(index.schema(), {seg});
 }
 
@@ -443,6 +521,9 @@ static void test_host_compat_framing(const std::string& dir) {
     CHECK(seg.fields[0].total_num_tokens() == 1);
     CHECK(seg.fields[0].idx_body.size() == 10 && seg.fields[0].idx_body[8] == 0x80 && seg.fields[0].idx_body[9] == 0x81);
     CHECK(seg.fields[0].fieldnorms.size() == 1 && seg.fields[0].fieldnorms[0] == 1);
+    // the TermInfo read from the `.term` file: 1 doc, postings bytes 0..2, positions bytes 0..2
+    const TermInfo ti = seg.fields[0].term_dict.at("dateformat");
+    CHECK(ti.doc_freq == 1 && ti.postings_start == 0 && ti.postings_end == 2 && ti.positions_start == 0 && ti.positions_end == 2);
     auto corrupted = idx;
     corrupted[0] ^= 1;
     bool crc = false;
@@ -536,6 +617,7 @@ int main(int argc, char** argv) {
   std::vector<std::pair<std::string, std::function<void()>>> tests;
   if (mode == "--cpu") {
     tests = {{"host_tokenizer_and_statistics", test_host_tokenizer_and_statistics},
+             {"host_term_info_store", test_host_term_info_store},
              {"host_search_without_device_raises", test_host_search_without_device_raises}};
     if (!dir.empty()) tests.push_back({"host_compat_framing", [dir]() { test_host_compat_framing(dir); }});
   } else {
