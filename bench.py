@@ -201,7 +201,8 @@ def main():
         if rank != 0:
             return 0
         shard = make_shard(wl, dens, 0, 1, args.seed)
-        sample = args.cpu_sample or 64
+        # several queries per host thread, so that the threads stay busy while the heavy queries of the sample finish
+        sample = args.cpu_sample or min(512, max(64, 4 * host_threads))
         qps, ms = cpu_reference_run(wl, shard, batches, args.steps, args.warmup, sample, host_threads)
         line = {"metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -354,8 +355,8 @@ def main():
                         "ms_per_step": 1000.0 * dt_e2e / args.steps},
                 "gpu_launches": int(launches)}
         if world == 1 and not args.no_cpu_baseline:
-            sample = args.cpu_sample or 64
-            # bounded: grow the sample until the CPU leg takes a few seconds per step
+            sample = args.cpu_sample or min(512, max(64, 4 * host_threads))
+            # bounded: a few seconds per step; several queries per host thread keep the threads busy
             qps, ms = cpu_reference_run(wl, shard, batches, 2, 1, sample, host_threads)
             line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": host_threads, "kind": "port",
                                     "sample": f"3 x {sample} queries of the same stream (1 warm-up), all host threads, oracle/ "
