@@ -56,6 +56,28 @@ inline void put_u32(uint32_t v, std::vector<uint8_t>& out) {
   out.push_back((uint8_t)v); out.push_back((uint8_t)(v >> 8)); out.push_back((uint8_t)(v >> 16)); out.push_back((uint8_t)(v >> 24));
 }
 
+// Writes one term's position deltas the way the reference's PositionSerializer does (src/positions/serializer.rs,
+// layout src/positions/mod.rs:13-31): VInt(number of bit-packed blocks), their bit widths, the blocks of 128 deltas
+// (plain values, not minus-one), then the rest as VInts.  `deltas` = for every posting, its first position followed by
+// the gaps between consecutive positions.  Appends to `out`; the byte range appended is the term's positions_range.
+inline void encode_positions(const uint32_t* deltas, size_t n, std::vector<uint8_t>& out) {
+  const size_t n_blocks = n / kBlock;
+  put_vint64(n_blocks, out);
+  const size_t widths_at = out.size();
+  out.resize(out.size() + n_blocks);
+  alignas(16) uint8_t packed[kBlock * 4];
+  for (size_t b = 0; b < n_blocks; ++b) {
+    const uint32_t* d = deltas + b * kBlock;
+    uint32_t orv = 0;
+    for (uint32_t i = 0; i < kBlock; ++i) orv |= d[i];
+    const uint32_t bits = bits_for(orv);
+    out[widths_at + b] = (uint8_t)bits;
+    pack_block_4x(d, bits, packed);
+    out.insert(out.end(), packed, packed + 16 * bits);
+  }
+  for (size_t i = n_blocks * kBlock; i < n; ++i) put_vint(deltas[i], out);
+}
+
 struct TermInfoOut { uint32_t doc_freq; uint64_t postings_start, postings_end; };
 
 // Encodes whole posting lists of one field of one segment.

@@ -188,6 +188,7 @@ struct FieldSegmentData {
   bool has_fieldnorms = false;
   std::vector<uint8_t> idx_body;   // the field's `.idx` sub-file: u64 total_num_tokens + posting lists (serializer.rs:128)
   std::vector<uint8_t> fieldnorms; // the field's `.fieldnorm` sub-file: one fieldnorm id per doc
+  std::vector<uint8_t> positions;  // the field's `.pos` sub-file (WithFreqsAndPositions fields written by the in-RAM writer)
   std::map<std::string, TermInfo> term_dict;          // term bytes -> TermInfo (the `.term` file, N2, is not read yet)
   std::map<std::string, std::vector<DocId>> term_docs; // kept by the in-RAM writer only, for delete_term
   uint64_t total_num_tokens() const {
@@ -621,14 +622,21 @@ inline Opstamp IndexWriter::commit() {
     const size_t nf = schema.num_fields();
     seg->fields.resize(nf);
     std::vector<std::map<std::string, std::vector<std::pair<DocId, uint32_t>>>> postings(nf);
+    std::vector<std::map<std::string, std::vector<uint32_t>>> pos_deltas(nf);  // per term: first position, then gaps, per posting
     std::vector<std::vector<uint32_t>> num_tokens(nf, std::vector<uint32_t>(seg->max_doc, 0));
     for (DocId d = 0; d < seg->max_doc; ++d) {
       for (auto& fv : pending_[d].doc.field_values()) {
         const FieldEntry& fe = schema.get_field_entry(fv.first);
         if (!fe.options.indexing) continue;
+        std::map<std::string, uint32_t> last_pos;  // within this field value
         for (auto& tok : tokenize(fe.options.indexing->tokenizer, fv.second)) {
           auto& pl = postings[fv.first.id][tok];
-          if (!pl.empty() && pl.back().first == d) ++pl.back().second; else pl.push_back({d, 1u});
+          const uint32_t position = num_tokens[fv.first.id][d];  // token ordinal in the doc's field (positions/mod.rs:1-5)
+          const bool again = !pl.empty() && pl.back().first == d;
+          if (again) ++pl.back().second; else pl.push_back({d, 1u});
+          auto lp = last_pos.find(tok);
+          pos_deltas[fv.first.id][tok].push_back(again && lp != last_pos.end() ? position - lp->second : position);
+          last_pos[tok] = position;
           ++num_tokens[fv.first.id][d];
         }
       }
@@ -652,7 +660,14 @@ inline Opstamp IndexWriter::commit() {
         docs.clear(); tfs.clear();
         for (auto& p : kv.second) { docs.push_back(p.first); tfs.push_back(p.second); }
         const tq::TermInfoOut ti = w.add_term(docs.data(), fd.record == IndexRecordOption::Basic ? nullptr : tfs.data(), (uint32_t)docs.size());
-        fd.term_dict[kv.first] = TermInfo{ti.doc_freq, ti.postings_start, ti.postings_end};
+        TermInfo info{ti.doc_freq, ti.postings_start, ti.postings_end};
+        if (fd.record == IndexRecordOption::WithFreqsAndPositions) {  // serializer.rs:436-454: positions_range of the term
+          const std::vector<uint32_t>& pd = pos_deltas[f][kv.first];
+          info.positions_start = fd.positions.size();
+          tq::encode_positions(pd.data(), pd.size(), fd.positions);
+          info.positions_end = fd.positions.size();
+        }
+        fd.term_dict[kv.first] = info;
         fd.term_docs[kv.first] = docs;
       }
       fd.idx_body = w.body();

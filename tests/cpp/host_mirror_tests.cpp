@@ -588,12 +588,13 @@ static void dump_all(const std::string& dir) {
         const std::string base = all[n].name + ".seg" + std::to_string(s) + ".f" + std::to_string(f);
         write_file(dir + "/" + base + ".idx", fd.idx_body.data(), fd.idx_body.size());
         if (fd.has_fieldnorms) write_file(dir + "/" + base + ".fieldnorm", fd.fieldnorms.data(), fd.fieldnorms.size());
+        write_file(dir + "/" + base + ".pos", fd.positions.data(), fd.positions.size());
         m << (f ? ", " : "") << "{\"record\": " << (int)fd.record << ", \"idx\": \"" << base << ".idx\", \"fieldnorm\": "
           << (fd.has_fieldnorms ? "\"" + base + ".fieldnorm\"" : std::string("null")) << ", \"terms\": {";
         bool first = true;
         for (auto& kv : fd.term_dict) {
           m << (first ? "" : ", ") << "\"" << json_escape(kv.first) << "\": [" << kv.second.doc_freq << ", " << kv.second.postings_start << ", "
-            << kv.second.postings_end << "]";
+            << kv.second.postings_end << ", " << kv.second.positions_start << ", " << kv.second.positions_end << "]";
           first = false;
         }
         m << "}}";

@@ -53,7 +53,9 @@ class DumpedField:
         self.fn_ids = np.frombuffer((d / spec["fieldnorm"]).read_bytes(), dtype=np.uint8) if spec["fieldnorm"] else None
         self.alive = np.frombuffer((d / seg["alive"]).read_bytes(), dtype=np.uint8) if seg["alive"] else None
         self.total_num_tokens = int(np.frombuffer(self.body[:8].tobytes(), dtype="<u8")[0])
-        self.terms = {t: tuple(v) for t, v in spec["terms"].items()}
+        self.terms = {t: tuple(v[:3]) for t, v in spec["terms"].items()}
+        self.positions_range = {t: (v[3], v[4]) for t, v in spec["terms"].items()}
+        self.pos = np.frombuffer((d / spec["idx"].replace(".idx", ".pos")).read_bytes(), dtype=np.uint8)
 
     def register(self, index):
         index.segment_register(self.segment_ord, self.field, self.max_doc, self.record_option, self.body, self.fn_ids, self.alive)
@@ -153,6 +155,41 @@ def test_mirror_multi_segment_index_is_well_formed(workdir):
     a = oracle_search(segs, query(TQ_OP_OR, segs, ["w0", "w3", "w11"], 300), 0)
     b = oracle_search(segs, query(TQ_OP_OR, segs, ["w0", "w3", "w11"], 300), 1)
     assert len(a) == 300 and [(g, d) for _, g, d in a[:50]] == [(g, d) for _, g, d in b[:50]]
+
+
+def test_mirror_writes_the_reference_position_format(workdir):
+    """`.pos` of the mirror's IndexWriter (tq::encode_positions): byte-identical to the oracle's PositionSerializer on a
+    text whose positions are known, and self-consistent (tf positions per posting, increasing, below the doc length)
+    on the pseudo-random three-segment index."""
+    segs = load(workdir, "droopy")["text"]
+    texts = ["hello happy tax payer", "droopy says hello happy tax payer", "i like droopy"]
+    seg = segs[0]
+    for term, (a, b) in seg.positions_range.items():
+        deltas = []
+        for text in texts:
+            ps = [i for i, t in enumerate(text.split()) if t == term]
+            if ps:
+                deltas += [ps[0]] + [y - x for x, y in zip(ps, ps[1:])]
+        assert bytes(seg.pos[a:b]) == bytes(O.positions_serialize(deltas)), term
+    ix = O.OracleIndex()
+    segs = load(workdir, "multi_segment")["body"]
+    for s in segs:
+        s.register(ix)
+    for s in segs:
+        for term in ("w0", "w3", "rare", "w16"):
+            if term not in s.terms:
+                continue
+            df, st, en = s.terms[term]
+            docs, tfs = ix.decode_postings((0, s.segment_ord, s.field, df, st, en))
+            a, b = s.positions_range[term]
+            reader = O.PositionReader(s.pos[a:b])
+            deltas = reader.read(0, int(tfs.sum()))
+            assert bytes(O.positions_serialize(deltas)) == bytes(s.pos[a:b])  # nothing but these deltas in the range
+            off = 0
+            for d, tf in zip(docs[:200], tfs[:200]):
+                ps = np.cumsum(deltas[off:off + tf])
+                off += int(tf)
+                assert (np.diff(ps) > 0).all() and ps[-1] < 64  # docs of this index have at most 31 + 1 tokens
 
 
 @pytest.mark.gpu
