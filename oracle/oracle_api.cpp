@@ -15,6 +15,7 @@
 #include "../include/tantivy_b200.h"
 #include "positions.hpp"
 #include "query.hpp"
+#include "phrase.hpp"
 
 using namespace tqo;
 
@@ -24,6 +25,7 @@ struct OSegment {
   std::vector<uint8_t> idx_body;  // incl. 8-byte total_num_tokens header
   std::vector<uint8_t> fieldnorm; bool has_fieldnorm;
   std::vector<uint8_t> alive; bool has_alive;
+  std::vector<uint8_t> positions;  // the field's `.pos` sub-file (phrase queries, N3)
   bool is_alive(uint32_t doc) const { return !has_alive || ((alive[doc >> 3] >> (doc & 7)) & 1); }
 };
 struct tqo_index {
@@ -332,6 +334,67 @@ uint8_t tqo_fieldnorm_to_id(uint32_t f) { return fieldnorm_to_id(f); }
 struct tqo_field_writer {
   std::vector<uint8_t> body; IndexRecordOption mode; std::vector<uint8_t> fieldnorm_ids; bool has_fn; float avg;
 };
+// ---- phrase queries (N3 groundwork): PhraseScorer over registered segments ------------------------------------------
+int tqo_segment_register_positions(tqo_index* ix, uint32_t segment_ord, uint32_t field, const uint8_t* pos, size_t len) {
+  auto it = ix->segs.find({segment_ord, field});
+  if (it == ix->segs.end()) { ix->err = "segment/field not registered"; return TQ_ERR_NOT_FOUND; }
+  it->second.positions.assign(pos, pos + len);
+  return TQ_OK;
+}
+
+typedef struct {
+  uint32_t offset;  // position of the term inside the phrase
+  uint32_t segment_ord, field, doc_freq;
+  uint64_t postings_start, postings_end, positions_start, positions_end;
+} tqo_phrase_term;
+
+// All matches of one phrase in (segment, doc) order: PhraseWeight::scorer + a collector that keeps everything
+// (phrase_weight.rs:41-110; weight = Bm25Weight::for_terms over the phrase's terms, supplied by the caller).
+int tqo_phrase_search(tqo_index* ix, const tqo_phrase_term* terms, size_t n, uint32_t n_phrase_terms, float weight, float avg_fieldnorm,
+                      uint32_t slop, size_t cap, uint32_t* out_seg, uint32_t* out_doc, float* out_score, uint32_t* out_count, size_t* out_n) {
+  try {
+    std::vector<uint32_t> seg_ords;
+    for (size_t i = 0; i < n; ++i) seg_ords.push_back(terms[i].segment_ord);
+    std::sort(seg_ords.begin(), seg_ords.end());
+    seg_ords.erase(std::unique(seg_ords.begin(), seg_ords.end()), seg_ords.end());
+    size_t w = 0;
+    for (uint32_t so : seg_ords) {
+      std::vector<std::pair<uint32_t, PhraseTerm>> tp;
+      const OSegment* seg = nullptr;
+      for (size_t i = 0; i < n; ++i) {
+        const tqo_phrase_term& t = terms[i];
+        if (t.segment_ord != so || t.doc_freq == 0) continue;
+        const OSegment& s = ix->segs.at({t.segment_ord, t.field});
+        seg = &s;
+        if (s.record_option != WithFreqsAndPositions) throw std::runtime_error("field has no positions");
+        PhraseTerm pt;
+        pt.postings.block_cursor = BlockSegmentPostings::open(t.doc_freq, s.idx_body.data() + 8 + t.postings_start,
+                                                              (size_t)(t.postings_end - t.postings_start), s.record_option, WithFreqsAndPositions);
+        pt.postings.cur = 0;
+        if (t.positions_end > s.positions.size() || !PositionReader::open(s.positions.data() + t.positions_start,
+                                                                          (size_t)(t.positions_end - t.positions_start), &pt.reader))
+          throw std::runtime_error("corrupt positions range");
+        tp.emplace_back(t.offset, std::move(pt));
+      }
+      if (!seg || tp.size() < n_phrase_terms) continue;  // a term without postings in this segment: no match
+      PhraseScorer sc;
+      sc.slop = slop;
+      sc.fieldnorm_reader = seg->has_fieldnorm ? FieldNormReader::from_data(seg->fieldnorm.data(), seg->max_doc) : FieldNormReader::constant(seg->max_doc, 1);
+      sc.similarity_weight.weight = weight;
+      sc.similarity_weight.average_fieldnorm = avg_fieldnorm;
+      for (int id = 0; id < 256; ++id) sc.similarity_weight.cache[id] = cached_tf_component(id_to_fieldnorm((uint8_t)id), avg_fieldnorm);
+      sc.init(std::move(tp));
+      for (uint32_t d = sc.doc(); d != TERMINATED; d = sc.advance()) {
+        if (!seg->is_alive(d)) continue;
+        if (w < cap) { out_seg[w] = so; out_doc[w] = d; out_score[w] = sc.score(); out_count[w] = sc.phrase_count(); }
+        ++w;
+      }
+    }
+    *out_n = w;
+  } catch (const std::exception& e) { ix->err = e.what(); return TQ_ERR_INVALID_ARGUMENT; }
+  return TQ_OK;
+}
+
 // ---- positions codec (N3 groundwork) ---------------------------------------------------------------------------
 // One term: serialises `n` position deltas handed over in chunks of `chunk` (write_positions_delta may be called
 // several times per term); returns the byte length, bytes in *out (malloc'd by the caller via two calls: out == NULL

@@ -35,6 +35,8 @@ def _load():
     lib.tqo_segment_register.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
     lib.tqo_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_int, C.c_int, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tqo_count_batch.argtypes = [vp, C.POINTER(Query), sz, u64p]
+    lib.tqo_segment_register_positions.argtypes = [vp, C.c_uint32, C.c_uint32, u8p, sz]
+    lib.tqo_phrase_search.argtypes = [vp, vp, sz, C.c_uint32, C.c_float, C.c_float, C.c_uint32, sz, u32p, u32p, f32p, u32p, C.POINTER(sz)]
     lib.tqo_positions_serialize.restype = sz
     lib.tqo_positions_serialize.argtypes = [u32p, sz, sz, u8p, sz]
     lib.tqo_position_reader_open.restype = vp
@@ -168,6 +170,31 @@ class OracleIndex:
             raise RuntimeError(lib().tqo_last_error(self.h).decode())
         return scores, segs, docs, counts
 
+    def register_positions(self, segment_ord, field, pos_bytes):
+        """The field's `.pos` sub-file of a registered segment (phrase queries)."""
+        p = np.ascontiguousarray(pos_bytes, dtype=np.uint8)
+        rc = lib().tqo_segment_register_positions(self.h, segment_ord, field, ptr(p, u8p), len(p))
+        if rc != 0:
+            raise RuntimeError(lib().tqo_last_error(self.h).decode())
+
+    def phrase_search(self, terms, weight, avg_fieldnorm, slop=0, cap=4096):
+        """PhraseScorer over the registered segments.  terms: (offset in phrase, segment_ord, field, doc_freq,
+        postings_start, postings_end, positions_start, positions_end) per (term, segment).
+        Returns [(segment, doc, score, phrase_count)] in (segment, doc) order."""
+        arr = np.zeros(len(terms), dtype=PHRASE_TERM_DTYPE)
+        for i, t in enumerate(terms):
+            arr[i] = tuple(int(x) for x in t)
+        n_phrase_terms = len({int(t[0]) for t in terms})
+        sg, dc = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+        sc, ct = np.zeros(cap, np.float32), np.zeros(cap, np.uint32)
+        n = C.c_size_t(0)
+        rc = lib().tqo_phrase_search(self.h, arr.ctypes.data, len(terms), n_phrase_terms, np.float32(weight), np.float32(avg_fieldnorm), slop,
+                                     cap, ptr(sg, u32p), ptr(dc, u32p), ptr(sc, f32p), ptr(ct, u32p), C.byref(n))
+        if rc != 0:
+            raise RuntimeError(lib().tqo_last_error(self.h).decode())
+        k = min(int(n.value), cap)
+        return [(int(sg[i]), int(dc[i]), float(sc[i]), int(ct[i])) for i in range(k)]
+
     def count_batch(self, batch: QueryBatch):
         """Count collector: alive docs matching each query (src/collector/count_collector.rs)."""
         out = np.zeros(max(batch.nq, 1), dtype=np.uint64)
@@ -260,6 +287,10 @@ def merge_top_k(hits, start, end):
     os_, og, od = np.zeros(max(end, 1), np.float32), np.zeros(max(end, 1), np.uint32), np.zeros(max(end, 1), np.uint32)
     m = lib().tqo_merge_top_k(ptr(sc, f32p), ptr(sg, u32p), ptr(dc, u32p), n, start, end, ptr(os_, f32p), ptr(og, u32p), ptr(od, u32p))
     return list(zip(os_[:m].tolist(), og[:m].tolist(), od[:m].tolist()))
+
+
+PHRASE_TERM_DTYPE = np.dtype([("offset", "<u4"), ("segment_ord", "<u4"), ("field", "<u4"), ("doc_freq", "<u4"),
+                              ("postings_start", "<u8"), ("postings_end", "<u8"), ("positions_start", "<u8"), ("positions_end", "<u8")])
 
 
 # ---- positions codec (src/positions, N3 groundwork) -------------------------------------------------------------

@@ -141,8 +141,32 @@ static Index index_multi_segment() {
   return index;
 }
 
+// phrase_query/mod.rs:24-38 create_index(texts): one TEXT field "text", one doc per text, one commit
+static Index index_from_texts(std::initializer_list<const char*> texts) {
+  SchemaBuilder sb;
+  Field text = sb.add_text_field("text", TEXT);
+  Index index = Index::create_in_ram(sb.build());
+  IndexWriter w = index.writer_for_tests();
+  for (const char* t : texts) w.add_document(doc(text, t));
+  w.commit();
+  return index;
+}
+
 static std::vector<Named> all_indexes() {
   std::vector<Named> v;
+  // the indexes of the reference's phrase tests (phrase_query/mod.rs:41-275): dumped for the oracle's PhraseScorer
+  v.push_back({"phrase_query", index_from_texts({"b b b d c g c", "a b b d c g c", "a b a b c", "c a b a d ga a", "a b c"})});
+  v.push_back({"phrase_simple", index_from_texts({"a b b d c g c", "a b a b c"})});
+  v.push_back({"phrase_score", index_from_texts({"a b c", "a b c a b"})});
+  v.push_back({"phrase_slop_bug", index_from_texts({"asdf asdf Captain Subject Wendy", "Captain"})});
+  v.push_back({"phrase_slop_bug_2a", index_from_texts({"a x b x c", "a a c"})});
+  v.push_back({"phrase_slop_bug_2b", index_from_texts({"a x b x c", "b c c"})});
+  v.push_back({"phrase_slop_repeating", index_from_texts({"wendy subject subject captain", "Captain"})});
+  v.push_back({"phrase_slop_size", index_from_texts({"a b e c", "a e e e c", "a e e e e c"})});
+  v.push_back({"phrase_slop_1", index_from_texts({"a x b c"})});
+  v.push_back({"phrase_slop_2", index_from_texts({"a x b x c"})});
+  v.push_back({"phrase_slop_3", index_from_texts({"a b"})});
+  v.push_back({"phrase_slop_ordering", index_from_texts({"a e b e c", "a e e e e e b e e e e c", "a c b", "a c e b e", "a e c b", "a e b c"})});
   v.push_back({"one_doc_string", index_one_doc_string()});
   v.push_back({"block_len_docs", index_block_len_docs()});
   v.push_back({"term_weight", index_term_weight()});

@@ -192,6 +192,58 @@ def test_mirror_writes_the_reference_position_format(workdir):
                 assert (np.diff(ps) > 0).all() and ps[-1] < 64  # docs of this index have at most 31 + 1 tokens
 
 
+def _phrase(workdir, name, words, slop=0):
+    """PhraseQuery::new(terms) with set_slop(slop) on a dumped index, through the oracle's PhraseScorer
+    (phrase_query/mod.rs:203-218 test_query): [(doc, score)] in doc order."""
+    segs = load(workdir, name)["text"]
+    ix = O.OracleIndex()
+    for s in segs:
+        s.register(ix)
+        ix.register_positions(s.segment_ord, s.field, s.pos)
+    n_docs = sum(s.max_doc for s in segs)
+    avg = f32(f32(sum(s.total_num_tokens for s in segs)) / f32(n_docs))
+    idf_sum = f32(0)
+    terms = []
+    for off, wd in enumerate(words):
+        df = sum(s.terms.get(wd, (0, 0, 0))[0] for s in segs)
+        if df == 0:
+            return []
+        idf_sum = f32(idf_sum + O.bm25_idf(df, n_docs))  # Bm25Weight::for_terms (bm25.rs:95-129)
+        for s in segs:
+            if wd in s.terms:
+                terms.append((off, s.segment_ord, s.field) + s.terms[wd] + s.positions_range[wd])
+    return [(d, sc) for _, d, sc, _ in ix.phrase_search(terms, f32(idf_sum * f32(2.2)), avg, slop=slop)]
+
+
+def test_oracle_phrase_scorer_reproduces_the_reference_phrase_tests(workdir):
+    docs = lambda name, words, slop=0: [d for d, _ in _phrase(workdir, name, words, slop)]  # noqa: E731
+    # phrase_query/mod.rs:41-73
+    assert docs("phrase_query", ["a", "b"]) == [1, 2, 3, 4]
+    assert docs("phrase_query", ["a", "b", "c"]) == [2, 4]
+    assert docs("phrase_query", ["b", "b"]) == [0, 1]
+    assert docs("phrase_query", ["g", "ewrwer"]) == [] and docs("phrase_query", ["g", "a"]) == []
+    assert docs("phrase_simple", ["a", "b"]) == [0, 1]  # :76-91
+    # :163-169
+    h = _phrase(workdir, "phrase_score", ["a", "b"])
+    assert [d for d, _ in h] == [0, 1] and near(h[0][1], 0.40618482) and near(h[1][1], 0.46844664)
+    # slop: :182-201, :220-226
+    assert len(_phrase(workdir, "phrase_slop_bug", ["captain", "wendy"], 1)) == 1
+    assert len(_phrase(workdir, "phrase_slop_bug_2a", ["a", "b", "c"], 2)) == 1
+    assert len(_phrase(workdir, "phrase_slop_bug_2b", ["a", "b", "c"], 2)) == 1
+    assert len(_phrase(workdir, "phrase_slop_repeating", ["wendy", "subject", "captain"], 1)) == 1
+    # :228-235
+    h = _phrase(workdir, "phrase_slop_size", ["a", "c"], 3)
+    assert len(h) == 2 and near(h[0][1], 0.29086056) and near(h[1][1], 0.26706287)
+    # :238-256
+    assert len(_phrase(workdir, "phrase_slop_1", ["a", "b", "c"], 1)) == 1
+    assert len(_phrase(workdir, "phrase_slop_2", ["a", "b", "c"], 1)) == 0
+    assert len(_phrase(workdir, "phrase_slop_3", ["b", "a"], 1)) == 0
+    assert len(_phrase(workdir, "phrase_slop_3", ["b", "a"], 2)) == 1
+    # :259-274
+    h = _phrase(workdir, "phrase_slop_ordering", ["a", "b", "c"], 3)
+    assert near(h[0][1], 0.23091172) and near(h[1][1], 0.27310878) and near(h[3][1], 0.25024384)
+
+
 @pytest.mark.gpu
 def test_cpp_search_tests_on_the_device(workdir):
     r = _run(["--compat", str(workdir)])
