@@ -25,6 +25,32 @@ def test_abi_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """sizeof / offsetof of the C ABI's structs, as a C compiler sees the header, equal the ctypes mirror's
+    (tantivy_b200/_abi.py): a drifted field would silently corrupt every query."""
+    import subprocess
+    from tantivy_b200 import _abi as A
+    src = tmp_path / "abi.c"
+    fields = {"tq_term_seg": A.TermSeg, "tq_query": A.Query, "tq_stats": A.Stats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "tantivy_b200.h")}"', "int main(void) {"]
+    for cname, ct in fields.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, ct in fields.items():
+        assert int(out[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(out[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+    assert A.QUERY_DTYPE.itemsize == C.sizeof(A.Query) and A.TERM_SEG_DTYPE.itemsize == C.sizeof(A.TermSeg)
+    for name in A.QUERY_DTYPE.names:
+        assert A.QUERY_DTYPE.fields[name][1] == getattr(A.Query, name).offset
+
+
 def test_ctx_create_fails_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
