@@ -625,13 +625,20 @@ inline Opstamp IndexWriter::commit() {
     std::vector<std::map<std::string, std::vector<uint32_t>>> pos_deltas(nf);  // per term: first position, then gaps, per posting
     std::vector<std::vector<uint32_t>> num_tokens(nf, std::vector<uint32_t>(seg->max_doc, 0));
     for (DocId d = 0; d < seg->max_doc; ++d) {
+      std::map<uint32_t, uint32_t> end_position;                        // per field: where the next value's positions start
+      std::map<uint32_t, std::map<std::string, uint32_t>> last_pos_of;  // per field: a term's previous position in this doc
       for (auto& fv : pending_[d].doc.field_values()) {
         const FieldEntry& fe = schema.get_field_entry(fv.first);
         if (!fe.options.indexing) continue;
-        std::map<std::string, uint32_t> last_pos;  // within this field value
+        // several values of one field: the next value starts POSITION_GAP = 1 after the previous one's last token
+        // (postings_writer.rs:19,140-163); the fieldnorm counts tokens only
+        const uint32_t start_position = end_position[fv.first.id];
+        uint32_t value_end = start_position, tok_index = 0;
+        std::map<std::string, uint32_t>& last_pos = last_pos_of[fv.first.id];
         for (auto& tok : tokenize(fe.options.indexing->tokenizer, fv.second)) {
           auto& pl = postings[fv.first.id][tok];
-          const uint32_t position = num_tokens[fv.first.id][d];  // token ordinal in the doc's field (positions/mod.rs:1-5)
+          const uint32_t position = start_position + tok_index++;  // token ordinal (positions/mod.rs:1-5)
+          value_end = position + 1;
           const bool again = !pl.empty() && pl.back().first == d;
           if (again) ++pl.back().second; else pl.push_back({d, 1u});
           auto lp = last_pos.find(tok);
@@ -639,6 +646,7 @@ inline Opstamp IndexWriter::commit() {
           last_pos[tok] = position;
           ++num_tokens[fv.first.id][d];
         }
+        end_position[fv.first.id] = value_end + 1;
       }
     }
     for (uint32_t f = 0; f < nf; ++f) {

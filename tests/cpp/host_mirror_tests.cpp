@@ -392,6 +392,21 @@ static void test_host_tokenizer_and_statistics() {
   // "x" + 45 x 'y' is dropped by RemoveLongFilter(40); only ASCII letters are lower-cased (the U-umlaut's bytes stay)
   CHECK((toks == std::vector<std::string>{"hello", "happy", "tax", "payer", "\xC3\x9C" "ber", "z9"}));
   CHECK(tokenize("raw", "Hello World").size() == 1);
+  {  // two values of one field: positions of the second value start POSITION_GAP = 1 after the first (postings_writer.rs:19,162)
+    SchemaBuilder sb;
+    Field f = sb.add_text_field("f", TEXT);
+    Index ix = Index::create_in_ram(sb.build());
+    IndexWriter w = ix.writer_for_tests();
+    w.add_document(Document().add_text(f, "a b").add_text(f, "c a"));
+    w.commit();
+    const FieldSegmentData& fd = ix.segments()[0]->fields[f.id];
+    CHECK(fd.fieldnorms[0] == 4 && fd.total_num_tokens() == 4);
+    const TermInfo a = fd.term_dict.at("a"), c = fd.term_dict.at("c");
+    // "a": positions 0 and 4 -> VInt(0 blocks), VInt(0), VInt(4);  "c": position 3
+    CHECK(a.positions_end - a.positions_start == 3 && fd.positions[a.positions_start] == 0x80 && fd.positions[a.positions_start + 1] == 0x80 &&
+          fd.positions[a.positions_start + 2] == 0x84);
+    CHECK(c.positions_end - c.positions_start == 2 && fd.positions[c.positions_start + 1] == 0x83);
+  }
   Index index = index_term_weight();
   Field left = *index.schema().get_field("left"), large = *index.schema().get_field("large");
   Searcher searcher = index.reader().searcher();
