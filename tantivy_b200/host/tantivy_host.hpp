@@ -26,7 +26,9 @@
 #include <cctype>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <functional>
+#include <iterator>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1127,6 +1129,17 @@ inline Index open_index(const std::string& meta_json, const std::function<std::v
     segments.push_back(seg);
   }
   return Index::from_segments(meta.schema, std::move(segments));
+}
+
+// Index::open_in_dir (src/index/index.rs): meta.json and the segment files of a directory the reference wrote.
+inline Index open_index_in_dir(const std::string& dir) {
+  auto read = [&](const std::string& name) {
+    std::ifstream f(dir + "/" + name, std::ios::binary);
+    if (!f) throw TantivyError(TantivyError::SystemError, "cannot open " + dir + "/" + name);
+    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  };
+  const std::vector<uint8_t> meta = read("meta.json");
+  return open_index(std::string(meta.begin(), meta.end()), read);
 }
 
 }  // namespace files

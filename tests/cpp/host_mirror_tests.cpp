@@ -522,7 +522,7 @@ static std::vector<uint8_t> read_file(const std::string& path) {
 static Index index_from_compat_files(const std::string& dir, const std::string& version) {
   const std::string base = dir + "/" + version + "/";
   const auto meta_bytes = read_file(base + "meta.json");
-  Index index = files::open_index(std::string(meta_bytes.begin(), meta_bytes.end()), [&](const std::string& name) { return read_file(base + name); });
+  Index index = files::open_index_in_dir(dir + "/" + version);  // Index::open_in_dir
   // the `.term` file: its framing and TermInfoStore are read (term ordinal 0 -> TermInfo); the FST that maps term
   // bytes to the ordinal is crate tantivy-fst (N2, not decoded): the dictionary has exactly one term, "dateformat"
   Field label = *index.schema().get_field("label");
@@ -572,6 +572,9 @@ static void test_host_compat_framing(const std::string& dir) {
   bool bad_meta = false;
   try { files::read_meta("{\"segments\": 3}"); } catch (const TantivyError& e) { bad_meta = e.kind() == TantivyError::DataCorruption; }
   CHECK(bad_meta);
+  bool missing = false;
+  try { files::open_index_in_dir(dir + "/no_such_index"); } catch (const TantivyError& e) { missing = e.kind() == TantivyError::SystemError; }
+  CHECK(missing);
 }
 
 static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
