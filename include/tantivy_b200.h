@@ -120,6 +120,16 @@ typedef struct {
    * routes (0 skipped, 1 exhaustive, 2 MaxScore route, 3 no promising doc, 4/5 overflows, 6/7 docs/postings scored). */
   uint64_t or_windows[8];
   uint64_t units_or_strip; /* of units_or: CTAs of the barrier-free strip kernel (k_or_strip); the rest ran k_or / k_or_pipe */
+  /* shared-decode tile engine (k_score_lists + k_tile, csrc/tq_tile.cuh) */
+  float score_ms, tile_ms, theta_ms;  /* device time of k_score_lists / all k_tile launches / the k_theta passes of the batch */
+  uint32_t pad0;
+  uint64_t units_tile;          /* CTAs of k_tile over all its launches */
+  uint64_t tile_groups;         /* query groups evaluated together (one decode-and-score pass each) */
+  uint64_t tile_postings;       /* postings decoded and scored by k_score_lists (every distinct list once) */
+  uint64_t tile_scratch_bytes;  /* HBM scratch of the pair arrays, tile indexes and samples */
+  uint64_t tile_fallbacks;      /* 1 if the run overflowed a tile engine buffer and was repeated on the per-query kernels */
+  uint64_t tile_counters[8];    /* cumulative, with TQ_TILE_COUNTERS=1: (query, tile) pairs seen / skipped / light / heavy,
+                                   essential postings applied, docs completed, docs at or above the threshold */
 } tq_stats;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -176,6 +186,15 @@ int tq_batch_phases(tq_batch*);
 int tq_batch_run_phase(tq_batch*, int phase);
 int tq_batch_thresholds_export_dev(tq_batch*, int64_t* keys_dev);
 int tq_batch_thresholds_import_dev(tq_batch*, const int64_t* keys_dev);
+/* The exact form of that exchange (what one GPU holding all segments computes): between two phases every shard exports,
+ * per query, the k best score keys it holds so far (u32 order-preserving images of f32 scores, k_stride entries per
+ * query, zero padded) -- enqueued on the batch's stream, no host synchronisation; the caller all-gathers the arrays of
+ * all shards ON THAT STREAM (tq_batch_stream; e.g. ncclAllGather, or torch.cuda.ExternalStream) into
+ * [n_shards][nq][k_stride] and hands them back: the k-th best key of the union becomes every shard's threshold
+ * (merge_top_k's bound, sort_key_top_collector.rs:76-95, available before the scoring is over). */
+int tq_batch_stream(tq_batch*, void** cuda_stream_out);
+int tq_batch_topkeys_export_dev(tq_batch*, uint32_t* keys_dev, uint32_t k_stride);
+int tq_batch_thresholds_from_keys_dev(tq_batch*, const uint32_t* gathered_keys_dev, uint32_t n_shards, uint32_t k_stride);
 int tq_batch_fetch(tq_batch*, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord,
                    uint32_t* out_doc, uint32_t* out_count);
 /* Device pointers of the result rows of a finished run: row stride = k_max of the batch. */

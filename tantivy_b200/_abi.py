@@ -91,6 +91,16 @@ class Stats(C.Structure):
         ("bytes_or", C.c_uint64),
         ("or_windows", C.c_uint64 * 8),
         ("units_or_strip", C.c_uint64),
+        ("score_ms", C.c_float),
+        ("tile_ms", C.c_float),
+        ("theta_ms", C.c_float),
+        ("pad0", C.c_uint32),
+        ("units_tile", C.c_uint64),
+        ("tile_groups", C.c_uint64),
+        ("tile_postings", C.c_uint64),
+        ("tile_scratch_bytes", C.c_uint64),
+        ("tile_fallbacks", C.c_uint64),
+        ("tile_counters", C.c_uint64 * 8),
     ]
 
 

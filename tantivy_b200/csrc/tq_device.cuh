@@ -107,6 +107,7 @@ struct BatchParams {
   uint32_t strip_prune;          // 0 disables the essential / non-essential split of k_or_strip
   uint32_t strip_ne_div;         // clauses with >= 1 posting per this many docs may turn non-essential
   uint32_t strip_ne_div2;        // ...and the densest clause of a union without such a clause, under this looser bound
+  uint32_t* ovf;                 // set by k_final when a query was handed more candidates than its region holds (tile engine only), or null
 };
 
 // ---- small helpers ---------------------------------------------------------------------------

@@ -21,7 +21,7 @@
 #include "../../include/tantivy_b200.h"
 #include "bm25_host.hpp"
 #include "segment_writer.hpp"
-#include "tq_kernels.cuh"
+#include "tq_tile.cuh"
 
 using namespace tq;
 
@@ -62,15 +62,6 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct Segment {
-  uint32_t segment_ord, field, max_doc;
-  int record_option;
-  uint8_t* d_idx = nullptr;  // field body incl. the 8-byte header, padded
-  size_t idx_len = 0;
-  uint8_t* d_fieldnorm = nullptr;
-  uint8_t* d_alive = nullptr;
-};
-
 struct ListKey {
   uint32_t segment_ord, field;
   uint64_t postings_start;  // bit 63: the table was built with term frequencies ignored (TQ_TERM_IGNORE_FREQ)
@@ -87,24 +78,35 @@ struct ListKeyHash {
 // individually; dropped with the context).
 struct Arena {
   std::vector<uint8_t*> chunks;
-  size_t chunk_size = 64u << 20, used = 0;
+  size_t chunk_size = 1u << 20, cap = 0, used = 0;  // chunks double up to 64 MiB: a small segment holds a small arena
   uint8_t* alloc(size_t n, cudaError_t* err) {
     n = (n + 255) & ~(size_t)255;
-    if (chunks.empty() || used + n > chunk_size) {
+    if (chunks.empty() || used + n > cap) {
       const size_t sz = std::max(chunk_size, n);
       uint8_t* p = nullptr;
       *err = cudaMalloc(&p, sz);
       if (*err != cudaSuccess) return nullptr;
       chunks.push_back(p);
+      cap = sz;
       used = 0;
-      if (sz > chunk_size) { used = sz; return p; }
+      chunk_size = std::min<size_t>(chunk_size * 2, 64u << 20);
     }
     uint8_t* r = chunks.back() + used;
     used += n;
     *err = cudaSuccess;
     return r;
   }
-  void release() { for (auto* c : chunks) cudaFree(c); chunks.clear(); used = 0; }
+  void release() { for (auto* c : chunks) cudaFree(c); chunks.clear(); used = 0; cap = 0; }
+};
+
+struct Segment {
+  uint32_t segment_ord, field, max_doc;
+  int record_option;
+  uint8_t* d_idx = nullptr;  // field body incl. the 8-byte header, padded
+  size_t idx_len = 0;
+  uint8_t* d_fieldnorm = nullptr;
+  uint8_t* d_alive = nullptr;
+  Arena arena;  // block tables + aligned block copies of this segment's posting lists; freed with the segment
 };
 
 uint32_t env_u32(const char* name, uint32_t def) {
@@ -122,22 +124,48 @@ struct tq_ctx {
   ListDesc* d_lists = nullptr;
   uint32_t lists_cap = 0, n_lists = 0;
   std::unordered_map<ListKey, uint32_t, ListKeyHash> list_cache;
-  Arena arena;
+  std::vector<uint32_t> free_ids;  // list ids of unregistered segments (and of rolled-back builds), reused first
   cudaStream_t build_stream = nullptr;
   PinBuf build_pin;
   DevBuf build_dev;
   std::vector<tq_batch*> pool;
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
-  unsigned long long* d_counters = nullptr;
+  unsigned long long* d_counters = nullptr;  // [0..8) k_or / k_or_strip window routes, [8..16) k_tile diagnostics
+  uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 32, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 24, tile_counters = 0;
+  uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 24, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
 
+constexpr int kTileRounds = 4;  // launches of k_tile per run: the sample launch + three exact ones
+
+// Deep copy of a batch's queries (only kept when the tile engine runs them: an overflowing run is repeated on the per-query kernels).
+struct OwnedQueries {
+  std::vector<tq_query> q;
+  std::vector<tq_term_seg> ts;
+  std::vector<float> w, avg, cache;
+  std::vector<uint8_t> flags;
+};
+
 struct tq_batch {
+  struct Span { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
+  struct TileGroup {
+    TileParams params{};
+    uint32_t n_chunks = 0;
+    uint32_t unit_base[kTileRounds] = {0, 0, 0, 0}, n_units[kTileRounds] = {0, 0, 0, 0};
+    size_t smem = 0;
+  };
   tq_ctx* ctx = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_op[4] = {nullptr, nullptr, nullptr, nullptr};  // after term / and / or / final
+  std::vector<Span> spans;  // per-kind kernel times of the current run (events are created once and reused)
+  size_t n_spans = 0;
+  std::vector<TileGroup> groups;
+  OwnedQueries owned;
+  DevBuf tile_dev;  // pair arrays, tile indexes, samples, flags of the tile engine
+  uint32_t* flags_pin = nullptr;  // [0] tile buffer overflow, [1] candidate region overflow (read back after the last phase)
+  size_t tile_zero_off = 0, tile_zero_bytes = 0, tile_flags_off = 0;
+  bool finalized = false, is_fallback = false, last_round_sampled = false;
   PinBuf pin;      // staged descriptors (H2D source)
   DevBuf dev;      // descriptors on device
   DevBuf scratch;  // qstate + candidates + results
@@ -201,13 +229,27 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->strip_ne_div2 = env_u32("TQ_STRIP_NE_DIV2", 64);
   c->strip_prune = env_u32("TQ_STRIP_PRUNE", 1);  // MaxScore split inside k_or_strip (exact)
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
+  c->tile = env_u32("TQ_TILE", 1);                          // unions take the shared-decode tile engine (tq_tile.cuh); 0 = per-query kernels only
+  c->tile_scratch_mb = env_u32("TQ_TILE_SCRATCH_MB", 24576);  // (doc, score) pairs one batch may materialise
+  c->tile_sample_div = env_u32("TQ_TILE_SAMPLE_DIV", 32);    // share of the tiles in the sample launch (0/1: none)
+  c->tile_round_div1 = env_u32("TQ_TILE_ROUND_DIV1", 8);     // the exact launches end at 1/8, 1/2 and all of a segment's tiles
+  c->tile_round_div2 = env_u32("TQ_TILE_ROUND_DIV2", 2);
+  c->tile_light_max = env_u32("TQ_TILE_LIGHT_MAX", 24);      // essential postings up to which a (query, tile) is one thread's work
+  c->tile_counters = env_u32("TQ_TILE_COUNTERS", 0);         // diagnostics (tile_counters of tq_stats)
+  c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 8192);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
+  c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
+  c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
+  c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 24);          // expected pairs per tile from which a list gets a tile index
+  c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
-  if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 8 * sizeof(unsigned long long));
-  if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 8 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(c->d_lists, 0, (size_t)c->lists_cap * sizeof(ListDesc));
+  if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes());
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem_bytes(kMaxCached));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(kTileMaxPairs, kTileMaxSlots));
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
   *out = c;
   return TQ_OK;
@@ -217,12 +259,13 @@ void tq_batch_destroy_real(tq_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
-  b->pin.release(); b->dev.release(); b->scratch.release(); b->res_pin.release();
+  b->pin.release(); b->dev.release(); b->scratch.release(); b->res_pin.release(); b->tile_dev.release();
+  if (b->flags_pin) cudaFreeHost(b->flags_pin);
   if (b->ev_start) cudaEventDestroy(b->ev_start);
   if (b->ev_k0) cudaEventDestroy(b->ev_k0);
   if (b->ev_k1) cudaEventDestroy(b->ev_k1);
   if (b->ev_end) cudaEventDestroy(b->ev_end);
-  for (auto& e : b->ev_op) if (e) cudaEventDestroy(e);
+  for (auto& sp : b->spans) { if (sp.a) cudaEventDestroy(sp.a); if (sp.b) cudaEventDestroy(sp.b); }
   if (b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -234,8 +277,8 @@ void tq_ctx_destroy(tq_ctx* c) {
   for (auto* b : c->pool) tq_batch_destroy_real(b);
   for (auto& kv : c->segments) {
     cudaFree(kv.second.d_idx); cudaFree(kv.second.d_fieldnorm); cudaFree(kv.second.d_alive);
+    kv.second.arena.release();
   }
-  c->arena.release();
   c->build_pin.release(); c->build_dev.release();
   if (c->build_stream) cudaStreamDestroy(c->build_stream);
   cudaFree(c->d_lists);
@@ -247,11 +290,11 @@ int tq_get_stats(tq_ctx* c, tq_stats* out) {
   if (!c || !out) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
   std::lock_guard<std::mutex> g(c->mu);
   *out = c->stats;
-  out->lists_cached = c->n_lists;
+  out->lists_cached = c->list_cache.size();
   cudaSetDevice(c->device);
-  unsigned long long h[8];
+  unsigned long long h[16];
   if (cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
-    for (int i = 0; i < 8; ++i) out->or_windows[i] = h[i];
+    for (int i = 0; i < 8; ++i) { out->or_windows[i] = h[i]; out->tile_counters[i] = h[8 + i]; }
   return TQ_OK;
 }
 
@@ -269,20 +312,24 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
   Segment s;
   s.segment_ord = segment_ord; s.field = field; s.max_doc = max_doc; s.record_option = record_option; s.idx_len = idx_len;
   const size_t pad = 256;  // decode_block reads one word past a block; the aligned block copy of k_build_tables reads 64 + 8 bytes past the last block
-  TQ_CUDA(cudaMalloc(&s.d_idx, idx_len + pad));
-  TQ_CUDA(cudaMemset(s.d_idx + idx_len, 0, pad));
-  TQ_CUDA(cudaMemcpy(s.d_idx, idx_body, idx_len, cudaMemcpyHostToDevice));
-  if (fieldnorm) {
+  cudaError_t e = cudaMalloc(&s.d_idx, idx_len + pad);
+  if (e == cudaSuccess) e = cudaMemset(s.d_idx + idx_len, 0, pad);
+  if (e == cudaSuccess) e = cudaMemcpy(s.d_idx, idx_body, idx_len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && fieldnorm) {
     const size_t padded = ((size_t)max_doc + kTileDocs - 1) / kTileDocs * kTileDocs + kTileDocs;  // k_or stages whole windows
-    TQ_CUDA(cudaMalloc(&s.d_fieldnorm, padded));
-    TQ_CUDA(cudaMemset(s.d_fieldnorm, 0, padded));
-    TQ_CUDA(cudaMemcpy(s.d_fieldnorm, fieldnorm, max_doc, cudaMemcpyHostToDevice));
+    e = cudaMalloc(&s.d_fieldnorm, padded);
+    if (e == cudaSuccess) e = cudaMemset(s.d_fieldnorm, 0, padded);
+    if (e == cudaSuccess) e = cudaMemcpy(s.d_fieldnorm, fieldnorm, max_doc, cudaMemcpyHostToDevice);
   }
-  if (alive_bitset) {
+  if (e == cudaSuccess && alive_bitset) {
     const size_t alive_padded = ((alive_len + 7) & ~(size_t)7) + 8;  // k_count reads whole 32-bit words
-    TQ_CUDA(cudaMalloc(&s.d_alive, alive_padded));
-    TQ_CUDA(cudaMemset(s.d_alive, 0, alive_padded));
-    TQ_CUDA(cudaMemcpy(s.d_alive, alive_bitset, alive_len, cudaMemcpyHostToDevice));
+    e = cudaMalloc(&s.d_alive, alive_padded);
+    if (e == cudaSuccess) e = cudaMemset(s.d_alive, 0, alive_padded);
+    if (e == cudaSuccess) e = cudaMemcpy(s.d_alive, alive_bitset, alive_len, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {  // nothing of a half-registered segment stays behind
+    cudaFree(s.d_idx); cudaFree(s.d_fieldnorm); cudaFree(s.d_alive);
+    return fail(TQ_ERR_CUDA, std::string("segment upload: ") + cudaGetErrorString(e));
   }
   c->segments[{segment_ord, field}] = s;
   return TQ_OK;
@@ -296,9 +343,10 @@ int tq_segment_unregister(tq_ctx* c, uint32_t segment_ord, uint32_t field) {
   if (it == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "segment/field not registered");
   cudaDeviceSynchronize();
   cudaFree(it->second.d_idx); cudaFree(it->second.d_fieldnorm); cudaFree(it->second.d_alive);
+  it->second.arena.release();  // the segment's block tables and aligned block copies go with it ...
   c->segments.erase(it);
   for (auto li = c->list_cache.begin(); li != c->list_cache.end();)
-    if (li->first.segment_ord == segment_ord && li->first.field == field) li = c->list_cache.erase(li); else ++li;
+    if (li->first.segment_ord == segment_ord && li->first.field == field) { c->free_ids.push_back(li->second); li = c->list_cache.erase(li); } else ++li;  // ... and their ids are reused
   return TQ_OK;
 }
 
@@ -307,13 +355,29 @@ int tq_segment_unregister(tq_ctx* c, uint32_t segment_ord, uint32_t field) {
 // ---- list cache ---------------------------------------------------------------------------------
 namespace {
 
-struct PendingBuild { BuildJob job; ListDesc desc; };
+struct PendingBuild { BuildJob job; ListDesc desc; ListKey key; };
+
+// Takes back every list that was scheduled but not built (an error path of the caller, or a corrupt list): its cache
+// entry would otherwise hand an uninitialised ListDesc to the next query on the same term.  ctx->mu held.
+void rollback_builds(tq_ctx* c, std::vector<PendingBuild>& pending) {
+  for (auto& pb : pending) {
+    auto it = c->list_cache.find(pb.key);
+    if (it != c->list_cache.end() && it->second == pb.job.list_id) c->list_cache.erase(it);
+    c->free_ids.push_back(pb.job.list_id);
+  }
+  pending.clear();
+}
+struct PendingScope {  // pending builds never outlive the call that scheduled them
+  tq_ctx* c;
+  std::vector<PendingBuild>& pending;
+  ~PendingScope() { if (!pending.empty()) rollback_builds(c, pending); }
+};
 
 // Looks a posting list up in the cache or schedules its table build. ctx->mu held.
 int get_list(tq_ctx* c, const tq_term_seg& ts, bool ignore_freq, std::vector<PendingBuild>& pending, uint32_t* list_id, const Segment** seg_out) {
   auto sit = c->segments.find({ts.segment_ord, ts.field});
   if (sit == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "term_seg names a segment/field that is not registered");
-  const Segment& seg = sit->second;
+  Segment& seg = sit->second;
   *seg_out = &seg;
   if (ts.postings_end < ts.postings_start || ts.postings_end + 8 > seg.idx_len) return fail(TQ_ERR_INVALID_ARGUMENT, "postings range outside the field body");
   if (ts.postings_end - ts.postings_start > 0xFFFFFFFFull) return fail(TQ_ERR_UNSUPPORTED, "posting list larger than 4 GiB");
@@ -321,13 +385,13 @@ int get_list(tq_ctx* c, const tq_term_seg& ts, bool ignore_freq, std::vector<Pen
   const ListKey key{ts.segment_ord, ts.field, ts.postings_start | (ignore_freq ? 1ull << 63 : 0ull)};
   auto it = c->list_cache.find(key);
   if (it != c->list_cache.end()) { *list_id = it->second; return TQ_OK; }
-  if (c->n_lists >= c->lists_cap) return fail(TQ_ERR_OOM, "posting-list table cache full (TQ_MAX_LISTS)");
+  if (c->free_ids.empty() && c->n_lists >= c->lists_cap) return fail(TQ_ERR_OOM, "posting-list table cache full (TQ_MAX_LISTS)");
   const uint32_t n_blocks = ts.doc_freq / 128u, tail_n = ts.doc_freq % 128u;
   cudaError_t e;
   const size_t n_last = (size_t)n_blocks + 1, n_blk = (size_t)n_blocks + 1;
   const size_t len = (size_t)(ts.postings_end - ts.postings_start);
   const size_t copy_bytes = ((len + 15) & ~(size_t)15) + 128;  // 16-byte aligned copy of the blocks + slack
-  uint8_t* mem = c->arena.alloc(copy_bytes + n_last * 16 + n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
+  uint8_t* mem = seg.arena.alloc(copy_bytes + n_last * 16 + n_last * 4 + 12 + n_blk * 8 + (size_t)tail_n * 8 + 16, &e);
   if (!mem) return fail(TQ_ERR_OOM, std::string("block table alloc: ") + cudaGetErrorString(e));
   PendingBuild pb;
   ListDesc& d = pb.desc;
@@ -341,37 +405,44 @@ int get_list(tq_ctx* c, const tq_term_seg& ts, bool ignore_freq, std::vector<Pen
   d.tail_tfs = reinterpret_cast<const uint32_t*>(p);
   d.fieldnorm = seg.d_fieldnorm;
   d.n_blocks = n_blocks; d.tail_n = tail_n; d.n_total = n_blocks + (tail_n ? 1u : 0u); d.doc_freq = ts.doc_freq;
+  d.build_status = 1;  // until k_build_tables says otherwise
   pb.job.bytes = seg.d_idx + 8 + ts.postings_start;
   pb.job.len = (uint32_t)(ts.postings_end - ts.postings_start);
   pb.job.doc_freq = ts.doc_freq;
   pb.job.record_option = (uint32_t)seg.record_option | (ignore_freq ? 0x100u : 0u);
-  pb.job.list_id = c->n_lists;
-  *list_id = c->n_lists++;
-  c->list_cache.emplace(key, *list_id);
+  if (!c->free_ids.empty()) { pb.job.list_id = c->free_ids.back(); c->free_ids.pop_back(); }
+  else pb.job.list_id = c->n_lists++;
+  pb.key = key;
+  *list_id = pb.job.list_id;
+  c->list_cache.emplace(key, *list_id);  // later clauses of the same batch share the id; rolled back if the build does not happen
   pending.push_back(pb);
   return TQ_OK;
 }
 
-// Builds every pending table and waits for it (first use of a term only). ctx->mu held.
+// Builds every pending table and waits for it (first use of a term only). ctx->mu held.  On any failure the
+// pending lists are rolled back (no cache entry survives for a list that was not built).
 int flush_builds(tq_ctx* c, std::vector<PendingBuild>& pending, uint64_t* built) {
   if (pending.empty()) return TQ_OK;
   const size_t n = pending.size();
-  // new lists have consecutive ids
-  const uint32_t first_id = pending.front().job.list_id;
-  TQ_CUDA(c->build_pin.ensure(n * (sizeof(ListDesc) + sizeof(BuildJob))));
-  TQ_CUDA(c->build_dev.ensure(n * sizeof(BuildJob)));
+  struct Fail { tq_ctx* c; std::vector<PendingBuild>& p; bool ok = false; ~Fail() { if (!ok) rollback_builds(c, p); } } guard{c, pending};
+  TQ_CUDA(c->build_pin.ensure(n * (sizeof(ListDesc) + sizeof(BuildJob) + 4)));
+  TQ_CUDA(c->build_dev.ensure(n * (sizeof(ListDesc) + sizeof(BuildJob) + 4)));
   ListDesc* hd = reinterpret_cast<ListDesc*>(c->build_pin.p);
   BuildJob* hj = reinterpret_cast<BuildJob*>(c->build_pin.p + n * sizeof(ListDesc));
-  for (size_t i = 0; i < n; ++i) { hd[i] = pending[i].desc; hj[i] = pending[i].job; }
-  TQ_CUDA(cudaMemcpyAsync(c->d_lists + first_id, hd, n * sizeof(ListDesc), cudaMemcpyHostToDevice, c->build_stream));
-  TQ_CUDA(cudaMemcpyAsync(c->build_dev.p, hj, n * sizeof(BuildJob), cudaMemcpyHostToDevice, c->build_stream));
-  k_build_tables<<<(unsigned)n, kThreads, 0, c->build_stream>>>(reinterpret_cast<const BuildJob*>(c->build_dev.p), c->d_lists);
+  uint32_t* hs = reinterpret_cast<uint32_t*>(c->build_pin.p + n * (sizeof(ListDesc) + sizeof(BuildJob)));
+  for (size_t i = 0; i < n; ++i) { hd[i] = pending[i].desc; hj[i] = pending[i].job; hs[i] = 1; }
+  const ListDesc* dd = reinterpret_cast<const ListDesc*>(c->build_dev.p);
+  const BuildJob* dj = reinterpret_cast<const BuildJob*>(c->build_dev.p + n * sizeof(ListDesc));
+  uint32_t* ds = reinterpret_cast<uint32_t*>(c->build_dev.p + n * (sizeof(ListDesc) + sizeof(BuildJob)));
+  TQ_CUDA(cudaMemcpyAsync(c->build_dev.p, c->build_pin.p, n * (sizeof(ListDesc) + sizeof(BuildJob) + 4), cudaMemcpyHostToDevice, c->build_stream));
+  k_build_tables<<<(unsigned)n, kThreads, 0, c->build_stream>>>(dj, dd, c->d_lists, ds);
   TQ_CUDA(cudaGetLastError());
-  TQ_CUDA(cudaMemcpyAsync(hd, c->d_lists + first_id, n * sizeof(ListDesc), cudaMemcpyDeviceToHost, c->build_stream));
+  TQ_CUDA(cudaMemcpyAsync(hs, ds, n * 4, cudaMemcpyDeviceToHost, c->build_stream));
   TQ_CUDA(cudaStreamSynchronize(c->build_stream));
   for (size_t i = 0; i < n; ++i)
-    if (hd[i].build_status != 0) return fail(TQ_ERR_CORRUPT, "posting list bytes are not a valid tantivy posting list");
+    if (hs[i] != 0) return fail(TQ_ERR_CORRUPT, "posting list bytes are not a valid tantivy posting list");
   *built += n;
+  guard.ok = true;
   pending.clear();
   return TQ_OK;
 }
@@ -383,13 +454,38 @@ struct CacheKey {
 }  // namespace
 
 // ---- batches ---------------------------------------------------------------------------------------
+// Kernel time by kind: CUDA events recorded on the batch's stream around every launch (group of launches) of that kind.
+enum SpanKind { SPAN_TERM = 0, SPAN_AND, SPAN_OR, SPAN_FINAL, SPAN_SCORE, SPAN_TILE, SPAN_THETA, SPAN_KINDS };
+
+static int span_begin(tq_batch* b, int kind) {
+  if (b->n_spans == b->spans.size()) {
+    tq_batch::Span s;
+    s.kind = kind;
+    if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return -1;
+    b->spans.push_back(s);
+  }
+  tq_batch::Span& s = b->spans[b->n_spans];
+  s.kind = kind;
+  cudaEventRecord(s.a, b->stream);
+  return (int)b->n_spans++;
+}
+static void span_end(tq_batch* b, int idx) {
+  if (idx >= 0) cudaEventRecord(b->spans[idx].b, b->stream);
+}
+
 static void collect_times(tq_batch* b) {
   float ms = 0;
   if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_k1) == cudaSuccess) b->stats.kernel_ms = ms;
-  if (cudaEventElapsedTime(&ms, b->ev_k0, b->ev_op[0]) == cudaSuccess) b->stats.term_ms = ms;
-  if (cudaEventElapsedTime(&ms, b->ev_op[0], b->ev_op[1]) == cudaSuccess) b->stats.and_ms = ms;
-  if (cudaEventElapsedTime(&ms, b->ev_op[1], b->ev_op[2]) == cudaSuccess) b->stats.or_ms = ms;
-  if (cudaEventElapsedTime(&ms, b->ev_op[2], b->ev_op[3]) == cudaSuccess) b->stats.final_ms = ms;
+  float by_kind[SPAN_KINDS] = {0};
+  for (size_t i = 0; i < b->n_spans; ++i)
+    if (cudaEventElapsedTime(&ms, b->spans[i].a, b->spans[i].b) == cudaSuccess) by_kind[b->spans[i].kind] += ms;
+  b->stats.term_ms = by_kind[SPAN_TERM];
+  b->stats.and_ms = by_kind[SPAN_AND];
+  b->stats.or_ms = by_kind[SPAN_OR];
+  b->stats.final_ms = by_kind[SPAN_FINAL];
+  b->stats.score_ms = by_kind[SPAN_SCORE];
+  b->stats.tile_ms = by_kind[SPAN_TILE];
+  b->stats.theta_ms = by_kind[SPAN_THETA];
 }
 
 static tq_batch* acquire_batch(tq_ctx* c) {
@@ -401,13 +497,121 @@ static tq_batch* acquire_batch(tq_ctx* c) {
   b->ctx = c;
   if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev_start) != cudaSuccess ||
       cudaEventCreate(&b->ev_k0) != cudaSuccess || cudaEventCreate(&b->ev_k1) != cudaSuccess || cudaEventCreate(&b->ev_end) != cudaSuccess ||
-      cudaEventCreate(&b->ev_op[0]) != cudaSuccess || cudaEventCreate(&b->ev_op[1]) != cudaSuccess || cudaEventCreate(&b->ev_op[2]) != cudaSuccess ||
-      cudaEventCreate(&b->ev_op[3]) != cudaSuccess) {
+      cudaMallocHost(&b->flags_pin, 64) != cudaSuccess) {
     tq_batch_destroy_real(b);
     return nullptr;
   }
   return b;
 }
+
+namespace {
+
+// One (query, segment) of the plan: its clauses in evaluation order with their block tables resolved.
+struct SegPlan {
+  uint32_t segment_ord = 0;
+  const Segment* seg = nullptr;
+  std::vector<std::pair<uint32_t, QList>> here;  // (doc_freq, clause)
+  const uint8_t* fn0 = nullptr;
+  bool uniform_fn = true, prunable = false;
+};
+
+// A group of queries that k_tile evaluates together (shared decode, see tq_tile.cuh), while it is being planned.
+struct TileGroupBuild {
+  struct SegB {
+    uint32_t segment_ord = 0, max_doc = 0;
+    const uint8_t* alive = nullptr;
+    std::vector<TSlot> slots;
+    std::unordered_map<uint64_t, std::vector<uint32_t>> slot_of;  // hash of (list, weight, table) -> candidate slots
+    std::vector<TQuery> queries;
+    std::vector<uint16_t> clauses;
+    double dens = 0;  // sum of doc_freq / max_doc over the slots: expected pairs per doc
+  };
+  std::vector<SegB> segs;
+  std::unordered_map<uint32_t, uint32_t> seg_of;  // segment_ord -> index in segs
+  uint64_t pairs = 0;                              // elements of the pair arrays (doc_freq rounded up to 128 per slot)
+};
+
+uint64_t slot_hash(uint32_t list_id, float w, uint32_t cache) {
+  uint32_t wb;
+  memcpy(&wb, &w, 4);
+  return ((uint64_t)list_id << 32 | wb) * 0x9E3779B97F4A7C15ull ^ (uint64_t)cache * 0xC2B2AE3D27D4EB4Full;
+}
+
+// Would the group still satisfy k_tile's limits with this query added?  Returns the number of NEW pair elements, or -1.
+int64_t tile_admit_cost(const TileGroupBuild& g, const std::vector<SegPlan>& plans, uint32_t max_dens_x1000) {
+  int64_t new_pairs = 0;
+  for (const SegPlan& sp : plans) {
+    auto it = g.seg_of.find(sp.segment_ord);
+    const TileGroupBuild::SegB* sb = it == g.seg_of.end() ? nullptr : &g.segs[it->second];
+    if (sb && sb->queries.size() + 1 > kTileMaxQueries) return -1;
+    size_t n_slots = sb ? sb->slots.size() : 0;
+    double dens = sb ? sb->dens : 0.0;
+    for (auto& h : sp.here) {
+      bool found = false;
+      if (sb) {
+        auto f = sb->slot_of.find(slot_hash(h.second.list_id, h.second.weight, h.second.cache_idx));
+        if (f != sb->slot_of.end())
+          for (uint32_t s : f->second) {
+            const TSlot& sl = sb->slots[s];
+            found = found || (sl.list_id == h.second.list_id && memcmp(&sl.weight, &h.second.weight, 4) == 0 && sl.cache_idx == h.second.cache_idx);
+          }
+      }
+      if (!found) {
+        ++n_slots;
+        dens += (double)h.first / std::max(1u, sp.seg->max_doc);
+        new_pairs += ((int64_t)h.first + 127) / 128 * 128;
+      }
+    }
+    if (n_slots > kTileMaxSlots) return -1;
+    if (dens * kTile * 1.5 + 256.0 > (double)kTileMaxPairs || (max_dens_x1000 && dens * 1000.0 > max_dens_x1000)) return -1;
+  }
+  return new_pairs;
+}
+
+void tile_admit(TileGroupBuild& g, uint32_t query, int op, const std::vector<SegPlan>& plans) {
+  for (const SegPlan& sp : plans) {
+    auto it = g.seg_of.find(sp.segment_ord);
+    if (it == g.seg_of.end()) {
+      it = g.seg_of.emplace(sp.segment_ord, (uint32_t)g.segs.size()).first;
+      g.segs.emplace_back();
+      g.segs.back().segment_ord = sp.segment_ord;
+      g.segs.back().max_doc = sp.seg->max_doc;
+      g.segs.back().alive = sp.seg->d_alive;
+    }
+    TileGroupBuild::SegB& sb = g.segs[it->second];
+    TQuery tq;
+    tq.query = query;
+    tq.clause_base = (uint32_t)sb.clauses.size();
+    tq.n_clauses = (uint16_t)sp.here.size();
+    tq.op = (uint8_t)op;
+    tq.flags = sp.prunable ? 1u : 0u;
+    for (auto& h : sp.here) {
+      const uint64_t key = slot_hash(h.second.list_id, h.second.weight, h.second.cache_idx);
+      auto& cands = sb.slot_of[key];
+      uint32_t slot = kNoSlot;
+      for (uint32_t s : cands) {
+        const TSlot& sl = sb.slots[s];
+        if (sl.list_id == h.second.list_id && memcmp(&sl.weight, &h.second.weight, 4) == 0 && sl.cache_idx == h.second.cache_idx) slot = s;
+      }
+      if (slot == kNoSlot) {
+        slot = (uint32_t)sb.slots.size();
+        TSlot sl{};
+        sl.list_id = h.second.list_id; sl.weight = h.second.weight; sl.cache_idx = h.second.cache_idx; sl.doc_freq = h.first;
+        sl.big = kNoSlot;
+        sb.slots.push_back(sl);
+        cands.push_back(slot);
+        sb.dens += (double)h.first / std::max(1u, sp.seg->max_doc);
+        g.pairs += ((uint64_t)h.first + 127) / 128 * 128;
+      }
+      sb.clauses.push_back((uint16_t)slot);
+    }
+    sb.queries.push_back(tq);
+  }
+}
+
+}  // namespace
+
+static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, bool force_legacy, tq_batch** out);
 
 extern "C" {
 
@@ -415,19 +619,33 @@ void tq_batch_destroy(tq_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   cudaStreamSynchronize(b->stream);
+  b->next_phase = 0;
+  b->ran = false;
   std::lock_guard<std::mutex> g(b->ctx->mu);
   b->ctx->pool.push_back(b);  // buffers are recycled by the next batch
 }
 
 int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** out) {
+  return batch_prepare_impl(c, queries, nq, false, out);
+}
+
+}  // extern "C"
+
+static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, bool force_legacy, tq_batch** out) {
   if (!c || !out || (!queries && nq)) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
   TQ_CUDA(cudaSetDevice(c->device));
   tq_batch* b = acquire_batch(c);
   if (!b) return fail(TQ_ERR_CUDA, "stream/event creation failed");
   struct Guard { tq_batch* b; bool ok = false; ~Guard() { if (!ok) tq_batch_destroy(b); } } guard{b};
   b->ran = false;
+  b->finalized = false;
+  b->next_phase = 0;  // a recycled batch may have been abandoned in the middle of a phased run
   b->nq = (uint32_t)nq;
   b->stats = tq_stats{};
+  b->n_spans = 0;
+  b->groups.clear();
+  b->owned = OwnedQueries{};
+  b->is_fallback = force_legacy;
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
@@ -444,9 +662,16 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   uint32_t n_qsegs_op[4] = {0, 0, 0, 0};
   std::vector<char> qseg_sample;  // strip pairs that get a threshold sample pass (MaxScore can then skip their dense clauses)
   uint32_t strip_cached_max = 0, or_max_lists = 0;
+  std::vector<TileGroupBuild> tgroups;
+  std::vector<size_t> q_cands(nq, 0);
+  const bool tile_on = c->tile != 0 && !force_legacy;
+  const uint64_t tile_pair_budget = (uint64_t)c->tile_scratch_mb * (1u << 20) / 8u;
+  uint64_t tile_pairs_total = 0;
   {
     std::lock_guard<std::mutex> g(c->mu);
+    PendingScope pending_scope{c, pending};  // an early error return leaves no half-built list in the cache
     std::vector<const tq_term_seg*> order;
+    std::vector<SegPlan> plans;
     for (size_t qi = 0; qi < nq; ++qi) {
       const tq_query& q = queries[qi];
       if (q.k == 0 || q.k > TQ_MAX_K) return fail(TQ_ERR_INVALID_ARGUMENT, "k must be in 1..TQ_MAX_K");
@@ -478,6 +703,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       }
       // effective shape: an AND / OR of one clause is that clause (boolean_weight.rs:57-68, block_wand_union.rs:154-157)
       const int op = q.n_terms == 1 ? TQ_OP_TERM : q.op;
+      dq[qi].k = q.k;
+      dq[qi].op = (uint32_t)op;
       // group the (clause, segment) lists by segment
       order.clear();
       for (uint32_t i = 0; i < q.n_term_segs; ++i) {
@@ -487,6 +714,8 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
       std::stable_sort(order.begin(), order.end(), [](const tq_term_seg* a, const tq_term_seg* b) {
         return a->segment_ord != b->segment_ord ? a->segment_ord < b->segment_ord : a->term_idx < b->term_idx;
       });
+      plans.clear();
+      uint64_t q_postings = 0;
       for (size_t i = 0; i < order.size();) {
         size_t j = i;
         while (j < order.size() && order[j]->segment_ord == order[i]->segment_ord) ++j;
@@ -496,46 +725,65 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         for (size_t a = i + 1; a < j; ++a) dup |= order[a]->term_idx == order[a - 1]->term_idx;
         if (dup) return fail(TQ_ERR_INVALID_ARGUMENT, "duplicate (term_idx, segment_ord)");
         if (op == TQ_OP_AND && n_here != q.n_terms) { i = j; continue; }  // a clause is absent: empty intersection
+        plans.emplace_back();
+        SegPlan& sp = plans.back();
+        sp.segment_ord = order[i]->segment_ord;
+        for (size_t a = i; a < j; ++a) {
+          uint32_t id;
+          int rc = get_list(c, *order[a], q.term_flags && (q.term_flags[order[a]->term_idx] & TQ_TERM_IGNORE_FREQ), pending, &id, &sp.seg);
+          if (rc != TQ_OK) return rc;
+          if (a == i) sp.fn0 = sp.seg->d_fieldnorm; else sp.uniform_fn &= (sp.seg->d_fieldnorm == sp.fn0);
+          QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
+          sp.here.push_back({order[a]->doc_freq, ql});
+          alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          op_bytes[op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          postings += order[a]->doc_freq;
+          q_postings += order[a]->doc_freq;
+        }
+        if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
+          std::stable_sort(sp.here.begin(), sp.here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
+        if (op == TQ_OP_OR)
+          // Canonical union order = descending Bm25Weight.weight, ties in clause order (the reference's own order is
+          // data dependent, block_wand_union.rs:205-208): the f32 sum is taken in this order, and the clauses with the
+          // smallest score bounds form a suffix, which is what the MaxScore splits of k_tile / k_or_strip need.
+          std::stable_sort(sp.here.begin(), sp.here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.second.weight > b.second.weight; });
+        sp.prunable = op != TQ_OP_TERM;
+        for (auto& h : sp.here) sp.prunable = sp.prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
+        i = j;
+      }
+      // ---- route: the shared-decode tile engine, or the per-query kernels -------------------------------------------------
+      bool on_tile = false;
+      if (tile_on && op == TQ_OP_OR && !plans.empty()) {
+        if (tgroups.empty()) tgroups.emplace_back();
+        int64_t cost = tile_admit_cost(tgroups.back(), plans, c->tile_max_dens_x1000);
+        if (cost < 0 && !(tgroups.back().segs.empty())) {  // the current group is full: open the next one
+          TileGroupBuild fresh;
+          const int64_t cost2 = tile_admit_cost(fresh, plans, c->tile_max_dens_x1000);
+          if (cost2 >= 0 && tile_pairs_total + (uint64_t)cost2 <= tile_pair_budget) { tgroups.emplace_back(); cost = cost2; }
+        }
+        if (cost >= 0 && tile_pairs_total + (uint64_t)cost <= tile_pair_budget) {
+          tile_admit(tgroups.back(), (uint32_t)qi, op, plans);
+          tile_pairs_total += (uint64_t)cost;
+          on_tile = true;
+          // every doc at or above the running threshold is handed over: the sample launch and the k_theta passes keep that
+          // near k; a query that still overflows sends the batch to the per-query kernels (flags[1])
+          const uint32_t cand_floor = c->tile_cand_floor;  // (test hook: tiny regions overflow)
+          q_cands[qi] += (size_t)std::min<uint64_t>(q_postings, std::max<uint64_t>((cand_floor >= 8192 ? 64ull : 1ull) * q.k, cand_floor));
+        }
+      }
+      if (on_tile) continue;
+      for (SegPlan& sp : plans) {
+        auto& here = sp.here;
         QSeg qs;
         memset(&qs, 0, sizeof(qs));
         qs.query = (uint32_t)qi;
         qs.lists_base = (uint32_t)qlists.size();
-        qs.segment_ord = order[i]->segment_ord;
-        uint32_t lead_total = 0;
-        std::vector<std::pair<uint32_t, QList>> here;  // (doc_freq, list)
-        const Segment* seg = nullptr;
-        const uint8_t* fn0 = nullptr;
-        bool uniform_fn = true;
-        for (size_t a = i; a < j; ++a) {
-          uint32_t id;
-          int rc = get_list(c, *order[a], q.term_flags && (q.term_flags[order[a]->term_idx] & TQ_TERM_IGNORE_FREQ), pending, &id, &seg);
-          if (rc != TQ_OK) return rc;
-          if (a == i) fn0 = seg->d_fieldnorm; else uniform_fn &= (seg->d_fieldnorm == fn0);
-          QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
-          here.push_back({order[a]->doc_freq, ql});
-          alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
-          op_bytes[op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
-          postings += order[a]->doc_freq;
-        }
-        qs.max_doc = seg->max_doc;
-        qs.alive = seg->d_alive;
-        qs.fieldnorm = uniform_fn ? fn0 : nullptr;
-        if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
-          std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
-        bool prunable = false;
-        if (op == TQ_OP_AND) {
-          prunable = true;
-          for (auto& h : here) prunable = prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
-        }
-        if (op == TQ_OP_OR) {
-          // Canonical union order = descending Bm25Weight.weight, ties in clause order (the reference's own order is
-          // data dependent, block_wand_union.rs:205-208): the f32 sum is taken in this order, and the clauses with the
-          // smallest score bounds form a suffix, which is what the MaxScore split of k_or_strip needs.
-          std::stable_sort(here.begin(), here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.second.weight > b.second.weight; });
-          prunable = true;
-          for (auto& h : here) prunable = prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
-        }
-        qs.flags = (uniform_fn ? 1u : 0u) | (prunable ? 2u : 0u);
+        qs.segment_ord = sp.segment_ord;
+        qs.max_doc = sp.seg->max_doc;
+        qs.alive = sp.seg->d_alive;
+        qs.fieldnorm = sp.uniform_fn ? sp.fn0 : nullptr;
+        const bool prunable = sp.prunable;
+        qs.flags = (sp.uniform_fn ? 1u : 0u) | (prunable ? 2u : 0u);
         int unit_class = op;
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
           // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
@@ -553,7 +801,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         if (unit_class == TQ_OP_OR) or_max_lists = std::max<uint32_t>(or_max_lists, (uint32_t)here.size());
         for (auto& h : here) qlists.push_back(h.second);
         qs.n_lists = (uint32_t)here.size();
-        lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
+        const uint32_t lead_total = here[0].first / 128u + ((here[0].first % 128u) ? 1u : 0u);
         qsegs.push_back(qs);
         qseg_op.push_back(unit_class);
         {
@@ -563,16 +811,12 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
         }
         qseg_total.push_back(unit_class == 3 ? (qs.max_doc + kWin - 1) / kWin : (op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total));
         ++n_qsegs_op[unit_class];
-        i = j;
       }
-      dq[qi].k = q.k;
-      dq[qi].op = (uint32_t)op;
     }
     // Work units. A unit is one CTA's share of a (query, segment). With few (query, segment) pairs in the
     // batch every pair is cut into many units (latency); with many, units grow so that a CTA's local
     // top-k threshold gets tight and few candidates reach k_final (throughput).
     const uint32_t target_units = env_u32("TQ_TARGET_UNITS", 148u * 4u * 32u);
-    std::vector<size_t> q_cands(nq, 0);
     for (size_t s = 0; s < qsegs.size(); ++s) {
       const int op = qseg_op[s];
       const uint32_t total = qseg_total[s];
@@ -612,6 +856,114 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   }
   if (caches.empty()) caches.resize(256, 0.0f);
 
+  // ---- tile groups: slot order, pair bases, score chunks, tile ranges of the launches -------------------------------------------
+  struct GroupStage {
+    std::vector<TSlot> slots;
+    std::vector<TSeg> segs;
+    std::vector<TQuery> queries;
+    std::vector<uint16_t> clauses;
+    std::vector<TUnit> units[kTileRounds];
+    std::vector<SChunk> chunks;
+    uint32_t max_slots = 1, p_cap = 1024;
+    size_t tix_words = 0;
+  };
+  std::vector<GroupStage> gstage(tgroups.size());
+  uint64_t pair_cursor = 0;
+  size_t tix_total_words = 0;
+  uint64_t tile_postings = 0, tile_units = 0;
+  const uint32_t big_min = c->tile_big_min;
+  for (size_t gi = 0; gi < tgroups.size(); ++gi) {
+    TileGroupBuild& tg = tgroups[gi];
+    GroupStage& gs = gstage[gi];
+    double dens_max = 0;
+    uint64_t tiles_total = 0;
+    uint32_t kmax_g = 1;
+    for (auto& sb : tg.segs) {
+      // dense lists first (they get a tile index and whole warps), then the rest; clause ordinals follow the permutation
+      std::vector<uint32_t> perm(sb.slots.size());
+      for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
+      auto is_big = [&](const TSlot& sl) { return (uint64_t)sl.doc_freq * kTile >= (uint64_t)big_min * std::max(1u, sb.max_doc); };
+      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b2) {
+        const bool ba = is_big(sb.slots[a]), bb = is_big(sb.slots[b2]);
+        if (ba != bb) return ba;
+        return ba ? sb.slots[a].doc_freq > sb.slots[b2].doc_freq : false;
+      });
+      std::vector<uint32_t> new_of(perm.size());
+      for (uint32_t i = 0; i < perm.size(); ++i) new_of[perm[i]] = i;
+      TSeg G{};
+      G.slot_base = (uint32_t)gs.slots.size();
+      G.n_slots = (uint32_t)sb.slots.size();
+      G.query_base = (uint32_t)gs.queries.size();
+      G.n_queries = (uint32_t)sb.queries.size();
+      G.max_doc = sb.max_doc;
+      G.segment_ord = sb.segment_ord;
+      G.n_tiles = (sb.max_doc + kTile - 1) / kTile;
+      G.alive = sb.alive;
+      uint32_t n_big = 0;
+      for (uint32_t i = 0; i < perm.size(); ++i) {
+        TSlot sl = sb.slots[perm[i]];
+        sl.tseg = (uint32_t)gs.segs.size();
+        sl.pair_base = (uint32_t)pair_cursor;
+        if (is_big(sl)) sl.big = n_big++;
+        const uint32_t n_total = sl.doc_freq / 128u + ((sl.doc_freq % 128u) ? 1u : 0u);
+        for (uint32_t b0 = 0; b0 < n_total; b0 += 64u) gs.chunks.push_back(SChunk{(uint32_t)gs.slots.size(), b0, std::min(n_total, b0 + 64u)});
+        pair_cursor += ((uint64_t)sl.doc_freq + 127) / 128 * 128;
+        tile_postings += sl.doc_freq;
+        gs.slots.push_back(sl);
+      }
+      G.n_big = n_big;
+      G.tix = reinterpret_cast<uint32_t*>(tix_total_words + gs.tix_words);  // offset for now, rebased below
+      gs.tix_words += (size_t)(G.n_tiles + 1) * n_big;
+      const uint32_t clause_shift = (uint32_t)gs.clauses.size();
+      for (auto& tq : sb.queries) {
+        TQuery t2 = tq;
+        t2.clause_base += clause_shift;
+        gs.queries.push_back(t2);
+        kmax_g = std::max(kmax_g, dq[tq.query].k);
+      }
+      for (uint16_t cl : sb.clauses) gs.clauses.push_back((uint16_t)new_of[cl]);
+      gs.max_slots = std::max(gs.max_slots, G.n_slots);
+      dens_max = std::max(dens_max, sb.dens);
+      tiles_total += G.n_tiles;
+      gs.segs.push_back(G);
+    }
+    tix_total_words += gs.tix_words;
+    gs.p_cap = (uint32_t)std::min<double>(kTileMaxPairs, std::max(1024.0, dens_max * kTile * 1.5 + 256.0));
+    gs.p_cap = (gs.p_cap + 63u) & ~63u;
+    if (c->tile_pcap_hook) gs.p_cap = c->tile_pcap_hook;  // (test hook: overflowing tiles)
+    // Launches: [0] samples scores on a spread of short tile runs, [1..3] are exact and cover every tile once.
+    const uint32_t target = std::max(1u, c->tile_units);
+    const uint32_t sample_div = std::max<uint32_t>(2u, c->tile_sample_div);
+    // enough sampled tiles for k_max samples to exist: each (query, tile) contributes at most kSamplePerTile
+    const uint64_t want_sample_tiles = std::min<uint64_t>(tiles_total / 2, std::max<uint64_t>(tiles_total / sample_div, (uint64_t)kmax_g / 2u + 8u));
+    for (uint32_t si = 0; si < gs.segs.size(); ++si) {
+      const uint32_t nt = gs.segs[si].n_tiles;
+      if (nt == 0) continue;
+      if (c->tile_sample_div > 1 && nt >= 8 && tiles_total) {
+        const uint32_t seg_sample = (uint32_t)std::max<uint64_t>(1, want_sample_tiles * nt / tiles_total);
+        const uint32_t runs = std::min<uint32_t>(std::min<uint32_t>(8u, nt / 8u), seg_sample);
+        const uint32_t len = std::max<uint32_t>(1u, seg_sample / runs);
+        for (uint32_t r = 0; r < runs; ++r) {
+          const uint32_t start = (uint32_t)(((uint64_t)(2 * r + 1) * nt) / (2 * runs));
+          const uint32_t t0 = std::min(start, nt - 1), t1 = std::min(nt, t0 + len);
+          gs.units[0].push_back(TUnit{si, t0, t1, 0});
+        }
+      }
+      const uint32_t cut1 = nt >= 16 ? nt / std::max(2u, c->tile_round_div1) : 0, cut2 = nt >= 16 ? std::max(cut1, nt / std::max(2u, c->tile_round_div2)) : 0;
+      const uint32_t cuts[4] = {0, cut1, cut2, nt};
+      for (int r = 0; r < 3; ++r) {
+        const uint32_t span = cuts[r + 1] - cuts[r];
+        if (!span) continue;
+        // this launch's share of the target, by its share of all tiles; at least 8 tiles per unit (cursor start-up)
+        const uint64_t round_tiles_all = std::max<uint64_t>(1, (uint64_t)tiles_total * span / nt);
+        const uint32_t per = (uint32_t)std::max<uint64_t>(8, (round_tiles_all + target - 1) / target);
+        for (uint32_t t0 = cuts[r]; t0 < cuts[r + 1]; t0 += per) gs.units[1 + r].push_back(TUnit{si, t0, std::min(cuts[r + 1], t0 + per), 0});
+      }
+    }
+    for (int r = 0; r < kTileRounds; ++r) tile_units += gs.units[r].size();
+  }
+  if (pair_cursor > 0xFFFFFF00ull) return fail(TQ_ERR_UNSUPPORTED, "batch decodes more than 4G postings: split it");
+
   // ---- stage descriptors -------------------------------------------------------------------------
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
   size_t off = 0;
@@ -626,9 +978,44 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
   const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
   const size_t o_qinit = off; off = align(off + std::max<size_t>(nq, 1) * sizeof(QState));  // per-run initial state (threshold keys)
+  struct GroupOff { size_t slots, segs, queries, clauses, units, chunks; };
+  std::vector<GroupOff> goff(gstage.size());
+  for (size_t gi = 0; gi < gstage.size(); ++gi) {
+    GroupStage& gs = gstage[gi];
+    size_t nu = 0;
+    for (int r = 0; r < kTileRounds; ++r) nu += gs.units[r].size();
+    goff[gi].slots = off; off = align(off + gs.slots.size() * sizeof(TSlot));
+    goff[gi].segs = off; off = align(off + gs.segs.size() * sizeof(TSeg));
+    goff[gi].queries = off; off = align(off + gs.queries.size() * sizeof(TQuery));
+    goff[gi].clauses = off; off = align(off + gs.clauses.size() * 2);
+    goff[gi].units = off; off = align(off + nu * sizeof(TUnit));
+    goff[gi].chunks = off; off = align(off + gs.chunks.size() * sizeof(SChunk));
+  }
   b->desc_bytes = off;
   TQ_CUDA(b->pin.ensure(off + 256));
   TQ_CUDA(b->dev.ensure(off + 256));
+
+  // ---- tile scratch: pair arrays | tile indexes | samples | sample counts | flags + counters --------------------------------
+  uint32_t sample_cap = 0;
+  size_t to_docs = 0, to_scores = 0, to_tix = 0, to_samples = 0, to_scount = 0, to_flags = 0, tile_bytes = 0;
+  if (!gstage.empty()) {
+    uint64_t sample_units_tiles = 0;
+    for (auto& gs : gstage) for (auto& u : gs.units[0]) sample_units_tiles += u.t1 - u.t0;
+    sample_cap = (uint32_t)std::min<uint64_t>(1u << 16, std::max<uint64_t>(256, sample_units_tiles * kSamplePerTile));
+    size_t so2 = 0;
+    to_docs = so2; so2 = align(so2 + (size_t)pair_cursor * 4);
+    to_scores = so2; so2 = align(so2 + (size_t)pair_cursor * 4);
+    to_tix = so2; so2 = align(so2 + tix_total_words * 4);
+    to_samples = so2; so2 = align(so2 + (size_t)std::max<size_t>(nq, 1) * sample_cap * 4);
+    to_scount = so2; so2 = align(so2 + std::max<size_t>(nq, 1) * 4);
+    to_flags = so2; so2 = align(so2 + 256);
+    tile_bytes = so2;
+    TQ_CUDA(b->tile_dev.ensure(tile_bytes));
+  }
+  b->tile_zero_off = to_scount;
+  b->tile_zero_bytes = gstage.empty() ? 0 : (to_flags + 256 - to_scount);
+  b->tile_flags_off = to_flags;
+
   memcpy(b->pin.p + o_caches, caches.data(), caches.size() * 4);
   if (!qlists.empty()) memcpy(b->pin.p + o_qlists, qlists.data(), qlists.size() * sizeof(QList));
   if (!qsegs.empty()) memcpy(b->pin.p + o_qsegs, qsegs.data(), qsegs.size() * sizeof(QSeg));
@@ -656,6 +1043,84 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     }
   }
   b->qinit_off = o_qinit;
+  size_t tix_cursor = 0;
+  for (size_t gi = 0; gi < gstage.size(); ++gi) {
+    GroupStage& gs = gstage[gi];
+    tq_batch::TileGroup run;
+    for (auto& G : gs.segs) {  // rebase the tile-index offsets to device addresses
+      const size_t w = reinterpret_cast<size_t>(G.tix);
+      G.tix = reinterpret_cast<uint32_t*>(b->tile_dev.p + to_tix) + w;
+    }
+    tix_cursor += gs.tix_words;
+    if (!gs.slots.empty()) memcpy(b->pin.p + goff[gi].slots, gs.slots.data(), gs.slots.size() * sizeof(TSlot));
+    if (!gs.segs.empty()) memcpy(b->pin.p + goff[gi].segs, gs.segs.data(), gs.segs.size() * sizeof(TSeg));
+    if (!gs.queries.empty()) memcpy(b->pin.p + goff[gi].queries, gs.queries.data(), gs.queries.size() * sizeof(TQuery));
+    if (!gs.clauses.empty()) memcpy(b->pin.p + goff[gi].clauses, gs.clauses.data(), gs.clauses.size() * 2);
+    {
+      TUnit* u = reinterpret_cast<TUnit*>(b->pin.p + goff[gi].units);
+      uint32_t base = 0;
+      for (int r = 0; r < kTileRounds; ++r) {
+        run.unit_base[r] = base;
+        run.n_units[r] = (uint32_t)gs.units[r].size();
+        if (!gs.units[r].empty()) memcpy(u + base, gs.units[r].data(), gs.units[r].size() * sizeof(TUnit));
+        base += (uint32_t)gs.units[r].size();
+      }
+    }
+    if (!gs.chunks.empty()) memcpy(b->pin.p + goff[gi].chunks, gs.chunks.data(), gs.chunks.size() * sizeof(SChunk));
+    run.n_chunks = (uint32_t)gs.chunks.size();
+    TileParams& TP = run.params;
+    TP.slots = reinterpret_cast<const TSlot*>(b->dev.p + goff[gi].slots);
+    TP.segs = reinterpret_cast<const TSeg*>(b->dev.p + goff[gi].segs);
+    TP.queries = reinterpret_cast<const TQuery*>(b->dev.p + goff[gi].queries);
+    TP.clauses = reinterpret_cast<const uint16_t*>(b->dev.p + goff[gi].clauses);
+    TP.units = reinterpret_cast<const TUnit*>(b->dev.p + goff[gi].units);
+    TP.chunks = reinterpret_cast<const SChunk*>(b->dev.p + goff[gi].chunks);
+    TP.p_docs = reinterpret_cast<uint32_t*>(b->tile_dev.p + to_docs);
+    TP.p_scores = reinterpret_cast<float*>(b->tile_dev.p + to_scores);
+    TP.samples = reinterpret_cast<uint32_t*>(b->tile_dev.p + to_samples);
+    TP.sample_count = reinterpret_cast<uint32_t*>(b->tile_dev.p + to_scount);
+    TP.flags = reinterpret_cast<uint32_t*>(b->tile_dev.p + to_flags);
+    TP.counters = c->tile_counters ? c->d_counters + 8 : nullptr;
+    TP.sample_cap = sample_cap;
+    TP.p_cap = gs.p_cap;
+    TP.max_slots = gs.max_slots;
+    TP.light_max = c->tile_light_max;
+    run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots);
+    b->groups.push_back(run);
+  }
+  (void)tix_cursor;
+  if (!b->groups.empty()) {  // the queries are kept: an overflowing run is repeated on the per-query kernels
+    OwnedQueries& o = b->owned;
+    o.q.assign(queries, queries + nq);
+    size_t n_ts = 0, n_t = 0;
+    for (size_t qi = 0; qi < nq; ++qi) { n_ts += queries[qi].n_term_segs; n_t += queries[qi].n_terms; }
+    o.ts.reserve(n_ts); o.w.reserve(n_t); o.avg.reserve(n_t); o.flags.reserve(n_t);
+    size_t n_cache = 0;
+    for (size_t qi = 0; qi < nq; ++qi) if (queries[qi].tf_cache) n_cache += 256 * (size_t)queries[qi].n_terms;
+    o.cache.reserve(n_cache);
+    for (size_t qi = 0; qi < nq; ++qi) {
+      const tq_query& q = queries[qi];
+      tq_query& d = o.q[qi];
+      d.term_segs = reinterpret_cast<const tq_term_seg*>(o.ts.size());  // offsets for now (the vectors do not move again: reserved)
+      o.ts.insert(o.ts.end(), q.term_segs, q.term_segs + q.n_term_segs);
+      d.weight = reinterpret_cast<const float*>(o.w.size());
+      o.w.insert(o.w.end(), q.weight, q.weight + q.n_terms);
+      d.avg_fieldnorm = nullptr;
+      if (q.avg_fieldnorm) { d.avg_fieldnorm = reinterpret_cast<const float*>(o.avg.size() + 1); o.avg.insert(o.avg.end(), q.avg_fieldnorm, q.avg_fieldnorm + q.n_terms); }
+      d.tf_cache = nullptr;
+      if (q.tf_cache) { d.tf_cache = reinterpret_cast<const float*>(o.cache.size() + 1); o.cache.insert(o.cache.end(), q.tf_cache, q.tf_cache + 256 * (size_t)q.n_terms); }
+      d.term_flags = nullptr;
+      if (q.term_flags) { d.term_flags = reinterpret_cast<const uint8_t*>(o.flags.size() + 1); o.flags.insert(o.flags.end(), q.term_flags, q.term_flags + q.n_terms); }
+    }
+    for (size_t qi = 0; qi < nq; ++qi) {
+      tq_query& d = o.q[qi];
+      d.term_segs = o.ts.data() + reinterpret_cast<size_t>(d.term_segs);
+      d.weight = o.w.data() + reinterpret_cast<size_t>(d.weight);
+      if (d.avg_fieldnorm) d.avg_fieldnorm = o.avg.data() + (reinterpret_cast<size_t>(d.avg_fieldnorm) - 1);
+      if (d.tf_cache) d.tf_cache = o.cache.data() + (reinterpret_cast<size_t>(d.tf_cache) - 1);
+      if (d.term_flags) d.term_flags = o.flags.data() + (reinterpret_cast<size_t>(d.term_flags) - 1);
+    }
+  }
 
   // ---- scratch: qstate | candidates | results ------------------------------------------------------
   b->kmax = kmax;
@@ -693,6 +1158,7 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
   P.strip_prune = c->strip_prune;
   P.strip_ne_div = c->strip_ne_div;
   P.strip_ne_div2 = c->strip_ne_div2;
+  P.ovf = b->groups.empty() ? nullptr : reinterpret_cast<uint32_t*>(b->tile_dev.p + to_flags) + 1;
 
   TQ_CUDA(cudaEventRecord(b->ev_start, b->stream));
   TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, b->desc_bytes, cudaMemcpyHostToDevice, b->stream));
@@ -702,61 +1168,141 @@ int tq_batch_prepare(tq_ctx* c, const tq_query* queries, size_t nq, tq_batch** o
     TQ_CUDA(cudaGetLastError());
   }
   b->stats.lists_built = built;
-  b->stats.units = n_units_total;
+  b->stats.units = n_units_total + tile_units;
   b->stats.h2d_bytes = b->desc_bytes;
   b->stats.algorithmic_bytes = alg_bytes;
   b->stats.postings = postings;
   b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size(); b->stats.units_or_strip = units[3].size() + units[4].size() + units[5].size() + units[6].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
+  b->stats.units_tile = tile_units;
+  b->stats.tile_groups = b->groups.size();
+  b->stats.tile_postings = tile_postings;
+  b->stats.tile_scratch_bytes = tile_bytes;
+  {
+    // SURVEY.md §8(d) for k_score_lists: every distinct list is read once (its packed blocks + one fieldnorm byte per posting)
+    // and written once as 8-byte (doc, score) pairs
+    uint64_t packed = 0;
+    (void)packed;
+  }
   guard.ok = true;
   *out = b;
   return TQ_OK;
 }
 
-// Phases of a run: 0 = term / AND / window-union kernels + the unions' first threshold round, 1 and 2 = the second
-// and third threshold rounds, 3 = the unions' main launch + k_final.  Sharded callers exchange thresholds in between.
+// Phases of a run: 0 = term / AND / window-union kernels + the decode-and-score pass and the sample launch of the tile engine
+// + the strips' first threshold round, 1 and 2 = the next (exact) tile launches / threshold rounds, 3 = the last tile launch,
+// the strips' main launch and k_final.  Every phase but the last ends with the per-query thresholds refreshed (k_theta).
+// Sharded callers exchange keys in between.
 constexpr int kPhases = 4;
+
+static int launch_tile_round(tq_batch* b, int r, uint64_t* launches) {
+  bool any = false;
+  for (auto& g : b->groups) any = any || g.n_units[r];
+  if (!any) return TQ_OK;
+  const int sp = span_begin(b, SPAN_TILE);
+  for (auto& g : b->groups) {
+    if (!g.n_units[r]) continue;
+    k_tile<<<g.n_units[r], kTileThreads, g.smem, b->stream>>>(b->params, g.params, g.unit_base[r], r == 0 ? 1u : 0u);
+    ++*launches;
+  }
+  span_end(b, sp);
+  TQ_CUDA(cudaGetLastError());
+  return TQ_OK;
+}
 
 static int run_phase(tq_batch* b, int phase) {
   TQ_CUDA(cudaSetDevice(b->ctx->device));
   const BatchParams& P = b->params;
   uint64_t launches = 0;
   if (phase != b->next_phase) return fail(TQ_ERR_INVALID_ARGUMENT, "phases run in order, each once per run");
+  const bool tiles = !b->groups.empty();
   if (phase == 0) {
+    b->n_spans = 0;
+    b->finalized = false;
     TQ_CUDA(cudaMemcpyAsync(P.qstate, b->dev.p + b->qinit_off, std::max<size_t>(b->nq, 1) * sizeof(QState), cudaMemcpyDeviceToDevice, b->stream));
+    if (tiles) TQ_CUDA(cudaMemsetAsync(b->tile_dev.p + b->tile_zero_off, 0, b->tile_zero_bytes, b->stream));
     TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
-    if (b->n_units[TQ_OP_TERM]) { k_term<<<b->n_units[TQ_OP_TERM], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_TERM]); ++launches; }
-    TQ_CUDA(cudaEventRecord(b->ev_op[0], b->stream));
-    if (b->n_units[TQ_OP_AND]) { k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches; }
-    TQ_CUDA(cudaEventRecord(b->ev_op[1], b->stream));
+    if (b->n_units[TQ_OP_TERM]) {
+      const int sp = span_begin(b, SPAN_TERM);
+      k_term<<<b->n_units[TQ_OP_TERM], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_TERM]); ++launches;
+      span_end(b, sp);
+    }
+    if (b->n_units[TQ_OP_AND]) {
+      const int sp = span_begin(b, SPAN_AND);
+      k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches;
+      span_end(b, sp);
+    }
     if (b->n_units[TQ_OP_OR]) {
+      const int sp = span_begin(b, SPAN_OR);
       // window unions: the TMA/mbarrier pipeline when every union has few enough clauses for its tables, else the plain kernel
       if (b->ctx->or_pipe && b->or_max_lists <= kPipeMaxLists && !b->ctx->or_prune)
         k_or_pipe<<<b->n_units[TQ_OP_OR], kPipeThreads, pipe_smem_bytes(), b->stream>>>(P, b->unit_base[TQ_OP_OR]);
       else
         k_or<<<b->n_units[TQ_OP_OR], kThreads, kOrDynSmem, b->stream>>>(P, b->unit_base[TQ_OP_OR]);
       ++launches;
+      span_end(b, sp);
+    }
+    if (tiles) {  // K1 + K2 once for every distinct list of the batch
+      const int sp = span_begin(b, SPAN_SCORE);
+      for (auto& g : b->groups)
+        if (g.n_chunks) { k_score_lists<<<g.n_chunks, kThreads, 0, b->stream>>>(P, g.params, 0u); ++launches; }
+      span_end(b, sp);
+      TQ_CUDA(cudaGetLastError());
     }
     b->stats.kernel_launches = 0;
   }
-  if (phase < kPhases - 1) {  // threshold round `phase`: its windows, then the exact k-th best so far per query
+  if (phase < kPhases - 1) {
+    // tile engine: phase 0 = sample launch, then exact launches; strips: threshold round `phase`
+    if (tiles) {
+      const int rc = launch_tile_round(b, phase, &launches);
+      if (rc != TQ_OK) return rc;
+      if (phase == 0 && (kTileRounds == kPhases + 0)) {}  // (rounds 1..3 belong to phases 1..3)
+    }
     const int r = 4 + phase;
     if (b->n_units[r]) {
+      const int sp = span_begin(b, SPAN_OR);
       k_or_strip<<<b->n_units[r], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[r], b->strip_cached_max);
+      ++launches;
+      span_end(b, sp);
+    }
+    bool tile_round = false;
+    for (auto& g : b->groups) tile_round = tile_round || g.n_units[phase];
+    if ((b->n_units[r] || (tile_round && phase > 0)) && b->nq) {
+      const int sp = span_begin(b, SPAN_THETA);
       k_theta<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P);
-      launches += 2;
+      ++launches;
+      span_end(b, sp);
+    }
+    if (tile_round && phase == 0 && b->nq) {
+      const int sp = span_begin(b, SPAN_THETA);
+      const TileParams& TP = b->groups[0].params;
+      k_theta_samples<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(P, TP.samples, TP.sample_count, TP.sample_cap);
+      ++launches;
+      span_end(b, sp);
     }
     TQ_CUDA(cudaGetLastError());
     b->stats.kernel_launches += launches;
     b->next_phase = phase + 1;
+    b->last_round_sampled = tile_round && phase == 0;
     return TQ_OK;
   }
-  if (b->n_units[3]) { k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches; }
+  if (tiles) {
+    const int rc = launch_tile_round(b, kTileRounds - 1, &launches);
+    if (rc != TQ_OK) return rc;
+  }
+  if (b->n_units[3]) {
+    const int sp = span_begin(b, SPAN_OR);
+    k_or_strip<<<b->n_units[3], kStripThreads, strip_smem_bytes(b->strip_cached_max), b->stream>>>(P, b->unit_base[3], b->strip_cached_max); ++launches;
+    span_end(b, sp);
+  }
   TQ_CUDA(cudaGetLastError());
-  TQ_CUDA(cudaEventRecord(b->ev_op[2], b->stream));
-  if (b->nq) { k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches; }
+  if (b->nq) {
+    const int sp = span_begin(b, SPAN_FINAL);
+    k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches;
+    span_end(b, sp);
+  }
   TQ_CUDA(cudaGetLastError());
-  TQ_CUDA(cudaEventRecord(b->ev_op[3], b->stream));
+  if (tiles) TQ_CUDA(cudaMemcpyAsync(b->flags_pin, b->tile_dev.p + b->tile_flags_off, 16, cudaMemcpyDeviceToHost, b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_k1, b->stream));
   b->stats.kernel_launches += launches;
   b->next_phase = 0;
@@ -764,11 +1310,40 @@ static int run_phase(tq_batch* b, int phase) {
   return TQ_OK;
 }
 
+// After the last phase: wait for the stream; a run whose tile engine overflowed (a tile with more pairs than its buffer, or a
+// query with more candidates than its region) is repeated on the per-query kernels and its rows replace ours.  Exactness
+// never depends on the fast path's capacity guesses.
+static int finalize_run(tq_batch* b) {
+  if (!b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  if (b->finalized) return TQ_OK;
+  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  b->finalized = true;
+  if (b->groups.empty() || b->is_fallback) return TQ_OK;
+  if (b->flags_pin[0] == 0 && b->flags_pin[1] == 0) return TQ_OK;
+  tq_batch* fb = nullptr;
+  int rc = batch_prepare_impl(b->ctx, b->owned.q.data(), b->owned.q.size(), true, &fb);
+  if (rc != TQ_OK) return rc;
+  rc = tq_batch_run(fb);
+  if (rc == TQ_OK) {
+    cudaError_t e = cudaStreamSynchronize(fb->stream);
+    if (e == cudaSuccess && fb->res_bytes == b->res_bytes)
+      e = cudaMemcpyAsync(b->scratch.p + b->res_off, fb->scratch.p + fb->res_off, b->res_bytes, cudaMemcpyDeviceToDevice, b->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess) rc = fail(TQ_ERR_CUDA, cudaGetErrorString(e));
+    else if (fb->res_bytes != b->res_bytes) rc = fail(TQ_ERR_CUDA, "fallback batch layout differs");
+  }
+  tq_batch_destroy(fb);
+  b->stats.tile_fallbacks = 1;
+  return rc;
+}
+
+extern "C" {
+
 int tq_batch_run(tq_batch* b) {
   if (!b) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
   for (int p = b->next_phase; p < kPhases; ++p) {
     const int rc = run_phase(b, p);
-    if (rc != TQ_OK) return rc;
+    if (rc != TQ_OK) { b->next_phase = 0; return rc; }
   }
   return TQ_OK;
 }
@@ -777,7 +1352,15 @@ int tq_batch_phases(tq_batch* b) { return b ? kPhases : 0; }
 
 int tq_batch_run_phase(tq_batch* b, int phase) {
   if (!b || phase < 0 || phase >= kPhases) return fail(TQ_ERR_INVALID_ARGUMENT, "batch / phase");
-  return run_phase(b, phase);
+  const int rc = run_phase(b, phase);
+  if (rc != TQ_OK && rc != TQ_ERR_INVALID_ARGUMENT) b->next_phase = 0;  // a failed run starts over
+  return rc;
+}
+
+int tq_batch_stream(tq_batch* b, void** stream_out) {
+  if (!b || !stream_out) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  *stream_out = (void*)b->stream;
+  return TQ_OK;
 }
 
 int tq_batch_thresholds_export_dev(tq_batch* b, int64_t* keys_dev) {
@@ -797,11 +1380,37 @@ int tq_batch_thresholds_import_dev(tq_batch* b, const int64_t* keys_dev) {
   return TQ_OK;
 }
 
+int tq_batch_topkeys_export_dev(tq_batch* b, uint32_t* keys_dev, uint32_t k_stride) {
+  if (!b || !keys_dev || !k_stride || b->next_phase == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "export needs a batch between two phases of a run");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  if (b->nq) {
+    const bool from_samples = b->last_round_sampled && !b->groups.empty();
+    const TileParams* TP = b->groups.empty() ? nullptr : &b->groups[0].params;
+    k_topkeys_export<<<(unsigned)b->nq, kThreads, 0, b->stream>>>(b->params, TP ? TP->samples : nullptr, TP ? TP->sample_count : nullptr,
+                                                                  TP ? TP->sample_cap : 0u, from_samples ? 1u : 0u, keys_dev, k_stride);
+  }
+  TQ_CUDA(cudaGetLastError());
+  return TQ_OK;  // enqueued on the batch's stream (tq_batch_stream): the caller's collective must be ordered behind it
+}
+
+int tq_batch_thresholds_from_keys_dev(tq_batch* b, const uint32_t* gathered_dev, uint32_t n_shards, uint32_t k_stride) {
+  if (!b || !gathered_dev || !n_shards || !k_stride || b->next_phase == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "import needs a batch between two phases of a run");
+  if ((size_t)n_shards * k_stride * 4 > 200u * 1024u) return fail(TQ_ERR_UNSUPPORTED, "n_shards * k_stride too large for one CTA");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  if (b->nq) {
+    const size_t smem = (size_t)n_shards * k_stride * 4;
+    if (smem > 48u * 1024u) TQ_CUDA(cudaFuncSetAttribute(k_theta_from_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_theta_from_keys<<<(unsigned)b->nq, kThreads, smem, b->stream>>>(b->params, gathered_dev, n_shards, (uint32_t)b->nq, k_stride);
+  }
+  TQ_CUDA(cudaGetLastError());
+  return TQ_OK;
+}
+
 int tq_batch_results_dev(tq_batch* b, const float** scores_dev, const uint32_t** segment_ord_dev, const uint32_t** doc_dev,
                          const uint32_t** count_dev, uint32_t* stride) {
   if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
   TQ_CUDA(cudaSetDevice(b->ctx->device));
-  TQ_CUDA(cudaStreamSynchronize(b->stream));
+  { const int rc = finalize_run(b); if (rc != TQ_OK) return rc; }
   if (scores_dev) *scores_dev = b->params.res_scores;
   if (segment_ord_dev) *segment_ord_dev = b->params.res_segs;
   if (doc_dev) *doc_dev = b->params.res_docs;
@@ -817,6 +1426,7 @@ int tq_batch_results_copy_dev(tq_batch* b, float* scores_dev, uint32_t* segment_
   if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
   if (!scores_dev || !segment_ord_dev || !doc_dev || !count_dev) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
   TQ_CUDA(cudaSetDevice(b->ctx->device));
+  { const int rc = finalize_run(b); if (rc != TQ_OK) return rc; }
   const size_t rows = (size_t)b->nq * b->kmax * 4;
   TQ_CUDA(cudaMemcpyAsync(scores_dev, b->params.res_scores, rows, cudaMemcpyDeviceToDevice, b->stream));
   TQ_CUDA(cudaMemcpyAsync(segment_ord_dev, b->params.res_segs, rows, cudaMemcpyDeviceToDevice, b->stream));
@@ -833,6 +1443,7 @@ int tq_batch_fetch(tq_batch* b, uint32_t out_stride, float* out_scores, uint32_t
   if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
   if (!out_scores || !out_segment_ord || !out_doc || !out_count) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
   TQ_CUDA(cudaSetDevice(b->ctx->device));
+  if (!b->groups.empty()) { const int rc = finalize_run(b); if (rc != TQ_OK) return rc; }  // (a run without tile groups cannot overflow: one sync below)
   TQ_CUDA(cudaMemcpyAsync(b->res_pin.p, b->scratch.p + b->res_off, b->res_bytes, cudaMemcpyDeviceToHost, b->stream));
   TQ_CUDA(cudaEventRecord(b->ev_end, b->stream));
   TQ_CUDA(cudaStreamSynchronize(b->stream));
@@ -898,6 +1509,7 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
   {
     std::lock_guard<std::mutex> g(c->mu);
     std::vector<PendingBuild> pending;
+    PendingScope pending_scope{c, pending};
     uint64_t built = 0;
     std::vector<const tq_term_seg*> order;
     for (size_t qi = 0; qi < nq; ++qi) {
@@ -979,6 +1591,7 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
 static int resolve_single(tq_ctx* c, const tq_term_seg* list, uint32_t* id) {
   std::lock_guard<std::mutex> g(c->mu);
   std::vector<PendingBuild> pending;
+  PendingScope pending_scope{c, pending};
   const Segment* seg;
   uint64_t built = 0;
   int rc = get_list(c, *list, false, pending, id, &seg);
@@ -1043,6 +1656,7 @@ uint8_t tq_fieldnorm_to_id(uint32_t fieldnorm) { return fieldnorm_to_id(fieldnor
 
 // ---- segment writer ----------------------------------------------------------------------------------
 struct tq_field_writer {
+  uint32_t max_doc = 0;
   std::vector<uint8_t> fieldnorm_ids;
   FieldPostingsWriter* w = nullptr;
 };
@@ -1050,6 +1664,7 @@ struct tq_field_writer {
 int tq_field_writer_create(int record_option, uint64_t total_num_tokens, const uint8_t* fieldnorm_ids, uint32_t max_doc, tq_field_writer** out) {
   if (!out || record_option < 0 || record_option > 2) return fail(TQ_ERR_INVALID_ARGUMENT, "args");
   auto* fw = new tq_field_writer();
+  fw->max_doc = max_doc;
   if (fieldnorm_ids) fw->fieldnorm_ids.assign(fieldnorm_ids, fieldnorm_ids + max_doc);
   fw->w = new FieldPostingsWriter(record_option, total_num_tokens, fieldnorm_ids ? fw->fieldnorm_ids.data() : nullptr, max_doc);
   *out = fw;
@@ -1060,7 +1675,7 @@ int tq_field_writer_add_term(tq_field_writer* fw, const uint32_t* docs, const ui
   if (!fw || (!docs && doc_freq)) return fail(TQ_ERR_INVALID_ARGUMENT, "args");
   for (uint32_t i = 0; i < doc_freq; ++i) {
     if (i && docs[i] <= docs[i - 1]) return fail(TQ_ERR_INVALID_ARGUMENT, "docs must be strictly ascending");
-    if (docs[i] >= TQ_TERMINATED) return fail(TQ_ERR_INVALID_ARGUMENT, "doc id out of range");
+    if (docs[i] >= TQ_TERMINATED || docs[i] >= fw->max_doc) return fail(TQ_ERR_INVALID_ARGUMENT, "doc id out of range (>= max_doc)");
     if (tfs && tfs[i] == 0) return fail(TQ_ERR_INVALID_ARGUMENT, "term frequency 0");
   }
   const TermInfoOut ti = fw->w->add_term(docs, tfs, doc_freq);

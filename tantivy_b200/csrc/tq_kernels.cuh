@@ -28,9 +28,12 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
 }
 
 // One CTA per posting list.  Fills last_doc / blk / tail arrays of its ListDesc.
-__global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __restrict__ jobs, ListDesc* __restrict__ lists) {
+__global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __restrict__ jobs, const ListDesc* __restrict__ init,
+                                                           ListDesc* __restrict__ lists, uint32_t* __restrict__ status_out) {
   const BuildJob J = jobs[blockIdx.x];
   ListDesc& L = lists[J.list_id];
+  if (threadIdx.x == 0) L = init[blockIdx.x];  // (list ids are recycled: the slot may hold an unregistered segment's table)
+  __syncthreads();
   uint32_t* last_doc = const_cast<uint32_t*>(L.last_doc);
   uint2* blk = const_cast<uint2*>(L.blk);
   uint4* tab4 = const_cast<uint4*>(L.tab4);
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) k_build_tables(const BuildJob* __res
     }
     L.has_freq = rec != 5u && !(J.record_option & 0x100u);  // SkipFreq: the tf bits stay in the block sizes, nobody reads them
     L.build_status = status;
+    status_out[blockIdx.x] = status;
   }
   // 16-byte aligned copy of the bit-packed blocks (L.blocks was pre-set by the host to an arena region of
   // >= len + 64 bytes): posting lists start at arbitrary byte offsets inside the .idx body; the copy lets
@@ -1633,6 +1637,7 @@ __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
   const uint32_t q = blockIdx.x;
   const DQuery Q = P.queries[q];
   const uint32_t C = min(P.qstate[q].cand_count, Q.cand_cap);
+  if (threadIdx.x == 0 && P.ovf && P.qstate[q].cand_count > Q.cand_cap) atomicExch(P.ovf, 1u);  // candidates were dropped: the host repeats the run
   const Cand* cands = P.cands + Q.cand_base;
   uint32_t have = 0;
   if (C <= kCap) {

@@ -1,0 +1,548 @@
+// The shared-decode query engine: every posting list a batch touches is decoded and scored ONCE per batch, and all
+// queries of the batch are evaluated against doc-id tiles of those scored postings held in shared memory.
+//
+// Why: a (term, doc) BM25 score = Bm25Weight.weight * tf/(tf + norm[fieldnorm_id]) (src/query/bm25.rs:158-175) does not
+// depend on the query that asks for it -- the weight belongs to the term.  A 512-query batch of 5-term unions over a
+// 100M-doc index asks for 14 G scored postings, but the index only holds 0.3 G: the per-query kernels (k_or_strip ...)
+// decode every list ~47 times per step.  Here:
+//
+//   k_score_lists   K1 + K2 of SURVEY.md §2, once per distinct (list, weight, tf-norm table) of the batch: one warp per
+//                   128-doc block, BitPacker4x unpack + strict-delta prefix sum (BlockDecoder::uncompress_block_sorted /
+//                   _unsorted, src/postings/compression/mod.rs:105-150), fieldnorm gather (src/fieldnorm/reader.rs:128),
+//                   BM25 -> (doc, score) pairs streamed to HBM scratch with 16-byte stores.
+//   k_tile          K3/K4/K5/K6 for all queries of the batch at once: a CTA walks a range of 1024-doc tiles; per tile it
+//                   stages the pairs of every list into shared memory (sorted by doc inside a list), then evaluates the
+//                   queries against them:
+//                     * MaxScore with per-tile maxima (the block-max idea of block_wand_union.rs:16-43,171-177 at tile
+//                       granularity, with maxima computed from the scores themselves, so they are exact under the
+//                       searcher's global statistics -- the stored block-max pair is only exact under the segment's own
+//                       average fieldnorm, term_scorer.rs:58-70): clauses are kept in the canonical summation order
+//                       (descending weight); the longest suffix whose tile maxima add up to less than the query's
+//                       threshold is non-essential and is only LOOKED UP for docs that the essential clauses make
+//                       promising;
+//                     * light (query, tile) pairs -- few essential postings -- are evaluated by one thread per query
+//                       (a scalar document-at-a-time merge over shared memory), heavy ones by one warp per query over a
+//                       warp-private window of f32 score slots (BufferedUnionScorer's shape, union/buffered_union.rs:63-86);
+//                     * f32 sums are taken clause by clause in the canonical order, so pruned and exhaustive evaluation
+//                       give bit-identical scores;
+//                     * survivors (score key >= the query's threshold) go to the query's candidate region, k_final
+//                       (TopNHeap / merge_fruits) selects exactly.
+//   thresholds      a first launch over 1/32 of the tiles only SAMPLES scores (the best few per (query, tile)); the k-th best
+//                   sample is a valid lower bound of the final k-th score (k_theta_samples).  The exact launches follow,
+//                   each ending in k_theta (exact k-th best candidate so far), so most tiles are visited under a
+//                   near-final threshold.  Sampled tiles are visited again by the exact launches: nothing is pushed twice.
+//
+// Everything is bit-exact w.r.t. the oracle's exhaustive mode: same per-posting IEEE operations, same summation order.
+#pragma once
+#include "tq_kernels.cuh"
+
+namespace tq {
+
+constexpr uint32_t kTile = 1024;            // docs per tile
+constexpr uint32_t kTileThreads = 256;
+constexpr uint32_t kTileWarps = kTileThreads / 32;
+constexpr uint32_t kTileMaxQueries = 1024;  // (query, segment) pairs of one group in one segment
+constexpr uint32_t kTileMaxSlots = 4096;    // distinct scored lists of one group in one segment
+constexpr uint32_t kTileMaxPairs = 12288;   // pairs of one tile held in shared memory (start | len are 16-bit fields)
+constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
+constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+
+struct TSlot {  // one distinct scored list of a group: (posting list, Bm25Weight.weight, tf-norm table)
+  uint32_t list_id;
+  float weight;
+  uint32_t cache_idx;
+  uint32_t doc_freq;
+  uint32_t pair_base;  // first element of this list's pairs in p_docs / p_scores (multiple of 128)
+  uint32_t big;        // column in the segment's tile index, kNoSlot for small lists
+  uint32_t tseg;
+  uint32_t pad;
+};
+struct TSeg {  // one segment of a group
+  uint32_t slot_base, n_slots, n_big;  // slots [0, n_big) have a tile index and are staged by whole warps
+  uint32_t query_base, n_queries;
+  uint32_t max_doc, segment_ord, n_tiles;
+  const uint8_t* alive;
+  uint32_t* tix;  // [(n_tiles + 1)][n_big]: index of the list's first pair with doc >= tile * kTile (written by k_score_lists)
+};
+struct TQuery {  // one (query, segment): what Collector::collect_segment sees
+  uint32_t query;
+  uint32_t clause_base;  // into TileParams::clauses: slot ordinals (local to the segment) in canonical summation order
+  uint16_t n_clauses;
+  uint8_t op;
+  uint8_t flags;  // bit 0: prunable (every weight finite and >= 0)
+};
+struct TUnit { uint32_t tseg, t0, t1, pad; };
+struct SChunk { uint32_t slot, b0, b1; };  // a CTA's share of k_score_lists: blocks [b0, b1) of one slot (global slot ordinal)
+
+struct TileParams {
+  const TSlot* slots;
+  const TSeg* segs;
+  const TQuery* queries;
+  const uint16_t* clauses;
+  const TUnit* units;
+  const SChunk* chunks;
+  uint32_t* p_docs;
+  float* p_scores;
+  uint32_t* samples;       // [n_queries of the batch][sample_cap] score keys
+  uint32_t* sample_count;  // [n_queries of the batch]
+  uint32_t* flags;         // [0]: a tile held more pairs than p_cap (the batch is re-run on the per-query kernels)
+  unsigned long long* counters;  // [8] diagnostics: 0 (query, tile) pairs seen, 1 skipped (bound / no essential posting / cold window),
+                                 //     2 light pairs, 3 heavy pairs, 4 essential postings applied, 5 docs completed, 6 docs at or above the threshold
+  uint32_t sample_cap;
+  uint32_t p_cap;      // pairs of one tile that fit in shared memory
+  uint32_t max_slots;  // largest n_slots of any segment of the group
+  uint32_t light_max;  // (query, tile) pairs with at most this many essential postings take the thread-per-query path
+};
+
+__host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots) {
+  return (size_t)p_cap * 4 + (size_t)kTileWarps * kTile * 4 + (size_t)max_slots * 16 + (size_t)p_cap * 2 + (size_t)kTileMaxQueries * 2 + 64;
+}
+
+// ---- K1 + K2, once per batch -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_score_lists(const BatchParams P, const TileParams TP, uint32_t chunk_base) {
+  const SChunk C = TP.chunks[chunk_base + blockIdx.x];
+  const TSlot sl = TP.slots[C.slot];
+  const ListDesc L = P.lists[sl.list_id];
+  const Scorer sc{sl.weight, P.caches + 256u * sl.cache_idx, P.tf_tables + (size_t)(kTfRows * 256u) * sl.cache_idx};
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t* out_docs = TP.p_docs + sl.pair_base;
+  float* out_scores = TP.p_scores + sl.pair_base;
+  uint32_t* tix = nullptr;
+  uint32_t n_big = 0, n_tiles = 0;
+  if (sl.big != kNoSlot) {
+    const TSeg G = TP.segs[sl.tseg];
+    tix = G.tix + sl.big;
+    n_big = G.n_big;
+    n_tiles = G.n_tiles;
+  }
+  BlockFetch f;
+  uint32_t b = C.b0 + warp;
+  if (b < C.b1) fetch_issue(L, b, lane, f);
+  for (; b < C.b1; b += kWarps) {
+    uint32_t doc[4], tf[4];
+    fetch_decode(L, b, f, lane, doc, tf);
+    const uint32_t prev_last = b ? __ldg(L.last_doc + b - 1) : 0xFFFFFFFFu;
+    if (b + kWarps < C.b1) fetch_issue(L, b + kWarps, lane, f);  // the next block travels while this one is scored
+    const uint32_t g0 = b * 128u + lane * 4u;
+    uint32_t id[4];
+    float s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool valid = g0 + i < L.doc_freq;  // the VInt tail pads with TERMINATED
+      id[i] = L.fieldnorm ? (uint32_t)__ldg(L.fieldnorm + (valid ? doc[i] : 0u)) : 1u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool valid = g0 + i < L.doc_freq;
+      s[i] = valid ? bm25_score_id(sc, id[i], tf[i]) : 0.0f;
+      if (!valid) doc[i] = 0xFFFFFFFFu;
+    }
+    reinterpret_cast<uint4*>(out_docs + g0)[0] = make_uint4(doc[0], doc[1], doc[2], doc[3]);
+    reinterpret_cast<float4*>(out_scores + g0)[0] = make_float4(s[0], s[1], s[2], s[3]);
+    if (tix) {  // tile index of a dense list: tix[t] = first pair with doc >= t * kTile
+      uint32_t pd = __shfl_up_sync(kFull, doc[3], 1);
+      if (lane == 0) pd = prev_last;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t g = g0 + i;
+        if (g < L.doc_freq) {
+          const uint32_t p = i == 0 ? pd : doc[i - 1];
+          const uint32_t t_cur = doc[i] / kTile;
+          for (uint32_t t = p == 0xFFFFFFFFu ? 0u : p / kTile + 1u; t <= t_cur; ++t) tix[(size_t)t * n_big] = g;
+          if (g + 1u == L.doc_freq)
+            for (uint32_t t = t_cur + 1u; t <= n_tiles; ++t) tix[(size_t)t * n_big] = L.doc_freq;
+        }
+      }
+    }
+  }
+}
+
+// ---- tile evaluation -----------------------------------------------------------------------------------------------------
+// info word of a slot in the current tile: start | len << 16 (pairs [start, start + len) of s_off / s_score, ascending docs)
+__device__ __forceinline__ float tile_find(const uint16_t* __restrict__ s_off, const float* __restrict__ s_score, uint32_t info, uint32_t off,
+                                           bool& found) {
+  uint32_t lo = info & 0xFFFFu;
+  const uint32_t end = lo + (info >> 16);
+  uint32_t hi = end;
+  while (lo < hi) {
+    const uint32_t m = (lo + hi) >> 1;
+    if (s_off[m] < off) lo = m + 1u; else hi = m;
+  }
+  found = lo < end && s_off[lo] == off;
+  return found ? s_score[lo] : 0.0f;
+}
+
+__device__ __forceinline__ void tile_push(const BatchParams& P, uint32_t query, float score, uint32_t doc, uint32_t segment_ord,
+                                          uint32_t th_key, const uint8_t* __restrict__ alive) {
+  const uint32_t key = score_to_key(score);
+  if (key < th_key) return;
+  if (alive && !is_alive(alive, doc)) return;
+  const DQuery Q = P.queries[query];
+  const uint32_t idx = atomicAdd(&P.qstate[query].cand_count, 1u);
+  if (idx < Q.cand_cap) P.cands[Q.cand_base + idx] = Cand{key, segment_ord, doc, 0u};
+}
+
+struct TileQueryState {
+  uint32_t th_key;
+  float theta_f;
+  uint32_t n_e;   // essential clauses [0, n_e)
+  float ne;       // upper bound of what the non-essential suffix can add in this tile
+  bool prune;     // bounds may be used (threshold present, weights >= 0, exact launch)
+};
+
+__device__ __forceinline__ TileQueryState tile_query_state(uint32_t th_key, const TQuery& tq, const uint16_t* __restrict__ cl,
+                                                           const float* __restrict__ s_max, bool sample_mode) {
+  TileQueryState st;
+  st.th_key = th_key;
+  st.theta_f = threshold_score(st.th_key);
+  st.n_e = tq.n_clauses;
+  st.ne = 0.0f;
+  st.prune = (tq.flags & 1u) && st.theta_f > 0.0f && !sample_mode;
+  if (st.prune) {
+    while (st.n_e > 0) {
+      const float b = st.ne + s_max[cl[st.n_e - 1u]];
+      if (!(b * 1.00001f < st.theta_f)) break;  // (f32 sums of <= 32 terms differ by < 4e-6 relative between orders)
+      st.ne = b;
+      --st.n_e;
+    }
+  }
+  return st;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, const TileParams TP, uint32_t unit_base, uint32_t sample_mode) {
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  float* s_score = reinterpret_cast<float*>(s_dyn);                       // [p_cap]
+  float* s_acc = s_score + TP.p_cap;                                      // [kTileWarps][kTile]
+  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_acc + kTileWarps * kTile);  // [max_slots]
+  float* s_max = reinterpret_cast<float*>(s_info + TP.max_slots);         // [max_slots] largest score of the slot in this tile (>= 0)
+  uint32_t* s_cur = reinterpret_cast<uint32_t*>(s_max + TP.max_slots);    // [max_slots] small slots: first pair not staged yet
+  uint32_t* s_nxt = s_cur + TP.max_slots;                                 // [max_slots] ... and its doc (0xFFFFFFFF: list exhausted)
+  uint16_t* s_off = reinterpret_cast<uint16_t*>(s_nxt + TP.max_slots);    // [p_cap]
+  uint16_t* s_heavy = s_off + TP.p_cap;                                   // [kTileMaxQueries]
+  __shared__ uint32_t s_total, s_nheavy, s_hpos;
+  __shared__ unsigned long long s_stat[8];
+  const TUnit U = TP.units[unit_base + blockIdx.x];
+  const TSeg G = TP.segs[U.tseg];
+  const TSlot* __restrict__ slots = TP.slots + G.slot_base;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const float neg_zero = __uint_as_float(0x80000000u);
+  for (uint32_t i = tid; i < kTileWarps * kTile; i += kTileThreads) s_acc[i] = neg_zero;
+  if (tid < 8) s_stat[tid] = 0ull;
+  // small slots: position the cursor on the first pair at or after the unit's first doc
+  for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {
+    const TSlot sl = slots[s];
+    const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base;
+    const uint32_t lo0 = U.t0 * kTile;
+    uint32_t a = 0, b = sl.doc_freq;
+    while (a < b) {
+      const uint32_t m = (a + b) >> 1;
+      if (__ldg(d + m) < lo0) a = m + 1u; else b = m;
+    }
+    s_cur[s] = a;
+    s_nxt[s] = a < sl.doc_freq ? __ldg(d + a) : 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  unsigned long long st_pairs = 0, st_skip = 0, st_light = 0, st_ess = 0, st_compl = 0, st_push = 0;  // per-thread diagnostics
+
+  for (uint32_t t = U.t0; t < U.t1; ++t) {
+    const uint32_t lo = t * kTile, hi = lo + kTile;
+    if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; }
+    __syncthreads();
+    // ---- stage A: this tile's pairs of every slot -> shared memory --------------------------------------------------------
+    for (uint32_t s = warp; s < G.n_big; s += kTileWarps) {  // dense lists: a warp copies [tix[t], tix[t+1])
+      const TSlot sl = slots[s];
+      const uint32_t a = __ldg(G.tix + (size_t)t * G.n_big + s), b = __ldg(G.tix + (size_t)(t + 1u) * G.n_big + s);
+      const uint32_t n = b - a;
+      uint32_t base = 0;
+      if (lane == 0 && n) base = atomicAdd(&s_total, n);
+      base = __shfl_sync(kFull, base, 0);
+      float mx = 0.0f;
+      const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base + a;
+      const float* __restrict__ sc = TP.p_scores + sl.pair_base + a;
+      if (base + n <= TP.p_cap) {
+        for (uint32_t i = lane; i < n; i += 32) {
+          const float v = __ldg(sc + i);
+          s_off[base + i] = (uint16_t)(__ldg(d + i) - lo);
+          s_score[base + i] = v;
+          mx = fmaxf(mx, v);
+        }
+      }
+      mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(mx)));  // mx >= 0
+      if (lane == 0) { s_info[s] = (base & 0xFFFFu) | (n << 16); s_max[s] = mx; }
+    }
+    for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {  // sparse lists: one thread walks its cursor
+      uint32_t nd = s_nxt[s];
+      if (nd >= hi) { s_info[s] = 0u; s_max[s] = 0.0f; continue; }
+      const TSlot sl = slots[s];
+      const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base;
+      const float* __restrict__ sc = TP.p_scores + sl.pair_base;
+      const uint32_t cur = s_cur[s];
+      uint32_t n = 1;  // nd < hi: the pair at the cursor belongs to this tile
+      for (;;) {       // four docs per round trip
+        const uint32_t c = cur + n;
+        uint32_t d4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d4[i] = c + i < sl.doc_freq ? __ldg(d + c + i) : 0xFFFFFFFFu;
+        uint32_t k = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) k += d4[i] < hi ? 1u : 0u;  // ascending: the ones below hi are a prefix
+        n += k;
+        if (k < 4u) { nd = d4[k]; break; }
+      }
+      s_cur[s] = cur + n;
+      s_nxt[s] = nd;
+      const uint32_t base = atomicAdd(&s_total, n);
+      float mx = 0.0f;
+      if (base + n <= TP.p_cap) {
+        for (uint32_t i = 0; i < n; ++i) {
+          const float v = __ldg(sc + cur + i);
+          s_off[base + i] = (uint16_t)(__ldg(d + cur + i) - lo);
+          s_score[base + i] = v;
+          mx = fmaxf(mx, v);
+        }
+      }
+      s_info[s] = (base & 0xFFFFu) | (n << 16);
+      s_max[s] = mx;
+    }
+    __syncthreads();
+    if (s_total > TP.p_cap) {  // more pairs than the tile buffer holds: give the batch back to the per-query kernels
+      if (tid == 0) atomicExch(TP.flags, 1u);
+      __syncthreads();
+      continue;
+    }
+    // ---- stage B1: one thread per query -- bounds, routing, and the light (query, tile) pairs -------------------------------
+    for (uint32_t qi = tid; qi < G.n_queries; qi += kTileThreads) {
+      const TQuery tq = TP.queries[G.query_base + qi];
+      const uint16_t* __restrict__ cl = TP.clauses + tq.clause_base;
+      const TileQueryState st = tile_query_state(*(volatile unsigned int*)&P.qstate[tq.query].theta, tq, cl, s_max, sample_mode != 0);
+      ++st_pairs;
+      if (st.n_e == 0) { ++st_skip; continue; }  // no doc of this tile can reach the threshold
+      uint32_t cnt = 0;
+      for (uint32_t c = 0; c < st.n_e; ++c) cnt += s_info[cl[c]] >> 16;
+      if (cnt == 0) { ++st_skip; continue; }  // a doc without an essential posting stays below the threshold
+      if (sample_mode || cnt > TP.light_max) { s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)qi; continue; }
+      ++st_light;
+      st_ess += cnt;
+      const uint32_t n = tq.n_clauses;
+      for (uint32_t c = 0; c < st.n_e; ++c) {
+        const uint32_t info = s_info[cl[c]];
+        const uint32_t a = info & 0xFFFFu, e = a + (info >> 16);
+        for (uint32_t p = a; p < e; ++p) {
+          const uint32_t off = s_off[p];
+          bool dup = false;  // the doc was evaluated when an earlier essential clause listed it
+          for (uint32_t c1 = 0; c1 < c && !dup; ++c1) tile_find(s_off, s_score, s_info[cl[c1]], off, dup);
+          if (dup) continue;
+          float sum = s_score[p];  // (-0.0 + s == s: SumCombiner starts from 0, score_combiner.rs:39-57)
+          for (uint32_t c2 = c + 1u; c2 < st.n_e; ++c2) {
+            bool f;
+            const float v = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
+            if (f) sum = __fadd_rn(sum, v);
+          }
+          if (st.prune && (sum + st.ne) * 1.00001f < st.theta_f) continue;
+          for (uint32_t c2 = st.n_e; c2 < n; ++c2) {
+            bool f;
+            const float v = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
+            if (f) sum = __fadd_rn(sum, v);
+          }
+          ++st_compl;
+          if (score_to_key(sum) >= st.th_key) ++st_push;
+          tile_push(P, tq.query, sum, lo + off, G.segment_ord, st.th_key, G.alive);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stage B2: one warp per heavy query, a window of f32 score slots ----------------------------------------------------
+    {
+      const uint32_t n_heavy = s_nheavy;
+      float* acc = s_acc + warp * kTile;
+      for (;;) {
+        uint32_t h = 0;
+        if (lane == 0) h = atomicAdd(&s_hpos, 1u);
+        h = __shfl_sync(kFull, h, 0);
+        if (h >= n_heavy) break;
+        const TQuery tq = TP.queries[G.query_base + s_heavy[h]];
+        const uint16_t* __restrict__ cl = TP.clauses + tq.clause_base;
+        uint32_t th_key = 0;
+        if (lane == 0) th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
+        th_key = __shfl_sync(kFull, th_key, 0);  // one value for the whole warp (the query-wide threshold moves)
+        const TileQueryState st = tile_query_state(th_key, tq, cl, s_max, sample_mode != 0);
+        const uint32_t n = tq.n_clauses;
+        float wmax = 0.0f;
+        for (uint32_t c = 0; c < st.n_e; ++c) {  // clause order is the f32 summation order
+          const uint32_t info = s_info[cl[c]];
+          const uint32_t a = info & 0xFFFFu, e = a + (info >> 16);
+          for (uint32_t p = a + lane; p < e; p += 32) {
+            const uint32_t o = s_off[p];
+            const float v = __fadd_rn(acc[o], s_score[p]);
+            acc[o] = v;
+            wmax = fmaxf(wmax, v);
+          }
+          if (lane == 0) st_ess += e - a;
+          __syncwarp();
+        }
+        if (sample_mode) {
+          // the best partial maximum of every lane's slots; the top few of the warp are this (query, tile)'s samples
+          uint32_t best = 0;
+          for (uint32_t g = 0; g < kTile / 128u; ++g) {
+            const uint32_t idx = g * 128u + lane * 4u;
+            const float4 v = *reinterpret_cast<const float4*>(acc + idx);
+            *reinterpret_cast<float4*>(acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (__float_as_uint(vv[c]) != 0x80000000u) best = max(best, score_to_key(vv[c]));
+          }
+          for (uint32_t r = 0; r < kSamplePerTile; ++r) {
+            const uint32_t m = __reduce_max_sync(kFull, best);
+            if (m == 0u || m < st.th_key) break;
+            const unsigned who = __ballot_sync(kFull, best == m);
+            if (lane == (uint32_t)__ffs(who) - 1u) {
+              const uint32_t idx = atomicAdd(&TP.sample_count[tq.query], 1u);
+              if (idx < TP.sample_cap) TP.samples[(size_t)tq.query * TP.sample_cap + idx] = m;
+              best = 0;
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        if (lane == 0) st_light += 0x100000000ull;  // (high half: heavy pairs)
+        // nothing of this window can reach the threshold when even its largest partial sum plus the bound cannot
+        const float mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(wmax)));
+        const bool cold = st.prune && (mx + st.ne) * 1.00001f < st.theta_f;
+        if (cold && lane == 0) ++st_skip;
+        for (uint32_t g = 0; g < kTile / 128u; ++g) {
+          const uint32_t idx = g * 128u + lane * 4u;
+          float4 v = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+          if (!cold) v = *reinterpret_cast<const float4*>(acc + idx);
+          *reinterpret_cast<float4*>(acc + idx) = make_float4(neg_zero, neg_zero, neg_zero, neg_zero);
+          if (cold) continue;
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float sum = vv[c];
+            if (__float_as_uint(sum) == 0x80000000u) continue;  // untouched
+            if (st.prune && (sum + st.ne) * 1.00001f < st.theta_f) continue;
+            const uint32_t off = idx + c;
+            for (uint32_t c2 = st.n_e; c2 < n; ++c2) {
+              bool f;
+              const float x = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
+              if (f) sum = __fadd_rn(sum, x);
+            }
+            ++st_compl;
+            if (score_to_key(sum) >= st.th_key) ++st_push;
+            tile_push(P, tq.query, sum, lo + off, G.segment_ord, st.th_key, G.alive);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  if (TP.counters) {
+    // warp-aggregated diagnostics
+    unsigned long long v[7] = {st_pairs, st_skip, st_light & 0xFFFFFFFFull, st_light >> 32, st_ess, st_compl, st_push};
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      unsigned long long x = v[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+      if (lane == 0 && x) atomicAdd(&s_stat[i], x);
+    }
+    __syncthreads();
+    if (tid < 7 && s_stat[tid]) atomicAdd(&TP.counters[tid], s_stat[tid]);
+  }
+}
+
+// ---- thresholds from score keys -------------------------------------------------------------------------------------------
+// k-th largest of n u32 keys (4-pass radix select), block-wide; returns 0 when n < k.  `need_out`: how many keys equal to the
+// result are needed on top of the strictly larger ones to make k.
+__device__ __forceinline__ uint32_t block_kth_key(const uint32_t* __restrict__ keys, uint32_t n, uint32_t stride_words, uint32_t k,
+                                                  uint32_t* s_hist, uint32_t* s_prefix, uint32_t* s_need) {
+  if (n < k) return 0u;
+  if (threadIdx.x == 0) { *s_prefix = 0; *s_need = k; }
+  uint32_t mask = 0;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = *s_prefix;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t key = keys[(size_t)i * stride_words];
+      if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t need = *s_need, bsel = 0;
+      for (int bin = 255; bin >= 0; --bin) {
+        const uint32_t h = s_hist[bin];
+        if (h >= need) { bsel = (uint32_t)bin; break; }
+        need -= h;
+      }
+      *s_need = need;
+      *s_prefix = prefix | (bsel << shift);
+    }
+    mask |= 0xFFu << shift;
+    __syncthreads();
+  }
+  return *s_prefix;
+}
+
+// After the sample launch: the k-th best sampled score of a query bounds its final k-th score from below.
+__global__ void __launch_bounds__(kThreads) k_theta_samples(const BatchParams P, const uint32_t* __restrict__ samples,
+                                                            const uint32_t* __restrict__ sample_count, uint32_t sample_cap) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_need;
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = min(sample_count[q], sample_cap);
+  const uint32_t kth = block_kth_key(samples + (size_t)q * sample_cap, n, 1u, P.queries[q].k, s_hist, &s_prefix, &s_need);
+  if (threadIdx.x == 0 && kth) atomicMax(&P.qstate[q].theta, kth);
+}
+
+// Cross-shard exchange, export side: the k best score keys a query holds so far (samples after the sample launch, else
+// candidates), k_stride entries per query, zero padded.  The caller all-gathers these over the shards.
+__global__ void __launch_bounds__(kThreads) k_topkeys_export(const BatchParams P, const uint32_t* __restrict__ samples,
+                                                             const uint32_t* __restrict__ sample_count, uint32_t sample_cap,
+                                                             uint32_t from_samples, uint32_t* __restrict__ out, uint32_t k_stride) {
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_need, s_n;
+  const uint32_t q = blockIdx.x;
+  const DQuery Q = P.queries[q];
+  const uint32_t* keys;
+  uint32_t n, stride;
+  if (from_samples && samples) { keys = samples + (size_t)q * sample_cap; n = min(sample_count[q], sample_cap); stride = 1u; }
+  else { keys = &P.cands[Q.cand_base].score_key; n = min(P.qstate[q].cand_count, Q.cand_cap); stride = sizeof(Cand) / 4u; }
+  const uint32_t k = min(Q.k, k_stride);
+  uint32_t* o = out + (size_t)q * k_stride;
+  for (uint32_t i = threadIdx.x; i < k_stride; i += blockDim.x) o[i] = 0u;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  if (n <= k) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = keys[(size_t)i * stride];
+    return;
+  }
+  const uint32_t kth = block_kth_key(keys, n, stride, k, s_hist, &s_prefix, &s_need);
+  const uint32_t above = k - s_need;  // strictly larger keys
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const uint32_t key = keys[(size_t)i * stride];
+    if (key > kth) o[atomicAdd(&s_n, 1u)] = key;
+  }
+  __syncthreads();
+  for (uint32_t i = above + threadIdx.x; i < k; i += blockDim.x) o[i] = kth;
+}
+
+// ... import side: gathered [n_shards][nq][k_stride] keys -> the exact k-th best of the union becomes the query's threshold.
+__global__ void __launch_bounds__(kThreads) k_theta_from_keys(const BatchParams P, const uint32_t* __restrict__ gathered, uint32_t n_shards,
+                                                              uint32_t nq, uint32_t k_stride) {
+  extern __shared__ uint32_t s_keys[];  // [n_shards * k_stride]
+  __shared__ uint32_t s_hist[256];
+  __shared__ uint32_t s_prefix, s_need;
+  const uint32_t q = blockIdx.x;
+  const uint32_t n = n_shards * k_stride;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    s_keys[i] = gathered[((size_t)(i / k_stride) * nq + q) * k_stride + (i % k_stride)];
+  __syncthreads();
+  const uint32_t kth = block_kth_key(s_keys, n, 1u, P.queries[q].k, s_hist, &s_prefix, &s_need);
+  if (threadIdx.x == 0 && kth) atomicMax(&P.qstate[q].theta, kth);
+}
+
+}  // namespace tq

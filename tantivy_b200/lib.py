@@ -38,6 +38,9 @@ def _load():
     lib.tq_batch_phases.argtypes = [vp]
     lib.tq_batch_thresholds_export_dev.argtypes = [vp, vp]
     lib.tq_batch_thresholds_import_dev.argtypes = [vp, vp]
+    lib.tq_batch_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.tq_batch_topkeys_export_dev.argtypes = [vp, vp, C.c_uint32]
+    lib.tq_batch_thresholds_from_keys_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
     lib.tq_batch_fetch.argtypes = [vp, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_results_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
     lib.tq_batch_results_copy_dev.argtypes = [vp, vp, vp, vp, vp]
@@ -249,7 +252,7 @@ class Context:
     def stats(self):
         s = Stats()
         _check(LIB.tq_get_stats(self.h, C.byref(s)), self.h)
-        return {name: (list(getattr(s, name)) if name == "or_windows" else getattr(s, name)) for name, _ in Stats._fields_}
+        return {name: (list(getattr(s, name)) if name in ("or_windows", "tile_counters") else getattr(s, name)) for name, _ in Stats._fields_}
 
     def merge_topk_dev(self, n_lists, nq, stride, k, scores, segs, docs, counts, out_scores, out_segs, out_docs, out_counts):
         """All arguments are raw device addresses (int), e.g. torch tensors' data_ptr()."""
@@ -290,6 +293,19 @@ class Batch:
 
     def thresholds_import_dev(self, keys_dev):
         _check(LIB.tq_batch_thresholds_import_dev(self.h, keys_dev), self.ctx.h)
+
+    def stream(self):
+        """The CUDA stream (cudaStream_t as int) every launch of this batch is enqueued on."""
+        s = C.c_void_p()
+        _check(LIB.tq_batch_stream(self.h, C.byref(s)), self.ctx.h)
+        return s.value or 0
+
+    def topkeys_export_dev(self, keys_dev, k_stride):
+        """keys_dev: device address of nq * k_stride uint32; enqueued on the batch's stream, no host sync."""
+        _check(LIB.tq_batch_topkeys_export_dev(self.h, keys_dev, k_stride), self.ctx.h)
+
+    def thresholds_from_keys_dev(self, gathered_dev, n_shards, k_stride):
+        _check(LIB.tq_batch_thresholds_from_keys_dev(self.h, gathered_dev, n_shards, k_stride), self.ctx.h)
 
     def fetch(self, out=None):
         stride, scores, segs, docs, counts = out or self.qb.alloc_out()

@@ -15,9 +15,29 @@ from tantivy_b200._abi import (TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM, TQ_RECORD_BASIC,
 from tests.helpers import OracleSegment, hits, make_query  # noqa: E402
 
 
-@pytest.fixture(scope="module")
-def ctx():
-    c = T.Context(0)
+import os  # noqa: E402
+
+
+def _ctx_with_env(**env):
+    """tq_ctx_create reads its tuning knobs from the environment."""
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return T.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+# every test runs on both union engines: "tile" = the shared-decode tile engine (k_score_lists + k_tile, the default),
+# "legacy" = the per-query kernels (k_or_strip / k_or_pipe / k_or) that the tile engine falls back to
+@pytest.fixture(scope="module", params=["tile", "legacy"])
+def ctx(request):
+    c = _ctx_with_env(TQ_TILE=1 if request.param == "tile" else 0)
+    c.engine = request.param
     yield c
     c.close()
 
@@ -69,13 +89,22 @@ def _lists_all_widths(rng, max_doc):
     big = np.ones(200, np.uint32)
     big[17] = 0xFFFFFFFF  # 32-bit tf width
     lists.append((np.arange(5, 205, dtype=np.uint32), big))
+    # doc bit widths 25..31 (skip.rs:16-22 allows up to 31): one gap of 2^(bits-1) + 1 in a full block (doc ids stay below
+    # TERMINATED = 2^31 - 1), both as the first block of a list and behind another block / in front of a VInt tail
+    for bits in range(25, 32):
+        for n, at in ((128 + int(rng.integers(0, 100)), 5), (256 + int(rng.integers(1, 128)), 128 + 77)):
+            gaps = rng.integers(1, 40, size=n, dtype=np.uint64)
+            gaps[at] = 2 ** (bits - 1) + 1
+            docs = (int(rng.integers(0, 3)) + np.cumsum(gaps) - gaps[0])
+            assert docs[-1] < max_doc
+            lists.append((docs.astype(np.uint32), rng.integers(1, 2 ** int(rng.integers(1, 12)) + 1, size=n, dtype=np.uint64).astype(np.uint32)))
     return lists
 
 
 @pytest.mark.parametrize("record_option", [TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS])
 def test_decode_every_width_and_alignment(ctx, record_option):
     rng = np.random.default_rng(42 + record_option)
-    max_doc = 2 ** 26
+    max_doc = 0x7FFFFFFE  # the largest max_doc there is (TERMINATED - 1): widths 25..31 need doc ids up to 2^31
     lists = _lists_all_widths(rng, max_doc)
     if record_option == TQ_RECORD_BASIC:
         lists = [(d, None) for d, _ in lists]
@@ -470,3 +499,124 @@ def test_count_collector_synth(ctx, synth):
     qb = QueryBatch([ix.query(op, terms, 1, segment_base=base) for op, terms in
                      [(TQ_OP_OR, [0, 1, 2, 3, 4, 5]), (TQ_OP_AND, [0, 1]), (TQ_OP_AND, [2, 0, 3]), (TQ_OP_OR, [4, 5]), (TQ_OP_TERM, [1])]])
     assert (ctx.count_batch(qb) == oi.count_batch(qb)).all()
+
+
+# ---- tile engine specifics -------------------------------------------------------------------------------------------
+def _tile_queries(ix, base):
+    qs = []
+    for k in (1, 10, 100, 1000):
+        for terms in ([0, 5], [0, 4, 5], [1, 0, 5, 3], [5, 4, 3, 2, 1, 0], [0, 1, 2], [2, 3, 4], [3, 5], [4, 5]):
+            qs.append(ix.query(TQ_OP_OR, terms, k, segment_base=base))
+    return qs
+
+
+def test_tile_engine_is_what_runs(ctx, synth):
+    ix, oi, base = synth
+    qb = QueryBatch(_tile_queries(ix, base))
+    g = ctx.search_batch(qb)
+    assert_same(g, oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+    st = ctx.stats()
+    if ctx.engine == "tile":
+        assert st["tile_groups"] == 1 and st["units_tile"] > 0 and st["tile_postings"] > 0 and st["tile_fallbacks"] == 0
+        assert st["units_or"] == 0  # no per-query union kernel ran
+    else:
+        assert st["tile_groups"] == 0 and st["units_or"] > 0
+
+
+@pytest.mark.parametrize("hook", [dict(TQ_TILE_PCAP=64), dict(TQ_TILE_CAND_FLOOR=4), dict(TQ_TILE_SAMPLE_DIV=0, TQ_TILE_CAND_FLOOR=64)])
+def test_tile_overflow_is_repeated_on_the_per_query_kernels(synth, hook):
+    """A tile with more pairs than its shared-memory buffer, or a query with more candidates than its region, never costs
+    exactness: the run is repeated on the per-query kernels (tile_fallbacks == 1) and returns the oracle's rows."""
+    ix, oi, base = synth
+    c = _ctx_with_env(TQ_TILE=1, **hook)
+    try:
+        ix.register(c, segment_base=base)
+        qb = QueryBatch(_tile_queries(ix, base))
+        g = c.search_batch(qb)
+        assert_same(g, oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+        assert c.stats()["tile_fallbacks"] == 1
+        bt = c.prepare(qb)  # device-resident results take the same route
+        bt.run()
+        bt.results_dev()
+        assert_same(bt.fetch(), g, qb.nq)
+        bt.close()
+    finally:
+        c.close()
+
+
+def test_tile_groups_split_on_capacity(synth):
+    """More distinct dense lists than one tile buffer holds: the planner opens further groups (one decode pass each)."""
+    ix, oi, base = synth
+    c = _ctx_with_env(TQ_TILE=1, TQ_TILE_MAX_DENS_X1000=400)
+    try:
+        ix.register(c, segment_base=base)
+        qb = QueryBatch(_tile_queries(ix, base))
+        g = c.search_batch(qb)
+        assert_same(g, oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+        st = c.stats()
+        assert st["tile_groups"] > 1 and st["tile_fallbacks"] == 0
+    finally:
+        c.close()
+
+
+def test_topkeys_exchange_matches_plain_run(ctx, synth):
+    """The exact cross-shard threshold exchange on one shard: export the k best keys after every phase, feed them back as if
+    gathered from n_shards = 1 (and duplicated, n_shards = 2): the rows equal the plain run's."""
+    import torch
+    ix, oi, base = synth
+    qb = QueryBatch(_tile_queries(ix, base)[:16])
+    plain = ctx.search_batch(qb)
+    kmax = qb.kmax
+    for shards in (1, 2):
+        keys = torch.zeros((shards, qb.nq, kmax), dtype=torch.int32, device="cuda:0")
+        b = ctx.prepare(qb)
+        n_phases = b.phases()
+        for phase in range(n_phases):
+            b.run_phase(phase)
+            if phase + 1 < n_phases:
+                b.topkeys_export_dev(keys[0].data_ptr(), kmax)
+                b.thresholds_from_keys_dev(keys.data_ptr(), shards, kmax)  # shard 1 (if any) reports nothing: zeros
+        out = b.fetch()
+        b.close()
+        for a, c in zip(plain, out):
+            assert (a == c).all()
+
+
+# ---- BASELINE.json configurations at full size (SURVEY.md §8d), one segment of each ------------------------------------
+def _zipf_queries(rng, n, n_terms, max_rank):
+    ranks = np.arange(1, max_rank + 1)
+    prob = (1.0 / ranks) / (1.0 / ranks).sum()
+    return [sorted(int(r) for r in rng.choice(ranks, size=n_terms, replace=False, p=prob)) for _ in range(n)]
+
+
+def test_bench_config_or5_top100_one_full_segment(ctx):
+    """configs[2] at its real segment size: 12.5M docs, 5-term unions of Zipf-drawn ranks from {1..1000} (density 0.3 / rank),
+    top-100 -- threshold rounds, MaxScore splits and tile maxima all active -- vs the exhaustive oracle, bit for bit."""
+    rng = np.random.default_rng(0x7A6E)
+    qranks = _zipf_queries(rng, 48, 5, 1000)
+    ranks = sorted({r for q in qranks for r in q})
+    dens = [min(0.5, 0.3 / r) for r in ranks]
+    ix = T.SynthIndex(1, 12_500_000, dens, seed=0x7A6E7469)
+    base = fresh_ord()
+    ix.register(ctx, segment_base=base)
+    oi = O.OracleIndex()
+    ix.register(oi, segment_base=base)
+    qb = QueryBatch([ix.query(TQ_OP_OR, [ranks.index(r) for r in q], 100, segment_base=base) for q in qranks])
+    g = ctx.search_batch(qb)
+    assert_same(g, oi.search_batch(qb, mode=0, n_threads=32), qb.nq)
+    assert ctx.stats()["tile_fallbacks"] == 0
+    ctx.segment_unregister(base, 0)
+
+
+def test_bench_config_and2_top10_10M(ctx):
+    """configs[1]: 10M docs, one segment, the three density pairs of benches/intersection_bench.rs:107-113, top-10."""
+    pairs = [(0.10, 0.10), (0.50, 0.02), (0.80, 0.005)]
+    dens = [p for ab in pairs for p in ab]
+    ix = T.SynthIndex(1, 10_000_000, dens, seed=0x7A6E7469)
+    base = fresh_ord()
+    ix.register(ctx, segment_base=base)
+    oi = O.OracleIndex()
+    ix.register(oi, segment_base=base)
+    qb = QueryBatch([ix.query(TQ_OP_AND, [2 * i, 2 * i + 1], k, segment_base=base) for i in range(3) for k in (10, 100)])
+    assert_same(ctx.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=32), qb.nq)
+    ctx.segment_unregister(base, 0)

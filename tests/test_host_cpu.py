@@ -121,12 +121,35 @@ def test_writer_bytes_match_oracle(record_option):
         assert (f == (tfs if tfs is not None else 1)).all()
 
 
+def test_writer_bytes_match_oracle_wide_doc_widths():
+    """Doc bit widths 25..31: the two independent encoders (oracle / product writer) agree byte for byte."""
+    rng = np.random.default_rng(77)
+    max_doc = 0x7FFFFFFE
+    lists = []
+    for bits in range(25, 32):
+        n = 128 + int(rng.integers(0, 100))
+        gaps = rng.integers(1, 40, size=n, dtype=np.uint64)
+        gaps[int(rng.integers(0, 128))] = 2 ** (bits - 1) + 1
+        docs = (np.cumsum(gaps) - gaps[0]).astype(np.uint32)
+        lists.append((docs, rng.integers(1, 9, size=n).astype(np.uint32)))
+    a = OracleSegment(lists, None, writer_cls=O.FieldWriter, max_doc=max_doc)
+    b = OracleSegment(lists, None, writer_cls=T.FieldWriter, max_doc=max_doc)
+    assert a.terms == b.terms and a.body.tobytes() == b.body.tobytes()
+    ix = O.OracleIndex()
+    b.register(ix)
+    for t, (docs, tfs) in enumerate(lists):
+        d, f = ix.decode_postings(b.term_seg(t))
+        assert (d == docs).all() and (f == tfs).all()
+
+
 def test_writer_rejects_bad_input():
     w = T.FieldWriter(TQ_RECORD_FREQS, 10, np.ones(10, np.uint8), 10)
     with pytest.raises(T.TqError):
         w.add_term([3, 3], [1, 1])
     with pytest.raises(T.TqError):
         w.add_term([1, 2], [1, 0])
+    with pytest.raises(T.TqError):
+        w.add_term([1, 10], [1, 1])  # doc id >= max_doc (would index past the fieldnorm array)
 
 
 def test_synth_segments_are_valid_postings():

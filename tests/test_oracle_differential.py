@@ -121,6 +121,27 @@ def test_codec_roundtrip_all_bit_widths():
                 assert (dec == docs).all()
 
 
+def test_codec_sorted_wide_doc_widths():
+    """Doc bit widths 21..31 (one large strict gap per block; doc ids stay below TERMINATED), offset 0 and > 0."""
+    L = O.lib()
+    rng = np.random.default_rng(5)
+    out = np.zeros(640, dtype=np.uint8)
+    written = C.c_size_t()
+    dec = np.zeros(128, dtype=np.uint32)
+    for b in range(21, 32):
+        for offset in (0, 777):
+            gaps = rng.integers(0, 50, size=128, dtype=np.uint64)  # stored value = gap - 1 (strict delta)
+            gaps[int(rng.integers(0, 128))] = 2 ** (b - 1) + int(rng.integers(0, 2 ** (b - 1) - 200)) if b < 31 else 2 ** 30
+            first = gaps[0] if offset == 0 else offset + 1 + gaps[0]
+            docs = first + np.concatenate([[0], np.cumsum(gaps[1:] + 1)])
+            assert docs[-1] < 2 ** 31 - 1
+            docs = docs.astype(np.uint32)
+            nb = L.tqo_compress_block_sorted(O.ptr(docs, O.u32p), offset, O.ptr(out, O.u8p), C.byref(written))
+            assert (nb & 31) == b and written.value == 16 * b
+            L.tqo_uncompress_block_sorted(O.ptr(out, O.u8p), offset, nb, 1, O.ptr(dec, O.u32p))
+            assert (dec == docs).all()
+
+
 def test_search_block_matches_linear_scan():
     L = O.lib()
     rng = np.random.default_rng(2)

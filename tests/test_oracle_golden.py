@@ -286,7 +286,18 @@ def test_positions_sizes_pinned_by_the_reference():
     O.PositionReader(empty)
     # postings/mod.rs:61-81 test_position_write: 120 docs x deltas [1, 2, 3, 2] -> a 207-byte `.pos` FILE = this term's
     # 196 bytes (VInt(3) + 3 widths + 3 x 32-byte blocks of 2-bit deltas + 96 VInt bytes) + the 11-byte composite footer
-    assert len(O.positions_serialize(np.tile([1, 2, 3, 2], 120))) == 207 - 11
+    pw = bytes(O.positions_serialize(np.tile([1, 2, 3, 2], 120)))
+    assert len(pw) == 207 - 11
+    # the field split the size implies (positions/mod.rs:22-28): 480 deltas = 3 full blocks + 96 in the VInt tail
+    assert pw[0] == 0x80 | 3                      # VInt(number of bit-packed blocks), stop bit on the last byte
+    assert pw[1:4] == bytes([2, 2, 2])            # one bit-width byte per block: deltas <= 3 need 2 bits
+    assert len(pw[4:4 + 3 * 32]) == 96            # 3 blocks x 16 * 2 bytes (BitPacker4x: 16 bytes per bit of width)
+    assert pw[100:] == bytes([0x80 | v for v in [1, 2, 3, 2]] * 24)  # 96 one-byte VInts
+    # what BitPacker4x's published layout says those 2-bit blocks hold: value j in bit stream j & 3 at bit 2 * (j >> 2);
+    # the deltas repeat with period 4, so stream c holds the constant (1, 2, 3, 2)[c] in all its 16 fields
+    words = np.frombuffer(pw[4:100], dtype="<u4").reshape(3, 2, 4)
+    for c, v in enumerate([1, 2, 3, 2]):
+        assert (words[:, :, c] == sum(v << (2 * i) for i in range(16))).all()
 
 
 def test_positions_read_offsets_and_rereads():
