@@ -11,6 +11,9 @@ merge (merge_fruits).
 value : whole-job queries/s with the batch descriptors already resident in HBM (kernels only).
 e2e   : the same through tq_search_batch with HOST buffers (H2D descriptors + D2H results inside
         the timed region) — the number to compare with the reference arm.
+parity: after the timed legs a sample of the queries the bench just timed is re-run on the CPU oracle's
+        exhaustive path over the WHOLE index (all segments, also at N > 1) and compared row by row
+        (doc, segment: equal; score: bit-equal) with what the GPU arm returned.
 --impl reference : the reference's CPU algorithm (oracle/ restatement of tantivy's Block-WAND path;
         the Rust crate itself cannot be built here) on all host cores, same workload/metric.
 """
@@ -35,6 +38,8 @@ WORKLOADS = {
                                 desc="BASELINE.json configs[1]: 2-term AND, top-10, 10M docs, 1 segment"),
     "term_top10_1M_1seg": dict(op="term", n_segments=1, docs_per_segment=1_000_000, k=10, n_terms=1, max_rank=0,
                                desc="BASELINE.json configs[0]: single-term top-10, 1M docs, 1 segment"),
+    "or20_top10_500M_64seg": dict(op="or", n_segments=64, docs_per_segment=7_812_500, k=10, n_terms=20, max_rank=10_000,
+                                  desc="BASELINE.json configs[4]: 20-term OR, top-10, 500M docs, 64 segments (8 per GPU at N=8)"),
     "mixed_top10_100M_8seg": dict(op="mixed", n_segments=8, docs_per_segment=12_500_000, k=10, n_terms=0, max_rank=1000,
                                   desc="BASELINE.json configs[3] shape: 40% 2-term AND, 40% 2-4-term OR, 20% term, top-10"),
 }
@@ -147,6 +152,57 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_info():
+    """Threads this process may use (affinity / cgroup quota), CPU model."""
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+            threads = max(1, min(threads, int(quota)))
+    except Exception:
+        pass
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"threads": threads, "cpu_model": model, "cpu_count": os.cpu_count(), "cgroup_cpu_quota": quota}
+
+
+def parity_check(wl, dens, seed, queries, rows, threads):
+    """rows = (scores, segs, docs, counts) the GPU arm returned for `queries` (a prefix of a timed batch).  The oracle's
+    exhaustive path (mode 0: canonical truth) runs over the whole index; docs and segments must be equal and
+    scores bit-equal."""
+    from oracle import tq_oracle as O
+    full = make_shard(wl, dens, 0, 1, seed)
+    oi = O.OracleIndex()
+    full.register(oi)
+    qb = marshal(full, queries)
+    t0 = time.perf_counter()
+    ref = oi.search_batch(qb, mode=0, n_threads=threads)
+    mism, rows_checked = 0, 0
+    first = None
+    for q in range(len(queries)):
+        n = int(ref[3][q])
+        rows_checked += n
+        ok = int(rows[3][q]) == n and (np.asarray(rows[1][q][:n], dtype=np.uint32) == ref[1][q, :n]).all() and \
+            (np.asarray(rows[2][q][:n], dtype=np.uint32) == ref[2][q, :n]).all() and \
+            (np.asarray(rows[0][q][:n], dtype=np.float32).view(np.uint32) == ref[0][q, :n].view(np.uint32)).all()
+        if not ok:
+            mism += 1
+            first = q if first is None else first
+    return {"checked": len(queries), "rows": rows_checked, "mismatches": mism, "first_mismatch": first, "oracle": "oracle/ mode 0 (exhaustive, canonical order), whole index",
+            "score_compare": "bit-equal", "oracle_s": round(time.perf_counter() - t0, 2)}
+
+
 def cpu_reference_run(wl, shard, batches, steps, warmup, sample_queries, threads):
     """The reference CPU algorithm (oracle restatement, Block-WAND + TopNHeap + merge_top_k), all host
     cores, on a bounded sample of the same query stream. One step = `sample_queries` queries."""
@@ -180,6 +236,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0x7A6E7469)
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-queries", type=int, default=32, help="queries of the first timed batch re-checked on the oracle (0 = off)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -190,11 +247,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    host_threads = os.cpu_count() or 1
+    hinfo = host_info()
+    host_threads = hinfo["threads"]
     dens, batches = build_query_plan(wl, args.nq, args.batches, args.seed)
+    # identical in both arms (the driver compares them); everything measured goes to `workload_stats`
     config = {"workload": args.workload, "desc": wl["desc"], "queries_per_step": args.nq, "docs": wl["n_segments"] * wl["docs_per_segment"],
               "segments": wl["n_segments"], "k": wl["k"], "vocab_terms_materialised": len(dens),
-              "sharding": f"segments round-robin over {world} rank(s)", "l2_policy": "inputs larger than L2 (see index_bytes/step_bytes)"}
+              "sharding": f"segments round-robin over {args.gpus} rank(s)",
+              "l2_policy": "inputs larger than L2: every step streams the index's posting bytes plus its (doc, score) pair scratch (see workload_stats)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -207,7 +267,7 @@ def main():
         line = {"metric": "queries/sec", "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "impl": "reference", "config": config,
-                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": host_threads, "kind": "port",
+                "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": host_threads, "kind": "port", "host": hinfo,
                                  "sample": f"{sample} queries per step of the same query stream, all host threads, "
                                            "Block-WAND + TopNHeap + merge_top_k restatement (oracle/, mode=1)"},
                 "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -245,45 +305,53 @@ def main():
         cross_gpu_merge = CrossGpuMerger(ctx, dist, dev, nq, k)  # NCCL all-gather + device merge (K7)
 
     # ---- leg 1: `value` — descriptors resident, kernels only -----------------------------------------
-    prepared = [ctx.prepare(qbs[i % len(qbs)]) for i in range(n_total)]  # also warms the block-table cache
+    prepared = [ctx.prepare(qb) for qb in qbs]  # also warms the block-table cache; cycled through the steps
+    n_prep = len(prepared)
+
+    def run_step(bt):
+        if world > 1:
+            cross_gpu_merge.run(bt)      # phases + exact threshold exchange (NCCL on the batch's stream)
+            rows = cross_gpu_merge(bt)   # packed all-gather + device merge
+            torch.cuda.synchronize()
+            return rows
+        bt.run()
+        bt.results_dev()  # waits for the step
+        return None
+
     barrier_sync()
     for i in range(args.warmup):
-        if world > 1:
-            cross_gpu_merge.run(prepared[i])
-            cross_gpu_merge(prepared[i])
-        else:
-            prepared[i].run()
+        run_step(prepared[i % n_prep])
     barrier_sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    # per-launch device times of the timed steps: CUDA events recorded by the library on the stream each
-    # kernel is launched on; steps are serialised (sync per step) so that the intervals do not overlap.
-    kern = {"term_ms": [], "and_ms": [], "or_ms": [], "final_ms": [], "kernel_ms": []}
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # one sampler per job, not per rank
+    if sampler:
+        sampler.start()
+    # per-kind device times of the timed steps: CUDA events recorded by the library on the stream each kernel is
+    # launched on; steps are serialised (sync per step) so that the intervals do not overlap.
+    kinds = ("score_ms", "tile_ms", "theta_ms", "term_ms", "and_ms", "or_ms", "final_ms", "kernel_ms")
+    kern = {name: [] for name in kinds}
     launches = 0
     stats = None
-    touched0 = ctx.stats()["or_windows"][5]  # cumulative bytes the pruned union kernel actually read
+    touched0 = ctx.stats()["or_windows"][5]  # cumulative bytes the pruned per-query union kernel actually read
+    fallbacks = 0
     t0 = time.perf_counter()
     for i in range(args.warmup, n_total):
-        if world > 1:
-            cross_gpu_merge.run(prepared[i])  # threshold exchange between the sample and the main pass
-            cross_gpu_merge(prepared[i])
-        else:
-            prepared[i].run()
-            prepared[i].results_dev()  # waits for the step
+        run_step(prepared[i % n_prep])
         stats = ctx.stats()
         for key in kern:
             kern[key].append(stats[key])
-        launches += stats["kernel_launches"] + (7 if world > 1 else 0)  # + 3 x threshold export / import, cross-GPU merge
+        fallbacks += stats["tile_fallbacks"]
+        launches += stats["kernel_launches"] + (7 if world > 1 else 0)  # + 3 x (key export + threshold import), cross-GPU merge
     barrier_sync()
     dt_value = time.perf_counter() - t0
     touched_per_step = (stats["or_windows"][5] - touched0) / max(args.steps, 1) if stats else 0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     for b in prepared:
         b.close()
 
     # ---- leg 2: `e2e` — public API with host buffers ---------------------------------------------------
     outs = [qbs[i % len(qbs)].alloc_out() for i in range(2)]
     h2d = d2h = 0
+    parity_rows = None
     barrier_sync()
     for i in range(args.warmup):
         ctx.search_batch(qbs[i % len(qbs)], outs[i % 2])
@@ -294,6 +362,8 @@ def main():
             ctx.search_batch(qbs[i % len(qbs)], outs[i % 2])
             st = ctx.stats()
             h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+            if i == 0 and args.parity_queries:
+                parity_rows = [np.array(x[:args.parity_queries]) for x in outs[0][1:]]  # what the timed call returned for batch 0
         else:
             bt = ctx.prepare(qbs[i % len(qbs)])
             cross_gpu_merge.run(bt)
@@ -301,8 +371,13 @@ def main():
             st = ctx.stats()
             h2d, d2h = st["h2d_bytes"], 0
             if rank == 0:
-                res = [t.cpu() for t in o]
+                res = [t.cpu() for t in o]  # waits for the merge
                 d2h = sum(t.numel() * t.element_size() for t in res)
+                if i == 0 and args.parity_queries:
+                    parity_rows = [res[0].numpy()[:args.parity_queries].copy(), res[1].numpy().astype(np.uint32)[:args.parity_queries],
+                                   res[2].numpy().astype(np.uint32)[:args.parity_queries], res[3].numpy().astype(np.uint32)[:args.parity_queries]]
+            else:
+                torch.cuda.synchronize()
             bt.close()
     barrier_sync()
     dt_e2e = time.perf_counter() - t0
@@ -316,52 +391,78 @@ def main():
     if rank == 0:
         value = nq * args.steps / dt_value
         e2e = nq * args.steps / dt_e2e
-        # roofline of the dominant kernel
+        # roofline of the dominant kernel (this rank's launches; at N > 1 every rank runs the same kernels on its shard)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        op_ms = {name: float(np.mean(kern[name + "_ms"])) for name in ("term", "and", "or")}
-        dominant = max(op_ms, key=op_ms.get)
-        alg_bytes = stats["bytes_" + dominant]  # SURVEY.md §8(d), exhaustive form: every posting of every clause
-        kernel_name = "k_" + dominant
-        touched = None
-        if dominant == "or" and stats.get("units_or_strip", 0) * 2 > stats["units_or"]:
-            kernel_name = "k_or_strip"
-            # pruned kernel (MaxScore): §8(d) asks for the formula restricted to the blocks actually decoded -- counted by
-            # the kernel itself (packed block bytes + staged / gathered fieldnorm bytes) -- next to the exhaustive figure
-            touched = float(touched_per_step) + 12.0 * wl["k"] * nq
-        read_bytes = touched if touched else float(alg_bytes)
-        basis = "bytes the kernel decoded (device counter)" if touched else ("exhaustive formula; k_and prunes leader docs, so this is an exhaustive-equivalent figure" if dominant == "and" else "exhaustive formula (the kernel reads every posting)")
-        achieved = read_bytes / (op_ms[dominant] * 1e-3) / 1e9 if op_ms[dominant] > 0 else 0.0
+        ms = {name[:-3]: float(np.mean(kern[name])) for name in kinds}
+        per_kernel = {k2: v for k2, v in ms.items() if k2 != "kernel"}
+        dominant = max(per_kernel, key=per_kernel.get)
+        n_tile_launches = 4  # the sample launch + three exact launches per step and group
+        tile_groups = max(1, int(stats["tile_groups"]))
+        # SURVEY.md §8(d) per kernel.  k_score_lists: every distinct list of the batch is read once (packed blocks + skip data =
+        # its postings range, + one fieldnorm byte per posting) and written once as 8-byte (doc, score) pairs.  k_tile: the pairs
+        # are read once per launch that covers their tile (the three exact launches partition the tiles, the sample launch re-reads
+        # 1/32 of them) + 16 B per candidate handed over.  Per-query kernels: exhaustive formula / device byte counter as before.
+        score_bytes = float(stats["tile_list_bytes"] + stats["tile_postings"] + 8 * stats["tile_postings"])
+        tile_bytes = float(8 * stats["tile_postings"]) * (1.0 + 1.0 / 32.0) + 12.0 * wl["k"] * nq
+        table = {
+            "score": ("k_score_lists", score_bytes, tile_groups, "postings ranges + 1 B fieldnorm + 8 B pair written per posting, every distinct list once"),
+            "tile": ("k_tile", tile_bytes, n_tile_launches * tile_groups, "8 B (doc, score) pair read per posting per covering launch + result rows"),
+            "or": ("k_or_strip" if stats.get("units_or_strip", 0) * 2 > stats["units_or"] else "k_or_pipe", float(touched_per_step) + 12.0 * wl["k"] * nq if touched_per_step else float(stats["bytes_or"]), 4, "bytes the kernel decoded (device counter)"),
+            "and": ("k_and", float(stats["bytes_and"]), 1, "exhaustive formula; k_and prunes leader docs, so this is an exhaustive-equivalent figure"),
+            "term": ("k_term", float(stats["bytes_term"]), 1, "exhaustive formula (the kernel reads every posting)"),
+            "final": ("k_final", 16.0 * 8192 * nq, 1, "candidate regions (upper bound)"),
+            "theta": ("k_theta", 16.0 * 8192 * nq, 3, "candidate regions (upper bound)"),
+        }
+        kernel_name, step_bytes, n_launch, basis = table[dominant]
+        step_ms = per_kernel[dominant]
+        achieved = step_bytes / (step_ms * 1e-3) / 1e9 if step_ms > 0 else 0.0
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get(kernel_name)
+        if os.path.exists(tpath) and world == 1:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(kernel_name)  # dram bytes per launch, one ncu --set full capture
+        exh = float(stats["algorithmic_bytes"])
         roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": read_bytes, "achieved_basis": basis, "avg_launch_ms": op_ms[dominant],
-                    "launches_per_step_of_this_kernel": 4 if kernel_name == "k_or_strip" else 1,  # 3 threshold rounds + the rest
-                    "exhaustive_algorithmic_bytes_per_step": alg_bytes,
-                    "exhaustive_equivalent_gbs": alg_bytes / (op_ms[dominant] * 1e-3) / 1e9 if op_ms[dominant] > 0 else 0.0,
-                    "postings_per_launch": stats["postings"], "kernel_ms_per_step": {k2: float(np.mean(v)) for k2, v in kern.items()}}
-        config.update({"index_bytes_this_rank": shard.index_bytes, "step_bytes_algorithmic": stats["algorithmic_bytes"],
-                       "units_per_step": stats["units"], "index_generation_s": round(shard.gen_s, 2), "host_threads": host_threads})
+                    "algorithmic_bytes_per_launch": step_bytes / n_launch, "avg_launch_ms": step_ms / n_launch,
+                    "launches_per_step_of_this_kernel": n_launch, "algorithmic_bytes_per_step": step_bytes, "kernel_ms_per_step": step_ms,
+                    "achieved_basis": basis,
+                    "exhaustive_algorithmic_bytes_per_step": exh,
+                    "exhaustive_equivalent_gbs": exh / (ms["kernel"] * 1e-3) / 1e9 if ms["kernel"] > 0 else 0.0,
+                    "exhaustive_equivalent_frac": exh / (ms["kernel"] * 1e-3) / 1e9 / peak if ms["kernel"] > 0 else 0.0,
+                    "exhaustive_note": "SURVEY.md §8(d) exhaustive bytes of the step (every posting of every clause of every query) / device time of ALL kernels of the step",
+                    "all_kernels_ms_per_step": {k2: round(v, 4) for k2, v in ms.items()},
+                    "second_kernel": None}
+        others = sorted(((v, k2) for k2, v in per_kernel.items() if k2 != dominant), reverse=True)
+        if others and others[0][0] > 0:
+            k2 = others[0][1]
+            n2, b2, l2, basis2 = table[k2]
+            roofline["second_kernel"] = {"kernel": n2, "kernel_ms_per_step": others[0][0], "algorithmic_bytes_per_step": b2, "launches_per_step": l2,
+                                         "achieved": b2 / (others[0][0] * 1e-3) / 1e9, "frac": b2 / (others[0][0] * 1e-3) / 1e9 / peak, "achieved_basis": basis2}
+        workload_stats = {"index_bytes_this_rank": shard.index_bytes, "step_bytes_algorithmic_exhaustive": stats["algorithmic_bytes"],
+                          "postings_per_step_exhaustive": stats["postings"], "postings_decoded_per_step": stats["tile_postings"],
+                          "pair_scratch_bytes": stats["tile_scratch_bytes"], "units_per_step": stats["units"], "tile_groups": stats["tile_groups"],
+                          "tile_fallback_steps": int(fallbacks), "index_generation_s": round(shard.gen_s, 2), "host": hinfo}
         line = {"metric": "queries/sec", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * dt_value / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config, "roofline": roofline, "clocks": clocks,
+                "dtype": "f32", "data": "synthetic", "config": config, "workload_stats": workload_stats, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1000.0 * dt_e2e / args.steps},
                 "gpu_launches": int(launches)}
+        if args.parity_queries and parity_rows is not None:
+            line["parity"] = parity_check(wl, dens, args.seed, batches[0][:args.parity_queries], parity_rows, host_threads)
+            line["parity"]["rows_from"] = "the first timed e2e step (tq_search_batch)" if world == 1 else f"rank 0's merged rows of the first timed e2e step ({world} ranks)"
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or min(512, max(64, 4 * host_threads))
             # bounded: a few seconds per step; several queries per host thread keep the threads busy
-            qps, ms = cpu_reference_run(wl, shard, batches, 2, 1, sample, host_threads)
-            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": host_threads, "kind": "port",
+            qps, ms_c = cpu_reference_run(wl, shard, batches, 2, 1, sample, host_threads)
+            line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": host_threads, "kind": "port", "host": hinfo,
                                     "sample": f"3 x {sample} queries of the same stream (1 warm-up), all host threads, oracle/ "
                                               "restatement of tantivy's Block-WAND + TopNHeap + merge_top_k (mode=1)",
-                                    "ms_per_sample": ms}
+                                    "ms_per_sample": ms_c}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

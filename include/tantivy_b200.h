@@ -44,6 +44,11 @@ extern "C" {
 #define TQ_OP_TERM 0
 #define TQ_OP_AND 1
 #define TQ_OP_OR 2
+/* PhraseQuery without slop (PhraseWeight / PhraseScorer, src/query/phrase_query/phrase_scorer.rs:349-589): docs that hold
+ * every term, at positions that line up with the terms' offsets in the phrase; score = bm25(fieldnorm, phrase_count)
+ * under ONE Bm25Weight for the whole phrase (Bm25Weight::for_terms: the idfs add up, bm25.rs:95-129).  Needs a field
+ * indexed WithFreqsAndPositions and its `.pos` bytes (tq_segment_register_positions). */
+#define TQ_OP_PHRASE 3
 
 /* TERMINATED sentinel of src/docset.rs:12 */
 #define TQ_TERMINATED 0x7FFFFFFFu
@@ -51,6 +56,8 @@ extern "C" {
 #define TQ_MAX_K 1024u
 /* Largest number of clauses in one query on the device path. */
 #define TQ_MAX_TERMS 32u
+/* Largest number of terms in a phrase on the device path. */
+#define TQ_MAX_PHRASE_TERMS 8u
 
 typedef struct tq_ctx tq_ctx;
 typedef struct tq_batch tq_batch;
@@ -68,6 +75,13 @@ typedef struct {
   uint64_t postings_start;
   uint64_t postings_end;
 } tq_term_seg;
+
+/* TermInfo::positions_range of one (clause, segment) (src/postings/term_info.rs:9-16): byte range of the term's position
+ * stream inside the field's `.pos` sub-file (layout: src/positions/mod.rs:22-28).  Only read for TQ_OP_PHRASE. */
+typedef struct {
+  uint64_t positions_start;
+  uint64_t positions_end;
+} tq_term_pos;
 
 /* One query = one `Weight` (built once for all segments, searcher.rs:226).
  * weight[i]        = Bm25Weight.weight = idf * (1 + K1) * boost        (bm25.rs:141-151)
@@ -95,6 +109,13 @@ typedef struct {
   const uint8_t* term_flags;
   uint32_t flags;
   float threshold;
+  /* TQ_OP_PHRASE only (NULL / 0 otherwise): term_pos[i] belongs to term_segs[i]; term_offset[t] = position of clause t
+   * inside the phrase (PhraseQuery::new_with_offset, phrase_query.rs); weight[0] / avg_fieldnorm[0] (or the first
+   * tf_cache table) describe the phrase's single Bm25Weight, the other entries are ignored; slop must be 0. */
+  const tq_term_pos* term_pos;
+  const uint32_t* term_offset;
+  uint32_t slop;
+  uint32_t reserved;
 } tq_query;
 
 /* Counters of the last finished batch (per ctx). */
@@ -122,10 +143,12 @@ typedef struct {
   uint64_t units_or_strip; /* of units_or: CTAs of the barrier-free strip kernel (k_or_strip); the rest ran k_or / k_or_pipe */
   /* shared-decode tile engine (k_score_lists + k_tile, csrc/tq_tile.cuh) */
   float score_ms, tile_ms, theta_ms;  /* device time of k_score_lists / all k_tile launches / the k_theta passes of the batch */
-  uint32_t pad0;
+  float phrase_ms;                    /* device time of k_phrase */
   uint64_t units_tile;          /* CTAs of k_tile over all its launches */
+  uint64_t units_phrase;        /* CTAs of k_phrase */
   uint64_t tile_groups;         /* query groups evaluated together (one decode-and-score pass each) */
   uint64_t tile_postings;       /* postings decoded and scored by k_score_lists (every distinct list once) */
+  uint64_t tile_list_bytes;     /* bytes of those lists' postings ranges (skip data + packed blocks + VInt tails) */
   uint64_t tile_scratch_bytes;  /* HBM scratch of the pair arrays, tile indexes and samples */
   uint64_t tile_fallbacks;      /* 1 if the run overflowed a tile engine buffer and was repeated on the per-query kernels */
   uint64_t tile_counters[8];    /* cumulative, with TQ_TILE_COUNTERS=1: (query, tile) pairs seen / skipped / light / heavy,
@@ -150,6 +173,9 @@ int tq_segment_register(tq_ctx*, uint32_t segment_ord, uint32_t field, uint32_t 
                         int record_option, const uint8_t* idx_body, size_t idx_len,
                         const uint8_t* fieldnorm, size_t fieldnorm_len,
                         const uint8_t* alive_bitset, size_t alive_len);
+/* The `.pos` sub-file of a registered (segment, field) with record_option TQ_RECORD_FREQS_POSITIONS (copied to HBM):
+ * what SegmentReader::inverted_index hands to PositionReader (src/positions/reader.rs:43-55).  Needed by TQ_OP_PHRASE. */
+int tq_segment_register_positions(tq_ctx*, uint32_t segment_ord, uint32_t field, const uint8_t* pos_body, size_t pos_len);
 int tq_segment_unregister(tq_ctx*, uint32_t segment_ord, uint32_t field);
 
 /* ---- search -------------------------------------------------------------------------- */
@@ -214,6 +240,34 @@ int tq_merge_topk_dev(tq_ctx*, uint32_t n_lists, uint32_t nq, uint32_t stride, u
                       const uint32_t* doc_dev, const uint32_t* count_dev, float* out_scores_dev,
                       uint32_t* out_segment_ord_dev, uint32_t* out_doc_dev,
                       uint32_t* out_count_dev);
+
+/* The same for sharded callers that move ONE buffer per shard: packed = [nq*stride scores | nq*stride segment ords |
+ * nq*stride docs | nq counts] as 32-bit words (tq_batch_results_pack_dev writes it with stride = k_max of the batch),
+ * n_lists of them pitch_words apart -- what one all-gather of the shards' buffers produces.  The merge is enqueued on
+ * cuda_stream (a cudaStream_t, e.g. tq_batch_stream's) and does not synchronise with the host. */
+int tq_batch_results_pack_dev(tq_batch*, uint32_t* packed_dev);
+int tq_merge_topk_packed_dev(tq_ctx*, void* cuda_stream, uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k,
+                             const uint32_t* packed_dev, size_t pitch_words, uint32_t* out_packed_dev);
+
+/* ---- several GPUs behind one handle --------------------------------------------------- */
+/* The reference fans a search out over segments inside ONE process (Executor::map, src/core/executor.rs:60-100;
+ * Searcher::search_with_executor, src/core/searcher.rs:220-237).  tq_multi is that shape for GPUs: one tq_ctx per
+ * device, every (segment, field) lives on one of them (device_index -1 = the least loaded), tq_multi_search_batch runs
+ * the devices' shares concurrently (one host thread per device), exchanges the exact k-th best score keys between the
+ * phases -- every device prunes like a single device holding all segments -- and merges the rows on the host
+ * (merge_fruits, sort_key_top_collector.rs:54-95).  Same arguments and result layout as tq_search_batch. */
+typedef struct tq_multi tq_multi;
+int tq_multi_create(const int* devices, int n_devices, tq_multi** out);
+void tq_multi_destroy(tq_multi*);
+const char* tq_multi_last_error(tq_multi*);
+int tq_multi_num_devices(tq_multi*);
+int tq_multi_segment_register(tq_multi*, int device_index, uint32_t segment_ord, uint32_t field, uint32_t max_doc,
+                              int record_option, const uint8_t* idx_body, size_t idx_len,
+                              const uint8_t* fieldnorm, size_t fieldnorm_len,
+                              const uint8_t* alive_bitset, size_t alive_len);
+int tq_multi_search_batch(tq_multi*, const tq_query* queries, size_t nq, uint32_t out_stride,
+                          float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc,
+                          uint32_t* out_count);
 
 /* ---- codec-level access (parity tests and the decode micro-benchmark) ----------------- */
 /* Decodes one whole posting list on the device (BlockSegmentPostings::open + advance loop,

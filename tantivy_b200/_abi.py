@@ -9,7 +9,7 @@ import numpy as np
 
 TQ_OK = 0
 TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS = 0, 1, 2
-TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR = 0, 1, 2
+TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR, TQ_OP_PHRASE = 0, 1, 2, 3
 TERMINATED = 0x7FFFFFFF
 TQ_MAX_K = 1024
 TQ_MAX_TERMS = 32
@@ -41,6 +41,14 @@ TERM_SEG_DTYPE = np.dtype(
 assert TERM_SEG_DTYPE.itemsize == C.sizeof(TermSeg) == 32
 
 
+class TermPos(C.Structure):
+    """tq_term_pos — TermInfo::positions_range of one (clause, segment)."""
+    _fields_ = [("positions_start", C.c_uint64), ("positions_end", C.c_uint64)]
+
+
+TERM_POS_DTYPE = np.dtype([("positions_start", "<u8"), ("positions_end", "<u8")])
+
+
 class Query(C.Structure):
     """tq_query — one Weight for all segments (src/core/searcher.rs:226)."""
     _fields_ = [
@@ -55,15 +63,19 @@ class Query(C.Structure):
         ("term_flags", u8p),
         ("flags", C.c_uint32),
         ("threshold", C.c_float),
+        ("term_pos", C.POINTER(TermPos)),
+        ("term_offset", u32p),
+        ("slop", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 
 QUERY_DTYPE = np.dtype(
     [("op", "<i4"), ("n_terms", "<u4"), ("k", "<u4"), ("n_term_segs", "<u4"),
      ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8"), ("term_flags", "<u8"),
-     ("flags", "<u4"), ("threshold", "<f4")]
+     ("flags", "<u4"), ("threshold", "<f4"), ("term_pos", "<u8"), ("term_offset", "<u8"), ("slop", "<u4"), ("reserved", "<u4")]
 )
-assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 64
+assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 88
 
 
 class Stats(C.Structure):
@@ -94,10 +106,12 @@ class Stats(C.Structure):
         ("score_ms", C.c_float),
         ("tile_ms", C.c_float),
         ("theta_ms", C.c_float),
-        ("pad0", C.c_uint32),
+        ("phrase_ms", C.c_float),
         ("units_tile", C.c_uint64),
+        ("units_phrase", C.c_uint64),
         ("tile_groups", C.c_uint64),
         ("tile_postings", C.c_uint64),
+        ("tile_list_bytes", C.c_uint64),
         ("tile_scratch_bytes", C.c_uint64),
         ("tile_fallbacks", C.c_uint64),
         ("tile_counters", C.c_uint64 * 8),
@@ -118,7 +132,9 @@ class QueryBatch:
       op, k, weights[n_terms], avg_fieldnorm[n_terms], term_segs: list of
       (term_idx, segment_ord, field, doc_freq, postings_start, postings_end),
       tf_cache (optional [n_terms,256]), term_flags (optional [n_terms] bytes, TQ_TERM_IGNORE_FREQ),
-      threshold (optional float: only docs scoring above it are collected).
+      threshold (optional float: only docs scoring above it are collected),
+      phrase queries (op TQ_OP_PHRASE): term_pos = list of (positions_start, positions_end) parallel to term_segs,
+      term_offset = [n_terms] offsets in the phrase, slop (optional, must be 0 on the device path).
     Built with numpy so that a batch of thousands of queries marshals in milliseconds.
     """
 
@@ -167,6 +183,18 @@ class QueryBatch:
             if q.get("threshold") is not None:
                 row["flags"] = TQ_QUERY_HAS_THRESHOLD
                 row["threshold"] = q["threshold"]
+            tpos = q.get("term_pos")
+            if tpos is not None:
+                tp = np.zeros(max(len(tpos), 1), dtype=TERM_POS_DTYPE)
+                if len(tpos):
+                    blockp = np.asarray(tpos, dtype=np.uint64).reshape(-1, 2)
+                    tp["positions_start"][:len(tpos)] = blockp[:, 0]
+                    tp["positions_end"][:len(tpos)] = blockp[:, 1]
+                toff = np.ascontiguousarray(q["term_offset"], dtype=np.uint32).reshape(nt)
+                self.caches += [tp, toff]
+                row["term_pos"] = tp.ctypes.data
+                row["term_offset"] = toff.ctypes.data
+                row["slop"] = int(q.get("slop", 0))
             flags = q.get("term_flags")
             if flags is not None:
                 flags = np.ascontiguousarray(flags, dtype=np.uint8).reshape(nt)

@@ -22,6 +22,7 @@
 #include "bm25_host.hpp"
 #include "segment_writer.hpp"
 #include "tq_tile.cuh"
+#include "tq_phrase.cuh"
 
 using namespace tq;
 
@@ -107,6 +108,10 @@ struct Segment {
   uint8_t* d_fieldnorm = nullptr;
   uint8_t* d_alive = nullptr;
   Arena arena;  // block tables + aligned block copies of this segment's posting lists; freed with the segment
+  uint8_t* d_pos = nullptr;  // the field's `.pos` sub-file (phrase queries), padded
+  size_t pos_len = 0;
+  uint8_t* d_pos_pool = nullptr;  // position tables of this segment's terms, bump-allocated by k_build_pos_tables
+  size_t pos_pool_cap = 0;        // (the first 8 bytes of the pool are the cursor)
 };
 
 uint32_t env_u32(const char* name, uint32_t def) {
@@ -125,6 +130,10 @@ struct tq_ctx {
   uint32_t lists_cap = 0, n_lists = 0;
   std::unordered_map<ListKey, uint32_t, ListKeyHash> list_cache;
   std::vector<uint32_t> free_ids;  // list ids of unregistered segments (and of rolled-back builds), reused first
+  PosDesc* d_pos_descs = nullptr;  // position tables (phrase queries), same life cycle as the block tables
+  uint32_t pos_cap = 0, n_pos = 0;
+  std::unordered_map<ListKey, uint32_t, ListKeyHash> pos_cache;  // (segment, field, positions_start) -> pos id
+  std::vector<uint32_t> free_pos_ids;
   cudaStream_t build_stream = nullptr;
   PinBuf build_pin;
   DevBuf build_dev;
@@ -132,7 +141,8 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;  // [0..8) k_or / k_or_strip window routes, [8..16) k_tile diagnostics
-  uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 32, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 24, tile_counters = 0;
+  uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 32, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
+  uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 24, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
@@ -145,6 +155,8 @@ struct OwnedQueries {
   std::vector<tq_term_seg> ts;
   std::vector<float> w, avg, cache;
   std::vector<uint8_t> flags;
+  std::vector<tq_term_pos> tp;
+  std::vector<uint32_t> toff;
 };
 
 struct tq_batch {
@@ -173,8 +185,9 @@ struct tq_batch {
   BatchParams params{};
   size_t desc_bytes = 0;
   uint32_t nq = 0, kmax = 0;
-  uint32_t n_units[7] = {0, 0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold rounds 1..3
-  uint32_t unit_base[7] = {0, 0, 0, 0, 0, 0, 0};
+  uint32_t n_units[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold rounds 1..3, phrase
+  uint32_t unit_base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const PhraseAux* phrase_aux = nullptr;  // device: per clause of the batch's phrase queries (parallel to qlists)
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
   size_t qinit_off = 0;
@@ -234,8 +247,9 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_sample_div = env_u32("TQ_TILE_SAMPLE_DIV", 32);    // share of the tiles in the sample launch (0/1: none)
   c->tile_round_div1 = env_u32("TQ_TILE_ROUND_DIV1", 8);     // the exact launches end at 1/8, 1/2 and all of a segment's tiles
   c->tile_round_div2 = env_u32("TQ_TILE_ROUND_DIV2", 2);
-  c->tile_light_max = env_u32("TQ_TILE_LIGHT_MAX", 24);      // essential postings up to which a (query, tile) is one thread's work
+  c->tile_light_max = env_u32("TQ_TILE_LIGHT_MAX", 96);      // essential postings up to which a (query, tile) pair is evaluated posting by posting
   c->tile_counters = env_u32("TQ_TILE_COUNTERS", 0);         // diagnostics (tile_counters of tq_stats)
+  c->tile_ops = env_u32("TQ_TILE_OPS", 7);                  // bit 0 term, 1 AND, 2 OR
   c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 8192);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
   c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
   c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
@@ -243,13 +257,17 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMemset(c->d_lists, 0, (size_t)c->lists_cap * sizeof(ListDesc));
+  c->pos_cap = env_u32("TQ_MAX_POS_LISTS", 1u << 18);
+  if (err == cudaSuccess) err = cudaMalloc(&c->d_pos_descs, (size_t)c->pos_cap * sizeof(PosDesc));
+  if (err == cudaSuccess) err = cudaMemset(c->d_pos_descs, 0, (size_t)c->pos_cap * sizeof(PosDesc));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_phrase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phrase_smem_bytes());
   if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kOrDynSmem);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pipe_smem_bytes());
   if (err == cudaSuccess) err = cudaFuncSetAttribute(k_or_strip, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)strip_smem_bytes(kMaxCached));
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes(kTileMaxPairs, kTileMaxSlots));
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (err != cudaSuccess) { delete c; return fail(TQ_ERR_CUDA, cudaGetErrorString(err)); }
   *out = c;
   return TQ_OK;
@@ -277,8 +295,10 @@ void tq_ctx_destroy(tq_ctx* c) {
   for (auto* b : c->pool) tq_batch_destroy_real(b);
   for (auto& kv : c->segments) {
     cudaFree(kv.second.d_idx); cudaFree(kv.second.d_fieldnorm); cudaFree(kv.second.d_alive);
+    cudaFree(kv.second.d_pos); cudaFree(kv.second.d_pos_pool);
     kv.second.arena.release();
   }
+  cudaFree(c->d_pos_descs);
   c->build_pin.release(); c->build_dev.release();
   if (c->build_stream) cudaStreamDestroy(c->build_stream);
   cudaFree(c->d_lists);
@@ -335,6 +355,33 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
   return TQ_OK;
 }
 
+int tq_segment_register_positions(tq_ctx* c, uint32_t segment_ord, uint32_t field, const uint8_t* pos_body, size_t pos_len) {
+  if (!c || (!pos_body && pos_len)) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> g(c->mu);
+  auto it = c->segments.find({segment_ord, field});
+  if (it == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "segment/field not registered");
+  Segment& s = it->second;
+  if (s.record_option != TQ_RECORD_FREQS_POSITIONS) return fail(TQ_ERR_INVALID_ARGUMENT, "the field was not indexed with positions");
+  if (s.d_pos) return fail(TQ_ERR_INVALID_ARGUMENT, "positions already registered");
+  // table pool: 4 bytes per position block (<= 1 per 16 bytes of `.pos`), 8 per posting block, 512 + slack per term that is
+  // ever queried as part of a phrase
+  const size_t pool = pos_len / 4 + s.idx_len / 8 + (4u << 20);
+  uint8_t *d_pos = nullptr, *d_pool = nullptr;
+  cudaError_t e = cudaMalloc(&d_pos, pos_len + 256);
+  if (e == cudaSuccess) e = cudaMemset(d_pos + pos_len, 0, 256);
+  if (e == cudaSuccess && pos_len) e = cudaMemcpy(d_pos, pos_body, pos_len, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&d_pool, pool);
+  if (e == cudaSuccess) e = cudaMemset(d_pool, 0, 64);
+  if (e == cudaSuccess) {
+    const unsigned long long first = 64;  // the cursor lives in the pool's first word; tables start behind it
+    e = cudaMemcpy(d_pool, &first, 8, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) { cudaFree(d_pos); cudaFree(d_pool); return fail(TQ_ERR_CUDA, std::string("positions upload: ") + cudaGetErrorString(e)); }
+  s.d_pos = d_pos; s.pos_len = pos_len; s.d_pos_pool = d_pool; s.pos_pool_cap = pool;
+  return TQ_OK;
+}
+
 int tq_segment_unregister(tq_ctx* c, uint32_t segment_ord, uint32_t field) {
   if (!c) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
   cudaSetDevice(c->device);
@@ -343,6 +390,9 @@ int tq_segment_unregister(tq_ctx* c, uint32_t segment_ord, uint32_t field) {
   if (it == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "segment/field not registered");
   cudaDeviceSynchronize();
   cudaFree(it->second.d_idx); cudaFree(it->second.d_fieldnorm); cudaFree(it->second.d_alive);
+  cudaFree(it->second.d_pos); cudaFree(it->second.d_pos_pool);
+  for (auto pi = c->pos_cache.begin(); pi != c->pos_cache.end();)
+    if (pi->first.segment_ord == segment_ord && pi->first.field == field) { c->free_pos_ids.push_back(pi->second); pi = c->pos_cache.erase(pi); } else ++pi;
   it->second.arena.release();  // the segment's block tables and aligned block copies go with it ...
   c->segments.erase(it);
   for (auto li = c->list_cache.begin(); li != c->list_cache.end();)
@@ -447,6 +497,76 @@ int flush_builds(tq_ctx* c, std::vector<PendingBuild>& pending, uint64_t* built)
   return TQ_OK;
 }
 
+struct PendingPos { PosJob job; ListKey key; };
+
+void rollback_pos(tq_ctx* c, std::vector<PendingPos>& pending) {
+  for (auto& pp : pending) {
+    auto it = c->pos_cache.find(pp.key);
+    if (it != c->pos_cache.end() && it->second == pp.job.pos_id) c->pos_cache.erase(it);
+    c->free_pos_ids.push_back(pp.job.pos_id);
+  }
+  pending.clear();
+}
+struct PendingPosScope {
+  tq_ctx* c;
+  std::vector<PendingPos>& pending;
+  ~PendingPosScope() { if (!pending.empty()) rollback_pos(c, pending); }
+};
+
+// The position table of one (term, segment): cached, or scheduled.  ctx->mu held.
+int get_pos(tq_ctx* c, const tq_term_seg& ts, const tq_term_pos& tp, std::vector<PendingPos>& pending, uint32_t* pos_id) {
+  auto sit = c->segments.find({ts.segment_ord, ts.field});
+  if (sit == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "term_seg names a segment/field that is not registered");
+  Segment& seg = sit->second;
+  if (!seg.d_pos) return fail(TQ_ERR_INVALID_ARGUMENT, "phrase query on a segment without registered positions (tq_segment_register_positions)");
+  if (tp.positions_end < tp.positions_start || tp.positions_end > seg.pos_len) return fail(TQ_ERR_INVALID_ARGUMENT, "positions range outside the `.pos` body");
+  if (tp.positions_end - tp.positions_start > 0xFFFFFFFFull) return fail(TQ_ERR_UNSUPPORTED, "position stream larger than 4 GiB");
+  const ListKey key{ts.segment_ord, ts.field, tp.positions_start ^ (ts.postings_start << 1) ^ (1ull << 62)};
+  auto it = c->pos_cache.find(key);
+  if (it != c->pos_cache.end()) { *pos_id = it->second; return TQ_OK; }
+  if (c->free_pos_ids.empty() && c->n_pos >= c->pos_cap) return fail(TQ_ERR_OOM, "position table cache full (TQ_MAX_POS_LISTS)");
+  PendingPos pp;
+  pp.job.pos_bytes = seg.d_pos + tp.positions_start;
+  pp.job.pos_len = (uint32_t)(tp.positions_end - tp.positions_start);
+  pp.job.list_bytes = seg.d_idx + 8 + ts.postings_start;
+  pp.job.list_len = (uint32_t)(ts.postings_end - ts.postings_start);
+  pp.job.doc_freq = ts.doc_freq;
+  pp.job.pool = seg.d_pos_pool;
+  pp.job.pool_cursor = reinterpret_cast<unsigned long long*>(seg.d_pos_pool);
+  pp.job.pool_cap = seg.pos_pool_cap;
+  if (!c->free_pos_ids.empty()) { pp.job.pos_id = c->free_pos_ids.back(); c->free_pos_ids.pop_back(); }
+  else pp.job.pos_id = c->n_pos++;
+  pp.key = key;
+  *pos_id = pp.job.pos_id;
+  c->pos_cache.emplace(key, *pos_id);
+  pending.push_back(pp);
+  return TQ_OK;
+}
+
+int flush_pos_builds(tq_ctx* c, std::vector<PendingPos>& pending) {
+  if (pending.empty()) return TQ_OK;
+  const size_t n = pending.size();
+  struct Fail { tq_ctx* c; std::vector<PendingPos>& p; bool ok = false; ~Fail() { if (!ok) rollback_pos(c, p); } } guard{c, pending};
+  TQ_CUDA(c->build_pin.ensure(n * (sizeof(PosJob) + 4)));
+  TQ_CUDA(c->build_dev.ensure(n * (sizeof(PosJob) + 4)));
+  PosJob* hj = reinterpret_cast<PosJob*>(c->build_pin.p);
+  uint32_t* hs = reinterpret_cast<uint32_t*>(c->build_pin.p + n * sizeof(PosJob));
+  for (size_t i = 0; i < n; ++i) { hj[i] = pending[i].job; hs[i] = 1; }
+  uint32_t* ds = reinterpret_cast<uint32_t*>(c->build_dev.p + n * sizeof(PosJob));
+  TQ_CUDA(cudaMemcpyAsync(c->build_dev.p, c->build_pin.p, n * (sizeof(PosJob) + 4), cudaMemcpyHostToDevice, c->build_stream));
+  k_build_pos_tables<<<(unsigned)n, kThreads, 0, c->build_stream>>>(reinterpret_cast<const PosJob*>(c->build_dev.p), c->d_pos_descs, ds);
+  TQ_CUDA(cudaGetLastError());
+  TQ_CUDA(cudaMemcpyAsync(hs, ds, n * 4, cudaMemcpyDeviceToHost, c->build_stream));
+  TQ_CUDA(cudaStreamSynchronize(c->build_stream));
+  for (size_t i = 0; i < n; ++i) {
+    if (hs[i] == 2) return fail(TQ_ERR_OOM, "the segment's position-table pool is exhausted");
+    if (hs[i] != 0) return fail(TQ_ERR_CORRUPT, "position bytes are not a valid tantivy position stream");
+  }
+  guard.ok = true;
+  pending.clear();
+  return TQ_OK;
+}
+
 struct CacheKey {
   std::vector<float> table;
 };
@@ -455,7 +575,7 @@ struct CacheKey {
 
 // ---- batches ---------------------------------------------------------------------------------------
 // Kernel time by kind: CUDA events recorded on the batch's stream around every launch (group of launches) of that kind.
-enum SpanKind { SPAN_TERM = 0, SPAN_AND, SPAN_OR, SPAN_FINAL, SPAN_SCORE, SPAN_TILE, SPAN_THETA, SPAN_KINDS };
+enum SpanKind { SPAN_TERM = 0, SPAN_AND, SPAN_OR, SPAN_FINAL, SPAN_SCORE, SPAN_TILE, SPAN_THETA, SPAN_PHRASE, SPAN_KINDS };
 
 static int span_begin(tq_batch* b, int kind) {
   if (b->n_spans == b->spans.size()) {
@@ -486,6 +606,7 @@ static void collect_times(tq_batch* b) {
   b->stats.score_ms = by_kind[SPAN_SCORE];
   b->stats.tile_ms = by_kind[SPAN_TILE];
   b->stats.theta_ms = by_kind[SPAN_THETA];
+  b->stats.phrase_ms = by_kind[SPAN_PHRASE];
 }
 
 static tq_batch* acquire_batch(tq_ctx* c) {
@@ -510,7 +631,9 @@ namespace {
 struct SegPlan {
   uint32_t segment_ord = 0;
   const Segment* seg = nullptr;
-  std::vector<std::pair<uint32_t, QList>> here;  // (doc_freq, clause)
+  struct Clause { uint32_t first; QList second; uint32_t range_len; };  // doc_freq, clause, bytes of its postings range
+  std::vector<Clause> here;
+  std::vector<uint32_t> term_idx;  // clause ordinals in arrival order (phrases: before `here` is sorted)
   const uint8_t* fn0 = nullptr;
   bool uniform_fn = true, prunable = false;
 };
@@ -529,6 +652,7 @@ struct TileGroupBuild {
   std::vector<SegB> segs;
   std::unordered_map<uint32_t, uint32_t> seg_of;  // segment_ord -> index in segs
   uint64_t pairs = 0;                              // elements of the pair arrays (doc_freq rounded up to 128 per slot)
+  uint64_t list_bytes = 0;                         // postings-range bytes of the distinct lists
 };
 
 uint64_t slot_hash(uint32_t list_id, float w, uint32_t cache) {
@@ -538,9 +662,10 @@ uint64_t slot_hash(uint32_t list_id, float w, uint32_t cache) {
 }
 
 // Would the group still satisfy k_tile's limits with this query added?  Returns the number of NEW pair elements, or -1.
-int64_t tile_admit_cost(const TileGroupBuild& g, const std::vector<SegPlan>& plans, uint32_t max_dens_x1000) {
+int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
   int64_t new_pairs = 0;
-  for (const SegPlan& sp : plans) {
+  for (size_t pi = 0; pi < n_plans; ++pi) {
+    const SegPlan& sp = plans[pi];
     auto it = g.seg_of.find(sp.segment_ord);
     const TileGroupBuild::SegB* sb = it == g.seg_of.end() ? nullptr : &g.segs[it->second];
     if (sb && sb->queries.size() + 1 > kTileMaxQueries) return -1;
@@ -568,8 +693,26 @@ int64_t tile_admit_cost(const TileGroupBuild& g, const std::vector<SegPlan>& pla
   return new_pairs;
 }
 
-void tile_admit(TileGroupBuild& g, uint32_t query, int op, const std::vector<SegPlan>& plans) {
-  for (const SegPlan& sp : plans) {
+// Cheap sufficient test (every clause counted as a new list): most queries pass it and skip the exact cost.
+bool tile_admit_surely_fits(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
+  for (size_t pi = 0; pi < n_plans; ++pi) {
+    const SegPlan& sp = plans[pi];
+    auto it = g.seg_of.find(sp.segment_ord);
+    const TileGroupBuild::SegB* sb = it == g.seg_of.end() ? nullptr : &g.segs[it->second];
+    if (sb && sb->queries.size() + 1 > kTileMaxQueries) return false;
+    double dens = sb ? sb->dens : 0.0;
+    for (auto& h : sp.here) dens += (double)h.first / std::max(1u, sp.seg->max_doc);
+    if ((sb ? sb->slots.size() : 0) + sp.here.size() > kTileMaxSlots) return false;
+    if (dens * kTile * 1.5 + 256.0 > (double)kTileMaxPairs || (max_dens_x1000 && dens * 1000.0 > max_dens_x1000)) return false;
+  }
+  return true;
+}
+
+// Adds the query to the group; returns the number of new pair elements it brought.
+uint64_t tile_admit(TileGroupBuild& g, uint32_t query, int op, const SegPlan* plans, size_t n_plans) {
+  const uint64_t pairs_before = g.pairs;
+  for (size_t pi = 0; pi < n_plans; ++pi) {
+    const SegPlan& sp = plans[pi];
     auto it = g.seg_of.find(sp.segment_ord);
     if (it == g.seg_of.end()) {
       it = g.seg_of.emplace(sp.segment_ord, (uint32_t)g.segs.size()).first;
@@ -602,11 +745,13 @@ void tile_admit(TileGroupBuild& g, uint32_t query, int op, const std::vector<Seg
         cands.push_back(slot);
         sb.dens += (double)h.first / std::max(1u, sp.seg->max_doc);
         g.pairs += ((uint64_t)h.first + 127) / 128 * 128;
+        g.list_bytes += h.range_len;
       }
       sb.clauses.push_back((uint16_t)slot);
     }
     sb.queries.push_back(tq);
   }
+  return g.pairs - pairs_before;
 }
 
 }  // namespace
@@ -649,7 +794,9 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
 
   std::vector<QList> qlists;
   std::vector<QSeg> qsegs;
-  std::vector<Unit> units[7];
+  std::vector<Unit> units[8];
+  std::vector<PhraseAux> qaux;  // parallel to qlists once a phrase query shows up
+  std::vector<PendingPos> pending_pos;
   std::vector<DQuery> dq(nq);
   std::vector<float> caches;  // n_caches * 256
   std::unordered_map<uint32_t, uint32_t> cache_by_avg;  // avg bits -> cache idx
@@ -670,18 +817,26 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   {
     std::lock_guard<std::mutex> g(c->mu);
     PendingScope pending_scope{c, pending};  // an early error return leaves no half-built list in the cache
+    PendingPosScope pending_pos_scope{c, pending_pos};
     std::vector<const tq_term_seg*> order;
-    std::vector<SegPlan> plans;
+    std::vector<SegPlan> plans;  // reused from query to query (n_plans live entries)
+    uint32_t last_avg_bits = 0, last_avg_idx = 0xFFFFFFFFu;
     for (size_t qi = 0; qi < nq; ++qi) {
       const tq_query& q = queries[qi];
       if (q.k == 0 || q.k > TQ_MAX_K) return fail(TQ_ERR_INVALID_ARGUMENT, "k must be in 1..TQ_MAX_K");
       if (q.n_terms == 0 || q.n_terms > TQ_MAX_TERMS) return fail(TQ_ERR_INVALID_ARGUMENT, "n_terms must be in 1..TQ_MAX_TERMS");
-      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
+      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR && q.op != TQ_OP_PHRASE) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
       if (q.op == TQ_OP_TERM && q.n_terms != 1) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_TERM takes one term");
       if (!q.weight || (!q.avg_fieldnorm && !q.tf_cache) || (!q.term_segs && q.n_term_segs)) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
+      const bool is_phrase = q.op == TQ_OP_PHRASE;
+      if (is_phrase) {
+        if (q.n_terms < 2 || q.n_terms > TQ_MAX_PHRASE_TERMS) return fail(TQ_ERR_UNSUPPORTED, "a phrase takes 2..TQ_MAX_PHRASE_TERMS terms on the device path");
+        if (q.slop != 0) return fail(TQ_ERR_UNSUPPORTED, "phrase slop stays on the reference's CPU path");
+        if ((!q.term_pos && q.n_term_segs) || !q.term_offset) return fail(TQ_ERR_INVALID_ARGUMENT, "a phrase needs term_pos and term_offset");
+      }
       kmax = std::max(kmax, q.k);
       alg_bytes += 12ull * q.k;
-      op_bytes[q.n_terms == 1 ? TQ_OP_TERM : q.op] += 12ull * q.k;
+      op_bytes[is_phrase ? TQ_OP_AND : (q.n_terms == 1 ? TQ_OP_TERM : q.op)] += 12ull * q.k;
       // tf-norm tables of this query's clauses
       uint32_t cache_idx[TQ_MAX_TERMS];
       for (uint32_t t = 0; t < q.n_terms; ++t) {
@@ -691,6 +846,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         } else {
           uint32_t bits;
           memcpy(&bits, &q.avg_fieldnorm[t], 4);
+          if (bits == last_avg_bits && last_avg_idx != 0xFFFFFFFFu) { cache_idx[t] = last_avg_idx; continue; }  // (nearly always the same field)
           auto it = cache_by_avg.find(bits);
           if (it == cache_by_avg.end()) {
             float tab[256];
@@ -699,10 +855,11 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
             caches.insert(caches.end(), tab, tab + 256);
           }
           cache_idx[t] = it->second;
+          last_avg_bits = bits; last_avg_idx = it->second;
         }
       }
       // effective shape: an AND / OR of one clause is that clause (boolean_weight.rs:57-68, block_wand_union.rs:154-157)
-      const int op = q.n_terms == 1 ? TQ_OP_TERM : q.op;
+      const int op = is_phrase ? TQ_OP_PHRASE : (q.n_terms == 1 ? TQ_OP_TERM : q.op);
       dq[qi].k = q.k;
       dq[qi].op = (uint32_t)op;
       // group the (clause, segment) lists by segment
@@ -714,7 +871,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       std::stable_sort(order.begin(), order.end(), [](const tq_term_seg* a, const tq_term_seg* b) {
         return a->segment_ord != b->segment_ord ? a->segment_ord < b->segment_ord : a->term_idx < b->term_idx;
       });
-      plans.clear();
+      size_t n_plans = 0;
       uint64_t q_postings = 0;
       for (size_t i = 0; i < order.size();) {
         size_t j = i;
@@ -724,46 +881,62 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         bool dup = false;
         for (size_t a = i + 1; a < j; ++a) dup |= order[a]->term_idx == order[a - 1]->term_idx;
         if (dup) return fail(TQ_ERR_INVALID_ARGUMENT, "duplicate (term_idx, segment_ord)");
-        if (op == TQ_OP_AND && n_here != q.n_terms) { i = j; continue; }  // a clause is absent: empty intersection
-        plans.emplace_back();
-        SegPlan& sp = plans.back();
+        if ((op == TQ_OP_AND || op == TQ_OP_PHRASE) && n_here != q.n_terms) { i = j; continue; }  // a clause is absent: empty intersection
+        if (n_plans == plans.size()) plans.emplace_back();
+        SegPlan& sp = plans[n_plans++];
+        sp.here.clear();
+        sp.term_idx.clear();
+        sp.uniform_fn = true;
         sp.segment_ord = order[i]->segment_ord;
         for (size_t a = i; a < j; ++a) {
           uint32_t id;
           int rc = get_list(c, *order[a], q.term_flags && (q.term_flags[order[a]->term_idx] & TQ_TERM_IGNORE_FREQ), pending, &id, &sp.seg);
           if (rc != TQ_OK) return rc;
           if (a == i) sp.fn0 = sp.seg->d_fieldnorm; else sp.uniform_fn &= (sp.seg->d_fieldnorm == sp.fn0);
-          QList ql{id, q.weight[order[a]->term_idx], cache_idx[order[a]->term_idx], 0};
-          sp.here.push_back({order[a]->doc_freq, ql});
+          QList ql{id, q.weight[is_phrase ? 0 : order[a]->term_idx], cache_idx[is_phrase ? 0 : order[a]->term_idx], 0};
+          if (is_phrase) {  // the clause's position table; QList.pad carries its id to the aux array below
+            if (sp.seg->record_option != TQ_RECORD_FREQS_POSITIONS) return fail(TQ_ERR_INVALID_ARGUMENT, "phrase query on a field without positions");
+            rc = get_pos(c, *order[a], q.term_pos[order[a] - q.term_segs], pending_pos, &ql.pad);
+            if (rc != TQ_OK) return rc;
+          }
+          sp.here.push_back(SegPlan::Clause{order[a]->doc_freq, ql, (uint32_t)(order[a]->postings_end - order[a]->postings_start)});
+          sp.term_idx.push_back(order[a]->term_idx);
           alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
-          op_bytes[op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          op_bytes[is_phrase ? TQ_OP_AND : op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
           postings += order[a]->doc_freq;
           q_postings += order[a]->doc_freq;
         }
+        if (op == TQ_OP_PHRASE) {
+          // PhraseScorer keeps its terms by ascending size_hint (intersection.rs:40-52); every clause carries
+          // (max_offset - its offset), the shift that lines the terms' positions up (phrase_scorer.rs:349-398)
+          uint32_t max_offset = 0;
+          for (uint32_t t = 0; t < q.n_terms; ++t) max_offset = std::max(max_offset, q.term_offset[t]);
+          for (size_t a = 0; a < sp.here.size(); ++a) sp.here[a].range_len = max_offset - q.term_offset[sp.term_idx[a]];  // (range_len is free here)
+          std::stable_sort(sp.here.begin(), sp.here.end(), [](const SegPlan::Clause& a, const SegPlan::Clause& b) { return a.first < b.first; });
+        }
         if (op == TQ_OP_AND)  // leader = rarest, then ascending doc_freq; stable (block_wand_intersection.rs:27)
-          std::stable_sort(sp.here.begin(), sp.here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.first < b.first; });
+          std::stable_sort(sp.here.begin(), sp.here.end(), [](const SegPlan::Clause& a, const SegPlan::Clause& b) { return a.first < b.first; });
         if (op == TQ_OP_OR)
           // Canonical union order = descending Bm25Weight.weight, ties in clause order (the reference's own order is
           // data dependent, block_wand_union.rs:205-208): the f32 sum is taken in this order, and the clauses with the
           // smallest score bounds form a suffix, which is what the MaxScore splits of k_tile / k_or_strip need.
-          std::stable_sort(sp.here.begin(), sp.here.end(), [](const std::pair<uint32_t, QList>& a, const std::pair<uint32_t, QList>& b) { return a.second.weight > b.second.weight; });
-        sp.prunable = op != TQ_OP_TERM;
+          std::stable_sort(sp.here.begin(), sp.here.end(), [](const SegPlan::Clause& a, const SegPlan::Clause& b) { return a.second.weight > b.second.weight; });
+        sp.prunable = true;
         for (auto& h : sp.here) sp.prunable = sp.prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
         i = j;
       }
       // ---- route: the shared-decode tile engine, or the per-query kernels -------------------------------------------------
       bool on_tile = false;
-      if (tile_on && op == TQ_OP_OR && !plans.empty()) {
+      if (tile_on && ((c->tile_ops >> op) & 1u) && n_plans) {
         if (tgroups.empty()) tgroups.emplace_back();
-        int64_t cost = tile_admit_cost(tgroups.back(), plans, c->tile_max_dens_x1000);
-        if (cost < 0 && !(tgroups.back().segs.empty())) {  // the current group is full: open the next one
+        bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000);
+        if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000) >= 0;
+        if (!fits && !tgroups.back().segs.empty()) {  // the current group is full: open the next one
           TileGroupBuild fresh;
-          const int64_t cost2 = tile_admit_cost(fresh, plans, c->tile_max_dens_x1000);
-          if (cost2 >= 0 && tile_pairs_total + (uint64_t)cost2 <= tile_pair_budget) { tgroups.emplace_back(); cost = cost2; }
+          if (tile_admit_cost(fresh, plans.data(), n_plans, c->tile_max_dens_x1000) >= 0) { tgroups.emplace_back(); fits = true; }
         }
-        if (cost >= 0 && tile_pairs_total + (uint64_t)cost <= tile_pair_budget) {
-          tile_admit(tgroups.back(), (uint32_t)qi, op, plans);
-          tile_pairs_total += (uint64_t)cost;
+        if (fits && tile_pairs_total + q_postings + 128ull * n_plans * q.n_terms <= tile_pair_budget) {
+          tile_pairs_total += tile_admit(tgroups.back(), (uint32_t)qi, op, plans.data(), n_plans);
           on_tile = true;
           // every doc at or above the running threshold is handed over: the sample launch and the k_theta passes keep that
           // near k; a query that still overflows sends the batch to the per-query kernels (flags[1])
@@ -772,7 +945,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         }
       }
       if (on_tile) continue;
-      for (SegPlan& sp : plans) {
+      for (size_t pi = 0; pi < n_plans; ++pi) {
+        SegPlan& sp = plans[pi];
         auto& here = sp.here;
         QSeg qs;
         memset(&qs, 0, sizeof(qs));
@@ -782,9 +956,13 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         qs.max_doc = sp.seg->max_doc;
         qs.alive = sp.seg->d_alive;
         qs.fieldnorm = sp.uniform_fn ? sp.fn0 : nullptr;
-        const bool prunable = sp.prunable;
+        const bool prunable = sp.prunable && op != TQ_OP_TERM;
         qs.flags = (sp.uniform_fn ? 1u : 0u) | (prunable ? 2u : 0u);
-        int unit_class = op;
+        int unit_class = op == TQ_OP_PHRASE ? 7 : op;
+        if (op == TQ_OP_PHRASE) {
+          if (qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0});
+          for (auto& h : here) { qaux.push_back(PhraseAux{h.second.pad, h.range_len}); h.second.pad = 0; }
+        }
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
           // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
           uint32_t n_thin = 0;
@@ -810,7 +988,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
           qseg_sample.push_back(unit_class == 3 && prunable && any_thick);
         }
         qseg_total.push_back(unit_class == 3 ? (qs.max_doc + kWin - 1) / kWin : (op == TQ_OP_OR ? (qs.max_doc + kTileDocs - 1) / kTileDocs : lead_total));
-        ++n_qsegs_op[unit_class];
+        ++n_qsegs_op[unit_class == 7 ? TQ_OP_AND : unit_class];
       }
     }
     // Work units. A unit is one CTA's share of a (query, segment). With few (query, segment) pairs in the
@@ -820,8 +998,9 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     for (size_t s = 0; s < qsegs.size(); ++s) {
       const int op = qseg_op[s];
       const uint32_t total = qseg_total[s];
-      const uint32_t min_per = op == TQ_OP_TERM ? c->term_blocks_per_unit : (op == TQ_OP_AND ? c->and_blocks_per_unit : (op == 3 ? kStripWarps * 64u : c->or_tiles_per_unit));
-      const uint32_t want_units = std::max<uint32_t>(1u, (target_units + n_qsegs_op[op] - 1) / n_qsegs_op[op]);
+      const uint32_t min_per = op == TQ_OP_TERM ? c->term_blocks_per_unit : ((op == TQ_OP_AND || op == 7) ? c->and_blocks_per_unit : (op == 3 ? kStripWarps * 64u : c->or_tiles_per_unit));
+      const uint32_t n_same = n_qsegs_op[op == 7 ? TQ_OP_AND : op];
+      const uint32_t want_units = std::max<uint32_t>(1u, (target_units + n_same - 1) / n_same);
       const uint32_t per = std::max<uint32_t>(min_per, (total + want_units - 1) / want_units);
       const uint32_t k = dq[qsegs[s].query].k;
       // Threshold sample: the first 1/sample_div of a strip pair's windows run in a launch of their own; the exact k-th
@@ -852,9 +1031,11 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       if (n_cands > 0xFFFFFFF0ull) return fail(TQ_ERR_UNSUPPORTED, "batch too large: split it");
     }
     int rc = flush_builds(c, pending, &built);
+    if (rc == TQ_OK) rc = flush_pos_builds(c, pending_pos);
     if (rc != TQ_OK) return rc;
   }
   if (caches.empty()) caches.resize(256, 0.0f);
+  if (!qaux.empty() && qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0});
 
   // ---- tile groups: slot order, pair bases, score chunks, tile ranges of the launches -------------------------------------------
   struct GroupStage {
@@ -864,7 +1045,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     std::vector<uint16_t> clauses;
     std::vector<TUnit> units[kTileRounds];
     std::vector<SChunk> chunks;
-    uint32_t max_slots = 1, p_cap = 1024;
+    uint32_t max_slots = 1, p_cap = 1024, max_big = 1, max_queries = 1, max_clause_words = 0;
     size_t tix_words = 0;
   };
   std::vector<GroupStage> gstage(tgroups.size());
@@ -915,6 +1096,9 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       G.tix = reinterpret_cast<uint32_t*>(tix_total_words + gs.tix_words);  // offset for now, rebased below
       gs.tix_words += (size_t)(G.n_tiles + 1) * n_big;
       const uint32_t clause_shift = (uint32_t)gs.clauses.size();
+      G.clause_base = clause_shift;
+      G.n_clause_words = (uint32_t)sb.clauses.size();
+      gs.max_clause_words = std::max(gs.max_clause_words, G.n_clause_words);
       for (auto& tq : sb.queries) {
         TQuery t2 = tq;
         t2.clause_base += clause_shift;
@@ -923,6 +1107,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       }
       for (uint16_t cl : sb.clauses) gs.clauses.push_back((uint16_t)new_of[cl]);
       gs.max_slots = std::max(gs.max_slots, G.n_slots);
+      gs.max_big = std::max(gs.max_big, G.n_big);
+      gs.max_queries = std::max(gs.max_queries, G.n_queries);
       dens_max = std::max(dens_max, sb.dens);
       tiles_total += G.n_tiles;
       gs.segs.push_back(G);
@@ -940,9 +1126,10 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       const uint32_t nt = gs.segs[si].n_tiles;
       if (nt == 0) continue;
       if (c->tile_sample_div > 1 && nt >= 8 && tiles_total) {
+        // short runs of tiles spread over the segment, one CTA each (a sample launch has few tiles: it needs them all in flight)
         const uint32_t seg_sample = (uint32_t)std::max<uint64_t>(1, want_sample_tiles * nt / tiles_total);
-        const uint32_t runs = std::min<uint32_t>(std::min<uint32_t>(8u, nt / 8u), seg_sample);
-        const uint32_t len = std::max<uint32_t>(1u, seg_sample / runs);
+        const uint32_t len = std::max<uint32_t>(1u, std::min<uint32_t>(4u, seg_sample / 64u + 1u));
+        const uint32_t runs = std::max<uint32_t>(1u, seg_sample / len);
         for (uint32_t r = 0; r < runs; ++r) {
           const uint32_t start = (uint32_t)(((uint64_t)(2 * r + 1) * nt) / (2 * runs));
           const uint32_t t0 = std::min(start, nt - 1), t1 = std::min(nt, t0 + len);
@@ -972,7 +1159,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   const size_t o_tftab = off; off = align(off + n_caches * kTfRows * 256 * 4);  // device only (built by k_build_tf_tables)
   const size_t o_qlists = off; off = align(off + qlists.size() * sizeof(QList));
   const size_t o_qsegs = off; off = align(off + qsegs.size() * sizeof(QSeg));
-  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size();
+  const size_t o_qaux = off; off = align(off + qaux.size() * sizeof(PhraseAux));
+  const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size() + units[7].size();
   b->strip_cached_max = strip_cached_max;
   b->or_max_lists = or_max_lists;
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
@@ -1019,10 +1207,12 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   memcpy(b->pin.p + o_caches, caches.data(), caches.size() * 4);
   if (!qlists.empty()) memcpy(b->pin.p + o_qlists, qlists.data(), qlists.size() * sizeof(QList));
   if (!qsegs.empty()) memcpy(b->pin.p + o_qsegs, qsegs.data(), qsegs.size() * sizeof(QSeg));
+  if (!qaux.empty()) memcpy(b->pin.p + o_qaux, qaux.data(), qaux.size() * sizeof(PhraseAux));
+  b->phrase_aux = reinterpret_cast<const PhraseAux*>(b->dev.p + o_qaux);
   {
     Unit* u = reinterpret_cast<Unit*>(b->pin.p + o_units);
     uint32_t base = 0;
-    for (int op = 0; op < 7; ++op) {
+    for (int op = 0; op < 8; ++op) {
       b->unit_base[op] = base;
       b->n_units[op] = (uint32_t)units[op].size();
       if (!units[op].empty()) memcpy(u + base, units[op].data(), units[op].size() * sizeof(Unit));
@@ -1084,8 +1274,13 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     TP.sample_cap = sample_cap;
     TP.p_cap = gs.p_cap;
     TP.max_slots = gs.max_slots;
+    TP.max_big = gs.max_big;
+    TP.max_queries = (gs.max_queries + 1u) & ~1u;
+    TP.seg_cap = std::min<uint32_t>(4096u, std::max<uint32_t>(256u, 3u * TP.max_queries));
     TP.light_max = c->tile_light_max;
-    run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots);
+    TP.cl_cap = gs.max_clause_words <= 16384u ? ((gs.max_clause_words + 3u) & ~3u) : 0u;
+    run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots, TP.max_big, TP.max_queries, TP.seg_cap, TP.cl_cap);
+    if (run.smem > 200u * 1024u) return fail(TQ_ERR_UNSUPPORTED, "tile group needs more shared memory than an SM has");
     b->groups.push_back(run);
   }
   (void)tix_cursor;
@@ -1098,9 +1293,14 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     size_t n_cache = 0;
     for (size_t qi = 0; qi < nq; ++qi) if (queries[qi].tf_cache) n_cache += 256 * (size_t)queries[qi].n_terms;
     o.cache.reserve(n_cache);
+    o.tp.reserve(n_ts); o.toff.reserve(n_t);
     for (size_t qi = 0; qi < nq; ++qi) {
       const tq_query& q = queries[qi];
       tq_query& d = o.q[qi];
+      d.term_pos = nullptr;
+      if (q.term_pos) { d.term_pos = reinterpret_cast<const tq_term_pos*>(o.tp.size() + 1); o.tp.insert(o.tp.end(), q.term_pos, q.term_pos + q.n_term_segs); }
+      d.term_offset = nullptr;
+      if (q.term_offset) { d.term_offset = reinterpret_cast<const uint32_t*>(o.toff.size() + 1); o.toff.insert(o.toff.end(), q.term_offset, q.term_offset + q.n_terms); }
       d.term_segs = reinterpret_cast<const tq_term_seg*>(o.ts.size());  // offsets for now (the vectors do not move again: reserved)
       o.ts.insert(o.ts.end(), q.term_segs, q.term_segs + q.n_term_segs);
       d.weight = reinterpret_cast<const float*>(o.w.size());
@@ -1119,6 +1319,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       if (d.avg_fieldnorm) d.avg_fieldnorm = o.avg.data() + (reinterpret_cast<size_t>(d.avg_fieldnorm) - 1);
       if (d.tf_cache) d.tf_cache = o.cache.data() + (reinterpret_cast<size_t>(d.tf_cache) - 1);
       if (d.term_flags) d.term_flags = o.flags.data() + (reinterpret_cast<size_t>(d.term_flags) - 1);
+      if (d.term_pos) d.term_pos = o.tp.data() + (reinterpret_cast<size_t>(d.term_pos) - 1);
+      if (d.term_offset) d.term_offset = o.toff.data() + (reinterpret_cast<size_t>(d.term_offset) - 1);
     }
   }
 
@@ -1175,15 +1377,11 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   b->stats.units_term = units[0].size(); b->stats.units_and = units[1].size(); b->stats.units_or = units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size(); b->stats.units_or_strip = units[3].size() + units[4].size() + units[5].size() + units[6].size();
   b->stats.bytes_term = op_bytes[0]; b->stats.bytes_and = op_bytes[1]; b->stats.bytes_or = op_bytes[2];
   b->stats.units_tile = tile_units;
+  b->stats.units_phrase = units[7].size();
   b->stats.tile_groups = b->groups.size();
   b->stats.tile_postings = tile_postings;
+  for (auto& tg : tgroups) b->stats.tile_list_bytes += tg.list_bytes;
   b->stats.tile_scratch_bytes = tile_bytes;
-  {
-    // SURVEY.md §8(d) for k_score_lists: every distinct list is read once (its packed blocks + one fieldnorm byte per posting)
-    // and written once as 8-byte (doc, score) pairs
-    uint64_t packed = 0;
-    (void)packed;
-  }
   guard.ok = true;
   *out = b;
   return TQ_OK;
@@ -1230,6 +1428,11 @@ static int run_phase(tq_batch* b, int phase) {
     if (b->n_units[TQ_OP_AND]) {
       const int sp = span_begin(b, SPAN_AND);
       k_and<<<b->n_units[TQ_OP_AND], kThreads, 0, b->stream>>>(P, b->unit_base[TQ_OP_AND]); ++launches;
+      span_end(b, sp);
+    }
+    if (b->n_units[7]) {
+      const int sp = span_begin(b, SPAN_PHRASE);
+      k_phrase<<<b->n_units[7], kPhraseThreads, phrase_smem_bytes(), b->stream>>>(P, b->ctx->d_pos_descs, b->phrase_aux, b->unit_base[7]); ++launches;
       span_end(b, sp);
     }
     if (b->n_units[TQ_OP_OR]) {
@@ -1487,10 +1690,46 @@ int tq_merge_topk_dev(tq_ctx* c, uint32_t n_lists, uint32_t nq, uint32_t stride,
   if (k == 0 || k > TQ_MAX_K || stride < 1) return fail(TQ_ERR_INVALID_ARGUMENT, "k / stride");
   TQ_CUDA(cudaSetDevice(c->device));
   if (nq == 0) return TQ_OK;
-  k_merge<<<nq, kThreads, 0, 0>>>(n_lists, nq, stride, std::min(k, stride), scores_dev, segment_ord_dev, doc_dev, count_dev, out_scores_dev,
-                                  out_segment_ord_dev, out_doc_dev, out_count_dev);
+  k_merge<<<nq, kThreads, 0, 0>>>(n_lists, nq, stride, std::min(k, stride), (size_t)nq * stride, (size_t)nq, scores_dev, segment_ord_dev, doc_dev,
+                                  count_dev, out_scores_dev, out_segment_ord_dev, out_doc_dev, out_count_dev);
   TQ_CUDA(cudaGetLastError());
   TQ_CUDA(cudaStreamSynchronize(0));
+  return TQ_OK;
+}
+
+// Packed form for sharded callers: one buffer per shard = [nq*stride scores | nq*stride segment ords | nq*stride docs | nq counts]
+// (32-bit words, what tq_batch_results_pack_dev writes), `n_lists` of them `pitch_words` apart -- the layout ONE all-gather
+// produces.  Enqueued on `cuda_stream` (a cudaStream_t; e.g. the batch's, tq_batch_stream) without any host synchronisation.
+int tq_merge_topk_packed_dev(tq_ctx* c, void* cuda_stream, uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k, const uint32_t* packed_dev,
+                             size_t pitch_words, uint32_t* out_packed_dev) {
+  if (!c || !packed_dev || !out_packed_dev) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  if (k == 0 || k > TQ_MAX_K || stride < 1 || pitch_words < (size_t)3 * nq * stride + nq) return fail(TQ_ERR_INVALID_ARGUMENT, "k / stride / pitch");
+  TQ_CUDA(cudaSetDevice(c->device));
+  if (nq == 0) return TQ_OK;
+  const size_t rows = (size_t)nq * stride;
+  k_merge<<<nq, kThreads, 0, (cudaStream_t)cuda_stream>>>(n_lists, nq, stride, std::min(k, stride), pitch_words, pitch_words,
+                                                          reinterpret_cast<const float*>(packed_dev), packed_dev + rows, packed_dev + 2 * rows,
+                                                          packed_dev + 3 * rows, reinterpret_cast<float*>(out_packed_dev), out_packed_dev + rows,
+                                                          out_packed_dev + 2 * rows, out_packed_dev + 3 * rows);
+  TQ_CUDA(cudaGetLastError());
+  return TQ_OK;
+}
+
+// The result rows of a finished run in the packed layout above (row stride = k_max of the batch), into a caller-owned DEVICE buffer
+// of 3 * nq * k_max + nq words.  Waits for the run (a tile-engine overflow is resolved first), then copies on the batch's stream.
+int tq_batch_results_pack_dev(tq_batch* b, uint32_t* packed_dev) {
+  if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  if (!packed_dev) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  { const int rc = finalize_run(b); if (rc != TQ_OK) return rc; }
+  const size_t rows = (size_t)b->nq * b->kmax;
+  TQ_CUDA(cudaMemcpyAsync(packed_dev, b->params.res_scores, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + rows, b->params.res_segs, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + 2 * rows, b->params.res_docs, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + 3 * rows, b->params.res_counts, (size_t)b->nq * 4, cudaMemcpyDeviceToDevice, b->stream));
+  collect_times(b);
+  std::lock_guard<std::mutex> g(b->ctx->mu);
+  b->ctx->stats = b->stats;
   return TQ_OK;
 }
 
@@ -1693,6 +1932,187 @@ void tq_field_writer_destroy(tq_field_writer* fw) {
   if (!fw) return;
   delete fw->w;
   delete fw;
+}
+
+}  // extern "C"
+
+// ---- several GPUs behind one handle -------------------------------------------------------------------------------------
+// The reference fans a search out over segments inside one process (Executor::map, src/core/executor.rs:60-100;
+// Searcher::search_with_executor, src/core/searcher.rs:220-237).  tq_multi is that shape for GPUs: one tq_ctx per device,
+// every segment lives on one of them, a search runs the devices' shares concurrently (one host thread per device), exchanges
+// the exact k-th best score keys between the phases (so that every device prunes like a single device holding everything),
+// and merges the per-device rows on the host (merge_fruits / merge_top_k, sort_key_top_collector.rs:54-95).
+#include <condition_variable>
+#include <thread>
+
+struct tq_multi {
+  std::vector<tq_ctx*> ctxs;
+  std::map<std::pair<uint32_t, uint32_t>, int> owner;  // (segment_ord, field) -> index into ctxs
+  std::vector<uint64_t> load;                           // bytes registered per device
+  std::mutex mu;
+  std::string err;
+};
+
+namespace {
+struct HostBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n, waiting = 0;
+  uint64_t gen = 0;
+  explicit HostBarrier(int n_) : n(n_) {}
+  template <class F> void arrive(F&& last) {  // `last` runs on exactly one thread while the others wait
+    std::unique_lock<std::mutex> lk(m);
+    const uint64_t g = gen;
+    if (++waiting == n) { last(); waiting = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g; });
+  }
+};
+}  // namespace
+
+extern "C" {
+
+int tq_multi_create(const int* devices, int n_devices, tq_multi** out) {
+  if (!devices || n_devices <= 0 || !out) return fail(TQ_ERR_INVALID_ARGUMENT, "devices");
+  auto* m = new tq_multi();
+  for (int i = 0; i < n_devices; ++i) {
+    tq_ctx* c = nullptr;
+    const int rc = tq_ctx_create(devices[i], &c);
+    if (rc != TQ_OK) { for (auto* x : m->ctxs) tq_ctx_destroy(x); delete m; return rc; }
+    m->ctxs.push_back(c);
+  }
+  m->load.assign(n_devices, 0);
+  *out = m;
+  return TQ_OK;
+}
+
+void tq_multi_destroy(tq_multi* m) {
+  if (!m) return;
+  for (auto* c : m->ctxs) tq_ctx_destroy(c);
+  delete m;
+}
+
+const char* tq_multi_last_error(tq_multi* m) { return m ? m->err.c_str() : g_err.c_str(); }
+
+int tq_multi_num_devices(tq_multi* m) { return m ? (int)m->ctxs.size() : 0; }
+
+int tq_multi_segment_register(tq_multi* m, int device_index, uint32_t segment_ord, uint32_t field, uint32_t max_doc, int record_option,
+                              const uint8_t* idx_body, size_t idx_len, const uint8_t* fieldnorm, size_t fieldnorm_len,
+                              const uint8_t* alive_bitset, size_t alive_len) {
+  if (!m) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  std::lock_guard<std::mutex> g(m->mu);
+  if (device_index >= (int)m->ctxs.size()) { m->err = "device_index"; return TQ_ERR_INVALID_ARGUMENT; }
+  if (device_index < 0) {  // least loaded device: segments shard naturally
+    device_index = 0;
+    for (size_t i = 1; i < m->load.size(); ++i) if (m->load[i] < m->load[device_index]) device_index = (int)i;
+  }
+  const int rc = tq_segment_register(m->ctxs[device_index], segment_ord, field, max_doc, record_option, idx_body, idx_len, fieldnorm, fieldnorm_len,
+                                     alive_bitset, alive_len);
+  if (rc != TQ_OK) { m->err = g_err; return rc; }
+  m->owner[{segment_ord, field}] = device_index;
+  m->load[device_index] += idx_len + fieldnorm_len;
+  return TQ_OK;
+}
+
+int tq_multi_search_batch(tq_multi* m, const tq_query* queries, size_t nq, uint32_t out_stride, float* out_scores, uint32_t* out_segment_ord,
+                          uint32_t* out_doc, uint32_t* out_count) {
+  if (!m || (!queries && nq) || !out_scores || !out_segment_ord || !out_doc || !out_count) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  const int nd = (int)m->ctxs.size();
+  uint32_t kmax = 1;
+  for (size_t q = 0; q < nq; ++q) kmax = std::max(kmax, queries[q].k);
+  // every device's share of every query: the (clause, segment) lists of the segments it owns
+  std::vector<std::vector<tq_query>> dq(nd, std::vector<tq_query>(queries, queries + nq));
+  std::vector<std::vector<tq_term_seg>> dts(nd);
+  {
+    std::lock_guard<std::mutex> g(m->mu);
+    std::vector<std::vector<size_t>> first(nd, std::vector<size_t>(nq + 1, 0));
+    for (size_t q = 0; q < nq; ++q) {
+      for (int d = 0; d < nd; ++d) first[d][q] = dts[d].size();
+      for (uint32_t i = 0; i < queries[q].n_term_segs; ++i) {
+        const tq_term_seg& ts = queries[q].term_segs[i];
+        auto it = m->owner.find({ts.segment_ord, ts.field});
+        if (it == m->owner.end()) { m->err = "term_seg names a segment/field that is not registered"; return TQ_ERR_NOT_FOUND; }
+        dts[it->second].push_back(ts);
+      }
+    }
+    for (int d = 0; d < nd; ++d) {
+      first[d][nq] = dts[d].size();
+      for (size_t q = 0; q < nq; ++q) {
+        dq[d][q].term_segs = dts[d].data() + first[d][q];
+        dq[d][q].n_term_segs = (uint32_t)(first[d][q + 1] - first[d][q]);
+      }
+    }
+  }
+  const size_t rows = std::max<size_t>(nq, 1) * kmax;
+  std::vector<std::vector<float>> r_sc(nd, std::vector<float>(rows));
+  std::vector<std::vector<uint32_t>> r_sg(nd, std::vector<uint32_t>(rows)), r_dc(nd, std::vector<uint32_t>(rows)), r_ct(nd, std::vector<uint32_t>(std::max<size_t>(nq, 1)));
+  std::vector<std::vector<uint32_t>> keys(nd, std::vector<uint32_t>(rows));  // [device][query][kmax] best keys so far
+  std::vector<long long> bound(std::max<size_t>(nq, 1), 0);                   // exact k-th best of the union, per query
+  std::vector<int> rcs(nd, TQ_OK);
+  std::vector<std::string> errs(nd);
+  HostBarrier bar(nd);
+  bool abort_all = false;
+  auto worker = [&](int d) {
+    tq_batch* b = nullptr;
+    uint32_t* d_keys = nullptr;
+    long long* d_bound = nullptr;
+    int rc = tq_batch_prepare(m->ctxs[d], dq[d].data(), nq, &b);
+    if (rc == TQ_OK && (cudaMalloc(&d_keys, rows * 4) != cudaSuccess || cudaMalloc(&d_bound, std::max<size_t>(nq, 1) * 8) != cudaSuccess)) rc = fail(TQ_ERR_OOM, "exchange buffers");
+    const int phases = kPhases;
+    for (int p = 0; p < phases; ++p) {
+      if (rc == TQ_OK) rc = tq_batch_run_phase(b, p);
+      if (p + 1 == phases) break;
+      if (rc == TQ_OK) rc = tq_batch_topkeys_export_dev(b, d_keys, kmax);
+      if (rc == TQ_OK && (cudaMemcpyAsync(keys[d].data(), d_keys, rows * 4, cudaMemcpyDeviceToHost, b->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(b->stream) != cudaSuccess)) rc = fail(TQ_ERR_CUDA, "key export");
+      if (rc != TQ_OK) { std::lock_guard<std::mutex> g(m->mu); abort_all = true; }
+      bar.arrive([&] {  // one thread: the exact k-th best key of the union of all devices' keys
+        std::vector<uint32_t> all((size_t)nd * kmax);
+        for (size_t q = 0; q < nq; ++q) {
+          for (int e = 0; e < nd; ++e) memcpy(all.data() + (size_t)e * kmax, keys[e].data() + q * kmax, (size_t)kmax * 4);
+          const uint32_t k = queries[q].k;
+          std::nth_element(all.begin(), all.begin() + (k - 1), all.end(), std::greater<uint32_t>());
+          bound[q] = (long long)all[k - 1];
+        }
+      });
+      if (abort_all) { if (rc == TQ_OK) rc = TQ_ERR_CUDA; break; }
+      if (rc == TQ_OK && cudaMemcpyAsync(d_bound, bound.data(), nq * 8, cudaMemcpyHostToDevice, b->stream) != cudaSuccess) rc = fail(TQ_ERR_CUDA, "bound import");
+      if (rc == TQ_OK && nq) rc = tq_batch_thresholds_import_dev(b, reinterpret_cast<const int64_t*>(d_bound));
+    }
+    if (rc == TQ_OK) rc = tq_batch_fetch(b, kmax, r_sc[d].data(), r_sg[d].data(), r_dc[d].data(), r_ct[d].data());
+    if (rc != TQ_OK) errs[d] = g_err;
+    rcs[d] = rc;
+    if (b) tq_batch_destroy(b);
+    cudaFree(d_keys);
+    cudaFree(d_bound);
+  };
+  std::vector<std::thread> th;
+  for (int d = 0; d < nd; ++d) th.emplace_back(worker, d);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < nd; ++d)
+    if (rcs[d] != TQ_OK) { m->err = errs[d]; g_err = errs[d]; return rcs[d]; }
+  // merge_fruits: (score desc, segment_ord asc, doc asc), keep k (top_score_collector.rs:591-600)
+  struct Row { float s; uint32_t g, d; };
+  std::vector<Row> all;
+  for (size_t q = 0; q < nq; ++q) {
+    all.clear();
+    for (int d = 0; d < nd; ++d) {
+      const uint32_t n = std::min(r_ct[d][q], kmax);
+      for (uint32_t i = 0; i < n; ++i) all.push_back(Row{r_sc[d][q * kmax + i], r_sg[d][q * kmax + i], r_dc[d][q * kmax + i]});
+    }
+    std::sort(all.begin(), all.end(), [](const Row& a, const Row& b) {
+      if (a.s != b.s) return a.s > b.s;
+      if (a.g != b.g) return a.g < b.g;
+      return a.d < b.d;
+    });
+    const uint32_t n = (uint32_t)std::min<size_t>(all.size(), queries[q].k);
+    out_count[q] = n;
+    for (uint32_t i = 0; i < std::min(n, out_stride); ++i) {
+      out_scores[q * out_stride + i] = all[i].s;
+      out_segment_ord[q * out_stride + i] = all[i].g;
+      out_doc[q * out_stride + i] = all[i].d;
+    }
+  }
+  return TQ_OK;
 }
 
 }  // extern "C"

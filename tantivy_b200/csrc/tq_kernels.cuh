@@ -1739,8 +1739,10 @@ __global__ void __launch_bounds__(kThreads) k_final(const BatchParams P) {
 }
 
 // K7 (device half): merge_fruits across result sets gathered from several GPUs.
-// in: [n_lists][nq][stride] rows sorted like k_final's output; out: [nq][stride].
-__global__ void __launch_bounds__(kThreads) k_merge(uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k,
+// in: n_lists result sets, each [nq][stride] rows sorted like k_final's output (+ [nq] counts), `row_pitch` / `count_pitch`
+// elements apart (contiguous [n_lists][nq][stride] arrays: nq * stride / nq; one packed buffer per shard: its size);
+// out: [nq][stride].
+__global__ void __launch_bounds__(kThreads) k_merge(uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k, size_t row_pitch, size_t count_pitch,
                                                     const float* __restrict__ in_scores, const uint32_t* __restrict__ in_segs,
                                                     const uint32_t* __restrict__ in_docs, const uint32_t* __restrict__ in_counts,
                                                     float* __restrict__ out_scores, uint32_t* __restrict__ out_segs,
@@ -1750,10 +1752,10 @@ __global__ void __launch_bounds__(kThreads) k_merge(uint32_t n_lists, uint32_t n
   const uint32_t q = blockIdx.x;
   uint32_t have = 0;
   for (uint32_t l = 0; l < n_lists; ++l) {
-    const uint32_t cnt = min(min(in_counts[(size_t)l * nq + q], stride), k);
+    const uint32_t cnt = min(min(in_counts[(size_t)l * count_pitch + q], stride), k);
     // have <= k <= 1024 and cnt <= 1024, so have + cnt <= kCap
     for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const size_t o = ((size_t)l * nq + q) * stride + i;
+      const size_t o = (size_t)l * row_pitch + (size_t)q * stride + i;
       s_a[have + i] = ((unsigned long long)score_to_key(in_scores[o]) << 32) | (unsigned long long)(0xFFFFFFFFu - in_segs[o]);
       s_b[have + i] = ~in_docs[o];
     }

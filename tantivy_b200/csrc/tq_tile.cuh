@@ -20,9 +20,12 @@
 //                       (descending weight); the longest suffix whose tile maxima add up to less than the query's
 //                       threshold is non-essential and is only LOOKED UP for docs that the essential clauses make
 //                       promising;
-//                     * light (query, tile) pairs -- few essential postings -- are evaluated by one thread per query
-//                       (a scalar document-at-a-time merge over shared memory), heavy ones by one warp per query over a
-//                       warp-private window of f32 score slots (BufferedUnionScorer's shape, union/buffered_union.rs:63-86);
+//                     * the essential postings of all (query, tile) pairs become one work list that the CTA's threads share
+//                       evenly: one thread = one posting = one doc, completed by lookups in the query's other clauses (a bit
+//                       test + popcount for dense lists, a short binary search for sparse ones), the non-essential suffix
+//                       with an early exit as soon as the rest of the bound cannot reach the threshold; pairs with very
+//                       many essential postings (and the sample launch) take a warp-private window of f32 score slots
+//                       instead (BufferedUnionScorer's shape, union/buffered_union.rs:63-86);
 //                     * f32 sums are taken clause by clause in the canonical order, so pruned and exhaustive evaluation
 //                       give bit-identical scores;
 //                     * survivors (score key >= the query's threshold) go to the query's candidate region, k_final
@@ -46,6 +49,7 @@ constexpr uint32_t kTileMaxSlots = 4096;    // distinct scored lists of one grou
 constexpr uint32_t kTileMaxPairs = 12288;   // pairs of one tile held in shared memory (start | len are 16-bit fields)
 constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+constexpr uint32_t kTileOpAnd = 1;  // TQ_OP_AND; term queries and unions share one evaluation (a union of one clause)
 
 struct TSlot {  // one distinct scored list of a group: (posting list, Bm25Weight.weight, tf-norm table)
   uint32_t list_id;
@@ -61,6 +65,8 @@ struct TSeg {  // one segment of a group
   uint32_t slot_base, n_slots, n_big;  // slots [0, n_big) have a tile index and are staged by whole warps
   uint32_t query_base, n_queries;
   uint32_t max_doc, segment_ord, n_tiles;
+  uint32_t clause_base, n_clause_words;  // this segment's share of TileParams::clauses (staged in shared memory when it fits)
+  uint32_t pad0, pad1;
   const uint8_t* alive;
   uint32_t* tix;  // [(n_tiles + 1)][n_big]: index of the list's first pair with doc >= tile * kTile (written by k_score_lists)
 };
@@ -91,12 +97,14 @@ struct TileParams {
   uint32_t sample_cap;
   uint32_t p_cap;      // pairs of one tile that fit in shared memory
   uint32_t max_slots;  // largest n_slots of any segment of the group
-  uint32_t light_max;  // (query, tile) pairs with at most this many essential postings take the thread-per-query path
+  uint32_t max_big;    // ... n_big
+  uint32_t max_queries;  // ... n_queries
+  uint32_t cl_cap;     // clause words staged in shared memory per CTA (0: the segment's clauses are read from global memory)
+  uint32_t seg_cap;    // entries of the per-tile work list (essential clauses of the flat pairs)
+  uint32_t light_max;  // (query, tile) pairs with at most this many essential postings are evaluated posting by posting (flat path);
+                       // above it a warp accumulates the query's window
 };
 
-__host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots) {
-  return (size_t)p_cap * 4 + (size_t)kTileWarps * kTile * 4 + (size_t)max_slots * 16 + (size_t)p_cap * 2 + (size_t)kTileMaxQueries * 2 + 64;
-}
 
 // ---- K1 + K2, once per batch -------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) k_score_lists(const BatchParams P, const TileParams TP, uint32_t chunk_base) {
@@ -158,18 +166,36 @@ __global__ void __launch_bounds__(kThreads) k_score_lists(const BatchParams P, c
 }
 
 // ---- tile evaluation -----------------------------------------------------------------------------------------------------
-// info word of a slot in the current tile: start | len << 16 (pairs [start, start + len) of s_off / s_score, ascending docs)
-__device__ __forceinline__ float tile_find(const uint16_t* __restrict__ s_off, const float* __restrict__ s_score, uint32_t info, uint32_t off,
-                                           bool& found) {
+// What a tile keeps in shared memory per slot: info = start | len << 16 (pairs [start, start + len) of s_off / s_score, ascending
+// docs), the largest score, and for DENSE slots (the first n_big of a segment) a 1024-bit presence map with per-word ranks, so that
+// "does this list hold doc x, and where" is one bit test + one popcount instead of a binary search over hundreds of pairs.
+struct TileView {
+  const uint16_t* s_off;
+  const float* s_score;
+  const uint32_t* s_info;
+  const uint32_t* s_bits;   // [max_big][32]
+  const uint16_t* s_rank;   // [max_big][32] pairs of the slot before word w
+  uint32_t n_big;
+};
+
+__device__ __forceinline__ float tile_find(const TileView& V, uint32_t slot, uint32_t off, bool& found) {
+  const uint32_t info = V.s_info[slot];
+  if (slot < V.n_big) {
+    const uint32_t w = V.s_bits[slot * 32u + (off >> 5)];
+    const uint32_t bit = 1u << (off & 31u);
+    found = (w & bit) != 0u;
+    if (!found) return 0.0f;
+    return V.s_score[(info & 0xFFFFu) + V.s_rank[slot * 32u + (off >> 5)] + __popc(w & (bit - 1u))];
+  }
   uint32_t lo = info & 0xFFFFu;
   const uint32_t end = lo + (info >> 16);
   uint32_t hi = end;
   while (lo < hi) {
     const uint32_t m = (lo + hi) >> 1;
-    if (s_off[m] < off) lo = m + 1u; else hi = m;
+    if (V.s_off[m] < off) lo = m + 1u; else hi = m;
   }
-  found = lo < end && s_off[lo] == off;
-  return found ? s_score[lo] : 0.0f;
+  found = lo < end && V.s_off[lo] == off;
+  return found ? V.s_score[lo] : 0.0f;
 }
 
 __device__ __forceinline__ void tile_push(const BatchParams& P, uint32_t query, float score, uint32_t doc, uint32_t segment_ord,
@@ -182,52 +208,104 @@ __device__ __forceinline__ void tile_push(const BatchParams& P, uint32_t query, 
   if (idx < Q.cand_cap) P.cands[Q.cand_base + idx] = Cand{key, segment_ord, doc, 0u};
 }
 
-struct TileQueryState {
-  uint32_t th_key;
-  float theta_f;
-  uint32_t n_e;   // essential clauses [0, n_e)
-  float ne;       // upper bound of what the non-essential suffix can add in this tile
-  bool prune;     // bounds may be used (threshold present, weights >= 0, exact launch)
+// One (query, tile) pair that is evaluated posting by posting: what every posting's thread needs to know.
+struct TileQ {
+  uint32_t query;        // ordinal in the batch
+  uint32_t clause_base;  // into TileParams::clauses
+  uint32_t th_key;       // the query's threshold when the tile was entered
+  float ne;              // bound of the non-essential suffix in this tile (unions); 0 for conjunctions
+  uint16_t n, n_e;       // clauses; essential prefix (unions) / driving clause (conjunctions)
+  uint16_t op, prune;
 };
+struct TileSeg { uint16_t q, clause, start, len; };  // postings [start, start + len) of one essential clause of flat pair q
 
-__device__ __forceinline__ TileQueryState tile_query_state(uint32_t th_key, const TQuery& tq, const uint16_t* __restrict__ cl,
-                                                           const float* __restrict__ s_max, bool sample_mode) {
-  TileQueryState st;
-  st.th_key = th_key;
-  st.theta_f = threshold_score(st.th_key);
-  st.n_e = tq.n_clauses;
-  st.ne = 0.0f;
-  st.prune = (tq.flags & 1u) && st.theta_f > 0.0f && !sample_mode;
-  if (st.prune) {
-    while (st.n_e > 0) {
-      const float b = st.ne + s_max[cl[st.n_e - 1u]];
-      if (!(b * 1.00001f < st.theta_f)) break;  // (f32 sums of <= 32 terms differ by < 4e-6 relative between orders)
-      st.ne = b;
-      --st.n_e;
-    }
+// Union: the doc at tile offset `off`, met as posting p of essential clause c.  Exact score in the canonical order, or nothing when
+// the bounds show it cannot reach the threshold.  Returns true when `sum` is a complete score.
+__device__ __forceinline__ bool tile_eval_or(const TileView& V, const float* __restrict__ s_max, const uint16_t* __restrict__ cl, const TileQ& q,
+                                             uint32_t c, uint32_t p, uint32_t off, float theta_f, float& sum) {
+  bool f;
+  for (uint32_t c1 = 0; c1 < c; ++c1) {  // an earlier essential clause lists the doc: it is evaluated there
+    tile_find(V, cl[c1], off, f);
+    if (f) return false;
   }
-  return st;
+  sum = V.s_score[p];  // (-0.0 + s == s: SumCombiner starts from 0, score_combiner.rs:39-57)
+  for (uint32_t c2 = c + 1u; c2 < q.n_e; ++c2) {
+    const float v = tile_find(V, cl[c2], off, f);
+    if (f) sum = __fadd_rn(sum, v);
+  }
+  // the non-essential suffix, densest last; stop as soon as what is left cannot lift the doc over the threshold
+  float rem = q.ne;
+  for (uint32_t c2 = q.n_e; c2 < q.n; ++c2) {
+    if (q.prune && (sum + rem) * 1.00001f < theta_f) return false;
+    const uint32_t slot = cl[c2];
+    rem -= s_max[slot];
+    const float v = tile_find(V, slot, off, f);
+    if (f) sum = __fadd_rn(sum, v);
+  }
+  return true;
+}
+
+// Conjunction: the doc (posting p of the driving clause) must be listed by every clause; the score is summed in clause order
+// (leader = rarest list first, block_wand_intersection.rs:27,146-158) whichever clause drives the iteration.
+__device__ __forceinline__ bool tile_eval_and(const TileView& V, const uint16_t* __restrict__ cl, uint32_t n, uint32_t drv, uint32_t p, uint32_t off,
+                                              float& sum) {
+  sum = 0.0f;
+  for (uint32_t c = 0; c < n; ++c) {
+    float v;
+    if (c == drv) v = V.s_score[p];
+    else {
+      bool f;
+      v = tile_find(V, cl[c], off, f);
+      if (!f) return false;
+    }
+    sum = c == 0 ? v : __fadd_rn(sum, v);
+  }
+  return true;
+}
+
+__host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots, uint32_t max_big, uint32_t max_queries, uint32_t seg_cap,
+                                                      uint32_t cl_cap) {
+  return (size_t)p_cap * 4 + (size_t)kTileWarps * kTile * 4 + (size_t)max_slots * 16 + (size_t)max_big * 128 + (size_t)max_queries * sizeof(TileQ) +
+         (size_t)max_queries * sizeof(TQuery) + (size_t)seg_cap * sizeof(TileSeg) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 +
+         (size_t)cl_cap * 2 + 64;
 }
 
 __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, const TileParams TP, uint32_t unit_base, uint32_t sample_mode) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
-  float* s_score = reinterpret_cast<float*>(s_dyn);                       // [p_cap]
-  float* s_acc = s_score + TP.p_cap;                                      // [kTileWarps][kTile]
+  float* s_score = reinterpret_cast<float*>(s_dyn);                            // [p_cap]
+  float* s_acc = s_score + TP.p_cap;                                           // [kTileWarps][kTile]
   uint32_t* s_info = reinterpret_cast<uint32_t*>(s_acc + kTileWarps * kTile);  // [max_slots]
-  float* s_max = reinterpret_cast<float*>(s_info + TP.max_slots);         // [max_slots] largest score of the slot in this tile (>= 0)
-  uint32_t* s_cur = reinterpret_cast<uint32_t*>(s_max + TP.max_slots);    // [max_slots] small slots: first pair not staged yet
-  uint32_t* s_nxt = s_cur + TP.max_slots;                                 // [max_slots] ... and its doc (0xFFFFFFFF: list exhausted)
-  uint16_t* s_off = reinterpret_cast<uint16_t*>(s_nxt + TP.max_slots);    // [p_cap]
-  uint16_t* s_heavy = s_off + TP.p_cap;                                   // [kTileMaxQueries]
-  __shared__ uint32_t s_total, s_nheavy, s_hpos;
+  float* s_max = reinterpret_cast<float*>(s_info + TP.max_slots);              // [max_slots] largest score of the slot in this tile (>= 0)
+  uint32_t* s_cur = reinterpret_cast<uint32_t*>(s_max + TP.max_slots);         // [max_slots] small slots: first pair not staged yet
+  uint32_t* s_nxt = s_cur + TP.max_slots;                                      // [max_slots] ... and its doc (0xFFFFFFFF: list exhausted)
+  uint32_t* s_bits = s_nxt + TP.max_slots;                                     // [max_big][32]
+  TileQ* s_q = reinterpret_cast<TileQ*>(s_bits + TP.max_big * 32u);            // [max_queries] flat pairs of this tile
+  TQuery* s_tq = reinterpret_cast<TQuery*>(s_q + TP.max_queries);              // [max_queries] this segment's queries
+  TileSeg* s_seg = reinterpret_cast<TileSeg*>(s_tq + TP.max_queries);          // [seg_cap]
+  uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_seg + TP.seg_cap);          // [max_big][32]
+  uint16_t* s_off = s_rank + TP.max_big * 32u;                                 // [p_cap]
+  uint16_t* s_heavy = s_off + TP.p_cap;                                        // [max_queries]
+  uint16_t* s_cl = s_heavy + TP.max_queries;                                   // [cl_cap] this segment's clause slots
+  __shared__ uint32_t s_total, s_nheavy, s_hpos, s_nflat, s_nseg, s_segpos, s_segvalid;
   __shared__ unsigned long long s_stat[8];
   const TUnit U = TP.units[unit_base + blockIdx.x];
   const TSeg G = TP.segs[U.tseg];
   const TSlot* __restrict__ slots = TP.slots + G.slot_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const float neg_zero = __uint_as_float(0x80000000u);
+  const TileView V{s_off, s_score, s_info, s_bits, s_rank, G.n_big};
   for (uint32_t i = tid; i < kTileWarps * kTile; i += kTileThreads) s_acc[i] = neg_zero;
   if (tid < 8) s_stat[tid] = 0ull;
+  // the segment's queries and their clause slots are read for every tile: keep them on chip (clause_base becomes an index into cl0)
+  const bool cl_staged = G.n_clause_words <= TP.cl_cap;
+  const uint16_t* __restrict__ cl0 = cl_staged ? s_cl : TP.clauses + G.clause_base;
+  for (uint32_t i = tid; i < G.n_queries; i += kTileThreads) {
+    TQuery tq = TP.queries[G.query_base + i];
+    tq.clause_base -= G.clause_base;
+    s_tq[i] = tq;
+  }
+  if (cl_staged)
+    for (uint32_t i = tid; i < G.n_clause_words; i += kTileThreads) s_cl[i] = TP.clauses[G.clause_base + i];
   // small slots: position the cursor on the first pair at or after the unit's first doc
   for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {
     const TSlot sl = slots[s];
@@ -242,14 +320,14 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
     s_nxt[s] = a < sl.doc_freq ? __ldg(d + a) : 0xFFFFFFFFu;
   }
   __syncthreads();
-  unsigned long long st_pairs = 0, st_skip = 0, st_light = 0, st_ess = 0, st_compl = 0, st_push = 0;  // per-thread diagnostics
+  unsigned long long st_pairs = 0, st_skip = 0, st_flat = 0, st_heavy = 0, st_ess = 0, st_compl = 0, st_push = 0;  // per-thread diagnostics
 
   for (uint32_t t = U.t0; t < U.t1; ++t) {
     const uint32_t lo = t * kTile, hi = lo + kTile;
-    if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; }
+    if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; s_nflat = 0; s_nseg = 0; s_segpos = 0; s_segvalid = TP.seg_cap; }
     __syncthreads();
     // ---- stage A: this tile's pairs of every slot -> shared memory --------------------------------------------------------
-    for (uint32_t s = warp; s < G.n_big; s += kTileWarps) {  // dense lists: a warp copies [tix[t], tix[t+1])
+    for (uint32_t s = warp; s < G.n_big; s += kTileWarps) {  // dense lists: a warp copies [tix[t], tix[t+1]) and maps the docs
       const TSlot sl = slots[s];
       const uint32_t a = __ldg(G.tix + (size_t)t * G.n_big + s), b = __ldg(G.tix + (size_t)(t + 1u) * G.n_big + s);
       const uint32_t n = b - a;
@@ -259,14 +337,22 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
       float mx = 0.0f;
       const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base + a;
       const float* __restrict__ sc = TP.p_scores + sl.pair_base + a;
+      uint32_t* bits = s_bits + s * 32u;
+      bits[lane] = 0u;
+      __syncwarp();
       if (base + n <= TP.p_cap) {
         for (uint32_t i = lane; i < n; i += 32) {
           const float v = __ldg(sc + i);
-          s_off[base + i] = (uint16_t)(__ldg(d + i) - lo);
+          const uint32_t off = __ldg(d + i) - lo;
+          s_off[base + i] = (uint16_t)off;
           s_score[base + i] = v;
+          atomicOr(&bits[off >> 5], 1u << (off & 31u));
           mx = fmaxf(mx, v);
         }
       }
+      __syncwarp();
+      const uint32_t cnt = (uint32_t)__popc(bits[lane]);
+      s_rank[s * 32u + lane] = (uint16_t)(warp_incl_scan(cnt, lane) - cnt);
       mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(mx)));  // mx >= 0
       if (lane == 0) { s_info[s] = (base & 0xFFFFu) | (n << 16); s_max[s] = mx; }
     }
@@ -310,48 +396,114 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
       __syncthreads();
       continue;
     }
-    // ---- stage B1: one thread per query -- bounds, routing, and the light (query, tile) pairs -------------------------------
+    // ---- stage B1: one thread per query -- bounds and routing ---------------------------------------------------------------
+    // skipped: no doc of the tile can reach the query's threshold;  flat: the essential postings become work items that the CTA's
+    // threads share evenly (B2);  heavy: a warp accumulates the query's window (B3; sample launches, and pairs with many postings).
     for (uint32_t qi = tid; qi < G.n_queries; qi += kTileThreads) {
-      const TQuery tq = TP.queries[G.query_base + qi];
-      const uint16_t* __restrict__ cl = TP.clauses + tq.clause_base;
-      const TileQueryState st = tile_query_state(*(volatile unsigned int*)&P.qstate[tq.query].theta, tq, cl, s_max, sample_mode != 0);
-      ++st_pairs;
-      if (st.n_e == 0) { ++st_skip; continue; }  // no doc of this tile can reach the threshold
-      uint32_t cnt = 0;
-      for (uint32_t c = 0; c < st.n_e; ++c) cnt += s_info[cl[c]] >> 16;
-      if (cnt == 0) { ++st_skip; continue; }  // a doc without an essential posting stays below the threshold
-      if (sample_mode || cnt > TP.light_max) { s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)qi; continue; }
-      ++st_light;
-      st_ess += cnt;
+      const TQuery tq = s_tq[qi];
+      const uint16_t* __restrict__ cl = cl0 + tq.clause_base;
+      const uint32_t th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
+      const float theta_f = threshold_score(th_key);
+      const bool prune = (tq.flags & 1u) && theta_f > 0.0f && !sample_mode;
       const uint32_t n = tq.n_clauses;
-      for (uint32_t c = 0; c < st.n_e; ++c) {
-        const uint32_t info = s_info[cl[c]];
-        const uint32_t a = info & 0xFFFFu, e = a + (info >> 16);
-        for (uint32_t p = a; p < e; ++p) {
-          const uint32_t off = s_off[p];
-          bool dup = false;  // the doc was evaluated when an earlier essential clause listed it
-          for (uint32_t c1 = 0; c1 < c && !dup; ++c1) tile_find(s_off, s_score, s_info[cl[c1]], off, dup);
-          if (dup) continue;
-          float sum = s_score[p];  // (-0.0 + s == s: SumCombiner starts from 0, score_combiner.rs:39-57)
-          for (uint32_t c2 = c + 1u; c2 < st.n_e; ++c2) {
-            bool f;
-            const float v = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
-            if (f) sum = __fadd_rn(sum, v);
+      ++st_pairs;
+      TileQ rec;
+      rec.query = tq.query; rec.clause_base = tq.clause_base; rec.th_key = th_key; rec.n = (uint16_t)n; rec.op = tq.op; rec.prune = prune ? 1 : 0;
+      uint32_t cnt = 0, n_segs = 0;
+      if (tq.op == kTileOpAnd) {
+        float bound = 0.0f;
+        uint32_t dmin = 0xFFFFFFFFu, drv = 0;
+        for (uint32_t c = 0; c < n; ++c) {  // the clause with the fewest postings in this tile drives
+          const uint32_t len = s_info[cl[c]] >> 16;
+          bound += s_max[cl[c]];
+          if (len < dmin) { dmin = len; drv = c; }
+        }
+        if (dmin == 0u || (prune && bound * 1.00001f < theta_f)) { ++st_skip; continue; }
+        rec.n_e = (uint16_t)drv; rec.ne = 0.0f;
+        cnt = dmin; n_segs = 1;
+      } else {
+        uint32_t n_e = n;
+        float ne = 0.0f;
+        if (prune) {
+          while (n_e > 0) {
+            const float b = ne + s_max[cl[n_e - 1u]];
+            if (!(b * 1.00001f < theta_f)) break;  // (f32 sums of <= 32 terms differ by < 4e-6 relative between orders)
+            ne = b;
+            --n_e;
           }
-          if (st.prune && (sum + st.ne) * 1.00001f < st.theta_f) continue;
-          for (uint32_t c2 = st.n_e; c2 < n; ++c2) {
-            bool f;
-            const float v = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
-            if (f) sum = __fadd_rn(sum, v);
+        }
+        if (n_e == 0) { ++st_skip; continue; }  // no doc of this tile can reach the threshold
+        for (uint32_t c = 0; c < n_e; ++c) { const uint32_t len = s_info[cl[c]] >> 16; cnt += len; n_segs += len ? 1u : 0u; }
+        if (cnt == 0) { ++st_skip; continue; }  // a doc without an essential posting stays below the threshold
+        rec.n_e = (uint16_t)n_e; rec.ne = ne;
+      }
+      bool heavy = sample_mode || cnt > TP.light_max;
+      if (!heavy) {
+        const uint32_t sb = atomicAdd(&s_nseg, n_segs);
+        if (sb + n_segs > TP.seg_cap) { heavy = true; atomicMin(&s_segvalid, sb); }  // the work list is full (entries from here on are not written): the window path takes any pair
+        else {
+          const uint32_t qslot = atomicAdd(&s_nflat, 1u);
+          s_q[qslot] = rec;
+          uint32_t w = sb;
+          if (tq.op == kTileOpAnd) {
+            const uint32_t info = s_info[cl[rec.n_e]];
+            s_seg[w] = TileSeg{(uint16_t)qslot, rec.n_e, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
+          } else {
+            for (uint32_t c = 0; c < rec.n_e; ++c) {
+              const uint32_t info = s_info[cl[c]];
+              if (info >> 16) s_seg[w++] = TileSeg{(uint16_t)qslot, (uint16_t)c, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
+            }
           }
-          ++st_compl;
-          if (score_to_key(sum) >= st.th_key) ++st_push;
-          tile_push(P, tq.query, sum, lo + off, G.segment_ord, st.th_key, G.alive);
+          ++st_flat;
+          st_ess += cnt;
+        }
+      }
+      if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)qi;
+    }
+    __syncthreads();
+    // ---- stage B2: the flat pairs' essential postings, one per thread --------------------------------------------------------
+    {
+      const uint32_t n_seg = min(s_nseg, s_segvalid);
+      for (;;) {
+        uint32_t sbase = 0;
+        if (lane == 0) sbase = atomicAdd(&s_segpos, 32u);
+        sbase = __shfl_sync(kFull, sbase, 0);
+        if (sbase >= n_seg) break;
+        // 32 segments, one per lane; their postings are dealt to the lanes 32 at a time (load-balanced expansion)
+        TileSeg mine = TileSeg{0, 0, 0, 0};
+        if (sbase + lane < n_seg) mine = s_seg[sbase + lane];
+        const uint32_t incl = warp_incl_scan((uint32_t)mine.len, lane);
+        const uint32_t total = __shfl_sync(kFull, incl, 31);
+        for (uint32_t ibase = 0; ibase < total; ibase += 32u) {
+          const uint32_t item = ibase + lane;
+          uint32_t j = 0;  // first lane whose inclusive count exceeds `item`
+#pragma unroll
+          for (uint32_t step = 16; step > 0; step >>= 1) {
+            const uint32_t v = __shfl_sync(kFull, incl, (j + step - 1u) & 31u);
+            if (v <= item) j += step;
+          }
+          const uint32_t incl_j = __shfl_sync(kFull, incl, j & 31u);
+          if (item < total) {
+            const TileSeg sg = s_seg[sbase + j];
+            const uint32_t before = incl_j - sg.len;
+            const uint32_t p = sg.start + (item - before);
+            const TileQ q = s_q[sg.q];
+            const uint16_t* __restrict__ cl = cl0 + q.clause_base;
+            const uint32_t off = s_off[p];
+            float sum;
+            bool ok;
+            if (q.op == kTileOpAnd) ok = tile_eval_and(V, cl, q.n, q.n_e, p, off, sum);
+            else ok = tile_eval_or(V, s_max, cl, q, sg.clause, p, off, threshold_score(q.th_key), sum);
+            if (ok) {
+              ++st_compl;
+              if (score_to_key(sum) >= q.th_key) ++st_push;
+              tile_push(P, q.query, sum, lo + off, G.segment_ord, q.th_key, G.alive);
+            }
+          }
         }
       }
     }
-    __syncthreads();
-    // ---- stage B2: one warp per heavy query, a window of f32 score slots ----------------------------------------------------
+    // ---- stage B3: one warp per heavy pair, a window of f32 score slots ----------------------------------------------------
     {
       const uint32_t n_heavy = s_nheavy;
       float* acc = s_acc + warp * kTile;
@@ -360,15 +512,59 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
         if (lane == 0) h = atomicAdd(&s_hpos, 1u);
         h = __shfl_sync(kFull, h, 0);
         if (h >= n_heavy) break;
-        const TQuery tq = TP.queries[G.query_base + s_heavy[h]];
-        const uint16_t* __restrict__ cl = TP.clauses + tq.clause_base;
+        const TQuery tq = s_tq[s_heavy[h]];
+        const uint16_t* __restrict__ cl = cl0 + tq.clause_base;
         uint32_t th_key = 0;
         if (lane == 0) th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
         th_key = __shfl_sync(kFull, th_key, 0);  // one value for the whole warp (the query-wide threshold moves)
-        const TileQueryState st = tile_query_state(th_key, tq, cl, s_max, sample_mode != 0);
+        const float theta_f = threshold_score(th_key);
+        const bool prune = (tq.flags & 1u) && theta_f > 0.0f && !sample_mode;
         const uint32_t n = tq.n_clauses;
+        if (lane == 0) ++st_heavy;
+        if (tq.op == kTileOpAnd) {  // lanes share the driving clause's postings; every lane looks its docs up in the others
+          uint32_t dmin = 0xFFFFFFFFu, drv = 0;
+          for (uint32_t c = 0; c < n; ++c) {
+            const uint32_t len = s_info[cl[c]] >> 16;
+            if (len < dmin) { dmin = len; drv = c; }
+          }
+          const uint32_t info = s_info[cl[drv]];
+          const uint32_t a = info & 0xFFFFu, e = a + (info >> 16);
+          uint32_t best = 0;
+          for (uint32_t p = a + lane; p < e; p += 32) {
+            const uint32_t off = s_off[p];
+            float sum;
+            if (!tile_eval_and(V, cl, n, drv, p, off, sum)) continue;
+            if (sample_mode) { if (!G.alive || is_alive(G.alive, lo + off)) best = max(best, score_to_key(sum)); }  // (a deleted doc bounds nothing)
+            else { ++st_compl; tile_push(P, tq.query, sum, lo + off, G.segment_ord, th_key, G.alive); }
+          }
+          if (lane == 0) st_ess += e - a;
+          if (sample_mode) {
+            for (uint32_t r = 0; r < kSamplePerTile; ++r) {
+              const uint32_t mk = __reduce_max_sync(kFull, best);
+              if (mk == 0u || mk < th_key) break;
+              const unsigned who = __ballot_sync(kFull, best == mk);
+              if (lane == (uint32_t)__ffs(who) - 1u) {
+                const uint32_t idx = atomicAdd(&TP.sample_count[tq.query], 1u);
+                if (idx < TP.sample_cap) TP.samples[(size_t)tq.query * TP.sample_cap + idx] = mk;
+                best = 0;
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
+        uint32_t n_e = n;
+        float ne = 0.0f;
+        if (prune) {
+          while (n_e > 0) {
+            const float b = ne + s_max[cl[n_e - 1u]];
+            if (!(b * 1.00001f < theta_f)) break;
+            ne = b;
+            --n_e;
+          }
+        }
         float wmax = 0.0f;
-        for (uint32_t c = 0; c < st.n_e; ++c) {  // clause order is the f32 summation order
+        for (uint32_t c = 0; c < n_e; ++c) {  // clause order is the f32 summation order
           const uint32_t info = s_info[cl[c]];
           const uint32_t a = info & 0xFFFFu, e = a + (info >> 16);
           for (uint32_t p = a + lane; p < e; p += 32) {
@@ -390,11 +586,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c)
-              if (__float_as_uint(vv[c]) != 0x80000000u) best = max(best, score_to_key(vv[c]));
+              if (__float_as_uint(vv[c]) != 0x80000000u && (!G.alive || is_alive(G.alive, lo + idx + c))) best = max(best, score_to_key(vv[c]));  // a deleted doc's score bounds nothing
           }
           for (uint32_t r = 0; r < kSamplePerTile; ++r) {
             const uint32_t m = __reduce_max_sync(kFull, best);
-            if (m == 0u || m < st.th_key) break;
+            if (m == 0u || m < th_key) break;
             const unsigned who = __ballot_sync(kFull, best == m);
             if (lane == (uint32_t)__ffs(who) - 1u) {
               const uint32_t idx = atomicAdd(&TP.sample_count[tq.query], 1u);
@@ -405,10 +601,9 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
           __syncwarp();
           continue;
         }
-        if (lane == 0) st_light += 0x100000000ull;  // (high half: heavy pairs)
         // nothing of this window can reach the threshold when even its largest partial sum plus the bound cannot
         const float mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(wmax)));
-        const bool cold = st.prune && (mx + st.ne) * 1.00001f < st.theta_f;
+        const bool cold = prune && (mx + ne) * 1.00001f < theta_f;
         if (cold && lane == 0) ++st_skip;
         for (uint32_t g = 0; g < kTile / 128u; ++g) {
           const uint32_t idx = g * 128u + lane * 4u;
@@ -421,16 +616,21 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
           for (int c = 0; c < 4; ++c) {
             float sum = vv[c];
             if (__float_as_uint(sum) == 0x80000000u) continue;  // untouched
-            if (st.prune && (sum + st.ne) * 1.00001f < st.theta_f) continue;
             const uint32_t off = idx + c;
-            for (uint32_t c2 = st.n_e; c2 < n; ++c2) {
+            float rem = ne;
+            bool dead = false;
+            for (uint32_t c2 = n_e; c2 < n; ++c2) {  // the non-essential suffix, with the same early exit as the flat path
+              if (prune && (sum + rem) * 1.00001f < theta_f) { dead = true; break; }
+              const uint32_t slot = cl[c2];
+              rem -= s_max[slot];
               bool f;
-              const float x = tile_find(s_off, s_score, s_info[cl[c2]], off, f);
+              const float x = tile_find(V, slot, off, f);
               if (f) sum = __fadd_rn(sum, x);
             }
+            if (dead) continue;
             ++st_compl;
-            if (score_to_key(sum) >= st.th_key) ++st_push;
-            tile_push(P, tq.query, sum, lo + off, G.segment_ord, st.th_key, G.alive);
+            if (score_to_key(sum) >= th_key) ++st_push;
+            tile_push(P, tq.query, sum, lo + off, G.segment_ord, th_key, G.alive);
           }
         }
         __syncwarp();
@@ -440,7 +640,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
   }
   if (TP.counters) {
     // warp-aggregated diagnostics
-    unsigned long long v[7] = {st_pairs, st_skip, st_light & 0xFFFFFFFFull, st_light >> 32, st_ess, st_compl, st_push};
+    unsigned long long v[7] = {st_pairs, st_skip, st_flat, st_heavy, st_ess, st_compl, st_push};
 #pragma unroll
     for (int i = 0; i < 7; ++i) {
       unsigned long long x = v[i];

@@ -29,6 +29,7 @@ def _load():
     lib.tq_ctx_destroy.argtypes = [vp]
     lib.tq_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.tq_segment_register.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
+    lib.tq_segment_register_positions.argtypes = [vp, C.c_uint32, C.c_uint32, u8p, sz]
     lib.tq_segment_unregister.argtypes = [vp, C.c_uint32, C.c_uint32]
     lib.tq_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_prepare.argtypes = [vp, C.POINTER(Query), sz, C.POINTER(vp)]
@@ -46,6 +47,15 @@ def _load():
     lib.tq_batch_results_copy_dev.argtypes = [vp, vp, vp, vp, vp]
     lib.tq_batch_destroy.argtypes = [vp]
     lib.tq_merge_topk_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.tq_batch_results_pack_dev.argtypes = [vp, vp]
+    lib.tq_merge_topk_packed_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, sz, vp]
+    lib.tq_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    lib.tq_multi_destroy.argtypes = [vp]
+    lib.tq_multi_last_error.restype = C.c_char_p
+    lib.tq_multi_last_error.argtypes = [vp]
+    lib.tq_multi_num_devices.argtypes = [vp]
+    lib.tq_multi_segment_register.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
+    lib.tq_multi_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_decode_postings.argtypes = [vp, C.POINTER(TermSeg), u32p, u32p]
     lib.tq_block_table.argtypes = [vp, C.POINTER(TermSeg), C.c_float, C.c_float, u32p, f32p]
     lib.tq_bm25_idf.restype = C.c_float
@@ -216,6 +226,11 @@ class Context:
         _check(LIB.tq_segment_register(self.h, segment_ord, field, max_doc, record_option, ptr(idx_body, u8p), idx_body.size,
                                        ptr(fn, u8p), 0 if fn is None else fn.size, ptr(al, u8p), 0 if al is None else al.size), self.h)
 
+    def register_positions(self, segment_ord, field, pos_bytes):
+        """The field's `.pos` sub-file of a registered segment (phrase queries)."""
+        p = np.ascontiguousarray(pos_bytes, dtype=np.uint8)
+        _check(LIB.tq_segment_register_positions(self.h, segment_ord, field, ptr(p, u8p), p.size), self.h)
+
     def segment_unregister(self, segment_ord, field):
         _check(LIB.tq_segment_unregister(self.h, segment_ord, field), self.h)
 
@@ -259,9 +274,47 @@ class Context:
         _check(LIB.tq_merge_topk_dev(self.h, n_lists, nq, stride, k, scores, segs, docs, counts, out_scores, out_segs, out_docs,
                                      out_counts), self.h)
 
+    def merge_topk_packed_dev(self, stream, n_lists, nq, stride, k, packed, pitch_words, out_packed):
+        """packed / out_packed: raw device addresses; stream: cudaStream_t as int (0 = the default stream).  No host sync."""
+        _check(LIB.tq_merge_topk_packed_dev(self.h, stream, n_lists, nq, stride, k, packed, pitch_words, out_packed), self.h)
+
     def close(self):
         if getattr(self, "h", None):
             LIB.tq_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+class MultiContext:
+    """tq_multi: several devices behind one handle (segments sharded over them, in-process fan-out and merge)."""
+
+    def __init__(self, devices):
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(LIB.tq_multi_create(arr, len(devices), C.byref(h)))
+        self.h = h
+
+    def segment_register(self, segment_ord, field, max_doc, record_option, idx_body, fieldnorm=None, alive=None, device_index=-1):
+        idx_body = np.ascontiguousarray(idx_body, dtype=np.uint8)
+        fn = None if fieldnorm is None else np.ascontiguousarray(fieldnorm, dtype=np.uint8)
+        al = None if alive is None else np.ascontiguousarray(alive, dtype=np.uint8)
+        rc = LIB.tq_multi_segment_register(self.h, device_index, segment_ord, field, max_doc, record_option, ptr(idx_body, u8p), idx_body.size,
+                                           ptr(fn, u8p), 0 if fn is None else fn.size, ptr(al, u8p), 0 if al is None else al.size)
+        if rc != 0:
+            raise TqError(f"tantivy_b200 error {rc}: {LIB.tq_multi_last_error(self.h).decode(errors='replace')}")
+
+    def search_batch(self, batch: QueryBatch, out=None):
+        stride, scores, segs, docs, counts = out or batch.alloc_out()
+        rc = LIB.tq_multi_search_batch(self.h, batch.ptr, batch.nq, stride, ptr(scores, f32p), ptr(segs, u32p), ptr(docs, u32p), ptr(counts, u32p))
+        if rc != 0:
+            raise TqError(f"tantivy_b200 error {rc}: {LIB.tq_multi_last_error(self.h).decode(errors='replace')}")
+        return scores, segs, docs, counts
+
+    def close(self):
+        if getattr(self, "h", None):
+            LIB.tq_multi_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -321,6 +374,10 @@ class Batch:
     def results_copy_dev(self, scores, segs, docs, counts):
         """raw device addresses (e.g. torch tensor .data_ptr()) of [nq, kmax] / [nq] buffers"""
         _check(LIB.tq_batch_results_copy_dev(self.h, scores, segs, docs, counts), self.ctx.h)
+
+    def results_pack_dev(self, packed):
+        """packed: raw device address of 3 * nq * kmax + nq 32-bit words (scores | segment ords | docs | counts)."""
+        _check(LIB.tq_batch_results_pack_dev(self.h, packed), self.ctx.h)
 
     def close(self):
         if getattr(self, "h", None):

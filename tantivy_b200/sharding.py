@@ -114,39 +114,80 @@ class ShardedIndex:
         return QueryBatch(out)
 
 
+def kth_of_gathered_keys(gathered, ks):
+    """Host twin of k_theta_from_keys (csrc/tq_tile.cuh): gathered = [n_shards, nq, k_stride] score keys (0 = nothing), ks[q] =
+    the query's k.  Returns per query the k-th largest key of the union, or 0 when fewer than k keys exist: the exact k-th best
+    score any single process holding all shards would have found over the same docs (merge_top_k's bound,
+    sort_key_top_collector.rs:76-95)."""
+    g = np.asarray(gathered, dtype=np.int64)
+    n_shards, nq, _ = g.shape
+    out = np.zeros(nq, dtype=np.int64)
+    for q in range(nq):
+        keys = np.sort(g[:, q, :].reshape(-1))[::-1]
+        k = int(ks[q])
+        out[q] = keys[k - 1] if k <= len(keys) else 0
+    return out
+
+
+def local_topkeys(scores, counts, ks, k_stride):
+    """Host twin of k_topkeys_export: the k best score keys of every query's rows, zero padded to k_stride."""
+    nq = len(ks)
+    out = np.zeros((nq, k_stride), dtype=np.int64)
+    for q in range(nq):
+        n = min(int(counts[q]), int(ks[q]), k_stride)
+        out[q, :n] = score_keys(np.sort(np.asarray(scores[q][:int(counts[q])], dtype=np.float32))[::-1][:n])
+    return out
+
+
 class CrossGpuMerger:
-    """NCCL all-gather of every rank's result rows + device merge (K7)."""
+    """The cross-shard steps of a sharded search, all enqueued on the batch's own CUDA stream (no host synchronisation
+    between the phases of a run):
+      * after every phase but the last, every rank exports the k best score keys it holds per query, ONE NCCL all-gather
+        moves them, and the exact k-th best of the union becomes every rank's threshold -- the bound a single GPU holding
+        all segments would prune with at that point;
+      * at the end ONE all-gather moves every rank's packed result rows (scores | segment ords | docs | counts) and
+        k_merge (merge_fruits, sort_key_top_collector.rs:76-95) merges them on the device."""
 
     def __init__(self, ctx, dist, device, nq, k):
         import torch
         self.ctx, self.dist, self.nq, self.k = ctx, dist, nq, k
         self.world = dist.get_world_size()
-        f32, i32 = torch.float32, torch.int32
-        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=device)  # noqa: E731
-        self.l = (mk((nq, k), f32), mk((nq, k), i32), mk((nq, k), i32), mk((nq,), i32))
-        self.g = (mk((self.world, nq, k), f32), mk((self.world, nq, k), i32), mk((self.world, nq, k), i32), mk((self.world, nq), i32))
-        self.o = (mk((nq, k), f32), mk((nq, k), i32), mk((nq, k), i32), mk((nq,), i32))
-        self.theta = mk((nq,), torch.int64)
         self.torch = torch
+        i32 = torch.int32
+        self.words = 3 * nq * k + nq
+        self.keys_l = torch.zeros((nq, k), dtype=i32, device=device)
+        self.keys_g = torch.zeros((self.world, nq, k), dtype=i32, device=device)
+        self.rows_l = torch.zeros((self.words,), dtype=i32, device=device)
+        self.rows_g = torch.zeros((self.world, self.words), dtype=i32, device=device)
+        self.rows_o = torch.zeros((self.words,), dtype=i32, device=device)
+        self._streams = {}
+
+    def _stream(self, batch):
+        h = batch.stream()
+        if h not in self._streams:
+            self._streams[h] = self.torch.cuda.ExternalStream(h)
+        return self._streams[h], h
 
     def run(self, batch):
-        """Runs a prepared batch with the cross-rank threshold exchange: after every threshold round of the unions the
-        per-query score keys are all-reduced (MAX, 8 bytes per query) over NCCL, so that every rank prunes against the
-        best lower bound any rank has found so far."""
+        """All phases of a prepared batch with the exact threshold exchange in between."""
+        ext, _ = self._stream(batch)
         n = batch.phases()
-        for phase in range(n):
-            batch.run_phase(phase)
-            if phase + 1 < n:
-                batch.thresholds_export_dev(self.theta.data_ptr())  # waits for the batch's stream
-                exchange_thresholds(self.dist, self.theta)
-                self.torch.cuda.synchronize()
-                batch.thresholds_import_dev(self.theta.data_ptr())
+        with self.torch.cuda.stream(ext):  # NCCL orders itself behind / in front of the kernels of this stream
+            for phase in range(n):
+                batch.run_phase(phase)
+                if phase + 1 < n:
+                    batch.topkeys_export_dev(self.keys_l.data_ptr(), self.k)
+                    self.dist.all_gather_into_tensor(self.keys_g, self.keys_l)
+                    batch.thresholds_from_keys_dev(self.keys_g.data_ptr(), self.world, self.k)
 
     def __call__(self, batch):
-        """batch: a finished tantivy_b200.Batch of this rank. Returns merged device tensors (every rank)."""
-        batch.results_copy_dev(*[t.data_ptr() for t in self.l])  # waits for the batch's stream
-        for g, l in zip(self.g, self.l):
-            self.dist.all_gather_into_tensor(g, l)
-        self.torch.cuda.synchronize()
-        self.ctx.merge_topk_dev(self.world, self.nq, self.k, self.k, *[t.data_ptr() for t in self.g], *[t.data_ptr() for t in self.o])
-        return self.o
+        """batch: a finished tantivy_b200.Batch of this rank.  Returns (scores, segment ords, docs, counts) device tensors of
+        the merged rows (every rank holds them); they are complete once the batch's stream is (torch.cuda.synchronize())."""
+        ext, h = self._stream(batch)
+        batch.results_pack_dev(self.rows_l.data_ptr())  # waits for the run; the copies are on the batch's stream
+        with self.torch.cuda.stream(ext):
+            self.dist.all_gather_into_tensor(self.rows_g, self.rows_l)
+            self.ctx.merge_topk_packed_dev(h, self.world, self.nq, self.k, self.k, self.rows_g.data_ptr(), self.words, self.rows_o.data_ptr())
+        r = self.nq * self.k
+        o = self.rows_o
+        return (o[:r].view(self.torch.float32).view(self.nq, self.k), o[r:2 * r].view(self.nq, self.k), o[2 * r:3 * r].view(self.nq, self.k), o[3 * r:])

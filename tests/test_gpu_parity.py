@@ -547,7 +547,7 @@ def test_tile_overflow_is_repeated_on_the_per_query_kernels(synth, hook):
 def test_tile_groups_split_on_capacity(synth):
     """More distinct dense lists than one tile buffer holds: the planner opens further groups (one decode pass each)."""
     ix, oi, base = synth
-    c = _ctx_with_env(TQ_TILE=1, TQ_TILE_MAX_DENS_X1000=400)
+    c = _ctx_with_env(TQ_TILE=1, TQ_TILE_MAX_DENS_X1000=320)  # {0,5},{0,4,5},{3,5},{4,5} fill the first group; {2,3,4} opens the second
     try:
         ix.register(c, segment_base=base)
         qb = QueryBatch(_tile_queries(ix, base))
@@ -620,3 +620,90 @@ def test_bench_config_and2_top10_10M(ctx):
     qb = QueryBatch([ix.query(TQ_OP_AND, [2 * i, 2 * i + 1], k, segment_base=base) for i in range(3) for k in (10, 100)])
     assert_same(ctx.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=32), qb.nq)
     ctx.segment_unregister(base, 0)
+
+
+# ---- the boundary under concurrency, and several devices behind one handle -------------------------------------------
+def test_concurrent_callers_on_one_ctx(ctx, synth):
+    """rayon threads call collect_segment concurrently (src/core/executor.rs:60-100): 8 host threads x tq_search_batch on ONE
+    ctx, new terms (block-table builds), cached terms, an invalid batch in the middle -- every call returns what it returns
+    alone, and the failing call poisons nothing."""
+    import threading
+    ix, oi, base = synth
+    batches = []
+    for t in range(8):
+        qs = [ix.query(TQ_OP_OR, [(t + i) % 6, (t + 2 * i + 1) % 6, 5], 10 + 7 * t, segment_base=base) for i in range(6) if (t + i) % 6 != (t + 2 * i + 1) % 6]
+        qs += [ix.query(TQ_OP_AND, [t % 6, (t + 1) % 6], 10, segment_base=base), ix.query(TQ_OP_TERM, [t % 6], 20, segment_base=base)]
+        batches.append(QueryBatch(qs))
+    expected = [ctx.search_batch(qb) for qb in batches]
+    fresh = _ctx_with_env(TQ_TILE=1 if ctx.engine == "tile" else 0)  # nothing cached: the threads race on the table builds
+    try:
+        ix.register(fresh, segment_base=base)
+        results, errors = [None] * 8, []
+        bad = dict(ix.query(TQ_OP_TERM, [0], 10, segment_base=base))
+        bad["term_segs"] = [(0, 424242, 0, 10, 0, 10)]  # unknown segment: the whole batch fails, after valid queries scheduled builds
+        bad_batch = QueryBatch([ix.query(TQ_OP_TERM, [4], 10, segment_base=base), bad])
+
+        def work(t):
+            try:
+                for rep in range(3):
+                    if t == 3 and rep == 1:
+                        with pytest.raises(T.TqError):
+                            fresh.search_batch(bad_batch)
+                    results[t] = fresh.search_batch(batches[t])
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        assert not errors, errors
+        for t in range(8):
+            for a, b in zip(results[t], expected[t]):
+                assert (a == b).all()
+        # the term the failing batch had scheduled is searchable afterwards
+        assert_same(fresh.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [4], 10, segment_base=base)])),
+                    oi.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [4], 10, segment_base=base)]), mode=0), 1)
+    finally:
+        fresh.close()
+
+
+def test_segment_churn_recycles_list_ids(ctx):
+    """register -> search -> unregister many times (merges): block tables and list ids are reclaimed with the segment."""
+    rng = np.random.default_rng(4242)
+    before = ctx.stats()["lists_cached"]
+    for _ in range(6):
+        segs = _random_segments(rng, 2, 4)
+        g, c, nq = _run_both(ctx, segs, [make_query(TQ_OP_OR, segs, [0, 1, 2, 3], 10), make_query(TQ_OP_AND, segs, [0, 1], 10)])
+        assert_same(g, c, nq)
+        for s in segs:
+            ctx.segment_unregister(s.segment_ord, 0)
+    assert ctx.stats()["lists_cached"] == before
+
+
+def _multi_check(devices, synth_ix, oi, base):
+    m = T.MultiContext(devices)
+    try:
+        for s in range(synth_ix.n_segments):
+            m.segment_register(base + s, 0, synth_ix.max_doc[s], synth_ix.record_option, synth_ix.body(s), synth_ix.fieldnorm(s), None)
+        qs = _tile_queries(synth_ix, base)[:24] + [synth_ix.query(TQ_OP_AND, [0, 1], 10, segment_base=base), synth_ix.query(TQ_OP_TERM, [2], 50, segment_base=base)]
+        qb = QueryBatch(qs)
+        assert_same(m.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+    finally:
+        m.close()
+
+
+def test_multi_handle_two_contexts_one_device(synth):
+    """tq_multi with two contexts (here on the same device): segments spread over them, concurrent phases, exact key exchange,
+    host merge -- the rows of a single process holding everything."""
+    ix, oi, base = synth
+    _multi_check([0, 0], ix, oi, base)
+
+
+def test_multi_handle_two_devices(synth):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    ix, oi, base = synth
+    _multi_check([0, 1], ix, oi, base)

@@ -14,8 +14,8 @@ import torch.multiprocessing as mp  # noqa: E402
 
 import tantivy_b200 as T  # noqa: E402
 from tantivy_b200._abi import TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM  # noqa: E402
-from tantivy_b200.sharding import (ShardedIndex, assign_segments, exchange_thresholds, key_scores, merge_rows_host,  # noqa: E402
-                                   score_keys)
+from tantivy_b200.sharding import (ShardedIndex, assign_segments, exchange_thresholds, key_scores, kth_of_gathered_keys,  # noqa: E402
+                                   local_topkeys, merge_rows_host, score_keys)
 
 DENS = [0.2, 0.05, 0.01, 0.001]
 N_SEG, DOCS = 4, 60_000
@@ -182,3 +182,77 @@ def test_two_rank_threshold_exchange_loses_nothing():
     # key mapping round trip
     x = np.array([0.0, 3.25e-3, 1.5, 1e9], dtype=np.float32)
     assert (key_scores(score_keys(x)) == x).all() and (np.diff(score_keys(x)) > 0).all()
+
+
+def _topkeys_worker(rank, world, port, out):
+    """The exact exchange of CrossGpuMerger.run on CPU: every rank exports the k best score keys of a SAMPLE of its shard (one
+    segment), one all-gather moves them, the k-th best key of the union is every rank's bound (k_topkeys_export /
+    k_theta_from_keys; host twins local_topkeys / kth_of_gathered_keys)."""
+    from oracle import tq_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ords = assign_segments(N_SEG, world, rank)
+        ix = T.SynthIndex(len(ords), DOCS, DENS, seed=99, segment_base=rank, segment_stride=world, n_threads=2)
+        shard = ShardedIndex(ix, ords, len(DENS), dist)
+        oi = O.OracleIndex()
+        shard.register(oi)
+        nq = len(QUERIES)
+        ks = [q[2] for q in QUERIES]
+        sample = shard.marshal(QUERIES)
+        keep = sample.term_segs["segment_ord"] == ords[0]
+        for i in range(nq):
+            row = sample.q[i]
+            first = (int(row["term_segs"]) - sample.term_segs.ctypes.data) // sample.term_segs.itemsize
+            sel = [j for j in range(first, first + int(row["n_term_segs"])) if keep[j]]
+            sample.term_segs[first:first + len(sel)] = sample.term_segs[sel]
+            row["n_term_segs"] = len(sel)
+        sc, _, _, ct = oi.search_batch(sample, mode=0)
+        mine = torch.from_numpy(local_topkeys(sc, ct, ks, KMAX))
+        lst = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(lst, mine)
+        gathered = torch.stack(lst).numpy()
+        bound = kth_of_gathered_keys(gathered, ks)
+        # the old protocol's bound: MAX over ranks of each rank's own k-th best
+        own = np.array([score_keys(sc[i, ks[i] - 1]) if ct[i] >= ks[i] else 0 for i in range(nq)], dtype=np.int64)
+        t = torch.from_numpy(own.copy())
+        exchange_thresholds(dist, t)
+        if rank == 0:
+            out.put(dict(bound=bound.tolist(), max_of_own=t.numpy().tolist(), gathered=gathered.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_topkeys_exchange_gives_the_union_kth():
+    from oracle import tq_oracle as O
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_topkeys_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single process over the two sampled segments (rank r sampled its first segment: global ordinals 0 and 1)
+    ix = T.SynthIndex(N_SEG, DOCS, DENS, seed=99, n_threads=2)
+    shard = ShardedIndex(ix, list(range(N_SEG)), len(DENS))
+    oi = O.OracleIndex()
+    shard.register(oi)
+    qb = shard.marshal(QUERIES)
+    keep = (qb.term_segs["segment_ord"] == 0) | (qb.term_segs["segment_ord"] == 1)
+    for i in range(len(QUERIES)):
+        row = qb.q[i]
+        first = (int(row["term_segs"]) - qb.term_segs.ctypes.data) // qb.term_segs.itemsize
+        sel = [j for j in range(first, first + int(row["n_term_segs"])) if keep[j]]
+        qb.term_segs[first:first + len(sel)] = qb.term_segs[sel]
+        row["n_term_segs"] = len(sel)
+    sc, _, _, ct = oi.search_batch(qb, mode=0)
+    full_sc, _, _, full_ct = oi.search_batch(shard.marshal(QUERIES), mode=0)
+    for i, (_, _, k) in enumerate(QUERIES):
+        want = int(score_keys(sc[i, k - 1])) if ct[i] >= k else 0
+        assert res["bound"][i] == want              # exactly the k-th best one process finds over the same docs
+        assert res["bound"][i] >= res["max_of_own"][i]  # never looser than the all-reduce(MAX) of the ranks' own k-th bests
+        if full_ct[i] >= k:                         # and a valid lower bound of the final k-th score
+            assert res["bound"][i] <= int(score_keys(full_sc[i, k - 1]))
