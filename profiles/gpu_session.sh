@@ -1,15 +1,16 @@
 #!/bin/bash
 # One GPU lease, several measurements; everything lands in gpurun_out/ (merged back by gpurun).
 mkdir -p gpurun_out
-# the snapshot may have been taken between an edit and its rebuild: make the libraries match the sources
 (make -C tantivy_b200/csrc -s 2>&1 | grep -E "error|Error" ; make -C oracle -s 2>&1 | grep -E "error|Error") > gpurun_out/build.log 2>&1
-echo "== probe (tile engine, or5 100M)" > gpurun_out/session.log
-timeout 600 python profiles/probe_tile.py or5_top100_100M_8seg 512 3 16 >> gpurun_out/session.log 2>&1
-echo "== launch list" >> gpurun_out/session.log
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_r2_tile.csv python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 > /dev/null 2>&1
-grep -E "k_tile|k_score|k_theta|k_final" gpurun_out/launches_r2_tile.csv | awk -F'","' '{print $5, $(NF)}' | head -12 >> gpurun_out/session.log
-echo "== pytest -m gpu" >> gpurun_out/session.log
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=6 2>&1 | tail -40 >> gpurun_out/session.log
-echo "== bench" >> gpurun_out/session.log
-timeout 600 python bench.py --steps 8 --warmup 3 >> gpurun_out/session.log 2>&1
-tail -c 3000 gpurun_out/session.log
+echo "== sweeps" > gpurun_out/session.log
+for lm in 8 16 32 64 192; do
+  echo "-- TQ_TILE_LIGHT_MAX=$lm" >> gpurun_out/session.log
+  TQ_TILE_LIGHT_MAX=$lm timeout 300 python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 2>&1 | grep '"step": 2' | cut -c1-420 >> gpurun_out/session.log
+done
+for u in 444 1776 3552; do
+  echo "-- TQ_TILE_UNITS=$u" >> gpurun_out/session.log
+  TQ_TILE_UNITS=$u timeout 300 python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 2>&1 | grep '"step": 2' | cut -c1-420 >> gpurun_out/session.log
+done
+echo "== ncu full k_tile + k_score_lists" >> gpurun_out/session.log
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"k_tile|k_score_lists" --launch-skip 5 --launch-count 5 -f -o gpurun_out/prof_tile_r2b python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 >> gpurun_out/session.log 2>&1
+tail -c 4000 gpurun_out/session.log

@@ -143,6 +143,7 @@ struct tq_ctx {
   unsigned long long* d_counters = nullptr;  // [0..8) k_or / k_or_strip window routes, [8..16) k_tile diagnostics
   uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 32, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
+  uint32_t tile_seg_cap_hook = 0;
   uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 24, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
@@ -253,6 +254,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 8192);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
   c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
   c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
+  c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces the window path)
   c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 24);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
@@ -643,23 +645,25 @@ struct TileGroupBuild {
   struct SegB {
     uint32_t segment_ord = 0, max_doc = 0;
     const uint8_t* alive = nullptr;
-    std::vector<TSlot> slots;
-    std::unordered_map<uint64_t, std::vector<uint32_t>> slot_of;  // hash of (list, weight, table) -> candidate slots
+    std::vector<TSlot> slots;  // (TSlot::pad chains the slots of one list: several weights / tables of a list are rare)
     std::vector<TQuery> queries;
     std::vector<uint16_t> clauses;
     double dens = 0;  // sum of doc_freq / max_doc over the slots: expected pairs per doc
   };
   std::vector<SegB> segs;
   std::unordered_map<uint32_t, uint32_t> seg_of;  // segment_ord -> index in segs
+  std::vector<uint32_t> slot_head;                 // list id -> first slot of that list in its segment (kNoSlot: none); a list lives in one segment
+  uint32_t find_slot(const SegB& sb, const QList& ql) const {
+    if (ql.list_id >= slot_head.size()) return kNoSlot;
+    for (uint32_t s = slot_head[ql.list_id]; s != kNoSlot; s = sb.slots[s].pad) {
+      const TSlot& sl = sb.slots[s];
+      if (memcmp(&sl.weight, &ql.weight, 4) == 0 && sl.cache_idx == ql.cache_idx) return s;
+    }
+    return kNoSlot;
+  }
   uint64_t pairs = 0;                              // elements of the pair arrays (doc_freq rounded up to 128 per slot)
   uint64_t list_bytes = 0;                         // postings-range bytes of the distinct lists
 };
-
-uint64_t slot_hash(uint32_t list_id, float w, uint32_t cache) {
-  uint32_t wb;
-  memcpy(&wb, &w, 4);
-  return ((uint64_t)list_id << 32 | wb) * 0x9E3779B97F4A7C15ull ^ (uint64_t)cache * 0xC2B2AE3D27D4EB4Full;
-}
 
 // Would the group still satisfy k_tile's limits with this query added?  Returns the number of NEW pair elements, or -1.
 int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
@@ -672,15 +676,7 @@ int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_
     size_t n_slots = sb ? sb->slots.size() : 0;
     double dens = sb ? sb->dens : 0.0;
     for (auto& h : sp.here) {
-      bool found = false;
-      if (sb) {
-        auto f = sb->slot_of.find(slot_hash(h.second.list_id, h.second.weight, h.second.cache_idx));
-        if (f != sb->slot_of.end())
-          for (uint32_t s : f->second) {
-            const TSlot& sl = sb->slots[s];
-            found = found || (sl.list_id == h.second.list_id && memcmp(&sl.weight, &h.second.weight, 4) == 0 && sl.cache_idx == h.second.cache_idx);
-          }
-      }
+      const bool found = sb && g.find_slot(*sb, h.second) != kNoSlot;
       if (!found) {
         ++n_slots;
         dens += (double)h.first / std::max(1u, sp.seg->max_doc);
@@ -729,20 +725,16 @@ uint64_t tile_admit(TileGroupBuild& g, uint32_t query, int op, const SegPlan* pl
     tq.op = (uint8_t)op;
     tq.flags = sp.prunable ? 1u : 0u;
     for (auto& h : sp.here) {
-      const uint64_t key = slot_hash(h.second.list_id, h.second.weight, h.second.cache_idx);
-      auto& cands = sb.slot_of[key];
-      uint32_t slot = kNoSlot;
-      for (uint32_t s : cands) {
-        const TSlot& sl = sb.slots[s];
-        if (sl.list_id == h.second.list_id && memcmp(&sl.weight, &h.second.weight, 4) == 0 && sl.cache_idx == h.second.cache_idx) slot = s;
-      }
+      uint32_t slot = g.find_slot(sb, h.second);
       if (slot == kNoSlot) {
         slot = (uint32_t)sb.slots.size();
         TSlot sl{};
         sl.list_id = h.second.list_id; sl.weight = h.second.weight; sl.cache_idx = h.second.cache_idx; sl.doc_freq = h.first;
         sl.big = kNoSlot;
+        if (h.second.list_id >= g.slot_head.size()) g.slot_head.resize((size_t)h.second.list_id + 1024, kNoSlot);
+        sl.pad = g.slot_head[h.second.list_id];  // chain
+        g.slot_head[h.second.list_id] = slot;
         sb.slots.push_back(sl);
-        cands.push_back(slot);
         sb.dens += (double)h.first / std::max(1u, sp.seg->max_doc);
         g.pairs += ((uint64_t)h.first + 127) / 128 * 128;
         g.list_bytes += h.range_len;
@@ -1085,7 +1077,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         TSlot sl = sb.slots[perm[i]];
         sl.tseg = (uint32_t)gs.segs.size();
         sl.pair_base = (uint32_t)pair_cursor;
-        if (is_big(sl)) sl.big = n_big++;
+        if (is_big(sl) && n_big < kTileMaxBig) sl.big = n_big++;  // (the densest ones: the order above is by descending doc_freq)
         const uint32_t n_total = sl.doc_freq / 128u + ((sl.doc_freq % 128u) ? 1u : 0u);
         for (uint32_t b0 = 0; b0 < n_total; b0 += 64u) gs.chunks.push_back(SChunk{(uint32_t)gs.slots.size(), b0, std::min(n_total, b0 + 64u)});
         pair_cursor += ((uint64_t)sl.doc_freq + 127) / 128 * 128;
@@ -1277,6 +1269,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     TP.max_big = gs.max_big;
     TP.max_queries = (gs.max_queries + 1u) & ~1u;
     TP.seg_cap = std::min<uint32_t>(4096u, std::max<uint32_t>(256u, 3u * TP.max_queries));
+    if (c->tile_seg_cap_hook) TP.seg_cap = c->tile_seg_cap_hook;
     TP.light_max = c->tile_light_max;
     TP.cl_cap = gs.max_clause_words <= 16384u ? ((gs.max_clause_words + 3u) & ~3u) : 0u;
     run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots, TP.max_big, TP.max_queries, TP.seg_cap, TP.cl_cap);

@@ -46,6 +46,7 @@ constexpr uint32_t kTileThreads = 256;
 constexpr uint32_t kTileWarps = kTileThreads / 32;
 constexpr uint32_t kTileMaxQueries = 1024;  // (query, segment) pairs of one group in one segment
 constexpr uint32_t kTileMaxSlots = 4096;    // distinct scored lists of one group in one segment
+constexpr uint32_t kTileMaxBig = 64;        // dense lists of one segment that get a tile index and a presence map
 constexpr uint32_t kTileMaxPairs = 12288;   // pairs of one tile held in shared memory (start | len are 16-bit fields)
 constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
@@ -145,8 +146,10 @@ __global__ void __launch_bounds__(kThreads) k_score_lists(const BatchParams P, c
       s[i] = valid ? bm25_score_id(sc, id[i], tf[i]) : 0.0f;
       if (!valid) doc[i] = 0xFFFFFFFFu;
     }
-    reinterpret_cast<uint4*>(out_docs + g0)[0] = make_uint4(doc[0], doc[1], doc[2], doc[3]);
-    reinterpret_cast<float4*>(out_scores + g0)[0] = make_float4(s[0], s[1], s[2], s[3]);
+    // the pairs are read back once, by another kernel, after the whole pass: stream them past the L2 lines the gathers re-use
+    // (fieldnorm bytes, block tables)
+    __stcs(reinterpret_cast<uint4*>(out_docs + g0), make_uint4(doc[0], doc[1], doc[2], doc[3]));
+    __stcs(reinterpret_cast<float4*>(out_scores + g0), make_float4(s[0], s[1], s[2], s[3]));
     if (tix) {  // tile index of a dense list: tix[t] = first pair with doc >= t * kTile
       uint32_t pd = __shfl_up_sync(kFull, doc[3], 1);
       if (lane == 0) pd = prev_last;

@@ -544,6 +544,30 @@ def test_tile_overflow_is_repeated_on_the_per_query_kernels(synth, hook):
         c.close()
 
 
+@pytest.mark.parametrize("hook", [dict(TQ_TILE_SEG_CAP=8), dict(TQ_TILE_LIGHT_MAX=0), dict(TQ_TILE_LIGHT_MAX=100000), dict(TQ_TILE_SAMPLE_DIV=0),
+                                  dict(TQ_TILE_BIG_MIN=1), dict(TQ_TILE_BIG_MIN=100000), dict(TQ_TILE_UNITS=1), dict(TQ_TILE_ROUND_DIV1=2, TQ_TILE_ROUND_DIV2=2)])
+def test_tile_paths_agree(synth, hook):
+    """Every route through k_tile gives the same rows: a full work list (pairs overflow to the window path), window path only,
+    flat path only, no sample launch, every list dense (bitmap lookups) / every list sparse (binary searches), one CTA per launch,
+    other launch cuts."""
+    ix, oi, base = synth
+    c = _ctx_with_env(TQ_TILE=1, **hook)
+    try:
+        ix.register(c, segment_base=base)
+        qs = _tile_queries(ix, base)
+        qs += [ix.query(TQ_OP_AND, terms, k, segment_base=base) for k in (10, 200) for terms in ([0, 1], [0, 3], [1, 4], [0, 5], [2, 3, 4], [0, 1, 2])]
+        qs += [ix.query(TQ_OP_TERM, [t], 10, segment_base=base) for t in range(6)]
+        qb = QueryBatch(qs)
+        assert_same(c.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+        st = c.stats()
+        assert st["tile_groups"] == 1
+        # without a sample launch the first exact launch hands over every match of its tiles: k = 1000 overflows its candidate
+        # region and the batch is repeated on the per-query kernels (still the oracle's rows, asserted above)
+        assert st["tile_fallbacks"] == (1 if "TQ_TILE_SAMPLE_DIV" in hook else 0)
+    finally:
+        c.close()
+
+
 def test_tile_groups_split_on_capacity(synth):
     """More distinct dense lists than one tile buffer holds: the planner opens further groups (one decode pass each)."""
     ix, oi, base = synth
