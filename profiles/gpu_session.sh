@@ -2,15 +2,16 @@
 # One GPU lease, several measurements; everything lands in gpurun_out/ (merged back by gpurun).
 mkdir -p gpurun_out
 (make -C tantivy_b200/csrc -s 2>&1 | grep -E "error|Error" ; make -C oracle -s 2>&1 | grep -E "error|Error") > gpurun_out/build.log 2>&1
-echo "== sweeps" > gpurun_out/session.log
-for lm in 8 16 32 64 192; do
-  echo "-- TQ_TILE_LIGHT_MAX=$lm" >> gpurun_out/session.log
-  TQ_TILE_LIGHT_MAX=$lm timeout 300 python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 2>&1 | grep '"step": 2' | cut -c1-420 >> gpurun_out/session.log
+echo "== probe (tile engine, or5 100M)" > gpurun_out/session.log
+timeout 600 python profiles/probe_tile.py or5_top100_100M_8seg 512 2 16 2>&1 | cut -c1-460 >> gpurun_out/session.log
+echo "== pytest -m gpu" >> gpurun_out/session.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=6 2>&1 | tail -30 >> gpurun_out/session.log
+echo "== sweeps" >> gpurun_out/session.log
+for cfg in "TQ_TILE_ROUND_DIV1=16 TQ_TILE_ROUND_DIV2=4" "TQ_TILE_ROUND_DIV1=32 TQ_TILE_ROUND_DIV2=4" "TQ_TILE_SAMPLE_DIV=16" "TQ_TILE_SAMPLE_DIV=64" "TQ_TILE_LIGHT_MAX=48" "TQ_TILE_BIG_MIN=12" "TQ_TILE_BIG_MIN=48"; do
+  echo "-- $cfg" >> gpurun_out/session.log
+  env $cfg timeout 300 python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 2>&1 | grep '"step": 2' | cut -c1-330 >> gpurun_out/session.log
 done
-for u in 444 1776 3552; do
-  echo "-- TQ_TILE_UNITS=$u" >> gpurun_out/session.log
-  TQ_TILE_UNITS=$u timeout 300 python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 2>&1 | grep '"step": 2' | cut -c1-420 >> gpurun_out/session.log
-done
-echo "== ncu full k_tile + k_score_lists" >> gpurun_out/session.log
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:"k_tile|k_score_lists" --launch-skip 5 --launch-count 5 -f -o gpurun_out/prof_tile_r2b python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 >> gpurun_out/session.log 2>&1
-tail -c 4000 gpurun_out/session.log
+echo "== launch list" >> gpurun_out/session.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20 --csv --log-file gpurun_out/launches_r2_tile.csv python profiles/probe_tile.py or5_top100_100M_8seg 512 1 0 > /dev/null 2>&1
+grep -E "k_tile|k_score|k_theta|k_final" gpurun_out/launches_r2_tile.csv | awk -F'","' '{print $5, $(NF)}' | tail -9 >> gpurun_out/session.log
+tail -c 3500 gpurun_out/session.log

@@ -141,10 +141,10 @@ struct tq_ctx {
   tq_stats stats{};
   uint32_t term_blocks_per_unit, and_blocks_per_unit, or_tiles_per_unit;
   unsigned long long* d_counters = nullptr;  // [0..8) k_or / k_or_strip window routes, [8..16) k_tile diagnostics
-  uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 32, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
+  uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 16, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_seg_cap_hook = 0;
-  uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 24, tile_units = 148 * 6;
+  uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 12, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
 
@@ -245,7 +245,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->or_prune = env_u32("TQ_OR_PRUNE", 0);  // MaxScore route: exact, but only pays off for small k / rare terms
   c->tile = env_u32("TQ_TILE", 1);                          // unions take the shared-decode tile engine (tq_tile.cuh); 0 = per-query kernels only
   c->tile_scratch_mb = env_u32("TQ_TILE_SCRATCH_MB", 24576);  // (doc, score) pairs one batch may materialise
-  c->tile_sample_div = env_u32("TQ_TILE_SAMPLE_DIV", 32);    // share of the tiles in the sample launch (0/1: none)
+  c->tile_sample_div = env_u32("TQ_TILE_SAMPLE_DIV", 16);    // share of the tiles in the sample launch (0/1: none)
   c->tile_round_div1 = env_u32("TQ_TILE_ROUND_DIV1", 8);     // the exact launches end at 1/8, 1/2 and all of a segment's tiles
   c->tile_round_div2 = env_u32("TQ_TILE_ROUND_DIV2", 2);
   c->tile_light_max = env_u32("TQ_TILE_LIGHT_MAX", 96);      // essential postings up to which a (query, tile) pair is evaluated posting by posting
@@ -255,7 +255,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
   c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
   c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces the window path)
-  c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 24);          // expected pairs per tile from which a list gets a tile index
+  c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 12);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMemset(c->d_lists, 0, (size_t)c->lists_cap * sizeof(ListDesc));
@@ -1106,7 +1106,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       gs.segs.push_back(G);
     }
     tix_total_words += gs.tix_words;
-    gs.p_cap = (uint32_t)std::min<double>(kTileMaxPairs, std::max(1024.0, dens_max * kTile * 1.5 + 256.0));
+    gs.p_cap = (uint32_t)std::min<double>(kTileMaxPairs, std::max(1024.0, dens_max * kTile * 1.25 + 192.0));
     gs.p_cap = (gs.p_cap + 63u) & ~63u;
     if (c->tile_pcap_hook) gs.p_cap = c->tile_pcap_hook;  // (test hook: overflowing tiles)
     // Launches: [0] samples scores on a spread of short tile runs, [1..3] are exact and cover every tile once.
@@ -1181,7 +1181,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   if (!gstage.empty()) {
     uint64_t sample_units_tiles = 0;
     for (auto& gs : gstage) for (auto& u : gs.units[0]) sample_units_tiles += u.t1 - u.t0;
-    sample_cap = (uint32_t)std::min<uint64_t>(1u << 16, std::max<uint64_t>(256, sample_units_tiles * kSamplePerTile));
+    sample_cap = (uint32_t)std::min<uint64_t>(1u << 16, std::max<uint64_t>(256, sample_units_tiles * 8u));
     size_t so2 = 0;
     to_docs = so2; so2 = align(so2 + (size_t)pair_cursor * 4);
     to_scores = so2; so2 = align(so2 + (size_t)pair_cursor * 4);
@@ -1268,7 +1268,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     TP.max_slots = gs.max_slots;
     TP.max_big = gs.max_big;
     TP.max_queries = (gs.max_queries + 1u) & ~1u;
-    TP.seg_cap = std::min<uint32_t>(4096u, std::max<uint32_t>(256u, 3u * TP.max_queries));
+    TP.seg_cap = std::min<uint32_t>(2048u, std::max<uint32_t>(256u, 2u * TP.max_queries));
     if (c->tile_seg_cap_hook) TP.seg_cap = c->tile_seg_cap_hook;
     TP.light_max = c->tile_light_max;
     TP.cl_cap = gs.max_clause_words <= 16384u ? ((gs.max_clause_words + 3u) & ~3u) : 0u;

@@ -30,8 +30,9 @@
 //                       give bit-identical scores;
 //                     * survivors (score key >= the query's threshold) go to the query's candidate region, k_final
 //                       (TopNHeap / merge_fruits) selects exactly.
-//   thresholds      a first launch over 1/32 of the tiles only SAMPLES scores (the best few per (query, tile)); the k-th best
-//                   sample is a valid lower bound of the final k-th score (k_theta_samples).  The exact launches follow,
+//   thresholds      a first launch over 1/16 of the tiles only SAMPLES scores (the complete scores of the docs that hold one of
+//                   a union's two heaviest clauses / a conjunction's matches); the k-th best sample is a valid lower bound of
+//                   the final k-th score (k_theta_samples).  The exact launches follow,
 //                   each ending in k_theta (exact k-th best candidate so far), so most tiles are visited under a
 //                   near-final threshold.  Sampled tiles are visited again by the exact launches: nothing is pushed twice.
 //
@@ -48,6 +49,7 @@ constexpr uint32_t kTileMaxQueries = 1024;  // (query, segment) pairs of one gro
 constexpr uint32_t kTileMaxSlots = 4096;    // distinct scored lists of one group in one segment
 constexpr uint32_t kTileMaxBig = 64;        // dense lists of one segment that get a tile index and a presence map
 constexpr uint32_t kTileMaxPairs = 12288;   // pairs of one tile held in shared memory (start | len are 16-bit fields)
+constexpr uint32_t kTileExactWindows = 2;   // warps that take heavy pairs in an exact launch (each owns a window of kTile f32 slots)
 constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr uint32_t kTileOpAnd = 1;  // TQ_OP_AND; term queries and unions share one evaluation (a union of one clause)
@@ -108,7 +110,7 @@ struct TileParams {
 
 
 // ---- K1 + K2, once per batch -------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_score_lists(const BatchParams P, const TileParams TP, uint32_t chunk_base) {
+__global__ void __launch_bounds__(kThreads, 4) k_score_lists(const BatchParams P, const TileParams TP, uint32_t chunk_base) {
   const SChunk C = TP.chunks[chunk_base + blockIdx.x];
   const TSlot sl = TP.slots[C.slot];
   const ListDesc L = P.lists[sl.list_id];
@@ -178,6 +180,7 @@ struct TileView {
   const uint32_t* s_info;
   const uint32_t* s_bits;   // [max_big][32]
   const uint16_t* s_rank;   // [max_big][32] pairs of the slot before word w
+  const uint32_t* s_mask;   // [max_slots] sparse slots: bit j set = the slot lists a doc of the tile's j-th 32-doc stripe
   uint32_t n_big;
 };
 
@@ -190,14 +193,22 @@ __device__ __forceinline__ float tile_find(const TileView& V, uint32_t slot, uin
     if (!found) return 0.0f;
     return V.s_score[(info & 0xFFFFu) + V.s_rank[slot * 32u + (off >> 5)] + __popc(w & (bit - 1u))];
   }
+  // sparse slot: most lookups miss -- one stripe bit answers them; the rest scans the few pairs of the slot
+  found = false;
+  if (!((V.s_mask[slot] >> (off >> 5)) & 1u)) return 0.0f;
   uint32_t lo = info & 0xFFFFu;
   const uint32_t end = lo + (info >> 16);
-  uint32_t hi = end;
-  while (lo < hi) {
-    const uint32_t m = (lo + hi) >> 1;
-    if (V.s_off[m] < off) lo = m + 1u; else hi = m;
+  if (end - lo > 8u) {
+    uint32_t hi = end;
+    while (hi - lo > 4u) {
+      const uint32_t m = (lo + hi) >> 1;
+      if (V.s_off[m] < off) lo = m + 1u; else hi = m;
+    }
   }
-  found = lo < end && V.s_off[lo] == off;
+  for (; lo < end; ++lo) {
+    const uint32_t o = V.s_off[lo];
+    if (o >= off) { found = o == off; break; }
+  }
   return found ? V.s_score[lo] : 0.0f;
 }
 
@@ -211,14 +222,26 @@ __device__ __forceinline__ void tile_push(const BatchParams& P, uint32_t query, 
   if (idx < Q.cand_cap) P.cands[Q.cand_base + idx] = Cand{key, segment_ord, doc, 0u};
 }
 
-// One (query, tile) pair that is evaluated posting by posting: what every posting's thread needs to know.
+// One (query, tile) pair that is evaluated posting by posting: what every posting's thread needs to know (16 bytes).
 struct TileQ {
-  uint32_t query;        // ordinal in the batch
-  uint32_t clause_base;  // into TileParams::clauses
+  uint16_t qi;           // the query: index into the CTA's copy of the segment's queries (batch ordinal, clause slots)
+  uint8_t n_op;          // clauses [0:6) | op << 6
+  uint8_t ne_prune;      // essential prefix (unions) / driving clause (conjunctions) [0:6) | prune << 7
   uint32_t th_key;       // the query's threshold when the tile was entered
   float ne;              // bound of the non-essential suffix in this tile (unions); 0 for conjunctions
-  uint16_t n, n_e;       // clauses; essential prefix (unions) / driving clause (conjunctions)
-  uint16_t op, prune;
+  uint32_t shared_stripes;  // unions: 32-doc stripes of the tile in which more than one essential clause lists a doc (a posting
+                            // outside them is the only essential posting of its doc: no lookup is needed to know its partial sum)
+  __device__ __forceinline__ uint32_t n() const { return n_op & 63u; }
+  __device__ __forceinline__ uint32_t op() const { return n_op >> 6; }
+  __device__ __forceinline__ uint32_t n_e() const { return ne_prune & 63u; }
+  __device__ __forceinline__ bool prune() const { return (ne_prune & 128u) != 0; }
+};
+// the segment's queries as the CTA keeps them on chip (8 bytes)
+struct TileTQ {
+  uint32_t query;
+  uint16_t clause_base;  // local to the segment
+  uint8_t n_clauses;
+  uint8_t op_flags;      // op [0:2) | prunable << 7
 };
 struct TileSeg { uint16_t q, clause, start, len; };  // postings [start, start + len) of one essential clause of flat pair q
 
@@ -227,19 +250,23 @@ struct TileSeg { uint16_t q, clause, start, len; };  // postings [start, start +
 __device__ __forceinline__ bool tile_eval_or(const TileView& V, const float* __restrict__ s_max, const uint16_t* __restrict__ cl, const TileQ& q,
                                              uint32_t c, uint32_t p, uint32_t off, float theta_f, float& sum) {
   bool f;
-  for (uint32_t c1 = 0; c1 < c; ++c1) {  // an earlier essential clause lists the doc: it is evaluated there
-    tile_find(V, cl[c1], off, f);
-    if (f) return false;
-  }
+  const uint32_t n_e = q.n_e(), n = q.n();
+  const bool prune = q.prune();
   sum = V.s_score[p];  // (-0.0 + s == s: SumCombiner starts from 0, score_combiner.rs:39-57)
-  for (uint32_t c2 = c + 1u; c2 < q.n_e; ++c2) {
-    const float v = tile_find(V, cl[c2], off, f);
-    if (f) sum = __fadd_rn(sum, v);
+  if ((q.shared_stripes >> (off >> 5)) & 1u) {  // another essential clause lists a doc near this one: look the doc up
+    for (uint32_t c1 = 0; c1 < c; ++c1) {  // an earlier essential clause lists the doc: it is evaluated there
+      tile_find(V, cl[c1], off, f);
+      if (f) return false;
+    }
+    for (uint32_t c2 = c + 1u; c2 < n_e; ++c2) {
+      const float v = tile_find(V, cl[c2], off, f);
+      if (f) sum = __fadd_rn(sum, v);
+    }
   }
   // the non-essential suffix, densest last; stop as soon as what is left cannot lift the doc over the threshold
   float rem = q.ne;
-  for (uint32_t c2 = q.n_e; c2 < q.n; ++c2) {
-    if (q.prune && (sum + rem) * 1.00001f < theta_f) return false;
+  for (uint32_t c2 = n_e; c2 < n; ++c2) {
+    if (prune && (sum + rem) * 1.00001f < theta_f) return false;
     const uint32_t slot = cl[c2];
     rem -= s_max[slot];
     const float v = tile_find(V, slot, off, f);
@@ -266,26 +293,33 @@ __device__ __forceinline__ bool tile_eval_and(const TileView& V, const uint16_t*
   return true;
 }
 
+// Shared memory of a k_tile CTA: the work list (TileQ records + segments) and two windows for the rare heavy pairs ...
+__host__ __device__ constexpr size_t tile_union_bytes(uint32_t max_queries, uint32_t seg_cap) {
+  return ((size_t)kTileExactWindows * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + (size_t)seg_cap * sizeof(TileSeg) + 15) & ~(size_t)15;
+}
 __host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots, uint32_t max_big, uint32_t max_queries, uint32_t seg_cap,
                                                       uint32_t cl_cap) {
-  return (size_t)p_cap * 4 + (size_t)kTileWarps * kTile * 4 + (size_t)max_slots * 16 + (size_t)max_big * 128 + (size_t)max_queries * sizeof(TileQ) +
-         (size_t)max_queries * sizeof(TQuery) + (size_t)seg_cap * sizeof(TileSeg) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 +
-         (size_t)cl_cap * 2 + 64;
+  return (size_t)p_cap * 4 + tile_union_bytes(max_queries, seg_cap) + (size_t)max_slots * 20 + (size_t)max_big * 128 +
+         (size_t)max_queries * sizeof(TileTQ) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 + (size_t)cl_cap * 2 + 64;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, const TileParams TP, uint32_t unit_base, uint32_t sample_mode) {
+__global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, const TileParams TP, uint32_t unit_base, uint32_t sample_mode) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   float* s_score = reinterpret_cast<float*>(s_dyn);                            // [p_cap]
-  float* s_acc = s_score + TP.p_cap;                                           // [kTileWarps][kTile]
-  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_acc + kTileWarps * kTile);  // [max_slots]
+  unsigned char* s_union = reinterpret_cast<unsigned char*>(s_score + TP.p_cap);
+  const size_t union_bytes = tile_union_bytes(TP.max_queries, TP.seg_cap);
+  const uint32_t n_win = kTileExactWindows;
+  float* s_acc = reinterpret_cast<float*>(s_union);                            // [n_win][kTile] windows of the heavy pairs
+  TileQ* s_q = reinterpret_cast<TileQ*>(s_acc + kTileExactWindows * kTile);    // [max_queries] flat pairs of this tile (exact launches)
+  TileSeg* s_seg = reinterpret_cast<TileSeg*>(s_q + TP.max_queries);           // [seg_cap]
+  uint32_t* s_info = reinterpret_cast<uint32_t*>(s_union + union_bytes);       // [max_slots]
   float* s_max = reinterpret_cast<float*>(s_info + TP.max_slots);              // [max_slots] largest score of the slot in this tile (>= 0)
   uint32_t* s_cur = reinterpret_cast<uint32_t*>(s_max + TP.max_slots);         // [max_slots] small slots: first pair not staged yet
   uint32_t* s_nxt = s_cur + TP.max_slots;                                      // [max_slots] ... and its doc (0xFFFFFFFF: list exhausted)
-  uint32_t* s_bits = s_nxt + TP.max_slots;                                     // [max_big][32]
-  TileQ* s_q = reinterpret_cast<TileQ*>(s_bits + TP.max_big * 32u);            // [max_queries] flat pairs of this tile
-  TQuery* s_tq = reinterpret_cast<TQuery*>(s_q + TP.max_queries);              // [max_queries] this segment's queries
-  TileSeg* s_seg = reinterpret_cast<TileSeg*>(s_tq + TP.max_queries);          // [seg_cap]
-  uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_seg + TP.seg_cap);          // [max_big][32]
+  uint32_t* s_mask = s_nxt + TP.max_slots;                                     // [max_slots] stripe masks of the sparse slots
+  uint32_t* s_bits = s_mask + TP.max_slots;                                    // [max_big][32]
+  TileTQ* s_tq = reinterpret_cast<TileTQ*>(s_bits + TP.max_big * 32u);         // [max_queries] this segment's queries
+  uint16_t* s_rank = reinterpret_cast<uint16_t*>(s_tq + TP.max_queries);       // [max_big][32]
   uint16_t* s_off = s_rank + TP.max_big * 32u;                                 // [p_cap]
   uint16_t* s_heavy = s_off + TP.p_cap;                                        // [max_queries]
   uint16_t* s_cl = s_heavy + TP.max_queries;                                   // [cl_cap] this segment's clause slots
@@ -296,16 +330,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
   const TSlot* __restrict__ slots = TP.slots + G.slot_base;
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const float neg_zero = __uint_as_float(0x80000000u);
-  const TileView V{s_off, s_score, s_info, s_bits, s_rank, G.n_big};
-  for (uint32_t i = tid; i < kTileWarps * kTile; i += kTileThreads) s_acc[i] = neg_zero;
+  const TileView V{s_off, s_score, s_info, s_bits, s_rank, s_mask, G.n_big};
+  for (uint32_t i = tid; i < n_win * kTile; i += kTileThreads) s_acc[i] = neg_zero;
   if (tid < 8) s_stat[tid] = 0ull;
   // the segment's queries and their clause slots are read for every tile: keep them on chip (clause_base becomes an index into cl0)
   const bool cl_staged = G.n_clause_words <= TP.cl_cap;
   const uint16_t* __restrict__ cl0 = cl_staged ? s_cl : TP.clauses + G.clause_base;
   for (uint32_t i = tid; i < G.n_queries; i += kTileThreads) {
-    TQuery tq = TP.queries[G.query_base + i];
-    tq.clause_base -= G.clause_base;
-    s_tq[i] = tq;
+    const TQuery tq = TP.queries[G.query_base + i];
+    s_tq[i] = TileTQ{tq.query, (uint16_t)(tq.clause_base - G.clause_base), (uint8_t)tq.n_clauses, (uint8_t)((tq.op & 3u) | ((tq.flags & 1u) << 7))};
   }
   if (cl_staged)
     for (uint32_t i = tid; i < G.n_clause_words; i += kTileThreads) s_cl[i] = TP.clauses[G.clause_base + i];
@@ -361,37 +394,66 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
     }
     for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {  // sparse lists: one thread walks its cursor
       uint32_t nd = s_nxt[s];
-      if (nd >= hi) { s_info[s] = 0u; s_max[s] = 0.0f; continue; }
+      if (nd >= hi) { s_info[s] = 0u; s_max[s] = 0.0f; s_mask[s] = 0u; continue; }
       const TSlot sl = slots[s];
       const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base;
       const float* __restrict__ sc = TP.p_scores + sl.pair_base;
       const uint32_t cur = s_cur[s];
-      uint32_t n = 1;  // nd < hi: the pair at the cursor belongs to this tile
-      for (;;) {       // four docs per round trip
-        const uint32_t c = cur + n;
-        uint32_t d4[4];
+      // the pair at the cursor belongs to this tile (nd < hi); fetch it and the next three, docs and scores, in ONE round trip
+      uint32_t d4[4];
+      float v4[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d4[i] = c + i < sl.doc_freq ? __ldg(d + c + i) : 0xFFFFFFFFu;
-        uint32_t k = 0;
+      for (int i = 0; i < 4; ++i) {
+        const bool in = cur + i < sl.doc_freq;
+        d4[i] = in ? __ldg(d + cur + i) : 0xFFFFFFFFu;
+        v4[i] = in ? __ldg(sc + cur + i) : 0.0f;
+      }
+      uint32_t n = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) k += d4[i] < hi ? 1u : 0u;  // ascending: the ones below hi are a prefix
-        n += k;
-        if (k < 4u) { nd = d4[k]; break; }
+      for (int i = 0; i < 4; ++i) n += d4[i] < hi ? 1u : 0u;  // ascending: the ones below hi are a prefix
+      if (n == 4u) {  // (rare for a sparse list) keep walking
+        for (;;) {
+          const uint32_t c = cur + n;
+          uint32_t e4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) e4[i] = c + i < sl.doc_freq ? __ldg(d + c + i) : 0xFFFFFFFFu;
+          uint32_t k = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) k += e4[i] < hi ? 1u : 0u;
+          n += k;
+          if (k < 4u) { nd = e4[k]; break; }
+        }
+      } else {
+        nd = d4[n];
       }
       s_cur[s] = cur + n;
       s_nxt[s] = nd;
       const uint32_t base = atomicAdd(&s_total, n);
       float mx = 0.0f;
+      uint32_t mask = 0;
       if (base + n <= TP.p_cap) {
-        for (uint32_t i = 0; i < n; ++i) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if ((uint32_t)i < n) {
+            const uint32_t off = d4[i] - lo;
+            s_off[base + i] = (uint16_t)off;
+            s_score[base + i] = v4[i];
+            mask |= 1u << (off >> 5);
+            mx = fmaxf(mx, v4[i]);
+          }
+        }
+        for (uint32_t i = 4; i < n; ++i) {
           const float v = __ldg(sc + cur + i);
-          s_off[base + i] = (uint16_t)(__ldg(d + cur + i) - lo);
+          const uint32_t off = __ldg(d + cur + i) - lo;
+          s_off[base + i] = (uint16_t)off;
           s_score[base + i] = v;
+          mask |= 1u << (off >> 5);
           mx = fmaxf(mx, v);
         }
       }
       s_info[s] = (base & 0xFFFFu) | (n << 16);
       s_max[s] = mx;
+      s_mask[s] = mask;
     }
     __syncthreads();
     if (s_total > TP.p_cap) {  // more pairs than the tile buffer holds: give the batch back to the per-query kernels
@@ -403,17 +465,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
     // skipped: no doc of the tile can reach the query's threshold;  flat: the essential postings become work items that the CTA's
     // threads share evenly (B2);  heavy: a warp accumulates the query's window (B3; sample launches, and pairs with many postings).
     for (uint32_t qi = tid; qi < G.n_queries; qi += kTileThreads) {
-      const TQuery tq = s_tq[qi];
+      const TileTQ tq = s_tq[qi];
       const uint16_t* __restrict__ cl = cl0 + tq.clause_base;
       const uint32_t th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
       const float theta_f = threshold_score(th_key);
-      const bool prune = (tq.flags & 1u) && theta_f > 0.0f && !sample_mode;
-      const uint32_t n = tq.n_clauses;
+      const bool prune = (tq.op_flags & 128u) && theta_f > 0.0f && !sample_mode;
+      const uint32_t n = tq.n_clauses, op = tq.op_flags & 3u;
       ++st_pairs;
       TileQ rec;
-      rec.query = tq.query; rec.clause_base = tq.clause_base; rec.th_key = th_key; rec.n = (uint16_t)n; rec.op = tq.op; rec.prune = prune ? 1 : 0;
-      uint32_t cnt = 0, n_segs = 0;
-      if (tq.op == kTileOpAnd) {
+      rec.qi = (uint16_t)qi; rec.th_key = th_key; rec.n_op = (uint8_t)(n | (op << 6));
+      uint32_t cnt = 0, n_segs = 0, rec_ne = 0;
+      if (op == kTileOpAnd) {
         float bound = 0.0f;
         uint32_t dmin = 0xFFFFFFFFu, drv = 0;
         for (uint32_t c = 0; c < n; ++c) {  // the clause with the fewest postings in this tile drives
@@ -422,10 +484,17 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
           if (len < dmin) { dmin = len; drv = c; }
         }
         if (dmin == 0u || (prune && bound * 1.00001f < theta_f)) { ++st_skip; continue; }
-        rec.n_e = (uint16_t)drv; rec.ne = 0.0f;
+        rec_ne = drv; rec.ne = 0.0f; rec.shared_stripes = 0u;
         cnt = dmin; n_segs = 1;
       } else {
+        // sample launch: only the docs of the two heaviest clauses are scored (completely): the best docs of a union nearly
+        // always hold its rarest terms, and ANY real score is a valid sample
         uint32_t n_e = n;
+        if (sample_mode) {  // ... extended by further clauses while the tile holds fewer than four of their postings
+          uint32_t have = 0;
+          n_e = 0;
+          while (n_e < n && (n_e < 2u || have < 4u)) { have += s_info[cl[n_e]] >> 16; ++n_e; }
+        }
         float ne = 0.0f;
         if (prune) {
           while (n_e > 0) {
@@ -436,11 +505,20 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
           }
         }
         if (n_e == 0) { ++st_skip; continue; }  // no doc of this tile can reach the threshold
-        for (uint32_t c = 0; c < n_e; ++c) { const uint32_t len = s_info[cl[c]] >> 16; cnt += len; n_segs += len ? 1u : 0u; }
+        uint32_t seen = 0, shared = 0;
+        for (uint32_t c = 0; c < n_e; ++c) {
+          const uint32_t slot = cl[c];
+          const uint32_t len = s_info[slot] >> 16;
+          cnt += len; n_segs += len ? 1u : 0u;
+          const uint32_t m = slot < G.n_big ? (len ? 0xFFFFFFFFu : 0u) : s_mask[slot];  // (dense lists: every stripe)
+          shared |= seen & m;
+          seen |= m;
+        }
         if (cnt == 0) { ++st_skip; continue; }  // a doc without an essential posting stays below the threshold
-        rec.n_e = (uint16_t)n_e; rec.ne = ne;
+        rec_ne = n_e; rec.ne = ne; rec.shared_stripes = shared;
       }
-      bool heavy = sample_mode || cnt > TP.light_max;
+      rec.ne_prune = (uint8_t)(rec_ne | (prune ? 128u : 0u));
+      bool heavy = cnt > TP.light_max;
       if (!heavy) {
         const uint32_t sb = atomicAdd(&s_nseg, n_segs);
         if (sb + n_segs > TP.seg_cap) { heavy = true; atomicMin(&s_segvalid, sb); }  // the work list is full (entries from here on are not written): the window path takes any pair
@@ -448,11 +526,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
           const uint32_t qslot = atomicAdd(&s_nflat, 1u);
           s_q[qslot] = rec;
           uint32_t w = sb;
-          if (tq.op == kTileOpAnd) {
-            const uint32_t info = s_info[cl[rec.n_e]];
-            s_seg[w] = TileSeg{(uint16_t)qslot, rec.n_e, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
+          if (op == kTileOpAnd) {
+            const uint32_t info = s_info[cl[rec_ne]];
+            s_seg[w] = TileSeg{(uint16_t)qslot, (uint16_t)rec_ne, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
           } else {
-            for (uint32_t c = 0; c < rec.n_e; ++c) {
+            for (uint32_t c = 0; c < rec_ne; ++c) {
               const uint32_t info = s_info[cl[c]];
               if (info >> 16) s_seg[w++] = TileSeg{(uint16_t)qslot, (uint16_t)c, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
             }
@@ -491,16 +569,22 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
             const uint32_t before = incl_j - sg.len;
             const uint32_t p = sg.start + (item - before);
             const TileQ q = s_q[sg.q];
-            const uint16_t* __restrict__ cl = cl0 + q.clause_base;
+            const TileTQ qq = s_tq[q.qi];
+            const uint16_t* __restrict__ cl = cl0 + qq.clause_base;
             const uint32_t off = s_off[p];
             float sum;
             bool ok;
-            if (q.op == kTileOpAnd) ok = tile_eval_and(V, cl, q.n, q.n_e, p, off, sum);
+            if (q.op() == kTileOpAnd) ok = tile_eval_and(V, cl, q.n(), q.n_e(), p, off, sum);
             else ok = tile_eval_or(V, s_max, cl, q, sg.clause, p, off, threshold_score(q.th_key), sum);
             if (ok) {
               ++st_compl;
-              if (score_to_key(sum) >= q.th_key) ++st_push;
-              tile_push(P, q.query, sum, lo + off, G.segment_ord, q.th_key, G.alive);
+              const uint32_t key = score_to_key(sum);
+              if (key >= q.th_key) ++st_push;
+              if (!sample_mode) tile_push(P, qq.query, sum, lo + off, G.segment_ord, q.th_key, G.alive);
+              else if (key >= q.th_key && key != 0u && (!G.alive || is_alive(G.alive, lo + off))) {  // (a deleted doc bounds nothing)
+                const uint32_t idx = atomicAdd(&TP.sample_count[qq.query], 1u);
+                if (idx < TP.sample_cap) TP.samples[(size_t)qq.query * TP.sample_cap + idx] = key;
+              }
             }
           }
         }
@@ -510,21 +594,21 @@ __global__ void __launch_bounds__(kTileThreads, 2) k_tile(const BatchParams P, c
     {
       const uint32_t n_heavy = s_nheavy;
       float* acc = s_acc + warp * kTile;
-      for (;;) {
+      for (; warp < n_win;) {  // (the warps without a window go straight to the barrier)
         uint32_t h = 0;
         if (lane == 0) h = atomicAdd(&s_hpos, 1u);
         h = __shfl_sync(kFull, h, 0);
         if (h >= n_heavy) break;
-        const TQuery tq = s_tq[s_heavy[h]];
+        const TileTQ tq = s_tq[s_heavy[h]];
         const uint16_t* __restrict__ cl = cl0 + tq.clause_base;
         uint32_t th_key = 0;
         if (lane == 0) th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
         th_key = __shfl_sync(kFull, th_key, 0);  // one value for the whole warp (the query-wide threshold moves)
         const float theta_f = threshold_score(th_key);
-        const bool prune = (tq.flags & 1u) && theta_f > 0.0f && !sample_mode;
+        const bool prune = (tq.op_flags & 128u) && theta_f > 0.0f && !sample_mode;
         const uint32_t n = tq.n_clauses;
         if (lane == 0) ++st_heavy;
-        if (tq.op == kTileOpAnd) {  // lanes share the driving clause's postings; every lane looks its docs up in the others
+        if ((tq.op_flags & 3u) == kTileOpAnd) {  // lanes share the driving clause's postings; every lane looks its docs up in the others
           uint32_t dmin = 0xFFFFFFFFu, drv = 0;
           for (uint32_t c = 0; c < n; ++c) {
             const uint32_t len = s_info[cl[c]] >> 16;
