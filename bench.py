@@ -40,8 +40,9 @@ WORKLOADS = {
                                desc="BASELINE.json configs[0]: single-term top-10, 1M docs, 1 segment"),
     "or20_top10_500M_64seg": dict(op="or", n_segments=64, docs_per_segment=7_812_500, k=10, n_terms=20, max_rank=10_000,
                                   desc="BASELINE.json configs[4]: 20-term OR, top-10, 500M docs, 64 segments (8 per GPU at N=8)"),
-    "mixed_top10_100M_8seg": dict(op="mixed", n_segments=8, docs_per_segment=12_500_000, k=10, n_terms=0, max_rank=1000,
-                                  desc="BASELINE.json configs[3] shape: 40% 2-term AND, 40% 2-4-term OR, 20% term, top-10"),
+    "mixed_top10_100M_8seg": dict(op="mixed", n_segments=8, docs_per_segment=12_500_000, k=10, n_terms=0, max_rank=1000, record_option=2,
+                                  desc="BASELINE.json configs[3]: search-benchmark-game shape, 35% 2-term AND, 35% 2-4-term OR, 15% term, 15% 2-3-term phrase, top-10, "
+                                       "100M docs with positions, 8 segments"),
 }
 AND_PAIRS = [(0.10, 0.10), (0.50, 0.02), (0.80, 0.005)]     # benches/intersection_bench.rs:107-113
 TERM_LADDER = [0.0001, 0.01, 0.05, 0.15, 0.30]              # benches/and_or_queries.rs:134-140
@@ -74,8 +75,8 @@ def build_query_plan(wl, nq, n_batches, seed):
             op = wl["op"]
             if op == "mixed":
                 u = rng.random()
-                op = "and" if u < 0.4 else ("or" if u < 0.8 else "term")
-                nt = 2 if op == "and" else (int(rng.integers(2, 5)) if op == "or" else 1)
+                op = "and" if u < 0.35 else ("or" if u < 0.70 else ("term" if u < 0.85 else "phrase"))
+                nt = 2 if op == "and" else (int(rng.integers(2, 5)) if op == "or" else (1 if op == "term" else int(rng.integers(2, 4))))
             else:
                 nt = wl["n_terms"]
             if wl["max_rank"]:
@@ -91,7 +92,7 @@ def build_query_plan(wl, nq, n_batches, seed):
     return dens, batches
 
 
-OPS = {"term": 0, "and": 1, "or": 2}
+OPS = {"term": 0, "and": 1, "or": 2, "phrase": 3}
 
 
 def make_shard(wl, dens, rank, world, seed, dist=None, device=None):
@@ -100,7 +101,8 @@ def make_shard(wl, dens, rank, world, seed, dist=None, device=None):
     from tantivy_b200.sharding import ShardedIndex, assign_segments
     ords = assign_segments(wl["n_segments"], world, rank)
     t0 = time.time()
-    ix = T.SynthIndex(len(ords), wl["docs_per_segment"], dens, seed=seed, segment_base=rank, segment_stride=world) if ords else None
+    ix = T.SynthIndex(len(ords), wl["docs_per_segment"], dens, seed=seed, segment_base=rank, segment_stride=world,
+                      record_option=wl.get("record_option", 1)) if ords else None
     shard = ShardedIndex(ix, ords, len(dens), dist, device)
     shard.gen_s = time.time() - t0
     return shard
@@ -327,7 +329,7 @@ def main():
         sampler.start()
     # per-kind device times of the timed steps: CUDA events recorded by the library on the stream each kernel is
     # launched on; steps are serialised (sync per step) so that the intervals do not overlap.
-    kinds = ("score_ms", "tile_ms", "theta_ms", "term_ms", "and_ms", "or_ms", "final_ms", "kernel_ms")
+    kinds = ("score_ms", "tile_ms", "theta_ms", "phrase_ms", "term_ms", "and_ms", "or_ms", "final_ms", "kernel_ms")
     kern = {name: [] for name in kinds}
     launches = 0
     stats = None
@@ -413,6 +415,7 @@ def main():
             "tile": ("k_tile", tile_bytes, n_tile_launches * tile_groups, "8 B (doc, score) pair read per posting per covering launch + result rows"),
             "or": ("k_or_strip" if stats.get("units_or_strip", 0) * 2 > stats["units_or"] else "k_or_pipe", float(touched_per_step) + 12.0 * wl["k"] * nq if touched_per_step else float(stats["bytes_or"]), 4, "bytes the kernel decoded (device counter)"),
             "and": ("k_and", float(stats["bytes_and"]), 1, "exhaustive formula; k_and prunes leader docs, so this is an exhaustive-equivalent figure"),
+            "phrase": ("k_phrase", float(stats["bytes_and"]), 1, "postings ranges + fieldnorm bytes of the phrases' terms (position bytes of the matching docs not counted)"),
             "term": ("k_term", float(stats["bytes_term"]), 1, "exhaustive formula (the kernel reads every posting)"),
             "final": ("k_final", 16.0 * 8192 * nq, 1, "candidate regions (upper bound)"),
             "theta": ("k_theta", 16.0 * 8192 * nq, 3, "candidate regions (upper bound)"),

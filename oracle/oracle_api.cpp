@@ -71,6 +71,41 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
     if (!seg) seg = &it->second;
   }
   if (!seg) return;
+  if (q.op == TQ_OP_PHRASE) {
+    // PhraseWeight::scorer + the same collector (phrase_weight.rs:41-110): every term of the phrase must have postings here
+    if (!q.term_pos || !q.term_offset || q.slop != 0) throw std::runtime_error("phrase query arrays");
+    std::vector<std::pair<uint32_t, PhraseTerm>> tp;
+    for (uint32_t t = 0; t < q.n_terms; ++t) {
+      if (!per_term[t] || per_term[t]->doc_freq == 0) return;
+      const tq_term_seg& ts = *per_term[t];
+      const tq_term_pos& ps = q.term_pos[per_term[t] - q.term_segs];
+      const OSegment& s = ix.segs.at({ts.segment_ord, ts.field});
+      if (s.record_option != WithFreqsAndPositions) throw std::runtime_error("field has no positions");
+      PhraseTerm pt;
+      pt.postings.block_cursor = BlockSegmentPostings::open(ts.doc_freq, s.idx_body.data() + 8 + ts.postings_start,
+                                                            (size_t)(ts.postings_end - ts.postings_start), s.record_option, WithFreqsAndPositions);
+      pt.postings.cur = 0;
+      if (ps.positions_end > s.positions.size() || !PositionReader::open(s.positions.data() + ps.positions_start,
+                                                                         (size_t)(ps.positions_end - ps.positions_start), &pt.reader))
+        throw std::runtime_error("corrupt positions range");
+      tp.emplace_back(q.term_offset[t], std::move(pt));
+    }
+    PhraseScorer sc;
+    sc.slop = 0;
+    sc.fieldnorm_reader = seg->has_fieldnorm ? FieldNormReader::from_data(seg->fieldnorm.data(), seg->max_doc) : FieldNormReader::constant(seg->max_doc, 1);
+    sc.similarity_weight = weight_for(q, 0);  // ONE Bm25Weight::for_terms weight for the whole phrase
+    sc.init(std::move(tp));
+    TopNHeap top_p(q.k);
+    const bool has_thr = (q.flags & TQ_QUERY_HAS_THRESHOLD) && q.threshold == q.threshold;
+    for (uint32_t d = sc.doc(); d != TERMINATED; d = sc.advance()) {
+      if (!seg->is_alive(d)) continue;
+      const Score score = sc.score();
+      if (has_thr && !(score > q.threshold)) continue;
+      top_p.push(score, d);
+    }
+    for (const ScoreHeapEntry& e : top_p.heap) fruit.push_back({e.score, segment_ord, e.doc});
+    return;
+  }
   std::vector<TermScorer> scorers;
   for (uint32_t t = 0; t < q.n_terms; ++t) {
     if (!per_term[t] || per_term[t]->doc_freq == 0) {

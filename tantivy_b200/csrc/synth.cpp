@@ -52,6 +52,8 @@ struct Segment {
   std::vector<uint8_t> fieldnorm_ids;
   std::unique_ptr<tq::FieldPostingsWriter> writer;
   std::vector<tq::TermInfoOut> terms;  // one per requested density, in request order
+  std::vector<uint8_t> positions;     // record_option 2: the field's `.pos` body (every term's position stream, in term order)
+  std::vector<std::pair<uint64_t, uint64_t>> pos_ranges;  // ... and every term's positions_range in it
 };
 
 }  // namespace
@@ -73,7 +75,8 @@ static void parallel_for(size_t n, int n_threads, F f) {
 extern "C" {
 
 // densities[i] in (0, 1]: fraction of the segment's docs containing term i.
-// record_option: 1 (WithFreqs) or 2 (WithFreqsAndPositions; positions themselves are not written).
+// record_option: 1 (WithFreqs) or 2 (WithFreqsAndPositions: every posting also gets tf distinct positions, uniform over the doc's
+// length, written like PositionSerializer does -- src/positions/serializer.rs; tqs_positions / tqs_term_pos).
 // segment_base: global ordinal of the first generated segment (seeds depend on the global ordinal, so a
 // rank that generates only its own shard gets the same bytes as a full generation would give it).
 tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const double* densities, uint32_t n_terms,
@@ -117,15 +120,17 @@ tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const do
   // 2. posting lists: one task per (segment, term), encoded independently then appended in order
   const size_t n_tasks = (size_t)n_segments * n_terms;
   std::vector<std::vector<uint8_t>> encoded(n_tasks);
+  std::vector<std::vector<uint8_t>> encoded_pos(record_option == 2 ? n_tasks : 0);
   std::vector<uint32_t> doc_freqs(n_tasks, 0);
   parallel_for(n_tasks, n_threads, [&](size_t task) {
     const uint32_t s = (uint32_t)(task / n_terms), t = (uint32_t)(task % n_terms);
     Segment& sg = ix->segs[s];
     const double p = std::min(1.0, std::max(1e-12, densities[t]));
     Rng rng(mix(seed + segment_base + (uint64_t)s * segment_stride, 0x7E63, t));
-    std::vector<uint32_t> docs, tfs;
+    std::vector<uint32_t> docs, tfs, deltas;
     docs.reserve((size_t)(p * sg.max_doc * 1.05) + 16);
     tfs.reserve(docs.capacity());
+    if (record_option == 2) deltas.reserve(docs.capacity() * 2);
     const double inv_log_q = p < 1.0 ? 1.0 / std::log1p(-p) : 0.0;
     const double inv_log_tf = 1.0 / std::log(0.3);  // geometric(p=0.7): P(extra >= j) = 0.3^j
     uint64_t doc = 0;
@@ -141,9 +146,23 @@ tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const do
       if (tf > sg.lengths[doc]) tf = sg.lengths[doc];
       docs.push_back((uint32_t)doc);
       tfs.push_back(tf);
+      if (record_option == 2) {
+        // tf distinct positions in [0, length): sorted draws, made distinct by insertion; stored as first position + gaps
+        uint32_t pos[10];
+        const uint32_t len = sg.lengths[doc];
+        for (uint32_t i = 0; i < tf; ++i) {
+          uint32_t v = (uint32_t)(rng.uniform() * (len - i));  // i-th draw among the len - i free positions
+          uint32_t j = 0;
+          while (j < i && pos[j] <= v) { ++v; ++j; }
+          for (uint32_t m = i; m > j; --m) pos[m] = pos[m - 1];
+          pos[j] = v;
+        }
+        for (uint32_t i = 0; i < tf; ++i) deltas.push_back(i ? pos[i] - pos[i - 1] : pos[0]);
+      }
     }
     doc_freqs[task] = (uint32_t)docs.size();
     sg.writer->encode_term(docs.data(), tfs.data(), (uint32_t)docs.size(), encoded[task]);
+    if (record_option == 2) tq::encode_positions(deltas.data(), deltas.size(), encoded_pos[task]);
   });
   for (uint32_t s = 0; s < n_segments; ++s) {
     Segment& sg = ix->segs[s];
@@ -154,6 +173,11 @@ tqs_index* tqs_generate(uint32_t n_segments, uint32_t docs_per_segment, const do
       const size_t task = (size_t)s * n_terms + t;
       sg.terms[t] = sg.writer->add_encoded(encoded[task], doc_freqs[task]);
       std::vector<uint8_t>().swap(encoded[task]);
+      if (record_option == 2) {
+        sg.pos_ranges.push_back({sg.positions.size(), sg.positions.size() + encoded_pos[task].size()});
+        sg.positions.insert(sg.positions.end(), encoded_pos[task].begin(), encoded_pos[task].end());
+        std::vector<uint8_t>().swap(encoded_pos[task]);
+      }
     }
     std::vector<uint32_t>().swap(sg.lengths);
   }
@@ -166,6 +190,11 @@ uint32_t tqs_max_doc(tqs_index* ix, uint32_t s) { return ix->segs[s].max_doc; }
 uint64_t tqs_total_num_tokens(tqs_index* ix, uint32_t s) { return ix->segs[s].total_num_tokens; }
 void tqs_body(tqs_index* ix, uint32_t s, const uint8_t** p, size_t* len) { *p = ix->segs[s].writer->body().data(); *len = ix->segs[s].writer->body().size(); }
 void tqs_fieldnorm(tqs_index* ix, uint32_t s, const uint8_t** p, size_t* len) { *p = ix->segs[s].fieldnorm_ids.data(); *len = ix->segs[s].fieldnorm_ids.size(); }
+void tqs_positions(tqs_index* ix, uint32_t s, const uint8_t** p, size_t* len) { *p = ix->segs[s].positions.data(); *len = ix->segs[s].positions.size(); }
+void tqs_term_pos(tqs_index* ix, uint32_t s, uint32_t term, uint64_t* start, uint64_t* end) {
+  const Segment& sg = ix->segs[s];
+  if (term < sg.pos_ranges.size()) { *start = sg.pos_ranges[term].first; *end = sg.pos_ranges[term].second; } else { *start = *end = 0; }
+}
 void tqs_term_info(tqs_index* ix, uint32_t s, uint32_t term, uint32_t* doc_freq, uint64_t* start, uint64_t* end) {
   const tq::TermInfoOut& ti = ix->segs[s].terms[term];
   *doc_freq = ti.doc_freq; *start = ti.postings_start; *end = ti.postings_end;

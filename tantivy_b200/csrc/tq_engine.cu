@@ -144,7 +144,7 @@ struct tq_ctx {
   uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 16, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_seg_cap_hook = 0;
-  uint32_t tile_cand_floor = 8192, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 12, tile_units = 148 * 6;
+  uint32_t tile_cand_floor = 32768, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 6, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
 
@@ -251,11 +251,11 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_light_max = env_u32("TQ_TILE_LIGHT_MAX", 96);      // essential postings up to which a (query, tile) pair is evaluated posting by posting
   c->tile_counters = env_u32("TQ_TILE_COUNTERS", 0);         // diagnostics (tile_counters of tq_stats)
   c->tile_ops = env_u32("TQ_TILE_OPS", 7);                  // bit 0 term, 1 AND, 2 OR
-  c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 8192);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
+  c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 32768);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
   c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
   c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
   c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces the window path)
-  c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 12);          // expected pairs per tile from which a list gets a tile index
+  c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 6);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
   if (err == cudaSuccess) err = cudaMemset(c->d_lists, 0, (size_t)c->lists_cap * sizeof(ListDesc));
@@ -933,7 +933,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
           // every doc at or above the running threshold is handed over: the sample launch and the k_theta passes keep that
           // near k; a query that still overflows sends the batch to the per-query kernels (flags[1])
           const uint32_t cand_floor = c->tile_cand_floor;  // (test hook: tiny regions overflow)
-          q_cands[qi] += (size_t)std::min<uint64_t>(q_postings, std::max<uint64_t>((cand_floor >= 8192 ? 64ull : 1ull) * q.k, cand_floor));
+          q_cands[qi] += (size_t)std::min<uint64_t>(q_postings, std::max<uint64_t>((cand_floor >= 8192 ? 128ull : 1ull) * q.k, cand_floor));
         }
       }
       if (on_tile) continue;
@@ -1056,11 +1056,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       std::vector<uint32_t> perm(sb.slots.size());
       for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
       auto is_big = [&](const TSlot& sl) { return (uint64_t)sl.doc_freq * kTile >= (uint64_t)big_min * std::max(1u, sb.max_doc); };
-      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b2) {
-        const bool ba = is_big(sb.slots[a]), bb = is_big(sb.slots[b2]);
-        if (ba != bb) return ba;
-        return ba ? sb.slots[a].doc_freq > sb.slots[b2].doc_freq : false;
-      });
+      // (by descending doc_freq throughout: the threads of a warp that stage sparse slots then see similar lists)
+      std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b2) { return sb.slots[a].doc_freq > sb.slots[b2].doc_freq; });
       std::vector<uint32_t> new_of(perm.size());
       for (uint32_t i = 0; i < perm.size(); ++i) new_of[perm[i]] = i;
       TSeg G{};

@@ -50,6 +50,7 @@ constexpr uint32_t kTileMaxSlots = 4096;    // distinct scored lists of one grou
 constexpr uint32_t kTileMaxBig = 64;        // dense lists of one segment that get a tile index and a presence map
 constexpr uint32_t kTileMaxPairs = 12288;   // pairs of one tile held in shared memory (start | len are 16-bit fields)
 constexpr uint32_t kTileExactWindows = 2;   // warps that take heavy pairs in an exact launch (each owns a window of kTile f32 slots)
+constexpr uint32_t kSampleSeg = 6;          // sample launch: postings scored per driving clause and (query, tile)
 constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr uint32_t kTileOpAnd = 1;  // TQ_OP_AND; term queries and unions share one evaluation (a union of one clause)
@@ -394,7 +395,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
     }
     for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {  // sparse lists: one thread walks its cursor
       uint32_t nd = s_nxt[s];
-      if (nd >= hi) { s_info[s] = 0u; s_max[s] = 0.0f; s_mask[s] = 0u; continue; }
+      if (nd >= hi) {
+        s_info[s] = 0u; s_max[s] = 0.0f; s_mask[s] = 0u;
+        continue;
+      }
       const TSlot sl = slots[s];
       const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base;
       const float* __restrict__ sc = TP.p_scores + sl.pair_base;
@@ -428,6 +432,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       }
       s_cur[s] = cur + n;
       s_nxt[s] = nd;
+      if (nd < hi + kTile) {  // the next tile reads this list again: start its pairs on their way to L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(d + cur + n));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(sc + cur + n));
+      }
       const uint32_t base = atomicAdd(&s_total, n);
       float mx = 0.0f;
       uint32_t mask = 0;
@@ -518,7 +526,9 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
         rec_ne = n_e; rec.ne = ne; rec.shared_stripes = shared;
       }
       rec.ne_prune = (uint8_t)(rec_ne | (prune ? 128u : 0u));
-      bool heavy = cnt > TP.light_max;
+      // sample launch: ANY set of real scores is a valid sample -- at most kSampleSeg postings per driving clause, no window path
+      if (sample_mode && *(volatile unsigned int*)&TP.sample_count[tq.query] >= TP.sample_cap) continue;
+      bool heavy = !sample_mode && cnt > TP.light_max;
       if (!heavy) {
         const uint32_t sb = atomicAdd(&s_nseg, n_segs);
         if (sb + n_segs > TP.seg_cap) { heavy = true; atomicMin(&s_segvalid, sb); }  // the work list is full (entries from here on are not written): the window path takes any pair
@@ -526,13 +536,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
           const uint32_t qslot = atomicAdd(&s_nflat, 1u);
           s_q[qslot] = rec;
           uint32_t w = sb;
+          const uint32_t len_cap = sample_mode ? kSampleSeg : 0xFFFFu;
           if (op == kTileOpAnd) {
             const uint32_t info = s_info[cl[rec_ne]];
-            s_seg[w] = TileSeg{(uint16_t)qslot, (uint16_t)rec_ne, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
+            s_seg[w] = TileSeg{(uint16_t)qslot, (uint16_t)rec_ne, (uint16_t)(info & 0xFFFFu), (uint16_t)min(info >> 16, len_cap)};
           } else {
             for (uint32_t c = 0; c < rec_ne; ++c) {
               const uint32_t info = s_info[cl[c]];
-              if (info >> 16) s_seg[w++] = TileSeg{(uint16_t)qslot, (uint16_t)c, (uint16_t)(info & 0xFFFFu), (uint16_t)(info >> 16)};
+              if (info >> 16) s_seg[w++] = TileSeg{(uint16_t)qslot, (uint16_t)c, (uint16_t)(info & 0xFFFFu), (uint16_t)min(info >> 16, len_cap)};
             }
           }
           ++st_flat;
@@ -564,6 +575,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
             if (v <= item) j += step;
           }
           const uint32_t incl_j = __shfl_sync(kFull, incl, j & 31u);
+          uint32_t s_query = 0xFFFFFFFFu - lane, s_key = 0;  // sample launch: this lane's sample (if any), handed over below
           if (item < total) {
             const TileSeg sg = s_seg[sbase + j];
             const uint32_t before = incl_j - sg.len;
@@ -581,10 +593,18 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
               const uint32_t key = score_to_key(sum);
               if (key >= q.th_key) ++st_push;
               if (!sample_mode) tile_push(P, qq.query, sum, lo + off, G.segment_ord, q.th_key, G.alive);
-              else if (key >= q.th_key && key != 0u && (!G.alive || is_alive(G.alive, lo + off))) {  // (a deleted doc bounds nothing)
-                const uint32_t idx = atomicAdd(&TP.sample_count[qq.query], 1u);
-                if (idx < TP.sample_cap) TP.samples[(size_t)qq.query * TP.sample_cap + idx] = key;
-              }
+              else if (key >= q.th_key && key != 0u && (!G.alive || is_alive(G.alive, lo + off))) { s_query = qq.query; s_key = key; }  // (a deleted doc bounds nothing)
+            }
+          }
+          if (sample_mode) {  // one atomic per query and warp step instead of one per sample (the counters are hot)
+            const unsigned peers = __match_any_sync(kFull, s_query);
+            if (s_key) {
+              const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+              uint32_t base = 0;
+              if (lane == leader) base = atomicAdd(&TP.sample_count[s_query], (uint32_t)__popc(peers));
+              base = __shfl_sync(peers, base, leader);
+              const uint32_t idx = base + (uint32_t)__popc(peers & lanemask_lt(lane));
+              if (idx < TP.sample_cap) TP.samples[(size_t)s_query * TP.sample_cap + idx] = s_key;
             }
           }
         }

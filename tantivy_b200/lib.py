@@ -84,6 +84,8 @@ def _load():
     lib.tqs_body.argtypes = [vp, C.c_uint32, C.POINTER(u8p), C.POINTER(sz)]
     lib.tqs_fieldnorm.argtypes = [vp, C.c_uint32, C.POINTER(u8p), C.POINTER(sz)]
     lib.tqs_term_info.argtypes = [vp, C.c_uint32, C.c_uint32, u32p, u64p, u64p]
+    lib.tqs_positions.argtypes = [vp, C.c_uint32, C.POINTER(u8p), C.POINTER(sz)]
+    lib.tqs_term_pos.argtypes = [vp, C.c_uint32, C.c_uint32, u64p, u64p]
     return lib
 
 
@@ -158,15 +160,19 @@ class SynthIndex:
         self.record_option = record_option
         self.max_doc = [LIB.tqs_max_doc(self.h, s) for s in range(n_segments)]
         self.total_num_tokens = [LIB.tqs_total_num_tokens(self.h, s) for s in range(n_segments)]
-        # term_info[s][t] = (doc_freq, start, end)
-        self.term_info = []
+        # term_info[s][t] = (doc_freq, start, end); term_pos[s][t] = (positions_start, positions_end) with record_option 2
+        self.term_info, self.term_pos = [], []
         df, st, en = C.c_uint32(), C.c_uint64(), C.c_uint64()
         for s in range(n_segments):
-            row = []
+            row, prow = [], []
             for t in range(len(dens)):
                 LIB.tqs_term_info(self.h, s, t, C.byref(df), C.byref(st), C.byref(en))
                 row.append((df.value, st.value, en.value))
+                if record_option == 2:
+                    LIB.tqs_term_pos(self.h, s, t, C.byref(st), C.byref(en))
+                    prow.append((st.value, en.value))
             self.term_info.append(row)
+            self.term_pos.append(prow)
 
     def body(self, s):
         p, n = u8p(), C.c_size_t()
@@ -177,6 +183,12 @@ class SynthIndex:
         p, n = u8p(), C.c_size_t()
         LIB.tqs_fieldnorm(self.h, s, C.byref(p), C.byref(n))
         return np.ctypeslib.as_array(p, shape=(n.value,))
+
+    def positions(self, s):
+        """The segment's `.pos` body (record_option 2)."""
+        p, n = u8p(), C.c_size_t()
+        LIB.tqs_positions(self.h, s, C.byref(p), C.byref(n))
+        return np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[:n.value]
 
     def num_docs(self):
         return sum(self.max_doc)
@@ -191,6 +203,26 @@ class SynthIndex:
         """target: Context (GPU) or an oracle index with the same segment_register signature."""
         for s in range(self.n_segments):
             target.segment_register(segment_base + s, field, self.max_doc[s], self.record_option, self.body(s), self.fieldnorm(s), None)
+            if self.record_option == 2:
+                target.register_positions(segment_base + s, field, self.positions(s))
+
+    def phrase_query(self, terms, k, field=0, segment_base=0, segments=None):
+        """PhraseQuery over `terms` (in phrase order): ONE Bm25Weight::for_terms weight (the idfs add up, bm25.rs:95-129)."""
+        n_docs = self.num_docs()
+        avg = self.avg_fieldnorm()
+        idf_sum = np.float32(0)
+        for t in terms:
+            idf_sum = np.float32(idf_sum + np.float32(bm25_idf(self.doc_freq(t), n_docs)))
+        weight = np.float32(idf_sum * np.float32(2.2))
+        term_segs, term_pos = [], []
+        for clause, t in enumerate(terms):
+            for s in (range(self.n_segments) if segments is None else segments):
+                df, st, en = self.term_info[s][t]
+                if df:
+                    term_segs.append((clause, segment_base + s, field, df, st, en))
+                    term_pos.append(self.term_pos[s][t])
+        return dict(op=3, k=k, weights=[weight] * len(terms), avg_fieldnorm=[avg] * len(terms), term_segs=term_segs, term_pos=term_pos,
+                    term_offset=list(range(len(terms))))
 
     def query(self, op, terms, k, field=0, segment_base=0, boost=1.0, segments=None):
         n_docs = self.num_docs()

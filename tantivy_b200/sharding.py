@@ -93,24 +93,39 @@ class ShardedIndex:
                 df += np.array([index.term_info[s][t][0] for t in range(n_terms)], dtype=np.int64)
             tokens, docs = sum(index.total_num_tokens), sum(index.max_doc)
         self.df, self.total_tokens, self.total_docs, self.avg = global_statistics(df, tokens, docs, dist, device)
-        self.index_bytes = sum(index.body(s).size + index.fieldnorm(s).size for s in range(index.n_segments)) if index is not None else 0
+        self.index_bytes = sum(index.body(s).size + index.fieldnorm(s).size + (index.positions(s).size if index.record_option == 2 else 0)
+                               for s in range(index.n_segments)) if index is not None else 0
 
     def register(self, target):
         for i, g in enumerate(self.global_ords):
             target.segment_register(g, 0, self.ix.max_doc[i], self.ix.record_option, self.ix.body(i), self.ix.fieldnorm(i), None)
+            if self.ix.record_option == 2:
+                target.register_positions(g, 0, self.ix.positions(i))
 
     def marshal(self, queries):
-        """queries: iterable of (op code, [term ordinals], k) -> QueryBatch restricted to this rank's segments."""
+        """queries: iterable of (op code, [term ordinals], k) -> QueryBatch restricted to this rank's segments.
+        op 3 = phrase (terms in phrase order): ONE Bm25Weight::for_terms weight from the GLOBAL statistics."""
+        from .lib import bm25_idf
         out = []
         for op, terms, k in queries:
-            weights = [bm25_weight(int(self.df[t]), self.total_docs, 1.0) for t in terms]
-            term_segs = []
+            term_segs, term_pos = [], []
             for clause, t in enumerate(terms):
                 for i, g in enumerate(self.global_ords):
                     d, st, en = self.ix.term_info[i][t]
                     if d:
                         term_segs.append((clause, g, 0, d, st, en))
-            out.append(dict(op=op, k=k, weights=weights, avg_fieldnorm=[self.avg] * len(terms), term_segs=term_segs))
+                        if op == 3:
+                            term_pos.append(self.ix.term_pos[i][t])
+            if op == 3:
+                idf_sum = np.float32(0)
+                for t in terms:
+                    idf_sum = np.float32(idf_sum + np.float32(bm25_idf(int(self.df[t]), self.total_docs)))
+                w = np.float32(idf_sum * np.float32(2.2))
+                out.append(dict(op=3, k=k, weights=[w] * len(terms), avg_fieldnorm=[self.avg] * len(terms), term_segs=term_segs, term_pos=term_pos,
+                                term_offset=list(range(len(terms)))))
+            else:
+                weights = [bm25_weight(int(self.df[t]), self.total_docs, 1.0) for t in terms]
+                out.append(dict(op=op, k=k, weights=weights, avg_fieldnorm=[self.avg] * len(terms), term_segs=term_segs))
         return QueryBatch(out)
 
 

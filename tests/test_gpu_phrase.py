@@ -172,3 +172,27 @@ def test_phrase_needs_positions_and_rejects_slop(ctx):
     q2["slop"] = 1
     with pytest.raises(T.TqError):
         ctx.search_batch(QueryBatch([q2]))
+
+
+def test_synthetic_index_with_positions_mixed_batch(ctx):
+    """The benchmark's generator with positions (csrc/synth.cpp, record_option 2): phrase queries in one batch with term / AND /
+    OR queries (BASELINE.json configs[3]'s mix), several segments, against the oracle's search_batch (PhraseScorer restatement)."""
+    from tantivy_b200._abi import TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM
+    dens = [0.3, 0.15, 0.05, 0.01, 0.002]
+    ix = T.SynthIndex(3, 400_000, dens, seed=11, record_option=TQ_RECORD_FREQS_POSITIONS)
+    base = 8800
+    ix.register(ctx, segment_base=base)
+    oi = O.OracleIndex()
+    ix.register(oi, segment_base=base)
+    qs = []
+    for k in (1, 10, 100):
+        for terms in ([0, 1], [1, 0], [0, 0], [0, 1, 2], [2, 0], [3, 0], [0, 1, 0], [4, 3]):
+            qs.append(ix.phrase_query(terms, k, segment_base=base))
+        qs += [ix.query(TQ_OP_OR, [0, 2, 4], k, segment_base=base), ix.query(TQ_OP_AND, [1, 2], k, segment_base=base), ix.query(TQ_OP_TERM, [3], k, segment_base=base)]
+    qb = QueryBatch(qs)
+    g = ctx.search_batch(qb)
+    c = oi.search_batch(qb, mode=0, n_threads=8)
+    for i in range(qb.nq):
+        assert hits(g, i) == hits(c, i), (i, hits(g, i)[:3], hits(c, i)[:3])
+    assert any(len(hits(g, i)) > 0 for i in range(8))  # the phrases do match
+    assert ctx.stats()["units_phrase"] > 0
