@@ -49,6 +49,18 @@ extern "C" {
  * under ONE Bm25Weight for the whole phrase (Bm25Weight::for_terms: the idfs add up, bm25.rs:95-129).  Needs a field
  * indexed WithFreqsAndPositions and its `.pos` bytes (tq_segment_register_positions). */
 #define TQ_OP_PHRASE 3
+/* BooleanQuery of TermQuery leaves with mixed Occurs, and one level of all-SHOULD sub-queries under MUST
+ * (`+a +(b OR c)`, `+(c OR b) +(d OR e)`, `a b -c`, minimum_number_should_match): BooleanWeight::complex_scorer
+ * (src/query/boolean_query/boolean_weight.rs:236-431) for these shapes.  Per clause term_occur[t] = TQ_OCCUR_*;
+ * MUST clauses that share term_group[t] are alternatives of one required group (a MUST clause of its own: a group of
+ * one).  A doc matches when every MUST group has a clause that lists it, at least `min_should_match` SHOULD clauses list
+ * it (at least one when there is no MUST group: boolean_weight.rs:354-366), and no MUST_NOT clause lists it (Exclude).
+ * Score = (sum over the MUST groups, ascending cost, of the sum of their matching clauses) + (sum of the matching SHOULD
+ * clauses) -- Intersection::score / RequiredOptionalScorer::score (intersection.rs:325-329, reqopt_scorer.rs:78-94). */
+#define TQ_OP_BOOL 4
+#define TQ_OCCUR_SHOULD 0
+#define TQ_OCCUR_MUST 1
+#define TQ_OCCUR_MUST_NOT 2
 
 /* TERMINATED sentinel of src/docset.rs:12 */
 #define TQ_TERMINATED 0x7FFFFFFFu
@@ -115,7 +127,11 @@ typedef struct {
   const tq_term_pos* term_pos;
   const uint32_t* term_offset;
   uint32_t slop;
-  uint32_t reserved;
+  uint32_t min_should_match; /* TQ_OP_BOOL: BooleanQuery::minimum_number_should_match */
+  /* TQ_OP_BOOL only (NULL otherwise): [n_terms] Occur of every clause; [n_terms] group of every MUST clause (NULL: every
+   * MUST clause is a group of its own; ignored for the other Occurs). */
+  const uint8_t* term_occur;
+  const uint8_t* term_group;
 } tq_query;
 
 /* Counters of the last finished batch (per ctx). */
@@ -188,10 +204,10 @@ int tq_search_batch(tq_ctx*, const tq_query* queries, size_t nq, uint32_t out_st
                     float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc,
                     uint32_t* out_count);
 
-/* The Count collector for the same query shapes (src/collector/count_collector.rs; Weight::count,
- * term_weight.rs:179-219): out_counts[q] = number of ALIVE docs matching query q over all its segments.  k, weights
- * and thresholds of the queries are ignored.  A term query on a segment without deletes is answered from doc_freq,
- * as the reference does. */
+/* The Count collector for term / AND / OR / mixed boolean (TQ_OP_BOOL) queries (src/collector/count_collector.rs;
+ * Weight::count, term_weight.rs:179-219): out_counts[q] = number of ALIVE docs matching query q over all its segments.
+ * k and thresholds of the queries are ignored (TQ_OP_BOOL reads the weights: they order the clauses).  A term query on a
+ * segment without deletes is answered from doc_freq, as the reference does. */
 int tq_count_batch(tq_ctx*, const tq_query* queries, size_t nq, uint64_t* out_counts);
 
 /* The same split in three so that callers can keep inputs/outputs device resident:

@@ -9,6 +9,7 @@
 //   src/query/boolean_query/boolean_weight.rs:581-600  dispatch to block_wand / block_wand_intersection
 //   src/query/term_query/term_weight.rs:118-141,179-219 TermWeight::for_each_pruning / specialized_scorer
 #include <atomic>
+#include <functional>
 #include <map>
 #include <thread>
 
@@ -57,6 +58,100 @@ static Bm25Weight weight_for(const tq_query& q, uint32_t term) {
   return w;
 }
 
+
+// ---- BooleanQuery with mixed Occurs over term leaves ------------------------------------------------
+// Restates, for TermQuery leaves and one level of all-SHOULD sub-queries under MUST, what BooleanWeight::complex_scorer builds
+// (src/query/boolean_query/boolean_weight.rs:236-431) and how its scorers add up:
+//   * EmptyScorers (clauses without postings in the segment) are removed first (:247-263); a MUST that is empty empties the query;
+//   * minimum_number_should_match m against the n remaining SHOULD scorers (:269-301): m > n -> nothing; m = 0 -> Optional;
+//     m = 1 -> Required(union); m = n (>= 2) -> the SHOULD clauses become MUST clauses; else Required(disjunction, m);
+//   * no MUST at all and Optional SHOULD -> the union is what matches (:354-366); Optional + MUST -> RequiredOptionalScorer:
+//     score = req + opt when the doc is in opt (reqopt_scorer.rs:78-94); Required + MUST -> Intersection of the two (:405-414);
+//   * MUST scorers intersect in ascending cost order, score = their sum (intersection.rs:20-57,325-329); a `+(b OR c)` clause is
+//     a union scorer: its score is the sum of its matching clauses (SumCombiner);
+//   * MUST_NOT: Exclude (:416-430).
+// Exhaustive, dense per-doc evaluation (test sizes).  f32 sums in a fixed order: groups by ascending cost (ties: first clause),
+// inside a group / among the SHOULD clauses by descending weight (ties: clause order) -- the canonical order of DESIGN.md §5.
+static void bool_for_each(const tqo_index& ix, const tq_query& q, uint32_t segment_ord, const std::function<void(uint32_t, Score)>& emit) {
+  if (!q.term_occur) throw std::runtime_error("TQ_OP_BOOL needs term_occur");
+  std::vector<const tq_term_seg*> per_term(q.n_terms, nullptr);
+  const OSegment* seg = nullptr;
+  for (uint32_t i = 0; i < q.n_term_segs; ++i) {
+    const tq_term_seg& ts = q.term_segs[i];
+    if (ts.segment_ord != segment_ord) continue;
+    per_term[ts.term_idx] = &ts;
+    if (!seg) seg = &ix.segs.at({ts.segment_ord, ts.field});
+  }
+  if (!seg) return;
+  struct Group { uint32_t id, first_term; uint64_t cost = 0; std::vector<TermScorer> clauses; };
+  std::vector<Group> groups;
+  std::vector<TermScorer> should, must_not;
+  auto scorer_of = [&](uint32_t t) {
+    const OSegment& s = ix.segs.at({per_term[t]->segment_ord, per_term[t]->field});
+    return make_term_scorer(s, *per_term[t], weight_for(q, t), t, q.term_flags && (q.term_flags[t] & TQ_TERM_IGNORE_FREQ));
+  };
+  for (uint32_t t = 0; t < q.n_terms; ++t) {
+    const bool present = per_term[t] && per_term[t]->doc_freq;
+    if (q.term_occur[t] == TQ_OCCUR_MUST) {
+      const uint32_t id = q.term_group ? q.term_group[t] : 256u + t;
+      Group* g = nullptr;
+      for (auto& x : groups) if (x.id == id) g = &x;
+      if (!g) { groups.push_back(Group{id, t}); g = &groups.back(); }
+      if (present) { g->clauses.push_back(scorer_of(t)); g->cost += per_term[t]->doc_freq; }
+    } else if (present) {
+      (q.term_occur[t] == TQ_OCCUR_SHOULD ? should : must_not).push_back(scorer_of(t));
+    }
+  }
+  for (auto& g : groups) if (g.clauses.empty()) return;  // an empty MUST
+  uint32_t m = q.min_should_match;
+  if (m > should.size()) return;
+  if (m >= 2 && m == should.size()) {  // as many as there are: they are MUST clauses
+    for (auto& sc : should) { Group g{512u + sc.clause, sc.clause}; g.cost = sc.postings.size_hint(); g.clauses.push_back(std::move(sc)); groups.push_back(std::move(g)); }
+    should.clear();
+    m = 0;
+  }
+  if (groups.empty() && should.empty()) return;
+  const uint32_t need_should = m >= 1 ? m : (groups.empty() ? 1u : 0u);
+  const uint32_t max_doc = seg->max_doc;
+  auto by_weight = [](std::vector<TermScorer>& v) {
+    std::stable_sort(v.begin(), v.end(), [](const TermScorer& a, const TermScorer& b) { return a.similarity_weight.weight > b.similarity_weight.weight; });
+  };
+  std::stable_sort(groups.begin(), groups.end(), [](const Group& a, const Group& b) { return a.cost < b.cost; });
+  std::vector<float> acc(max_doc, 0.0f), gsum(max_doc), ssum(max_doc, 0.0f);
+  std::vector<uint8_t> ok(max_doc, 1), gm(max_doc), scount(max_doc, 0);
+  bool first = true;
+  for (auto& g : groups) {
+    by_weight(g.clauses);
+    std::fill(gm.begin(), gm.end(), 0);
+    for (auto& sc : g.clauses)
+      for (uint32_t d = sc.doc(); d != TERMINATED; d = sc.advance()) {
+        const Score s = sc.score();
+        if (!gm[d]) { gsum[d] = s; gm[d] = 1; } else gsum[d] += s;
+      }
+    for (uint32_t d = 0; d < max_doc; ++d) {
+      if (!ok[d]) continue;
+      if (!gm[d]) { ok[d] = 0; continue; }
+      acc[d] = first ? gsum[d] : acc[d] + gsum[d];
+    }
+    first = false;
+  }
+  by_weight(should);
+  for (auto& sc : should)
+    for (uint32_t d = sc.doc(); d != TERMINATED; d = sc.advance()) {
+      const Score s = sc.score();
+      if (!scount[d]) ssum[d] = s; else ssum[d] += s;
+      if (scount[d] < 255) ++scount[d];
+    }
+  for (auto& sc : must_not)
+    for (uint32_t d = sc.doc(); d != TERMINATED; d = sc.advance()) ok[d] = 0;
+  for (uint32_t d = 0; d < max_doc; ++d) {
+    if (!ok[d] || scount[d] < need_should) continue;
+    if (groups.empty() && !scount[d]) continue;
+    const Score total = groups.empty() ? ssum[d] : (scount[d] ? acc[d] + ssum[d] : acc[d]);
+    emit(d, total);
+  }
+}
+
 // mode 0: exhaustive canonical; mode 1: reference-faithful pruned path.
 static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t segment_ord, int mode, std::vector<Hit>& fruit) {
   // gather this segment's lists per clause
@@ -71,6 +166,17 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
     if (!seg) seg = &it->second;
   }
   if (!seg) return;
+  if (q.op == TQ_OP_BOOL) {  // (no pruned variant restated: both modes evaluate exhaustively)
+    TopNHeap top_b(q.k);
+    const bool has_thr = (q.flags & TQ_QUERY_HAS_THRESHOLD) && q.threshold == q.threshold;
+    bool_for_each(ix, q, segment_ord, [&](uint32_t d, Score score) {
+      if (!seg->is_alive(d)) return;
+      if (has_thr && !(score > q.threshold)) return;
+      top_b.push(score, d);
+    });
+    for (const ScoreHeapEntry& e : top_b.heap) fruit.push_back({e.score, segment_ord, e.doc});
+    return;
+  }
   if (q.op == TQ_OP_PHRASE) {
     // PhraseWeight::scorer + the same collector (phrase_weight.rs:41-110): every term of the phrase must have postings here
     if (!q.term_pos || !q.term_offset || q.slop != 0) throw std::runtime_error("phrase query arrays");
@@ -244,6 +350,10 @@ int tqo_count_batch(tqo_index* ix, const tq_query* queries, size_t nq, uint64_t*
           if (ts.segment_ord != so) continue;
           per_term[ts.term_idx] = &ts;
           if (!seg) seg = &ix->segs.at({ts.segment_ord, ts.field});
+        }
+        if (q.op == TQ_OP_BOOL) {
+          if (seg) bool_for_each(*ix, q, so, [&](uint32_t d, Score) { if (seg->is_alive(d)) ++total; });
+          continue;
         }
         std::vector<TermScorer> scorers;
         bool empty = false;

@@ -9,7 +9,8 @@ import numpy as np
 
 TQ_OK = 0
 TQ_RECORD_BASIC, TQ_RECORD_FREQS, TQ_RECORD_FREQS_POSITIONS = 0, 1, 2
-TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR, TQ_OP_PHRASE = 0, 1, 2, 3
+TQ_OP_TERM, TQ_OP_AND, TQ_OP_OR, TQ_OP_PHRASE, TQ_OP_BOOL = 0, 1, 2, 3, 4
+TQ_OCCUR_SHOULD, TQ_OCCUR_MUST, TQ_OCCUR_MUST_NOT = 0, 1, 2
 TERMINATED = 0x7FFFFFFF
 TQ_MAX_K = 1024
 TQ_MAX_TERMS = 32
@@ -66,16 +67,19 @@ class Query(C.Structure):
         ("term_pos", C.POINTER(TermPos)),
         ("term_offset", u32p),
         ("slop", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("min_should_match", C.c_uint32),
+        ("term_occur", u8p),
+        ("term_group", u8p),
     ]
 
 
 QUERY_DTYPE = np.dtype(
     [("op", "<i4"), ("n_terms", "<u4"), ("k", "<u4"), ("n_term_segs", "<u4"),
      ("term_segs", "<u8"), ("weight", "<u8"), ("avg_fieldnorm", "<u8"), ("tf_cache", "<u8"), ("term_flags", "<u8"),
-     ("flags", "<u4"), ("threshold", "<f4"), ("term_pos", "<u8"), ("term_offset", "<u8"), ("slop", "<u4"), ("reserved", "<u4")]
+     ("flags", "<u4"), ("threshold", "<f4"), ("term_pos", "<u8"), ("term_offset", "<u8"), ("slop", "<u4"), ("min_should_match", "<u4"),
+     ("term_occur", "<u8"), ("term_group", "<u8")]
 )
-assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 88
+assert QUERY_DTYPE.itemsize == C.sizeof(Query) == 104
 
 
 class Stats(C.Structure):
@@ -134,7 +138,9 @@ class QueryBatch:
       tf_cache (optional [n_terms,256]), term_flags (optional [n_terms] bytes, TQ_TERM_IGNORE_FREQ),
       threshold (optional float: only docs scoring above it are collected),
       phrase queries (op TQ_OP_PHRASE): term_pos = list of (positions_start, positions_end) parallel to term_segs,
-      term_offset = [n_terms] offsets in the phrase, slop (optional, must be 0 on the device path).
+      term_offset = [n_terms] offsets in the phrase, slop (optional, must be 0 on the device path);
+      boolean queries (op TQ_OP_BOOL): term_occur = [n_terms] TQ_OCCUR_*, term_group = optional [n_terms] group ids of the MUST
+      clauses, min_should_match (optional).
     Built with numpy so that a batch of thousands of queries marshals in milliseconds.
     """
 
@@ -195,6 +201,17 @@ class QueryBatch:
                 row["term_pos"] = tp.ctypes.data
                 row["term_offset"] = toff.ctypes.data
                 row["slop"] = int(q.get("slop", 0))
+            occ = q.get("term_occur")
+            if occ is not None:
+                occ = np.ascontiguousarray(occ, dtype=np.uint8).reshape(nt)
+                self.caches.append(occ)
+                row["term_occur"] = occ.ctypes.data
+                grp = q.get("term_group")
+                if grp is not None:
+                    grp = np.ascontiguousarray(grp, dtype=np.uint8).reshape(nt)
+                    self.caches.append(grp)
+                    row["term_group"] = grp.ctypes.data
+                row["min_should_match"] = int(q.get("min_should_match", 0))
             flags = q.get("term_flags")
             if flags is not None:
                 flags = np.ascontiguousarray(flags, dtype=np.uint8).reshape(nt)

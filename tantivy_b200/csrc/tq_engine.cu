@@ -636,6 +636,8 @@ struct SegPlan {
   struct Clause { uint32_t first; QList second; uint32_t range_len; };  // doc_freq, clause, bytes of its postings range
   std::vector<Clause> here;
   std::vector<uint32_t> term_idx;  // clause ordinals in arrival order (phrases: before `here` is sorted)
+  std::vector<uint16_t> bool_words;  // TQ_OP_BOOL: [n_groups, need_should, n_should, n_not, (len, clauses..) per group, shoulds.., nots..],
+                                     // clauses as indices into `here` (tile_admit turns them into slots)
   const uint8_t* fn0 = nullptr;
   bool uniform_fn = true, prunable = false;
 };
@@ -664,6 +666,59 @@ struct TileGroupBuild {
   uint64_t pairs = 0;                              // elements of the pair arrays (doc_freq rounded up to 128 per slot)
   uint64_t list_bytes = 0;                         // postings-range bytes of the distinct lists
 };
+
+// BooleanWeight::complex_scorer for ONE segment (boolean_weight.rs:236-431), term leaves only: `here` = the clauses that have
+// postings in the segment (term_idx / doc_freq / weight per entry).  Clauses without postings are EmptyScorers -- removed before
+// anything is counted; an empty MUST group empties the query in this segment.  Writes
+//   [n_groups, need_should, n_should, n_not, (len, entries..) per MUST group, SHOULD entries.., MUST_NOT entries..]
+// (entries = indices into `here`; groups by ascending cost = Intersection's order, entries by descending weight = the union order)
+// and returns 1; 0 when nothing can match in this segment; -1 on a bad Occur.
+int bool_structure(const tq_query& q, const uint32_t* term_idx, const uint32_t* dfs, const float* ws, size_t n_here, std::vector<uint16_t>& words) {
+  struct Grp { uint32_t id, first; uint64_t cost; std::vector<uint16_t> cl; };
+  std::vector<Grp> groups;
+  std::vector<uint16_t> shoulds, nots;
+  for (uint32_t t = 0; t < q.n_terms; ++t) {  // declared MUST groups, present or not
+    if (q.term_occur[t] > TQ_OCCUR_MUST_NOT) return -1;
+    if (q.term_occur[t] != TQ_OCCUR_MUST) continue;
+    const uint32_t id = q.term_group ? q.term_group[t] : 256u + t;
+    bool known = false;
+    for (auto& g : groups) known = known || g.id == id;
+    if (!known) groups.push_back(Grp{id, t, 0, {}});
+  }
+  for (size_t a = 0; a < n_here; ++a) {
+    const uint32_t t = term_idx[a];
+    if (q.term_occur[t] == TQ_OCCUR_MUST) {
+      const uint32_t id = q.term_group ? q.term_group[t] : 256u + t;
+      for (auto& g : groups) if (g.id == id) { g.cl.push_back((uint16_t)a); g.cost += dfs[a]; }
+    } else (q.term_occur[t] == TQ_OCCUR_SHOULD ? shoulds : nots).push_back((uint16_t)a);
+  }
+  for (auto& g : groups) if (g.cl.empty()) return 0;
+  uint32_t m = q.min_should_match;
+  if (m > shoulds.size()) return 0;
+  if (m >= 2 && m == shoulds.size()) {  // as many as there are SHOULD clauses: they are MUST clauses (boolean_weight.rs:287-292)
+    for (uint16_t a : shoulds) groups.push_back(Grp{512u + a, term_idx[a], dfs[a], {a}});
+    shoulds.clear();
+    m = 0;
+  }
+  if (groups.empty() && shoulds.empty()) return 0;
+  const uint32_t need = m >= 1 ? m : (groups.empty() ? 1u : 0u);
+  auto by_weight = [&](std::vector<uint16_t>& v) { std::stable_sort(v.begin(), v.end(), [&](uint16_t x, uint16_t y) { return ws[x] > ws[y]; }); };
+  std::stable_sort(groups.begin(), groups.end(), [](const Grp& x, const Grp& y) { return x.cost < y.cost; });
+  words.clear();
+  words.push_back((uint16_t)groups.size());
+  words.push_back((uint16_t)need);
+  words.push_back((uint16_t)shoulds.size());
+  words.push_back((uint16_t)nots.size());
+  for (auto& g : groups) {
+    by_weight(g.cl);
+    words.push_back((uint16_t)g.cl.size());
+    for (uint16_t a : g.cl) words.push_back(a);
+  }
+  by_weight(shoulds);
+  for (uint16_t a : shoulds) words.push_back(a);
+  for (uint16_t a : nots) words.push_back(a);
+  return 1;
+}
 
 // Would the group still satisfy k_tile's limits with this query added?  Returns the number of NEW pair elements, or -1.
 int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
@@ -721,9 +776,11 @@ uint64_t tile_admit(TileGroupBuild& g, uint32_t query, int op, const SegPlan* pl
     TQuery tq;
     tq.query = query;
     tq.clause_base = (uint32_t)sb.clauses.size();
-    tq.n_clauses = (uint16_t)sp.here.size();
-    tq.op = (uint8_t)op;
+    tq.n_clauses = (uint16_t)(op == TQ_OP_BOOL ? sp.bool_words.size() : sp.here.size());
+    tq.op = (uint8_t)(op == TQ_OP_BOOL ? kTileOpBool : op);
     tq.flags = sp.prunable ? 1u : 0u;
+    uint16_t slot_of_here[TQ_MAX_TERMS];
+    size_t hi_idx = 0;
     for (auto& h : sp.here) {
       uint32_t slot = g.find_slot(sb, h.second);
       if (slot == kNoSlot) {
@@ -739,7 +796,19 @@ uint64_t tile_admit(TileGroupBuild& g, uint32_t query, int op, const SegPlan* pl
         g.pairs += ((uint64_t)h.first + 127) / 128 * 128;
         g.list_bytes += h.range_len;
       }
-      sb.clauses.push_back((uint16_t)slot);
+      slot_of_here[hi_idx++] = (uint16_t)slot;
+      if (op != TQ_OP_BOOL) sb.clauses.push_back((uint16_t)slot);
+    }
+    if (op == TQ_OP_BOOL) {  // the structure words stay, the clause indices become slots
+      const std::vector<uint16_t>& w = sp.bool_words;
+      size_t x = 0;
+      for (int k = 0; k < 4; ++k) sb.clauses.push_back(w[x++]);
+      for (uint32_t g = 0; g < w[0]; ++g) {
+        const uint16_t len = w[x++];
+        sb.clauses.push_back(len);
+        for (uint16_t e = 0; e < len; ++e) sb.clauses.push_back(slot_of_here[w[x++]]);
+      }
+      while (x < w.size()) sb.clauses.push_back(slot_of_here[w[x++]]);
     }
     sb.queries.push_back(tq);
   }
@@ -817,7 +886,9 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       const tq_query& q = queries[qi];
       if (q.k == 0 || q.k > TQ_MAX_K) return fail(TQ_ERR_INVALID_ARGUMENT, "k must be in 1..TQ_MAX_K");
       if (q.n_terms == 0 || q.n_terms > TQ_MAX_TERMS) return fail(TQ_ERR_INVALID_ARGUMENT, "n_terms must be in 1..TQ_MAX_TERMS");
-      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR && q.op != TQ_OP_PHRASE) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
+      const bool is_bool = q.op == TQ_OP_BOOL;
+      if (is_bool && (!tile_on || !q.term_occur)) return fail(!q.term_occur ? TQ_ERR_INVALID_ARGUMENT : TQ_ERR_UNSUPPORTED, "TQ_OP_BOOL needs term_occur and the tile engine (TQ_TILE=1)");
+      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR && q.op != TQ_OP_PHRASE && !is_bool) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
       if (q.op == TQ_OP_TERM && q.n_terms != 1) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_TERM takes one term");
       if (!q.weight || (!q.avg_fieldnorm && !q.tf_cache) || (!q.term_segs && q.n_term_segs)) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
       const bool is_phrase = q.op == TQ_OP_PHRASE;
@@ -828,7 +899,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       }
       kmax = std::max(kmax, q.k);
       alg_bytes += 12ull * q.k;
-      op_bytes[is_phrase ? TQ_OP_AND : (q.n_terms == 1 ? TQ_OP_TERM : q.op)] += 12ull * q.k;
+      op_bytes[is_phrase ? TQ_OP_AND : (is_bool ? TQ_OP_OR : (q.n_terms == 1 ? TQ_OP_TERM : q.op))] += 12ull * q.k;
       // tf-norm tables of this query's clauses
       uint32_t cache_idx[TQ_MAX_TERMS];
       for (uint32_t t = 0; t < q.n_terms; ++t) {
@@ -851,7 +922,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         }
       }
       // effective shape: an AND / OR of one clause is that clause (boolean_weight.rs:57-68, block_wand_union.rs:154-157)
-      const int op = is_phrase ? TQ_OP_PHRASE : (q.n_terms == 1 ? TQ_OP_TERM : q.op);
+      const int op = is_phrase ? TQ_OP_PHRASE : (is_bool ? TQ_OP_BOOL : (q.n_terms == 1 ? TQ_OP_TERM : q.op));
       dq[qi].k = q.k;
       dq[qi].op = (uint32_t)op;
       // group the (clause, segment) lists by segment
@@ -894,7 +965,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
           sp.here.push_back(SegPlan::Clause{order[a]->doc_freq, ql, (uint32_t)(order[a]->postings_end - order[a]->postings_start)});
           sp.term_idx.push_back(order[a]->term_idx);
           alg_bytes += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
-          op_bytes[is_phrase ? TQ_OP_AND : op] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
+          op_bytes[is_phrase ? TQ_OP_AND : (is_bool ? TQ_OP_OR : op)] += (order[a]->postings_end - order[a]->postings_start) + order[a]->doc_freq;
           postings += order[a]->doc_freq;
           q_postings += order[a]->doc_freq;
         }
@@ -915,11 +986,19 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
           std::stable_sort(sp.here.begin(), sp.here.end(), [](const SegPlan::Clause& a, const SegPlan::Clause& b) { return a.second.weight > b.second.weight; });
         sp.prunable = true;
         for (auto& h : sp.here) sp.prunable = sp.prunable && std::isfinite(h.second.weight) && h.second.weight >= 0.0f;
+        if (op == TQ_OP_BOOL) {
+          uint32_t dfs[TQ_MAX_TERMS];
+          float ws[TQ_MAX_TERMS];
+          for (size_t a = 0; a < sp.here.size(); ++a) { dfs[a] = sp.here[a].first; ws[a] = sp.here[a].second.weight; }
+          const int st = bool_structure(q, sp.term_idx.data(), dfs, ws, sp.here.size(), sp.bool_words);
+          if (st < 0) return fail(TQ_ERR_INVALID_ARGUMENT, "term_occur");
+          if (st == 0) { --n_plans; i = j; continue; }
+        }
         i = j;
       }
       // ---- route: the shared-decode tile engine, or the per-query kernels -------------------------------------------------
       bool on_tile = false;
-      if (tile_on && ((c->tile_ops >> op) & 1u) && n_plans) {
+      if (tile_on && (((c->tile_ops >> op) & 1u) || op == TQ_OP_BOOL) && n_plans) {
         if (tgroups.empty()) tgroups.emplace_back();
         bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000);
         if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000) >= 0;
@@ -937,6 +1016,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         }
       }
       if (on_tile) continue;
+      if (op == TQ_OP_BOOL && n_plans) return fail(TQ_ERR_UNSUPPORTED, "TQ_OP_BOOL query does not fit the tile engine's buffers (split the batch / raise TQ_TILE_SCRATCH_MB)");
       for (size_t pi = 0; pi < n_plans; ++pi) {
         SegPlan& sp = plans[pi];
         auto& here = sp.here;
@@ -1037,7 +1117,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     std::vector<uint16_t> clauses;
     std::vector<TUnit> units[kTileRounds];
     std::vector<SChunk> chunks;
-    uint32_t max_slots = 1, p_cap = 1024, max_big = 1, max_queries = 1, max_clause_words = 0;
+    uint32_t max_slots = 1, p_cap = 1024, max_big = 1, max_queries = 1, max_clause_words = 0, max_clauses = 1;
     size_t tix_words = 0;
   };
   std::vector<GroupStage> gstage(tgroups.size());
@@ -1093,8 +1173,19 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         t2.clause_base += clause_shift;
         gs.queries.push_back(t2);
         kmax_g = std::max(kmax_g, dq[tq.query].k);
+        gs.max_clauses = std::max<uint32_t>(gs.max_clauses, tq.n_clauses);
       }
-      for (uint16_t cl : sb.clauses) gs.clauses.push_back((uint16_t)new_of[cl]);
+      {  // clause slots follow the permutation (the structure words of TQ_OP_BOOL queries do not)
+        const size_t c0 = gs.clauses.size();
+        for (uint16_t cl : sb.clauses) gs.clauses.push_back(cl);
+        for (auto& tq : sb.queries) {
+          uint16_t* w = gs.clauses.data() + c0 + tq.clause_base;
+          if (tq.op != kTileOpBool) { for (uint32_t e = 0; e < tq.n_clauses; ++e) w[e] = (uint16_t)new_of[w[e]]; continue; }
+          size_t x = 4;
+          for (uint32_t g = 0; g < w[0]; ++g) { const uint16_t len = w[x++]; for (uint16_t e = 0; e < len; ++e, ++x) w[x] = (uint16_t)new_of[w[x]]; }
+          for (; x < tq.n_clauses; ++x) w[x] = (uint16_t)new_of[w[x]];
+        }
+      }
       gs.max_slots = std::max(gs.max_slots, G.n_slots);
       gs.max_big = std::max(gs.max_big, G.n_big);
       gs.max_queries = std::max(gs.max_queries, G.n_queries);
@@ -1132,7 +1223,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         if (!span) continue;
         // this launch's share of the target, by its share of all tiles; at least 8 tiles per unit (cursor start-up)
         const uint64_t round_tiles_all = std::max<uint64_t>(1, (uint64_t)tiles_total * span / nt);
-        const uint32_t per = (uint32_t)std::max<uint64_t>(8, (round_tiles_all + target - 1) / target);
+        const uint32_t per = (uint32_t)std::max<uint64_t>(tiles_total >= 16ull * target ? 8 : 2, (round_tiles_all + target - 1) / target);
         for (uint32_t t0 = cuts[r]; t0 < cuts[r + 1]; t0 += per) gs.units[1 + r].push_back(TUnit{si, t0, std::min(cuts[r + 1], t0 + per), 0});
       }
     }
@@ -1269,7 +1360,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     if (c->tile_seg_cap_hook) TP.seg_cap = c->tile_seg_cap_hook;
     TP.light_max = c->tile_light_max;
     TP.cl_cap = gs.max_clause_words <= 16384u ? ((gs.max_clause_words + 3u) & ~3u) : 0u;
-    run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots, TP.max_big, TP.max_queries, TP.seg_cap, TP.cl_cap);
+    TP.n_win = gs.max_clauses > 8u ? kTileWarps : kTileExactWindows;  // wide unions: many (query, tile) pairs take the window path
+    run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots, TP.max_big, TP.max_queries, TP.seg_cap, TP.cl_cap, TP.n_win);
     if (run.smem > 200u * 1024u) return fail(TQ_ERR_UNSUPPORTED, "tile group needs more shared memory than an SM has");
     b->groups.push_back(run);
   }
@@ -1735,6 +1827,9 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
   std::vector<uint32_t> list_ids;
   std::vector<CountSeg> segs;
   std::vector<Unit> units;
+  std::vector<uint32_t> bool_words;  // TQ_OP_BOOL (query, segment) pairs: their structure words with list ids
+  std::vector<CountBoolSeg> bool_segs;
+  std::vector<Unit> bool_units;
   {
     std::lock_guard<std::mutex> g(c->mu);
     std::vector<PendingBuild> pending;
@@ -1744,9 +1839,10 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
     for (size_t qi = 0; qi < nq; ++qi) {
       const tq_query& q = queries[qi];
       if (q.n_terms == 0 || q.n_terms > TQ_MAX_TERMS) return fail(TQ_ERR_INVALID_ARGUMENT, "n_terms must be in 1..TQ_MAX_TERMS");
-      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
+      if (q.op != TQ_OP_TERM && q.op != TQ_OP_AND && q.op != TQ_OP_OR && q.op != TQ_OP_BOOL) return fail(TQ_ERR_INVALID_ARGUMENT, "op");
       if (q.op == TQ_OP_TERM && q.n_terms != 1) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_TERM takes one term");
       if (!q.term_segs && q.n_term_segs) return fail(TQ_ERR_INVALID_ARGUMENT, "query arrays");
+      if (q.op == TQ_OP_BOOL && (!q.term_occur || !q.weight)) return fail(TQ_ERR_INVALID_ARGUMENT, "TQ_OP_BOOL needs term_occur and weights");
       order.clear();
       for (uint32_t i = 0; i < q.n_term_segs; ++i) {
         if (q.term_segs[i].term_idx >= q.n_terms) return fail(TQ_ERR_INVALID_ARGUMENT, "term_idx out of range");
@@ -1759,6 +1855,32 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
         size_t j = i;
         while (j < order.size() && order[j]->segment_ord == order[i]->segment_ord) ++j;
         const uint32_t n_here = (uint32_t)(j - i);
+        if (q.op == TQ_OP_BOOL) {  // mixed shapes: the structure of this segment, with list ids in place of the clause indices
+          uint32_t tix_[TQ_MAX_TERMS], dfs_[TQ_MAX_TERMS], ids_[TQ_MAX_TERMS];
+          float ws_[TQ_MAX_TERMS];
+          const Segment* seg = nullptr;
+          for (size_t a = i; a < j; ++a) {
+            int rc = get_list(c, *order[a], false, pending, &ids_[a - i], &seg);
+            if (rc != TQ_OK) return rc;
+            tix_[a - i] = order[a]->term_idx; dfs_[a - i] = order[a]->doc_freq; ws_[a - i] = q.weight[order[a]->term_idx];
+          }
+          std::vector<uint16_t> words;
+          const int st = bool_structure(q, tix_, dfs_, ws_, n_here, words);
+          if (st < 0) return fail(TQ_ERR_INVALID_ARGUMENT, "term_occur");
+          if (st > 0) {
+            CountBoolSeg bs{};
+            bs.query = (uint32_t)qi; bs.words_base = (uint32_t)bool_words.size(); bs.max_doc = seg->max_doc; bs.alive = seg->d_alive;
+            size_t x = 0;
+            for (int k4 = 0; k4 < 4; ++k4) bool_words.push_back(words[x++]);
+            for (uint32_t g2 = 0; g2 < words[0]; ++g2) { const uint16_t len = words[x++]; bool_words.push_back(len); for (uint16_t e = 0; e < len; ++e) bool_words.push_back(ids_[words[x++]]); }
+            while (x < words.size()) bool_words.push_back(ids_[words[x++]]);
+            const uint32_t tiles = (bs.max_doc + kTileDocs - 1) / kTileDocs, per = 8;
+            for (uint32_t t0 = 0; t0 < tiles; t0 += per) bool_units.push_back(Unit{(uint32_t)bool_segs.size(), t0, std::min(tiles, t0 + per), 0});
+            bool_segs.push_back(bs);
+          }
+          i = j;
+          continue;
+        }
         if (q.op == TQ_OP_AND && n_here < q.n_terms) { i = j; continue; }  // a clause without postings: empty intersection
         CountSeg cs{};
         cs.query = (uint32_t)qi; cs.lists_base = (uint32_t)list_ids.size(); cs.n_lists = n_here; cs.op = (uint32_t)q.op;
@@ -1786,6 +1908,33 @@ int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_
     }
     int rc = flush_builds(c, pending, &built);
     if (rc != TQ_OK) return rc;
+  }
+  if (!bool_units.empty()) {  // mixed boolean shapes: their own kernel, counts added to out_counts
+    auto align2 = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o2 = 0;
+    const size_t o_w = o2; o2 = align2(o2 + bool_words.size() * 4);
+    const size_t o_s = o2; o2 = align2(o2 + bool_segs.size() * sizeof(CountBoolSeg));
+    const size_t o_u = o2; o2 = align2(o2 + bool_units.size() * sizeof(Unit));
+    const size_t o_c = o2; o2 = align2(o2 + nq * 8);
+    TQ_CUDA(b->pin.ensure(o2 + 256));
+    TQ_CUDA(b->dev.ensure(o2 + 256));
+    memcpy(b->pin.p + o_w, bool_words.data(), bool_words.size() * 4);
+    memcpy(b->pin.p + o_s, bool_segs.data(), bool_segs.size() * sizeof(CountBoolSeg));
+    memcpy(b->pin.p + o_u, bool_units.data(), bool_units.size() * sizeof(Unit));
+    memset(b->pin.p + o_c, 0, nq * 8);
+    TQ_CUDA(cudaMemcpyAsync(b->dev.p, b->pin.p, o2, cudaMemcpyHostToDevice, b->stream));
+    CountBoolParams BP;
+    BP.lists = c->d_lists;
+    BP.words = reinterpret_cast<const uint32_t*>(b->dev.p + o_w);
+    BP.segs = reinterpret_cast<const CountBoolSeg*>(b->dev.p + o_s);
+    BP.units = reinterpret_cast<const Unit*>(b->dev.p + o_u);
+    BP.counts = reinterpret_cast<unsigned long long*>(b->dev.p + o_c);
+    k_count_bool<<<(unsigned)bool_units.size(), kThreads, 0, b->stream>>>(BP);
+    TQ_CUDA(cudaGetLastError());
+    TQ_CUDA(cudaMemcpyAsync(b->pin.p + o_c, b->dev.p + o_c, nq * 8, cudaMemcpyDeviceToHost, b->stream));
+    TQ_CUDA(cudaStreamSynchronize(b->stream));
+    const unsigned long long* dc = reinterpret_cast<const unsigned long long*>(b->pin.p + o_c);
+    for (size_t qi = 0; qi < nq; ++qi) out_counts[qi] += dc[qi];
   }
   if (units.empty()) return TQ_OK;
   auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };

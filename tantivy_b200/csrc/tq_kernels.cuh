@@ -1580,6 +1580,116 @@ __global__ void __launch_bounds__(kThreads) k_count(const CountParams P) {
   }
 }
 
+// Count for mixed boolean shapes (TQ_OP_BOOL; Weight::count over BooleanWeight::complex_scorer's scorer, boolean_weight.rs:236-431):
+// per 8192-doc tile a result bitmap = AND over the MUST groups of (OR of the group's clauses), SHOULD clauses counted per doc
+// (byte counters, four to a word) against `need`, MUST_NOT clauses cleared, alive bits and-ed in, popcount.
+// words = [n_groups, need, n_should, n_not, (len, list ids..) per group, should list ids.., not list ids..] (32-bit).
+struct CountBoolSeg {
+  uint32_t query, words_base, max_doc, pad;
+  const uint8_t* alive;
+};
+struct CountBoolParams {
+  const ListDesc* lists;
+  const uint32_t* words;
+  const CountBoolSeg* segs;
+  const Unit* units;
+  unsigned long long* counts;
+};
+
+template <class F>
+__device__ __forceinline__ void count_for_each_posting(const ListDesc& L, uint32_t lo, uint32_t hi, uint32_t lane, uint32_t warp, F f) {
+  const uint32_t j0 = first_block_ge(L.last_doc, 0, L.n_total, lo, lane);
+  for (uint32_t j = j0 + warp; j < L.n_total; j += kWarps) {
+    const uint32_t prev = __ldg(&L.tab4[j].w);
+    if (prev != 0xFFFFFFFFu && prev + 1u >= hi) break;  // the block starts at or after the tile's end
+    uint32_t doc[4], tf[4];
+    decode_block(L, j, lane, doc, tf);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (doc[i] >= lo && doc[i] < hi) f(doc[i] - lo);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_count_bool(const CountBoolParams P) {
+  constexpr uint32_t kWords = kTileDocs / 32u;
+  __shared__ uint32_t s_acc[kWords], s_tmp[kWords];
+  __shared__ uint32_t s_cnt[kTileDocs / 4u];
+  __shared__ uint32_t s_part[kWarps];
+  const Unit U = P.units[blockIdx.x];
+  const CountBoolSeg S = P.segs[U.qseg];
+  const uint32_t* __restrict__ W = P.words + S.words_base;
+  const uint32_t ng = W[0], need = W[1], ns = W[2], nn = W[3];
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t total = 0;
+  for (uint32_t tile = U.begin; tile < U.end; ++tile) {
+    const uint32_t lo = tile * kTileDocs, hi = min(lo + kTileDocs, S.max_doc);
+    for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_acc[w] = 0xFFFFFFFFu;
+    uint32_t x = 4;
+    for (uint32_t g = 0; g < ng; ++g) {
+      const uint32_t glen = W[x++];
+      for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_tmp[w] = 0;
+      __syncthreads();
+      for (uint32_t e = 0; e < glen; ++e, ++x) {
+        const ListDesc L = P.lists[W[x]];
+        count_for_each_posting(L, lo, hi, lane, warp, [&](uint32_t o) { atomicOr(&s_tmp[o >> 5], 1u << (o & 31u)); });
+      }
+      __syncthreads();
+      for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_acc[w] &= s_tmp[w];
+      __syncthreads();
+    }
+    if (need) {
+      for (uint32_t w = threadIdx.x; w < kTileDocs / 4u; w += blockDim.x) s_cnt[w] = 0;
+      __syncthreads();
+      for (uint32_t e = 0; e < ns; ++e) {
+        const ListDesc L = P.lists[W[x + e]];
+        count_for_each_posting(L, lo, hi, lane, warp, [&](uint32_t o) { atomicAdd(&s_cnt[o >> 2], 1u << ((o & 3u) * 8u)); });  // <= 32 clauses: no carry
+      }
+      __syncthreads();
+      for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) {
+        uint32_t m = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < 8; ++b) {
+          const uint32_t c4 = s_cnt[w * 8u + b];
+#pragma unroll
+          for (uint32_t k = 0; k < 4; ++k) m |= (((c4 >> (8u * k)) & 255u) >= need ? 1u : 0u) << (b * 4u + k);
+        }
+        s_acc[w] &= m;
+      }
+      __syncthreads();
+    }
+    x += ns;
+    if (nn) {
+      for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_tmp[w] = 0;
+      __syncthreads();
+      for (uint32_t e = 0; e < nn; ++e) {
+        const ListDesc L = P.lists[W[x + e]];
+        count_for_each_posting(L, lo, hi, lane, warp, [&](uint32_t o) { atomicOr(&s_tmp[o >> 5], 1u << (o & 31u)); });
+      }
+      __syncthreads();
+      for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) s_acc[w] &= ~s_tmp[w];
+      __syncthreads();
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < kWords; w += blockDim.x) {
+      uint32_t bits = s_acc[w];
+      const uint32_t first = lo + w * 32u;
+      if (first >= hi) bits = 0;
+      else if (hi - first < 32u) bits &= (1u << (hi - first)) - 1u;  // docs beyond max_doc
+      if (bits && S.alive) bits &= __ldg(reinterpret_cast<const uint32_t*>(S.alive) + ((lo >> 5) + w));
+      total += (uint32_t)__popc(bits);
+    }
+    __syncthreads();
+  }
+  total = __reduce_add_sync(kFull, total);
+  if (lane == 0) s_part[warp] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long sum = 0;
+    for (int w = 0; w < kWarps; ++w) sum += s_part[w];
+    if (sum) atomicAdd(&P.counts[S.query], sum);
+  }
+}
+
 // The exact k-th largest score key among a query's candidates so far (4-pass radix select) becomes a lower bound of
 // its threshold: run between the sampled windows and the main launch of k_or_strip.
 __global__ void __launch_bounds__(kThreads) k_theta(const BatchParams P) {

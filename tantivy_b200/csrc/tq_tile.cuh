@@ -54,6 +54,8 @@ constexpr uint32_t kSampleSeg = 6;          // sample launch: postings scored pe
 constexpr uint32_t kSamplePerTile = 4;      // sample launch: the best few partial maxima of a (query, tile)
 constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
 constexpr uint32_t kTileOpAnd = 1;  // TQ_OP_AND; term queries and unions share one evaluation (a union of one clause)
+constexpr uint32_t kTileOpBool = 3;  // TQ_OP_BOOL: the clause words are [n_groups, need_should, n_should, n_not, (len, slots..) per MUST group,
+                                     // SHOULD slots.., MUST_NOT slots..], groups by ascending cost, slots inside by descending weight
 
 struct TSlot {  // one distinct scored list of a group: (posting list, Bm25Weight.weight, tf-norm table)
   uint32_t list_id;
@@ -106,7 +108,8 @@ struct TileParams {
   uint32_t cl_cap;     // clause words staged in shared memory per CTA (0: the segment's clauses are read from global memory)
   uint32_t seg_cap;    // entries of the per-tile work list (essential clauses of the flat pairs)
   uint32_t light_max;  // (query, tile) pairs with at most this many essential postings are evaluated posting by posting (flat path);
-                       // above it a warp accumulates the query's window
+                       // above it (and with more than one essential clause) a warp accumulates the query's window
+  uint32_t n_win;      // warps of a CTA that own a window (2: heavy pairs are rare; 8 for groups with wide queries)
 };
 
 
@@ -294,13 +297,56 @@ __device__ __forceinline__ bool tile_eval_and(const TileView& V, const uint16_t*
   return true;
 }
 
+// Mixed boolean query (BooleanWeight::complex_scorer for term leaves, boolean_weight.rs:236-431): the doc at `off` is met as posting p
+// of the clause at word `wi`, one of the driving words [d0, d0 + dn).  It is evaluated once (by the first driving clause that lists
+// it): every MUST group needs a clause that lists it (group score = sum of its matching clauses), MUST_NOT clauses must not, at least
+// `need` SHOULD clauses must; score = (sum of the group scores, ascending cost) + (sum of the matching SHOULD clauses)
+// (Intersection::score, RequiredOptionalScorer::score).
+__device__ __forceinline__ bool tile_eval_bool(const TileView& V, const uint16_t* __restrict__ cl, uint32_t d0, uint32_t wi, uint32_t p, uint32_t off,
+                                               float& sum) {
+  bool f;
+  for (uint32_t i = d0; i < wi; ++i) {
+    tile_find(V, cl[i], off, f);
+    if (f) return false;
+  }
+  const uint32_t ng = cl[0], need = cl[1], ns = cl[2], nn = cl[3];
+  uint32_t w = 4;
+  float total = 0.0f;
+  for (uint32_t g = 0; g < ng; ++g) {
+    const uint32_t glen = cl[w++];
+    float gs = 0.0f;
+    bool any = false;
+    for (uint32_t e = 0; e < glen; ++e, ++w) {
+      float v;
+      if (w == wi) { v = V.s_score[p]; f = true; } else v = tile_find(V, cl[w], off, f);
+      if (f) { gs = any ? __fadd_rn(gs, v) : v; any = true; }
+    }
+    if (!any) return false;
+    total = g ? __fadd_rn(total, gs) : gs;
+  }
+  float ss = 0.0f;
+  uint32_t cnt = 0;
+  for (uint32_t e = 0; e < ns; ++e, ++w) {
+    float v;
+    if (w == wi) { v = V.s_score[p]; f = true; } else v = tile_find(V, cl[w], off, f);
+    if (f) { ss = cnt ? __fadd_rn(ss, v) : v; ++cnt; }
+  }
+  for (uint32_t e = 0; e < nn; ++e, ++w) {
+    tile_find(V, cl[w], off, f);
+    if (f) return false;
+  }
+  if (cnt < need) return false;
+  sum = ng ? (cnt ? __fadd_rn(total, ss) : total) : ss;
+  return true;
+}
+
 // Shared memory of a k_tile CTA: the work list (TileQ records + segments) and two windows for the rare heavy pairs ...
-__host__ __device__ constexpr size_t tile_union_bytes(uint32_t max_queries, uint32_t seg_cap) {
-  return ((size_t)kTileExactWindows * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + (size_t)seg_cap * sizeof(TileSeg) + 15) & ~(size_t)15;
+__host__ __device__ constexpr size_t tile_union_bytes(uint32_t max_queries, uint32_t seg_cap, uint32_t n_win) {
+  return ((size_t)n_win * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + (size_t)seg_cap * sizeof(TileSeg) + 15) & ~(size_t)15;
 }
 __host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots, uint32_t max_big, uint32_t max_queries, uint32_t seg_cap,
-                                                      uint32_t cl_cap) {
-  return (size_t)p_cap * 4 + tile_union_bytes(max_queries, seg_cap) + (size_t)max_slots * 20 + (size_t)max_big * 128 +
+                                                      uint32_t cl_cap, uint32_t n_win) {
+  return (size_t)p_cap * 4 + tile_union_bytes(max_queries, seg_cap, n_win) + (size_t)max_slots * 20 + (size_t)max_big * 128 +
          (size_t)max_queries * sizeof(TileTQ) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 + (size_t)cl_cap * 2 + 64;
 }
 
@@ -308,10 +354,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   extern __shared__ __align__(16) unsigned char s_dyn[];
   float* s_score = reinterpret_cast<float*>(s_dyn);                            // [p_cap]
   unsigned char* s_union = reinterpret_cast<unsigned char*>(s_score + TP.p_cap);
-  const size_t union_bytes = tile_union_bytes(TP.max_queries, TP.seg_cap);
-  const uint32_t n_win = kTileExactWindows;
+  const size_t union_bytes = tile_union_bytes(TP.max_queries, TP.seg_cap, TP.n_win);
+  const uint32_t n_win = TP.n_win;
   float* s_acc = reinterpret_cast<float*>(s_union);                            // [n_win][kTile] windows of the heavy pairs
-  TileQ* s_q = reinterpret_cast<TileQ*>(s_acc + kTileExactWindows * kTile);    // [max_queries] flat pairs of this tile (exact launches)
+  TileQ* s_q = reinterpret_cast<TileQ*>(s_acc + n_win * kTile);                // [max_queries] flat pairs of this tile
   TileSeg* s_seg = reinterpret_cast<TileSeg*>(s_q + TP.max_queries);           // [seg_cap]
   uint32_t* s_info = reinterpret_cast<uint32_t*>(s_union + union_bytes);       // [max_slots]
   float* s_max = reinterpret_cast<float*>(s_info + TP.max_slots);              // [max_slots] largest score of the slot in this tile (>= 0)
@@ -481,9 +527,31 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       const uint32_t n = tq.n_clauses, op = tq.op_flags & 3u;
       ++st_pairs;
       TileQ rec;
-      rec.qi = (uint16_t)qi; rec.th_key = th_key; rec.n_op = (uint8_t)(n | (op << 6));
+      rec.qi = (uint16_t)qi; rec.th_key = th_key; rec.n_op = (uint8_t)((op == kTileOpBool ? 0u : n) | (op << 6));
       uint32_t cnt = 0, n_segs = 0, rec_ne = 0;
-      if (op == kTileOpAnd) {
+      uint32_t b_d0 = 0, b_dn = 0;  // kTileOpBool: the driving words
+      if (op == kTileOpBool) {
+        const uint32_t ng = cl[0], ns = cl[2];
+        uint32_t w = 4, best = 0xFFFFFFFFu;
+        float bound = 0.0f;
+        bool dead = false;
+        for (uint32_t g = 0; g < ng; ++g) {  // the MUST group with the fewest postings in this tile drives
+          const uint32_t glen = cl[w];
+          uint32_t tot = 0;
+          for (uint32_t e = 0; e < glen; ++e) { const uint32_t slot = cl[w + 1u + e]; tot += s_info[slot] >> 16; bound += s_max[slot]; }
+          if (tot == 0u) dead = true;
+          if (tot < best) { best = tot; b_d0 = w + 1u; b_dn = glen; }
+          w += 1u + glen;
+        }
+        uint32_t s_tot = 0;
+        for (uint32_t e = 0; e < ns; ++e) { const uint32_t slot = cl[w + e]; s_tot += s_info[slot] >> 16; bound += s_max[slot]; }
+        if (ng == 0u) { best = s_tot; b_d0 = w; b_dn = ns; }
+        if (dead || best == 0u || (prune && bound * 1.00001f < theta_f)) { ++st_skip; continue; }
+        cnt = best;
+        for (uint32_t e = 0; e < b_dn; ++e) n_segs += (s_info[cl[b_d0 + e]] >> 16) ? 1u : 0u;
+        rec.ne = __uint_as_float(b_d0 | (b_dn << 16));
+        rec.shared_stripes = 0u;
+      } else if (op == kTileOpAnd) {
         float bound = 0.0f;
         uint32_t dmin = 0xFFFFFFFFu, drv = 0;
         for (uint32_t c = 0; c < n; ++c) {  // the clause with the fewest postings in this tile drives
@@ -528,7 +596,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       rec.ne_prune = (uint8_t)(rec_ne | (prune ? 128u : 0u));
       // sample launch: ANY set of real scores is a valid sample -- at most kSampleSeg postings per driving clause, no window path
       if (sample_mode && *(volatile unsigned int*)&TP.sample_count[tq.query] >= TP.sample_cap) continue;
-      bool heavy = !sample_mode && cnt > TP.light_max;
+      bool heavy = !sample_mode && cnt > TP.light_max && op != kTileOpAnd && op != kTileOpBool && rec_ne >= 2u;
       if (!heavy) {
         const uint32_t sb = atomicAdd(&s_nseg, n_segs);
         if (sb + n_segs > TP.seg_cap) { heavy = true; atomicMin(&s_segvalid, sb); }  // the work list is full (entries from here on are not written): the window path takes any pair
@@ -537,7 +605,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
           s_q[qslot] = rec;
           uint32_t w = sb;
           const uint32_t len_cap = sample_mode ? kSampleSeg : 0xFFFFu;
-          if (op == kTileOpAnd) {
+          if (op == kTileOpBool) {
+            for (uint32_t e = 0; e < b_dn; ++e) {
+              const uint32_t info = s_info[cl[b_d0 + e]];
+              if (info >> 16) s_seg[w++] = TileSeg{(uint16_t)qslot, (uint16_t)(b_d0 + e), (uint16_t)(info & 0xFFFFu), (uint16_t)min(info >> 16, len_cap)};
+            }
+          } else if (op == kTileOpAnd) {
             const uint32_t info = s_info[cl[rec_ne]];
             s_seg[w] = TileSeg{(uint16_t)qslot, (uint16_t)rec_ne, (uint16_t)(info & 0xFFFFu), (uint16_t)min(info >> 16, len_cap)};
           } else {
@@ -586,7 +659,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
             const uint32_t off = s_off[p];
             float sum;
             bool ok;
-            if (q.op() == kTileOpAnd) ok = tile_eval_and(V, cl, q.n(), q.n_e(), p, off, sum);
+            if (q.op() == kTileOpBool) ok = tile_eval_bool(V, cl, __float_as_uint(q.ne) & 0xFFFFu, sg.clause, p, off, sum);
+            else if (q.op() == kTileOpAnd) ok = tile_eval_and(V, cl, q.n(), q.n_e(), p, off, sum);
             else ok = tile_eval_or(V, s_max, cl, q, sg.clause, p, off, threshold_score(q.th_key), sum);
             if (ok) {
               ++st_compl;
@@ -628,6 +702,45 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
         const bool prune = (tq.op_flags & 128u) && theta_f > 0.0f && !sample_mode;
         const uint32_t n = tq.n_clauses;
         if (lane == 0) ++st_heavy;
+        if ((tq.op_flags & 3u) == kTileOpBool) {  // lanes share the driving group's postings (as for conjunctions below)
+          const uint32_t ng = cl[0], ns = cl[2];
+          uint32_t w = 4, best_tot = 0xFFFFFFFFu, d0 = 0, dn = 0;
+          for (uint32_t g = 0; g < ng; ++g) {
+            const uint32_t glen = cl[w];
+            uint32_t tot = 0;
+            for (uint32_t e = 0; e < glen; ++e) tot += s_info[cl[w + 1u + e]] >> 16;
+            if (tot < best_tot) { best_tot = tot; d0 = w + 1u; dn = glen; }
+            w += 1u + glen;
+          }
+          if (ng == 0u) { d0 = w; dn = ns; }
+          uint32_t best = 0;
+          for (uint32_t e = 0; e < dn; ++e) {
+            const uint32_t info = s_info[cl[d0 + e]];
+            const uint32_t a = info & 0xFFFFu, en = a + (info >> 16);
+            for (uint32_t p = a + lane; p < en; p += 32) {
+              const uint32_t off = s_off[p];
+              float sum;
+              if (!tile_eval_bool(V, cl, d0, d0 + e, p, off, sum)) continue;
+              if (sample_mode) { if (!G.alive || is_alive(G.alive, lo + off)) best = max(best, score_to_key(sum)); }
+              else { ++st_compl; tile_push(P, tq.query, sum, lo + off, G.segment_ord, th_key, G.alive); }
+            }
+            if (lane == 0) st_ess += en - a;
+          }
+          if (sample_mode) {
+            for (uint32_t r = 0; r < kSamplePerTile; ++r) {
+              const uint32_t mk = __reduce_max_sync(kFull, best);
+              if (mk == 0u || mk < th_key) break;
+              const unsigned who = __ballot_sync(kFull, best == mk);
+              if (lane == (uint32_t)__ffs(who) - 1u) {
+                const uint32_t idx = atomicAdd(&TP.sample_count[tq.query], 1u);
+                if (idx < TP.sample_cap) TP.samples[(size_t)tq.query * TP.sample_cap + idx] = mk;
+                best = 0;
+              }
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         if ((tq.op_flags & 3u) == kTileOpAnd) {  // lanes share the driving clause's postings; every lane looks its docs up in the others
           uint32_t dmin = 0xFFFFFFFFu, drv = 0;
           for (uint32_t c = 0; c < n; ++c) {

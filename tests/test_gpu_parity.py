@@ -731,3 +731,81 @@ def test_multi_handle_two_devices(synth):
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     ix, oi, base = synth
     _multi_check([0, 1], ix, oi, base)
+
+
+# ---- N4: mixed boolean shapes (TQ_OP_BOOL) --------------------------------------------------------------------------
+def _bool_query(ix_query, occurs, groups=None, msm=0):
+    q = dict(ix_query)
+    q["op"] = T.TQ_OP_BOOL
+    q["term_occur"] = occurs
+    if groups is not None:
+        q["term_group"] = groups
+    q["min_should_match"] = msm
+    return q
+
+
+_BOOL_SHAPES = [  # (terms, occurs, groups, msm): the shapes of benches/and_or_queries.rs:142-155 and of boolean_query/mod.rs
+    ([2, 1, 3], [1, 1, 1], [0, 1, 1], 0),            # +c +(b OR d)
+    ([0, 2, 5], [1, 1, 1], [0, 1, 1], 0),            # +e +(c OR a)
+    ([2, 1, 3, 0], [1, 1, 1, 1], [0, 0, 1, 1], 0),   # +(c OR b) +(d OR e)
+    ([0, 1, 4], [1, 0, 0], None, 0),                 # +a b e   (RequiredOptionalScorer)
+    ([1, 2, 0], [0, 0, 2], None, 0),                 # b c -a
+    ([3, 0, 1], [1, 2, 2], None, 0),                 # +d -a -b (Exclude with two scorers)
+    ([1, 2, 3, 4], [1, 1, 0, 2], [7, 7, 9, 9], 0),   # +(b OR c) d -e
+    ([0, 1, 2, 3], [1, 0, 0, 0], None, 2),           # +a and at least two of b c d
+    ([1, 2, 3, 4], [0, 0, 0, 0], None, 2),           # at least two of b c d e (Disjunction with minimum match)
+    ([1, 2], [0, 0], None, 2),                       # as many as there are: they act as MUST clauses
+    ([0, 1], [1, 1], None, 0),                       # plain conjunction
+    ([3, 4, 5], [0, 0, 0], None, 0),                 # plain union
+    ([2], [1], None, 0),                             # +c
+    ([2], [2], None, 0),                             # -c alone: nothing
+]
+
+
+def test_mixed_boolean_shapes(ctx, synth):
+    if ctx.engine != "tile":
+        pytest.skip("TQ_OP_BOOL runs on the tile engine only")
+    ix, oi, base = synth
+    qs = []
+    for k in (1, 10, 300):
+        for terms, occ, grp, msm in _BOOL_SHAPES:
+            qs.append(_bool_query(ix.query(TQ_OP_OR, terms, k, segment_base=base), occ, grp, msm))
+    qb = QueryBatch(qs)
+    g, c = ctx.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8)
+    assert_same(g, c, qb.nq)
+    n = len(_BOOL_SHAPES)
+    assert len(hits(g, 2 * n + 0)) > 0 and hits(g, 2 * n + 13) == []
+    # pure shapes return the rows of the specialised paths
+    plain = ctx.search_batch(QueryBatch([ix.query(TQ_OP_AND, [0, 1], 300, segment_base=base), ix.query(TQ_OP_OR, [3, 4, 5], 300, segment_base=base)]))
+    assert hits(g, 2 * n + 10) == hits(plain, 0) and hits(g, 2 * n + 11) == hits(plain, 1)
+
+
+def test_mixed_boolean_small_segments_with_deletes_and_absent_terms(ctx):
+    if ctx.engine != "tile":
+        pytest.skip("TQ_OP_BOOL runs on the tile engine only")
+    rng = np.random.default_rng(4711)
+    segs = _random_segments(rng, 3, 6, deletes=True)
+    segs[1].terms[3] = (0, 0, 0)  # term 3 absent from one segment: an EmptyScorer there
+    segs[2].terms[1] = (0, 0, 0)
+    queries = []
+    for terms, occ, grp, msm in _BOOL_SHAPES:
+        for k in (5, 1000):
+            queries.append(_bool_query(make_query(TQ_OP_OR, segs, terms, k), occ, grp, msm))
+    g, c, nq = _run_both(ctx, segs, queries)
+    assert_same(g, c, nq)
+
+
+def test_count_mixed_boolean_shapes(ctx, synth):
+    """searcher.search(&query, &Count) for the mixed shapes (k_count_bool): alive docs matching, vs the oracle's Count."""
+    ix, oi, base = synth
+    qs = [_bool_query(ix.query(TQ_OP_OR, terms, 1, segment_base=base), occ, grp, msm) for terms, occ, grp, msm in _BOOL_SHAPES]
+    qb = QueryBatch(qs)
+    g, c = ctx.count_batch(qb), oi.count_batch(qb)
+    assert (g == c).all(), (g, c)
+    assert g[0] > 0 and g[13] == 0
+    rng = np.random.default_rng(815)
+    segs = _random_segments(rng, 3, 6, deletes=True)
+    segs[0].terms[2] = (0, 0, 0)
+    oi2 = both(ctx, segs)
+    qb2 = QueryBatch([_bool_query(make_query(TQ_OP_OR, segs, terms, 1), occ, grp, msm) for terms, occ, grp, msm in _BOOL_SHAPES])
+    assert (ctx.count_batch(qb2) == oi2.count_batch(qb2)).all()
