@@ -340,9 +340,12 @@ __device__ __forceinline__ bool tile_eval_bool(const TileView& V, const uint16_t
   return true;
 }
 
+constexpr uint32_t kTileStageWords = 2u * kTileMaxBig + kTileWarps * 17u;
 // Shared memory of a k_tile CTA: the work list (TileQ records + segments) and two windows for the rare heavy pairs ...
 __host__ __device__ constexpr size_t tile_union_bytes(uint32_t max_queries, uint32_t seg_cap, uint32_t n_win) {
-  return ((size_t)n_win * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + (size_t)seg_cap * sizeof(TileSeg) + 15) & ~(size_t)15;
+  // (the segment list doubles as stage A's scratch: never smaller than kTileStageWords words)
+  const size_t seg_bytes = (size_t)seg_cap * sizeof(TileSeg) > kTileStageWords * 4u ? (size_t)seg_cap * sizeof(TileSeg) : kTileStageWords * 4u;
+  return ((size_t)n_win * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + seg_bytes + 15) & ~(size_t)15;
 }
 __host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots, uint32_t max_big, uint32_t max_queries, uint32_t seg_cap,
                                                       uint32_t cl_cap, uint32_t n_win) {
@@ -372,6 +375,12 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   uint16_t* s_cl = s_heavy + TP.max_queries;                                   // [cl_cap] this segment's clause slots
   __shared__ uint32_t s_total, s_nheavy, s_hpos, s_nflat, s_nseg, s_segpos, s_segvalid;
   __shared__ unsigned long long s_stat[8];
+  // stage A scratch, in the (then idle) segment list: the dense slots' ranges of this tile and each warp's prefix over its slots
+  uint32_t* s_ba = reinterpret_cast<uint32_t*>(s_seg);                         // [kTileMaxBig] first pair of the slot in this tile
+  uint32_t* s_bn = s_ba + kTileMaxBig;                                         // [kTileMaxBig] ... and how many
+  uint32_t (*s_wpre)[9] = reinterpret_cast<uint32_t (*)[9]>(s_bn + kTileMaxBig);
+  uint32_t (*s_wa)[8] = reinterpret_cast<uint32_t (*)[8]>(s_bn + kTileMaxBig + kTileWarps * 9u);
+  static_assert(2u * kTileMaxBig + kTileWarps * 17u <= kTileStageWords, "stage A scratch");
   const TUnit U = TP.units[unit_base + blockIdx.x];
   const TSeg G = TP.segs[U.tseg];
   const TSlot* __restrict__ slots = TP.slots + G.slot_base;
@@ -407,37 +416,76 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
 
   for (uint32_t t = U.t0; t < U.t1; ++t) {
     const uint32_t lo = t * kTile, hi = lo + kTile;
+    if (tid < G.n_big) {  // three independent loads per dense slot: one round trip for the whole tile
+      const uint32_t a = __ldg(G.tix + (size_t)t * G.n_big + tid), b = __ldg(G.tix + (size_t)(t + 1u) * G.n_big + tid);
+      s_ba[tid] = __ldg(&slots[tid].pair_base) + a;
+      s_bn[tid] = b - a;
+    }
     if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; s_nflat = 0; s_nseg = 0; s_segpos = 0; s_segvalid = TP.seg_cap; }
     __syncthreads();
     // ---- stage A: this tile's pairs of every slot -> shared memory --------------------------------------------------------
-    for (uint32_t s = warp; s < G.n_big; s += kTileWarps) {  // dense lists: a warp copies [tix[t], tix[t+1]) and maps the docs
-      const TSlot sl = slots[s];
-      const uint32_t a = __ldg(G.tix + (size_t)t * G.n_big + s), b = __ldg(G.tix + (size_t)(t + 1u) * G.n_big + s);
-      const uint32_t n = b - a;
+    if (warp < G.n_big) {
+      // dense lists: warp w owns slots w, w+8, ... (<= 8 of them).  Their [tix[t], tix[t+1]) ranges are laid end to end and copied as
+      // ONE flat loop, so the loads of all the warp's slots are in flight together (one DRAM round trip per 128 pairs instead
+      // of three dependent ones per slot)
+      const uint32_t ne = (G.n_big - warp + kTileWarps - 1u) / kTileWarps;
+      uint32_t n_e = 0;
+      if (lane < ne) {
+        const uint32_t s = warp + lane * kTileWarps;
+        n_e = s_bn[s];
+        s_wa[warp][lane] = s_ba[s];
+      }
+      const uint32_t incl = warp_incl_scan(n_e, lane);
+      if (lane < 8u) s_wpre[warp][lane + 1u] = incl;
+      if (lane == 0) s_wpre[warp][0] = 0u;
+      const uint32_t total_w = __shfl_sync(kFull, incl, 7);
       uint32_t base = 0;
-      if (lane == 0 && n) base = atomicAdd(&s_total, n);
+      if (lane == 0 && total_w) base = atomicAdd(&s_total, total_w);
       base = __shfl_sync(kFull, base, 0);
-      float mx = 0.0f;
-      const uint32_t* __restrict__ d = TP.p_docs + sl.pair_base + a;
-      const float* __restrict__ sc = TP.p_scores + sl.pair_base + a;
-      uint32_t* bits = s_bits + s * 32u;
-      bits[lane] = 0u;
+      for (uint32_t e = 0; e < ne; ++e) s_bits[(warp + e * kTileWarps) * 32u + lane] = 0u;
       __syncwarp();
-      if (base + n <= TP.p_cap) {
-        for (uint32_t i = lane; i < n; i += 32) {
-          const float v = __ldg(sc + i);
-          const uint32_t off = __ldg(d + i) - lo;
-          s_off[base + i] = (uint16_t)off;
-          s_score[base + i] = v;
-          atomicOr(&bits[off >> 5], 1u << (off & 31u));
-          mx = fmaxf(mx, v);
+      const bool fits = base + total_w <= TP.p_cap;
+      if (fits) {
+        for (uint32_t i0 = 0; i0 < total_w; i0 += 128u) {
+          uint32_t dd[4], ss[4];
+          float vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            dd[u] = 0xFFFFFFFFu;
+            if (i < total_w) {
+              uint32_t e = 0;
+              while (i >= s_wpre[warp][e + 1u]) ++e;
+              ss[u] = warp + e * kTileWarps;
+              const size_t g = (size_t)s_wa[warp][e] + (i - s_wpre[warp][e]);
+              dd[u] = __ldg(TP.p_docs + g);
+              vv[u] = __ldg(TP.p_scores + g);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const uint32_t i = i0 + (uint32_t)u * 32u + lane;
+            if (dd[u] != 0xFFFFFFFFu) {
+              const uint32_t off = dd[u] - lo;
+              s_off[base + i] = (uint16_t)off;
+              s_score[base + i] = vv[u];
+              atomicOr(&s_bits[ss[u] * 32u + (off >> 5)], 1u << (off & 31u));
+            }
+          }
         }
       }
       __syncwarp();
-      const uint32_t cnt = (uint32_t)__popc(bits[lane]);
-      s_rank[s * 32u + lane] = (uint16_t)(warp_incl_scan(cnt, lane) - cnt);
-      mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(mx)));  // mx >= 0
-      if (lane == 0) { s_info[s] = (base & 0xFFFFu) | (n << 16); s_max[s] = mx; }
+      for (uint32_t e = 0; e < ne; ++e) {
+        const uint32_t s = warp + e * kTileWarps;
+        const uint32_t b = base + s_wpre[warp][e], n = s_wpre[warp][e + 1u] - s_wpre[warp][e];
+        const uint32_t cnt = (uint32_t)__popc(s_bits[s * 32u + lane]);
+        s_rank[s * 32u + lane] = (uint16_t)(warp_incl_scan(cnt, lane) - cnt);
+        float mx = 0.0f;
+        if (fits)
+          for (uint32_t i = lane; i < n; i += 32) mx = fmaxf(mx, s_score[b + i]);
+        mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(mx)));  // mx >= 0
+        if (lane == 0) { s_info[s] = (b & 0xFFFFu) | (n << 16); s_max[s] = mx; }
+      }
     }
     for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {  // sparse lists: one thread walks its cursor
       uint32_t nd = s_nxt[s];
