@@ -373,10 +373,10 @@ def main():
             if i == 0 and args.parity_queries:
                 parity_rows = [np.array(x[:args.parity_queries]) for x in outs[0][1:]]
         else:
-            cross_gpu_merge.run(bt)
-            o = cross_gpu_merge(bt)
+            cross_gpu_merge.run(bt)                    # phases + key exchanges, all enqueued on the batch's stream
             if nxt_index is not None:
                 nxt = ctx.prepare(qbs[nxt_index])
+            o = cross_gpu_merge(bt)                    # waits for the run; packed all-gather + device merge
             st = ctx.stats()
             h2d, d2h = st["h2d_bytes"], 0
             if rank == 0:

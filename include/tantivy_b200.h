@@ -168,7 +168,8 @@ typedef struct {
   uint64_t tile_scratch_bytes;  /* HBM scratch of the pair arrays, tile indexes and samples */
   uint64_t tile_fallbacks;      /* 1 if the run overflowed a tile engine buffer and was repeated on the per-query kernels */
   uint64_t tile_counters[8];    /* cumulative, with TQ_TILE_COUNTERS=1: (query, tile) pairs seen / skipped / light / heavy,
-                                   essential postings applied, docs completed, docs at or above the threshold */
+                                   essential postings applied, docs completed, docs at or above the threshold;
+                                   [7] (always): dynamic shared memory bytes of a k_tile CTA of the last prepared group */
 } tq_stats;
 
 /* ---- context ------------------------------------------------------------------------- */

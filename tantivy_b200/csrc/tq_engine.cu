@@ -144,6 +144,9 @@ struct tq_ctx {
   uint32_t tile = 1, tile_scratch_mb = 24576, tile_sample_div = 16, tile_round_div1 = 8, tile_round_div2 = 2, tile_light_max = 96, tile_counters = 0;
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_seg_cap_hook = 0;
+  uint32_t tile_windows = 0;
+  uint32_t tile_max_slots = kTileMaxSlots, tile_max_queries = kTileMaxQueries;
+  uint64_t tile_smem_last = 0;
   uint32_t tile_cand_floor = 32768, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 6, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
 };
@@ -254,7 +257,10 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_cand_floor = env_u32("TQ_TILE_CAND_FLOOR", 32768);  // smallest candidate region of a tile query (test hook: tiny regions overflow)
   c->tile_max_dens_x1000 = env_u32("TQ_TILE_MAX_DENS_X1000", 0);  // test hook: cap on a group's pairs per 1000 docs (forces several groups)
   c->tile_pcap_hook = env_u32("TQ_TILE_PCAP", 0);            // test hook: tile buffer size (forces overflowing tiles)
-  c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces the window path)
+  c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces extra routing rounds)
+  c->tile_max_slots = std::min<uint32_t>(kTileMaxSlots, std::max<uint32_t>(64u, env_u32("TQ_TILE_MAX_SLOTS", kTileMaxSlots)));  // distinct lists of one segment per group (shared memory per CTA grows by 20 B per list)
+  c->tile_max_queries = std::min<uint32_t>(kTileMaxQueries, std::max<uint32_t>(1u, env_u32("TQ_TILE_MAX_QUERIES", kTileMaxQueries)));  // queries of one segment per group
+  c->tile_windows = env_u32("TQ_TILE_WINDOWS", 0);           // warps with a window for the heavy pairs (0 = kTileExactWindows)
   c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 6);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
   cudaError_t err = cudaMalloc(&c->d_lists, (size_t)c->lists_cap * sizeof(ListDesc));
@@ -317,6 +323,7 @@ int tq_get_stats(tq_ctx* c, tq_stats* out) {
   unsigned long long h[16];
   if (cudaMemcpy(h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
     for (int i = 0; i < 8; ++i) { out->or_windows[i] = h[i]; out->tile_counters[i] = h[8 + i]; }
+  out->tile_counters[7] = c->tile_smem_last;
   return TQ_OK;
 }
 
@@ -721,13 +728,13 @@ int bool_structure(const tq_query& q, const uint32_t* term_idx, const uint32_t* 
 }
 
 // Would the group still satisfy k_tile's limits with this query added?  Returns the number of NEW pair elements, or -1.
-int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
+int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000, uint32_t max_slots, uint32_t max_queries) {
   int64_t new_pairs = 0;
   for (size_t pi = 0; pi < n_plans; ++pi) {
     const SegPlan& sp = plans[pi];
     auto it = g.seg_of.find(sp.segment_ord);
     const TileGroupBuild::SegB* sb = it == g.seg_of.end() ? nullptr : &g.segs[it->second];
-    if (sb && sb->queries.size() + 1 > kTileMaxQueries) return -1;
+    if (sb && sb->queries.size() + 1 > max_queries) return -1;
     size_t n_slots = sb ? sb->slots.size() : 0;
     double dens = sb ? sb->dens : 0.0;
     for (auto& h : sp.here) {
@@ -738,22 +745,22 @@ int64_t tile_admit_cost(const TileGroupBuild& g, const SegPlan* plans, size_t n_
         new_pairs += ((int64_t)h.first + 127) / 128 * 128;
       }
     }
-    if (n_slots > kTileMaxSlots) return -1;
+    if (n_slots > max_slots) return -1;
     if (dens * kTile * 1.5 + 256.0 > (double)kTileMaxPairs || (max_dens_x1000 && dens * 1000.0 > max_dens_x1000)) return -1;
   }
   return new_pairs;
 }
 
 // Cheap sufficient test (every clause counted as a new list): most queries pass it and skip the exact cost.
-bool tile_admit_surely_fits(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000) {
+bool tile_admit_surely_fits(const TileGroupBuild& g, const SegPlan* plans, size_t n_plans, uint32_t max_dens_x1000, uint32_t max_slots, uint32_t max_queries) {
   for (size_t pi = 0; pi < n_plans; ++pi) {
     const SegPlan& sp = plans[pi];
     auto it = g.seg_of.find(sp.segment_ord);
     const TileGroupBuild::SegB* sb = it == g.seg_of.end() ? nullptr : &g.segs[it->second];
-    if (sb && sb->queries.size() + 1 > kTileMaxQueries) return false;
+    if (sb && sb->queries.size() + 1 > max_queries) return false;
     double dens = sb ? sb->dens : 0.0;
     for (auto& h : sp.here) dens += (double)h.first / std::max(1u, sp.seg->max_doc);
-    if ((sb ? sb->slots.size() : 0) + sp.here.size() > kTileMaxSlots) return false;
+    if ((sb ? sb->slots.size() : 0) + sp.here.size() > max_slots) return false;
     if (dens * kTile * 1.5 + 256.0 > (double)kTileMaxPairs || (max_dens_x1000 && dens * 1000.0 > max_dens_x1000)) return false;
   }
   return true;
@@ -1000,11 +1007,11 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       bool on_tile = false;
       if (tile_on && (((c->tile_ops >> op) & 1u) || op == TQ_OP_BOOL) && n_plans) {
         if (tgroups.empty()) tgroups.emplace_back();
-        bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000);
-        if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000) >= 0;
+        bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries);
+        if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries) >= 0;
         if (!fits && !tgroups.back().segs.empty()) {  // the current group is full: open the next one
           TileGroupBuild fresh;
-          if (tile_admit_cost(fresh, plans.data(), n_plans, c->tile_max_dens_x1000) >= 0) { tgroups.emplace_back(); fits = true; }
+          if (tile_admit_cost(fresh, plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries) >= 0) { tgroups.emplace_back(); fits = true; }
         }
         if (fits && tile_pairs_total + q_postings + 128ull * n_plans * q.n_terms <= tile_pair_budget) {
           tile_pairs_total += tile_admit(tgroups.back(), (uint32_t)qi, op, plans.data(), n_plans);
@@ -1356,12 +1363,15 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     TP.max_slots = gs.max_slots;
     TP.max_big = gs.max_big;
     TP.max_queries = (gs.max_queries + 1u) & ~1u;
-    TP.seg_cap = std::min<uint32_t>(2048u, std::max<uint32_t>(256u, 2u * TP.max_queries));
+    // per-tile work list: about two (query, essential clause) entries per query, more for wide unions; a tile that needs more
+    // takes another round of routing + expansion
+    TP.seg_cap = std::min<uint32_t>(4096u, std::max<uint32_t>(256u, std::max<uint32_t>(2u, gs.max_clauses / 4u) * TP.max_queries));
     if (c->tile_seg_cap_hook) TP.seg_cap = c->tile_seg_cap_hook;
     TP.light_max = c->tile_light_max;
     TP.cl_cap = gs.max_clause_words <= 16384u ? ((gs.max_clause_words + 3u) & ~3u) : 0u;
-    TP.n_win = gs.max_clauses > 8u ? kTileWarps : kTileExactWindows;  // wide unions: many (query, tile) pairs take the window path
+    TP.n_win = c->tile_windows ? std::min<uint32_t>(c->tile_windows, kTileWarps) : kTileExactWindows;
     run.smem = tile_smem_bytes(gs.p_cap, gs.max_slots, TP.max_big, TP.max_queries, TP.seg_cap, TP.cl_cap, TP.n_win);
+    c->tile_smem_last = run.smem;
     if (run.smem > 200u * 1024u) return fail(TQ_ERR_UNSUPPORTED, "tile group needs more shared memory than an SM has");
     b->groups.push_back(run);
   }

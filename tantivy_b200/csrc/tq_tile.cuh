@@ -373,7 +373,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   uint16_t* s_off = s_rank + TP.max_big * 32u;                                 // [p_cap]
   uint16_t* s_heavy = s_off + TP.p_cap;                                        // [max_queries]
   uint16_t* s_cl = s_heavy + TP.max_queries;                                   // [cl_cap] this segment's clause slots
-  __shared__ uint32_t s_total, s_nheavy, s_hpos, s_nflat, s_nseg, s_segpos, s_segvalid;
+  __shared__ uint32_t s_total, s_nheavy, s_hpos, s_nflat, s_nseg, s_segpos, s_segvalid, s_ndefer;
+  __shared__ uint32_t s_defer[kTileMaxQueries / 32u];  // queries that did not fit this round's work list
   __shared__ unsigned long long s_stat[8];
   // stage A scratch, in the (then idle) segment list: the dense slots' ranges of this tile and each warp's prefix over its slots
   uint32_t* s_ba = reinterpret_cast<uint32_t*>(s_seg);                         // [kTileMaxBig] first pair of the slot in this tile
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   const TileView V{s_off, s_score, s_info, s_bits, s_rank, s_mask, G.n_big};
   for (uint32_t i = tid; i < n_win * kTile; i += kTileThreads) s_acc[i] = neg_zero;
   if (tid < 8) s_stat[tid] = 0ull;
+  if (tid < kTileMaxQueries / 32u) s_defer[tid] = 0u;
   // the segment's queries and their clause slots are read for every tile: keep them on chip (clause_base becomes an index into cl0)
   const bool cl_staged = G.n_clause_words <= TP.cl_cap;
   const uint16_t* __restrict__ cl0 = cl_staged ? s_cl : TP.clauses + G.clause_base;
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       s_ba[tid] = __ldg(&slots[tid].pair_base) + a;
       s_bn[tid] = b - a;
     }
-    if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; s_nflat = 0; s_nseg = 0; s_segpos = 0; s_segvalid = TP.seg_cap; }
+    if (tid == 0) { s_total = 0; s_nheavy = 0; s_hpos = 0; s_nflat = 0; s_nseg = 0; s_segpos = 0; s_segvalid = TP.seg_cap; s_ndefer = 0; }
     __syncthreads();
     // ---- stage A: this tile's pairs of every slot -> shared memory --------------------------------------------------------
     if (warp < G.n_big) {
@@ -566,7 +568,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
     // ---- stage B1: one thread per query -- bounds and routing ---------------------------------------------------------------
     // skipped: no doc of the tile can reach the query's threshold;  flat: the essential postings become work items that the CTA's
     // threads share evenly (B2);  heavy: a warp accumulates the query's window (B3; sample launches, and pairs with many postings).
+    // (a work list that fills up defers the remaining pairs to another round of B1 + B2: the list is sized for the common case)
+    for (uint32_t round = 0;; ++round) {
     for (uint32_t qi = tid; qi < G.n_queries; qi += kTileThreads) {
+      if (round) {
+        const uint32_t bit = 1u << (qi & 31u);
+        if (!(s_defer[qi >> 5] & bit)) continue;
+        atomicAnd(&s_defer[qi >> 5], ~bit);
+      }
       const TileTQ tq = s_tq[qi];
       const uint16_t* __restrict__ cl = cl0 + tq.clause_base;
       const uint32_t th_key = *(volatile unsigned int*)&P.qstate[tq.query].theta;
@@ -645,10 +654,14 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       // sample launch: ANY set of real scores is a valid sample -- at most kSampleSeg postings per driving clause, no window path
       if (sample_mode && *(volatile unsigned int*)&TP.sample_count[tq.query] >= TP.sample_cap) continue;
       bool heavy = !sample_mode && cnt > TP.light_max && op != kTileOpAnd && op != kTileOpBool && rec_ne >= 2u;
+      if (n_segs > TP.seg_cap) heavy = true;  // (test hook sizes only)
       if (!heavy) {
         const uint32_t sb = atomicAdd(&s_nseg, n_segs);
-        if (sb + n_segs > TP.seg_cap) { heavy = true; atomicMin(&s_segvalid, sb); }  // the work list is full (entries from here on are not written): the window path takes any pair
-        else {
+        if (sb + n_segs > TP.seg_cap) {  // the work list is full (entries from here on are not written): next round
+          atomicMin(&s_segvalid, sb);
+          atomicOr(&s_defer[qi >> 5], 1u << (qi & 31u));
+          s_ndefer = 1u;
+        } else {
           const uint32_t qslot = atomicAdd(&s_nflat, 1u);
           s_q[qslot] = rec;
           uint32_t w = sb;
@@ -674,6 +687,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint16_t)qi;
     }
     __syncthreads();
+    const bool more_rounds = s_ndefer != 0u;
     // ---- stage B2: the flat pairs' essential postings, one per thread --------------------------------------------------------
     {
       const uint32_t n_seg = min(s_nseg, s_segvalid);
@@ -687,14 +701,15 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
         if (sbase + lane < n_seg) mine = s_seg[sbase + lane];
         const uint32_t incl = warp_incl_scan((uint32_t)mine.len, lane);
         const uint32_t total = __shfl_sync(kFull, incl, 31);
+        const uint32_t excl = incl - mine.len;
         for (uint32_t ibase = 0; ibase < total; ibase += 32u) {
           const uint32_t item = ibase + lane;
-          uint32_t j = 0;  // first lane whose inclusive count exceeds `item`
-#pragma unroll
-          for (uint32_t step = 16; step > 0; step >>= 1) {
-            const uint32_t v = __shfl_sync(kFull, incl, (j + step - 1u) & 31u);
-            if (v <= item) j += step;
-          }
+          // the segment of item `ibase + lane`: every listed segment holds a posting, so segment numbers grow by one at each
+          // start; (segments that start before this chunk) - 1 + (starts at or before the lane's item)
+          const uint32_t rel = excl - ibase;  // (wraps for segments that start before the chunk)
+          const uint32_t starts = __reduce_or_sync(kFull, (mine.len && rel < 32u) ? (1u << rel) : 0u);
+          const uint32_t earlier = (uint32_t)__popc(__ballot_sync(kFull, mine.len && excl < ibase));
+          const uint32_t j = earlier - 1u + (uint32_t)__popc(starts & (0xFFFFFFFFu >> (31u - lane)));
           const uint32_t incl_j = __shfl_sync(kFull, incl, j & 31u);
           uint32_t s_query = 0xFFFFFFFFu - lane, s_key = 0;  // sample launch: this lane's sample (if any), handed over below
           if (item < total) {
@@ -731,6 +746,11 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
           }
         }
       }
+    }
+    if (!more_rounds) break;
+    __syncthreads();
+    if (tid == 0) { s_nflat = 0; s_nseg = 0; s_segpos = 0; s_segvalid = TP.seg_cap; s_ndefer = 0; }
+    __syncthreads();
     }
     // ---- stage B3: one warp per heavy pair, a window of f32 score slots ----------------------------------------------------
     {

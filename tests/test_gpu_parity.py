@@ -544,10 +544,11 @@ def test_tile_overflow_is_repeated_on_the_per_query_kernels(synth, hook):
         c.close()
 
 
-@pytest.mark.parametrize("hook", [dict(TQ_TILE_SEG_CAP=8), dict(TQ_TILE_LIGHT_MAX=0), dict(TQ_TILE_LIGHT_MAX=100000), dict(TQ_TILE_SAMPLE_DIV=0),
+@pytest.mark.parametrize("hook", [dict(TQ_TILE_SEG_CAP=8), dict(TQ_TILE_SEG_CAP=3), dict(TQ_TILE_LIGHT_MAX=0), dict(TQ_TILE_LIGHT_MAX=0, TQ_TILE_WINDOWS=8), dict(TQ_TILE_LIGHT_MAX=100000), dict(TQ_TILE_SAMPLE_DIV=0),
                                   dict(TQ_TILE_BIG_MIN=1), dict(TQ_TILE_BIG_MIN=100000), dict(TQ_TILE_UNITS=1), dict(TQ_TILE_ROUND_DIV1=2, TQ_TILE_ROUND_DIV2=2)])
 def test_tile_paths_agree(synth, hook):
-    """Every route through k_tile gives the same rows: a full work list (pairs overflow to the window path), window path only,
+    """Every route through k_tile gives the same rows: a full work list (further routing rounds per tile; with 3 entries the
+    wider unions take the window path), window path only (2 or 8 window warps),
     flat path only, no sample launch, every list dense (bitmap lookups) / every list sparse (binary searches), one CTA per launch,
     other launch cuts."""
     ix, oi, base = synth
