@@ -26,7 +26,7 @@ print("index", round(time.time() - t0, 2), "s", shard.index_bytes, "bytes", len(
 ctx = T.Context(0)
 shard.register(ctx)
 qbs = [bench.marshal(shard, b) for b in batches]
-keys = ("kernel_ms", "score_ms", "tile_ms", "theta_ms", "final_ms", "or_ms", "and_ms", "term_ms")
+keys = keys_ms = ("kernel_ms", "score_ms", "tile_ms", "theta_ms", "final_ms", "or_ms", "and_ms", "term_ms")
 c0 = np.array(ctx.stats()["tile_counters"], dtype=np.int64)
 for i in range(steps + 2):
     t0 = time.perf_counter()
@@ -43,6 +43,33 @@ for i in range(steps + 2):
                       "groups": st["tile_groups"], "smem": int(c1[7]),
                       "counters(pairs,skip,light,heavy,ess,compl,pass)": (c1 - c0)[:7].tolist()}), flush=True)
     c0 = c1
+    bt.close()
+if os.environ.get("PROBE_THETA"):
+    # how much better would the step be with (nearly) final thresholds from the start?  Run a batch up to its last phase, keep
+    # its thresholds, then run the same batch again with those thresholds imported after the sample phase.
+    import torch
+    keys = torch.zeros(nq, dtype=torch.int64, device="cuda:0")
+    bt = ctx.prepare(qbs[0])
+    n_ph = bt.phases()
+    for ph in range(n_ph - 1):
+        bt.run_phase(ph)
+    bt.thresholds_export_dev(keys.data_ptr())
+    bt.run_phase(n_ph - 1)
+    bt.results_dev()
+    bt.close()
+    c0 = np.array(ctx.stats()["tile_counters"], dtype=np.int64)
+    bt = ctx.prepare(qbs[0])
+    t1 = time.perf_counter()
+    bt.run_phase(0)
+    bt.thresholds_import_dev(keys.data_ptr())
+    for ph in range(1, n_ph):
+        bt.run_phase(ph)
+    bt.results_dev()
+    t2 = time.perf_counter()
+    st = ctx.stats()
+    c1 = np.array(st["tile_counters"], dtype=np.int64)
+    print(json.dumps({"theta_import": True, "run_ms": round(1e3 * (t2 - t1), 2), **{k: round(st[k], 3) for k in keys_ms},
+                      "counters(pairs,skip,light,heavy,ess,compl,pass)": (c1 - c0)[:7].tolist()}), flush=True)
     bt.close()
 t0 = time.perf_counter()
 out = ctx.search_batch(qbs[0])

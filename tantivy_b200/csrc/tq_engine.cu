@@ -145,7 +145,7 @@ struct tq_ctx {
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_seg_cap_hook = 0;
   uint32_t tile_windows = 0;
-  uint32_t tile_max_slots = kTileMaxSlots, tile_max_queries = kTileMaxQueries;
+  uint32_t tile_max_slots = kTileMaxSlots, tile_max_queries = kTileMaxQueries, tile_wide_queries = 256;
   uint64_t tile_smem_last = 0;
   uint32_t tile_cand_floor = 32768, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 6, tile_units = 148 * 6;
   uint32_t or_prune = 1, or_strip = 1, or_pipe = 1, strip_prune = 1, strip_sample_div = 32, strip_sample_div2 = 8, strip_sample_div3 = 2, strip_ne_div = 8, strip_ne_div2 = 64;
@@ -260,6 +260,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_seg_cap_hook = env_u32("TQ_TILE_SEG_CAP", 0);      // test hook: entries of the per-tile work list (forces extra routing rounds)
   c->tile_max_slots = std::min<uint32_t>(kTileMaxSlots, std::max<uint32_t>(64u, env_u32("TQ_TILE_MAX_SLOTS", kTileMaxSlots)));  // distinct lists of one segment per group (shared memory per CTA grows by 20 B per list)
   c->tile_max_queries = std::min<uint32_t>(kTileMaxQueries, std::max<uint32_t>(1u, env_u32("TQ_TILE_MAX_QUERIES", kTileMaxQueries)));  // queries of one segment per group
+  c->tile_wide_queries = std::max<uint32_t>(1u, env_u32("TQ_TILE_WIDE_QUERIES", 256));  // ... for queries of more than 8 terms
   c->tile_windows = env_u32("TQ_TILE_WINDOWS", 0);           // warps with a window for the heavy pairs (0 = kTileExactWindows)
   c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 6);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
@@ -1007,11 +1008,14 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       bool on_tile = false;
       if (tile_on && (((c->tile_ops >> op) & 1u) || op == TQ_OP_BOOL) && n_plans) {
         if (tgroups.empty()) tgroups.emplace_back();
-        bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries);
-        if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries) >= 0;
+        // wide unions: every query brings its clause words, work-list entries and (mostly distinct) lists into the CTA's shared
+        // memory; smaller groups keep two CTAs per SM (configs[4]: 1.64 s -> 1.05 s per 512 20-term queries on 500M docs)
+        const uint32_t max_q = q.n_terms > 8 ? std::min(c->tile_max_queries, c->tile_wide_queries) : c->tile_max_queries;
+        bool fits = tile_admit_surely_fits(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, max_q);
+        if (!fits) fits = tile_admit_cost(tgroups.back(), plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, max_q) >= 0;
         if (!fits && !tgroups.back().segs.empty()) {  // the current group is full: open the next one
           TileGroupBuild fresh;
-          if (tile_admit_cost(fresh, plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, c->tile_max_queries) >= 0) { tgroups.emplace_back(); fits = true; }
+          if (tile_admit_cost(fresh, plans.data(), n_plans, c->tile_max_dens_x1000, c->tile_max_slots, max_q) >= 0) { tgroups.emplace_back(); fits = true; }
         }
         if (fits && tile_pairs_total + q_postings + 128ull * n_plans * q.n_terms <= tile_pair_budget) {
           tile_pairs_total += tile_admit(tgroups.back(), (uint32_t)qi, op, plans.data(), n_plans);
