@@ -380,11 +380,10 @@ def main():
             st = ctx.stats()
             h2d, d2h = st["h2d_bytes"], 0
             if rank == 0:
-                res = [t.cpu() for t in o]  # waits for the merge
-                d2h = sum(t.numel() * t.element_size() for t in res)
+                res = cross_gpu_merge.fetch_host(bt)  # one D2H of the merged rows on the batch's stream; waits for it
+                d2h = sum(a.nbytes for a in res)
                 if i == 0 and args.parity_queries:
-                    parity_rows = [res[0].numpy()[:args.parity_queries].copy(), res[1].numpy().astype(np.uint32)[:args.parity_queries],
-                                   res[2].numpy().astype(np.uint32)[:args.parity_queries], res[3].numpy().astype(np.uint32)[:args.parity_queries]]
+                    parity_rows = [np.array(a[:args.parity_queries]) for a in res]
             else:
                 torch.cuda.synchronize()
         bt.close()

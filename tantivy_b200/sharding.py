@@ -7,6 +7,7 @@ already merged on its GPU (k_final); the cross-rank step is merge_fruits again
 (src/collector/sort_key_top_collector.rs:54-60,76-95) over `world` lists of k rows.
 The statistics follow Bm25StatisticsProvider for Searcher (src/query/bm25.rs:27-50):
 N = sum of max_doc, avg fieldnorm = sum(total_num_tokens) / N, n = sum of doc_freq."""
+import os
 import numpy as np
 
 from ._abi import QueryBatch
@@ -170,11 +171,18 @@ class CrossGpuMerger:
         self.torch = torch
         i32 = torch.int32
         self.words = 3 * nq * k + nq
-        self.keys_l = torch.zeros((nq, k), dtype=i32, device=device)
-        self.keys_g = torch.zeros((self.world, nq, k), dtype=i32, device=device)
+        # keys per rank and query in the threshold exchange: the k-th best of the union of every rank's top-kx is a valid lower
+        # bound of the global k-th best for any kx (the keys are scores of distinct docs); it is the exact one unless a shard
+        # holds more than kx of the global top-k, which 2k/world + 8 makes unlikely for evenly sharded segments
+        self.kx = k if self.world <= 2 else min(k, (2 * k + self.world - 1) // self.world + 8)
+        if os.environ.get("TANTIVY_B200_EXCHANGE_KEYS"):  # (tests: any value >= 1 is valid)
+            self.kx = max(1, min(k, int(os.environ["TANTIVY_B200_EXCHANGE_KEYS"])))
+        self.keys_l = torch.zeros((nq, self.kx), dtype=i32, device=device)
+        self.keys_g = torch.zeros((self.world, nq, self.kx), dtype=i32, device=device)
         self.rows_l = torch.zeros((self.words,), dtype=i32, device=device)
         self.rows_g = torch.zeros((self.world, self.words), dtype=i32, device=device)
         self.rows_o = torch.zeros((self.words,), dtype=i32, device=device)
+        self.rows_h = None  # pinned host copy of the merged rows (fetch_host)
         self._streams = {}
 
     def _stream(self, batch):
@@ -191,9 +199,9 @@ class CrossGpuMerger:
             for phase in range(n):
                 batch.run_phase(phase)
                 if phase + 1 < n:
-                    batch.topkeys_export_dev(self.keys_l.data_ptr(), self.k)
+                    batch.topkeys_export_dev(self.keys_l.data_ptr(), self.kx)
                     self.dist.all_gather_into_tensor(self.keys_g, self.keys_l)
-                    batch.thresholds_from_keys_dev(self.keys_g.data_ptr(), self.world, self.k)
+                    batch.thresholds_from_keys_dev(self.keys_g.data_ptr(), self.world, self.kx)
 
     def __call__(self, batch):
         """batch: a finished tantivy_b200.Batch of this rank.  Returns (scores, segment ords, docs, counts) device tensors of
@@ -206,3 +214,18 @@ class CrossGpuMerger:
         r = self.nq * self.k
         o = self.rows_o
         return (o[:r].view(self.torch.float32).view(self.nq, self.k), o[r:2 * r].view(self.nq, self.k), o[2 * r:3 * r].view(self.nq, self.k), o[3 * r:])
+
+    def fetch_host(self, batch):
+        """After __call__(batch): ONE device-to-host copy of the merged rows on the batch's stream, then waits for that stream.
+        Returns numpy (scores f32 [nq, k], segment ords u32, docs u32, counts u32 [nq]); valid until the next fetch_host."""
+        import numpy as np
+        ext, _ = self._stream(batch)
+        if self.rows_h is None:
+            self.rows_h = self.torch.empty((self.words,), dtype=self.torch.int32, pin_memory=True)
+        with self.torch.cuda.stream(ext):
+            self.rows_h.copy_(self.rows_o, non_blocking=True)
+        ext.synchronize()
+        a = self.rows_h.numpy()
+        r = self.nq * self.k
+        return (a[:r].view(np.float32).reshape(self.nq, self.k), a[r:2 * r].view(np.uint32).reshape(self.nq, self.k),
+                a[2 * r:3 * r].view(np.uint32).reshape(self.nq, self.k), a[3 * r:].view(np.uint32))
