@@ -429,9 +429,9 @@ def main():
         # SURVEY.md §8(d) per kernel.  k_score_lists: every distinct list of the batch is read once (packed blocks + skip data =
         # its postings range, + one fieldnorm byte per posting) and written once as 8-byte (doc, score) pairs.  k_tile: the pairs
         # are read once per launch that covers their tile (the three exact launches partition the tiles, the sample launch re-reads
-        # 1/32 of them) + 16 B per candidate handed over.  Per-query kernels: exhaustive formula / device byte counter as before.
+        # 1/16 of them) + 16 B per candidate handed over.  Per-query kernels: exhaustive formula / device byte counter as before.
         score_bytes = float(stats["tile_list_bytes"] + stats["tile_postings"] + 8 * stats["tile_postings"])
-        tile_bytes = float(8 * stats["tile_postings"]) * (1.0 + 1.0 / 32.0) + 12.0 * wl["k"] * nq
+        tile_bytes = float(8 * stats["tile_postings"]) * (1.0 + 1.0 / 16.0) + 12.0 * wl["k"] * nq
         table = {
             "score": ("k_score_lists", score_bytes, tile_groups, "postings ranges + 1 B fieldnorm + 8 B pair written per posting, every distinct list once"),
             "tile": ("k_tile", tile_bytes, n_tile_launches * tile_groups, "8 B (doc, score) pair read per posting per covering launch + result rows"),

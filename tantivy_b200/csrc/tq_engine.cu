@@ -145,6 +145,8 @@ struct tq_ctx {
   uint32_t tile_ops = 7;  // bit per TQ_OP_*: which query shapes the tile engine takes
   uint32_t tile_seg_cap_hook = 0;
   uint32_t tile_windows = 0;
+  uint32_t phrase_side = 1;
+  uint32_t tile_terms = 2;
   uint32_t tile_max_slots = kTileMaxSlots, tile_max_queries = kTileMaxQueries, tile_wide_queries = 256;
   uint64_t tile_smem_last = 0;
   uint32_t tile_cand_floor = 32768, tile_max_dens_x1000 = 0, tile_pcap_hook = 0, tile_big_min = 6, tile_units = 148 * 6;
@@ -173,6 +175,9 @@ struct tq_batch {
   };
   tq_ctx* ctx = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;             // k_phrase runs here, next to the tile engine's launches on `stream`
+  cudaEvent_t ev_side0 = nullptr, ev_side1 = nullptr;
+  bool side_pending = false;               // `stream` has not waited for ev_side1 yet
   cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
   std::vector<Span> spans;  // per-kind kernel times of the current run (events are created once and reused)
   size_t n_spans = 0;
@@ -191,6 +196,7 @@ struct tq_batch {
   uint32_t nq = 0, kmax = 0;
   uint32_t n_units[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // term, and, or (window kernel), or (strip kernel), strip threshold rounds 1..3, phrase
   uint32_t unit_base[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t phrase_ct = 2;                 // most terms of a phrase in the batch (k_phrase's candidate stride)
   const PhraseAux* phrase_aux = nullptr;  // device: per clause of the batch's phrase queries (parallel to qlists)
   uint32_t strip_cached_max = 0;
   uint32_t or_max_lists = 0;  // most clauses of any window-kernel union in the batch
@@ -261,6 +267,8 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->tile_max_slots = std::min<uint32_t>(kTileMaxSlots, std::max<uint32_t>(64u, env_u32("TQ_TILE_MAX_SLOTS", kTileMaxSlots)));  // distinct lists of one segment per group (shared memory per CTA grows by 20 B per list)
   c->tile_max_queries = std::min<uint32_t>(kTileMaxQueries, std::max<uint32_t>(1u, env_u32("TQ_TILE_MAX_QUERIES", kTileMaxQueries)));  // queries of one segment per group
   c->tile_wide_queries = std::max<uint32_t>(1u, env_u32("TQ_TILE_WIDE_QUERIES", 256));  // ... for queries of more than 8 terms
+  c->tile_terms = env_u32("TQ_TILE_TERMS", 2);               // single-term queries on the tile engine: 0 never, 1 always, 2 when the batch has multi-term queries
+  c->phrase_side = env_u32("TQ_PHRASE_SIDE_STREAM", 1);      // k_phrase on the batch's second stream, next to the tile engine
   c->tile_windows = env_u32("TQ_TILE_WINDOWS", 0);           // warps with a window for the heavy pairs (0 = kTileExactWindows)
   c->tile_big_min = env_u32("TQ_TILE_BIG_MIN", 6);          // expected pairs per tile from which a list gets a tile index
   c->tile_units = env_u32("TQ_TILE_UNITS", 148u * 6u);       // CTAs an exact launch aims for
@@ -269,7 +277,7 @@ int tq_ctx_create(int device, tq_ctx** out) {
   c->pos_cap = env_u32("TQ_MAX_POS_LISTS", 1u << 18);
   if (err == cudaSuccess) err = cudaMalloc(&c->d_pos_descs, (size_t)c->pos_cap * sizeof(PosDesc));
   if (err == cudaSuccess) err = cudaMemset(c->d_pos_descs, 0, (size_t)c->pos_cap * sizeof(PosDesc));
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_phrase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phrase_smem_bytes());
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(k_phrase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)phrase_smem_bytes(kPhraseMaxTerms));
   if (err == cudaSuccess) err = cudaMalloc(&c->d_counters, 16 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(c->d_counters, 0, 16 * sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->build_stream, cudaStreamNonBlocking);
@@ -286,6 +294,9 @@ void tq_batch_destroy_real(tq_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
+  if (b->side) { cudaStreamSynchronize(b->side); cudaStreamDestroy(b->side); }
+  if (b->ev_side0) cudaEventDestroy(b->ev_side0);
+  if (b->ev_side1) cudaEventDestroy(b->ev_side1);
   b->pin.release(); b->dev.release(); b->scratch.release(); b->res_pin.release(); b->tile_dev.release();
   if (b->flags_pin) cudaFreeHost(b->flags_pin);
   if (b->ev_start) cudaEventDestroy(b->ev_start);
@@ -587,7 +598,7 @@ struct CacheKey {
 // Kernel time by kind: CUDA events recorded on the batch's stream around every launch (group of launches) of that kind.
 enum SpanKind { SPAN_TERM = 0, SPAN_AND, SPAN_OR, SPAN_FINAL, SPAN_SCORE, SPAN_TILE, SPAN_THETA, SPAN_PHRASE, SPAN_KINDS };
 
-static int span_begin(tq_batch* b, int kind) {
+static int span_begin(tq_batch* b, int kind, cudaStream_t on = nullptr) {
   if (b->n_spans == b->spans.size()) {
     tq_batch::Span s;
     s.kind = kind;
@@ -596,11 +607,11 @@ static int span_begin(tq_batch* b, int kind) {
   }
   tq_batch::Span& s = b->spans[b->n_spans];
   s.kind = kind;
-  cudaEventRecord(s.a, b->stream);
+  cudaEventRecord(s.a, on ? on : b->stream);
   return (int)b->n_spans++;
 }
-static void span_end(tq_batch* b, int idx) {
-  if (idx >= 0) cudaEventRecord(b->spans[idx].b, b->stream);
+static void span_end(tq_batch* b, int idx, cudaStream_t on = nullptr) {
+  if (idx >= 0) cudaEventRecord(b->spans[idx].b, on ? on : b->stream);
 }
 
 static void collect_times(tq_batch* b) {
@@ -626,7 +637,9 @@ static tq_batch* acquire_batch(tq_ctx* c) {
   }
   auto* b = new tq_batch();
   b->ctx = c;
-  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&b->ev_start) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&b->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&b->ev_side0, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&b->ev_side1, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&b->ev_start) != cudaSuccess ||
       cudaEventCreate(&b->ev_k0) != cudaSuccess || cudaEventCreate(&b->ev_k1) != cudaSuccess || cudaEventCreate(&b->ev_end) != cudaSuccess ||
       cudaMallocHost(&b->flags_pin, 64) != cudaSuccess) {
     tq_batch_destroy_real(b);
@@ -877,12 +890,19 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   std::vector<uint32_t> qseg_total;
   uint32_t n_qsegs_op[4] = {0, 0, 0, 0};
   std::vector<char> qseg_sample;  // strip pairs that get a threshold sample pass (MaxScore can then skip their dense clauses)
-  uint32_t strip_cached_max = 0, or_max_lists = 0;
+  uint32_t strip_cached_max = 0, or_max_lists = 0, phrase_ct = 2;
   std::vector<TileGroupBuild> tgroups;
   std::vector<size_t> q_cands(nq, 0);
   const bool tile_on = c->tile != 0 && !force_legacy;
   const uint64_t tile_pair_budget = (uint64_t)c->tile_scratch_mb * (1u << 20) / 8u;
   uint64_t tile_pairs_total = 0;
+  // Single-term queries ride along on the tile engine when the batch has multi-term queries whose decoded lists they share
+  // (mixed workload: 32.6 K q/s against 28.6 K with them on k_term); a batch of nothing but single-term queries has nothing to
+  // share and streams its lists through k_term (configs[0]: 1.39 M q/s against 0.49 M).  TQ_TILE_TERMS: 0 never, 1 always, 2 this rule.
+  bool terms_on_tile = c->tile_terms == 1;
+  if (c->tile_terms >= 2)
+    for (size_t qi = 0; qi < nq && !terms_on_tile; ++qi)
+      terms_on_tile = queries[qi].n_terms >= 2 && queries[qi].op != TQ_OP_PHRASE;
   {
     std::lock_guard<std::mutex> g(c->mu);
     PendingScope pending_scope{c, pending};  // an early error return leaves no half-built list in the cache
@@ -1006,7 +1026,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       }
       // ---- route: the shared-decode tile engine, or the per-query kernels -------------------------------------------------
       bool on_tile = false;
-      if (tile_on && (((c->tile_ops >> op) & 1u) || op == TQ_OP_BOOL) && n_plans) {
+      if (tile_on && (((c->tile_ops >> op) & 1u) || op == TQ_OP_BOOL) && (op != TQ_OP_TERM || terms_on_tile) && n_plans) {
         if (tgroups.empty()) tgroups.emplace_back();
         // wide unions: every query brings its clause words, work-list entries and (mostly distinct) lists into the CTA's shared
         // memory; smaller groups keep two CTAs per SM (configs[4]: 1.64 s -> 1.05 s per 512 20-term queries on 500M docs)
@@ -1045,6 +1065,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         if (op == TQ_OP_PHRASE) {
           if (qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0});
           for (auto& h : here) { qaux.push_back(PhraseAux{h.second.pad, h.range_len}); h.second.pad = 0; }
+          phrase_ct = std::max<uint32_t>(phrase_ct, (uint32_t)here.size());
         }
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
           // strip kernel: clauses with less than one block per kWin-doc window keep their current block decoded in shared memory
@@ -1254,6 +1275,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
   const size_t n_units_total = units[0].size() + units[1].size() + units[2].size() + units[3].size() + units[4].size() + units[5].size() + units[6].size() + units[7].size();
   b->strip_cached_max = strip_cached_max;
   b->or_max_lists = or_max_lists;
+  b->phrase_ct = std::min<uint32_t>(phrase_ct, kPhraseMaxTerms);
   const size_t o_units = off; off = align(off + n_units_total * sizeof(Unit));
   const size_t o_queries = off; off = align(off + dq.size() * sizeof(DQuery));
   const size_t o_qinit = off; off = align(off + std::max<size_t>(nq, 1) * sizeof(QState));  // per-run initial state (threshold keys)
@@ -1513,6 +1535,7 @@ static int run_phase(tq_batch* b, int phase) {
   if (phase == 0) {
     b->n_spans = 0;
     b->finalized = false;
+    if (b->side_pending) { TQ_CUDA(cudaStreamWaitEvent(b->stream, b->ev_side1, 0)); b->side_pending = false; }  // (a run that was abandoned)
     TQ_CUDA(cudaMemcpyAsync(P.qstate, b->dev.p + b->qinit_off, std::max<size_t>(b->nq, 1) * sizeof(QState), cudaMemcpyDeviceToDevice, b->stream));
     if (tiles) TQ_CUDA(cudaMemsetAsync(b->tile_dev.p + b->tile_zero_off, 0, b->tile_zero_bytes, b->stream));
     TQ_CUDA(cudaEventRecord(b->ev_k0, b->stream));
@@ -1527,9 +1550,21 @@ static int run_phase(tq_batch* b, int phase) {
       span_end(b, sp);
     }
     if (b->n_units[7]) {
-      const int sp = span_begin(b, SPAN_PHRASE);
-      k_phrase<<<b->n_units[7], kPhraseThreads, phrase_smem_bytes(), b->stream>>>(P, b->ctx->d_pos_descs, b->phrase_aux, b->unit_base[7]); ++launches;
-      span_end(b, sp);
+      // phrase queries share nothing with the tile engine's launches (their own candidate regions; k_theta and the key export
+      // skip them) and k_phrase waits on dependent position loads most of the time: it runs on a second stream next to them
+      const bool aside = tiles && b->ctx->phrase_side;
+      cudaStream_t on = aside ? b->side : b->stream;
+      if (aside) {
+        TQ_CUDA(cudaEventRecord(b->ev_side0, b->stream));
+        TQ_CUDA(cudaStreamWaitEvent(b->side, b->ev_side0, 0));
+      }
+      const int sp = span_begin(b, SPAN_PHRASE, on);
+      k_phrase<<<b->n_units[7], kPhraseThreads, phrase_smem_bytes(b->phrase_ct), on>>>(P, b->ctx->d_pos_descs, b->phrase_aux, b->unit_base[7], b->phrase_ct); ++launches;
+      span_end(b, sp, on);
+      if (aside) {
+        TQ_CUDA(cudaEventRecord(b->ev_side1, b->side));
+        b->side_pending = true;
+      }
     }
     if (b->n_units[TQ_OP_OR]) {
       const int sp = span_begin(b, SPAN_OR);
@@ -1595,6 +1630,7 @@ static int run_phase(tq_batch* b, int phase) {
     span_end(b, sp);
   }
   TQ_CUDA(cudaGetLastError());
+  if (b->side_pending) { TQ_CUDA(cudaStreamWaitEvent(b->stream, b->ev_side1, 0)); b->side_pending = false; }
   if (b->nq) {
     const int sp = span_begin(b, SPAN_FINAL);
     k_final<<<b->nq, kThreads, 0, b->stream>>>(P); ++launches;

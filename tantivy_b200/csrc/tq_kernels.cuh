@@ -1697,6 +1697,7 @@ __global__ void __launch_bounds__(kThreads) k_theta(const BatchParams P) {
   __shared__ uint32_t s_prefix, s_need;
   const uint32_t q = blockIdx.x;
   const DQuery Q = P.queries[q];
+  if (Q.op == 3u) return;  // TQ_OP_PHRASE: one launch, possibly still running on the batch's second stream
   const uint32_t C = min(P.qstate[q].cand_count, Q.cand_cap);
   if (C < Q.k) return;  // fewer than k hits so far: no bound
   const Cand* cands = P.cands + Q.cand_base;

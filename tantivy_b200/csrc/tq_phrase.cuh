@@ -229,11 +229,12 @@ __device__ __forceinline__ void tf_prefix(const uint32_t (&tf)[4], uint32_t lane
   pre[0] = incl - s; pre[1] = pre[0] + tf[0]; pre[2] = pre[1] + tf[1]; pre[3] = pre[2] + tf[2];
 }
 
-// dynamic shared memory: per warp [128][kPhraseMaxTerms] PhraseCand + [128 docs | 128 tfs | 128 prefixes] of a decoded secondary block
-__host__ __device__ constexpr size_t phrase_smem_bytes() { return kPhraseWarps * (128u * kPhraseMaxTerms * sizeof(PhraseCand) + 384u * 4u); }
+// dynamic shared memory: per warp [128][ct] PhraseCand (ct = most terms of a phrase in the batch) + [128 docs | 128 tfs | 128 prefixes]
+// of a decoded secondary block (reused for the compacted matches)
+__host__ __device__ constexpr size_t phrase_smem_bytes(uint32_t ct) { return kPhraseWarps * (128u * ct * sizeof(PhraseCand) + 384u * 4u); }
 
-__global__ void __launch_bounds__(kPhraseThreads) k_phrase(const BatchParams P, const PosDesc* __restrict__ pdescs, const PhraseAux* __restrict__ aux_all,
-                                                           uint32_t unit_base) {
+__global__ void __launch_bounds__(kPhraseThreads, 5) k_phrase(const BatchParams P, const PosDesc* __restrict__ pdescs, const PhraseAux* __restrict__ aux_all,
+                                                           uint32_t unit_base, uint32_t ct) {
   extern __shared__ __align__(16) unsigned char s_dyn[];
   __shared__ CtaTopK s_top;
   const Unit U = P.units[unit_base + blockIdx.x];
@@ -241,8 +242,8 @@ __global__ void __launch_bounds__(kPhraseThreads) k_phrase(const BatchParams P, 
   const DQuery Q = P.queries[S.query];
   QState* qs = P.qstate + S.query;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  PhraseCand* cands = reinterpret_cast<PhraseCand*>(s_dyn) + (size_t)warp * 128u * kPhraseMaxTerms;
-  uint32_t* dec = reinterpret_cast<uint32_t*>(s_dyn + kPhraseWarps * 128u * kPhraseMaxTerms * sizeof(PhraseCand)) + warp * 384u;
+  PhraseCand* cands = reinterpret_cast<PhraseCand*>(s_dyn) + (size_t)warp * 128u * ct;
+  uint32_t* dec = reinterpret_cast<uint32_t*>(s_dyn + kPhraseWarps * 128u * ct * sizeof(PhraseCand)) + warp * 384u;
   const PhraseAux* aux = aux_all + S.lists_base;
   const QList ql0 = P.qlists[S.lists_base];
   const ListDesc L0 = P.lists[ql0.list_id];
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kPhraseThreads) k_phrase(const BatchParams P, 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const unsigned long long g = base + pre[i];
-          cands[(lane * 4 + i) * kPhraseMaxTerms] = PhraseCand{(uint32_t)g, (uint32_t)(g >> 32), tf0[i]};
+          cands[(lane * 4 + i) * ct] = PhraseCand{(uint32_t)g, (uint32_t)(g >> 32), tf0[i]};
         }
       }
       for (uint32_t s = 1; s < S.n_lists; ++s) {
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kPhraseThreads) k_phrase(const BatchParams P, 
                 if (dec[lo + step - 1] < doc[i]) lo += step;
               if (dec[lo] == doc[i]) {
                 const unsigned long long g = base + dec[256 + lo];
-                cands[(lane * 4 + i) * kPhraseMaxTerms + s] = PhraseCand{(uint32_t)g, (uint32_t)(g >> 32), dec[128 + lo]};
+                cands[(lane * 4 + i) * ct + s] = PhraseCand{(uint32_t)g, (uint32_t)(g >> 32), dec[128 + lo]};
               } else {
                 alive_m &= ~(1u << i);
               }
@@ -313,19 +314,33 @@ __global__ void __launch_bounds__(kPhraseThreads) k_phrase(const BatchParams P, 
         }
       }
       __syncwarp();
-      // the docs that hold every term: their phrase counts, scalar per doc
-      const unsigned long long theta = *T.theta;
-#pragma unroll 1
+      // the docs that hold every term, compacted (a block of the rarest list keeps few of its 128 docs): their phrase counts, one
+      // doc per lane -- the position deltas are read with dependent loads, so the fewer sequential rounds the better
+      uint32_t n_match = 0;
+#pragma unroll
       for (int i = 0; i < 4; ++i) {
+        const bool m = (alive_m >> i) & 1u;
+        const unsigned bal = __ballot_sync(kFull, m);
+        if (m) {
+          const uint32_t at = n_match + (uint32_t)__popc(bal & lanemask_lt(lane));
+          dec[at] = lane * 4u + (uint32_t)i;
+          dec[128u + at] = doc[i];
+        }
+        n_match += (uint32_t)__popc(bal);
+      }
+      __syncwarp();
+      const unsigned long long theta = *T.theta;
+      for (uint32_t base = 0; base < n_match; base += 32u) {
         bool pass = false;
         unsigned long long key = 0;
-        if ((alive_m >> i) & 1u) {
-          const uint32_t cnt = phrase_count(pdescs, aux, cands + (lane * 4 + i) * kPhraseMaxTerms, S.n_lists);
+        if (base + lane < n_match) {
+          const uint32_t c = dec[base + lane], d = dec[128u + base + lane];
+          const uint32_t cnt = phrase_count(pdescs, aux, cands + c * ct, S.n_lists);
           if (cnt) {
-            const float score = bm25_score(sc, L0.fieldnorm, doc[i], cnt);
-            key = make_key(score, doc[i]);
+            const float score = bm25_score(sc, L0.fieldnorm, d, cnt);
+            key = make_key(score, d);
             pass = key >= theta;
-            if (pass && S.alive) pass = is_alive(S.alive, doc[i]);
+            if (pass && S.alive) pass = is_alive(S.alive, d);
           }
         }
         topk_push(T, pass, key, lane);

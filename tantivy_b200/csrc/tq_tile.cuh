@@ -1028,6 +1028,7 @@ __global__ void __launch_bounds__(kThreads) k_topkeys_export(const BatchParams P
   for (uint32_t i = threadIdx.x; i < k_stride; i += blockDim.x) o[i] = 0u;
   if (threadIdx.x == 0) s_n = 0;
   __syncthreads();
+  if (Q.op == 3u) return;  // TQ_OP_PHRASE: its candidates may still be arriving (second stream); no threshold exchange for phrases
   if (n <= k) {
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = keys[(size_t)i * stride];
     return;

@@ -216,15 +216,14 @@ class CrossGpuMerger:
         return (o[:r].view(self.torch.float32).view(self.nq, self.k), o[r:2 * r].view(self.nq, self.k), o[2 * r:3 * r].view(self.nq, self.k), o[3 * r:])
 
     def fetch_host(self, batch):
-        """After __call__(batch): ONE device-to-host copy of the merged rows on the batch's stream, then waits for that stream.
-        Returns numpy (scores f32 [nq, k], segment ords u32, docs u32, counts u32 [nq]); valid until the next fetch_host."""
+        """After __call__(batch): ONE device-to-host copy of the merged rows, issued on the batch's stream (behind the merge kernel)
+        and waited for.  Returns numpy (scores f32 [nq, k], segment ords u32, docs u32, counts u32 [nq]); valid until the next
+        fetch_host.  (Pageable host memory on purpose: a pinned torch tensor that outlives the CUDA context aborts the interpreter
+        at exit.)"""
         import numpy as np
         ext, _ = self._stream(batch)
-        if self.rows_h is None:
-            self.rows_h = self.torch.empty((self.words,), dtype=self.torch.int32, pin_memory=True)
         with self.torch.cuda.stream(ext):
-            self.rows_h.copy_(self.rows_o, non_blocking=True)
-        ext.synchronize()
+            self.rows_h = self.rows_o.cpu()  # cudaMemcpyAsync on `ext` + synchronisation of `ext`
         a = self.rows_h.numpy()
         r = self.nq * self.k
         return (a[:r].view(np.float32).reshape(self.nq, self.k), a[r:2 * r].view(np.uint32).reshape(self.nq, self.k),

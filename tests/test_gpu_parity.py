@@ -36,7 +36,8 @@ def _ctx_with_env(**env):
 # "legacy" = the per-query kernels (k_or_strip / k_or_pipe / k_or) that the tile engine falls back to
 @pytest.fixture(scope="module", params=["tile", "legacy"])
 def ctx(request):
-    c = _ctx_with_env(TQ_TILE=1 if request.param == "tile" else 0)
+    # (TQ_TILE_TERMS=1: single-term batches stay on the tile engine here; the default rule has a test of its own)
+    c = _ctx_with_env(TQ_TILE=1 if request.param == "tile" else 0, TQ_TILE_TERMS=1)
     c.engine = request.param
     yield c
     c.close()
@@ -565,6 +566,26 @@ def test_tile_paths_agree(synth, hook):
         # without a sample launch the first exact launch hands over every match of its tiles: k = 1000 overflows its candidate
         # region and the batch is repeated on the per-query kernels (still the oracle's rows, asserted above)
         assert st["tile_fallbacks"] == (1 if "TQ_TILE_SAMPLE_DIV" in hook else 0)
+    finally:
+        c.close()
+
+
+def test_single_term_batches_take_k_term_unless_they_can_share(synth):
+    """Default routing (TQ_TILE_TERMS=2): a batch of nothing but single-term queries streams its lists through k_term; as soon
+    as the batch holds a multi-term query the single-term queries ride along on the tile engine.  Same rows either way."""
+    ix, oi, base = synth
+    c = _ctx_with_env(TQ_TILE=1)
+    try:
+        ix.register(c, segment_base=base)
+        terms = [ix.query(TQ_OP_TERM, [t], k, segment_base=base) for t in range(6) for k in (10, 100)]
+        qb = QueryBatch(terms)
+        assert_same(c.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+        st = c.stats()
+        assert st["tile_groups"] == 0 and st["units_tile"] == 0
+        qb = QueryBatch(terms + [ix.query(TQ_OP_OR, [0, 3], 10, segment_base=base)])
+        assert_same(c.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+        st = c.stats()
+        assert st["tile_groups"] == 1 and st["units_tile"] > 0
     finally:
         c.close()
 
