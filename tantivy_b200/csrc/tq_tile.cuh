@@ -81,7 +81,7 @@ struct TQuery {  // one (query, segment): what Collector::collect_segment sees
   uint32_t clause_base;  // into TileParams::clauses: slot ordinals (local to the segment) in canonical summation order
   uint16_t n_clauses;
   uint8_t op;
-  uint8_t flags;  // bit 0: prunable (every weight finite and >= 0)
+  uint8_t flags;  // bit 0: prunable (every weight finite and >= 0); bit 1: phrase (op = AND; `query` is the QSeg ordinal of the phrase)
 };
 struct TUnit { uint32_t tseg, t0, t1, pad; };
 struct SChunk { uint32_t slot, b0, b1; };  // a CTA's share of k_score_lists: blocks [b0, b1) of one slot (global slot ordinal)
@@ -110,6 +110,15 @@ struct TileParams {
   uint32_t light_max;  // (query, tile) pairs with at most this many essential postings are evaluated posting by posting (flat path);
                        // above it (and with more than one essential clause) a warp accumulates the query's window
   uint32_t n_win;      // warps of a CTA that own a window (2: heavy pairs are rare; 8 for groups with wide queries)
+  // phrase queries on the tile engine: conjunctions whose matches are handed to k_phrase_verify as records
+  //   [qseg, doc, (global slot, pair index) per term]  (pair index: into p_docs / p_scores / p_pos)
+  uint32_t has_phrase; // the group holds phrase queries (k_tile keeps every slot's first staged pair index on chip)
+  uint32_t ph_stride;  // words per record = 2 + 2 * (most terms of a phrase in the batch)
+  uint32_t ph_cap;     // records the buffer holds (more: flags[2], the batch is repeated on the per-query kernels)
+  uint32_t pad_ph;
+  uint32_t* p_pos;     // per pair of a slot with TSlot::pad & 1: sum of the term frequencies before it in its 128-doc block
+  uint32_t* ph_recs;
+  uint32_t* ph_count;
 };
 
 
@@ -124,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_score_lists(const BatchParams P
   float* out_scores = TP.p_scores + sl.pair_base;
   uint32_t* tix = nullptr;
   uint32_t n_big = 0, n_tiles = 0;
+  const bool want_pos = TP.p_pos != nullptr && (sl.pad & 1u);
   if (sl.big != kNoSlot) {
     const TSeg G = TP.segs[sl.tseg];
     tix = G.tix + sl.big;
@@ -156,6 +166,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_score_lists(const BatchParams P
     // (fieldnorm bytes, block tables)
     __stcs(reinterpret_cast<uint4*>(out_docs + g0), make_uint4(doc[0], doc[1], doc[2], doc[3]));
     __stcs(reinterpret_cast<float4*>(out_scores + g0), make_float4(s[0], s[1], s[2], s[3]));
+    if (want_pos) {  // where the doc's positions start inside the block's share of the position stream (segment_postings.rs:232-254)
+      uint32_t tfv[4], pre[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) tfv[i] = g0 + i < L.doc_freq ? tf[i] : 0u;
+      const uint32_t sum4 = tfv[0] + tfv[1] + tfv[2] + tfv[3];
+      const uint32_t incl = warp_incl_scan(sum4, lane);
+      pre[0] = incl - sum4; pre[1] = pre[0] + tfv[0]; pre[2] = pre[1] + tfv[1]; pre[3] = pre[2] + tfv[2];
+      __stcs(reinterpret_cast<uint4*>(TP.p_pos + sl.pair_base + g0), make_uint4(pre[0], pre[1], pre[2], pre[3]));
+    }
     if (tix) {  // tile index of a dense list: tix[t] = first pair with doc >= t * kTile
       uint32_t pd = __shfl_up_sync(kFull, doc[3], 1);
       if (lane == 0) pd = prev_last;
@@ -230,7 +249,7 @@ __device__ __forceinline__ void tile_push(const BatchParams& P, uint32_t query, 
 struct TileQ {
   uint16_t qi;           // the query: index into the CTA's copy of the segment's queries (batch ordinal, clause slots)
   uint8_t n_op;          // clauses [0:6) | op << 6
-  uint8_t ne_prune;      // essential prefix (unions) / driving clause (conjunctions) [0:6) | prune << 7
+  uint8_t ne_prune;      // essential prefix (unions) / driving clause (conjunctions) [0:6) | phrase << 6 | prune << 7
   uint32_t th_key;       // the query's threshold when the tile was entered
   float ne;              // bound of the non-essential suffix in this tile (unions); 0 for conjunctions
   uint32_t shared_stripes;  // unions: 32-doc stripes of the tile in which more than one essential clause lists a doc (a posting
@@ -245,7 +264,7 @@ struct TileTQ {
   uint32_t query;
   uint16_t clause_base;  // local to the segment
   uint8_t n_clauses;
-  uint8_t op_flags;      // op [0:2) | prunable << 7
+  uint8_t op_flags;      // op [0:2) | phrase << 6 | prunable << 7
 };
 struct TileSeg { uint16_t q, clause, start, len; };  // postings [start, start + len) of one essential clause of flat pair q
 
@@ -348,9 +367,10 @@ __host__ __device__ constexpr size_t tile_union_bytes(uint32_t max_queries, uint
   return ((size_t)n_win * kTile * 4 + (size_t)max_queries * sizeof(TileQ) + seg_bytes + 15) & ~(size_t)15;
 }
 __host__ __device__ constexpr size_t tile_smem_bytes(uint32_t p_cap, uint32_t max_slots, uint32_t max_big, uint32_t max_queries, uint32_t seg_cap,
-                                                      uint32_t cl_cap, uint32_t n_win) {
+                                                      uint32_t cl_cap, uint32_t n_win, uint32_t has_phrase = 0) {
   return (size_t)p_cap * 4 + tile_union_bytes(max_queries, seg_cap, n_win) + (size_t)max_slots * 20 + (size_t)max_big * 128 +
-         (size_t)max_queries * sizeof(TileTQ) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 + (size_t)cl_cap * 2 + 64;
+         (size_t)max_queries * sizeof(TileTQ) + (size_t)max_big * 64 + (size_t)p_cap * 2 + (size_t)max_queries * 2 + (size_t)cl_cap * 2 + 64 +
+         (has_phrase ? (size_t)max_slots * 4 + 8 : 0);
 }
 
 __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, const TileParams TP, uint32_t unit_base, uint32_t sample_mode) {
@@ -373,6 +393,8 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   uint16_t* s_off = s_rank + TP.max_big * 32u;                                 // [p_cap]
   uint16_t* s_heavy = s_off + TP.p_cap;                                        // [max_queries]
   uint16_t* s_cl = s_heavy + TP.max_queries;                                   // [cl_cap] this segment's clause slots
+  // [max_slots] phrase groups only: index (into the pair arrays) of the slot's first pair staged for the current tile
+  uint32_t* s_ord0 = TP.has_phrase ? reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(s_cl + TP.cl_cap) + 3u) & ~(uintptr_t)3u) : nullptr;
   __shared__ uint32_t s_total, s_nheavy, s_hpos, s_nflat, s_nseg, s_segpos, s_segvalid, s_ndefer;
   __shared__ uint32_t s_defer[kTileMaxQueries / 32u];  // queries that did not fit this round's work list
   __shared__ unsigned long long s_stat[8];
@@ -396,7 +418,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
   const uint16_t* __restrict__ cl0 = cl_staged ? s_cl : TP.clauses + G.clause_base;
   for (uint32_t i = tid; i < G.n_queries; i += kTileThreads) {
     const TQuery tq = TP.queries[G.query_base + i];
-    s_tq[i] = TileTQ{tq.query, (uint16_t)(tq.clause_base - G.clause_base), (uint8_t)tq.n_clauses, (uint8_t)((tq.op & 3u) | ((tq.flags & 1u) << 7))};
+    s_tq[i] = TileTQ{tq.query, (uint16_t)(tq.clause_base - G.clause_base), (uint8_t)tq.n_clauses, (uint8_t)((tq.op & 3u) | ((tq.flags & 2u) << 5) | ((tq.flags & 1u) << 7))};
   }
   if (cl_staged)
     for (uint32_t i = tid; i < G.n_clause_words; i += kTileThreads) s_cl[i] = TP.clauses[G.clause_base + i];
@@ -510,7 +532,10 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
         if (fits)
           for (uint32_t i = lane; i < n; i += 32) mx = fmaxf(mx, s_score[b + i]);
         mx = __uint_as_float(__reduce_max_sync(kFull, __float_as_uint(mx)));  // mx >= 0
-        if (lane == 0) { s_info[s] = (b & 0xFFFFu) | (n << 16); s_max[s] = mx; }
+        if (lane == 0) {
+          s_info[s] = (b & 0xFFFFu) | (n << 16); s_max[s] = mx;
+          if (s_ord0) s_ord0[s] = s_wa[warp][e];
+        }
       }
     }
     for (uint32_t s = G.n_big + tid; s < G.n_slots; s += kTileThreads) {  // sparse lists: one thread walks its cursor
@@ -582,6 +607,7 @@ __global__ void __launch_bounds__(kTileThreads, 3) k_tile(const BatchParams P, c
       s_info[s] = (base & 0xFFFFu) | (n << 16);
       s_max[s] = mx;
       s_mask[s] = mask;
+      if (s_ord0) s_ord0[s] = sl.pair_base + cur;
     }
     __syncthreads();
     if (s_total > TP.p_cap) {  // more pairs than the tile buffer holds: give the batch back to the per-query kernels
