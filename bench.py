@@ -98,12 +98,15 @@ OPS = {"term": 0, "and": 1, "or": 2, "phrase": 3}
 def make_shard(wl, dens, rank, world, seed, dist=None, device=None):
     """This rank's segments of the synthetic index (segment s always has seed base+s) + global statistics."""
     import tantivy_b200 as T
-    from tantivy_b200.sharding import ShardedIndex, assign_segments
-    ords = assign_segments(wl["n_segments"], world, rank)
+    from tantivy_b200.sharding import ShardedIndex, assign_parts
+    units = assign_parts(wl["n_segments"], world, rank)  # whole segments round-robin; fewer segments than ranks: doc-range parts
+    ords = [u[0] for u in units]
     t0 = time.time()
-    ix = T.SynthIndex(len(ords), wl["docs_per_segment"], dens, seed=seed, segment_base=rank, segment_stride=world,
+    # (segment s of the index always has seed base + s: local segment i is global segment ords[0] + i * stride)
+    stride = world if wl["n_segments"] >= world else wl["n_segments"]
+    ix = T.SynthIndex(len(ords), wl["docs_per_segment"], dens, seed=seed, segment_base=ords[0], segment_stride=stride,
                       record_option=wl.get("record_option", 1)) if ords else None
-    shard = ShardedIndex(ix, ords, len(dens), dist, device)
+    shard = ShardedIndex(ix, ords, len(dens), dist, device, parts=[(u[1], u[2]) for u in units])
     shard.gen_s = time.time() - t0
     return shard
 
@@ -255,7 +258,8 @@ def main():
     # identical in both arms (the driver compares them); everything measured goes to `workload_stats`
     config = {"workload": args.workload, "desc": wl["desc"], "queries_per_step": args.nq, "docs": wl["n_segments"] * wl["docs_per_segment"],
               "segments": wl["n_segments"], "k": wl["k"], "vocab_terms_materialised": len(dens),
-              "sharding": f"segments round-robin over {args.gpus} rank(s)",
+              "sharding": f"segments round-robin over {args.gpus} rank(s)" if wl["n_segments"] >= args.gpus else
+                          f"{wl['n_segments']} segment(s) split by doc-id range into {args.gpus // wl['n_segments']} parts each, one per rank",
               "l2_policy": "inputs larger than L2: every step streams the index's posting bytes plus its (doc, score) pair scratch (see workload_stats)"}
 
     # ------------------------------------------------------------------ reference arm (CPU)

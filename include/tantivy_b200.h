@@ -194,6 +194,13 @@ int tq_segment_register(tq_ctx*, uint32_t segment_ord, uint32_t field, uint32_t 
  * what SegmentReader::inverted_index hands to PositionReader (src/positions/reader.rs:43-55).  Needed by TQ_OP_PHRASE. */
 int tq_segment_register_positions(tq_ctx*, uint32_t segment_ord, uint32_t field, const uint8_t* pos_body, size_t pos_len);
 int tq_segment_unregister(tq_ctx*, uint32_t segment_ord, uint32_t field);
+/* Restricts what THIS context evaluates of a registered (segment, field) to the docs [doc_lo, doc_hi): the intra-segment split of
+ * SURVEY.md §8(e) -- one huge segment registered on several contexts / GPUs, each with its own doc range (the posting lists are
+ * block-addressable through the skip list, src/postings/skip.rs:205-302, so a doc range is a unit of work like a segment is in
+ * Executor::map, src/core/executor.rs:60-100).  Statistics stay the segment's (the caller counts the segment once); the rows of
+ * the ranges merge like the rows of segments (merge_fruits).  Call it before the first search on the segment; a range can only be
+ * narrowed.  Docs outside the range behave like deleted docs (Count included); the tile engine skips their tiles altogether. */
+int tq_segment_set_doc_range(tq_ctx*, uint32_t segment_ord, uint32_t field, uint32_t doc_lo, uint32_t doc_hi);
 
 /* ---- search -------------------------------------------------------------------------- */
 /* The whole hot path for a batch of queries, host buffers in / host buffers out:
@@ -282,6 +289,12 @@ int tq_multi_segment_register(tq_multi*, int device_index, uint32_t segment_ord,
                               int record_option, const uint8_t* idx_body, size_t idx_len,
                               const uint8_t* fieldnorm, size_t fieldnorm_len,
                               const uint8_t* alive_bitset, size_t alive_len);
+/* One (huge) segment over ALL devices of the handle: every device holds the segment's bytes and evaluates its own doc range
+ * (tq_segment_set_doc_range; ranges are whole 1024-doc tiles, ceil(max_doc / n_devices) docs each). */
+int tq_multi_segment_register_split(tq_multi*, uint32_t segment_ord, uint32_t field, uint32_t max_doc,
+                                    int record_option, const uint8_t* idx_body, size_t idx_len,
+                                    const uint8_t* fieldnorm, size_t fieldnorm_len,
+                                    const uint8_t* alive_bitset, size_t alive_len);
 int tq_multi_search_batch(tq_multi*, const tq_query* queries, size_t nq, uint32_t out_stride,
                           float* out_scores, uint32_t* out_segment_ord, uint32_t* out_doc,
                           uint32_t* out_count);

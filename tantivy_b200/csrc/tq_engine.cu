@@ -107,6 +107,7 @@ struct Segment {
   size_t idx_len = 0;
   uint8_t* d_fieldnorm = nullptr;
   uint8_t* d_alive = nullptr;
+  uint32_t doc_lo = 0, doc_hi = 0;  // the docs this context evaluates (tq_segment_set_doc_range; [0, max_doc) by default)
   Arena arena;  // block tables + aligned block copies of this segment's posting lists; freed with the segment
   uint8_t* d_pos = nullptr;  // the field's `.pos` sub-file (phrase queries), padded
   size_t pos_len = 0;
@@ -352,6 +353,7 @@ int tq_segment_register(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_
   if (c->segments.count({segment_ord, field})) return fail(TQ_ERR_INVALID_ARGUMENT, "segment/field already registered");
   Segment s;
   s.segment_ord = segment_ord; s.field = field; s.max_doc = max_doc; s.record_option = record_option; s.idx_len = idx_len;
+  s.doc_lo = 0; s.doc_hi = max_doc;
   const size_t pad = 256;  // decode_block reads one word past a block; the aligned block copy of k_build_tables reads 64 + 8 bytes past the last block
   cudaError_t e = cudaMalloc(&s.d_idx, idx_len + pad);
   if (e == cudaSuccess) e = cudaMemset(s.d_idx + idx_len, 0, pad);
@@ -400,6 +402,56 @@ int tq_segment_register_positions(tq_ctx* c, uint32_t segment_ord, uint32_t fiel
   }
   if (e != cudaSuccess) { cudaFree(d_pos); cudaFree(d_pool); return fail(TQ_ERR_CUDA, std::string("positions upload: ") + cudaGetErrorString(e)); }
   s.d_pos = d_pos; s.pos_len = pos_len; s.d_pos_pool = d_pool; s.pos_pool_cap = pool;
+  return TQ_OK;
+}
+
+// A single huge segment split by doc-id range over several contexts / GPUs (every block's first and last doc is known
+// from the skip list, so any doc range of a segment is a unit of work of its own; the reference's own parallel axis stops at whole
+// segments, src/core/executor.rs:60-100).  Correctness rests on the alive bitset (docs outside the range are "deleted" for this
+// context: every kernel already honours it); the speed-up comes from the tile engine, which only visits the tiles of the range.
+int tq_segment_set_doc_range(tq_ctx* c, uint32_t segment_ord, uint32_t field, uint32_t doc_lo, uint32_t doc_hi) {
+  if (!c) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  TQ_CUDA(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> g(c->mu);
+  auto it = c->segments.find({segment_ord, field});
+  if (it == c->segments.end()) return fail(TQ_ERR_NOT_FOUND, "segment/field not registered");
+  Segment& s = it->second;
+  if (doc_lo > doc_hi || doc_hi > s.max_doc) return fail(TQ_ERR_INVALID_ARGUMENT, "doc range must satisfy lo <= hi <= max_doc");
+  if (doc_lo < s.doc_lo || doc_hi > s.doc_hi) return fail(TQ_ERR_INVALID_ARGUMENT, "a doc range can only be narrowed");
+  TQ_CUDA(cudaDeviceSynchronize());  // batches in flight read the bitset
+  const size_t nbytes = ((size_t)s.max_doc + 7) / 8;
+  if (!s.d_alive) {
+    for (auto& kv : c->list_cache)  // prepared batches keep the segment's (null) alive pointer: set the range before the first search
+      if (kv.first.segment_ord == segment_ord && kv.first.field == field) return fail(TQ_ERR_INVALID_ARGUMENT, "set the doc range before the segment is searched");
+    const size_t padded = ((nbytes + 7) & ~(size_t)7) + 8;
+    uint8_t* d = nullptr;
+    TQ_CUDA(cudaMalloc(&d, padded));
+    cudaError_t e = cudaMemset(d, 0, padded);
+    if (e == cudaSuccess && nbytes) e = cudaMemset(d, 0xFF, nbytes);
+    if (e != cudaSuccess) { cudaFree(d); return fail(TQ_ERR_CUDA, cudaGetErrorString(e)); }
+    s.d_alive = d;
+  }
+  auto patch = [&](size_t byte, uint8_t keep) -> cudaError_t {  // alive[byte] &= keep
+    uint8_t v = 0;
+    cudaError_t e = cudaMemcpy(&v, s.d_alive + byte, 1, cudaMemcpyDeviceToHost);
+    v &= keep;
+    if (e == cudaSuccess) e = cudaMemcpy(s.d_alive + byte, &v, 1, cudaMemcpyHostToDevice);
+    return e;
+  };
+  auto clear_bits = [&](uint32_t a, uint32_t b) -> cudaError_t {  // docs [a, b) are not alive here (bit d & 7 of byte d >> 3)
+    if (a >= b) return cudaSuccess;
+    const size_t fb = ((size_t)a + 7) / 8, lb = (size_t)b / 8;  // whole bytes [fb, lb)
+    cudaError_t e = cudaSuccess;
+    if (fb > lb) return patch(a / 8, (uint8_t)~(((1u << (b - a)) - 1u) << (a & 7u)));  // a and b inside one byte
+    if (lb > fb) e = cudaMemset(s.d_alive + fb, 0, lb - fb);
+    if (e == cudaSuccess && (a & 7u)) e = patch(a / 8, (uint8_t)((1u << (a & 7u)) - 1u));
+    if (e == cudaSuccess && (b & 7u)) e = patch(b / 8, (uint8_t)~((1u << (b & 7u)) - 1u));
+    return e;
+  };
+  cudaError_t e = clear_bits(s.doc_lo, doc_lo);
+  if (e == cudaSuccess) e = clear_bits(doc_hi, s.doc_hi);
+  if (e != cudaSuccess) return fail(TQ_ERR_CUDA, std::string("doc range: ") + cudaGetErrorString(e));
+  s.doc_lo = doc_lo; s.doc_hi = doc_hi;
   return TQ_OK;
 }
 
@@ -667,6 +719,7 @@ struct SegPlan {
 struct TileGroupBuild {
   struct SegB {
     uint32_t segment_ord = 0, max_doc = 0;
+    uint32_t t_lo = 0, t_hi = 0;  // tiles that overlap the segment's doc range (tq_segment_set_doc_range)
     const uint8_t* alive = nullptr;
     std::vector<TSlot> slots;  // (TSlot::pad chains the slots of one list: several weights / tables of a list are rare)
     std::vector<TQuery> queries;
@@ -792,6 +845,8 @@ uint64_t tile_admit(TileGroupBuild& g, uint32_t query, int op, const SegPlan* pl
       g.segs.back().segment_ord = sp.segment_ord;
       g.segs.back().max_doc = sp.seg->max_doc;
       g.segs.back().alive = sp.seg->d_alive;
+      g.segs.back().t_lo = sp.seg->doc_lo / kTile;
+      g.segs.back().t_hi = (uint32_t)(((uint64_t)sp.seg->doc_hi + kTile - 1) / kTile);
     }
     TileGroupBuild::SegB& sb = g.segs[it->second];
     TQuery tq;
@@ -1222,7 +1277,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       gs.max_big = std::max(gs.max_big, G.n_big);
       gs.max_queries = std::max(gs.max_queries, G.n_queries);
       dens_max = std::max(dens_max, sb.dens);
-      tiles_total += G.n_tiles;
+      tiles_total += sb.t_hi - sb.t_lo;
       gs.segs.push_back(G);
     }
     tix_total_words += gs.tix_words;
@@ -1235,7 +1290,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     // enough sampled tiles for k_max samples to exist: each (query, tile) contributes at most kSamplePerTile
     const uint64_t want_sample_tiles = std::min<uint64_t>(tiles_total / 2, std::max<uint64_t>(tiles_total / sample_div, (uint64_t)kmax_g / 2u + 8u));
     for (uint32_t si = 0; si < gs.segs.size(); ++si) {
-      const uint32_t nt = gs.segs[si].n_tiles;
+      const uint32_t tl = tg.segs[si].t_lo, nt = tg.segs[si].t_hi - tl;  // (the whole segment unless a doc range was set)
       if (nt == 0) continue;
       if (c->tile_sample_div > 1 && nt >= 8 && tiles_total) {
         // short runs of tiles spread over the segment, one CTA each (a sample launch has few tiles: it needs them all in flight)
@@ -1245,7 +1300,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         for (uint32_t r = 0; r < runs; ++r) {
           const uint32_t start = (uint32_t)(((uint64_t)(2 * r + 1) * nt) / (2 * runs));
           const uint32_t t0 = std::min(start, nt - 1), t1 = std::min(nt, t0 + len);
-          gs.units[0].push_back(TUnit{si, t0, t1, 0});
+          gs.units[0].push_back(TUnit{si, tl + t0, tl + t1, 0});
         }
       }
       const uint32_t cut1 = nt >= 16 ? nt / std::max(2u, c->tile_round_div1) : 0, cut2 = nt >= 16 ? std::max(cut1, nt / std::max(2u, c->tile_round_div2)) : 0;
@@ -1256,7 +1311,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         // this launch's share of the target, by its share of all tiles; at least 8 tiles per unit (cursor start-up)
         const uint64_t round_tiles_all = std::max<uint64_t>(1, (uint64_t)tiles_total * span / nt);
         const uint32_t per = (uint32_t)std::max<uint64_t>(tiles_total >= 16ull * target ? 8 : 2, (round_tiles_all + target - 1) / target);
-        for (uint32_t t0 = cuts[r]; t0 < cuts[r + 1]; t0 += per) gs.units[1 + r].push_back(TUnit{si, t0, std::min(cuts[r + 1], t0 + per), 0});
+        for (uint32_t t0 = cuts[r]; t0 < cuts[r + 1]; t0 += per) gs.units[1 + r].push_back(TUnit{si, tl + t0, tl + std::min(cuts[r + 1], t0 + per), 0});
       }
     }
     for (int r = 0; r < kTileRounds; ++r) tile_units += gs.units[r].size();
@@ -2136,7 +2191,7 @@ void tq_field_writer_destroy(tq_field_writer* fw) {
 
 struct tq_multi {
   std::vector<tq_ctx*> ctxs;
-  std::map<std::pair<uint32_t, uint32_t>, int> owner;  // (segment_ord, field) -> index into ctxs
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<int>> owner;  // (segment_ord, field) -> indices into ctxs (several: the segment is split by doc range)
   std::vector<uint64_t> load;                           // bytes registered per device
   std::mutex mu;
   std::string err;
@@ -2197,8 +2252,36 @@ int tq_multi_segment_register(tq_multi* m, int device_index, uint32_t segment_or
   const int rc = tq_segment_register(m->ctxs[device_index], segment_ord, field, max_doc, record_option, idx_body, idx_len, fieldnorm, fieldnorm_len,
                                      alive_bitset, alive_len);
   if (rc != TQ_OK) { m->err = g_err; return rc; }
-  m->owner[{segment_ord, field}] = device_index;
+  m->owner[{segment_ord, field}] = std::vector<int>{device_index};
   m->load[device_index] += idx_len + fieldnorm_len;
+  return TQ_OK;
+}
+
+// One segment over ALL devices of the handle, device i evaluating the docs [i, i + 1) * ceil(max_doc / n / 1024) * 1024 (whole
+// tiles of the tile engine): the intra-segment split of SURVEY.md §8(e) for an index of one (or few) huge segments.
+int tq_multi_segment_register_split(tq_multi* m, uint32_t segment_ord, uint32_t field, uint32_t max_doc, int record_option,
+                                    const uint8_t* idx_body, size_t idx_len, const uint8_t* fieldnorm, size_t fieldnorm_len,
+                                    const uint8_t* alive_bitset, size_t alive_len) {
+  if (!m) return fail(TQ_ERR_INVALID_ARGUMENT, "null");
+  std::lock_guard<std::mutex> g(m->mu);
+  const uint32_t nd = (uint32_t)m->ctxs.size();
+  const uint32_t per = (uint32_t)((((uint64_t)max_doc + nd - 1) / nd + kTile - 1) / kTile * kTile);
+  std::vector<int> owners;
+  for (uint32_t d = 0; d < nd; ++d) {
+    const uint32_t lo = (uint32_t)std::min<uint64_t>((uint64_t)d * per, max_doc), hi = (uint32_t)std::min<uint64_t>((uint64_t)(d + 1) * per, max_doc);
+    int rc = tq_segment_register(m->ctxs[d], segment_ord, field, max_doc, record_option, idx_body, idx_len, fieldnorm, fieldnorm_len, alive_bitset, alive_len);
+    if (rc == TQ_OK) rc = tq_segment_set_doc_range(m->ctxs[d], segment_ord, field, lo, hi);
+    if (rc != TQ_OK) {
+      m->err = g_err;
+      tq_segment_unregister(m->ctxs[d], segment_ord, field);
+      for (int o : owners) tq_segment_unregister(m->ctxs[o], segment_ord, field);
+      g_err = m->err;
+      return rc;
+    }
+    owners.push_back((int)d);
+    m->load[d] += idx_len + fieldnorm_len;
+  }
+  m->owner[{segment_ord, field}] = owners;
   return TQ_OK;
 }
 
@@ -2220,7 +2303,7 @@ int tq_multi_search_batch(tq_multi* m, const tq_query* queries, size_t nq, uint3
         const tq_term_seg& ts = queries[q].term_segs[i];
         auto it = m->owner.find({ts.segment_ord, ts.field});
         if (it == m->owner.end()) { m->err = "term_seg names a segment/field that is not registered"; return TQ_ERR_NOT_FOUND; }
-        dts[it->second].push_back(ts);
+        for (int d : it->second) dts[d].push_back(ts);
       }
     }
     for (int d = 0; d < nd; ++d) {

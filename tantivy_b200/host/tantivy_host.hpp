@@ -1039,6 +1039,44 @@ inline Json parse_json(const std::string& text) {
   return v;
 }
 
+// `.del` (SegmentComponent::Delete, named <uuid>.<delete opstamp>.del, index_meta.rs:134-146): BitSet::serialize = u32 max_value LE ‖
+// ceil(max_value / 64) little-endian u64 words, bit (d & 63) of word d >> 6 set = doc d alive (common/src/bitset.rs:36-47,217-224;
+// ReadOnlyBitSet::open / contains, :362-367,404-409; written by write_alive_bitset, src/fastfield/alive_bitset.rs:12-15, read by
+// SegmentReader::open, src/index/segment_reader.rs:177) ‖ the managed-directory footer.  Returns the words as bytes: exactly what
+// tq_segment_register takes as alive_bitset.
+inline std::vector<uint8_t> read_alive_bitset(const uint8_t* file, size_t len, uint32_t max_doc, uint32_t* num_alive = nullptr) {
+  const Footer f = read_footer(file, len);
+  if (f.body_len < 4) throw TantivyError(TantivyError::DataCorruption, ".del: too short for the max_value header");
+  uint32_t max_value;
+  std::memcpy(&max_value, file, 4);
+  if (max_value != max_doc) throw TantivyError(TantivyError::DataCorruption, ".del: max_value differs from the segment's max_doc");
+  const size_t n_bytes = ((size_t)max_value + 63) / 64 * 8;
+  if (f.body_len - 4 != n_bytes) throw TantivyError(TantivyError::DataCorruption, ".del: bitset length does not match max_value");
+  std::vector<uint8_t> words(file + 4, file + 4 + n_bytes);
+  if (num_alive) {
+    uint32_t n = 0;
+    for (uint32_t d = 0; d < max_value; ++d) n += (words[d >> 3] >> (d & 7u)) & 1u;  // (ReadOnlyBitSet::iter stops at max_value)
+    *num_alive = n;
+  }
+  return words;
+}
+// BitSet::serialize + the footer FooterProxy::terminate_ref appends (footer.rs:44-51): what the reference writes for `alive` (test side)
+inline std::vector<uint8_t> write_alive_bitset(const std::vector<uint8_t>& alive_words, uint32_t max_doc, uint32_t index_format_version = 7) {
+  std::vector<uint8_t> out(4);
+  std::memcpy(out.data(), &max_doc, 4);
+  const size_t n_bytes = ((size_t)max_doc + 63) / 64 * 8;
+  for (size_t i = 0; i < n_bytes; ++i) out.push_back(i < alive_words.size() ? alive_words[i] : 0);
+  const std::string json = "{\"version\":{\"major\":0,\"minor\":26,\"patch\":0,\"index_format_version\":" + std::to_string(index_format_version) +
+                           "},\"crc\":" + std::to_string(crc32(out.data(), out.size())) + "}";
+  const uint32_t json_len = (uint32_t)json.size(), magic = 1337u;
+  out.insert(out.end(), json.begin(), json.end());
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(&json_len);
+  out.insert(out.end(), p, p + 4);
+  p = reinterpret_cast<const uint8_t*>(&magic);
+  out.insert(out.end(), p, p + 4);
+  return out;
+}
+
 struct SegmentMeta {  // index_meta.rs: InnerSegmentMeta { segment_id, max_doc, deletes: Option<DeleteMeta{num_deleted_docs, opstamp}> }
   std::string segment_id;  // with dashes, as written
   uint32_t max_doc = 0;
@@ -1109,15 +1147,23 @@ inline IndexMeta read_meta(const std::string& meta_json) {
 
 // Index::open_in_dir for this path: meta.json + every segment's `.idx` / `.fieldnorm` (read through `read_file(name)`),
 // one SegmentData per segment in meta order.  Term dictionaries (`.term`, N2) are not read: terms are looked up through
-// FieldSegmentData::term_dict, which the caller fills.  Segments with deletes need their `.del` file's bitset, which
-// no fixture of the reference pins yet: refused.
+// FieldSegmentData::term_dict, which the caller fills.  A segment with deletes brings its alive bitset from
+// `<uuid>.<delete opstamp>.del` (SegmentReader::open, src/index/segment_reader.rs:170-181).
 inline Index open_index(const std::string& meta_json, const std::function<std::vector<uint8_t>(const std::string&)>& read_file) {
   const IndexMeta meta = read_meta(meta_json);
   std::vector<std::shared_ptr<const SegmentData>> segments;
   for (const SegmentMeta& sm : meta.segments) {
-    if (sm.has_deletes) throw TantivyError(TantivyError::Unsupported, "segment " + sm.segment_id + " has deletes (.del is not read yet)");
     auto seg = std::make_shared<SegmentData>();
     seg->max_doc = sm.max_doc;
+    if (sm.has_deletes) {
+      const std::vector<uint8_t> del = read_file(sm.file_stem() + "." + std::to_string(sm.delete_opstamp) + ".del");
+      uint32_t n_alive = 0;
+      seg->alive = read_alive_bitset(del.data(), del.size(), sm.max_doc, &n_alive);
+      seg->num_deleted = sm.max_doc - n_alive;
+      if (sm.max_doc - n_alive != sm.num_deleted_docs)
+        throw TantivyError(TantivyError::DataCorruption, "segment " + sm.segment_id + ": .del holds " + std::to_string(sm.max_doc - n_alive) +
+                                                             " deleted docs, meta.json says " + std::to_string(sm.num_deleted_docs));
+    }
     seg->fields.resize(meta.schema.num_fields());
     const std::vector<uint8_t> idx = read_file(sm.file_stem() + ".idx");
     const std::vector<uint8_t> fn = read_file(sm.file_stem() + ".fieldnorm");

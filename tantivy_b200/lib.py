@@ -31,6 +31,7 @@ def _load():
     lib.tq_segment_register.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
     lib.tq_segment_register_positions.argtypes = [vp, C.c_uint32, C.c_uint32, u8p, sz]
     lib.tq_segment_unregister.argtypes = [vp, C.c_uint32, C.c_uint32]
+    lib.tq_segment_set_doc_range.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
     lib.tq_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_batch_prepare.argtypes = [vp, C.POINTER(Query), sz, C.POINTER(vp)]
     lib.tq_count_batch.argtypes = [vp, C.POINTER(Query), sz, u64p]
@@ -55,6 +56,7 @@ def _load():
     lib.tq_multi_last_error.argtypes = [vp]
     lib.tq_multi_num_devices.argtypes = [vp]
     lib.tq_multi_segment_register.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
+    lib.tq_multi_segment_register_split.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, u8p, sz, u8p, sz, u8p, sz]
     lib.tq_multi_search_batch.argtypes = [vp, C.POINTER(Query), sz, C.c_uint32, f32p, u32p, u32p, u32p]
     lib.tq_decode_postings.argtypes = [vp, C.POINTER(TermSeg), u32p, u32p]
     lib.tq_block_table.argtypes = [vp, C.POINTER(TermSeg), C.c_float, C.c_float, u32p, f32p]
@@ -266,6 +268,10 @@ class Context:
     def segment_unregister(self, segment_ord, field):
         _check(LIB.tq_segment_unregister(self.h, segment_ord, field), self.h)
 
+    def segment_set_doc_range(self, segment_ord, field, doc_lo, doc_hi):
+        """This context evaluates only the docs [doc_lo, doc_hi) of the segment (intra-segment split over GPUs)."""
+        _check(LIB.tq_segment_set_doc_range(self.h, segment_ord, field, doc_lo, doc_hi), self.h)
+
     def search_batch(self, batch: QueryBatch, out=None):
         stride, scores, segs, docs, counts = out or batch.alloc_out()
         _check(LIB.tq_search_batch(self.h, batch.ptr, batch.nq, stride, ptr(scores, f32p), ptr(segs, u32p), ptr(docs, u32p),
@@ -334,6 +340,16 @@ class MultiContext:
         al = None if alive is None else np.ascontiguousarray(alive, dtype=np.uint8)
         rc = LIB.tq_multi_segment_register(self.h, device_index, segment_ord, field, max_doc, record_option, ptr(idx_body, u8p), idx_body.size,
                                            ptr(fn, u8p), 0 if fn is None else fn.size, ptr(al, u8p), 0 if al is None else al.size)
+        if rc != 0:
+            raise TqError(f"tantivy_b200 error {rc}: {LIB.tq_multi_last_error(self.h).decode(errors='replace')}")
+
+    def segment_register_split(self, segment_ord, field, max_doc, record_option, idx_body, fieldnorm=None, alive=None):
+        """One segment on every device of the handle, each evaluating its own doc range."""
+        idx_body = np.ascontiguousarray(idx_body, dtype=np.uint8)
+        fn = None if fieldnorm is None else np.ascontiguousarray(fieldnorm, dtype=np.uint8)
+        al = None if alive is None else np.ascontiguousarray(alive, dtype=np.uint8)
+        rc = LIB.tq_multi_segment_register_split(self.h, segment_ord, field, max_doc, record_option, ptr(idx_body, u8p), idx_body.size,
+                                                 ptr(fn, u8p), 0 if fn is None else fn.size, ptr(al, u8p), 0 if al is None else al.size)
         if rc != 0:
             raise TqError(f"tantivy_b200 error {rc}: {LIB.tq_multi_last_error(self.h).decode(errors='replace')}")
 

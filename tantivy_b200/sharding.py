@@ -19,6 +19,33 @@ def assign_segments(n_segments, world, rank):
     return [s for s in range(n_segments) if s % world == rank]
 
 
+def assign_parts(n_segments, world, rank):
+    """Units of work of `rank`: [(global segment ordinal, part, n_parts)].  With at least as many segments as ranks, whole
+    segments round-robin (part 0 of 1).  With fewer, every segment is split by doc-id range into world // n_segments parts
+    (SURVEY.md §8e: posting lists are block-addressable through the skip list, so a doc range is a unit of work of its own);
+    rank r takes part r // n_segments of segment r % n_segments (ranks beyond n_segments * parts stay idle)."""
+    if n_segments >= world:
+        return [(s, 0, 1) for s in assign_segments(n_segments, world, rank)]
+    parts = world // n_segments
+    s, part = rank % n_segments, rank // n_segments
+    return [(s, part, parts)] if part < parts else []
+
+
+def doc_range(max_doc, part, n_parts, tile=1024):
+    """Docs [lo, hi) of part `part` of `n_parts`: whole 1024-doc tiles of the tile engine, ceil(max_doc / n_parts) docs each
+    (the same cut tq_multi_segment_register_split makes)."""
+    per = ((max_doc + n_parts - 1) // n_parts + tile - 1) // tile * tile
+    return min(part * per, max_doc), min((part + 1) * per, max_doc)
+
+
+def range_alive_bitset(max_doc, lo, hi):
+    """The alive bitset (bit d & 7 of byte d >> 3, common/src/bitset.rs:362-407) of "only docs [lo, hi) exist here": what a
+    target without tq_segment_set_doc_range (the CPU oracle in the tests) gets instead."""
+    m = np.zeros(max_doc, dtype=bool)
+    m[lo:hi] = True
+    return np.packbits(m, bitorder="little")
+
+
 def global_statistics(local_doc_freq, local_tokens, local_docs, dist=None, device=None):
     """Sums per-term doc_freq, token count and doc count over all ranks (all_reduce)."""
     stats = np.concatenate([np.asarray(local_doc_freq, dtype=np.int64), [int(local_tokens), int(local_docs)]]).astype(np.int64)
@@ -84,22 +111,33 @@ class ShardedIndex:
     `index` must expose n_segments, max_doc[], total_num_tokens[], term_info[s][t], record_option,
     body(s), fieldnorm(s); `global_ords[i]` is the global ordinal of local segment i."""
 
-    def __init__(self, index, global_ords, n_terms, dist=None, device=None):
+    def __init__(self, index, global_ords, n_terms, dist=None, device=None, parts=None):
+        """parts[i] = (part, n_parts) of local segment i when it is split by doc range over several ranks (default: whole)."""
         self.ix = index
         self.global_ords = list(global_ords)
+        self.parts = list(parts) if parts is not None else [(0, 1)] * len(self.global_ords)
         df = np.zeros(n_terms, dtype=np.int64)
         tokens = docs = 0
         if index is not None:
             for s in range(index.n_segments):
+                if self.parts[s][0] != 0:
+                    continue  # a split segment is counted once, by the rank that holds its first part
                 df += np.array([index.term_info[s][t][0] for t in range(n_terms)], dtype=np.int64)
-            tokens, docs = sum(index.total_num_tokens), sum(index.max_doc)
+                tokens += index.total_num_tokens[s]
+                docs += index.max_doc[s]
         self.df, self.total_tokens, self.total_docs, self.avg = global_statistics(df, tokens, docs, dist, device)
         self.index_bytes = sum(index.body(s).size + index.fieldnorm(s).size + (index.positions(s).size if index.record_option == 2 else 0)
                                for s in range(index.n_segments)) if index is not None else 0
 
     def register(self, target):
         for i, g in enumerate(self.global_ords):
-            target.segment_register(g, 0, self.ix.max_doc[i], self.ix.record_option, self.ix.body(i), self.ix.fieldnorm(i), None)
+            part, n_parts = self.parts[i]
+            lo, hi = doc_range(self.ix.max_doc[i], part, n_parts)
+            ranged = n_parts > 1 and hasattr(target, "segment_set_doc_range")
+            alive = range_alive_bitset(self.ix.max_doc[i], lo, hi) if n_parts > 1 and not ranged else None
+            target.segment_register(g, 0, self.ix.max_doc[i], self.ix.record_option, self.ix.body(i), self.ix.fieldnorm(i), alive)
+            if ranged:
+                target.segment_set_doc_range(g, 0, lo, hi)
             if self.ix.record_option == 2:
                 target.register_positions(g, 0, self.ix.positions(i))
 

@@ -577,6 +577,63 @@ static void test_host_compat_framing(const std::string& dir) {
   CHECK(missing);
 }
 
+// A segment with deletes: meta.json's DeleteMeta + `<uuid>.<opstamp>.del` (BitSet::serialize + footer).  The byte layout is pinned by
+// the reference's own (de)serialisation code (common/src/bitset.rs:217-224,362-367,404-409) and by alive_bitset.rs:107-156, whose
+// cases are replayed here; the compat index is opened with its only doc deleted.
+static void test_host_alive_bitset_file(const std::string& dir) {
+  auto from_deleted = [](std::vector<uint32_t> deleted, uint32_t max_doc) {  // AliveBitSet::for_test_from_deleted_docs
+    std::vector<uint8_t> w(((size_t)max_doc + 63) / 64 * 8, 0);
+    for (uint32_t d = 0; d < max_doc; ++d) w[d >> 3] |= (uint8_t)(1u << (d & 7u));  // BitSet::with_max_value_and_full: padding bits stay 0
+    for (uint32_t d : deleted) w[d >> 3] &= (uint8_t)~(1u << (d & 7u));
+    return files::write_alive_bitset(w, max_doc);
+  };
+  {
+    const auto file = from_deleted({1, 9}, 10);  // test_alive_bitset
+    CHECK(file.size() > 12 && file[0] == 10 && file[1] == 0 && file[4] == 0xFD && file[5] == 0x01 && file[6] == 0);  // 4 + 8 bytes of body
+    uint32_t alive = 0;
+    const auto words = files::read_alive_bitset(file.data(), file.size(), 10, &alive);
+    CHECK(words.size() == 8 && alive == 8);
+    for (uint32_t d = 0; d < 10; ++d) CHECK((((words[d >> 3] >> (d & 7u)) & 1u) == 1u) == (d != 1 && d != 9));
+  }
+  {
+    const auto file = from_deleted({0, 1, 1000}, 1001);  // test_alive_bitset_iter
+    uint32_t alive = 0;
+    const auto words = files::read_alive_bitset(file.data(), file.size(), 1001, &alive);
+    CHECK(words.size() == 16 * 8 && alive == 998);
+    bool wrong_max = false, bad_crc = false;
+    try { files::read_alive_bitset(file.data(), file.size(), 1000); } catch (const TantivyError& e) { wrong_max = e.kind() == TantivyError::DataCorruption; }
+    auto corrupted = file;
+    corrupted[5] ^= 4;
+    try { files::read_alive_bitset(corrupted.data(), corrupted.size(), 1001); } catch (const TantivyError& e) { bad_crc = e.kind() == TantivyError::DataCorruption; }
+    CHECK(wrong_max && bad_crc);
+  }
+  // Index::open_in_dir over the compat files + a DeleteMeta: the segment's only doc is deleted
+  const std::string base = dir + "/index_v7/";
+  const auto meta_bytes = read_file(base + "meta.json");
+  std::string meta_json(meta_bytes.begin(), meta_bytes.end());
+  const files::IndexMeta meta0 = files::read_meta(meta_json);
+  const std::string none = "\"deletes\": null";
+  const size_t at = meta_json.find(none);
+  CHECK(at != std::string::npos);
+  if (at == std::string::npos) return;
+  meta_json.replace(at, none.size(), "\"deletes\": {\"num_deleted_docs\": 1, \"opstamp\": 5}");
+  const std::string del_name = meta0.segments[0].file_stem() + ".5.del";
+  int asked = 0;
+  auto read = [&](const std::string& name) {
+    if (name == del_name) { ++asked; return from_deleted({0}, 1); }
+    return read_file(base + name);
+  };
+  Index index = files::open_index(meta_json, read);
+  CHECK(asked == 1);
+  const SegmentData& seg = *index.segments()[0];
+  CHECK(seg.alive.size() == 8 && !seg.is_alive(0));
+  CHECK(index.reader().searcher().num_docs() == 0);
+  bool mismatch = false;  // meta.json and the bitset must agree on the number of deleted docs
+  try { files::open_index(meta_json, [&](const std::string& name) { return name == del_name ? from_deleted({}, 1) : read_file(base + name); }); }
+  catch (const TantivyError& e) { mismatch = e.kind() == TantivyError::DataCorruption; }
+  CHECK(mismatch);
+}
+
 static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
   for (const std::string version : {"index_v6", "index_v7"}) {
     Index index = index_from_compat_files(dir, version);
@@ -663,6 +720,7 @@ int main(int argc, char** argv) {
              {"host_term_info_store", test_host_term_info_store},
              {"host_search_without_device_raises", test_host_search_without_device_raises}};
     if (!dir.empty()) tests.push_back({"host_compat_framing", [dir]() { test_host_compat_framing(dir); }});
+    if (!dir.empty()) tests.push_back({"host_alive_bitset_file", [dir]() { test_host_alive_bitset_file(dir); }});
   } else {
     tests = {{"term_query_no_freq", test_term_query_no_freq},
              {"term_query_multiple_of_block_len", test_term_query_multiple_of_block_len},

@@ -755,6 +755,98 @@ def test_multi_handle_two_devices(synth):
     _multi_check([0, 1], ix, oi, base)
 
 
+# ---- one segment split by doc-id range ---------------------------------------------------------------
+def _range_ctx(engine):
+    return _ctx_with_env(TQ_TILE=1 if engine == "tile" else 0, TQ_TILE_TERMS=1)
+
+
+@pytest.mark.parametrize("cuts", [[0, 101_376, 202_752, 300_000], [0, 1, 77_777, 77_780, 262_144, 299_999, 300_000], [0, 0, 300_000]])
+def test_doc_range_parts_merge_to_the_whole_segment(ctx, cuts):
+    """tq_segment_set_doc_range: every part of a segment (one context each, as on several GPUs) returns the top-k / the Count of its
+    docs; merged like segment fruits (merge_fruits) they are the rows of the whole segment.  Cuts inside tiles, inside bytes of the
+    alive bitset, one-doc and empty parts; with and without deletes."""
+    from tantivy_b200.sharding import merge_rows_host
+    ix = T.SynthIndex(1, 300_000, [0.3, 0.05, 0.01, 0.002, 0.0004], seed=31)
+    for deletes in (False, True):
+        alive = None
+        if deletes:
+            alive = np.packbits(np.random.default_rng(5).random(300_000) > 0.3, bitorder="little")
+        base = fresh_ord()
+        oi = O.OracleIndex()
+        oi.segment_register(base, 0, ix.max_doc[0], ix.record_option, ix.body(0), ix.fieldnorm(0), alive)
+        qs = [ix.query(TQ_OP_TERM, [t], 10, segment_base=base) for t in range(5)]
+        qs += [ix.query(TQ_OP_AND, ts, 10, segment_base=base) for ts in ([0, 1], [1, 2], [0, 3])]
+        qs += [ix.query(TQ_OP_OR, ts, 50, segment_base=base) for ts in ([0, 1, 2, 3, 4], [3, 4], [1, 4], [2, 3])]
+        qb = QueryBatch(qs)
+        want = oi.search_batch(qb, mode=0, n_threads=8)
+        want_counts = oi.count_batch(qb)
+        rows, counts = [], np.zeros(qb.nq, dtype=np.uint64)
+        for lo, hi in zip(cuts[:-1], cuts[1:]):
+            c = _range_ctx(ctx.engine)
+            try:
+                c.segment_register(base, 0, ix.max_doc[0], ix.record_option, ix.body(0), ix.fieldnorm(0), alive)
+                c.segment_set_doc_range(base, 0, lo, hi)
+                r = c.search_batch(qb)
+                for q in range(qb.nq):
+                    assert all(lo <= d < hi for _, _, d in hits(r, q))
+                rows.append([np.array(x) for x in r])
+                counts += c.count_batch(qb)
+                if ctx.engine == "tile":
+                    assert c.stats()["tile_fallbacks"] == 0
+            finally:
+                c.close()
+        assert (counts == want_counts).all(), (counts, want_counts)
+        kmax = max(q["k"] for q in qs)
+        m = merge_rows_host(np.stack([r[0] for r in rows]), np.stack([r[1] for r in rows]), np.stack([r[2] for r in rows]), np.stack([r[3] for r in rows]), kmax)
+        for q in range(qb.nq):
+            n = int(want[3][q])
+            assert int(m[3][q]) >= n
+            assert (m[1][q, :n] == want[1][q, :n]).all() and (m[2][q, :n] == want[2][q, :n]).all()
+            assert (m[0][q, :n].view(np.uint32) == want[0][q, :n].view(np.uint32)).all()
+
+
+def test_doc_range_argument_checks(ctx):
+    ix = T.SynthIndex(1, 5000, [0.2], seed=3)
+    base = fresh_ord()
+    ctx.segment_register(base, 0, ix.max_doc[0], ix.record_option, ix.body(0), ix.fieldnorm(0), None)
+    with pytest.raises(T.TqError):
+        ctx.segment_set_doc_range(base + 1, 0, 0, 10)      # not registered
+    with pytest.raises(T.TqError):
+        ctx.segment_set_doc_range(base, 0, 10, 5001)       # beyond max_doc
+    with pytest.raises(T.TqError):
+        ctx.segment_set_doc_range(base, 0, 20, 10)         # lo > hi
+    ctx.segment_set_doc_range(base, 0, 1000, 4000)
+    with pytest.raises(T.TqError):
+        ctx.segment_set_doc_range(base, 0, 0, 4000)        # a range can only be narrowed
+    ctx.segment_set_doc_range(base, 0, 1024, 3000)
+    r = ctx.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [0], 5000, segment_base=base)]))
+    docs = [d for _, _, d in hits(r, 0)]
+    assert docs and min(docs) >= 1024 and max(docs) < 3000
+    base2 = fresh_ord()
+    ctx.segment_register(base2, 0, ix.max_doc[0], ix.record_option, ix.body(0), ix.fieldnorm(0), None)
+    ctx.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [0], 5, segment_base=base2)]))
+    with pytest.raises(T.TqError):
+        ctx.segment_set_doc_range(base2, 0, 0, 100)        # after the first search on a segment without deletes
+    ctx.segment_unregister(base, 0)
+    ctx.segment_unregister(base2, 0)
+
+
+def test_multi_handle_split_segment(synth):
+    """tq_multi_segment_register_split: ONE segment over the handle's devices by doc range (here two contexts on one device, and
+    next to a whole segment on one of them) -- the rows of a single context holding everything."""
+    ix, oi, base = synth
+    m = T.MultiContext([0, 0])
+    try:
+        m.segment_register_split(base + 0, 0, ix.max_doc[0], ix.record_option, ix.body(0), ix.fieldnorm(0), None)
+        m.segment_register(base + 1, 0, ix.max_doc[1], ix.record_option, ix.body(1), ix.fieldnorm(1), None)
+        m.segment_register_split(base + 2, 0, ix.max_doc[2], ix.record_option, ix.body(2), ix.fieldnorm(2), None)
+        qs = _tile_queries(ix, base)[:24] + [ix.query(TQ_OP_AND, [0, 1], 10, segment_base=base), ix.query(TQ_OP_TERM, [2], 50, segment_base=base)]
+        qb = QueryBatch(qs)
+        assert_same(m.search_batch(qb), oi.search_batch(qb, mode=0, n_threads=8), qb.nq)
+    finally:
+        m.close()
+
+
 # ---- N4: mixed boolean shapes (TQ_OP_BOOL) --------------------------------------------------------------------------
 def _bool_query(ix_query, occurs, groups=None, msm=0):
     q = dict(ix_query)

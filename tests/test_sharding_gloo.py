@@ -14,7 +14,7 @@ import torch.multiprocessing as mp  # noqa: E402
 
 import tantivy_b200 as T  # noqa: E402
 from tantivy_b200._abi import TQ_OP_AND, TQ_OP_OR, TQ_OP_TERM  # noqa: E402
-from tantivy_b200.sharding import (ShardedIndex, assign_segments, exchange_thresholds, key_scores, kth_of_gathered_keys,  # noqa: E402
+from tantivy_b200.sharding import (ShardedIndex, assign_parts, assign_segments, doc_range, range_alive_bitset, exchange_thresholds, key_scores, kth_of_gathered_keys,  # noqa: E402
                                    local_topkeys, merge_rows_host, score_keys)
 
 DENS = [0.2, 0.05, 0.01, 0.001]
@@ -84,6 +84,78 @@ def test_two_rank_sharded_search_matches_single_process():
         assert n <= k and int(m_ct[q]) >= n  # the merge ran with k = KMAX for every query
         assert (m_sg[q, :n] == sg[q, :n]).all() and (m_dc[q, :n] == dc[q, :n]).all()
         assert (m_sc[q, :n].astype(np.float32) == sc[q, :n]).all()
+
+
+def _split_worker(rank, world, port, out, n_seg, docs):
+    """SURVEY.md §8(e), second half: fewer segments than ranks -> every segment is split by doc-id range (assign_parts); a part
+    behaves like a segment of its own (here on the oracle: the range as an alive bitset), statistics count the segment once."""
+    from oracle import tq_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        units = assign_parts(n_seg, world, rank)
+        ords = [u[0] for u in units]
+        ix = T.SynthIndex(len(ords), docs, DENS, seed=99, segment_base=ords[0], segment_stride=n_seg, n_threads=2)
+        shard = ShardedIndex(ix, ords, len(DENS), dist, parts=[(u[1], u[2]) for u in units])
+        oi = O.OracleIndex()
+        shard.register(oi)
+        sc, sg, dc, ct = oi.search_batch(shard.marshal(QUERIES), mode=0)
+        gathered = []
+        for arr, dt in ((sc, torch.float32), (sg.astype(np.int64), torch.int64), (dc.astype(np.int64), torch.int64), (ct.astype(np.int64), torch.int64)):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dt)
+            lst = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(lst, t)
+            gathered.append(torch.stack(lst).numpy())
+        merged = merge_rows_host(gathered[0], gathered[1].astype(np.uint32), gathered[2].astype(np.uint32), gathered[3].astype(np.uint32), KMAX)
+        if rank == 0:
+            out.put(dict(df=shard.df.tolist(), docs=shard.total_docs, tokens=shard.total_tokens, avg=float(shard.avg),
+                         merged=[m.tolist() for m in merged]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_one_segment_split_by_doc_range_over_two_ranks():
+    from oracle import tq_oracle as O
+    docs = 150_001  # not a multiple of the tile: the last part is the short one
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, out, 1, docs)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ix = T.SynthIndex(1, docs, DENS, seed=99, n_threads=2)
+    shard = ShardedIndex(ix, [0], len(DENS))
+    assert res["df"] == shard.df.tolist() and res["docs"] == shard.total_docs and res["tokens"] == shard.total_tokens
+    assert res["avg"] == float(shard.avg)
+    oi = O.OracleIndex()
+    shard.register(oi)
+    sc, sg, dc, ct = oi.search_batch(shard.marshal(QUERIES), mode=0)
+    m_sc, m_sg, m_dc, m_ct = [np.array(x) for x in res["merged"]]
+    for q, (_, _, k) in enumerate(QUERIES):
+        n = int(ct[q])
+        assert n == k and int(m_ct[q]) >= n
+        assert (m_sg[q, :n] == sg[q, :n]).all() and (m_dc[q, :n] == dc[q, :n]).all()
+        assert (m_sc[q, :n].astype(np.float32) == sc[q, :n]).all()
+
+
+def test_assign_parts_and_doc_ranges_partition():
+    for n_seg, world in ((8, 1), (8, 2), (8, 8), (3, 2), (1, 2), (1, 8), (2, 8), (3, 8)):
+        units = [u for r in range(world) for u in assign_parts(n_seg, world, r)]
+        for s in range(n_seg):
+            mine = sorted((u[1], u[2]) for u in units if u[0] == s)
+            assert mine and mine == [(p, mine[0][1]) for p in range(mine[0][1])]  # every part of every segment exactly once
+    for max_doc in (0, 1, 1023, 1024, 1025, 150_001, 10_000_000):
+        for n_parts in (1, 2, 3, 8):
+            cuts = [doc_range(max_doc, p, n_parts) for p in range(n_parts)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == max_doc
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(n_parts - 1))
+            assert all(lo % 1024 == 0 for lo, _ in cuts if lo < max_doc)
+    bits = range_alive_bitset(21, 3, 18)
+    assert bits.tolist() == [0b11111000, 0b11111111, 0b00000011]
 
 
 def test_assign_segments_partitions():
