@@ -242,6 +242,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-queries", type=int, default=32, help="queries of the first timed batch re-checked on the oracle (0 = off)")
+    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2],
+                    help="batches in flight per GPU in the timed legs (2: step i+1 is queued on its own stream before the host waits for step i)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -305,14 +307,19 @@ def main():
     nq = args.nq
     n_total = args.warmup + args.steps
 
-    cross_gpu_merge = None
+    depth = args.in_flight
+    mergers = []
     if world > 1:
         from tantivy_b200.sharding import CrossGpuMerger
-        cross_gpu_merge = CrossGpuMerger(ctx, dist, dev, nq, k)  # NCCL all-gather + device merge (K7)
+        # NCCL all-gathers + device merge (K7); one set of exchange buffers per batch in flight, ONE process group: every rank
+        # issues the collectives of the batches in the same program order
+        mergers = [CrossGpuMerger(ctx, dist, dev, nq, k) for _ in range(depth)]
+    cross_gpu_merge = mergers[0] if mergers else None
 
     # ---- leg 1: `value` — descriptors resident, kernels only -----------------------------------------
     prepared = [ctx.prepare(qb) for qb in qbs]  # also warms the block-table cache; cycled through the steps
     n_prep = len(prepared)
+    assert n_prep >= depth or depth == 1
 
     def run_step(bt):
         if world > 1:
@@ -324,15 +331,29 @@ def main():
         bt.results_dev()  # waits for the step
         return None
 
+    def submit(bt, slot):
+        """Queues one whole step on the batch's own stream and returns without waiting."""
+        if world > 1:
+            mergers[slot].run(bt)            # phases + key exchanges
+            mergers[slot].finish_async(bt)   # pack + all-gather + merge (+ every rank's overflow flags)
+        else:
+            bt.run()
+
+    def complete(bt, slot, out=None, rows_to_host=False):
+        """Waits for a submitted step; rows to host buffers when asked (e2e leg)."""
+        if world > 1:
+            return mergers[slot].complete(bt, rows_to_host=rows_to_host)
+        if out is not None:
+            return bt.fetch(out)[0:4]
+        bt.results_dev()
+        return None
+
     barrier_sync()
     for i in range(args.warmup):
         run_step(prepared[i % n_prep])
     barrier_sync()
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # one sampler per job, not per rank
-    if sampler:
-        sampler.start()
-    # per-kind device times of the timed steps: CUDA events recorded by the library on the stream each kernel is
-    # launched on; steps are serialised (sync per step) so that the intervals do not overlap.
+    # (a) serialised steps (one batch at a time, a synchronisation per step): the per-kind device times of the kernels come from
+    # here -- CUDA events recorded by the library on the stream each kernel is launched on; the intervals of a step do not overlap
     kinds = ("score_ms", "tile_ms", "theta_ms", "phrase_ms", "term_ms", "and_ms", "or_ms", "final_ms", "kernel_ms")
     kern = {name: [] for name in kinds}
     launches = 0
@@ -347,6 +368,29 @@ def main():
             kern[key].append(stats[key])
         fallbacks += stats["tile_fallbacks"]
         launches += stats["kernel_launches"] + (7 if world > 1 else 0)  # + 3 x (key export + threshold import), cross-GPU merge
+    barrier_sync()
+    dt_value_serial = time.perf_counter() - t0
+    # (b) the timed `value` steps: the same K steps with `depth` batches in flight -- step i+1 (another prepared batch, its own stream
+    # and scratch) is queued before the host waits for step i, so the GPU fills the tails of step i's launches and the waits of
+    # its cross-rank exchanges with step i+1's first kernels.  Every step still runs every kernel; nothing is cached across steps.
+    def pipelined_steps(first, count):
+        pending = []
+        for j in range(count):
+            bt, slot = prepared[(first + j) % n_prep], j % depth
+            submit(bt, slot)
+            pending.append((bt, slot))
+            if len(pending) >= depth:
+                complete(*pending.pop(0))
+        while pending:
+            complete(*pending.pop(0))
+
+    pipelined_steps(0, args.warmup)
+    barrier_sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # one sampler per job, not per rank
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    pipelined_steps(args.warmup, args.steps)
     barrier_sync()
     dt_value = time.perf_counter() - t0
     touched_per_step = (stats["or_windows"][5] - touched0) / max(args.steps, 1) if stats else 0
@@ -363,58 +407,58 @@ def main():
         ctx.search_batch(qbs[i % len(qbs)], outs[i % 2])
     barrier_sync()
     # (a) one call per step, nothing overlapped: tq_search_batch (N=1) / prepare + phases + exchange + merge + read-back (N>1)
-    def e2e_step(i, bt, nxt_index):
-        """Runs step i on the prepared batch `bt`; prepares batch `nxt_index` (or nothing) while the GPU works. -> next batch"""
-        nonlocal h2d, d2h, parity_rows
-        nxt = None
-        if world == 1:
-            bt.run()                                   # asynchronous launches on the batch's stream
-            if nxt_index is not None:
-                nxt = ctx.prepare(qbs[nxt_index])      # host planning + H2D of the NEXT step's descriptors
-            bt.fetch(outs[i % 2])                      # D2H of the rows + wait
-            st = ctx.stats()
-            h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
-            if i == 0 and args.parity_queries:
-                parity_rows = [np.array(x[:args.parity_queries]) for x in outs[0][1:]]
+    def e2e_serial_step(bt):
+        cross_gpu_merge.run(bt)
+        cross_gpu_merge(bt)
+        if rank == 0:
+            cross_gpu_merge.fetch_host(bt)
         else:
-            cross_gpu_merge.run(bt)                    # phases + key exchanges, all enqueued on the batch's stream
-            if nxt_index is not None:
-                nxt = ctx.prepare(qbs[nxt_index])
-            o = cross_gpu_merge(bt)                    # waits for the run; packed all-gather + device merge
-            st = ctx.stats()
-            h2d, d2h = st["h2d_bytes"], 0
-            if rank == 0:
-                res = cross_gpu_merge.fetch_host(bt)  # one D2H of the merged rows on the batch's stream; waits for it
-                d2h = sum(a.nbytes for a in res)
-                if i == 0 and args.parity_queries:
-                    parity_rows = [np.array(a[:args.parity_queries]) for a in res]
-            else:
-                torch.cuda.synchronize()
+            torch.cuda.synchronize()
         bt.close()
-        return nxt
 
     t0 = time.perf_counter()
     for i in range(args.steps):
         if world == 1:
             ctx.search_batch(qbs[i % len(qbs)], outs[i % 2])
         else:
-            e2e_step(-1, ctx.prepare(qbs[i % len(qbs)]), None)
+            e2e_serial_step(ctx.prepare(qbs[i % len(qbs)]))
     barrier_sync()
     dt_e2e_serial = time.perf_counter() - t0
-    # (b) the same calls with the host side of step i+1 (tq_batch_prepare) issued while step i runs on the GPU: every step still
-    # plans, copies its descriptors up and its rows down inside the timed region
+    # (b) the same work with `depth` batches in flight: while step i runs on the GPU the host plans step i+1 (tq_batch_prepare: host
+    # planning + H2D of its descriptors) and queues it, then waits for step i and reads its rows back (D2H).  Every step still
+    # plans, copies its descriptors up and its rows down inside the timed region.
+    def e2e_pipelined(count):
+        nonlocal h2d, d2h, parity_rows
+        cur = ctx.prepare(qbs[0])
+        submit(cur, 0)
+        for i in range(count):
+            nxt = None
+            if i + 1 < count and depth > 1:
+                nxt = ctx.prepare(qbs[(i + 1) % len(qbs)])
+                submit(nxt, (i + 1) % depth)
+            res = complete(cur, i % depth, out=outs[i % 2], rows_to_host=(rank == 0))
+            st = ctx.stats()
+            h2d = st["h2d_bytes"]
+            d2h = st["d2h_bytes"] if world == 1 else (sum(a.nbytes for a in res) if res is not None else 0)
+            if i == 0 and args.parity_queries and res is not None:
+                rows = outs[0][1:] if world == 1 else res
+                parity_rows = [np.array(x[:args.parity_queries]) for x in rows]
+            cur.close()
+            if nxt is None and i + 1 < count:
+                nxt = ctx.prepare(qbs[(i + 1) % len(qbs)])
+                submit(nxt, (i + 1) % depth)
+            cur = nxt
+
     t0 = time.perf_counter()
-    bt = ctx.prepare(qbs[0])
-    for i in range(args.steps):
-        bt = e2e_step(i, bt, (i + 1) % len(qbs) if i + 1 < args.steps else None)
+    e2e_pipelined(args.steps)
     barrier_sync()
     dt_e2e = time.perf_counter() - t0
 
     # max over ranks
     if dist is not None:
-        t = torch.tensor([dt_value, dt_e2e, dt_e2e_serial], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt_value, dt_e2e, dt_e2e_serial, dt_value_serial], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_value, dt_e2e, dt_e2e_serial = float(t[0]), float(t[1]), float(t[2])
+        dt_value, dt_e2e, dt_e2e_serial, dt_value_serial = float(t[0]), float(t[1]), float(t[2]), float(t[3])
 
     if rank == 0:
         value = nq * args.steps / dt_value
@@ -480,8 +524,15 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config, "workload_stats": workload_stats, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1000.0 * dt_e2e / args.steps,
-                        "mode": "tq_batch_prepare(i+1) issued while step i runs on the GPU; tq_batch_run + tq_batch_results per step",
+                        "mode": f"{depth} batch(es) in flight: step i+1 is planned (tq_batch_prepare: host planning + H2D) and queued while step i runs; "
+                                "the host then waits for step i and reads its rows back (D2H); serial_* = one step at a time",
                         "serial_value": nq * args.steps / dt_e2e_serial, "serial_ms_per_step": 1000.0 * dt_e2e_serial / args.steps},
+                "pipeline": {"batches_in_flight": depth,
+                             "note": "value / ms_per_step: K steps with `batches_in_flight` prepared batches queued on their own streams (the host waits "
+                                     "for step i after queueing step i+1); serial_* and every per-kernel time of `roofline`: the same K steps one at a "
+                                     "time with a synchronisation per step",
+                             "serial_value": nq * args.steps / dt_value_serial, "serial_ms_per_step": 1000.0 * dt_value_serial / args.steps,
+                             "overflow_repeats": int(sum(getattr(m, "repeats", 0) for m in mergers))},
                 "gpu_launches": int(launches)}
         if args.parity_queries and parity_rows is not None:
             line["parity"] = parity_check(wl, dens, args.seed, batches[0][:args.parity_queries], parity_rows, host_threads)

@@ -270,6 +270,11 @@ int tq_merge_topk_dev(tq_ctx*, uint32_t n_lists, uint32_t nq, uint32_t stride, u
  * n_lists of them pitch_words apart -- what one all-gather of the shards' buffers produces.  The merge is enqueued on
  * cuda_stream (a cudaStream_t, e.g. tq_batch_stream's) and does not synchronise with the host. */
 int tq_batch_results_pack_dev(tq_batch*, uint32_t* packed_dev);
+/* tq_batch_results_pack_dev without the wait: the copies are enqueued behind the run on the batch's stream, so that pack, all-gather,
+ * merge and the NEXT batch's run can all be queued before the host waits for this batch (two batches in flight per GPU).
+ * packed_dev holds 3 * nq * k_max + nq + 4 words; the last four are the run's overflow flags -- non-zero on any shard: take
+ * tq_batch_results_pack_dev instead (it repeats an overflowed run on the per-query kernels). */
+int tq_batch_results_pack_dev_async(tq_batch*, uint32_t* packed_dev);
 int tq_merge_topk_packed_dev(tq_ctx*, void* cuda_stream, uint32_t n_lists, uint32_t nq, uint32_t stride, uint32_t k,
                              const uint32_t* packed_dev, size_t pitch_words, uint32_t* out_packed_dev);
 

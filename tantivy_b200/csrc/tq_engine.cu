@@ -1920,6 +1920,28 @@ int tq_batch_results_pack_dev(tq_batch* b, uint32_t* packed_dev) {
   return TQ_OK;
 }
 
+// The same rows WITHOUT waiting for the run: everything is enqueued on the batch's stream right behind the run's last kernel, so a
+// sharded caller can queue pack -> all-gather -> merge -> the next batch's run and only then wait for this one (two batches in
+// flight).  packed_dev holds 3 * nq * k_max + nq + 4 words; the last four are the run's overflow flags -- all zero: the rows are
+// final; anything else: the tile engine overflowed a buffer and the caller must take tq_batch_results_pack_dev (which repeats the
+// run on the per-query kernels) instead.  The flags travel with the rows, so every shard sees every shard's.
+int tq_batch_results_pack_dev_async(tq_batch* b, uint32_t* packed_dev) {
+  if (!b || !b->ran) return fail(TQ_ERR_INVALID_ARGUMENT, "batch has not run");
+  if (!packed_dev) return fail(TQ_ERR_INVALID_ARGUMENT, "null output");
+  TQ_CUDA(cudaSetDevice(b->ctx->device));
+  const size_t rows = (size_t)b->nq * b->kmax;
+  TQ_CUDA(cudaMemcpyAsync(packed_dev, b->params.res_scores, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + rows, b->params.res_segs, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + 2 * rows, b->params.res_docs, rows * 4, cudaMemcpyDeviceToDevice, b->stream));
+  TQ_CUDA(cudaMemcpyAsync(packed_dev + 3 * rows, b->params.res_counts, (size_t)b->nq * 4, cudaMemcpyDeviceToDevice, b->stream));
+  uint32_t* flags = packed_dev + 3 * rows + b->nq;
+  if (!b->groups.empty() && !b->is_fallback && !b->finalized)
+    TQ_CUDA(cudaMemcpyAsync(flags, b->tile_dev.p + b->tile_flags_off, 16, cudaMemcpyDeviceToDevice, b->stream));
+  else
+    TQ_CUDA(cudaMemsetAsync(flags, 0, 16, b->stream));  // (per-query kernels cannot overflow; a finalized run has been repaired already)
+  return TQ_OK;
+}
+
 // ---- Count collector -------------------------------------------------------------------------------------------
 int tq_count_batch(tq_ctx* c, const tq_query* queries, size_t nq, uint64_t* out_counts) {
   if (!c || (!queries && nq) || (!out_counts && nq)) return fail(TQ_ERR_INVALID_ARGUMENT, "null");

@@ -49,6 +49,7 @@ def _load():
     lib.tq_batch_destroy.argtypes = [vp]
     lib.tq_merge_topk_dev.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.tq_batch_results_pack_dev.argtypes = [vp, vp]
+    lib.tq_batch_results_pack_dev_async.argtypes = [vp, vp]
     lib.tq_merge_topk_packed_dev.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, vp, sz, vp]
     lib.tq_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     lib.tq_multi_destroy.argtypes = [vp]
@@ -426,6 +427,11 @@ class Batch:
     def results_pack_dev(self, packed):
         """packed: raw device address of 3 * nq * kmax + nq 32-bit words (scores | segment ords | docs | counts)."""
         _check(LIB.tq_batch_results_pack_dev(self.h, packed), self.ctx.h)
+
+    def results_pack_dev_async(self, packed):
+        """As results_pack_dev, enqueued behind the run WITHOUT waiting for it; packed holds 4 more words (the run's overflow
+        flags: non-zero on any shard = take results_pack_dev)."""
+        _check(LIB.tq_batch_results_pack_dev_async(self.h, packed), self.ctx.h)
 
     def close(self):
         if getattr(self, "h", None):

@@ -209,6 +209,7 @@ class CrossGpuMerger:
         self.torch = torch
         i32 = torch.int32
         self.words = 3 * nq * k + nq
+        self.pitch = self.words + 4  # + the run's overflow flags (tq_batch_results_pack_dev_async)
         # keys per rank and query in the threshold exchange: the k-th best of the union of every rank's top-kx is a valid lower
         # bound of the global k-th best for any kx (the keys are scores of distinct docs); it is the exact one unless a shard
         # holds more than kx of the global top-k, which 2k/world + 8 makes unlikely for evenly sharded segments
@@ -217,9 +218,9 @@ class CrossGpuMerger:
             self.kx = max(1, min(k, int(os.environ["TANTIVY_B200_EXCHANGE_KEYS"])))
         self.keys_l = torch.zeros((nq, self.kx), dtype=i32, device=device)
         self.keys_g = torch.zeros((self.world, nq, self.kx), dtype=i32, device=device)
-        self.rows_l = torch.zeros((self.words,), dtype=i32, device=device)
-        self.rows_g = torch.zeros((self.world, self.words), dtype=i32, device=device)
-        self.rows_o = torch.zeros((self.words,), dtype=i32, device=device)
+        self.rows_l = torch.zeros((self.pitch,), dtype=i32, device=device)
+        self.rows_g = torch.zeros((self.world, self.pitch), dtype=i32, device=device)
+        self.rows_o = torch.zeros((self.pitch,), dtype=i32, device=device)
         self.rows_h = None  # pinned host copy of the merged rows (fetch_host)
         self._streams = {}
 
@@ -248,10 +249,48 @@ class CrossGpuMerger:
         batch.results_pack_dev(self.rows_l.data_ptr())  # waits for the run; the copies are on the batch's stream
         with self.torch.cuda.stream(ext):
             self.dist.all_gather_into_tensor(self.rows_g, self.rows_l)
-            self.ctx.merge_topk_packed_dev(h, self.world, self.nq, self.k, self.k, self.rows_g.data_ptr(), self.words, self.rows_o.data_ptr())
+            self.ctx.merge_topk_packed_dev(h, self.world, self.nq, self.k, self.k, self.rows_g.data_ptr(), self.pitch, self.rows_o.data_ptr())
+            self.rows_o[self.words:].zero_()
+        return self._views()
+
+    def _views(self):
         r = self.nq * self.k
         o = self.rows_o
-        return (o[:r].view(self.torch.float32).view(self.nq, self.k), o[r:2 * r].view(self.nq, self.k), o[2 * r:3 * r].view(self.nq, self.k), o[3 * r:])
+        return (o[:r].view(self.torch.float32).view(self.nq, self.k), o[r:2 * r].view(self.nq, self.k), o[2 * r:3 * r].view(self.nq, self.k), o[3 * r:self.words])
+
+    def finish_async(self, batch):
+        """__call__ without the wait: pack, all-gather and merge are enqueued behind the run on the batch's stream and the host
+        returns at once -- the caller may queue the NEXT batch's run (on its own stream, with a merger of its own) before it waits
+        for this one in complete().  The run's overflow flags travel with the rows (4 words per rank; their maximum lands behind
+        the merged rows), so every rank takes the same decision in complete()."""
+        ext, h = self._stream(batch)
+        batch.results_pack_dev_async(self.rows_l.data_ptr())
+        with self.torch.cuda.stream(ext):
+            self.dist.all_gather_into_tensor(self.rows_g, self.rows_l)
+            self.ctx.merge_topk_packed_dev(h, self.world, self.nq, self.k, self.k, self.rows_g.data_ptr(), self.pitch, self.rows_o.data_ptr())
+            self.torch.amax(self.rows_g[:, self.words:], dim=0, out=self.rows_o[self.words:])
+
+    def complete(self, batch, rows_to_host=True):
+        """Waits for a batch queued with run() + finish_async().  Returns the merged rows as numpy (see fetch_host) when
+        rows_to_host, else None.  If ANY rank's tile engine overflowed a buffer, every rank repeats the hand-over on the
+        waiting path (tq_batch_results_pack_dev repeats an overflowed run on the per-query kernels): same collectives on all ranks."""
+        batch.results_dev()  # waits for the batch's stream; an overflowed run of THIS rank is repaired here
+        ext, _ = self._stream(batch)
+        with self.torch.cuda.stream(ext):
+            host = (self.rows_o if rows_to_host else self.rows_o[self.words:]).cpu()
+        flags = host[-4:]
+        self.repeats = getattr(self, "repeats", 0)
+        if int(flags.max()) != 0:
+            self.repeats += 1
+            self(batch)
+            if rows_to_host:
+                return self.fetch_host(batch)
+            ext.synchronize()
+            return None
+        if not rows_to_host:
+            return None
+        self.rows_h = host
+        return self._host_views(host.numpy())
 
     def fetch_host(self, batch):
         """After __call__(batch): ONE device-to-host copy of the merged rows, issued on the batch's stream (behind the merge kernel)
@@ -262,7 +301,10 @@ class CrossGpuMerger:
         ext, _ = self._stream(batch)
         with self.torch.cuda.stream(ext):
             self.rows_h = self.rows_o.cpu()  # cudaMemcpyAsync on `ext` + synchronisation of `ext`
-        a = self.rows_h.numpy()
+        return self._host_views(self.rows_h.numpy())
+
+    def _host_views(self, a):
+        import numpy as np
         r = self.nq * self.k
         return (a[:r].view(np.float32).reshape(self.nq, self.k), a[r:2 * r].view(np.uint32).reshape(self.nq, self.k),
-                a[2 * r:3 * r].view(np.uint32).reshape(self.nq, self.k), a[3 * r:].view(np.uint32))
+                a[2 * r:3 * r].view(np.uint32).reshape(self.nq, self.k), a[3 * r:self.words].view(np.uint32))
