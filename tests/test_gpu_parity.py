@@ -819,7 +819,7 @@ def test_doc_range_argument_checks(ctx):
     with pytest.raises(T.TqError):
         ctx.segment_set_doc_range(base, 0, 0, 4000)        # a range can only be narrowed
     ctx.segment_set_doc_range(base, 0, 1024, 3000)
-    r = ctx.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [0], 5000, segment_base=base)]))
+    r = ctx.search_batch(QueryBatch([ix.query(TQ_OP_TERM, [0], 1000, segment_base=base)]))
     docs = [d for _, _, d in hits(r, 0)]
     assert docs and min(docs) >= 1024 and max(docs) < 3000
     base2 = fresh_ord()
