@@ -242,8 +242,10 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the cpu_baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity-queries", type=int, default=32, help="queries of the first timed batch re-checked on the oracle (0 = off)")
-    ap.add_argument("--in-flight", type=int, default=2, choices=[1, 2],
-                    help="batches in flight per GPU in the timed legs (2: step i+1 is queued on its own stream before the host waits for step i)")
+    ap.add_argument("--in-flight", type=int, default=0, choices=[0, 1, 2],
+                    help="batches in flight per GPU in the timed legs (2: step i+1 is queued on its own stream before the host waits for step i; "
+                         "0 = auto: 2 on one GPU, 1 at N > 1, where queueing step i+1 early skews the ranks between the key exchanges of step i "
+                         "and measured 4 %% slower at N = 2)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -307,7 +309,7 @@ def main():
     nq = args.nq
     n_total = args.warmup + args.steps
 
-    depth = args.in_flight
+    depth = args.in_flight or (2 if world == 1 else 1)  # (both timed legs)
     mergers = []
     if world > 1:
         from tantivy_b200.sharding import CrossGpuMerger
@@ -432,21 +434,19 @@ def main():
         cur = ctx.prepare(qbs[0])
         submit(cur, 0)
         for i in range(count):
-            nxt = None
-            if i + 1 < count and depth > 1:
-                nxt = ctx.prepare(qbs[(i + 1) % len(qbs)])
+            nxt = ctx.prepare(qbs[(i + 1) % len(qbs)]) if i + 1 < count else None  # host planning + H2D while step i runs
+            if nxt is not None and depth > 1:
                 submit(nxt, (i + 1) % depth)
             res = complete(cur, i % depth, out=outs[i % 2], rows_to_host=(rank == 0))
             st = ctx.stats()
             h2d = st["h2d_bytes"]
             d2h = st["d2h_bytes"] if world == 1 else (sum(a.nbytes for a in res) if res is not None else 0)
-            if i == 0 and args.parity_queries and res is not None:
+            if i == 0 and args.parity_queries and (world == 1 or res is not None):
                 rows = outs[0][1:] if world == 1 else res
                 parity_rows = [np.array(x[:args.parity_queries]) for x in rows]
             cur.close()
-            if nxt is None and i + 1 < count:
-                nxt = ctx.prepare(qbs[(i + 1) % len(qbs)])
-                submit(nxt, (i + 1) % depth)
+            if nxt is not None and depth == 1:
+                submit(nxt, 0)
             cur = nxt
 
     t0 = time.perf_counter()
@@ -524,8 +524,9 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config, "workload_stats": workload_stats, "roofline": roofline, "clocks": clocks,
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": 1000.0 * dt_e2e / args.steps,
-                        "mode": f"{depth} batch(es) in flight: step i+1 is planned (tq_batch_prepare: host planning + H2D) and queued while step i runs; "
-                                "the host then waits for step i and reads its rows back (D2H); serial_* = one step at a time",
+                        "mode": f"{depth} batch(es) in flight: step i+1 is planned (tq_batch_prepare: host planning + H2D) while step i runs" +
+                                (" and queued behind it" if depth > 1 else "") + "; the host then waits for step i and reads its rows back (D2H); "
+                                "serial_* = one step at a time, nothing overlapped",
                         "serial_value": nq * args.steps / dt_e2e_serial, "serial_ms_per_step": 1000.0 * dt_e2e_serial / args.steps},
                 "pipeline": {"batches_in_flight": depth,
                              "note": "value / ms_per_step: K steps with `batches_in_flight` prepared batches queued on their own streams (the host waits "
