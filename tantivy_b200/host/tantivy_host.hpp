@@ -950,6 +950,165 @@ inline TermDictionaryParts open_term_dictionary(const uint8_t* sub, size_t len) 
   return parts;
 }
 
+// ---- term dictionary, SSTable kind (N2; the `quickwit` feature: src/termdict/mod.rs:20-30,62-72) -------------------------
+// Unlike the FST, this dictionary is specified entirely inside the reference tree (crate `sstable/`, format in sstable/README.md):
+//   dictionary = blocks ‖ index ‖ [u64 store_offset (v3)] ‖ u64 index_offset ‖ u64 num_terms ‖ u32 version (2 or 3)
+//                                                              (Dictionary::open, sstable/src/dictionary.rs:278-296; index/mod.rs:19-50)
+//   block      = u32 block_len (incl. the compress byte; <= 1 ends the stream) ‖ u8 compress (1 = zstd) ‖ values ‖ deltas
+//                                                              (BlockReader::read_block, sstable/src/block_reader.rs:47-106)
+//   values     = VInt n ‖ VInt postings_start ‖ VInt positions_start ‖ n x (VInt doc_freq, VInt postings_len, VInt positions_len),
+//                common::VInt (stop bit 0x80 on the last byte)          (TermInfoValueReader::load, sstable_termdict/mod.rs:56-81)
+//   delta      = keep|add byte (add << 4 | keep), or 0x01 ‖ vint keep ‖ vint add (sstable's own vint: 0x80 = continue) ‖ `add`
+//                suffix bytes                                           (DeltaReader::read_keep_add, sstable/src/delta.rs:166-196)
+// The block index (which of its two forms holds a tantivy-fst map) only accelerates point look-ups: the keys and TermInfos
+// of ALL blocks are streamed here, in order, which is what fills FieldSegmentData::term_dict.  Pinned on the byte-level golden of
+// sstable/src/lib.rs:417-448 and on sstable_termdict/mod.rs:117-150.
+inline uint64_t read_sstable_vint(const uint8_t* p, size_t len, size_t* pos) {  // sstable/src/vint.rs:25-39 (0x80 = more bytes follow)
+  uint64_t v = 0;
+  uint32_t shift = 0;
+  while (*pos < len) {
+    const uint8_t b = p[(*pos)++];
+    v |= (uint64_t)(b & 127u) << shift;
+    if (b < 128u) return v;
+    shift += 7;
+    if (shift > 63) break;
+  }
+  throw TantivyError(TantivyError::DataCorruption, "sstable: truncated vint");
+}
+
+struct SSTableEntry { std::string key; TermInfo info; };
+
+// `with_term_infos` = false reads a VoidSSTable (no values: the reference's own golden vector)
+inline std::vector<SSTableEntry> read_sstable(const uint8_t* dict, size_t len, bool with_term_infos = true) {
+  if (len < 20) throw TantivyError(TantivyError::DataCorruption, "sstable: too short for its footer");
+  uint64_t index_offset, num_terms;
+  uint32_t version;
+  std::memcpy(&index_offset, dict + len - 20, 8);
+  std::memcpy(&num_terms, dict + len - 12, 8);
+  std::memcpy(&version, dict + len - 4, 4);
+  if (version != 2u && version != 3u) throw TantivyError(TantivyError::Unsupported, "sstable: version " + std::to_string(version) + " (expected 2 or 3)");
+  if (index_offset > len - 20) throw TantivyError(TantivyError::DataCorruption, "sstable: index offset out of range");
+  std::vector<SSTableEntry> out;
+  out.reserve((size_t)std::min<uint64_t>(num_terms, 1u << 20));
+  std::string key;
+  size_t at = 0;
+  const size_t end = (size_t)index_offset;
+  for (;;) {
+    if (at == end) break;                                   // (out of data: BlockReader::read_block's `0 =>` arm)
+    if (end - at < 4) throw TantivyError(TantivyError::DataCorruption, "sstable: failed to read block_len");
+    uint32_t block_len;
+    std::memcpy(&block_len, dict + at, 4);
+    at += 4;
+    if (block_len <= 1) break;                              // the empty block that ends the stream
+    const uint8_t compress = dict[at++];
+    const size_t body = block_len - 1;
+    if (end - at < body) throw TantivyError(TantivyError::DataCorruption, "sstable: failed to read block content");
+    if (compress == 1) throw TantivyError(TantivyError::Unsupported, "sstable: zstd-compressed block");
+    const uint8_t* b = dict + at;
+    at += body;
+    size_t pos = 0;
+    std::vector<TermInfo> infos;
+    if (with_term_infos) {
+      const uint64_t n = read_vint(b, body, &pos);
+      uint64_t postings = read_vint(b, body, &pos), positions = read_vint(b, body, &pos);
+      infos.reserve((size_t)n);
+      for (uint64_t i = 0; i < n; ++i) {
+        TermInfo ti;
+        ti.doc_freq = (uint32_t)read_vint(b, body, &pos);
+        const uint64_t pl = read_vint(b, body, &pos), ql = read_vint(b, body, &pos);
+        ti.postings_start = postings; ti.postings_end = postings + pl;
+        ti.positions_start = positions; ti.positions_end = positions + ql;
+        postings += pl; positions += ql;
+        infos.push_back(ti);
+      }
+    }
+    size_t idx = 0;
+    while (pos < body) {
+      size_t keep, add;
+      const uint8_t ka = b[pos++];
+      if (ka == 1u) { keep = (size_t)read_sstable_vint(b, body, &pos); add = (size_t)read_sstable_vint(b, body, &pos); }
+      else { keep = ka & 15u; add = ka >> 4; }
+      if (keep > key.size() || add > body - pos) throw TantivyError(TantivyError::DataCorruption, "sstable: bad key delta");
+      key.resize(keep);
+      key.append(reinterpret_cast<const char*>(b + pos), add);
+      pos += add;
+      SSTableEntry e;
+      e.key = key;
+      if (with_term_infos) {
+        if (idx >= infos.size()) throw TantivyError(TantivyError::DataCorruption, "sstable: more keys than values in a block");
+        e.info = infos[idx];
+      }
+      ++idx;
+      if (!out.empty() && !(out.back().key < e.key)) throw TantivyError(TantivyError::DataCorruption, "sstable: keys are not strictly increasing");
+      out.push_back(std::move(e));
+    }
+    if (with_term_infos && idx != infos.size()) throw TantivyError(TantivyError::DataCorruption, "sstable: more values than keys in a block");
+  }
+  if (out.size() != num_terms) throw TantivyError(TantivyError::DataCorruption, "sstable: " + std::to_string(out.size()) + " keys read, footer says " + std::to_string(num_terms));
+  return out;
+}
+
+// What the reference writes for one field with the SSTable dictionary (test side and host-mirror files): sstable::Writer with
+// TermInfoValueWriter, blocks flushed when they pass `block_len` bytes (sstable/src/lib.rs Writer::insert / finish,
+// delta.rs:55-104), a single-block table keeps no index (store_offset 0: "SingleBlockSStable" in the README); tables of
+// several blocks would need the block index (an FST map, crate tantivy-fst) and are not written here.
+inline std::vector<uint8_t> write_single_block_sstable(const std::vector<SSTableEntry>& entries, bool with_term_infos = true) {
+  auto vint = [](std::vector<uint8_t>& o, uint64_t v) {  // common::VInt: stop bit on the last byte
+    for (;;) { const uint8_t b = (uint8_t)(v & 127u); v >>= 7; if (v == 0) { o.push_back(b | 128u); return; } o.push_back(b); }
+  };
+  auto svint = [](std::vector<uint8_t>& o, uint64_t v) {  // sstable vint: continue bit
+    for (;;) { const uint8_t b = (uint8_t)(v & 127u); v >>= 7; if (v == 0) { o.push_back(b); return; } o.push_back(b | 128u); }
+  };
+  std::vector<uint8_t> block;
+  if (with_term_infos) {
+    vint(block, entries.size());
+    if (!entries.empty()) {
+      vint(block, entries[0].info.postings_start);
+      vint(block, entries[0].info.positions_start);
+      for (auto& e : entries) { vint(block, e.info.doc_freq); vint(block, e.info.postings_end - e.info.postings_start); vint(block, e.info.positions_end - e.info.positions_start); }
+    }
+  }
+  std::string prev;
+  for (auto& e : entries) {
+    size_t keep = 0;
+    while (keep < prev.size() && keep < e.key.size() && prev[keep] == e.key[keep]) ++keep;
+    const size_t add = e.key.size() - keep;
+    if (keep < 16 && add < 16) block.push_back((uint8_t)((add << 4) | keep));
+    else { block.push_back(1u); svint(block, keep); svint(block, add); }
+    block.insert(block.end(), e.key.begin() + (long)keep, e.key.end());
+    prev = e.key;
+  }
+  std::vector<uint8_t> out;
+  auto u32le = [&](uint32_t v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); out.insert(out.end(), p, p + 4); };
+  auto u64le = [&](uint64_t v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); out.insert(out.end(), p, p + 8); };
+  if (!entries.empty()) {
+    u32le((uint32_t)block.size() + 1u);
+    out.push_back(0u);  // not compressed
+    out.insert(out.end(), block.begin(), block.end());
+  }
+  u32le(0u);            // no more block
+  const uint64_t index_offset = out.size();
+  u64le(0u);            // store_offset 0: single block, no index
+  u64le(index_offset);
+  u64le(entries.size());
+  u32le(3u);
+  return out;
+}
+
+// A field's `.term` sub-file, either kind: the trailing u32 says which (src/termdict/mod.rs:51-90).  SSTable dictionaries are read
+// completely (term -> TermInfo); of an FST dictionary only the TermInfoStore is (term ordinal -> TermInfo), see above.
+inline uint32_t term_dictionary_type(const uint8_t* sub, size_t len) {
+  if (len < 4) throw TantivyError(TantivyError::DataCorruption, "term dictionary too short");
+  uint32_t t;
+  std::memcpy(&t, sub + len - 4, 4);
+  if (t != 1u && t != 2u) throw TantivyError(TantivyError::DataCorruption, "invalid value for DictionaryType");
+  return t;
+}
+inline std::vector<SSTableEntry> open_sstable_term_dictionary(const uint8_t* sub, size_t len) {
+  if (term_dictionary_type(sub, len) != 2u) throw TantivyError(TantivyError::Unsupported, "term dictionary is not the SSTable kind");
+  return read_sstable(sub, len - 4, true);
+}
+
 // ---- meta.json (src/index/index_meta.rs: IndexMeta { index_settings, segments, schema, opstamp }) ---------------------
 // A small JSON reader, enough for the meta file the reference writes.
 struct Json {
@@ -1171,6 +1330,20 @@ inline Index open_index(const std::string& meta_json, const std::function<std::v
       const FieldEntry& fe = meta.schema.get_field_entry(Field{f});
       if (!fe.options.indexing) continue;
       load_field(*seg, Field{f}, fe.options.indexing->record, idx, fe.options.indexing->fieldnorms ? &fn : nullptr);
+    }
+    // `.term`: a dictionary of the SSTable kind is read completely (term -> TermInfo); of the FST kind only its TermInfoStore can be
+    // (the caller maps terms to ordinals), so term_dict stays the caller's to fill
+    std::vector<uint8_t> term_file;
+    try { term_file = read_file(sm.file_stem() + ".term"); } catch (const TantivyError&) { term_file.clear(); }
+    if (!term_file.empty()) {
+      const Footer tf = read_footer(term_file.data(), term_file.size());
+      for (auto& part : open_composite(term_file.data(), tf.body_len)) {
+        const uint32_t f = part.first.first;
+        if (f >= seg->fields.size() || !seg->fields[f].indexed || part.second.len < 4) continue;
+        const uint8_t* sub = term_file.data() + part.second.offset;
+        if (term_dictionary_type(sub, part.second.len) != 2u) continue;
+        for (auto& e : open_sstable_term_dictionary(sub, part.second.len)) seg->fields[f].term_dict[e.key] = e.info;
+      }
     }
     segments.push_back(seg);
   }

@@ -634,6 +634,108 @@ static void test_host_alive_bitset_file(const std::string& dir) {
   CHECK(mismatch);
 }
 
+// N2, SSTable kind: the term dictionary of the `quickwit` feature, specified inside the reference tree (sstable/).  Golden bytes:
+// sstable/src/lib.rs:417-448 (test_simple_sstable); value block: sstable_termdict/mod.rs:117-150 (test_block_terminfos); long keys:
+// lib.rs:394-414 (test_long_key_diff).
+static void test_host_sstable_term_dictionary(const std::string& dir) {
+  const std::vector<uint8_t> golden = {8, 0, 0, 0, 0, 16, 17, 33, 18, 19, 17, 20, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                       16, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0, 0, 0, 0, 0, 3, 0, 0, 0};
+  {
+    const auto keys = files::read_sstable(golden.data(), golden.size(), false);
+    CHECK(keys.size() == 3 && keys[0].key == std::string("\x11") && keys[1].key == std::string("\x11\x12\x13") && keys[2].key == std::string("\x11\x14"));
+    CHECK(files::write_single_block_sstable(keys, false) == golden);  // the test-side writer reproduces the reference's bytes
+    auto bad = golden;
+    bad[40] = 4;  // version
+    bool unsupported = false;
+    try { files::read_sstable(bad.data(), bad.size(), false); } catch (const TantivyError& e) { unsupported = e.kind() == TantivyError::Unsupported; }
+    CHECK(unsupported);
+    bad = golden;
+    bad[32] = 2;  // num_terms
+    bool corrupt = false;
+    try { files::read_sstable(bad.data(), bad.size(), false); } catch (const TantivyError& e) { corrupt = e.kind() == TantivyError::DataCorruption; }
+    CHECK(corrupt);
+  }
+  auto ti = [](uint32_t df, uint64_t ps, uint64_t pe, uint64_t qs, uint64_t qe) { TermInfo t; t.doc_freq = df; t.postings_start = ps; t.postings_end = pe; t.positions_start = qs; t.positions_end = qe; return t; };
+  {  // test_block_terminfos' three TermInfos under three keys
+    std::vector<files::SSTableEntry> in = {{"abba", ti(120, 17, 45, 10, 122)}, {"bjork", ti(10, 45, 450, 122, 1100)}, {"blur", ti(17, 450, 462, 1100, 1302)}};
+    const auto bytes = files::write_single_block_sstable(in);
+    // values: VInt(3) VInt(17) VInt(10) (120, 28, 112) (10, 405, 978) (17, 12, 202), common::VInt (stop bit on the last byte)
+    const std::vector<uint8_t> values = {0x83, 0x91, 0x8A, 0xF8, 0x9C, 0xF0, 0x8A, 0x15, 0x83, 0x52, 0x87, 0x91, 0x8C, 0x4A, 0x81};
+    CHECK(bytes.size() > 5 + values.size() && std::equal(values.begin(), values.end(), bytes.begin() + 5));
+    // deltas: (keep 0, add 4) "abba", (0, 5) "bjork", (1, 3) "lur"
+    const std::vector<uint8_t> deltas = {0x40, 'a', 'b', 'b', 'a', 0x50, 'b', 'j', 'o', 'r', 'k', 0x31, 'l', 'u', 'r'};
+    CHECK(std::equal(deltas.begin(), deltas.end(), bytes.begin() + 5 + (long)values.size()));
+    const auto out = files::read_sstable(bytes.data(), bytes.size());
+    CHECK(out.size() == 3);
+    for (size_t i = 0; i < out.size() && i < in.size(); ++i) CHECK(out[i].key == in[i].key && out[i].info == in[i].info);
+    // as a field's `.term` sub-file: + the dictionary type (SSTable = 2)
+    auto sub = bytes;
+    sub.insert(sub.end(), {2, 0, 0, 0});
+    CHECK(files::term_dictionary_type(sub.data(), sub.size()) == 2u);
+    CHECK(files::open_sstable_term_dictionary(sub.data(), sub.size()).size() == 3);
+    bool not_fst = false;  // ... which the FST reader refuses
+    try { files::open_term_dictionary(sub.data(), sub.size()); } catch (const TantivyError& e) { not_fst = e.kind() == TantivyError::Unsupported; }
+    CHECK(not_fst);
+  }
+  {  // test_long_key_diff: keep / add beyond 15 take the vint form
+    std::string k1, k3;
+    for (int x = 0; x < 1024; ++x) k1.push_back((char)(x % 255));
+    for (int x = 1; x < 300; ++x) k3.push_back((char)(x % 255));
+    std::vector<files::SSTableEntry> in = {{k1, ti(1, 0, 2, 0, 0)}, {std::string("\x00\x03\x04", 3), ti(2, 2, 9, 0, 0)}, {k3, ti(3, 9, 11, 0, 0)}};
+    const auto bytes = files::write_single_block_sstable(in);
+    const auto out = files::read_sstable(bytes.data(), bytes.size());
+    CHECK(out.size() == 3);
+    for (size_t i = 0; i < out.size() && i < in.size(); ++i) CHECK(out[i].key == in[i].key && out[i].info == in[i].info);
+  }
+  {  // two blocks + an index the reader does not need (v3 with a block-address store): keys restart at every block
+    std::vector<files::SSTableEntry> a = {{"aa", ti(1, 0, 2, 0, 0)}, {"ab", ti(2, 2, 4, 0, 0)}}, b = {{"ba", ti(3, 4, 9, 0, 0)}};
+    const auto ba = files::write_single_block_sstable(a), bb = files::write_single_block_sstable(b);
+    auto body_of = [](const std::vector<uint8_t>& t) { return std::vector<uint8_t>(t.begin(), t.end() - 4 - 28); };  // block without terminator + footer
+    std::vector<uint8_t> two = body_of(ba);
+    const auto second = body_of(bb);
+    two.insert(two.end(), second.begin(), second.end());
+    two.insert(two.end(), {0, 0, 0, 0});
+    const uint64_t index_offset = two.size();
+    two.insert(two.end(), {0xDE, 0xAD, 0xBE, 0xEF});                      // "index" bytes (an FST map + block addresses in a real file)
+    auto u64le = [&](uint64_t v) { const uint8_t* p = reinterpret_cast<const uint8_t*>(&v); two.insert(two.end(), p, p + 8); };
+    u64le(index_offset + 2);                                              // store_offset != 0: a real index
+    u64le(index_offset);
+    u64le(3);
+    two.insert(two.end(), {3, 0, 0, 0});
+    const auto out = files::read_sstable(two.data(), two.size());
+    CHECK(out.size() == 3 && out[0].key == "aa" && out[1].key == "ab" && out[2].key == "ba" && out[2].info == b[0].info);
+  }
+  // Index::open_in_dir over the compat segment with its `.term` swapped for an SSTable dictionary of the same term: term_dict is filled
+  // by open_index itself (the FST kind leaves it to the caller)
+  const std::string base = dir + "/index_v7/";
+  const auto meta_bytes = read_file(base + "meta.json");
+  const std::string meta_json(meta_bytes.begin(), meta_bytes.end());
+  const files::IndexMeta meta = files::read_meta(meta_json);
+  const std::string term_name = meta.segments[0].file_stem() + ".term";
+  {
+    Index plain = files::open_index(meta_json, [&](const std::string& name) { return read_file(base + name); });
+    CHECK(plain.segments()[0]->fields[0].term_dict.empty());
+  }
+  std::vector<uint8_t> sub = files::write_single_block_sstable({{"dateformat", ti(1, 0, 2, 0, 2)}});
+  sub.insert(sub.end(), {2, 0, 0, 0});
+  // composite file with one sub-file (field 0): body ‖ VInt(1) ‖ VInt(0) u32 field VInt(0) ‖ u32 footer_len, then the directory footer
+  std::vector<uint8_t> file = sub;
+  const std::vector<uint8_t> cfoot = {0x81, 0x80, 0, 0, 0, 0, 0x80};
+  file.insert(file.end(), cfoot.begin(), cfoot.end());
+  const uint32_t cfoot_len = (uint32_t)cfoot.size();
+  file.insert(file.end(), reinterpret_cast<const uint8_t*>(&cfoot_len), reinterpret_cast<const uint8_t*>(&cfoot_len) + 4);
+  const std::string json = "{\"version\":{\"major\":0,\"minor\":26,\"patch\":0,\"index_format_version\":7},\"crc\":" + std::to_string(files::crc32(file.data(), file.size())) + "}";
+  const uint32_t json_len = (uint32_t)json.size(), magic = 1337u;
+  file.insert(file.end(), json.begin(), json.end());
+  file.insert(file.end(), reinterpret_cast<const uint8_t*>(&json_len), reinterpret_cast<const uint8_t*>(&json_len) + 4);
+  file.insert(file.end(), reinterpret_cast<const uint8_t*>(&magic), reinterpret_cast<const uint8_t*>(&magic) + 4);
+  Index index = files::open_index(meta_json, [&](const std::string& name) { return name == term_name ? file : read_file(base + name); });
+  const auto& dict = index.segments()[0]->fields[0].term_dict;
+  CHECK(dict.size() == 1 && dict.count("dateformat") == 1);
+  if (dict.count("dateformat")) CHECK(dict.at("dateformat") == ti(1, 0, 2, 0, 2));
+  CHECK(index.reader().searcher().doc_freq(Term::from_field_text(*index.schema().get_field("label"), "dateformat")) == 1);
+}
+
 static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
   for (const std::string version : {"index_v6", "index_v7"}) {
     Index index = index_from_compat_files(dir, version);
@@ -721,6 +823,7 @@ int main(int argc, char** argv) {
              {"host_search_without_device_raises", test_host_search_without_device_raises}};
     if (!dir.empty()) tests.push_back({"host_compat_framing", [dir]() { test_host_compat_framing(dir); }});
     if (!dir.empty()) tests.push_back({"host_alive_bitset_file", [dir]() { test_host_alive_bitset_file(dir); }});
+    if (!dir.empty()) tests.push_back({"host_sstable_term_dictionary", [dir]() { test_host_sstable_term_dictionary(dir); }});
   } else {
     tests = {{"term_query_no_freq", test_term_query_no_freq},
              {"term_query_multiple_of_block_len", test_term_query_multiple_of_block_len},
