@@ -44,7 +44,8 @@ extern "C" {
 #define TQ_OP_TERM 0
 #define TQ_OP_AND 1
 #define TQ_OP_OR 2
-/* PhraseQuery without slop (PhraseWeight / PhraseScorer, src/query/phrase_query/phrase_scorer.rs:349-589): docs that hold
+/* PhraseQuery (PhraseWeight / PhraseScorer, src/query/phrase_query/phrase_scorer.rs:349-589; slop > 0 for two-term phrases only,
+ * intersection_count_with_slop :145-186 -- sloppy phrases of more terms return TQ_ERR_UNSUPPORTED): docs that hold
  * every term, at positions that line up with the terms' offsets in the phrase; score = bm25(fieldnorm, phrase_count)
  * under ONE Bm25Weight for the whole phrase (Bm25Weight::for_terms: the idfs add up, bm25.rs:95-129).  Needs a field
  * indexed WithFreqsAndPositions and its `.pos` bytes (tq_segment_register_positions). */
@@ -123,7 +124,8 @@ typedef struct {
   float threshold;
   /* TQ_OP_PHRASE only (NULL / 0 otherwise): term_pos[i] belongs to term_segs[i]; term_offset[t] = position of clause t
    * inside the phrase (PhraseQuery::new_with_offset, phrase_query.rs); weight[0] / avg_fieldnorm[0] (or the first
-   * tf_cache table) describe the phrase's single Bm25Weight, the other entries are ignored; slop must be 0. */
+   * tf_cache table) describe the phrase's single Bm25Weight, the other entries are ignored; slop (PhraseQuery::set_slop) may be non-zero
+   * for two-term phrases. */
   const tq_term_pos* term_pos;
   const uint32_t* term_offset;
   uint32_t slop;

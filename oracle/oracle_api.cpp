@@ -179,7 +179,7 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
   }
   if (q.op == TQ_OP_PHRASE) {
     // PhraseWeight::scorer + the same collector (phrase_weight.rs:41-110): every term of the phrase must have postings here
-    if (!q.term_pos || !q.term_offset || q.slop != 0) throw std::runtime_error("phrase query arrays");
+    if (!q.term_pos || !q.term_offset) throw std::runtime_error("phrase query arrays");
     std::vector<std::pair<uint32_t, PhraseTerm>> tp;
     for (uint32_t t = 0; t < q.n_terms; ++t) {
       if (!per_term[t] || per_term[t]->doc_freq == 0) return;
@@ -197,7 +197,7 @@ static void collect_segment(const tqo_index& ix, const tq_query& q, uint32_t seg
       tp.emplace_back(q.term_offset[t], std::move(pt));
     }
     PhraseScorer sc;
-    sc.slop = 0;
+    sc.slop = q.slop;  // PhraseWeight hands the query's slop to the scorer (phrase_weight.rs:41-110)
     sc.fieldnorm_reader = seg->has_fieldnorm ? FieldNormReader::from_data(seg->fieldnorm.data(), seg->max_doc) : FieldNormReader::constant(seg->max_doc, 1);
     sc.similarity_weight = weight_for(q, 0);  // ONE Bm25Weight::for_terms weight for the whole phrase
     sc.init(std::move(tp));

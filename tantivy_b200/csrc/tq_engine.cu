@@ -977,7 +977,9 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
       const bool is_phrase = q.op == TQ_OP_PHRASE;
       if (is_phrase) {
         if (q.n_terms < 2 || q.n_terms > TQ_MAX_PHRASE_TERMS) return fail(TQ_ERR_UNSUPPORTED, "a phrase takes 2..TQ_MAX_PHRASE_TERMS terms on the device path");
-        if (q.slop != 0) return fail(TQ_ERR_UNSUPPORTED, "phrase slop stays on the reference's CPU path");
+        // slop: two terms take intersection_count_with_slop on the device; three and more carry per-position slops through
+        // growing buffers (intersection_count_with_carrying_slop, phrase_scorer.rs:236-345) and stay on the reference's CPU path
+        if (q.slop != 0 && q.n_terms != 2) return fail(TQ_ERR_UNSUPPORTED, "phrase slop with more than two terms stays on the reference's CPU path");
         if ((!q.term_pos && q.n_term_segs) || !q.term_offset) return fail(TQ_ERR_INVALID_ARGUMENT, "a phrase needs term_pos and term_offset");
       }
       kmax = std::max(kmax, q.k);
@@ -1118,8 +1120,8 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
         qs.flags = (sp.uniform_fn ? 1u : 0u) | (prunable ? 2u : 0u);
         int unit_class = op == TQ_OP_PHRASE ? 7 : op;
         if (op == TQ_OP_PHRASE) {
-          if (qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0});
-          for (auto& h : here) { qaux.push_back(PhraseAux{h.second.pad, h.range_len}); h.second.pad = 0; }
+          if (qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0, 0});
+          for (auto& h : here) { qaux.push_back(PhraseAux{h.second.pad, h.range_len, q.slop}); h.second.pad = 0; }
           phrase_ct = std::max<uint32_t>(phrase_ct, (uint32_t)here.size());
         }
         if (op == TQ_OP_OR && c->or_strip && q.k <= kStripMaxK && here.size() <= kStripMaxLists) {
@@ -1194,7 +1196,7 @@ static int batch_prepare_impl(tq_ctx* c, const tq_query* queries, size_t nq, boo
     if (rc != TQ_OK) return rc;
   }
   if (caches.empty()) caches.resize(256, 0.0f);
-  if (!qaux.empty() && qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0});
+  if (!qaux.empty() && qaux.size() < qlists.size()) qaux.resize(qlists.size(), PhraseAux{0, 0, 0});
 
   // ---- tile groups: slot order, pair bases, score chunks, tile ranges of the launches -------------------------------------------
   struct GroupStage {

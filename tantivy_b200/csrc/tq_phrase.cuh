@@ -1,4 +1,4 @@
-// Phrase queries on the device: PhraseScorer without slop.
+// Phrase queries on the device: PhraseScorer; slop for two-term phrases (intersection_count_with_slop).
 //
 //   k_build_pos_tables  PositionReader::open + advance_num_blocks as ONE exclusive scan over the term's bit-width bytes
 //                       (src/positions/reader.rs:43-80), the VInt rest decoded once (reader.rs:82-102), and the position
@@ -40,7 +40,7 @@ struct PosJob {
   unsigned long long* pool_cursor;  // ... bump-allocated on the device (the sizes are in the data)
   unsigned long long pool_cap;
 };
-struct PhraseAux { uint32_t pos_id, offset; };  // per clause of a phrase (parallel to qlists): its position table, max_offset - its offset
+struct PhraseAux { uint32_t pos_id, offset, slop = 0; };  // per clause of a phrase (parallel to qlists): its position table, max_offset - its offset, the phrase's slop
 
 __global__ void __launch_bounds__(kThreads) k_build_pos_tables(const PosJob* __restrict__ jobs, PosDesc* __restrict__ descs, uint32_t* __restrict__ status_out) {
   const PosJob J = jobs[blockIdx.x];
@@ -187,9 +187,45 @@ __device__ __forceinline__ uint32_t pos_delta(const PosDesc& D, unsigned long lo
 
 struct PhraseCand { uint32_t pos_lo, pos_hi, tf; };  // first delta of the doc in the term's stream (64-bit), its term frequency
 
+// Two terms with slop: intersection_count_with_slop (phrase_scorer.rs:145-186) over the two position streams, left = the term the
+// Intersection puts first (ascending size_hint).  A left position within `slop` of the right one matches; the left cursor first moves
+// to the LAST left position that is not beyond the right one ("there could be a better match"), then both advance.
+__device__ __noinline__ uint32_t phrase_count_slop2(const PosDesc* __restrict__ pdescs, const PhraseAux* __restrict__ aux, const PhraseCand* __restrict__ cand,
+                                                    uint32_t slop) {
+  const PosDesc& DL = pdescs[aux[0].pos_id];
+  const PosDesc& DR = pdescs[aux[1].pos_id];
+  unsigned long long gl = ((unsigned long long)cand[0].pos_hi << 32) | cand[0].pos_lo, gr = ((unsigned long long)cand[1].pos_hi << 32) | cand[1].pos_lo;
+  uint32_t ll = cand[0].tf, rl = cand[1].tf;  // positions not read yet
+  if (ll == 0u || rl == 0u) return 0u;
+  uint32_t lv = aux[0].offset + pos_delta(DL, gl), rv = aux[1].offset + pos_delta(DR, gr);
+  ++gl; --ll; ++gr; --rl;
+  uint32_t count = 0;
+  for (;;) {
+    const uint32_t distance = lv > rv ? lv - rv : rv - lv;
+    if (distance <= slop) {
+      while (ll) {  // there could be a better match
+        const uint32_t nxt = lv + pos_delta(DL, gl);
+        if (nxt > rv) break;
+        lv = nxt; ++gl; --ll;
+      }
+      ++count;
+      if (ll == 0u || rl == 0u) return count;
+      lv += pos_delta(DL, gl); ++gl; --ll;
+      rv += pos_delta(DR, gr); ++gr; --rl;
+    } else if (lv < rv) {
+      if (ll == 0u) return count;
+      lv += pos_delta(DL, gl); ++gl; --ll;
+    } else {
+      if (rl == 0u) return count;
+      rv += pos_delta(DR, gr); ++gr; --rl;
+    }
+  }
+}
+
 // |intersection of the terms' shifted position sets| for one doc (k-way leap-frog; the sets are strictly ascending).
 __device__ __noinline__ uint32_t phrase_count(const PosDesc* __restrict__ pdescs, const PhraseAux* __restrict__ aux, const PhraseCand* __restrict__ cand,
                                               uint32_t n_terms) {
+  if (aux[0].slop != 0u) return phrase_count_slop2(pdescs, aux, cand, aux[0].slop);  // (the planner admits slop for two terms only)
   unsigned long long g[kPhraseMaxTerms];
   uint32_t left[kPhraseMaxTerms], pos[kPhraseMaxTerms];
   for (uint32_t t = 0; t < n_terms; ++t) {

@@ -84,14 +84,14 @@ def phrase_query(segs, phrase, k, offsets=None):
     return q, oracle_terms, weight, avg
 
 
-def expected_rows(oi, segs, oracle_terms, n_phrase_terms, weight, avg, k):
+def expected_rows(oi, segs, oracle_terms, n_phrase_terms, weight, avg, k, slop=0):
     """PhraseScorer per segment (only segments that hold every term), then TopDocs order."""
     rows = []
     for s in segs:
         mine = [t for t in oracle_terms if t[1] == s.ord]
         if len({t[0] for t in mine}) < n_phrase_terms:
             continue
-        rows += oi.phrase_search(mine, weight, avg, cap=1 << 16)
+        rows += oi.phrase_search(mine, weight, avg, slop=slop, cap=1 << 16)
     rows = sorted(((np.float32(sc), sg, d) for sg, d, sc, _ in rows), key=lambda r: (-r[0], r[1], r[2]))
     return [(float(sc), sg, d) for sc, sg, d in rows[:k]]
 
@@ -160,6 +160,54 @@ def test_long_documents_cross_position_blocks(ctx):
     check(ctx, segs, [["x", "y"], ["y", "x", "x"], ["q", "z"], ["x", "x", "x", "x"]], ks=(5, 300))
 
 
+def check_slop(ctx, segs, phrases, slops, ks=(1, 10, 400), offsets=None):
+    oi = O.OracleIndex()
+    for s in segs:
+        s.register(oi)
+        s.register(ctx)
+    queries, want, names = [], [], []
+    for phrase in phrases:
+        for slop in slops:
+            for k in ks:
+                q, ot, w, avg = phrase_query(segs, phrase, k, offsets=offsets)
+                q["slop"] = slop
+                queries.append(q)
+                want.append(expected_rows(oi, segs, ot, len(phrase), w, avg, k, slop=slop))
+                names.append((phrase, slop, k))
+    qb = QueryBatch(queries)
+    g = ctx.search_batch(qb)
+    c = oi.search_batch(qb, mode=0)  # the oracle's batch path takes the query's slop too
+    for i, w in enumerate(want):
+        got = hits(g, i)
+        assert [(s, d) for _, s, d in got] == [(s, d) for _, s, d in w], (names[i], got[:5], w[:5])
+        assert [np.float32(x[0]) for x in got] == [np.float32(x[0]) for x in w], names[i]
+        assert hits(c, i) == got, names[i]
+    return g
+
+
+def test_two_term_phrases_with_slop(ctx):
+    """PhraseQuery::set_slop for two terms = intersection_count_with_slop (phrase_scorer.rs:145-186; the reference's cases
+    phrase_query/mod.rs:117-160,292-330 are pinned on the oracle in tests/test_phrase_goldens.py): the doc sets and phrase counts of
+    the oracle's PhraseScorer, for both term orders (which term is `left` follows the per-segment doc_freq), repeated terms,
+    long docs whose positions cross 128-delta blocks, several segments."""
+    seg = PosSegment(["a b c d", "a c b", "b a", "a x x b", "a x x x b", "b x a x b a", "a a a b b b", "c c", "b"])
+    g = check_slop(ctx, [seg], [["a", "b"], ["b", "a"], ["a", "a"], ["c", "a"]], slops=(1, 2, 3), ks=(10,))
+    by = lambda i: sorted(d for _, _, d in hits(g, i))
+    assert by(0) == [0, 1, 5, 6]           # "a b"~1: adjacent or one word in between (a swap costs 2)
+    assert by(1) == [0, 1, 2, 3, 5, 6]     # "a b"~2
+    assert 4 in by(2) and 3 in by(2)       # "a b"~3
+    rng = np.random.default_rng(77)
+    vocab = [f"w{i}" for i in range(8)]
+    p = np.array([0.35, 0.25, 0.15, 0.1, 0.07, 0.05, 0.02, 0.01])
+    segs = [PosSegment(_random_texts(rng, n, vocab, 2, 50, p)) for n in (900, 1700)]
+    check_slop(ctx, segs, [["w0", "w1"], ["w1", "w0"], ["w4", "w0"], ["w0", "w5"], ["w2", "w2"], ["w6", "w7"], ["w0", "zzz"]], slops=(1, 2, 5))
+    long_seg = PosSegment(_random_texts(rng, 250, ["x", "y", "z", "q"], 200, 700, [0.5, 0.3, 0.15, 0.05]))
+    check_slop(ctx, [long_seg], [["x", "y"], ["q", "z"], ["z", "q"], ["x", "x"]], slops=(1, 4), ks=(5, 300))
+    # offsets other than 0, 1 (PhraseQuery::new_with_offset): "w0 * w1" with slop
+    segs2 = [PosSegment(_random_texts(rng, n, vocab, 2, 50, p)) for n in (600, 800)]
+    check_slop(ctx, segs2, [["w0", "w1"], ["w3", "w0"]], slops=(1, 3), offsets=[0, 2], ks=(10,))
+
+
 def test_phrase_needs_positions_and_rejects_slop(ctx):
     seg = PosSegment(["a b c", "a b"])
     seg.seg.register(ctx)  # postings only, no positions yet
@@ -170,8 +218,11 @@ def test_phrase_needs_positions_and_rejects_slop(ctx):
     assert len(hits(ctx.search_batch(QueryBatch([q])), 0)) == 2
     q2 = dict(q)
     q2["slop"] = 1
-    with pytest.raises(T.TqError):
-        ctx.search_batch(QueryBatch([q2]))
+    assert len(hits(ctx.search_batch(QueryBatch([q2])), 0)) == 2  # two terms: slop runs on the device
+    q3, _, _, _ = phrase_query([seg], ["a", "b", "c"], 10)
+    q3["slop"] = 1
+    with pytest.raises(T.TqError):  # three and more terms with slop (carrying slops) stay on the reference's CPU path
+        ctx.search_batch(QueryBatch([q3]))
 
 
 def test_synthetic_index_with_positions_mixed_batch(ctx):
