@@ -191,7 +191,7 @@ struct FieldSegmentData {
   std::vector<uint8_t> idx_body;   // the field's `.idx` sub-file: u64 total_num_tokens + posting lists (serializer.rs:128)
   std::vector<uint8_t> fieldnorms; // the field's `.fieldnorm` sub-file: one fieldnorm id per doc
   std::vector<uint8_t> positions;  // the field's `.pos` sub-file (WithFreqsAndPositions fields written by the in-RAM writer)
-  std::map<std::string, TermInfo> term_dict;          // term bytes -> TermInfo (the `.term` file, N2, is not read yet)
+  std::map<std::string, TermInfo> term_dict;          // term bytes -> TermInfo (filled from the `.term` file by files::open_index, or by the caller)
   std::map<std::string, std::vector<DocId>> term_docs; // kept by the in-RAM writer only, for delete_term
   uint64_t total_num_tokens() const {
     uint64_t v = 0;
@@ -950,6 +950,153 @@ inline TermDictionaryParts open_term_dictionary(const uint8_t* sub, size_t len) 
   return parts;
 }
 
+// ---- term dictionary, FST kind: the term -> ordinal map (N2) --------------------------------------------------------------------
+// Third-party format: crate `tantivy-fst` 0.5 (Cargo.toml:28; a fork of BurntSushi's `fst`, same file format), NOT in the reference
+// tree.  Its published layout (fst `raw/node.rs`, `raw/mod.rs`, `raw/common_inputs.rs`) is restated here:
+//   file   = u64 version (1 or 2) ‖ u64 type ‖ nodes ‖ u64 number of keys ‖ u64 root address; address 0 is the empty final state
+//   node   = addressed by its LAST byte (the state byte), fields laid out towards lower addresses:
+//     11cccccc  one transition to the node compiled just before (address = end of this node - 1); c = input code (0: the input byte
+//               precedes the state byte), output 0
+//     10cccccc  one transition: [output (osize)] [address delta (tsize)] [sizes = tsize << 4 | osize] [input] state
+//     0Fnnnnnn  any number: F = final; n = transitions (0: the count precedes the state byte, a stored 1 means 256);
+//               [final output] [outputs] [address deltas] [inputs] [256-byte index if version >= 2 and more than 32 transitions]
+//               [sizes] [count] state; transition i has its input at distance i + 1 below the index, its delta and output i slots below
+//               theirs; address = end of the node - delta (delta 0: the empty final state)
+//   value of a key = sum of the outputs on its path + the final output of its last node (here: the term ordinal,
+//   fst_termdict/termdict.rs:60-66)
+//   input codes 1..63 = the 63 most common bytes of the crate's reference corpus (table below).
+// PARITY UNPINNED beyond what the reference tree holds: the compat fixtures' one-term FST ("dateformat": nine 11cccccc nodes, one
+// 10cccccc node, codes of t e o a r m d f) decodes as restated; multi-transition nodes, outputs and the other 55 table entries are
+// pinned by nothing in the tree.  Every dictionary is therefore checked when it is opened (for_each below): the keys must come
+// out strictly ascending, as many as the footer says, with the ordinals 0, 1, 2, ... -- a structural misreading throws
+// DataCorruption instead of answering wrongly (a wrong table entry that keeps the order would not be caught).
+class Fst {
+ public:
+  Fst() = default;
+  Fst(const uint8_t* data, size_t len) : d_(data, data + len) {
+    if (len < 32) throw TantivyError(TantivyError::DataCorruption, "fst: too short");
+    std::memcpy(&version_, d_.data(), 8);
+    if (version_ != 1 && version_ != 2) throw TantivyError(TantivyError::Unsupported, "fst: version " + std::to_string(version_));
+    std::memcpy(&len_, d_.data() + len - 16, 8);
+    std::memcpy(&root_, d_.data() + len - 8, 8);
+    if (root_ >= len - 16) throw TantivyError(TantivyError::DataCorruption, "fst: root address out of range");
+  }
+  uint64_t len() const { return len_; }
+  // Fst::get: the value of `key`, if it is in the set
+  std::optional<uint64_t> get(const std::string& key) const {
+    Node n = node(root_);
+    uint64_t out = 0;
+    for (unsigned char b : key) {
+      bool found = false;
+      for (size_t i = 0; i < n.ntrans && !found; ++i) {
+        const Trans t = transition(n, i);
+        if (t.input == b) { out += t.output; n = node(t.addr); found = true; }
+      }
+      if (!found) return std::nullopt;
+    }
+    if (!n.is_final) return std::nullopt;
+    return out + n.final_output;
+  }
+  // every (key, value) in key order
+  void for_each(const std::function<void(const std::string&, uint64_t)>& f) const {
+    std::string key;
+    walk(node(root_), 0, key, f, 0);
+  }
+
+ private:
+  struct Node { int kind = 0; size_t start = 0, end = 0, ntrans = 0; bool is_final = false; uint64_t final_output = 0; uint8_t state = 0, tsize = 0, osize = 0; };
+  struct Trans { uint8_t input; uint64_t output; size_t addr; };
+  static uint8_t common_input(uint8_t code) {  // COMMON_INPUTS_INV[code - 1] (fst raw/common_inputs.rs): the first 63 entries
+    static const char kInv[] = "te/oasripcnw.hlm-du012g=:bf3y5&_4v9678k%?xCDASFIBEjPTzRNM+LOqHG";
+    return (uint8_t)kInv[code - 1];
+  }
+  uint8_t at(size_t i) const {
+    if (i >= d_.size()) throw TantivyError(TantivyError::DataCorruption, "fst: address out of range");
+    return d_[i];
+  }
+  uint64_t unpack(size_t i, uint8_t n) const {  // little-endian, n bytes
+    uint64_t v = 0;
+    for (uint8_t k = 0; k < n; ++k) v |= (uint64_t)at(i + k) << (8 * k);
+    return v;
+  }
+  size_t delta_addr(size_t i, uint8_t tsize, size_t node_end) const {
+    const uint64_t delta = unpack(i, tsize);
+    if (delta == 0) return 0;
+    if (delta > node_end) throw TantivyError(TantivyError::DataCorruption, "fst: transition address out of range");
+    return node_end - (size_t)delta;
+  }
+  size_t index_size(const Node& n) const { return version_ >= 2 && n.ntrans > 32 ? 256 : 0; }
+  Node node(size_t addr) const {
+    Node n;
+    if (addr == 0) { n.kind = 0; n.is_final = true; return n; }  // EMPTY_ADDRESS: the final state without transitions
+    if (addr < 16) throw TantivyError(TantivyError::DataCorruption, "fst: node address inside the header");
+    n.start = addr;
+    n.state = at(addr);
+    const uint8_t top = n.state >> 6;
+    if (top == 3) {  // OneTransNext
+      n.kind = 1; n.ntrans = 1;
+      const size_t input_len = (n.state & 63u) ? 0 : 1;
+      n.end = addr - input_len;
+    } else if (top == 2) {  // OneTrans
+      n.kind = 2; n.ntrans = 1;
+      const size_t input_len = (n.state & 63u) ? 0 : 1;
+      const uint8_t sizes = at(addr - input_len - 1);
+      n.tsize = sizes >> 4; n.osize = sizes & 15u;
+      n.end = addr - input_len - 1 - n.tsize - n.osize;
+    } else {  // AnyTrans
+      n.kind = 3;
+      n.is_final = (n.state & 64u) != 0;
+      const size_t ntrans_len = (n.state & 63u) ? 0 : 1;
+      if (ntrans_len) { n.ntrans = at(addr - 1); if (n.ntrans == 1) n.ntrans = 256; } else n.ntrans = n.state & 63u;
+      const uint8_t sizes = at(addr - ntrans_len - 1);
+      n.tsize = sizes >> 4; n.osize = sizes & 15u;
+      const size_t total_trans = n.ntrans + n.ntrans * n.tsize + index_size(n);
+      const size_t final_osize = n.is_final ? n.osize : 0;
+      const size_t body = ntrans_len + 1 + total_trans + n.ntrans * n.osize + final_osize;
+      if (body > addr) throw TantivyError(TantivyError::DataCorruption, "fst: node larger than the file");
+      n.end = addr - body;
+      if (n.is_final && n.osize) n.final_output = unpack(n.end, n.osize);
+    }
+    if (n.tsize > 8 || n.osize > 8) throw TantivyError(TantivyError::DataCorruption, "fst: pack size above 8");
+    return n;
+  }
+  Trans transition(const Node& n, size_t i) const {
+    if (n.kind == 1) {
+      const uint8_t code = n.state & 63u;
+      return Trans{code ? common_input(code) : at(n.start - 1), 0, n.end - 1};
+    }
+    if (n.kind == 2) {
+      const uint8_t code = n.state & 63u;
+      const size_t input_len = code ? 0 : 1;
+      const size_t ti = n.start - input_len - 1 - n.tsize;
+      return Trans{code ? common_input(code) : at(n.start - 1), n.osize ? unpack(ti - n.osize, n.osize) : 0, delta_addr(ti, n.tsize, n.end)};
+    }
+    const size_t ntrans_len = (n.state & 63u) ? 0 : 1;
+    const size_t below_sizes = n.start - ntrans_len - 1 - index_size(n);  // the inputs end here
+    const uint8_t input = at(below_sizes - i - 1);
+    const size_t ti = below_sizes - n.ntrans - i * n.tsize - n.tsize;
+    const size_t total_trans = n.ntrans + n.ntrans * n.tsize + index_size(n);
+    const uint64_t out = n.osize ? unpack(n.start - ntrans_len - 1 - total_trans - i * n.osize - n.osize, n.osize) : 0;
+    return Trans{input, out, delta_addr(ti, n.tsize, n.end)};
+  }
+  void walk(const Node& n, uint64_t out, std::string& key, const std::function<void(const std::string&, uint64_t)>& f, int depth) const {
+    if (depth > 70000) throw TantivyError(TantivyError::DataCorruption, "fst: cycle");
+    if (n.is_final) f(key, out + n.final_output);
+    // transitions in input order (AnyTrans keeps them sorted; walk them by ascending input whichever way they are stored)
+    std::vector<Trans> ts;
+    ts.reserve(n.ntrans);
+    for (size_t i = 0; i < n.ntrans; ++i) ts.push_back(transition(n, i));
+    std::sort(ts.begin(), ts.end(), [](const Trans& a, const Trans& b) { return a.input < b.input; });
+    for (const Trans& t : ts) {
+      key.push_back((char)t.input);
+      walk(node(t.addr), out + t.output, key, f, depth + 1);
+      key.pop_back();
+    }
+  }
+  std::vector<uint8_t> d_;
+  uint64_t version_ = 0, len_ = 0, root_ = 0;
+};
+
 // ---- term dictionary, SSTable kind (N2; the `quickwit` feature: src/termdict/mod.rs:20-30,62-72) -------------------------
 // Unlike the FST, this dictionary is specified entirely inside the reference tree (crate `sstable/`, format in sstable/README.md):
 //   dictionary = blocks ‖ index ‖ [u64 store_offset (v3)] ‖ u64 index_offset ‖ u64 num_terms ‖ u32 version (2 or 3)
@@ -1107,6 +1254,22 @@ inline uint32_t term_dictionary_type(const uint8_t* sub, size_t len) {
 inline std::vector<SSTableEntry> open_sstable_term_dictionary(const uint8_t* sub, size_t len) {
   if (term_dictionary_type(sub, len) != 2u) throw TantivyError(TantivyError::Unsupported, "term dictionary is not the SSTable kind");
   return read_sstable(sub, len - 4, true);
+}
+// An FST dictionary opened completely: every (term, TermInfo) in term order.  The consistency check of the Fst comment above runs
+// here: keys strictly ascending, ordinals 0, 1, 2, ..., as many as both the FST's footer and the TermInfoStore say.
+inline std::vector<SSTableEntry> open_fst_term_dictionary(const uint8_t* sub, size_t len) {
+  const TermDictionaryParts parts = open_term_dictionary(sub, len);
+  const Fst fst(parts.fst.data(), parts.fst.size());
+  if (fst.len() != parts.store.num_terms()) throw TantivyError(TantivyError::DataCorruption, "term dictionary: the FST and the TermInfoStore disagree on the number of terms");
+  std::vector<SSTableEntry> out;
+  out.reserve((size_t)std::min<uint64_t>(fst.len(), 1u << 20));
+  fst.for_each([&](const std::string& key, uint64_t ord) {
+    if (ord != out.size()) throw TantivyError(TantivyError::DataCorruption, "fst: term ordinals are not 0, 1, 2, ... in key order (format misread)");
+    if (!out.empty() && !(out.back().key < key)) throw TantivyError(TantivyError::DataCorruption, "fst: keys are not strictly ascending (format misread)");
+    out.push_back(SSTableEntry{key, parts.store.get(ord)});
+  });
+  if (out.size() != fst.len()) throw TantivyError(TantivyError::DataCorruption, "fst: " + std::to_string(out.size()) + " keys found, footer says " + std::to_string(fst.len()));
+  return out;
 }
 
 // ---- meta.json (src/index/index_meta.rs: IndexMeta { index_settings, segments, schema, opstamp }) ---------------------
@@ -1305,8 +1468,8 @@ inline IndexMeta read_meta(const std::string& meta_json) {
 }
 
 // Index::open_in_dir for this path: meta.json + every segment's `.idx` / `.fieldnorm` (read through `read_file(name)`),
-// one SegmentData per segment in meta order.  Term dictionaries (`.term`, N2) are not read: terms are looked up through
-// FieldSegmentData::term_dict, which the caller fills.  A segment with deletes brings its alive bitset from
+// one SegmentData per segment in meta order.  A `.term` file, when there is one, fills FieldSegmentData::term_dict (both kinds of
+// dictionary, see above); without it the caller fills it.  A segment with deletes brings its alive bitset from
 // `<uuid>.<delete opstamp>.del` (SegmentReader::open, src/index/segment_reader.rs:170-181).
 inline Index open_index(const std::string& meta_json, const std::function<std::vector<uint8_t>(const std::string&)>& read_file) {
   const IndexMeta meta = read_meta(meta_json);
@@ -1331,8 +1494,7 @@ inline Index open_index(const std::string& meta_json, const std::function<std::v
       if (!fe.options.indexing) continue;
       load_field(*seg, Field{f}, fe.options.indexing->record, idx, fe.options.indexing->fieldnorms ? &fn : nullptr);
     }
-    // `.term`: a dictionary of the SSTable kind is read completely (term -> TermInfo); of the FST kind only its TermInfoStore can be
-    // (the caller maps terms to ordinals), so term_dict stays the caller's to fill
+    // `.term`: either kind of dictionary is read completely (term -> TermInfo)
     std::vector<uint8_t> term_file;
     try { term_file = read_file(sm.file_stem() + ".term"); } catch (const TantivyError&) { term_file.clear(); }
     if (!term_file.empty()) {
@@ -1341,8 +1503,9 @@ inline Index open_index(const std::string& meta_json, const std::function<std::v
         const uint32_t f = part.first.first;
         if (f >= seg->fields.size() || !seg->fields[f].indexed || part.second.len < 4) continue;
         const uint8_t* sub = term_file.data() + part.second.offset;
-        if (term_dictionary_type(sub, part.second.len) != 2u) continue;
-        for (auto& e : open_sstable_term_dictionary(sub, part.second.len)) seg->fields[f].term_dict[e.key] = e.info;
+        const bool sstable = term_dictionary_type(sub, part.second.len) == 2u;
+        for (auto& e : sstable ? open_sstable_term_dictionary(sub, part.second.len) : open_fst_term_dictionary(sub, part.second.len))
+          seg->fields[f].term_dict[e.key] = e.info;
       }
     }
     segments.push_back(seg);

@@ -712,9 +712,9 @@ static void test_host_sstable_term_dictionary(const std::string& dir) {
   const std::string meta_json(meta_bytes.begin(), meta_bytes.end());
   const files::IndexMeta meta = files::read_meta(meta_json);
   const std::string term_name = meta.segments[0].file_stem() + ".term";
-  {
+  {  // (the fixture's own `.term` is of the FST kind: read too, see test_host_fst_term_dictionary)
     Index plain = files::open_index(meta_json, [&](const std::string& name) { return read_file(base + name); });
-    CHECK(plain.segments()[0]->fields[0].term_dict.empty());
+    CHECK(plain.segments()[0]->fields[0].term_dict.size() == 1);
   }
   std::vector<uint8_t> sub = files::write_single_block_sstable({{"dateformat", ti(1, 0, 2, 0, 2)}});
   sub.insert(sub.end(), {2, 0, 0, 0});
@@ -734,6 +734,160 @@ static void test_host_sstable_term_dictionary(const std::string& dir) {
   CHECK(dict.size() == 1 && dict.count("dateformat") == 1);
   if (dict.count("dateformat")) CHECK(dict.at("dateformat") == ti(1, 0, 2, 0, 2));
   CHECK(index.reader().searcher().doc_freq(Term::from_field_text(*index.schema().get_field("label"), "dateformat")) == 1);
+}
+
+// N2, FST kind: crate tantivy-fst's map (term -> ordinal), restated from its published layout (tantivy_host.hpp, class files::Fst).
+// What the reference tree pins: the compat fixtures' one-term dictionary.  Everything else is checked for self-consistency only,
+// against a test-side compiler of the same layout (a plain trie: valid, not minimal).
+namespace {
+struct TrieNode { std::map<uint8_t, int> next; bool is_final = false; uint64_t value = 0; };
+struct FstCompiler {
+  std::vector<uint8_t> out;
+  size_t last_addr = 0;  // address (last byte) of the node compiled most recently
+  static int code_of(uint8_t b) {
+    static const char kInv[] = "te/oasripcnw.hlm-du012g=:bf3y5&_4v9678k%?xCDASFIBEjPTzRNM+LOqHG";
+    for (int i = 0; i < 63; ++i) if ((uint8_t)kInv[i] == b) return i + 1;
+    return 0;
+  }
+  static uint8_t bytes_for(uint64_t v) { uint8_t n = 0; while (v) { ++n; v >>= 8; } return n; }
+  void put(uint64_t v, uint8_t n) { for (uint8_t k = 0; k < n; ++k) out.push_back((uint8_t)(v >> (8 * k))); }
+  struct T { uint8_t input; uint64_t output; size_t addr; };
+  // compiles one state whose targets are compiled already; returns its address
+  size_t compile(const std::vector<T>& ts, bool is_final, uint64_t final_output) {
+    if (ts.empty() && is_final && final_output == 0) return 0;  // the empty final state
+    const size_t cur = out.size();
+    if (ts.size() == 1 && !is_final) {
+      const T& t = ts[0];
+      const int code = code_of(t.input);
+      if (t.addr == last_addr && t.addr != 0 && t.output == 0 && t.addr + 1 == cur) {  // 11cccccc: the target is the node just before
+        if (!code) out.push_back(t.input);
+        out.push_back((uint8_t)(0xC0 | code));
+      } else {
+        const uint64_t delta = t.addr ? cur - t.addr : 0;
+        const uint8_t tsize = std::max<uint8_t>(1, bytes_for(delta)), osize = bytes_for(t.output);
+        put(t.output, osize);
+        put(delta, tsize);
+        out.push_back((uint8_t)((tsize << 4) | osize));
+        if (!code) out.push_back(t.input);
+        out.push_back((uint8_t)(0x80 | code));
+      }
+      return last_addr = out.size() - 1;
+    }
+    uint64_t max_delta = 0, max_out = is_final ? final_output : 0;
+    for (auto& t : ts) { max_delta = std::max<uint64_t>(max_delta, t.addr ? cur - t.addr : 0); max_out = std::max(max_out, t.output); }
+    const uint8_t tsize = std::max<uint8_t>(1, bytes_for(max_delta)), osize = bytes_for(max_out);
+    const size_t n = ts.size();
+    if (is_final) put(final_output, osize);
+    for (size_t i = n; i-- > 0;) put(ts[i].output, osize);
+    for (size_t i = n; i-- > 0;) put(ts[i].addr ? cur - ts[i].addr : 0, tsize);
+    for (size_t i = n; i-- > 0;) out.push_back(ts[i].input);
+    if (n > 32) {  // the 256-byte input index of version 2
+      std::vector<uint8_t> index(256, 255);
+      for (size_t i = 0; i < n; ++i) index[ts[i].input] = (uint8_t)i;
+      out.insert(out.end(), index.begin(), index.end());
+    }
+    out.push_back((uint8_t)((tsize << 4) | osize));
+    const bool inline_count = n >= 1 && n <= 63;
+    if (!inline_count) out.push_back((uint8_t)(n == 256 ? 1 : n));
+    out.push_back((uint8_t)((is_final ? 0x40 : 0) | (inline_count ? n : 0)));
+    return last_addr = out.size() - 1;
+  }
+};
+// keys sorted ascending, value of key i = i (what TermDictionaryBuilder inserts)
+std::vector<uint8_t> compile_fst(const std::vector<std::string>& keys) {
+  std::vector<TrieNode> trie(1);
+  for (size_t k = 0; k < keys.size(); ++k) {
+    int at = 0;
+    for (unsigned char b : keys[k]) {
+      auto it = trie[at].next.find(b);
+      if (it == trie[at].next.end()) { trie.emplace_back(); it = trie[at].next.emplace(b, (int)trie.size() - 1).first; }
+      at = it->second;
+    }
+    trie[at].is_final = true;
+    trie[at].value = k;
+  }
+  FstCompiler c;
+  c.out.assign(16, 0);
+  c.out[0] = 2;  // version 2, type 0
+  // post-order; a leaf's value rides on the transition that reaches it (the leaf is the empty final state), a key that is a prefix of
+  // others keeps its value as the final output of its node
+  std::function<size_t(int)> emit = [&](int id) -> size_t {
+    std::vector<FstCompiler::T> ts;
+    for (auto& kv : trie[id].next) {
+      const TrieNode& child = trie[kv.second];
+      if (child.next.empty()) ts.push_back({kv.first, child.value, 0});
+      else ts.push_back({kv.first, 0, emit(kv.second)});
+    }
+    return c.compile(ts, trie[id].is_final, trie[id].is_final ? trie[id].value : 0);
+  };
+  const size_t root = emit(0);
+  auto u64le = [&](uint64_t v) { for (int k = 0; k < 8; ++k) c.out.push_back((uint8_t)(v >> (8 * k))); };
+  u64le(keys.size());
+  u64le(root);
+  return c.out;
+}
+}  // namespace
+
+static void test_host_fst_term_dictionary(const std::string& dir) {
+  // (1) what the reference tree pins: the compat fixtures' dictionaries (one term each), through the whole `.term` framing
+  for (const std::string version : {"index_v6", "index_v7"}) {
+    const std::string base = dir + "/" + version + "/";
+    const auto meta_bytes = read_file(base + "meta.json");
+    const files::IndexMeta meta = files::read_meta(std::string(meta_bytes.begin(), meta_bytes.end()));
+    const auto term_file = read_file(base + meta.segments[0].file_stem() + ".term");
+    const files::Footer tf = files::read_footer(term_file.data(), term_file.size());
+    auto parts = files::open_composite(term_file.data(), tf.body_len);
+    const files::FileSlice sl = parts.at({0u, 0u});
+    const auto entries = files::open_fst_term_dictionary(term_file.data() + sl.offset, sl.len);
+    CHECK(entries.size() == 1 && entries[0].key == "dateformat");
+    if (!entries.empty()) CHECK(entries[0].info.doc_freq == 1 && entries[0].info.postings_start == 0 && entries[0].info.postings_end == 2);
+    const files::TermDictionaryParts dict = files::open_term_dictionary(term_file.data() + sl.offset, sl.len);
+    const files::Fst fst(dict.fst.data(), dict.fst.size());
+    CHECK(fst.len() == 1 && fst.get("dateformat") == std::optional<uint64_t>(0));
+    CHECK(!fst.get("dateforma") && !fst.get("dateformats") && !fst.get("") && !fst.get("x"));
+    // Index::open_in_dir alone now answers a term look-up
+    Index index = files::open_index_in_dir(dir + "/" + version);
+    CHECK(index.reader().searcher().doc_freq(Term::from_field_text(*index.schema().get_field("label"), "dateformat")) == 1);
+    // the test-side compiler writes the fixture's FST byte for byte (single-transition nodes, input codes, header, footer)
+    CHECK(compile_fst({"dateformat"}) == dict.fst);
+  }
+  // (2) self-consistency beyond the fixture: prefixes that are keys, shared prefixes, explicit input bytes, outputs of several bytes
+  {
+    std::vector<std::string> keys = {"a", "ab", "abc", "abd", "b", "ba", "date", "dateformat", "dates", "zz", std::string("zz\xC3\xA9"), "zzz"};
+    std::sort(keys.begin(), keys.end());
+    const auto bytes = compile_fst(keys);
+    const files::Fst fst(bytes.data(), bytes.size());
+    CHECK(fst.len() == keys.size());
+    for (size_t i = 0; i < keys.size(); ++i) CHECK(fst.get(keys[i]) == std::optional<uint64_t>(i));
+    CHECK(!fst.get("") && !fst.get("dat") && !fst.get("abcd") && !fst.get("c") && !fst.get("zzzz"));
+    std::vector<std::string> seen;
+    fst.for_each([&](const std::string& k, uint64_t v) { CHECK(v == seen.size()); seen.push_back(k); });
+    CHECK(seen == keys);
+  }
+  {  // a root with more than 32 transitions (the 256-byte index), 3000 keys (two-byte outputs), all byte values
+    std::vector<std::string> keys;
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { x ^= x << 7; x ^= x >> 9; return x; };
+    for (int i = 0; i < 3000; ++i) {
+      std::string k;
+      const int n = 1 + (int)(rnd() % 9);
+      for (int j = 0; j < n; ++j) k.push_back((char)(j == 0 ? rnd() % 256 : "etaoinshrdlu0123456789XYZ_\xC3\xA9\x01"[rnd() % 29]));
+      keys.push_back(k);
+    }
+    std::sort(keys.begin(), keys.end());
+    keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+    const auto bytes = compile_fst(keys);
+    const files::Fst fst(bytes.data(), bytes.size());
+    size_t n = 0;
+    bool ordered = true;
+    fst.for_each([&](const std::string& k, uint64_t v) { ordered = ordered && n < keys.size() && k == keys[n] && v == n; ++n; });
+    CHECK(n == keys.size() && ordered);
+    for (size_t i = 0; i < keys.size(); i += 37) CHECK(fst.get(keys[i]) == std::optional<uint64_t>(i));
+    // a truncated / damaged file is refused, not misread
+    bool refused = false;
+    try { files::Fst bad(bytes.data(), 20); (void)bad; } catch (const TantivyError& e) { refused = e.kind() == TantivyError::DataCorruption; }
+    CHECK(refused);
+  }
 }
 
 static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
@@ -824,6 +978,7 @@ int main(int argc, char** argv) {
     if (!dir.empty()) tests.push_back({"host_compat_framing", [dir]() { test_host_compat_framing(dir); }});
     if (!dir.empty()) tests.push_back({"host_alive_bitset_file", [dir]() { test_host_alive_bitset_file(dir); }});
     if (!dir.empty()) tests.push_back({"host_sstable_term_dictionary", [dir]() { test_host_sstable_term_dictionary(dir); }});
+    if (!dir.empty()) tests.push_back({"host_fst_term_dictionary", [dir]() { test_host_fst_term_dictionary(dir); }});
   } else {
     tests = {{"term_query_no_freq", test_term_query_no_freq},
              {"term_query_multiple_of_block_len", test_term_query_multiple_of_block_len},

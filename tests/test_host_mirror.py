@@ -104,6 +104,7 @@ def test_host_side_checks(workdir):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ok   host_search_without_device_raises" in r.stdout or "ok   host_tokenizer_and_statistics" in r.stdout
     assert "ok   host_compat_framing" in r.stdout and "ok   host_term_info_store" in r.stdout
+    assert "ok   host_fst_term_dictionary" in r.stdout  # N2, FST kind: the fixtures' dictionaries + self-consistency of the restated layout
     assert "ok   host_sstable_term_dictionary" in r.stdout  # N2, SSTable kind: sstable/'s golden bytes, `.term` of that kind opened
     assert "ok   host_alive_bitset_file" in r.stdout  # `.del`: BitSet::serialize + footer, a segment opened with deletes
 
