@@ -1080,7 +1080,7 @@ class Fst {
     return Trans{input, out, delta_addr(ti, n.tsize, n.end)};
   }
   void walk(const Node& n, uint64_t out, std::string& key, const std::function<void(const std::string&, uint64_t)>& f, int depth) const {
-    if (depth > 70000) throw TantivyError(TantivyError::DataCorruption, "fst: cycle");
+    if (depth > 4096) throw TantivyError(TantivyError::Unsupported, "fst: a key of more than 4096 bytes (or a cycle)");
     if (n.is_final) f(key, out + n.final_output);
     // transitions in input order (AnyTrans keeps them sorted; walk them by ascending input whichever way they are stored)
     std::vector<Trans> ts;
