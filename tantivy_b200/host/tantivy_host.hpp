@@ -1000,7 +1000,8 @@ class Fst {
   // every (key, value) in key order
   void for_each(const std::function<void(const std::string&, uint64_t)>& f) const {
     std::string key;
-    walk(node(root_), 0, key, f, 0);
+    size_t budget = 64 * d_.size() + 1024;  // a well-formed FST is walked in far fewer steps; a damaged one must not run away
+    walk(node(root_), 0, key, f, 0, budget);
   }
 
  private:
@@ -1079,8 +1080,10 @@ class Fst {
     const uint64_t out = n.osize ? unpack(n.start - ntrans_len - 1 - total_trans - i * n.osize - n.osize, n.osize) : 0;
     return Trans{input, out, delta_addr(ti, n.tsize, n.end)};
   }
-  void walk(const Node& n, uint64_t out, std::string& key, const std::function<void(const std::string&, uint64_t)>& f, int depth) const {
+  void walk(const Node& n, uint64_t out, std::string& key, const std::function<void(const std::string&, uint64_t)>& f, int depth, size_t& budget) const {
     if (depth > 4096) throw TantivyError(TantivyError::Unsupported, "fst: a key of more than 4096 bytes (or a cycle)");
+    if (budget < n.ntrans + 1) throw TantivyError(TantivyError::DataCorruption, "fst: more states than the file can hold (damaged)");
+    budget -= n.ntrans + 1;
     if (n.is_final) f(key, out + n.final_output);
     // transitions in input order (AnyTrans keeps them sorted; walk them by ascending input whichever way they are stored)
     std::vector<Trans> ts;
@@ -1089,7 +1092,7 @@ class Fst {
     std::sort(ts.begin(), ts.end(), [](const Trans& a, const Trans& b) { return a.input < b.input; });
     for (const Trans& t : ts) {
       key.push_back((char)t.input);
-      walk(node(t.addr), out + t.output, key, f, depth + 1);
+      walk(node(t.addr), out + t.output, key, f, depth + 1, budget);
       key.pop_back();
     }
   }
@@ -1157,6 +1160,7 @@ inline std::vector<SSTableEntry> read_sstable(const uint8_t* dict, size_t len, b
     std::vector<TermInfo> infos;
     if (with_term_infos) {
       const uint64_t n = read_vint(b, body, &pos);
+      if (n > body) throw TantivyError(TantivyError::DataCorruption, "sstable: more values than the block has bytes");
       uint64_t postings = read_vint(b, body, &pos), positions = read_vint(b, body, &pos);
       infos.reserve((size_t)n);
       for (uint64_t i = 0; i < n; ++i) {

@@ -888,6 +888,24 @@ static void test_host_fst_term_dictionary(const std::string& dir) {
     try { files::Fst bad(bytes.data(), 20); (void)bad; } catch (const TantivyError& e) { refused = e.kind() == TantivyError::DataCorruption; }
     CHECK(refused);
   }
+  {  // damaged dictionaries: an error or an answer, never a crash or a runaway walk (2000 random byte flips each, FST and SSTable)
+    const auto fst_bytes = compile_fst({"a", "ab", "abc", "b", "date", "dateformat", "dates", "zz", "zzz"});
+    std::vector<files::SSTableEntry> es;
+    for (int i = 0; i < 40; ++i) { TermInfo t; t.doc_freq = (uint32_t)i + 1; t.postings_start = (uint64_t)i * 7; t.postings_end = t.postings_start + 7; es.push_back({"k" + std::to_string(100 + i), t}); }
+    const auto sst_bytes = files::write_single_block_sstable(es);
+    uint64_t x = 88172645463325252ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    size_t survived = 0;
+    for (int it = 0; it < 2000; ++it) {
+      auto f = fst_bytes;
+      for (int k = 0; k < 1 + (int)(rnd() % 3); ++k) f[rnd() % f.size()] ^= (uint8_t)(1u << (rnd() % 8));
+      try { files::Fst t(f.data(), f.size()); size_t n = 0; t.for_each([&](const std::string&, uint64_t) { ++n; }); (void)t.get("dateformat"); ++survived; } catch (const TantivyError&) {}
+      auto s2 = sst_bytes;
+      for (int k = 0; k < 1 + (int)(rnd() % 3); ++k) s2[rnd() % s2.size()] ^= (uint8_t)(1u << (rnd() % 8));
+      try { (void)files::read_sstable(s2.data(), s2.size()); ++survived; } catch (const TantivyError&) {}
+    }
+    CHECK(survived > 0);
+  }
 }
 
 static void test_compat_index_search(const std::string& dir) {  // GPU: segments the reference wrote, searched on the device
